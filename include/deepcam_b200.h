@@ -1,0 +1,178 @@
+/*
+ * deepcam_b200.h — C ABI of the B200-native DeepCAM training-step kernels.
+ *
+ * Every entry point replaces one PyTorch/ATen operator call that the reference
+ * (azrael417/mlperf-deepcam) makes on its training hot path.  The reference is
+ * pure Python; the "FFI" it would bind is therefore ctypes.
+ * Citations are file:line in the reference tree:
+ *   DX = src/deepCam/architecture/deeplab_xception.py
+ *   LS = src/deepCam/utils/losses.py
+ *   UT = src/deepCam/utils/utils.py
+ *   TR = src/deepCam/train_hdf5_ddp.py
+ *
+ * Conventions
+ *   - plain C types only; no torch types.  All pointers are DEVICE pointers unless
+ *     a parameter is documented as host.
+ *   - the library never allocates or frees device memory and keeps no pointer
+ *     after a call returns.  Workspaces are passed in by the caller.
+ *   - every launch goes to the `stream` argument (a cudaStream_t passed as void*);
+ *     the library never synchronises the device and never uses the legacy stream.
+ *   - return value: 0 = ok, <0 = invalid argument / unsupported configuration,
+ *     >0 = cudaError_t of a failed launch.  dc_last_error_string() describes the
+ *     last failure on the calling thread.  No C++ exception crosses the ABI.
+ *   - re-entrant and thread-safe (autograd calls backward from its own thread).
+ *   - activations are channels-last: logical [N,H,W,C] addressed through dc_view.
+ */
+#ifndef DEEPCAM_B200_H
+#define DEEPCAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DC_ABI_VERSION 1
+
+enum { DC_F32 = 0, DC_BF16 = 1 };
+
+/* Strided 4-D view, logical order (n, h, w, c); strides in ELEMENTS.
+ * Channel slices of a concat buffer, parity sub-grids of a transposed
+ * convolution and NCHW tensors are all expressed this way. */
+typedef struct dc_view {
+  void*   ptr;
+  int32_t n, h, w, c;
+  int64_t sn, sh, sw, sc;
+  int32_t dtype;      /* DC_F32 | DC_BF16 */
+  int32_t reserved;
+} dc_view;
+
+/* Gather-GEMM descriptor shared by every dense contraction on the path
+ * (nn.Conv2d fprop/dgrad DX:145,149,60,74,291,426,430,434,360-366 and
+ *  nn.ConvTranspose2d fprop/dgrad DX:352,356,369,374):
+ *    out[n,y,x,co] (+)= bias[co] + sum_t sum_ci in[n, y*stride_h+dh[t], x*stride_w+dw[t], ci] * W[wt[t]][ci][co]
+ * Out-of-range input coordinates contribute zero (this is the zero padding). */
+#define DC_MAX_TAPS 9
+typedef struct dc_conv_desc {
+  int32_t ntaps;
+  int32_t dh[DC_MAX_TAPS];
+  int32_t dw[DC_MAX_TAPS];
+  int32_t wt[DC_MAX_TAPS];   /* weight-slice index of tap t inside the packed weights */
+  int32_t stride_h, stride_w;
+  int32_t accumulate;        /* 1: out += result (gradient accumulation at graph forks) */
+  int32_t wtaps;             /* number of tap slices in the packed weight tensor */
+} dc_conv_desc;
+
+/* ---- library / diagnostics ------------------------------------------------ */
+int         dc_abi_version(void);
+const char* dc_last_error_string(void);
+/* returns 1 when the current device is sm_100 (tcgen05 kernels usable), 0 otherwise, <0 on error */
+int         dc_device_supports_tcgen05(void);
+
+/* ---- layout / packing ------------------------------------------------------ */
+/* Generic strided copy with dtype conversion, dst[n,h,w,c] = src[n,h,w,c] for c < src.c;
+ * channels src.c..dst.c-1 of dst are zero-filled (channel padding, e.g. 3 -> 4 logits).
+ * Replaces .to(device)/.contiguous()/permute glue around the model (TR:348, DX:441). */
+int dc_copy_view(dc_view src, dc_view dst, void* stream);
+int dc_fill_zero(void* ptr, size_t bytes, void* stream);
+/* *ptrs[i] += 1 for i < count  (BatchNorm num_batches_tracked, 77 counters, DX:70.. normalizer) */
+int dc_i64_increment_many(int64_t* const* ptrs, int count, void* stream);
+
+/* Weight packing from the fp32 master parameter (PyTorch layout [A][B][taps]) into a kernel layout.
+ *   src_k_first = 1: src is [k][n][taps]; 0: src is [n][k][taps]
+ *   layout DC_PACK_TKN: dst[tap][k][n_pad]      (SIMT gather-GEMM B operand)
+ *   layout DC_PACK_NTK: dst[n][tap][k_pad]      (tcgen05 B operand, K-major rows)
+ *   layout DC_PACK_TC : dst[tap][c]             (depthwise, k = 1, n = c)
+ * padded entries are written as zero. */
+enum { DC_PACK_TKN = 0, DC_PACK_NTK = 1 };
+int dc_pack_weight(const float* src, int K, int N, int taps, int src_k_first,
+                   void* dst, int layout, int K_pad, int N_pad, int dst_dtype, void* stream);
+/* Gradient unpack: G is [taps][n][k_stride] fp32 (k < K valid; k_stride >= K allows channel padding);
+ * dst is the parameter-layout gradient: dst_k_first=0 -> [n][k][taps], 1 -> [k][n][taps]. */
+int dc_unpack_wgrad(const float* G, int K, int N, int taps, int k_stride, int dst_k_first, float* dst, void* stream);
+
+/* ---- dense contractions ---------------------------------------------------- */
+/* SIMT fp32-accumulate gather-GEMM (fp32 parity mode, and the small/odd layers in bf16 mode).
+ * `w` is DC_PACK_TKN with k = in.c, n_pad = round_up(out.c, 4), same dtype as `in`. */
+int dc_conv_gemm_simt(const dc_conv_desc* d, dc_view in, const void* w, const float* bias,
+                      dc_view out, void* stream);
+/* SIMT weight gradient: G[wt[t]][co][ci] += sum_m in[pix(m,t), ci] * dout[m, co]; G fp32, pre-zeroed by caller. */
+int dc_conv_wgrad_simt(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, void* stream);
+
+/* tcgen05/TMEM/TMA implicit GEMM, bf16 operands, fp32 accumulation (sm_100a only).
+ * `w` is DC_PACK_NTK bf16 with k_pad = round_up(in.c, 64).  in.c % 8 == 0, strides 16-byte aligned. */
+int dc_conv_gemm_tc(const dc_conv_desc* d, dc_view in, const void* w, const float* bias,
+                    dc_view out, void* stream);
+/* tcgen05 weight gradient (both operands pixel-major): same contract as dc_conv_wgrad_simt. */
+int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, void* stream);
+
+/* ---- depthwise 3x3 (SeparableConv2d_same.conv1 + fixed_padding, DX:45-51, 58-59, 63-64) --------- */
+/* out[n,y,x,c] = sum_{kh,kw} in[n, y*stride - dil + kh*dil, x*stride - dil + kw*dil, c] * w[kh*3+kw][c] */
+int dc_dw_fwd(dc_view in, const void* w9c, int stride, int dil, dc_view out, void* stream);
+int dc_dw_bwd_data(dc_view dout, const void* w9c, int stride, int dil, dc_view din, int accumulate, void* stream);
+/* G[9][C] fp32 += ..., pre-zeroed by the caller */
+int dc_dw_bwd_weight(dc_view in, dc_view dout, int stride, int dil, float* G9c, void* stream);
+
+/* ---- BatchNorm2d (+ReLU, +residual add) (normalizer, DX:70,129,283,348,399; relu DX:79,147; add DX:120) ---- */
+/* per-channel sum / sum of squares accumulated in double (pre-zeroed), sums = [2][C] */
+int dc_bn_stats(dc_view y, double* sums, void* stream);
+enum {
+  DC_BN_RELU       = 1,   /* out = relu(...) */
+  DC_BN_TRAIN      = 2,   /* batch statistics from `sums`; update running stats (block 0) */
+  DC_BN_IDENTITY   = 4,   /* skip normalisation (pure relu / add) */
+  DC_BN_RES_WRITE  = 8    /* backward: residual gradient is written, not accumulated */
+};
+typedef struct dc_bn_params {
+  const float* gamma;  const float* beta;      /* [C] */
+  float* running_mean; float* running_var;     /* [C]; updated in train mode */
+  const double* sums;                          /* [2][C] from dc_bn_stats (train) */
+  double count;                                /* N*H*W */
+  float momentum, eps;
+  int32_t flags;
+  int32_t reserved;
+} dc_bn_params;
+/* out = [relu]( bn(y) [+ residual] ); residual.ptr may be NULL */
+int dc_bn_apply(const dc_bn_params* p, dc_view y, dc_view residual, dc_view out, void* stream);
+/* backward pass 1: g = dout * (out > 0 if RELU); rsums[0][c] += sum g, rsums[1][c] += sum g*y   (double, pre-zeroed) */
+int dc_bn_bwd_reduce(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, double* rsums, void* stream);
+/* backward pass 2: dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); optional dres (+)= g;
+ * dgamma/dbeta ([C] fp32) written by block 0 when non-NULL. */
+int dc_bn_bwd_apply(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, const double* rsums,
+                    dc_view dy, dc_view dres, float* dgamma, float* dbeta, void* stream);
+/* per-channel sum over n,h,w into fp32 [C] (bias gradient of upsample.conv1.6, DX:366); ws_c: C doubles of scratch */
+int dc_channel_sum(dc_view x, double* ws_c, float* out_c, void* stream);
+
+/* ---- image-pooling branch (AdaptiveAvgPool2d DX:425, F.interpolate 1x1 -> HxW DX:450) ---------- */
+int dc_gap_fwd(dc_view x, float* mean_nc, void* stream);                       /* [N][C] fp32 */
+int dc_broadcast_hw(const float* src_nc, dc_view dst, void* stream);           /* dst[n,h,w,c] = src[n][c] */
+int dc_reduce_hw(dc_view x, float* sum_nc, void* stream);                      /* sum over h,w -> [N][C] */
+int dc_gap_bwd(const float* dmean_nc, dc_view dx, int accumulate, void* stream); /* dx (+)= dmean/(H*W) */
+
+/* ---- weighted cross-entropy "fp_loss" (LS:28-52) ------------------------------------------------ */
+/* logits: fp32 view [N,H,W,C] (any strides, e.g. NCHW); target int64 [N*H*W] contiguous;
+ * loss_out[0] = mean over N*H*W of w[t]*(-log softmax(logit)[t])  (fp32).  acc: 1 double scratch. */
+int dc_wce_fwd(dc_view logits, const int64_t* target, const float* class_w, double* acc,
+               float* loss_out, void* stream);
+/* dlogits[n,h,w,c] = (*gscale) * w[t]*(softmax_c - [c==t]) / (N*H*W) */
+int dc_wce_bwd(dc_view logits, const int64_t* target, const float* class_w, const float* gscale,
+               dc_view dlogits, void* stream);
+
+/* ---- IoU metric (compute_score UT:32-60, argmax TR:376/406/458) --------------------------------- */
+/* counts[0..C) = tp, [C..2C) = fp, [2C..3C) = fn  (int64, pre-zeroed by the caller or accumulated) */
+int dc_iou_counts(const int64_t* pred, const int64_t* gt, int64_t numel, int num_classes,
+                  int64_t* counts, void* stream);
+/* argmax over c with first-max tie rule (torch.max) fused with the counters; pred_out may be NULL */
+int dc_argmax_iou(dc_view logits, const int64_t* gt, int num_classes, int64_t* pred_out,
+                  int64_t* counts, void* stream);
+/* score = ((iou0 + iou1) + ...)/C in fp32, iou_j = tp/(tp+fp+fn) or 1 when the union is empty */
+int dc_iou_finalize(const int64_t* counts, int num_classes, float* score_out, void* stream);
+
+/* ---- gradient buckets (DDP all-reduce payload, TR:227) ------------------------------------------ */
+/* x[i] *= s  (1/world_size after an NCCL SUM all-reduce) */
+int dc_scale_f32(float* x, size_t count, float s, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPCAM_B200_H */

@@ -1,0 +1,120 @@
+// Shared device/host helpers for the deepcam_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/deepcam_b200.h"
+
+namespace dc {
+
+// ---- error reporting ---------------------------------------------------------------------------
+char* err_buf();                       // thread-local, 512 bytes
+int fail(int code, const char* fmt, ...);
+
+#define DC_REQUIRE(cond, ...)                                   \
+  do {                                                          \
+    if (!(cond)) return ::dc::fail(-1, __VA_ARGS__);            \
+  } while (0)
+
+inline int launch_status(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+constexpr int kNumSMs = 148;
+
+// ---- element access ----------------------------------------------------------------------------
+template <typename T> struct elem;
+template <> struct elem<float> {
+  static constexpr int dtype = DC_F32;
+  __device__ static __forceinline__ float ld(const float* p) { return *p; }
+  __device__ static __forceinline__ void st(float* p, float v) { *p = v; }
+  // 4 contiguous elements, 16-byte aligned
+  __device__ static __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  __device__ static __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct elem<__nv_bfloat16> {
+  static constexpr int dtype = DC_BF16;
+  __device__ static __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  __device__ static __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+  // 4 contiguous elements, 8-byte aligned
+  __device__ static __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    float4 r;
+    r.x = __uint_as_float(u.x << 16);
+    r.y = __uint_as_float(u.x & 0xffff0000u);
+    r.z = __uint_as_float(u.y << 16);
+    r.w = __uint_as_float(u.y & 0xffff0000u);
+    return r;
+  }
+  __device__ static __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+// Round a float the way the storage type would (identity for fp32).
+template <typename T> __device__ __forceinline__ float round_to(float v);
+template <> __device__ __forceinline__ float round_to<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) {
+  return __bfloat162float(__float2bfloat16_rn(v));
+}
+
+// Device-side view with typed pointer.
+template <typename T>
+struct View {
+  T* p;
+  int n, h, w, c;
+  long long sn, sh, sw, sc;
+  __device__ __forceinline__ T* at(int in_, int ih, int iw) const {
+    return p + in_ * sn + ih * sh + iw * sw;
+  }
+};
+template <typename T>
+static inline View<T> make_view(const dc_view& v) {
+  View<T> r;
+  r.p = reinterpret_cast<T*>(v.ptr);
+  r.n = v.n; r.h = v.h; r.w = v.w; r.c = v.c;
+  r.sn = v.sn; r.sh = v.sh; r.sw = v.sw; r.sc = v.sc;
+  return r;
+}
+
+static inline size_t dtype_size(int dt) { return dt == DC_BF16 ? 2 : 4; }
+static inline bool view_ok(const dc_view& v) {
+  return v.ptr != nullptr && v.n > 0 && v.h > 0 && v.w > 0 && v.c > 0 && (v.dtype == DC_F32 || v.dtype == DC_BF16);
+}
+// channel-vectorisable: unit channel stride, C % 4 == 0, base and strides aligned to 4 elements
+static inline bool view_vec4(const dc_view& v) {
+  size_t es = dtype_size(v.dtype);
+  return v.sc == 1 && (v.c % 4 == 0) && (v.sn % 4 == 0) && (v.sh % 4 == 0) && (v.sw % 4 == 0) &&
+         ((reinterpret_cast<uintptr_t>(v.ptr) % (4 * es)) == 0);
+}
+static inline bool same_shape(const dc_view& a, const dc_view& b) {
+  return a.n == b.n && a.h == b.h && a.w == b.w && a.c == b.c;
+}
+
+// ---- warp / block reductions -------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace dc

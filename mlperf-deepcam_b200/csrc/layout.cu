@@ -1,0 +1,258 @@
+// Layout / packing kernels: strided copies with dtype conversion (NCHW fp32 <-> NHWC bf16/fp32),
+// weight packing from the fp32 master parameters, gradient unpacking, small utilities.
+// These replace the .to()/.contiguous()/permute glue around the reference model (TR:348-349, DX:441).
+#include "common.cuh"
+#include <algorithm>
+
+namespace dc {
+
+static thread_local char g_err[512] = "ok";
+char* err_buf() { return g_err; }
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// ---- generic strided copy ----------------------------------------------------------------------
+// Path A: both sides channel-contiguous -> vector of 4 channels per thread.
+template <typename TS, typename TD>
+__global__ void copy_vec4_kernel(View<const TS> s, View<TD> d, long long npix) {
+  const int cv = d.c >> 2;
+  const int scv = s.c >> 2;
+  long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = npix * cv;
+  for (; item < total; item += (long long)gridDim.x * blockDim.x) {
+    long long pix = item / cv;
+    int c4 = (int)(item - pix * cv);
+    int w = (int)(pix % d.w);
+    long long t = pix / d.w;
+    int h = (int)(t % d.h);
+    int n = (int)(t / d.h);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < scv) v = elem<TS>::ld4(s.at(n, h, w) + c4 * 4);
+    elem<TD>::st4(d.at(n, h, w) + c4 * 4, v);
+  }
+}
+
+// Path B: tiled transpose between a w-contiguous side and a c-contiguous side (NCHW <-> NHWC).
+// tile = 32 (w) x 32 (c); block = (32, 8)
+template <typename TS, typename TD, bool SRC_W_CONTIG>
+__global__ void copy_transpose_kernel(View<const TS> s, View<TD> d) {
+  __shared__ float tile[32][33];
+  const int wt = blockIdx.x * 32;
+  const int ct = blockIdx.y * 32;
+  const int nh = blockIdx.z;
+  const int n = nh / d.h, h = nh % d.h;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  if (SRC_W_CONTIG) {
+    // read: tx along w, ty along c
+    for (int j = ty; j < 32; j += 8) {
+      int c = ct + j, w = wt + tx;
+      float v = 0.f;
+      if (c < s.c && w < s.w) v = elem<TS>::ld(s.p + n * s.sn + h * s.sh + w * s.sw + c * s.sc);
+      tile[j][tx] = v;   // [c][w]
+    }
+    __syncthreads();
+    // write: tx along c, ty along w
+    for (int j = ty; j < 32; j += 8) {
+      int w = wt + j, c = ct + tx;
+      if (c < d.c && w < d.w) elem<TD>::st(d.p + n * d.sn + h * d.sh + w * d.sw + c * d.sc, tile[tx][j]);
+    }
+  } else {
+    // source is c-contiguous: read tx along c, ty along w
+    for (int j = ty; j < 32; j += 8) {
+      int w = wt + j, c = ct + tx;
+      float v = 0.f;
+      if (c < s.c && w < s.w) v = elem<TS>::ld(s.p + n * s.sn + h * s.sh + w * s.sw + c * s.sc);
+      tile[j][tx] = v;   // [w][c]
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      int c = ct + j, w = wt + tx;
+      if (c < d.c && w < d.w) elem<TD>::st(d.p + n * d.sn + h * d.sh + w * d.sw + c * d.sc, tile[tx][j]);
+    }
+  }
+}
+
+// Path C: fully generic scalar copy.
+template <typename TS, typename TD>
+__global__ void copy_scalar_kernel(View<const TS> s, View<TD> d, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % d.c);
+    long long t = i / d.c;
+    int w = (int)(t % d.w); t /= d.w;
+    int h = (int)(t % d.h);
+    int n = (int)(t / d.h);
+    float v = 0.f;
+    if (c < s.c) v = elem<TS>::ld(s.p + n * s.sn + h * s.sh + w * s.sw + c * s.sc);
+    elem<TD>::st(d.p + n * d.sn + h * d.sh + w * d.sw + c * d.sc, v);
+  }
+}
+
+template <typename TS, typename TD>
+static int copy_dispatch(const dc_view& src, const dc_view& dst, cudaStream_t st) {
+  View<const TS> s = make_view<const TS>(src);
+  View<TD> d = make_view<TD>(dst);
+  const long long npix = (long long)dst.n * dst.h * dst.w;
+  if (view_vec4(src) && view_vec4(dst)) {
+    long long total = npix * (dst.c / 4);
+    int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+    copy_vec4_kernel<TS, TD><<<blocks, 256, 0, st>>>(s, d, npix);
+  } else if (src.sw == 1 && dst.sc == 1 && src.c <= dst.c) {
+    dim3 grid(ceil_div(dst.w, 32), ceil_div(dst.c, 32), dst.n * dst.h);
+    copy_transpose_kernel<TS, TD, true><<<grid, dim3(32, 8), 0, st>>>(s, d);
+  } else if (src.sc == 1 && dst.sw == 1 && src.c >= dst.c) {
+    dim3 grid(ceil_div(dst.w, 32), ceil_div(dst.c, 32), dst.n * dst.h);
+    copy_transpose_kernel<TS, TD, false><<<grid, dim3(32, 8), 0, st>>>(s, d);
+  } else {
+    long long total = npix * dst.c;
+    int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+    copy_scalar_kernel<TS, TD><<<blocks, 256, 0, st>>>(s, d, total);
+  }
+  return launch_status("dc_copy_view");
+}
+
+// ---- small utilities ---------------------------------------------------------------------------
+__global__ void i64_increment_kernel(int64_t* const* ptrs, int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) *ptrs[i] += 1;
+}
+
+__global__ void scale_f32_kernel(float* x, size_t count, float s) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t n4 = count / 4;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  for (size_t j = i; j < n4; j += stride) {
+    float4 v = x4[j];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    x4[j] = v;
+  }
+  for (size_t j = n4 * 4 + i; j < count; j += stride) x[j] *= s;
+}
+
+// ---- weight packing ----------------------------------------------------------------------------
+// one thread per destination element; destinations are small (<= 4.7 M elements per layer).
+template <typename TD>
+__global__ void pack_weight_kernel(const float* __restrict__ src, int K, int N, int taps, int src_k_first,
+                                   TD* __restrict__ dst, int layout, int K_pad, int N_pad) {
+  long long total = (long long)taps * K_pad * N_pad;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int t, k, n;
+    if (layout == DC_PACK_TKN) {          // [tap][k][n_pad]
+      n = (int)(i % N_pad);
+      long long r = i / N_pad;
+      k = (int)(r % K_pad);
+      t = (int)(r / K_pad);
+    } else {                               // [n][tap][k_pad]
+      k = (int)(i % K_pad);
+      long long r = i / K_pad;
+      t = (int)(r % taps);
+      n = (int)(r / taps);
+    }
+    float v = 0.f;
+    if (k < K && n < N) {
+      long long si = src_k_first ? ((long long)k * N + n) * taps + t : ((long long)n * K + k) * taps + t;
+      v = src[si];
+    }
+    elem<TD>::st(dst + i, v);
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ G, int K, int N, int taps, int k_stride, int dst_k_first,
+                                    float* __restrict__ dst) {
+  long long total = (long long)taps * K * N;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // i indexes dst
+    int t = (int)(i % taps);
+    long long r = i / taps;
+    int k, n;
+    if (dst_k_first) { n = (int)(r % N); k = (int)(r / N); }
+    else             { k = (int)(r % K); n = (int)(r / K); }
+    dst[i] = G[((long long)t * N + n) * k_stride + k];
+  }
+}
+
+}  // namespace dc
+
+using namespace dc;
+
+extern "C" {
+
+int dc_abi_version(void) { return DC_ABI_VERSION; }
+const char* dc_last_error_string(void) { return dc::err_buf(); }
+
+int dc_device_supports_tcgen05(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { dc::fail(-1, "cudaGetDevice: %s", cudaGetErrorString(e)); return -1; }
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  return (major == 10 && minor == 0) ? 1 : 0;
+}
+
+int dc_copy_view(dc_view src, dc_view dst, void* stream) {
+  DC_REQUIRE(view_ok(src) && view_ok(dst), "dc_copy_view: bad view");
+  DC_REQUIRE(src.n == dst.n && src.h == dst.h && src.w == dst.w, "dc_copy_view: shape mismatch");
+  cudaStream_t st = as_stream(stream);
+  if (src.dtype == DC_F32 && dst.dtype == DC_F32) return copy_dispatch<float, float>(src, dst, st);
+  if (src.dtype == DC_F32 && dst.dtype == DC_BF16) return copy_dispatch<float, __nv_bfloat16>(src, dst, st);
+  if (src.dtype == DC_BF16 && dst.dtype == DC_F32) return copy_dispatch<__nv_bfloat16, float>(src, dst, st);
+  return copy_dispatch<__nv_bfloat16, __nv_bfloat16>(src, dst, st);
+}
+
+int dc_fill_zero(void* ptr, size_t bytes, void* stream) {
+  DC_REQUIRE(ptr != nullptr || bytes == 0, "dc_fill_zero: null pointer");
+  if (bytes == 0) return 0;
+  cudaError_t e = cudaMemsetAsync(ptr, 0, bytes, as_stream(stream));
+  if (e != cudaSuccess) return dc::fail((int)e, "dc_fill_zero: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int dc_i64_increment_many(int64_t* const* ptrs, int count, void* stream) {
+  DC_REQUIRE(ptrs != nullptr && count >= 0, "dc_i64_increment_many: bad arguments");
+  if (count == 0) return 0;
+  i64_increment_kernel<<<ceil_div(count, 128), 128, 0, as_stream(stream)>>>(ptrs, count);
+  return launch_status("dc_i64_increment_many");
+}
+
+int dc_scale_f32(float* x, size_t count, float s, void* stream) {
+  DC_REQUIRE(x != nullptr, "dc_scale_f32: null pointer");
+  DC_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16) == 0, "dc_scale_f32: pointer must be 16-byte aligned");
+  if (count == 0) return 0;
+  int blocks = (int)std::min<size_t>((count / 4 + 255) / 256 + 1, (size_t)kNumSMs * 8);
+  scale_f32_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, count, s);
+  return launch_status("dc_scale_f32");
+}
+
+int dc_pack_weight(const float* src, int K, int N, int taps, int src_k_first, void* dst, int layout,
+                   int K_pad, int N_pad, int dst_dtype, void* stream) {
+  DC_REQUIRE(src && dst && K > 0 && N > 0 && taps > 0 && K_pad >= K && N_pad >= N, "dc_pack_weight: bad arguments");
+  DC_REQUIRE(layout == DC_PACK_TKN || layout == DC_PACK_NTK, "dc_pack_weight: unknown layout %d", layout);
+  long long total = (long long)taps * K_pad * N_pad;
+  int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 8);
+  if (dst_dtype == DC_F32)
+    pack_weight_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>(src, K, N, taps, src_k_first, (float*)dst, layout, K_pad, N_pad);
+  else if (dst_dtype == DC_BF16)
+    pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, as_stream(stream)>>>(src, K, N, taps, src_k_first, (__nv_bfloat16*)dst, layout, K_pad, N_pad);
+  else
+    return dc::fail(-1, "dc_pack_weight: bad dtype %d", dst_dtype);
+  return launch_status("dc_pack_weight");
+}
+
+int dc_unpack_wgrad(const float* G, int K, int N, int taps, int k_stride, int dst_k_first, float* dst, void* stream) {
+  DC_REQUIRE(G && dst && K > 0 && N > 0 && taps > 0 && k_stride >= K, "dc_unpack_wgrad: bad arguments");
+  long long total = (long long)taps * K * N;
+  int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 8);
+  unpack_wgrad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(G, K, N, taps, k_stride, dst_k_first, dst);
+  return launch_status("dc_unpack_wgrad");
+}
+
+}  // extern "C"

@@ -1,0 +1,637 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution kernels for sm_100a (bf16 operands, fp32 accumulation).
+//
+// fprop-like kernel (Conv2d fprop + dgrad, ConvTranspose2d fprop per parity class + dgrad):
+//   D[m, co] = sum_t sum_ci A_t[m, ci] * B[co, t, ci]
+//   * M tile = 128 output pixels arranged as a TH x TW rectangle of one image; the A operand of tap t is
+//     one 4-D TMA box {64 ch, TW, TH, 1} of the NHWC activation tensor at the tap's offset.  Out-of-range
+//     coordinates are zero-filled by TMA, which implements the zero padding (no im2col, no F.pad copy).
+//   * strided gathers (1x1 stride-2 skips, ConvTranspose dgrad) use up to four "parity" tensor maps
+//     (sub-grids with doubled strides), so every box is unit-stride.
+//   * B = packed weights [Co][taps][Ci_pad64] (K-major), one 2-D TMA box {64, BN}.
+//   * both operands land in shared memory in the 128-byte-swizzled K-major UMMA canonical layout;
+//     one elected thread issues tcgen05.mma (M=128, N=BN, K=16) accumulating in TMEM.
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+//     (tcgen05.ld -> bias -> bf16 -> global, generic output strides so concat slices / parity sub-grids work).
+// wgrad kernel: D[co, ci] = sum_pixels dY[p, co] * X_t[p, ci]; both operands are pixel-major in memory,
+//   i.e. MN-major UMMA operands (a_major = b_major = 1), reduction (pixels) split across CTAs, fp32 atomics.
+#include "common.cuh"
+#include <cuda.h>
+#include <algorithm>
+#include <mutex>
+
+namespace dc {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 |
+//   [46,48) version = 1 (Blackwell) | [61,64) layout type (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10,
+// a_major @15, b_major @16 (0 = K-major, 1 = MN-major), N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------------
+struct TcMaps {
+  CUtensorMap a[4];   // activation (gathered operand) parity maps
+  CUtensorMap b;      // fprop: packed weights; wgrad: dY
+};
+
+struct TcOut {
+  void* p;
+  int n, h, w, c;
+  long long sn, sh, sw, sc;
+  int dtype;
+};
+
+struct TcFpropParams {
+  int ntaps;
+  int map_id[DC_MAX_TAPS];
+  int qh[DC_MAX_TAPS], qw[DC_MAX_TAPS];   // box offset (in the tap's parity sub-grid) relative to the output tile origin
+  int wt[DC_MAX_TAPS];
+  int kblocks;         // ceil(Ci / 64)
+  int TH, TW, tiles_x, tiles_y;
+  int accumulate;
+  int out_vec_ok;      // output rows are 16-byte aligned bf16 with unit channel stride
+  const float* bias;
+  TcOut out;
+};
+
+constexpr int kTcThreads = 192;
+constexpr int kABytes = 128 * 128;   // 128 rows x 64 bf16
+
+template <int BN> struct FpropCfg {
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kTcThreads) conv_gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcFpropParams p) {
+  using Cfg = FpropCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment required by the 128B swizzle atoms
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
+  // barriers: full[STAGES], empty[STAGES], tmem_full, then tmem base pointer slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int mt = blockIdx.x;
+  const int tile_x = mt % p.tiles_x; mt /= p.tiles_x;
+  const int tile_y = mt % p.tiles_y;
+  const int img = mt / p.tiles_y;
+  const int x0 = tile_x * p.TW, y0 = tile_y * p.TH;
+  const int n0 = blockIdx.y * BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.b);
+    tma_prefetch_desc(&maps.a[0]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int total_k = p.ntaps * p.kblocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const CUtensorMap* am = &maps.a[p.map_id[t]];
+        const int bx = x0 + p.qw[t], by = y0 + p.qh[t];
+        const int kb0 = p.wt[t] * p.kblocks;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+          tma_load_4d(am, full_bar(s), sa, kb * 64, bx, by, img);
+          tma_load_2d(&maps.b, full_bar(s), sa + kABytes, (kb0 + kb) * 64, n0);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+      int s = 0; uint32_t ph = 0;
+      for (int it = 0; it < total_k; ++it) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        const uint64_t da = make_smem_desc(sa, 16, 1024);
+        const uint64_t db = make_smem_desc(sa + kABytes, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the (>>4) address field
+          umma_bf16(tmem_base, da + 2u * k, db + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ---- epilogue: warps 2..5; warp w may only touch TMEM lanes 32*(w%4) .. +31 ----
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;             // row of the 128 x BN accumulator = pixel of the tile
+    const int ty = row / p.TW, tx = row - ty * p.TW;
+    const int oy = y0 + ty, ox = x0 + tx;
+    const bool pix_ok = (oy < p.out.h) && (ox < p.out.w);
+    const long long base = (long long)img * p.out.sn + (long long)oy * p.out.sh + (long long)ox * p.out.sw;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const bool fast = p.out_vec_ok != 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.out.c) break;            // warp-uniform
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (!pix_ok) continue;
+      const int co0 = n0 + c0;
+      if (fast && co0 + 32 <= p.out.c) {
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out.p) + base + co0;
+        uint4* op4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            f[j] = __uint_as_float(v[q * 8 + j]);
+            if (p.bias) f[j] += p.bias[co0 + q * 8 + j];
+          }
+          if (p.accumulate) {
+            uint4 o = op4[q];
+            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              f[2 * j] += __uint_as_float(ow[j] << 16);
+              f[2 * j + 1] += __uint_as_float(ow[j] & 0xffff0000u);
+            }
+          }
+          uint4 r;
+          __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]);
+          __nv_bfloat162 b1 = __floats2bfloat162_rn(f[2], f[3]);
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(f[4], f[5]);
+          __nv_bfloat162 b3 = __floats2bfloat162_rn(f[6], f[7]);
+          r.x = *reinterpret_cast<uint32_t*>(&b0); r.y = *reinterpret_cast<uint32_t*>(&b1);
+          r.z = *reinterpret_cast<uint32_t*>(&b2); r.w = *reinterpret_cast<uint32_t*>(&b3);
+          op4[q] = r;
+        }
+      } else {
+        for (int j = 0; j < 32; ++j) {
+          const int co = co0 + j;
+          if (co >= p.out.c) break;
+          float f = __uint_as_float(v[j]);
+          if (p.bias) f += p.bias[co];
+          const long long off = base + (long long)co * p.out.sc;
+          if (p.out.dtype == DC_F32) {
+            float* q = reinterpret_cast<float*>(p.out.p) + off;
+            if (p.accumulate) f += *q;
+            *q = f;
+          } else {
+            __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p.out.p) + off;
+            if (p.accumulate) f += __bfloat162float(*q);
+            *q = __float2bfloat16_rn(f);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: D[co (128)][ci (BNW)] += sum over pixel tiles of dY^T X_t ; MN-major operands.
+// ------------------------------------------------------------------------------------------------
+struct TcWgradParams {
+  int ntaps;
+  int map_id[DC_MAX_TAPS];
+  int qh[DC_MAX_TAPS], qw[DC_MAX_TAPS];
+  int wt[DC_MAX_TAPS];
+  int TH, TW, tiles_x, tiles_y, n_img;
+  int mtiles_total, mtiles_per_split;
+  int n_ci_tiles;
+  int Co, Ci;
+  float* G;
+};
+
+template <int BNW> struct WgradCfg {
+  static constexpr int kABytes = 2 * 16384;            // 128 co = 2 boxes of [128 px][64 ch]
+  static constexpr int kBBytes = (BNW / 64) * 16384;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = 3;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BNW>
+__global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const __grid_constant__ TcMaps maps, const TcWgradParams p) {
+  using Cfg = WgradCfg<BNW>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int co0 = (blockIdx.x / p.n_ci_tiles) * 128;
+  const int ci0 = (blockIdx.x % p.n_ci_tiles) * BNW;
+  const int t = blockIdx.y;
+  const int mt_begin = blockIdx.z * p.mtiles_per_split;
+  const int mt_end = min(p.mtiles_total, mt_begin + p.mtiles_per_split);
+  const int n_iter = mt_end - mt_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BNW);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.b);
+    tma_prefetch_desc(&maps.a[p.map_id[t]]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (n_iter > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const CUtensorMap* am = &maps.a[p.map_id[t]];
+        int s = 0; uint32_t ph = 0;
+        for (int mt = mt_begin; mt < mt_end; ++mt) {
+          int r = mt;
+          const int tile_x = r % p.tiles_x; r /= p.tiles_x;
+          const int tile_y = r % p.tiles_y;
+          const int img = r / p.tiles_y;
+          const int x0 = tile_x * p.TW, y0 = tile_y * p.TH;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+          // A = dY tile: two 64-channel boxes (co0, co0+64)
+          tma_load_4d(&maps.b, full_bar(s), sa, co0, x0, y0, img);
+          tma_load_4d(&maps.b, full_bar(s), sa + 16384, co0 + 64, x0, y0, img);
+          // B = gathered X tile: BNW/64 boxes
+#pragma unroll
+          for (int j = 0; j < BNW / 64; ++j)
+            tma_load_4d(am, full_bar(s), sa + Cfg::kABytes + j * 16384, ci0 + j * 64, x0 + p.qw[t], y0 + p.qh[t], img);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(128, BNW, 1, 1);
+        int s = 0; uint32_t ph = 0;
+        for (int it = 0; it < n_iter; ++it) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+          // MN-major SW128: LBO = stride between 64-element MN blocks (one box = 16 KB), SBO = 8 k-rows = 1024 B
+          const uint64_t da = make_smem_desc(sa, 16384, 1024);
+          const uint64_t db = make_smem_desc(sa + Cfg::kABytes, 16384, 1024);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            // advance 16 pixels (K) = 16 rows of 128 B = 2048 B -> +128 in the (>>4) address field
+            umma_bf16(tmem_base, da + 128u * k, db + 128u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(tmem_full_bar);
+      }
+    } else {
+      const int lg = warp & 3;
+      const int co = co0 + lg * 32 + lane;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      float* Grow = p.G + ((size_t)p.wt[t] * p.Co + (size_t)(co < p.Co ? co : 0)) * p.Ci;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BNW; c0 += 32) {
+        if (ci0 + c0 >= p.Ci) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (co < p.Co) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int ci = ci0 + c0 + j;
+            if (ci < p.Ci) atomicAdd(Grow + ci, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BNW);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  });
+  return fn;
+}
+
+// 4-D bf16 NHWC map over a (sub-)grid: dims {C, W, H, N}, box {64, TW, TH, 1}, 128B swizzle, zero OOB fill.
+static int encode_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, long long sw, long long sh, long long sn,
+                          int TW, int TH, const char* what) {
+  PFN_encodeTiled enc = get_encode();
+  DC_REQUIRE(enc != nullptr, "%s: cuTensorMapEncodeTiled unavailable", what);
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sn * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DC_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(act) failed with %d (C=%d W=%d H=%d N=%d sw=%lld sh=%lld sn=%lld)", what,
+             (int)r, C, W, H, N, sw, sh, sn);
+  return 0;
+}
+
+static int encode_weight_map(CUtensorMap* m, const void* ptr, long long Ktot, int Co, int BN, const char* what) {
+  PFN_encodeTiled enc = get_encode();
+  DC_REQUIRE(enc != nullptr, "%s: cuTensorMapEncodeTiled unavailable", what);
+  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Co};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)BN};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DC_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(weights) failed with %d (Ktot=%lld Co=%d)", what, (int)r, Ktot, Co);
+  return 0;
+}
+
+static void pick_tile(int H, int W, int& TH, int& TW) {
+  long long best = -1;
+  for (int tw = 128; tw >= 1; tw >>= 1) {
+    int th = 128 / tw;
+    long long tiles = (long long)ceil_div(W, tw) * ceil_div(H, th);
+    if (best < 0 || tiles < best) { best = tiles; TW = tw; TH = th; }
+  }
+}
+
+static inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+static bool tc_view_ok(const dc_view& v) {
+  return view_ok(v) && v.dtype == DC_BF16 && v.sc == 1 && (v.c % 8 == 0) && (v.sw % 8 == 0) && (v.sh % 8 == 0) && (v.sn % 8 == 0) &&
+         ((reinterpret_cast<uintptr_t>(v.ptr) % 16) == 0);
+}
+
+// Build the parity maps of the gathered operand and the per-tap (map, offset) table.
+template <typename P>
+static int build_gather(const char* what, const dc_conv_desc* d, const dc_view& in, int TH, int TW, TcMaps& maps, P& p) {
+  const int s_h = d->stride_h, s_w = d->stride_w;
+  DC_REQUIRE(s_h <= 2 && s_w <= 2, "%s: stride > 2 unsupported", what);
+  bool used[4] = {false, false, false, false};
+  for (int t = 0; t < d->ntaps; ++t) {
+    int qh = floor_div(d->dh[t], s_h), rh = d->dh[t] - qh * s_h;
+    int qw = floor_div(d->dw[t], s_w), rw = d->dw[t] - qw * s_w;
+    int id = rh * 2 + rw;
+    p.map_id[t] = id; p.qh[t] = qh; p.qw[t] = qw; p.wt[t] = d->wt[t];
+    used[id] = true;
+  }
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(in.ptr);
+  int first = -1;
+  for (int id = 0; id < 4; ++id) {
+    if (!used[id]) continue;
+    int rh = id >> 1, rw = id & 1;
+    int Hs = (in.h - rh + s_h - 1) / s_h, Ws = (in.w - rw + s_w - 1) / s_w;
+    DC_REQUIRE(Hs > 0 && Ws > 0, "%s: empty parity sub-grid", what);
+    if (int r = encode_act_map(&maps.a[id], base + rh * in.sh + rw * in.sw, in.c, Ws, Hs, in.n, in.sw * s_w, in.sh * s_h, in.sn, TW, TH, what))
+      return r;
+    if (first < 0) first = id;
+  }
+  for (int id = 0; id < 4; ++id)
+    if (!used[id]) maps.a[id] = maps.a[first];
+  return 0;
+}
+
+template <int BN>
+static int launch_fprop(const TcMaps& maps, const TcFpropParams& p, int mtiles, int ntiles, cudaStream_t st) {
+  using Cfg = FpropCfg<BN>;
+  cudaError_t attr_err = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+  if (attr_err != cudaSuccess) return fail((int)attr_err, "dc_conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  dim3 grid(mtiles, ntiles, 1);
+  conv_gemm_tc_kernel<BN><<<grid, kTcThreads, Cfg::kSmem, st>>>(maps, p);
+  return launch_status("dc_conv_gemm_tc");
+}
+
+template <int BNW>
+static int launch_wgrad(const TcMaps& maps, const TcWgradParams& p, dim3 grid, cudaStream_t st) {
+  using Cfg = WgradCfg<BNW>;
+  cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+  if (e != cudaSuccess) return fail((int)e, "dc_conv_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  conv_wgrad_tc_kernel<BNW><<<grid, kTcThreads, Cfg::kSmem, st>>>(maps, p);
+  return launch_status("dc_conv_wgrad_tc");
+}
+
+}  // namespace dc
+
+using namespace dc;
+
+extern "C" {
+
+int dc_conv_gemm_tc(const dc_conv_desc* d, dc_view in, const void* w, const float* bias, dc_view out, void* stream) {
+  DC_REQUIRE(d != nullptr && d->ntaps >= 1 && d->ntaps <= DC_MAX_TAPS, "dc_conv_gemm_tc: bad descriptor");
+  DC_REQUIRE(tc_view_ok(in), "dc_conv_gemm_tc: input must be bf16, channel-contiguous, C %% 8 == 0, 16-byte aligned strides");
+  DC_REQUIRE(view_ok(out) && out.n == in.n, "dc_conv_gemm_tc: bad output view");
+  DC_REQUIRE(w != nullptr && (reinterpret_cast<uintptr_t>(w) % 16) == 0, "dc_conv_gemm_tc: weights must be 16-byte aligned");
+  DC_REQUIRE(d->wtaps >= 1 && d->wtaps <= DC_MAX_TAPS, "dc_conv_gemm_tc: bad wtaps");
+  TcMaps maps;
+  TcFpropParams p;
+  p.ntaps = d->ntaps;
+  pick_tile(out.h, out.w, p.TH, p.TW);
+  p.tiles_x = ceil_div(out.w, p.TW);
+  p.tiles_y = ceil_div(out.h, p.TH);
+  p.kblocks = ceil_div(in.c, 64);
+  p.accumulate = d->accumulate;
+  p.bias = bias;
+  p.out.p = out.ptr; p.out.n = out.n; p.out.h = out.h; p.out.w = out.w; p.out.c = out.c;
+  p.out.sn = out.sn; p.out.sh = out.sh; p.out.sw = out.sw; p.out.sc = out.sc; p.out.dtype = out.dtype;
+  p.out_vec_ok = (out.dtype == DC_BF16 && out.sc == 1 && out.sw % 8 == 0 && out.sh % 8 == 0 && out.sn % 8 == 0 &&
+                  (reinterpret_cast<uintptr_t>(out.ptr) % 16) == 0) ? 1 : 0;
+  if (int r = build_gather("dc_conv_gemm_tc", d, in, p.TH, p.TW, maps, p)) return r;
+  const long long Ktot = (long long)d->wtaps * p.kblocks * 64;
+  const int mtiles = p.tiles_x * p.tiles_y * out.n;
+  // N tile: prefer the widest tile that keeps >= ~1 wave of CTAs
+  int BN = 256;
+  if (out.c <= 64) BN = 64;
+  else if (out.c <= 128) BN = 128;
+  else if ((long long)mtiles * ceil_div(out.c, 256) < kNumSMs) BN = 128;
+  if (int r = encode_weight_map(&maps.b, w, Ktot, out.c, BN, "dc_conv_gemm_tc")) return r;
+  cudaStream_t st = as_stream(stream);
+  const int ntiles = ceil_div(out.c, BN);
+  if (BN == 256) return launch_fprop<256>(maps, p, mtiles, ntiles, st);
+  if (BN == 128) return launch_fprop<128>(maps, p, mtiles, ntiles, st);
+  return launch_fprop<64>(maps, p, mtiles, ntiles, st);
+}
+
+int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, void* stream) {
+  DC_REQUIRE(d != nullptr && d->ntaps >= 1 && d->ntaps <= DC_MAX_TAPS, "dc_conv_wgrad_tc: bad descriptor");
+  DC_REQUIRE(tc_view_ok(in) && tc_view_ok(dout), "dc_conv_wgrad_tc: views must be bf16, channel-contiguous, C %% 8 == 0, aligned");
+  DC_REQUIRE(in.n == dout.n && G != nullptr, "dc_conv_wgrad_tc: bad arguments");
+  TcMaps maps;
+  TcWgradParams p;
+  p.ntaps = d->ntaps;
+  pick_tile(dout.h, dout.w, p.TH, p.TW);
+  p.tiles_x = ceil_div(dout.w, p.TW);
+  p.tiles_y = ceil_div(dout.h, p.TH);
+  p.n_img = dout.n;
+  p.mtiles_total = p.tiles_x * p.tiles_y * dout.n;
+  p.Co = dout.c; p.Ci = in.c; p.G = G;
+  if (int r = build_gather("dc_conv_wgrad_tc", d, in, p.TH, p.TW, maps, p)) return r;
+  if (int r = encode_act_map(&maps.b, dout.ptr, dout.c, dout.w, dout.h, dout.n, dout.sw, dout.sh, dout.sn, p.TW, p.TH, "dc_conv_wgrad_tc"))
+    return r;
+  const int BNW = in.c <= 64 ? 64 : 128;
+  p.n_ci_tiles = ceil_div(in.c, BNW);
+  const int n_co_tiles = ceil_div(dout.c, 128);
+  const int tiles = n_co_tiles * p.n_ci_tiles * d->ntaps;
+  int splits = std::max(1, std::min(p.mtiles_total, ceil_div(kNumSMs * 2, tiles)));
+  p.mtiles_per_split = ceil_div(p.mtiles_total, splits);
+  splits = ceil_div(p.mtiles_total, p.mtiles_per_split);
+  dim3 grid(n_co_tiles * p.n_ci_tiles, d->ntaps, splits);
+  cudaStream_t st = as_stream(stream);
+  if (BNW == 64) return launch_wgrad<64>(maps, p, grid, st);
+  return launch_wgrad<128>(maps, p, grid, st);
+}
+
+}  // extern "C"

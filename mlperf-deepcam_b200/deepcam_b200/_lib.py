@@ -1,0 +1,104 @@
+"""ctypes binding of include/deepcam_b200.h.
+
+The product path has no CPU or library fallback: if the shared library cannot be loaded (and cannot be
+built), importing the kernels raises.  ctypes releases the GIL during every call.
+"""
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p)
+
+from . import build as _build
+
+DC_F32, DC_BF16 = 0, 1
+DC_MAX_TAPS = 9
+DC_PACK_TKN, DC_PACK_NTK = 0, 1
+DC_BN_RELU, DC_BN_TRAIN, DC_BN_IDENTITY, DC_BN_RES_WRITE = 1, 2, 4, 8
+
+
+class dc_view(Structure):
+    _fields_ = [("ptr", c_void_p), ("n", c_int32), ("h", c_int32), ("w", c_int32), ("c", c_int32),
+                ("sn", c_int64), ("sh", c_int64), ("sw", c_int64), ("sc", c_int64),
+                ("dtype", c_int32), ("reserved", c_int32)]
+
+
+class dc_conv_desc(Structure):
+    _fields_ = [("ntaps", c_int32), ("dh", c_int32 * DC_MAX_TAPS), ("dw", c_int32 * DC_MAX_TAPS),
+                ("wt", c_int32 * DC_MAX_TAPS), ("stride_h", c_int32), ("stride_w", c_int32),
+                ("accumulate", c_int32), ("wtaps", c_int32)]
+
+
+class dc_bn_params(Structure):
+    _fields_ = [("gamma", c_void_p), ("beta", c_void_p), ("running_mean", c_void_p), ("running_var", c_void_p),
+                ("sums", c_void_p), ("count", c_double), ("momentum", c_float), ("eps", c_float),
+                ("flags", c_int32), ("reserved", c_int32)]
+
+
+# name -> (restype, argtypes); must list every symbol declared in include/deepcam_b200.h
+SIGNATURES = {
+    "dc_abi_version": (c_int, []),
+    "dc_last_error_string": (c_char_p, []),
+    "dc_device_supports_tcgen05": (c_int, []),
+    "dc_copy_view": (c_int, [dc_view, dc_view, c_void_p]),
+    "dc_fill_zero": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "dc_i64_increment_many": (c_int, [c_void_p, c_int, c_void_p]),
+    "dc_pack_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dc_unpack_wgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dc_conv_gemm_simt": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p]),
+    "dc_conv_wgrad_simt": (c_int, [POINTER(dc_conv_desc), dc_view, dc_view, c_void_p, c_void_p]),
+    "dc_conv_gemm_tc": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p]),
+    "dc_conv_wgrad_tc": (c_int, [POINTER(dc_conv_desc), dc_view, dc_view, c_void_p, c_void_p]),
+    "dc_dw_fwd": (c_int, [dc_view, c_void_p, c_int, c_int, dc_view, c_void_p]),
+    "dc_dw_bwd_data": (c_int, [dc_view, c_void_p, c_int, c_int, dc_view, c_int, c_void_p]),
+    "dc_dw_bwd_weight": (c_int, [dc_view, dc_view, c_int, c_int, c_void_p, c_void_p]),
+    "dc_bn_stats": (c_int, [dc_view, c_void_p, c_void_p]),
+    "dc_bn_apply": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p]),
+    "dc_bn_bwd_reduce": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, c_void_p]),
+    "dc_bn_bwd_apply": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, dc_view, dc_view,
+                                c_void_p, c_void_p, c_void_p]),
+    "dc_channel_sum": (c_int, [dc_view, c_void_p, c_void_p, c_void_p]),
+    "dc_gap_fwd": (c_int, [dc_view, c_void_p, c_void_p]),
+    "dc_broadcast_hw": (c_int, [c_void_p, dc_view, c_void_p]),
+    "dc_reduce_hw": (c_int, [dc_view, c_void_p, c_void_p]),
+    "dc_gap_bwd": (c_int, [c_void_p, dc_view, c_int, c_void_p]),
+    "dc_wce_fwd": (c_int, [dc_view, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dc_wce_bwd": (c_int, [dc_view, c_void_p, c_void_p, c_void_p, dc_view, c_void_p]),
+    "dc_iou_counts": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "dc_argmax_iou": (c_int, [dc_view, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "dc_iou_finalize": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "dc_scale_f32": (c_int, [c_void_p, c_size_t, c_float, c_void_p]),
+}
+
+_LIB = None
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if necessary) the kernel library; raises if that is impossible."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        path = _build.build()
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError here = ABI mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dc_abi_version() != 1:
+        raise RuntimeError("libdeepcam_b200.so: unexpected ABI version %d" % lib.dc_abi_version())
+    _LIB = lib
+    return lib
+
+
+class KernelError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().dc_last_error_string().decode("utf-8", "replace")
+        raise KernelError("%s failed (code %d): %s" % (what or "deepcam_b200 kernel", rc, msg))

@@ -1,0 +1,335 @@
+"""CUDA backend: maps the engine's layer-level operations onto the C-ABI kernels.
+
+There is exactly one product backend and it needs a B200: no CPU path, no cuDNN/cuBLAS path.  (tests/ holds
+a torch-CPU interpreter of the same engine operations, used only to check the graph logic without a GPU.)
+
+Layer specs (ConvSpec / DwSpec / BnSpec) reference the fp32 master parameters owned by the nn.Modules of
+architecture/deeplab_xception.py; kernel-layout copies (bf16, packed) are caches keyed on the parameter version.
+"""
+import torch
+
+from . import convdesc, ops
+from ._lib import DC_BN_IDENTITY, DC_BN_RELU, DC_BN_RES_WRITE, DC_BN_TRAIN, DC_PACK_NTK, DC_PACK_TKN
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+class ConvSpec:
+    """Dense convolution (nn.Conv2d) or transposed convolution (nn.ConvTranspose2d k3 s2 p1 op1)."""
+
+    def __init__(self, name, weight, bias=None, stride=1, pad=0, dil=1, transposed=False):
+        self.name = name
+        self.weight = weight            # nn.Parameter: Conv2d [Co,Ci,k,k]; ConvTranspose2d [Ci,Co,k,k]
+        self.bias = bias
+        self.stride, self.pad, self.dil = stride, pad, dil
+        self.transposed = transposed
+        if transposed:
+            self.ci, self.co = weight.shape[0], weight.shape[1]
+        else:
+            self.co, self.ci = weight.shape[0], weight.shape[1]
+        self.k = weight.shape[2]
+        self._cache = {}
+
+    def out_hw(self, h, w):
+        if self.transposed:   # output_padding = 1 (DX:352): (h-1)*s - 2p + k + 1
+            f = lambda v: (v - 1) * self.stride - 2 * self.pad + self.k + 1
+        else:
+            f = lambda v: convdesc.conv_out_size(v, self.k, self.stride, self.pad, self.dil)
+        return f(h), f(w)
+
+
+class DwSpec:
+    """Depthwise 3x3 of SeparableConv2d_same (DX:58-59) with fixed_padding (DX:45-51)."""
+
+    def __init__(self, name, weight, stride=1, dil=1):
+        self.name = name
+        self.weight = weight            # [C,1,3,3]
+        self.c = weight.shape[0]
+        self.stride, self.dil = stride, dil
+        self._cache = {}
+
+    def out_hw(self, h, w):
+        return (h - 1) // self.stride + 1, (w - 1) // self.stride + 1
+
+
+class BnSpec:
+    def __init__(self, name, module):
+        self.name = name
+        self.module = module            # nn.BatchNorm2d holding weight/bias/running stats
+
+    @property
+    def c(self):
+        return self.module.num_features
+
+
+def _cached(spec, key, param, make):
+    ver = (param._version, param.data_ptr())
+    ent = spec._cache.get(key)
+    if ent is None or ent[0] != ver:
+        ent = (ver, make())
+        spec._cache[key] = ent
+    return ent[1]
+
+
+class CudaBackend:
+    name = "cuda"
+
+    def __init__(self, dtype=torch.bfloat16, device=None, use_tc=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("deepcam_b200: CUDA device required (the kernels are sm_100a only; no CPU fallback)")
+        self.dtype = dtype
+        self.device = torch.device(device if device is not None else torch.cuda.current_device())
+        if use_tc is None:
+            use_tc = dtype == torch.bfloat16 and ops._lib.load().dc_device_supports_tcgen05() == 1
+        self.use_tc = bool(use_tc)
+        self.launches = 0
+
+    # ---- memory -----------------------------------------------------------------------------------
+    def empty(self, n, h, w, c, dtype=None):
+        return torch.empty((n, h, w, c), dtype=dtype or self.dtype, device=self.device)
+
+    def zeros(self, n, h, w, c, dtype=None):
+        t = self.empty(n, h, w, c, dtype)
+        ops.fill_zero(t)
+        self.launches += 1
+        return t
+
+    def scratch(self, numel, dtype, zero=False):
+        t = torch.empty(numel, dtype=dtype, device=self.device)
+        if zero:
+            ops.fill_zero(t)
+            self.launches += 1
+        return t
+
+    # ---- layout -------------------------------------------------------------------------------------
+    def from_nchw(self, x_nchw, c_pad=None):
+        n, c, h, w = x_nchw.shape
+        out = self.empty(n, h, w, c_pad or c)
+        src = x_nchw if x_nchw.dtype in (torch.float32, torch.bfloat16) else x_nchw.float()
+        ops.copy_view(src.permute(0, 2, 3, 1), out)
+        self.launches += 1
+        return out
+
+    def to_nchw_f32(self, act, c):
+        n, h, w, _ = act.shape
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=self.device)
+        ops.copy_view(act[..., :c] if act.shape[3] != c else act, out.permute(0, 2, 3, 1))
+        self.launches += 1
+        return out
+
+    # ---- helpers --------------------------------------------------------------------------------------
+    def _tc_ok(self, gathered, other_c):
+        """tcgen05 path eligibility for a contraction whose gathered operand is `gathered`."""
+        if not self.use_tc or gathered.dtype != torch.bfloat16:
+            return False
+        c = gathered.shape[3]
+        if c % 8 or c < 32 or other_c < 16:
+            return False
+        if gathered.stride(3) != 1 or any(s % 8 for s in gathered.stride()[:3]) or gathered.data_ptr() % 16:
+            return False
+        return gathered.shape[0] * gathered.shape[1] * gathered.shape[2] >= 128
+
+    def _packed(self, spec, role, impl, x):
+        """role: 'fprop' (k = op input channels) or 'dgrad' (k = op output channels); x = gathered operand."""
+        w = spec.weight
+        taps = spec.k * spec.k
+        if role == "fprop":
+            K, N = spec.ci, spec.co
+            src_k_first = spec.transposed          # ConvT weight is [ci][co][taps] = [k][n]
+        else:
+            K, N = spec.co, spec.ci
+            src_k_first = not spec.transposed      # Conv weight is [co][ci][taps] = [k][n]
+        if impl == "tc":
+            layout, K_pad, N_pad, dt = DC_PACK_NTK, _round_up(K, 64), N, torch.bfloat16
+        else:
+            layout, K_pad, N_pad, dt = DC_PACK_TKN, x.shape[3], _round_up(N, 4), x.dtype
+
+        def make():
+            self.launches += 1
+            return ops.pack_weight(w.detach(), K, N, taps, src_k_first, layout, K_pad, N_pad, dt)
+
+        return _cached(spec, (role, impl, dt, K_pad), w, make)
+
+    def _gemm(self, taps, stride, accumulate, wtaps, x, w, bias, out, impl):
+        desc = ops.make_desc(taps, (stride, stride), accumulate, wtaps)
+        ops.conv_gemm(desc, x, w, bias, out, impl)
+        self.launches += 1
+
+    # ---- dense convolution ---------------------------------------------------------------------------------
+    def conv_fwd(self, x, spec, out):
+        """out <- conv(x) (+ bias).  `out` is a preallocated logical-NHWC tensor (possibly a channel slice)."""
+        impl = "tc" if self._tc_ok(x, spec.co) and out.shape[3] == spec.co else "simt"
+        w = self._packed(spec, "fprop", impl, x)
+        bias = spec.bias.detach() if spec.bias is not None else None
+        kk = spec.k * spec.k
+        if not spec.transposed:
+            self._gemm(convdesc.conv_fprop_taps(spec.k, spec.pad, spec.dil), spec.stride, False, kk, x, w, bias, out, impl)
+        else:
+            s = spec.stride
+            for ph in range(s):
+                for pw in range(s):
+                    taps = convdesc.convT_fprop_taps(spec.k, s, spec.pad, ph, pw)
+                    self._gemm(taps, 1, False, kk, x, w, bias, out[:, ph::s, pw::s, :], impl)
+        return out
+
+    def conv_bwd_data(self, dy, spec, dx, accumulate):
+        """dx (+)= conv^T(dy)."""
+        impl = "tc" if self._tc_ok(dy, spec.ci) else "simt"
+        w = self._packed(spec, "dgrad", impl, dy)
+        kk = spec.k * spec.k
+        if spec.transposed:
+            self._gemm(convdesc.convT_dgrad_taps(spec.k, spec.pad), spec.stride, accumulate, kk, dy, w, None, dx, impl)
+        elif spec.stride == 1:
+            self._gemm(convdesc.conv_dgrad_taps(spec.k, spec.pad, spec.dil), 1, accumulate, kk, dy, w, None, dx, impl)
+        else:
+            # strided Conv2d: the input gradient of parity class (ph, pw) is a stride-1 gather of dy
+            s = spec.stride
+            if not accumulate:
+                if dx.is_contiguous():
+                    ops.fill_zero(dx)
+                else:
+                    raise NotImplementedError("strided dgrad into a non-contiguous gradient needs accumulate=True")
+                self.launches += 1
+            for ph in range(s):
+                for pw in range(s):
+                    taps = []
+                    for kh in range(spec.k):
+                        if (ph + spec.pad - kh * spec.dil) % s:
+                            continue
+                        for kw in range(spec.k):
+                            if (pw + spec.pad - kw * spec.dil) % s:
+                                continue
+                            taps.append(((ph + spec.pad - kh * spec.dil) // s, (pw + spec.pad - kw * spec.dil) // s,
+                                         kh * spec.k + kw))
+                    sub = dx[:, ph::s, pw::s, :]
+                    if taps and sub.shape[1] > 0 and sub.shape[2] > 0:
+                        self._gemm(taps, 1, True, kk, dy, w, None, sub, impl)
+        return dx
+
+    def conv_bwd_weight(self, x, dy, spec, wgrad, bgrad=None):
+        """wgrad <- dL/dW in the parameter's own layout (fp32, contiguous view of the flat gradient buffer).
+        The destination must be zero on entry when it is written in place (1x1 Conv2d)."""
+        kk = spec.k * spec.k
+        if spec.transposed:
+            gathered, enumerated = dy, x
+            taps = convdesc.convT_wgrad_taps(spec.k, spec.pad)
+            K, N = spec.co, spec.ci          # G is [tap][ci_in][co_out]
+        else:
+            gathered, enumerated = x, dy
+            taps = convdesc.conv_wgrad_taps(spec.k, spec.pad, spec.dil)
+            K, N = spec.ci, spec.co          # G is [tap][co][ci]
+        impl = "tc" if (self._tc_ok(gathered, 16) and self._tc_ok(enumerated, 16)) else "simt"
+        desc = ops.make_desc(taps, (spec.stride, spec.stride), False, kk)
+        if kk == 1:
+            ops.conv_wgrad(desc, gathered, enumerated, wgrad, impl)       # [co][ci] is already the parameter layout
+            self.launches += 1
+        else:
+            ks = gathered.shape[3]               # >= K when the gathered operand is channel-padded (3 -> 4 logits)
+            G = self.scratch(kk * ks * enumerated.shape[3], torch.float32, zero=True)
+            ops.conv_wgrad(desc, gathered, enumerated, G, impl)
+            ops.unpack_wgrad(G, K, N, kk, False, wgrad, k_stride=ks)
+            self.launches += 2
+        if bgrad is not None:
+            ws = self.scratch(spec.co, torch.float64)
+            ops.channel_sum(dy, ws, bgrad)
+            self.launches += 2
+        return wgrad
+
+    # ---- depthwise ---------------------------------------------------------------------------------------------
+    def _dw_packed(self, spec):
+        def make():
+            self.launches += 1
+            return ops.pack_weight(spec.weight.detach(), 1, spec.c, 9, False, DC_PACK_TKN, 1, spec.c, self.dtype)
+        return _cached(spec, ("dw", self.dtype), spec.weight, make)
+
+    def dw_fwd(self, x, spec, out):
+        ops.dw_fwd(x, self._dw_packed(spec), spec.stride, spec.dil, out)
+        self.launches += 1
+        return out
+
+    def dw_bwd_data(self, dy, spec, dx, accumulate):
+        ops.dw_bwd_data(dy, self._dw_packed(spec), spec.stride, spec.dil, dx, accumulate)
+        self.launches += 1
+        return dx
+
+    def dw_bwd_weight(self, x, dy, spec, wgrad):
+        """wgrad: fp32 [C,1,3,3] view of the flat gradient buffer."""
+        G = self.scratch(9 * spec.c, torch.float32, zero=True)
+        ops.dw_bwd_weight(x, dy, spec.stride, spec.dil, G)
+        ops.unpack_wgrad(G, 1, spec.c, 9, False, wgrad)    # G[tap][c][1] -> [c][1][tap]
+        self.launches += 2
+        return wgrad
+
+    # ---- batch norm (+relu, +residual) ------------------------------------------------------------------------------
+    def bn_fwd(self, y, spec, relu, residual, out, training):
+        """out <- [relu](bn(y) [+ residual]).  spec None = identity (pure relu / add).  Returns the saved statistics."""
+        flags = DC_BN_RELU if relu else 0
+        n, h, w, c = y.shape
+        if spec is None:
+            p = ops.bn_params(None, None, None, None, None, n * h * w, 0.0, 0.0, flags | DC_BN_IDENTITY)
+            ops.bn_apply(p, y, residual, out)
+            self.launches += 1
+            return None
+        m = spec.module
+        sums = None
+        if training:
+            if n * h * w <= 1:
+                raise ValueError("Expected more than 1 value per channel when training, got input size %s"
+                                 % (torch.Size((n, c, h, w)),))
+            sums = self.scratch(2 * c, torch.float64, zero=True)
+            ops.bn_stats(y, sums)
+            self.launches += 1
+            flags |= DC_BN_TRAIN
+        mom = m.momentum if m.momentum is not None else 0.1
+        track = m.running_mean is not None
+        p = ops.bn_params(m.weight.detach(), m.bias.detach(), m.running_mean if track else None,
+                          m.running_var if track else None, sums, n * h * w, mom, m.eps, flags)
+        ops.bn_apply(p, y, residual, out)
+        self.launches += 1
+        return sums
+
+    def bn_bwd(self, dout, out, y, spec, sums, relu, dy, dres, res_accumulate, dgamma, dbeta, training=True):
+        flags = DC_BN_RELU if relu else 0
+        if not res_accumulate:
+            flags |= DC_BN_RES_WRITE
+        n, h, w, c = dout.shape
+        if spec is None:
+            p = ops.bn_params(None, None, None, None, None, n * h * w, 0.0, 0.0, flags | DC_BN_IDENTITY)
+            ops.bn_bwd_apply(p, dout, out, None, None, dy, dres, None, None)
+            self.launches += 1
+            return
+        m = spec.module
+        if training:
+            flags |= DC_BN_TRAIN
+        p = ops.bn_params(m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var, sums, n * h * w, 0.0, m.eps, flags)
+        rsums = self.scratch(2 * c, torch.float64, zero=True)
+        ops.bn_bwd_reduce(p, dout, out if relu else None, y, rsums)
+        ops.bn_bwd_apply(p, dout, out if relu else None, y, rsums, dy, dres, dgamma, dbeta)
+        self.launches += 2
+
+    # ---- image pooling branch ------------------------------------------------------------------------------------------
+    def gap_fwd(self, x):
+        n, _, _, c = x.shape
+        out = torch.empty((n, c), dtype=torch.float32, device=self.device)
+        ops.gap_fwd(x, out)
+        self.launches += 2
+        return out
+
+    def reduce_hw(self, x):
+        n, _, _, c = x.shape
+        out = torch.empty((n, c), dtype=torch.float32, device=self.device)
+        ops.reduce_hw(x, out)
+        self.launches += 2
+        return out
+
+    def broadcast_hw(self, src_nc, out):
+        ops.broadcast_hw(src_nc, out)
+        self.launches += 1
+        return out
+
+    def gap_bwd(self, dmean_nc, dx, accumulate):
+        ops.gap_bwd(dmean_nc, dx, accumulate)
+        self.launches += 1
+        return dx

@@ -1,0 +1,251 @@
+"""Tensor-level wrappers over the C ABI (include/deepcam_b200.h).
+
+Activations are torch CUDA tensors in *logical* NHWC order, i.e. shape [N, H, W, C] with arbitrary strides
+(a channel slice of a concat buffer, a parity sub-grid `t[:, ph::2, pw::2]`, or an NCHW tensor seen through
+`.permute(0, 2, 3, 1)` are all valid).  torch is used for memory and streams only; every kernel is ours.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (DC_BF16, DC_BN_IDENTITY, DC_BN_RELU, DC_BN_RES_WRITE, DC_BN_TRAIN, DC_F32, DC_MAX_TAPS,
+                   DC_PACK_NTK, DC_PACK_TKN, check, dc_bn_params, dc_conv_desc, dc_view)
+
+_DT = {torch.float32: DC_F32, torch.bfloat16: DC_BF16}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("deepcam_b200 kernels need CUDA tensors (got %s); there is no CPU fallback" % t.device)
+
+
+def view(t):
+    """dc_view of a logical-NHWC tensor (None -> null view)."""
+    if t is None:
+        return dc_view()
+    if t.dim() != 4:
+        raise ValueError("expected a 4-D logical NHWC tensor, got shape %s" % (tuple(t.shape),))
+    if t.dtype not in _DT:
+        raise TypeError("unsupported dtype %s" % t.dtype)
+    n, h, w, c = t.shape
+    sn, sh, sw, sc = t.stride()
+    return dc_view(t.data_ptr(), n, h, w, c, sn, sh, sw, sc, _DT[t.dtype], 0)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+# ---- descriptors ---------------------------------------------------------------------------------
+def make_desc(taps, stride=(1, 1), accumulate=False, wtaps=None):
+    """taps: sequence of (dh, dw, weight_slice)."""
+    if not 1 <= len(taps) <= DC_MAX_TAPS:
+        raise ValueError("1..%d taps supported, got %d" % (DC_MAX_TAPS, len(taps)))
+    d = dc_conv_desc()
+    d.ntaps = len(taps)
+    for i, (dh, dw, wt) in enumerate(taps):
+        d.dh[i], d.dw[i], d.wt[i] = dh, dw, wt
+    d.stride_h, d.stride_w = stride
+    d.accumulate = 1 if accumulate else 0
+    d.wtaps = wtaps if wtaps is not None else (max(t[2] for t in taps) + 1)
+    return d
+
+
+# ---- layout / packing ------------------------------------------------------------------------------
+def copy_view(src, dst):
+    _require_cuda(src, dst)
+    check(_lib.load().dc_copy_view(view(src), view(dst), _stream()), "dc_copy_view")
+    return dst
+
+
+def fill_zero(t):
+    _require_cuda(t)
+    if not t.is_contiguous():
+        raise ValueError("fill_zero needs a contiguous tensor")
+    check(_lib.load().dc_fill_zero(_p(t), t.numel() * t.element_size(), _stream()), "dc_fill_zero")
+    return t
+
+
+def i64_increment_many(ptr_table, count):
+    """ptr_table: int64 CUDA tensor holding `count` device addresses of int64 scalars."""
+    check(_lib.load().dc_i64_increment_many(_p(ptr_table), count, _stream()), "dc_i64_increment_many")
+
+
+def pack_weight(src, K, N, taps, src_k_first, layout, K_pad, N_pad, dtype, out=None):
+    _require_cuda(src)
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    numel = taps * K_pad * N_pad
+    if out is None:
+        out = torch.empty(numel, dtype=dtype, device=src.device)
+    assert out.numel() == numel and out.dtype == dtype
+    check(_lib.load().dc_pack_weight(_p(src), K, N, taps, int(src_k_first), _p(out), layout, K_pad, N_pad, _DT[dtype], _stream()),
+          "dc_pack_weight")
+    return out
+
+
+def unpack_wgrad(G, K, N, taps, dst_k_first, dst, k_stride=None):
+    assert G.dtype == torch.float32 and dst.dtype == torch.float32 and dst.is_contiguous()
+    assert dst.numel() == K * N * taps
+    check(_lib.load().dc_unpack_wgrad(_p(G), K, N, taps, k_stride or K, int(dst_k_first), _p(dst), _stream()), "dc_unpack_wgrad")
+    return dst
+
+
+# ---- dense contractions -----------------------------------------------------------------------------
+def conv_gemm(desc, x, w, bias, out, impl):
+    _require_cuda(x, w, out)
+    lib = _lib.load()
+    fn = lib.dc_conv_gemm_tc if impl == "tc" else lib.dc_conv_gemm_simt
+    check(fn(ctypes.byref(desc), view(x), _p(w), _p(bias), view(out), _stream()), "dc_conv_gemm_" + impl)
+    return out
+
+
+def conv_wgrad(desc, x, dout, G, impl):
+    _require_cuda(x, dout, G)
+    assert G.dtype == torch.float32
+    lib = _lib.load()
+    fn = lib.dc_conv_wgrad_tc if impl == "tc" else lib.dc_conv_wgrad_simt
+    check(fn(ctypes.byref(desc), view(x), view(dout), _p(G), _stream()), "dc_conv_wgrad_" + impl)
+    return G
+
+
+# ---- depthwise ----------------------------------------------------------------------------------------
+def dw_fwd(x, w9c, stride, dil, out):
+    _require_cuda(x, w9c, out)
+    check(_lib.load().dc_dw_fwd(view(x), _p(w9c), stride, dil, view(out), _stream()), "dc_dw_fwd")
+    return out
+
+
+def dw_bwd_data(dout, w9c, stride, dil, din, accumulate):
+    _require_cuda(dout, w9c, din)
+    check(_lib.load().dc_dw_bwd_data(view(dout), _p(w9c), stride, dil, view(din), int(accumulate), _stream()), "dc_dw_bwd_data")
+    return din
+
+
+def dw_bwd_weight(x, dout, stride, dil, G9c):
+    _require_cuda(x, dout, G9c)
+    assert G9c.dtype == torch.float32
+    check(_lib.load().dc_dw_bwd_weight(view(x), view(dout), stride, dil, _p(G9c), _stream()), "dc_dw_bwd_weight")
+    return G9c
+
+
+# ---- batch norm -----------------------------------------------------------------------------------------
+def bn_stats(y, sums):
+    _require_cuda(y, sums)
+    assert sums.dtype == torch.float64 and sums.numel() == 2 * y.shape[3]
+    check(_lib.load().dc_bn_stats(view(y), _p(sums), _stream()), "dc_bn_stats")
+    return sums
+
+
+def bn_params(gamma, beta, running_mean, running_var, sums, count, momentum, eps, flags):
+    p = dc_bn_params()
+    p.gamma = gamma.data_ptr() if gamma is not None else None
+    p.beta = beta.data_ptr() if beta is not None else None
+    p.running_mean = running_mean.data_ptr() if running_mean is not None else None
+    p.running_var = running_var.data_ptr() if running_var is not None else None
+    p.sums = sums.data_ptr() if sums is not None else None
+    p.count = float(count)
+    p.momentum = float(momentum)
+    p.eps = float(eps)
+    p.flags = int(flags)
+    return p
+
+
+def bn_apply(params, y, residual, out):
+    _require_cuda(y, residual, out)
+    check(_lib.load().dc_bn_apply(ctypes.byref(params), view(y), view(residual), view(out), _stream()), "dc_bn_apply")
+    return out
+
+
+def bn_bwd_reduce(params, dout, out, y, rsums):
+    _require_cuda(dout, rsums)
+    assert rsums.dtype == torch.float64
+    check(_lib.load().dc_bn_bwd_reduce(ctypes.byref(params), view(dout), view(out), view(y), _p(rsums), _stream()), "dc_bn_bwd_reduce")
+    return rsums
+
+
+def bn_bwd_apply(params, dout, out, y, rsums, dy, dres, dgamma, dbeta):
+    _require_cuda(dout)
+    check(_lib.load().dc_bn_bwd_apply(ctypes.byref(params), view(dout), view(out), view(y), _p(rsums), view(dy), view(dres),
+                                      _p(dgamma), _p(dbeta), _stream()), "dc_bn_bwd_apply")
+
+
+def channel_sum(x, ws, out_c):
+    _require_cuda(x, ws, out_c)
+    assert ws.dtype == torch.float64 and ws.numel() >= x.shape[3] and out_c.dtype == torch.float32
+    check(_lib.load().dc_channel_sum(view(x), _p(ws), _p(out_c), _stream()), "dc_channel_sum")
+    return out_c
+
+
+# ---- pooling branch ---------------------------------------------------------------------------------------
+def gap_fwd(x, mean_nc):
+    _require_cuda(x, mean_nc)
+    assert mean_nc.dtype == torch.float32 and mean_nc.is_contiguous()
+    check(_lib.load().dc_gap_fwd(view(x), _p(mean_nc), _stream()), "dc_gap_fwd")
+    return mean_nc
+
+
+def reduce_hw(x, sum_nc):
+    _require_cuda(x, sum_nc)
+    assert sum_nc.dtype == torch.float32 and sum_nc.is_contiguous()
+    check(_lib.load().dc_reduce_hw(view(x), _p(sum_nc), _stream()), "dc_reduce_hw")
+    return sum_nc
+
+
+def broadcast_hw(src_nc, dst):
+    _require_cuda(src_nc, dst)
+    assert src_nc.dtype == torch.float32 and src_nc.is_contiguous()
+    check(_lib.load().dc_broadcast_hw(_p(src_nc), view(dst), _stream()), "dc_broadcast_hw")
+    return dst
+
+
+def gap_bwd(dmean_nc, dx, accumulate):
+    _require_cuda(dmean_nc, dx)
+    assert dmean_nc.dtype == torch.float32 and dmean_nc.is_contiguous()
+    check(_lib.load().dc_gap_bwd(_p(dmean_nc), view(dx), int(accumulate), _stream()), "dc_gap_bwd")
+    return dx
+
+
+# ---- loss / metric -------------------------------------------------------------------------------------------
+def wce_fwd(logits_nhwc, target, class_w, acc, loss_out):
+    _require_cuda(logits_nhwc, target, class_w)
+    assert target.dtype == torch.int64 and target.is_contiguous()
+    check(_lib.load().dc_wce_fwd(view(logits_nhwc), _p(target), _p(class_w), _p(acc), _p(loss_out), _stream()), "dc_wce_fwd")
+    return loss_out
+
+
+def wce_bwd(logits_nhwc, target, class_w, gscale, dlogits_nhwc):
+    _require_cuda(logits_nhwc, target, class_w, dlogits_nhwc)
+    assert target.dtype == torch.int64 and target.is_contiguous()
+    check(_lib.load().dc_wce_bwd(view(logits_nhwc), _p(target), _p(class_w), _p(gscale), view(dlogits_nhwc), _stream()), "dc_wce_bwd")
+    return dlogits_nhwc
+
+
+def iou_counts(pred, gt, num_classes, counts):
+    _require_cuda(pred, gt, counts)
+    assert pred.dtype == torch.int64 and gt.dtype == torch.int64 and counts.dtype == torch.int64
+    assert pred.is_contiguous() and gt.is_contiguous() and pred.numel() == gt.numel()
+    check(_lib.load().dc_iou_counts(_p(pred), _p(gt), pred.numel(), num_classes, _p(counts), _stream()), "dc_iou_counts")
+    return counts
+
+
+def argmax_iou(logits_nhwc, gt, num_classes, pred_out, counts):
+    _require_cuda(logits_nhwc)
+    check(_lib.load().dc_argmax_iou(view(logits_nhwc), _p(gt), num_classes, _p(pred_out), _p(counts), _stream()), "dc_argmax_iou")
+
+
+def iou_finalize(counts, num_classes, score_out):
+    check(_lib.load().dc_iou_finalize(_p(counts), num_classes, _p(score_out), _stream()), "dc_iou_finalize")
+    return score_out
+
+
+def scale_f32(x, s):
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    check(_lib.load().dc_scale_f32(_p(x), x.numel(), float(s), _stream()), "dc_scale_f32")
+    return x

@@ -1,0 +1,382 @@
+"""Per-kernel parity on the GPU: every C-ABI kernel against the plain torch operator it replaces,
+teacher-forced (same inputs), fp32 mode at 1e-4 and bf16 mode at 2e-2 relative (BASELINE.json north_star).
+Integer kernels (IoU counters) must be bit-exact."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def to_nhwc(x_nchw, dtype):
+    return x_nchw.permute(0, 2, 3, 1).contiguous().to(dtype).to(dev())
+
+
+def from_nhwc(x):
+    return x.detach().double().cpu().permute(0, 3, 1, 2)
+
+
+def rounded(x, dtype):
+    """value after storage rounding, as double on CPU"""
+    return x.to(dtype).double()
+
+
+def backend(dtype, use_tc=None):
+    from deepcam_b200.backend import CudaBackend
+    return CudaBackend(dtype=dtype, device=dev(), use_tc=use_tc)
+
+
+# --------------------------------------------------------------------------------------------------
+def test_library_loads_and_reports_tcgen05():
+    from deepcam_b200 import _lib
+    lib = _lib.load()
+    assert lib.dc_abi_version() == 1
+    assert lib.dc_device_supports_tcgen05() == 1, "the GPU box must be an sm_100 B200"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_copy_view_layouts(dtype):
+    from deepcam_b200 import ops
+    torch.manual_seed(0)
+    x = torch.rand(2, 16, 24, 40)
+    xd = x.to(dev())
+    out = torch.empty(2, 24, 40, 16, dtype=dtype, device=dev())
+    ops.copy_view(xd.permute(0, 2, 3, 1), out)
+    assert torch.equal(out.cpu(), x.permute(0, 2, 3, 1).to(dtype))
+    # NHWC -> NCHW fp32, dropping a padded channel (4 -> 3)
+    y = torch.rand(2, 24, 40, 4).to(dtype).to(dev())
+    back = torch.empty(2, 3, 24, 40, dtype=torch.float32, device=dev())
+    ops.copy_view(y[..., :3], back.permute(0, 2, 3, 1))
+    assert torch.equal(back.cpu(), y[..., :3].permute(0, 3, 1, 2).float().cpu())
+    # NCHW (3 ch) -> NHWC padded to 4, pad channel zero
+    g = torch.rand(2, 3, 24, 40, device=dev())
+    gp = torch.full((2, 24, 40, 4), 7.0, dtype=dtype, device=dev())
+    ops.copy_view(g.permute(0, 2, 3, 1), gp)
+    assert torch.equal(gp[..., :3].cpu(), g.permute(0, 2, 3, 1).to(dtype).cpu())
+    assert float(gp[..., 3].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,relu,use_res", [(32, True, False), (728, True, True), (48, False, False), (256, False, True)])
+def test_bn_forward_backward(dtype, C, relu, use_res):
+    be = backend(dtype)
+    from deepcam_b200.backend import BnSpec
+    torch.manual_seed(1)
+    N, H, W = 2, 12, 20
+    bn = torch.nn.BatchNorm2d(C).to(dev())
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+    y = rounded(torch.randn(N, C, H, W) * 2 + 0.5, dtype)
+    res = rounded(torch.randn(N, C, H, W), dtype) if use_res else None
+    dout = rounded(torch.randn(N, C, H, W), dtype)
+    # reference in double
+    ref_bn = torch.nn.BatchNorm2d(C).double()
+    ref_bn.load_state_dict({k: v.cpu().double() if v.is_floating_point() else v.cpu() for k, v in bn.state_dict().items()})
+    yr = y.clone().requires_grad_(True)
+    rr = res.clone().requires_grad_(True) if use_res else None
+    o = ref_bn(yr)
+    if use_res:
+        o = o + rr
+    if relu:
+        o = torch.relu(o)
+    o.backward(dout)
+    # ours; y lives in a wider buffer (channel slice) to exercise strides
+    buf = torch.zeros(N, H, W, C + 8, dtype=dtype, device=dev())
+    yv = buf[..., 4:4 + C]
+    yv.copy_(to_nhwc(y, dtype))
+    out = be.empty(N, H, W, C)
+    sums = be.bn_fwd(yv, BnSpec("bn", bn), relu, to_nhwc(res, dtype) if use_res else None, out, training=True)
+    tol = TOL[dtype]
+    assert rel(from_nhwc(out), o) < tol
+    assert rel(bn.running_mean, ref_bn.running_mean) < 1e-5
+    assert rel(bn.running_var, ref_bn.running_var) < 1e-5
+    dy = be.empty(N, H, W, C)
+    dres = be.empty(N, H, W, C) if use_res else None
+    dgamma = torch.empty(C, device=dev())
+    dbeta = torch.empty(C, device=dev())
+    be.bn_bwd(to_nhwc(dout, dtype), out, yv, BnSpec("bn", bn), sums, relu, dy, dres, False, dgamma, dbeta)
+    # the ReLU mask comes from the stored (rounded) output; compare where that does not flip anything
+    assert rel(from_nhwc(dy), yr.grad) < (tol if dtype == torch.float32 else 3e-2)
+    assert rel(dgamma, ref_bn.weight.grad) < (tol if dtype == torch.float32 else 3e-2)
+    assert rel(dbeta, ref_bn.bias.grad) < (tol if dtype == torch.float32 else 3e-2)
+    if use_res:
+        assert rel(from_nhwc(dres), rr.grad) < tol
+
+
+def test_bn_eval_mode_and_n1_error():
+    be = backend(torch.float32)
+    from deepcam_b200.backend import BnSpec
+    bn = torch.nn.BatchNorm2d(16).to(dev())
+    with torch.no_grad():
+        bn.running_mean.uniform_(-1, 1)
+        bn.running_var.uniform_(0.5, 2)
+    x = torch.randn(1, 16, 1, 1)
+    out = be.empty(1, 1, 1, 16)
+    with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
+        be.bn_fwd(to_nhwc(x, torch.float32), BnSpec("bn", bn), True, None, out, training=True)
+    be.bn_fwd(to_nhwc(x, torch.float32), BnSpec("bn", bn), True, None, out, training=False)
+    ref = torch.relu(F.batch_norm(x.to(dev()), bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.1, bn.eps))
+    assert rel(from_nhwc(out), ref) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,stride,dil", [(64, 1, 1), (128, 2, 1), (728, 1, 1), (1024, 1, 2)])
+def test_depthwise(dtype, C, stride, dil):
+    be = backend(dtype)
+    from deepcam_b200.backend import DwSpec
+    torch.manual_seed(2)
+    N, H, W = 2, 14, 22
+    w = torch.nn.Parameter(rounded(torch.randn(C, 1, 3, 3) * 0.3, dtype).float().to(dev()))
+    spec = DwSpec("dw", w, stride, dil)
+    x = rounded(torch.randn(N, C, H, W), dtype)
+    xr = x.clone().requires_grad_(True)
+    wr = w.detach().double().cpu().requires_grad_(True)
+    ref = F.conv2d(F.pad(xr, (dil, dil, dil, dil)), wr, None, stride, 0, dil, C)
+    Ho, Wo = spec.out_hw(H, W)
+    assert ref.shape[2:] == (Ho, Wo)
+    dy = rounded(torch.randn_like(ref), dtype)
+    ref.backward(dy)
+    xg = to_nhwc(x, dtype)
+    out = be.dw_fwd(xg, spec, be.empty(N, Ho, Wo, C))
+    tol = TOL[dtype]
+    assert rel(from_nhwc(out), ref) < tol
+    dyg = to_nhwc(dy, dtype)
+    dx = be.dw_bwd_data(dyg, spec, be.empty(N, H, W, C), False)
+    assert rel(from_nhwc(dx), xr.grad) < tol
+    dx2 = be.dw_bwd_data(dyg, spec, dx.clone(), True)
+    assert rel(from_nhwc(dx2), 2 * from_nhwc(dx)) < tol
+    wg = torch.zeros(C, 1, 3, 3, device=dev())
+    be.dw_bwd_weight(xg, dyg, spec, wg)
+    assert rel(wg, wr.grad) < tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_pooling_branch(dtype):
+    be = backend(dtype)
+    torch.manual_seed(3)
+    N, C, H, W = 2, 2048, 6, 9
+    x = rounded(torch.randn(N, C, H, W), dtype)
+    xg = to_nhwc(x, dtype)
+    m = be.gap_fwd(xg)
+    assert rel(m, x.mean(dim=(2, 3))) < 1e-5
+    s = be.reduce_hw(xg)
+    assert rel(s, x.sum(dim=(2, 3))) < 1e-5
+    cat = torch.zeros(N, H, W, 64 + 256, dtype=dtype, device=dev())
+    src = torch.randn(N, 256, device=dev())
+    be.broadcast_hw(src, cat[..., 64:])
+    assert torch.equal(cat[..., 64:].float().cpu(), src.to(dtype).float().cpu()[:, None, None, :].expand(N, H, W, 256))
+    assert float(cat[..., :64].abs().max()) == 0.0
+    dm = torch.randn(N, C, device=dev())
+    dx = be.gap_bwd(dm, be.empty(N, H, W, C), False)
+    assert rel(from_nhwc(dx), (dm.cpu().double() / (H * W))[:, :, None, None].expand(N, C, H, W)) < TOL[dtype]
+    dx2 = be.gap_bwd(dm, dx.clone(), True)
+    assert rel(from_nhwc(dx2), 2 * from_nhwc(dx)) < TOL[dtype]
+
+
+def _ref_fp_loss(logit, target, weight):
+    crit = torch.nn.CrossEntropyLoss(weight=torch.tensor(weight, dtype=logit.dtype), reduction="none")
+    return crit(logit, target).mean()
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 8, 12), (2, 3, 96, 144), (1, 5, 7, 9)])
+def test_weighted_ce(shape):
+    from deepcam_b200 import ops
+    torch.manual_seed(0)
+    N, C, H, W = shape
+    weight = [1.001729912096556, 2.6146112239752224, 1.7164197479589602, 0.5, 1.5][:C]
+    logit = torch.randn(N, C, H, W)
+    target = torch.randint(0, C, (N, H, W))
+    lr = logit.double().requires_grad_(True)
+    ref = _ref_fp_loss(lr, target, weight)
+    ref.backward()
+    lg = logit.to(dev())
+    tg = target.to(dev())
+    cw = torch.tensor(weight, dtype=torch.float32, device=dev())
+    acc = torch.zeros(1, dtype=torch.float64, device=dev())
+    loss = torch.zeros(1, dtype=torch.float32, device=dev())
+    ops.wce_fwd(lg.permute(0, 2, 3, 1), tg, cw, acc, loss)
+    assert abs(float(loss) - float(ref)) < 1e-6 * max(1.0, abs(float(ref)))
+    grad = torch.empty_like(lg)
+    gs = torch.tensor([2.0], device=dev())
+    ops.wce_bwd(lg.permute(0, 2, 3, 1), tg, cw, gs, grad.permute(0, 2, 3, 1))
+    assert rel(grad, 2.0 * lr.grad) < 1e-5
+
+
+def _ref_counts(pred, gt, C):
+    tp = [int(((pred == gt) & (gt == j)).sum()) for j in range(C)]
+    fp = [int(((pred != gt) & (pred == j)).sum()) for j in range(C)]
+    fn = [int(((pred != gt) & (gt == j)).sum()) for j in range(C)]
+    return tp + fp + fn
+
+
+@pytest.mark.parametrize("C,numel", [(3, 8), (3, 2 * 768 * 1152), (8, 100003), (21, 50001)])
+def test_iou_counts_bit_exact(C, numel):
+    from deepcam_b200 import ops
+    torch.manual_seed(4)
+    pred = torch.randint(0, C, (numel,))
+    gt = torch.randint(0, C, (numel,))
+    if C == 3 and numel > 100:
+        gt[: numel // 2] = 0
+        pred[: numel // 2] = 0
+    counts = torch.zeros(3 * C, dtype=torch.int64, device=dev())
+    ops.iou_counts(pred.to(dev()), gt.to(dev()), C, counts)
+    assert counts.cpu().tolist() == _ref_counts(pred, gt, C)
+    score = torch.zeros(1, device=dev())
+    ops.iou_finalize(counts, C, score)
+    c = counts.cpu()
+    ious = []
+    for j in range(C):
+        u = c[j] + c[C + j] + c[2 * C + j]
+        ious.append(torch.tensor(1.0) if u.item() == 0 else c[j].float() / u.float())
+    assert float(score) == float(sum(ious) / float(C))
+
+
+def test_argmax_iou_first_max_tie_rule():
+    from deepcam_b200 import ops
+    torch.manual_seed(5)
+    N, C, H, W = 2, 3, 32, 48
+    logits = torch.randn(N, C, H, W)
+    logits[:, 1] = logits[:, 0]          # ties between class 0 and 1 everywhere
+    logits[0, 2, :4] = 10.0
+    gt = torch.randint(0, C, (N, H, W))
+    ref_pred = torch.max(logits, 1)[1]
+    pred = torch.empty(N, H, W, dtype=torch.int64, device=dev())
+    counts = torch.zeros(3 * C, dtype=torch.int64, device=dev())
+    ops.argmax_iou(logits.to(dev()).permute(0, 2, 3, 1), gt.to(dev()), C, pred, counts)
+    assert torch.equal(pred.cpu(), ref_pred)
+    assert counts.cpu().tolist() == _ref_counts(ref_pred, gt, C)
+
+
+# ---- dense convolutions ---------------------------------------------------------------------------
+CONV_CASES = [
+    # name, Ci, Co, k, stride, pad, dil, H, W, bias
+    ("entry3x3s2", 16, 32, 3, 2, 1, 1, 32, 48, False),
+    ("pw64_128", 64, 128, 1, 1, 0, 1, 24, 40, False),
+    ("pw728", 728, 728, 1, 1, 0, 1, 16, 24, False),
+    ("skip_s2", 128, 256, 1, 2, 0, 1, 24, 40, False),
+    ("aspp_d6", 256, 64, 3, 1, 6, 6, 16, 24, False),
+    ("dec3x3_304", 304, 256, 3, 1, 1, 1, 16, 24, False),
+    ("pw_bias", 256, 256, 1, 1, 0, 1, 16, 24, True),
+    ("lowlevel48", 128, 48, 1, 1, 0, 1, 16, 24, False),
+]
+
+
+def _conv_case(be, dtype, Ci, Co, k, stride, pad, dil, H, W, bias, transposed=False, co_pad=None):
+    from deepcam_b200.backend import ConvSpec
+    N = 2
+    if transposed:
+        mod = torch.nn.ConvTranspose2d(Ci, Co, k, stride=stride, padding=pad, output_padding=1, bias=bias)
+    else:
+        mod = torch.nn.Conv2d(Ci, Co, k, stride=stride, padding=pad, dilation=dil, bias=bias)
+    with torch.no_grad():
+        mod.weight.copy_(rounded(mod.weight, dtype).float())
+    x = rounded(torch.randn(N, Ci, H, W), dtype)
+    ref_mod = (torch.nn.ConvTranspose2d(Ci, Co, k, stride=stride, padding=pad, output_padding=1, bias=bias) if transposed
+               else torch.nn.Conv2d(Ci, Co, k, stride=stride, padding=pad, dilation=dil, bias=bias)).double()
+    ref_mod.load_state_dict({kk: v.double() for kk, v in mod.state_dict().items()})
+    xr = x.clone().requires_grad_(True)
+    ref = ref_mod(xr)
+    dy = rounded(torch.randn_like(ref) * 0.5, dtype)
+    ref.backward(dy)
+    mod = mod.to(dev())
+    spec = ConvSpec("c", mod.weight, mod.bias, stride, pad, dil, transposed)
+    Ho, Wo = spec.out_hw(H, W)
+    assert (Ho, Wo) == tuple(ref.shape[2:])
+    xg = to_nhwc(x, dtype)
+    cp = co_pad or Co
+    out = torch.zeros(N, Ho, Wo, cp, dtype=dtype, device=dev())
+    be.conv_fwd(xg, spec, out)
+    res = {"fwd": rel(from_nhwc(out[..., :Co]), ref)}
+    dyg = torch.zeros(N, Ho, Wo, cp, dtype=dtype, device=dev())
+    dyg[..., :Co] = to_nhwc(dy, dtype)
+    dx = be.conv_bwd_data(dyg, spec, be.empty(N, H, W, Ci), False)
+    res["dgrad"] = rel(from_nhwc(dx), xr.grad)
+    dx_acc = dx.clone()
+    be.conv_bwd_data(dyg, spec, dx_acc, True)
+    res["dgrad_acc"] = rel(from_nhwc(dx_acc), 2 * from_nhwc(dx))
+    wg = torch.zeros_like(mod.weight)
+    bg = torch.zeros(Co, device=dev()) if bias else None
+    be.conv_bwd_weight(xg, dyg, spec, wg, bg)
+    res["wgrad"] = rel(wg, ref_mod.weight.grad)
+    if bias:
+        res["bgrad"] = rel(bg, ref_mod.bias.grad)
+    return res
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_simt(dtype, case):
+    torch.manual_seed(6)
+    be = backend(dtype, use_tc=False)
+    res = _conv_case(be, dtype, *case[1:])
+    for k, v in res.items():
+        assert v < TOL[dtype], (case[0], k, v, res)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("Ci,Co,H,W,co_pad", [(256, 256, 12, 18, None), (256, 3, 24, 36, 4)])
+def test_conv_transpose_simt(dtype, Ci, Co, H, W, co_pad):
+    torch.manual_seed(7)
+    be = backend(dtype, use_tc=False)
+    res = _conv_case(be, dtype, Ci, Co, 3, 2, 1, 1, H, W, False, transposed=True, co_pad=co_pad)
+    for k, v in res.items():
+        assert v < TOL[dtype], (k, v, res)
+
+
+@pytest.mark.parametrize("case", CONV_CASES[1:], ids=[c[0] for c in CONV_CASES[1:]])
+def test_conv_tcgen05(case):
+    torch.manual_seed(8)
+    be = backend(torch.bfloat16, use_tc=True)
+    res = _conv_case(be, torch.bfloat16, *case[1:])
+    for k, v in res.items():
+        assert v < TOL[torch.bfloat16], (case[0], k, v, res)
+
+
+def test_conv_transpose_tcgen05():
+    torch.manual_seed(9)
+    be = backend(torch.bfloat16, use_tc=True)
+    res = _conv_case(be, torch.bfloat16, 256, 256, 3, 2, 1, 1, 12, 18, False, transposed=True)
+    for k, v in res.items():
+        assert v < TOL[torch.bfloat16], (k, v, res)
+
+
+def test_conv_tcgen05_full_size_middle_flow_layer():
+    """728 -> 728 pointwise at 48x72, N=2: the layer that repeats 50 times."""
+    torch.manual_seed(10)
+    be = backend(torch.bfloat16, use_tc=True)
+    res = _conv_case(be, torch.bfloat16, 728, 728, 1, 1, 0, 1, 48, 72, False)
+    for k, v in res.items():
+        assert v < TOL[torch.bfloat16], (k, v, res)
+
+
+def test_conv_tcgen05_writes_concat_slice():
+    from deepcam_b200.backend import ConvSpec
+    torch.manual_seed(11)
+    be = backend(torch.bfloat16, use_tc=True)
+    N, Ci, Co, H, W = 2, 256, 256, 16, 24
+    mod = torch.nn.Conv2d(Ci, Co, 1, bias=False)
+    with torch.no_grad():
+        mod.weight.copy_(mod.weight.bfloat16().float())
+    x = torch.randn(N, Ci, H, W).bfloat16().double()
+    ref = F.conv2d(x, mod.weight.double())
+    mod = mod.to(dev())
+    cat = torch.zeros(N, H, W, 1280, dtype=torch.bfloat16, device=dev())
+    be.conv_fwd(to_nhwc(x, torch.bfloat16), ConvSpec("c", mod.weight), cat[..., 512:768])
+    assert rel(from_nhwc(cat[..., 512:768]), ref) < 2e-2
+    assert float(cat[..., :512].abs().max()) == 0.0 and float(cat[..., 768:].abs().max()) == 0.0
