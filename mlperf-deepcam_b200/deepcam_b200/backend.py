@@ -64,6 +64,9 @@ class BnSpec:
         return self.module.num_features
 
 
+_COUNTER_TABLES = {}      # tuple of counter addresses -> device table (built once per module instance)
+
+
 def _cached(spec, key, param, make):
     ver = (param._version, param.data_ptr())
     ent = spec._cache.get(key)
@@ -102,6 +105,22 @@ class CudaBackend:
             ops.fill_zero(t)
             self.launches += 1
         return t
+
+    def fill_zero_flat(self, flat):
+        ops.fill_zero(flat)
+        self.launches += 1
+
+    def increment_counters(self, counters):
+        """num_batches_tracked += 1 for every BatchNorm that ran in training mode: one launch for all of them."""
+        key = tuple(c.data_ptr() for c in counters)
+        table = _COUNTER_TABLES.get(key)
+        if table is None:
+            table = torch.tensor(key, dtype=torch.int64, device=self.device)
+            if len(_COUNTER_TABLES) > 64:
+                _COUNTER_TABLES.clear()
+            _COUNTER_TABLES[key] = table
+        ops.i64_increment_many(table, len(key))
+        self.launches += 1
 
     # ---- layout -------------------------------------------------------------------------------------
     def from_nchw(self, x_nchw, c_pad=None):

@@ -1,0 +1,371 @@
+"""Forward/backward engine of the DeepCAM network on top of a layer-level backend.
+
+The nn.Modules in architecture/deeplab_xception.py only own parameters (so state_dict, optimizers and
+checkpoints behave exactly as in the reference).  Their forward() describes the network to this engine as a
+sequence of layer operations on channels-last activations; the engine executes them immediately on the
+backend and, when gradients are needed, records one closure per operation.  backward() replays the closures
+in reverse with explicit gradient-buffer management: the first writer of a gradient buffer writes, later
+writers accumulate in their epilogue (no separate add kernels), concat buffers are never materialised twice
+(producers write channel slices), and parameter gradients land in one flat fp32 buffer that the
+data-parallel wrapper all-reduces bucket by bucket while backward is still running.
+
+The whole plan is wrapped in ONE torch.autograd.Function per root module call, so autograd sees
+(input, *parameters) -> outputs and the reference training loop (TR:345-371) runs unchanged.
+"""
+import os
+import threading
+
+import torch
+
+from .backend import BnSpec, ConvSpec, CudaBackend, DwSpec  # noqa: F401  (re-exported for the modules)
+
+_PRECISIONS = {"bf16": torch.bfloat16, "fp32": torch.float32}
+_state = threading.local()
+
+
+def default_precision():
+    return os.environ.get("DEEPCAM_B200_PRECISION", "bf16")
+
+
+def set_backend_factory(factory):
+    """TEST HOOK: tests/ installs a torch-CPU interpreter of the backend interface to check the graph logic
+    without a GPU.  The product never calls this; the default factory builds the CUDA backend and raises on CPU."""
+    _state.factory = factory
+
+
+def _make_backend(precision, device):
+    factory = getattr(_state, "factory", None)
+    if factory is not None:
+        return factory(_PRECISIONS[precision], device)
+    if device.type != "cuda":
+        raise RuntimeError(
+            "deepcam_b200 runs on CUDA (sm_100a) only: input is on %s and there is no CPU fallback. "
+            "Move the module and its inputs to a B200 device." % device)
+    return CudaBackend(_PRECISIONS[precision], device)
+
+
+class Act:
+    """Channels-last activation: tensor [N,H,W,C] (possibly a channel slice of a concat buffer) + its gradient."""
+    __slots__ = ("t", "_grad", "is_relu", "needs_grad", "parent", "c_off")
+
+    def __init__(self, t, is_relu=False, needs_grad=True, parent=None, c_off=0):
+        self.t = t
+        self._grad = None
+        self.is_relu = is_relu
+        self.needs_grad = needs_grad
+        self.parent = parent
+        self.c_off = c_off
+
+    @property
+    def shape(self):
+        return tuple(self.t.shape)
+
+    @property
+    def grad(self):
+        if self.parent is not None:
+            g = self.parent.grad
+            return None if g is None else g[..., self.c_off:self.c_off + self.t.shape[3]]
+        return self._grad
+
+    @grad.setter
+    def grad(self, g):
+        if self.parent is not None:
+            raise RuntimeError("gradient of a concat slice is owned by the concat buffer")
+        self._grad = g
+
+    def slice(self, c_off, c):
+        return Act(self.t[..., c_off:c_off + c], parent=self, c_off=c_off)
+
+
+class GradStore:
+    """Flat fp32 gradient buffer with one parameter-shaped view per parameter (gradient-as-bucket-view).
+
+    Views handed to autograd are fresh tensors, so AccumulateGrad adopts them without a copy when the
+    parameter's .grad is None (optimizer.zero_grad() default).  If any parameter still holds a gradient that
+    aliases the buffer (gradient accumulation, zero_grad(set_to_none=False)) a new buffer is allocated for the
+    next backward so the held gradients stay intact and autograd accumulates into them."""
+
+    def __init__(self, params, device):
+        self.params = list(params)
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
+        self.total = max(off, 4)
+        self.device = device
+        self.flat = None
+        self._index = {id(p): i for i, p in enumerate(self.params)}
+        self._views = {}
+        self.on_ready = None      # callback(param_index): all gradient kernels of that parameter have been launched
+
+    def matches(self, params, device):
+        return self.device == device and len(self.params) == len(params) and all(a is b for a, b in zip(self.params, params))
+
+    def begin_backward(self):
+        """Pick (or allocate) the flat buffer for this backward; returns it un-zeroed."""
+        if self.flat is not None:
+            lo = self.flat.data_ptr()
+            hi = lo + self.flat.numel() * 4
+            for p in self.params:
+                g = p.grad
+                if g is not None and lo <= g.data_ptr() < hi:
+                    self.flat = None
+                    break
+        if self.flat is None:
+            self.flat = torch.empty(self.total, dtype=torch.float32, device=self.device)
+        self._views = {}
+        return self.flat
+
+    def view(self, p):
+        v = self._views.get(id(p))
+        if v is None:
+            o = self.offsets[self._index[id(p)]]
+            v = self.flat[o:o + p.numel()].view(p.shape)
+            self._views[id(p)] = v
+        return v
+
+    def take_views(self):
+        """Parameter-ordered gradient views for autograd; drops our own references so autograd can adopt them."""
+        out = tuple(self.view(p) if p.requires_grad else None for p in self.params)
+        self._views = {}
+        return out
+
+    def ready(self, p):
+        if self.on_ready is not None:
+            self.on_ready(self._index[id(p)])
+
+
+class Engine:
+    def __init__(self, backend, record, grads=None):
+        self.be = backend
+        self.record = record
+        self.grads = grads
+        self.tape = []
+        self.bn_trained = []        # BatchNorm modules that ran in training mode (num_batches_tracked += 1)
+
+    # ---- activations ---------------------------------------------------------------------------------
+    def new_act(self, n, h, w, c, dtype=None):
+        return Act(self.be.empty(n, h, w, c, dtype))
+
+    def from_nchw(self, x, needs_grad, c_pad=None):
+        return Act(self.be.from_nchw(x, c_pad), needs_grad=needs_grad)
+
+    def grad_target(self, act):
+        """(gradient tensor, accumulate?) for a writer of act's gradient: the first writer writes."""
+        g = act.grad
+        if g is not None:
+            return g, True
+        if act.parent is not None:
+            raise RuntimeError("concat-slice gradient requested before the concat consumer ran backward")
+        n, h, w, c = act.shape
+        act.grad = self.be.empty(n, h, w, c, act.t.dtype)
+        return act.grad, False
+
+    # ---- operations -------------------------------------------------------------------------------------
+    def conv(self, x, spec, out=None, out_c=None, out_dtype=None):
+        n, h, w, _ = x.shape
+        ho, wo = spec.out_hw(h, w)
+        if out is None:
+            out = self.new_act(n, ho, wo, out_c or spec.co, out_dtype or x.t.dtype)
+        elif out.shape[:3] != (n, ho, wo):
+            raise RuntimeError("conv %s: output buffer %s does not match %s" % (spec.name, out.shape, (n, ho, wo)))
+        self.be.conv_fwd(x.t, spec, out.t)
+        if self.record:
+            self.tape.append(lambda: self._conv_bwd(x, out, spec))
+        return out
+
+    def _conv_bwd(self, x, out, spec):
+        dy = out.grad
+        if dy is None:
+            return
+        if spec.weight.requires_grad:
+            bgrad = self.grads.view(spec.bias) if (spec.bias is not None and spec.bias.requires_grad) else None
+            self.be.conv_bwd_weight(x.t, dy, spec, self.grads.view(spec.weight), bgrad)
+            self.grads.ready(spec.weight)
+            if bgrad is not None:
+                self.grads.ready(spec.bias)
+        if x.needs_grad:
+            dx, acc = self.grad_target(x)
+            self.be.conv_bwd_data(dy, spec, dx, acc)
+
+    def dw(self, x, spec):
+        n, h, w, c = x.shape
+        ho, wo = spec.out_hw(h, w)
+        out = self.new_act(n, ho, wo, c, x.t.dtype)
+        self.be.dw_fwd(x.t, spec, out.t)
+        if self.record:
+            self.tape.append(lambda: self._dw_bwd(x, out, spec))
+        return out
+
+    def _dw_bwd(self, x, out, spec):
+        dy = out.grad
+        if dy is None:
+            return
+        if spec.weight.requires_grad:
+            self.be.dw_bwd_weight(x.t, dy, spec, self.grads.view(spec.weight))
+            self.grads.ready(spec.weight)
+        if x.needs_grad:
+            dx, acc = self.grad_target(x)
+            self.be.dw_bwd_data(dy, spec, dx, acc)
+
+    def bn(self, y, spec, relu, residual=None, out=None):
+        """out = [relu](bn(y) [+ residual]); spec None = identity (plain relu / add / copy)."""
+        n, h, w, c = y.shape
+        if out is None:
+            out = self.new_act(n, h, w, c, y.t.dtype)
+        elif out.shape != y.shape:
+            raise RuntimeError("output buffer %s does not match the normalised tensor %s (concat size mismatch)"
+                               % (out.shape, y.shape))
+        out.is_relu = relu
+        training = bool(spec.module.training) if spec is not None else False
+        if spec is not None and not training and spec.module.running_mean is None:
+            training = True          # track_running_stats=False always uses batch statistics
+        sums = self.be.bn_fwd(y.t, spec, relu, residual.t if residual is not None else None, out.t, training)
+        if spec is not None and training and spec.module.num_batches_tracked is not None:
+            self.bn_trained.append(spec.module)
+        if self.record:
+            self.tape.append(lambda: self._bn_bwd(y, out, spec, sums, relu, residual, training))
+        return out
+
+    def _bn_bwd(self, y, out, spec, sums, relu, residual, training):
+        dout = out.grad
+        if dout is None:
+            return
+        dres, racc = (None, False)
+        if residual is not None and residual.needs_grad:
+            dres, racc = self.grad_target(residual)
+        dy = None
+        if y.needs_grad:
+            dy, yacc = self.grad_target(y)
+            if yacc:
+                raise RuntimeError("BatchNorm input gradient must have a single writer")
+        dgamma = dbeta = None
+        if spec is not None:
+            m = spec.module
+            if m.weight is not None and m.weight.requires_grad:
+                dgamma = self.grads.view(m.weight)
+            if m.bias is not None and m.bias.requires_grad:
+                dbeta = self.grads.view(m.bias)
+        self.be.bn_bwd(dout, out.t, y.t, spec, sums, relu, dy, dres, racc, dgamma, dbeta, training)
+        if dgamma is not None:
+            self.grads.ready(spec.module.weight)
+        if dbeta is not None:
+            self.grads.ready(spec.module.bias)
+
+    def gap(self, x):
+        """AdaptiveAvgPool2d(1): [N,H,W,C] -> fp32 [N,1,1,C]."""
+        n, h, w, c = x.shape
+        m = self.be.gap_fwd(x.t)
+        out = Act(m.view(n, 1, 1, c))
+        if self.record:
+            self.tape.append(lambda: self._gap_bwd(x, out))
+        return out
+
+    def _gap_bwd(self, x, out):
+        if out.grad is None or not x.needs_grad:
+            return
+        n, h, w, c = x.shape
+        dx, acc = self.grad_target(x)
+        self.be.gap_bwd(out.grad.reshape(n, c), dx, acc)
+
+    def broadcast(self, src, out):
+        """F.interpolate(1x1 -> HxW, bilinear, align_corners=True) == broadcast (DX:450)."""
+        n, _, _, c = src.shape
+        self.be.broadcast_hw(src.t.reshape(n, c), out.t)
+        if self.record:
+            self.tape.append(lambda: self._broadcast_bwd(src, out))
+        return out
+
+    def _broadcast_bwd(self, src, out):
+        g = out.grad
+        if g is None or not src.needs_grad:
+            return
+        n, _, _, c = src.shape
+        if src.grad is not None:
+            raise RuntimeError("broadcast source gradient must have a single writer")
+        src.grad = self.be.reduce_hw(g).view(n, 1, 1, c)
+
+    # ---- execution ----------------------------------------------------------------------------------------
+    def finish_forward(self):
+        if self.bn_trained:
+            self.be.increment_counters([m.num_batches_tracked for m in self.bn_trained])
+            self.bn_trained = []
+
+    def backward(self):
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+
+
+# ------------------------------------------------------------------------------------------------------------
+# autograd bridge
+# ------------------------------------------------------------------------------------------------------------
+class _PlanFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, precision, n_in, need_grad, *tensors):
+        inputs, params = tensors[:n_in], tensors[n_in:]
+        device = inputs[0].device
+        be = _make_backend(precision, device)
+        need_grad = bool(need_grad)
+        grads = None
+        if need_grad:
+            grads = getattr(module, "_dc_gradstore", None)
+            if grads is None or not grads.matches(params, device):
+                grads = GradStore(params, device)
+                module._dc_gradstore = grads
+        eng = Engine(be, need_grad, grads)
+        xin = [eng.from_nchw(x.detach(), needs_grad=bool(x.requires_grad and need_grad)) for x in inputs]
+        outs = module._emit_root(eng, *xin)          # list of (Act, valid channels)
+        eng.finish_forward()
+        results = tuple(be.to_nchw_f32(act.t, c) for act, c in outs)
+        module._dc_last_launches = be.launches
+        if need_grad:
+            ctx.eng, ctx.outs, ctx.xin, ctx.module = eng, outs, xin, module
+            ctx.in_dtypes = [x.dtype for x in inputs]
+        else:
+            ctx.eng = None
+        return results
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        eng = ctx.eng
+        if eng is None:
+            raise RuntimeError("backward through a deepcam_b200 module that ran without gradient recording")
+        be = eng.be
+        be.launches = 0
+        flat = eng.grads.begin_backward()
+        be.fill_zero_flat(flat)
+        sync = getattr(ctx.module, "_dc_grad_sync", None)
+        if sync is not None:
+            sync.begin(eng.grads)
+        for (act, c), g in zip(ctx.outs, gouts):
+            if g is not None:
+                act.grad = be.from_nchw(g.contiguous(), act.t.shape[3] if act.t.shape[3] != c else None)
+        eng.backward()
+        if sync is not None:
+            sync.finish(eng.grads)
+        dxs = []
+        for xa, dt in zip(ctx.xin, ctx.in_dtypes):
+            if xa.needs_grad and xa.grad is not None:
+                dxs.append(be.to_nchw_f32(xa.grad, xa.t.shape[3]).to(dt))
+            else:
+                dxs.append(None)
+        ctx.module._dc_last_launches_bwd = be.launches
+        grads = eng.grads.take_views()
+        ctx.eng = ctx.outs = ctx.xin = None
+        return (None, None, None, None) + tuple(dxs) + grads
+
+
+def run_module(module, inputs, precision=None):
+    """Execute `module` (any class of architecture/deeplab_xception.py) on NCHW inputs through the engine.
+    Returns the tuple of NCHW fp32 outputs."""
+    for x in inputs:
+        if not isinstance(x, torch.Tensor) or x.dim() != 4:
+            raise ValueError("expected [N, C, H, W] tensors")
+    precision = precision or getattr(module, "precision", None) or default_precision()
+    if precision not in _PRECISIONS:
+        raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
+    params = list(module.parameters())
+    need_grad = torch.is_grad_enabled() and (any(x.requires_grad for x in inputs) or any(p.requires_grad for p in params))
+    return _PlanFunction.apply(module, precision, len(inputs), need_grad, *inputs, *params)

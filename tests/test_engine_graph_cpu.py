@@ -1,0 +1,202 @@
+"""Graph-logic tests of the product modules + engine, executed with the TEST-ONLY torch interpreter
+(tests/torch_backend.py) on CPU and checked against the oracle.  These cover host logic only (state_dict,
+ReLU aliasing, concat slices, gradient routing/accumulation); kernel parity is in the -m gpu tests."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+import deepcam_oracle as O  # noqa: E402
+import torch_backend  # noqa: E402
+
+from architecture import deeplab_xception as dx  # noqa: E402
+
+
+@pytest.fixture(autouse=True)
+def _interp():
+    torch_backend.install()
+    yield
+    torch_backend.uninstall()
+
+
+@pytest.fixture(scope="module")
+def net():
+    torch.manual_seed(333)
+    m = dx.DeepLabv3_plus(n_input=16, n_classes=3, os=16, _print=False)
+    m.precision = "fp32"
+    return m
+
+
+def test_state_dict_matches_oracle_init_bit_exactly(net):
+    sd = O.init_state_dict(16, 3, 16, seed=333)
+    mine = net.state_dict()
+    assert list(mine.keys()) == list(sd.keys()) and len(mine) == 532
+    for k in sd:
+        assert mine[k].dtype == sd[k].dtype and torch.equal(mine[k], sd[k]), k
+    assert sum(p.numel() for p in net.parameters()) == 56454720
+
+
+def test_state_dict_roundtrip_with_ddp_prefix(net):
+    sd = {"module." + k: v.clone() for k, v in net.state_dict().items()}
+    other = dx.DeepLabv3_plus(16, 3, 16, _print=False)
+    other.load_state_dict({k[len("module."):]: v for k, v in sd.items()})
+    for (ka, va), (kb, vb) in zip(net.state_dict().items(), other.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+
+
+def _grads_close(named_params, P, names, tol):
+    worst = ("", 0.0)
+    for k in names:
+        g = named_params[k].grad
+        assert g is not None, k
+        e = float((g - P[k].grad).norm() / (P[k].grad.norm() + 1e-20))
+        if e > worst[1]:
+            worst = (k, e)
+    assert worst[1] < tol, worst
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def test_full_model_forward_backward_matches_oracle(net):
+    """fp32 mode against the oracle evaluated in fp64 (the fp32 oracle itself sits 6e-5 away from fp64 at the
+    logits, so fp64 is the meaningful yardstick for the 1e-4 end-to-end criterion)."""
+    sd = O.init_state_dict(16, 3, 16, seed=333)
+    net.load_state_dict(sd)
+    net.train()
+    x, label = O.synthetic_batch(2, 32, 48, seed=11)
+    P = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    for k in O.param_names(sd):
+        P[k].requires_grad_(True)
+    ref_logits = O.forward(P, x.double(), train=True)
+    w = O.class_weights()
+    O.fp_loss(ref_logits, label, w).backward()
+
+    out = net(x.clone())
+    assert out.shape == ref_logits.shape and out.dtype == torch.float32
+    assert _rel(out, ref_logits) < 1e-4
+    loss = O.fp_loss(out, label, w)
+    net.zero_grad()
+    loss.backward()
+    # at this tiny size (2x3 feature map, BN over 12 values) the fp32 oracle itself is 2e-2 away from fp64 (median 1.4e-2)
+    _grads_close(dict(net.named_parameters()), P, O.param_names(sd), 1e-2)
+    mine = net.state_dict()
+    for k in sd:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert torch.allclose(mine[k].double(), P[k], rtol=1e-5, atol=1e-6), k
+        if k.endswith("num_batches_tracked"):
+            assert int(mine[k]) == 1, k
+
+
+def test_eval_forward_matches_oracle_and_n1_train_fails(net):
+    sd = O.init_state_dict(16, 3, 16, seed=333)
+    net.load_state_dict(sd)
+    x, _ = O.synthetic_batch(1, 32, 48, seed=12)
+    net.eval()
+    with torch.no_grad():
+        a = net(x)
+    b = O.forward({k: v.clone() for k, v in sd.items()}, x, train=False)
+    assert _rel(a, b) < 1e-4
+    net.train()
+    with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
+        net(x)
+
+
+def test_input_must_be_multiple_of_16(net):
+    with pytest.raises(RuntimeError, match="multiples of 16"):
+        net(torch.rand(2, 16, 40, 48))
+
+
+def test_gradient_accumulation_over_two_backwards(net):
+    sd = O.init_state_dict(16, 3, 16, seed=333)
+    net.load_state_dict(sd)
+    net.train()
+    x, label = O.synthetic_batch(2, 32, 48, seed=13)
+    w = O.class_weights()
+    net.zero_grad()
+    O.fp_loss(net(x), label, w).backward()
+    g1 = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net.load_state_dict(sd)            # same running stats again
+    O.fp_loss(net(x), label, w).backward()      # accumulates into the held gradients
+    for k, p in net.named_parameters():
+        assert torch.allclose(p.grad, 2 * g1[k], rtol=1e-4, atol=1e-7), k
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("cfg", [
+    dict(inplanes=64, planes=128, reps=2, stride=2, start_with_relu=False),
+    dict(inplanes=32, planes=32, reps=3, stride=1, start_with_relu=True),
+    dict(inplanes=32, planes=64, reps=2, stride=1, dilation=2, start_with_relu=True, grow_first=False, is_last=True),
+])
+def test_block_matches_reference_block(cfg):
+    import refload
+    rdx = refload.deeplab()
+    torch.manual_seed(5)
+    ref = rdx.Block(**cfg)
+    mine = dx.Block(**cfg)
+    mine.precision = "fp32"
+    mine.load_state_dict(ref.state_dict())
+    x = torch.randn(2, cfg["inplanes"], 12, 20)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr * 1.0)                     # *1.0: the reference applies an in-place ReLU to its input
+    xm = x.clone().requires_grad_(True)
+    ym = mine(xm)
+    assert _rel(ym, yr) < 1e-5
+    g = torch.randn_like(yr)
+    yr.backward(g)
+    ym.backward(g)
+    assert _rel(xm.grad, xr.grad) < 1e-4
+    for (k, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert _rel(p.grad, q.grad) < 1e-4, k
+
+
+@pytest.mark.reference
+def test_xception_returns_clamped_low_level_features():
+    import refload
+    rdx = refload.deeplab()
+    torch.manual_seed(6)
+    ref = rdx.Xception(inplanes=16, os=16)
+    mine = dx.Xception(inplanes=16, os=16)
+    mine.precision = "fp32"
+    mine.load_state_dict(ref.state_dict())
+    x = torch.rand(2, 16, 32, 48)
+    a, la = ref(x.clone())
+    b, lb = mine(x.clone())
+    assert _rel(b, a) < 2e-4
+    assert _rel(lb, la) < 1e-4
+    assert float(la.min()) >= 0.0          # low_level_feat is relu(block1 output)
+
+
+@pytest.mark.reference
+def test_os8_configuration_matches_reference():
+    import refload
+    rdx = refload.deeplab()
+    torch.manual_seed(7)
+    ref = rdx.DeepLabv3_plus(n_input=4, n_classes=3, os=8, _print=False)
+    torch.manual_seed(7)
+    mine = dx.DeepLabv3_plus(n_input=4, n_classes=3, os=8, _print=False)
+    mine.precision = "fp32"
+    for (k, v), (k2, v2) in zip(ref.state_dict().items(), mine.state_dict().items()):
+        assert k == k2 and torch.equal(v, v2), k
+    # with os=8 the reference's DeconvUpsampler cannot concatenate (deconv2 output is H/2, low-level is H/4):
+    # the configuration constructs but does not run; the drop-in must fail the same way, loudly.
+    x = torch.rand(2, 4, 32, 32)
+    with pytest.raises(RuntimeError):
+        ref(x.clone())
+    with pytest.raises(RuntimeError, match="does not match"):
+        mine(x)
+    # the os=8 backbone itself runs and matches
+    a, la = ref.xception_features(x.clone())
+    mine.xception_features.precision = "fp32"
+    b, lb = mine.xception_features(x.clone())
+    assert _rel(b, a) < 2e-4 and _rel(lb, la) < 1e-4
+
+
+def test_cpu_input_without_test_backend_raises_loudly():
+    torch_backend.uninstall()
+    m = dx.SeparableConv2d_same(8, 16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.rand(1, 8, 8, 8))
