@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — DeepCAM training-step throughput on B200 (BASELINE.json metric: train samples/s @768x1152x16).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (hand-written sm_100a kernels behind the reference API)
+  python bench.py --impl reference --gpus N --steps K ...  reference arm: the CPU oracle port of the reference step
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REPO, "mlperf-deepcam_b200"))
+
+H, W, C_IN, N_CLASSES, LOCAL_BATCH = 768, 1152, 16, 3, 2
+METRIC = "train_samples_per_s_768x1152x16"
+FWD_BWD_GFLOP_PER_SAMPLE = 1963.976
+WORKLOAD = ("configs[1]: DeepLabv3+/Xception (n_input=16, n_classes=3, os=16) fwd + weighted-CE + bwd + Adam, "
+            "local batch 2, synthetic 768x1152x16 tiles")
+
+
+def _peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            with open(self.path) as fh:
+                for line in fh:
+                    f = [x.strip() for x in line.split(",")]
+                    if len(f) < 9 or not f[0].isdigit() or int(f[0]) != self.index:
+                        continue
+                    try:
+                        sm.append(float(f[1])); mx.append(float(f[2]))
+                    except ValueError:
+                        continue
+                    for nm, val in zip(names, f[5:9]):
+                        if val.lower().startswith("active"):
+                            reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the step, i.e. the oracle port (the reference is
+    Python/torch and cannot travel to the GPU box; oracle/deepcam_oracle.py restates it op for op and is pinned
+    against it in the build container).  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import deepcam_oracle as O
+    cores = torch.get_num_threads()
+    sd = O.init_state_dict(C_IN, N_CLASSES, 16, seed=333)
+    st = O.TrainState(sd)
+    # calibrate the per-pixel cost on a 192x288 crop, then size the per-step sample so K+W steps fit the budget
+    x, label = O.synthetic_batch(LOCAL_BATCH, 192, 288, seed=333)
+    t0 = time.time()
+    st.step(x, label)
+    t_cal = time.time() - t0
+    budget = float(os.environ.get("DEEPCAM_REF_BUDGET_S", "150"))
+    n_steps = args.steps + args.warmup
+    per_row = t_cal / 192.0 * (W / 288.0)
+    rows = int(budget / max(n_steps, 1) / per_row) // 16 * 16
+    rows = max(32, min(H, rows))
+    x, label = O.synthetic_batch(LOCAL_BATCH, rows, W, seed=333)
+    for _ in range(args.warmup):
+        st.step(x, label)
+    t0 = time.time()
+    for _ in range(args.steps):
+        st.step(x, label)
+    dt = time.time() - t0
+    frac = rows / float(H)
+    value = LOCAL_BATCH * frac * args.steps / dt
+    sample = "%d steps of N=%d crops %dx%dx%d (%.4f of a 768x1152 tile each; value scaled by pixel count), fp32, %d threads" % (
+        args.steps, LOCAL_BATCH, rows, W, C_IN, frac, cores)
+    line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1000.0 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD, local_batch=LOCAL_BATCH, optimizer="Adam lr=1e-3 eps=1e-8 wd=1e-6"),
+                cpu_baseline=dict(value=value, unit="samples/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample():
+    """One full-size reference step (N=2, 768x1152x16, fp32) on the host cores with the oracle port."""
+    import torch
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import deepcam_oracle as O
+    cores = torch.get_num_threads()
+    rows = int(os.environ.get("DEEPCAM_CPU_BASELINE_ROWS", str(H)))
+    sd = O.init_state_dict(C_IN, N_CLASSES, 16, seed=333)
+    st = O.TrainState(sd)
+    x, label = O.synthetic_batch(LOCAL_BATCH, rows, W, seed=333)
+    t0 = time.time()
+    st.step(x, label)
+    dt = time.time() - t0
+    frac = rows / float(H)
+    return dict(value=LOCAL_BATCH * frac / dt, unit="samples/s", cores=cores, kind="port",
+                sample="1 cold step, N=%d, %dx%dx%d, fp32, Adam, %.1f s on %d threads" % (LOCAL_BATCH, rows, W, C_IN, dt, cores))
+
+
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from architecture import deeplab_xception as dx
+    from utils import losses
+    from deepcam_b200 import _lib, ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    precision = os.environ.get("DEEPCAM_B200_PRECISION", "bf16")
+
+    torch.manual_seed(333)
+    net = dx.DeepLabv3_plus(n_input=C_IN, n_classes=N_CLASSES, os=16, _print=False)
+    net.precision = precision
+    net = net.to(dev).train()
+    model = net
+    if world > 1:
+        from deepcam_b200.parallel import DistributedDataParallel
+        model = DistributedDataParallel(net)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, eps=1e-8, weight_decay=1e-6)
+    cw = [1.001729912096556, 2.6146112239752224, 1.7164197479589602]
+
+    g = torch.Generator().manual_seed(333 + rank)
+    x_host = torch.rand((LOCAL_BATCH, C_IN, H, W), generator=g).pin_memory()
+    u = torch.rand((LOCAL_BATCH, H, W), generator=g)
+    label_host = torch.zeros((LOCAL_BATCH, H, W), dtype=torch.long)
+    label_host[u > 0.986267818] = 2
+    label_host[u > 0.986267818 + 0.013274311] = 1
+    label_host = label_host.pin_memory()
+    x_dev, label_dev = x_host.to(dev), label_host.to(dev)
+
+    def step(x, label):
+        out = model.forward(x)
+        loss = losses.fp_loss(out, label, weight=cw, fpw_1=cw[1], fpw_2=cw[2])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        sync_all()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(warmup):
+        step(x_dev, label_dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count
+    ms = timed(lambda: step(x_dev, label_dev), args.steps)
+    launches = _lib.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else {}
+    value = world * LOCAL_BATCH * args.steps / (ms / 1000.0)
+
+    # ---- end to end through the public API with host buffers: H2D of the batch + D2H of the loss every step ----
+    last = {}
+
+    def e2e_step():
+        xb = x_host.to(dev, non_blocking=True)
+        lb = label_host.to(dev, non_blocking=True)
+        last["loss"] = step(xb, lb).item()
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * LOCAL_BATCH * args.steps / (ms_e2e / 1000.0)
+    h2d = x_host.numel() * 4 + label_host.numel() * 8
+
+    # ---- per-kernel-class roofline pass: CUDA events around every launch, same process, right after timing ----
+    roofline = None
+    classes = None
+    if rank == 0 and not args.no_profile:
+        peaks = _peaks()
+        prof = ops.Profiler()
+        ops.set_profiler(prof)
+        psteps = 2
+        for _ in range(psteps):
+            step(x_dev, label_dev)
+        ops.set_profiler(None)
+        classes = prof.summary()
+        tensor_kinds = ("conv_gemm_tc", "conv_wgrad_tc", "conv_gemm_simt", "conv_wgrad_simt")
+        top = max(classes.items(), key=lambda kv: kv[1]["ms"])
+        name, d = top
+        sec = d["ms"] / 1000.0
+        if name in tensor_kinds:
+            ach = d["flops"] / sec / 1e12
+            roofline = dict(kernel=name, bound="tensor", achieved=ach, peak=peaks["tf_sustained"], unit="TFLOP/s",
+                            frac=ach / peaks["tf_sustained"], traffic=None)
+        else:
+            ach = d["bytes"] / sec / 1e9
+            roofline = dict(kernel=name, bound="hbm", achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"],
+                            traffic=None)
+        roofline.update(peak_source=peaks["source"] + (" sustained" if name in tensor_kinds else " copy"),
+                        launches_per_step=d["launches"] / psteps, avg_launch_us=1000.0 * d["ms"] / d["launches"],
+                        class_ms_per_step=d["ms"] / psteps,
+                        how="CUDA events around every launch of the class, %d instrumented steps after the timed region" % psteps)
+        out_dir = os.path.join(REPO, "gpurun_out")
+        try:
+            os.makedirs(out_dir, exist_ok=True)
+            table = {}
+            for k, v in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):
+                s = v["ms"] / 1000.0
+                table[k] = dict(launches_per_step=v["launches"] / psteps, ms_per_step=v["ms"] / psteps,
+                                tflops=v["flops"] / s / 1e12 if s > 0 else 0.0, gbs=v["bytes"] / s / 1e9 if s > 0 else 0.0)
+            with open(os.path.join(out_dir, "bench_kernel_classes.json"), "w") as fh:
+                json.dump(dict(ms_per_step_timed=ms / args.steps, classes=table, peaks=peaks), fh, indent=1)
+        except Exception:
+            pass
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline_sample()
+
+    if rank == 0:
+        peaks = _peaks()
+        line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="bf16" if precision == "bf16" else "f32", data="synthetic",
+                    config=dict(workload=WORKLOAD, local_batch=LOCAL_BATCH, global_batch=LOCAL_BATCH * world,
+                                optimizer="torch.optim.Adam lr=1e-3 eps=1e-8 wd=1e-6 (TR:566-568)",
+                                parallelism="dp%d" % world,
+                                l2="per-step working set (>7 GB of activations) exceeds the 126 MB L2; no explicit flush"),
+                    e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                             ms_per_step=ms_e2e / args.steps, loss=last.get("loss")),
+                    gpu_launches=launches, clocks=clocks,
+                    tensor_frac_of_step=(FWD_BWD_GFLOP_PER_SAMPLE * value / 1000.0) / peaks["tf_sustained"],
+                    roofline=roofline, cpu_baseline=cpu_base)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -98,7 +98,18 @@ class KernelError(RuntimeError):
     pass
 
 
+# kernels launched per successful C call (cudaMemsetAsync nodes are not counted as kernels)
+_KERNELS_PER_CALL = {"dc_fill_zero": 0, "dc_wce_fwd": 2, "dc_channel_sum": 2}
+launch_count = 0          # number of deepcam_b200 kernels launched by this process (bench.py reports it)
+launch_hist = {}
+
+
 def check(rc, what=""):
+    global launch_count
+    n = _KERNELS_PER_CALL.get(what, 1)
+    launch_count += n
+    if n:
+        launch_hist[what] = launch_hist.get(what, 0) + n
     if rc != 0:
         msg = load().dc_last_error_string().decode("utf-8", "replace")
         raise KernelError("%s failed (code %d): %s" % (what or "deepcam_b200 kernel", rc, msg))

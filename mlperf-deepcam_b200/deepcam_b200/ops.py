@@ -51,6 +51,56 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+# ---- optional per-launch timing (bench.py roofline pass): CUDA events on the launching stream ------------
+class Profiler:
+    """Collects (kernel class, start event, end event, algorithmic FLOPs, algorithmic bytes) per launch."""
+
+    def __init__(self):
+        self.items = []
+
+    def begin(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, name, start, flops, nbytes):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.items.append((name, start, e, flops, nbytes))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, s, e, fl, nb in self.items:
+            d = out.setdefault(name, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["launches"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["flops"] += fl
+            d["bytes"] += nb
+        return out
+
+
+_prof = None
+
+
+def set_profiler(p):
+    global _prof
+    _prof = p
+
+
+def _nbytes(*ts):
+    return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
+
+
+def _timed(name, flops, nbytes, rc_fn, what):
+    if _prof is None:
+        check(rc_fn(), what)
+        return
+    st = _prof.begin()
+    check(rc_fn(), what)
+    _prof.end(name, st, flops, nbytes)
+
+
 # ---- descriptors ---------------------------------------------------------------------------------
 def make_desc(taps, stride=(1, 1), accumulate=False, wtaps=None):
     """taps: sequence of (dh, dw, weight_slice)."""
@@ -69,7 +119,7 @@ def make_desc(taps, stride=(1, 1), accumulate=False, wtaps=None):
 # ---- layout / packing ------------------------------------------------------------------------------
 def copy_view(src, dst):
     _require_cuda(src, dst)
-    check(_lib.load().dc_copy_view(view(src), view(dst), _stream()), "dc_copy_view")
+    _timed("copy_view", 0.0, _nbytes(src, dst), lambda: _lib.load().dc_copy_view(view(src), view(dst), _stream()), "dc_copy_view")
     return dst
 
 
@@ -110,7 +160,11 @@ def conv_gemm(desc, x, w, bias, out, impl):
     _require_cuda(x, w, out)
     lib = _lib.load()
     fn = lib.dc_conv_gemm_tc if impl == "tc" else lib.dc_conv_gemm_simt
-    check(fn(ctypes.byref(desc), view(x), _p(w), _p(bias), view(out), _stream()), "dc_conv_gemm_" + impl)
+    m = out.shape[0] * out.shape[1] * out.shape[2]
+    flops = 2.0 * m * out.shape[3] * x.shape[3] * desc.ntaps
+    nbytes = _nbytes(x, out) + desc.ntaps * x.shape[3] * out.shape[3] * x.element_size()
+    _timed("conv_gemm_" + impl, flops, nbytes,
+           lambda: fn(ctypes.byref(desc), view(x), _p(w), _p(bias), view(out), _stream()), "dc_conv_gemm_" + impl)
     return out
 
 
@@ -119,27 +173,34 @@ def conv_wgrad(desc, x, dout, G, impl):
     assert G.dtype == torch.float32
     lib = _lib.load()
     fn = lib.dc_conv_wgrad_tc if impl == "tc" else lib.dc_conv_wgrad_simt
-    check(fn(ctypes.byref(desc), view(x), view(dout), _p(G), _stream()), "dc_conv_wgrad_" + impl)
+    m = dout.shape[0] * dout.shape[1] * dout.shape[2]
+    flops = 2.0 * m * dout.shape[3] * x.shape[3] * desc.ntaps
+    nbytes = _nbytes(x, dout) + 4.0 * desc.ntaps * x.shape[3] * dout.shape[3]
+    _timed("conv_wgrad_" + impl, flops, nbytes,
+           lambda: fn(ctypes.byref(desc), view(x), view(dout), _p(G), _stream()), "dc_conv_wgrad_" + impl)
     return G
 
 
 # ---- depthwise ----------------------------------------------------------------------------------------
 def dw_fwd(x, w9c, stride, dil, out):
     _require_cuda(x, w9c, out)
-    check(_lib.load().dc_dw_fwd(view(x), _p(w9c), stride, dil, view(out), _stream()), "dc_dw_fwd")
+    _timed("dw_fwd", 18.0 * out.numel(), _nbytes(x, out),
+           lambda: _lib.load().dc_dw_fwd(view(x), _p(w9c), stride, dil, view(out), _stream()), "dc_dw_fwd")
     return out
 
 
 def dw_bwd_data(dout, w9c, stride, dil, din, accumulate):
     _require_cuda(dout, w9c, din)
-    check(_lib.load().dc_dw_bwd_data(view(dout), _p(w9c), stride, dil, view(din), int(accumulate), _stream()), "dc_dw_bwd_data")
+    _timed("dw_bwd_data", 18.0 * dout.numel(), _nbytes(dout, din) * (1.0 if not accumulate else 1.0) + (_nbytes(din) if accumulate else 0.0),
+           lambda: _lib.load().dc_dw_bwd_data(view(dout), _p(w9c), stride, dil, view(din), int(accumulate), _stream()), "dc_dw_bwd_data")
     return din
 
 
 def dw_bwd_weight(x, dout, stride, dil, G9c):
     _require_cuda(x, dout, G9c)
     assert G9c.dtype == torch.float32
-    check(_lib.load().dc_dw_bwd_weight(view(x), view(dout), stride, dil, _p(G9c), _stream()), "dc_dw_bwd_weight")
+    _timed("dw_bwd_weight", 18.0 * dout.numel(), _nbytes(x, dout),
+           lambda: _lib.load().dc_dw_bwd_weight(view(x), view(dout), stride, dil, _p(G9c), _stream()), "dc_dw_bwd_weight")
     return G9c
 
 
@@ -147,7 +208,7 @@ def dw_bwd_weight(x, dout, stride, dil, G9c):
 def bn_stats(y, sums):
     _require_cuda(y, sums)
     assert sums.dtype == torch.float64 and sums.numel() == 2 * y.shape[3]
-    check(_lib.load().dc_bn_stats(view(y), _p(sums), _stream()), "dc_bn_stats")
+    _timed("bn_stats", 3.0 * y.numel(), _nbytes(y), lambda: _lib.load().dc_bn_stats(view(y), _p(sums), _stream()), "dc_bn_stats")
     return sums
 
 
@@ -167,21 +228,25 @@ def bn_params(gamma, beta, running_mean, running_var, sums, count, momentum, eps
 
 def bn_apply(params, y, residual, out):
     _require_cuda(y, residual, out)
-    check(_lib.load().dc_bn_apply(ctypes.byref(params), view(y), view(residual), view(out), _stream()), "dc_bn_apply")
+    _timed("bn_apply", 3.0 * y.numel(), _nbytes(y, residual, out),
+           lambda: _lib.load().dc_bn_apply(ctypes.byref(params), view(y), view(residual), view(out), _stream()), "dc_bn_apply")
     return out
 
 
 def bn_bwd_reduce(params, dout, out, y, rsums):
     _require_cuda(dout, rsums)
     assert rsums.dtype == torch.float64
-    check(_lib.load().dc_bn_bwd_reduce(ctypes.byref(params), view(dout), view(out), view(y), _p(rsums), _stream()), "dc_bn_bwd_reduce")
+    _timed("bn_bwd_reduce", 4.0 * dout.numel(), _nbytes(dout, out, y),
+           lambda: _lib.load().dc_bn_bwd_reduce(ctypes.byref(params), view(dout), view(out), view(y), _p(rsums), _stream()),
+           "dc_bn_bwd_reduce")
     return rsums
 
 
 def bn_bwd_apply(params, dout, out, y, rsums, dy, dres, dgamma, dbeta):
     _require_cuda(dout)
-    check(_lib.load().dc_bn_bwd_apply(ctypes.byref(params), view(dout), view(out), view(y), _p(rsums), view(dy), view(dres),
-                                      _p(dgamma), _p(dbeta), _stream()), "dc_bn_bwd_apply")
+    _timed("bn_bwd_apply", 8.0 * dout.numel(), _nbytes(dout, out, y, dy, dres),
+           lambda: _lib.load().dc_bn_bwd_apply(ctypes.byref(params), view(dout), view(out), view(y), _p(rsums), view(dy),
+                                               view(dres), _p(dgamma), _p(dbeta), _stream()), "dc_bn_bwd_apply")
 
 
 def channel_sum(x, ws, out_c):

@@ -1,0 +1,173 @@
+"""Data-parallel wrapper for the deepcam_b200 modules (the reference wraps its model at TR:227 with apex or torch
+DistributedDataParallel; SURVEY §2.3 collectives C1-C3).
+
+Semantics kept from torch DDP: parameters and buffers are broadcast from rank 0 at construction (C1), buffers
+(BatchNorm running statistics) are broadcast from rank 0 at every forward (C3, `broadcast_buffers=True`), and the
+gradients every rank sees after backward are the world average (C2).  BatchNorm statistics stay per rank (no
+SyncBN), as in the reference.
+
+B200-native mechanics: the engine writes all parameter gradients into ONE flat fp32 buffer (GradStore), so a
+bucket is a contiguous slice of it: no gather/scatter copies before the collective.  Buckets are all-reduced
+(NCCL AVG over NVLink/NVSwitch) on a dedicated communication stream as soon as the backward plan has launched
+the last gradient kernel of the bucket, overlapping with the remaining backward kernels.  BatchNorm buffers are
+re-homed into one flat tensor at wrap time, so the per-forward buffer broadcast is a single collective.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import ops
+
+
+class _GradSync:
+    def __init__(self, owner):
+        self.owner = owner
+        self.buckets = None          # list of (start, end, [param indices])
+        self.pending = None
+        self.works = []
+
+    # -- bucket layout (reverse parameter order ~ backward completion order) --
+    def _layout(self, grads):
+        cap = self.owner.bucket_cap_elems
+        buckets, cur, cur_end = [], [], None
+        n = len(grads.params)
+        for i in range(n - 1, -1, -1):
+            start = grads.offsets[i]
+            end = grads.offsets[i + 1] if i + 1 < n else grads.total
+            if cur and (cur_end - start) > cap:
+                buckets.append((cur_start, cur_end, cur))
+                cur = []
+            if not cur:
+                cur_end = end
+            cur.append(i)
+            cur_start = start
+        if cur:
+            buckets.append((cur_start, cur_end, cur))
+        self.buckets = buckets
+        self.bucket_of = {}
+        for b, (_, _, idxs) in enumerate(buckets):
+            for i in idxs:
+                self.bucket_of[i] = b
+
+    def begin(self, grads):
+        if self.buckets is None or self._total != grads.total:
+            self._total = grads.total
+            self._layout(grads)
+        self.flat = grads.flat
+        self.pending = []
+        for (_, _, idxs) in self.buckets:
+            self.pending.append(sum(1 for i in idxs if grads.params[i].requires_grad))
+        self.launched = [False] * len(self.buckets)
+        self.works = []
+        grads.on_ready = self._ready
+        self.next_bucket = 0
+
+    def _ready(self, i):
+        b = self.bucket_of[i]
+        self.pending[b] -= 1
+        # launch in order so every rank issues the collectives in the same sequence
+        while self.next_bucket < len(self.buckets) and self.pending[self.next_bucket] <= 0:
+            self._launch(self.next_bucket)
+            self.next_bucket += 1
+
+    def _launch(self, b):
+        if self.launched[b]:
+            return
+        self.launched[b] = True
+        start, end, _ = self.buckets[b]
+        self.owner._allreduce_slice(self.flat[start:end], self.works)
+
+    def finish(self, grads):
+        for b in range(len(self.buckets)):
+            self._launch(b)
+        self.owner._wait(self.works, self.flat)
+        grads.on_ready = None
+        self.works = []
+
+
+class DistributedDataParallel(nn.Module):
+    def __init__(self, module, device_ids=None, output_device=None, broadcast_buffers=True, bucket_cap_mb=25,
+                 process_group=None):
+        super().__init__()
+        if not dist.is_initialized():
+            raise RuntimeError("deepcam_b200.parallel.DistributedDataParallel needs torch.distributed to be initialised")
+        self.module = module
+        self.process_group = process_group
+        self.world_size = dist.get_world_size(process_group)
+        self.broadcast_buffers = broadcast_buffers
+        self.bucket_cap_elems = int(bucket_cap_mb * 1024 * 1024 // 4)
+        p0 = next(module.parameters())
+        self.on_cuda = p0.is_cuda
+        self.comm_stream = torch.cuda.Stream(device=p0.device) if self.on_cuda else None
+        self._flatten_buffers()
+        self._sync_module_states()
+        self._sync = _GradSync(self)
+        module._dc_grad_sync = self._sync if self.world_size > 1 else None
+
+    # -- C1: initial state broadcast --
+    def _sync_module_states(self):
+        if self.world_size == 1:
+            return
+        with torch.no_grad():
+            for p in self.module.parameters():
+                dist.broadcast(p.data, 0, group=self.process_group)
+            self._broadcast_buffers()
+
+    # -- C3: buffers live in two flat tensors (float statistics, int64 counters) --
+    def _flatten_buffers(self):
+        fl, it = [], []
+        for mod in self.module.modules():
+            for name, buf in mod._buffers.items():
+                if buf is None:
+                    continue
+                (fl if buf.is_floating_point() else it).append((mod, name, buf))
+        self._flat_buffers = []
+        for group in (fl, it):
+            if not group:
+                continue
+            dtype, device = group[0][2].dtype, group[0][2].device
+            total = sum(b.numel() for _, _, b in group)
+            flat = torch.empty(total, dtype=dtype, device=device)
+            off = 0
+            with torch.no_grad():
+                for mod, name, buf in group:
+                    n = buf.numel()
+                    view = flat[off:off + n].view(buf.shape)
+                    view.copy_(buf)
+                    mod._buffers[name] = view
+                    off += n
+            self._flat_buffers.append(flat)
+
+    def _broadcast_buffers(self):
+        for flat in self._flat_buffers:
+            dist.broadcast(flat, 0, group=self.process_group)
+
+    # -- C2: gradient buckets --
+    def _allreduce_slice(self, t, works):
+        if self.on_cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.process_group)
+                done = torch.cuda.Event()
+                done.record(self.comm_stream)
+            works.append(done)
+        else:
+            works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group, async_op=True))
+
+    def _wait(self, works, flat):
+        if self.on_cuda:
+            cur = torch.cuda.current_stream()
+            for ev in works:
+                cur.wait_event(ev)
+        else:
+            for w in works:
+                w.wait()
+            flat.mul_(1.0 / self.world_size)       # gloo has no AVG; CPU path exists only for the host-logic tests
+
+    def forward(self, *inputs, **kwargs):
+        if self.world_size > 1 and self.broadcast_buffers:
+            with torch.no_grad():
+                self._broadcast_buffers()
+        return self.module(*inputs, **kwargs)

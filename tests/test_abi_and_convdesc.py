@@ -1,0 +1,139 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol declared in include/deepcam_b200.h
+(no compute calls without a GPU), ctypes struct layouts match the header, and the tap tables of convdesc.py
+express Conv2d / ConvTranspose2d fprop, dgrad and wgrad correctly (emulated gather-GEMM vs torch.nn.functional)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from deepcam_b200 import _lib, convdesc
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(REPO, "include", "deepcam_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "missing export: " + n
+        assert n in _lib.SIGNATURES, "ctypes binding missing for " + n
+    assert set(_lib.SIGNATURES) == set(names)
+    assert lib.dc_abi_version() == 1
+    assert isinstance(lib.dc_last_error_string(), bytes)
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.dc_view) == 8 + 4 * 4 + 4 * 8 + 8
+    assert ctypes.sizeof(_lib.dc_conv_desc) == 4 * (1 + 3 * 9 + 4)
+    assert ctypes.sizeof(_lib.dc_bn_params) == 5 * 8 + 8 + 4 * 4
+    assert _lib.dc_view.sn.offset == 24 and _lib.dc_view.dtype.offset == 56
+
+
+def test_argument_validation_without_gpu():
+    """Invalid arguments are rejected on the host before any CUDA call; the error string names the problem."""
+    lib = _lib.load()
+    d = _lib.dc_conv_desc()
+    d.ntaps = 0
+    v = _lib.dc_view()
+    rc = lib.dc_conv_gemm_simt(ctypes.byref(d), v, None, None, v, None)
+    assert rc < 0
+    assert b"ntaps" in lib.dc_last_error_string()
+    rc = lib.dc_bn_stats(v, None, None)
+    assert rc < 0 and b"dc_bn_stats" in lib.dc_last_error_string()
+    rc = lib.dc_iou_counts(None, None, 0, 3, None, None)
+    assert rc < 0
+
+
+# ---- gather-GEMM emulation ------------------------------------------------------------------------
+def _gather(x, dh, dw, stride, ho, wo):
+    """x: [N,H,W,C] -> [N,ho,wo,C] with x[n, y*s+dh, x*s+dw] or zero outside."""
+    n, h, w, c = x.shape
+    out = torch.zeros(n, ho, wo, c, dtype=x.dtype)
+    for y in range(ho):
+        iy = y * stride + dh
+        if iy < 0 or iy >= h:
+            continue
+        for xx in range(wo):
+            ix = xx * stride + dw
+            if 0 <= ix < w:
+                out[:, y, xx] = x[:, iy, ix]
+    return out
+
+
+def emul_gemm(taps, stride, x, wslices, ho, wo):
+    """out[n,y,x,co] = sum_t gather_t(x)[..., ci] @ W[wt][ci][co]"""
+    out = 0
+    for dh, dw, wt in taps:
+        out = out + _gather(x, dh, dw, stride, ho, wo) @ wslices[wt]
+    return out
+
+
+def emul_wgrad(taps, stride, x, dout, ntaps):
+    """G[wt][co][ci] = sum_m gather_t(x)[m, ci] * dout[m, co]"""
+    n, ho, wo, co = dout.shape
+    G = torch.zeros(ntaps, co, x.shape[3], dtype=x.dtype)
+    for dh, dw, wt in taps:
+        g = _gather(x, dh, dw, stride, ho, wo)
+        G[wt] += dout.reshape(-1, co).t() @ g.reshape(-1, x.shape[3])
+    return G
+
+
+@pytest.mark.parametrize("k,stride,pad,dil", [(1, 1, 0, 1), (3, 1, 1, 1), (3, 1, 6, 6), (3, 2, 1, 1), (1, 2, 0, 1)])
+def test_conv2d_tap_tables(k, stride, pad, dil):
+    torch.manual_seed(0)
+    N, Ci, Co, H, W = 2, 5, 4, 9, 11
+    x = torch.randn(N, Ci, H, W, dtype=torch.double, requires_grad=True)
+    w = torch.randn(Co, Ci, k, k, dtype=torch.double, requires_grad=True)
+    y = F.conv2d(x, w, None, stride, pad, dil)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    ho, wo = y.shape[2:]
+    assert ho == convdesc.conv_out_size(H, k, stride, pad, dil)
+    xh, dyh = x.detach().permute(0, 2, 3, 1), dy.permute(0, 2, 3, 1)
+    wf = [w.detach()[:, :, t // k, t % k].t() for t in range(k * k)]          # [ci][co] per tap
+    out = emul_gemm(convdesc.conv_fprop_taps(k, pad, dil), stride, xh, wf, ho, wo)
+    assert torch.allclose(out, y.detach().permute(0, 2, 3, 1), atol=1e-10)
+    G = emul_wgrad(convdesc.conv_wgrad_taps(k, pad, dil), stride, xh, dyh, k * k)   # [tap][co][ci]
+    assert torch.allclose(G.permute(1, 2, 0).reshape(Co, Ci, k, k), w.grad, atol=1e-9)
+    if stride == 1:
+        wd = [w.detach()[:, :, t // k, t % k] for t in range(k * k)]           # [co][ci] per tap (k = co)
+        dx = emul_gemm(convdesc.conv_dgrad_taps(k, pad, dil), 1, dyh, wd, H, W)
+        assert torch.allclose(dx, x.grad.permute(0, 2, 3, 1), atol=1e-10)
+
+
+def test_conv_transpose_tap_tables():
+    torch.manual_seed(1)
+    N, Ci, Co, H, W = 2, 4, 3, 5, 6
+    x = torch.randn(N, Ci, H, W, dtype=torch.double, requires_grad=True)
+    w = torch.randn(Ci, Co, 3, 3, dtype=torch.double, requires_grad=True)
+    y = F.conv_transpose2d(x, w, None, 2, 1, 1)
+    assert y.shape[2:] == (2 * H, 2 * W)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xh, dyh = x.detach().permute(0, 2, 3, 1), dy.permute(0, 2, 3, 1)
+    wf = [w.detach()[:, :, t // 3, t % 3] for t in range(9)]                  # [ci][co]
+    out = torch.zeros(N, 2 * H, 2 * W, Co, dtype=torch.double)
+    ntaps = 0
+    for ph in range(2):
+        for pw in range(2):
+            taps = convdesc.convT_fprop_taps(3, 2, 1, ph, pw)
+            ntaps += len(taps)
+            out[:, ph::2, pw::2] = emul_gemm(taps, 1, xh, wf, H, W)
+    assert ntaps == 9
+    assert torch.allclose(out, y.detach().permute(0, 2, 3, 1), atol=1e-10)
+    wd = [w.detach()[:, :, t // 3, t % 3].t() for t in range(9)]              # [co][ci] (k = co_out)
+    dx = emul_gemm(convdesc.convT_dgrad_taps(3, 1), 2, dyh, wd, H, W)
+    assert torch.allclose(dx, x.grad.permute(0, 2, 3, 1), atol=1e-10)
+    # wgrad: gathered = dy (stride 2), enumerated = x  ->  G[tap][ci_in][co_out]
+    G = emul_wgrad(convdesc.convT_wgrad_taps(3, 1), 2, dyh, xh, 9)
+    assert torch.allclose(G.permute(1, 2, 0).reshape(Ci, Co, 3, 3), w.grad, atol=1e-9)
