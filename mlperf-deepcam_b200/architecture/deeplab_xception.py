@@ -338,9 +338,11 @@ class DeconvUpsampler(_EngineModule):
         y = eng.bn(eng.conv(y, _conv_spec(self.conv1[3])), _bn_spec(self.conv1[4]), relu=True)
         y = eng.conv(y, _conv_spec(self.conv1[6]))
         y = eng.bn(eng.conv(y, _conv_spec(self.deconv3[0])), _bn_spec(self.deconv3[1]), relu=True)
-        # logits stay fp32; channels padded to a multiple of 4 for the vectorised kernels
+        # logits stay fp32; channels padded for the vectorised kernels (8 in bf16 mode so that the logit gradient
+        # is a legal TMA operand: 16-byte pixel pitch)
         co = self.n_output
-        return eng.conv(y, _conv_spec(self.last_deconv[0]), out_c=(co + 3) // 4 * 4, out_dtype=torch.float32)
+        pad = 8 if y.t.dtype == torch.bfloat16 else 4
+        return eng.conv(y, _conv_spec(self.last_deconv[0]), out_c=(co + pad - 1) // pad * pad, out_dtype=torch.float32)
 
     def _emit_root(self, eng, x, low):
         out = self._emit(eng, x, low=low)

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_gemm_tc_kernel(const __grid_c
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
     tmem_relinquish();
   }
   if (warp == 0 && lane == 0) {
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_gemm_tc_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -594,7 +594,9 @@ int dc_conv_gemm_tc(const dc_conv_desc* d, dc_view in, const void* w, const floa
   const int mtiles = p.tiles_x * p.tiles_y * out.n;
   // N tile: prefer the widest tile that keeps >= ~1 wave of CTAs
   int BN = 256;
-  if (out.c <= 64) BN = 64;
+  if (out.c <= 16) BN = 16;
+  else if (out.c <= 32) BN = 32;
+  else if (out.c <= 64) BN = 64;
   else if (out.c <= 128) BN = 128;
   else if ((long long)mtiles * ceil_div(out.c, 256) < kNumSMs) BN = 128;
   if (int r = encode_weight_map(&maps.b, w, Ktot, out.c, BN, "dc_conv_gemm_tc")) return r;
@@ -602,7 +604,9 @@ int dc_conv_gemm_tc(const dc_conv_desc* d, dc_view in, const void* w, const floa
   const int ntiles = ceil_div(out.c, BN);
   if (BN == 256) return launch_fprop<256>(maps, p, mtiles, ntiles, st);
   if (BN == 128) return launch_fprop<128>(maps, p, mtiles, ntiles, st);
-  return launch_fprop<64>(maps, p, mtiles, ntiles, st);
+  if (BN == 64) return launch_fprop<64>(maps, p, mtiles, ntiles, st);
+  if (BN == 32) return launch_fprop<32>(maps, p, mtiles, ntiles, st);
+  return launch_fprop<16>(maps, p, mtiles, ntiles, st);
 }
 
 int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, void* stream) {

@@ -144,13 +144,13 @@ class CudaBackend:
         if not self.use_tc or gathered.dtype != torch.bfloat16:
             return False
         c = gathered.shape[3]
-        if c % 8 or c < 32 or other_c < 16:
+        if c % 8 or c < 8 or other_c < 1:
             return False
         if gathered.stride(3) != 1 or any(s % 8 for s in gathered.stride()[:3]) or gathered.data_ptr() % 16:
             return False
         return gathered.shape[0] * gathered.shape[1] * gathered.shape[2] >= 128
 
-    def _packed(self, spec, role, impl, x):
+    def _packed(self, spec, role, impl, x, n_pad=None):
         """role: 'fprop' (k = op input channels) or 'dgrad' (k = op output channels); x = gathered operand."""
         w = spec.weight
         taps = spec.k * spec.k
@@ -161,7 +161,7 @@ class CudaBackend:
             K, N = spec.co, spec.ci
             src_k_first = not spec.transposed      # Conv weight is [co][ci][taps] = [k][n]
         if impl == "tc":
-            layout, K_pad, N_pad, dt = DC_PACK_NTK, _round_up(K, 64), N, torch.bfloat16
+            layout, K_pad, N_pad, dt = DC_PACK_NTK, _round_up(K, 64), max(N, n_pad or 0), torch.bfloat16
         else:
             layout, K_pad, N_pad, dt = DC_PACK_TKN, x.shape[3], _round_up(N, 4), x.dtype
 
@@ -169,7 +169,7 @@ class CudaBackend:
             self.launches += 1
             return ops.pack_weight(w.detach(), K, N, taps, src_k_first, layout, K_pad, N_pad, dt)
 
-        return _cached(spec, (role, impl, dt, K_pad), w, make)
+        return _cached(spec, (role, impl, dt, K_pad, N_pad), w, make)
 
     def _gemm(self, taps, stride, accumulate, wtaps, x, w, bias, out, impl):
         desc = ops.make_desc(taps, (stride, stride), accumulate, wtaps)
@@ -179,8 +179,8 @@ class CudaBackend:
     # ---- dense convolution ---------------------------------------------------------------------------------
     def conv_fwd(self, x, spec, out):
         """out <- conv(x) (+ bias).  `out` is a preallocated logical-NHWC tensor (possibly a channel slice)."""
-        impl = "tc" if self._tc_ok(x, spec.co) and out.shape[3] == spec.co else "simt"
-        w = self._packed(spec, "fprop", impl, x)
+        impl = "tc" if self._tc_ok(x, spec.co) else "simt"
+        w = self._packed(spec, "fprop", impl, x, n_pad=out.shape[3])
         bias = spec.bias.detach() if spec.bias is not None else None
         kk = spec.k * spec.k
         if not spec.transposed:

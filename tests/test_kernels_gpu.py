@@ -339,7 +339,7 @@ def test_conv_transpose_simt(dtype, Ci, Co, H, W, co_pad):
         assert v < TOL[dtype], (k, v, res)
 
 
-@pytest.mark.parametrize("case", CONV_CASES[1:], ids=[c[0] for c in CONV_CASES[1:]])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv_tcgen05(case):
     torch.manual_seed(8)
     be = backend(torch.bfloat16, use_tc=True)
@@ -352,6 +352,15 @@ def test_conv_transpose_tcgen05():
     torch.manual_seed(9)
     be = backend(torch.bfloat16, use_tc=True)
     res = _conv_case(be, torch.bfloat16, 256, 256, 3, 2, 1, 1, 12, 18, False, transposed=True)
+    for k, v in res.items():
+        assert v < TOL[torch.bfloat16], (k, v, res)
+
+
+def test_conv_transpose_tcgen05_three_logit_channels():
+    """last_deconv (256 -> 3, DX:374): output padded to 8 channels, N tile of 16, logit gradient as a TMA operand."""
+    torch.manual_seed(12)
+    be = backend(torch.bfloat16, use_tc=True)
+    res = _conv_case(be, torch.bfloat16, 256, 3, 3, 2, 1, 1, 24, 36, False, transposed=True, co_pad=8)
     for k, v in res.items():
         assert v < TOL[torch.bfloat16], (k, v, res)
 
