@@ -151,21 +151,24 @@ struct TcFpropParams {
 constexpr int kTcThreads = 192;
 constexpr int kABytes = 128 * 128;   // 128 rows x 64 bf16
 
-template <int BN> struct FpropCfg {
-  static constexpr int kBBytes = BN * 128;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+// Runtime tile configuration of the fprop-like kernel.
+struct TcFpropCfg {
+  int BN;            // N tile (multiple of 16, 16..256) = UMMA N
+  int stages;        // smem pipeline depth
+  int stage_bytes;   // 16384 (A) + BN*128 (B); multiple of 1024
+  int tmem_cols;     // power of two >= max(32, BN)
+  int smem_bytes;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kTcThreads) conv_gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcFpropParams p) {
-  using Cfg = FpropCfg<BN>;
-  constexpr int STAGES = Cfg::kStages;
+__global__ void __launch_bounds__(kTcThreads) conv_gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcFpropParams p,
+                                                                  const TcFpropCfg cfg) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int STAGES = cfg.stages;
+  const int BN = cfg.BN;
+  const uint32_t bar_base = smem_base + STAGES * cfg.stage_bytes;
   // barriers: full[STAGES], empty[STAGES], tmem_full, then tmem base pointer slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -189,12 +192,12 @@ __global__ void __launch_bounds__(kTcThreads) conv_gemm_tc_kernel(const __grid_c
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+    tmem_alloc(tmem_slot, cfg.tmem_cols);
     tmem_relinquish();
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.b);
-    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.a[p.map_id[0]]);
   }
   tc_fence_before();
   __syncthreads();
@@ -213,8 +216,8 @@ __global__ void __launch_bounds__(kTcThreads) conv_gemm_tc_kernel(const __grid_c
         const int kb0 = p.wt[t] * p.kblocks;
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
-          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+          mbar_expect_tx(full_bar(s), cfg.stage_bytes);
+          const uint32_t sa = smem_base + s * cfg.stage_bytes;
           tma_load_4d(am, full_bar(s), sa, kb * 64, bx, by, img);
           tma_load_2d(&maps.b, full_bar(s), sa + kABytes, (kb0 + kb) * 64, n0);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -223,12 +226,12 @@ __global__ void __launch_bounds__(kTcThreads) conv_gemm_tc_kernel(const __grid_c
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+      const uint32_t idesc = make_idesc(128, BN, 0, 0);
       int s = 0; uint32_t ph = 0;
       for (int it = 0; it < total_k; ++it) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        const uint32_t sa = smem_base + s * cfg.stage_bytes;
         const uint64_t da = make_smem_desc(sa, 16, 1024);
         const uint64_t db = make_smem_desc(sa + kABytes, 16, 1024);
 #pragma unroll
@@ -243,67 +246,115 @@ __global__ void __launch_bounds__(kTcThreads) conv_gemm_tc_kernel(const __grid_c
     }
   } else {
     // ---- epilogue: warps 2..5; warp w may only touch TMEM lanes 32*(w%4) .. +31 ----
+    // Phase 1: TMEM -> registers -> (+bias) -> per-warp staging rows in shared memory (the pipeline stages are
+    //          free once tmem_full has fired).  Phase 2: lanes walk along the channels of one pixel row at a time,
+    //          so every global store / load-add-store instruction covers one contiguous run of the output row.
     const int lg = warp & 3;
     const int row = lg * 32 + lane;             // row of the 128 x BN accumulator = pixel of the tile
     const int ty = row / p.TW, tx = row - ty * p.TW;
     const int oy = y0 + ty, ox = x0 + tx;
     const bool pix_ok = (oy < p.out.h) && (ox < p.out.w);
     const long long base = (long long)img * p.out.sn + (long long)oy * p.out.sh + (long long)ox * p.out.sw;
+    const int ncols = min(BN, p.out.c - n0);    // valid columns of this tile
+    const bool stage_f32 = (p.accumulate != 0) || (p.out.dtype == DC_F32);
+    const int es = stage_f32 ? 4 : 2;
+    // bytes per staged row: whole 32-column chunks; (pitch/16) is odd -> conflict-free 16-byte row accesses
+    const int pitch = ((BN + 31) & ~31) * es + 16;
+    uint8_t* stg = smem_gen + (size_t)lg * 32 * pitch;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const bool fast = p.out_vec_ok != 0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= p.out.c) break;            // warp-uniform
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
-      if (!pix_ok) continue;
-      const int co0 = n0 + c0;
-      if (fast && co0 + 32 <= p.out.c) {
-        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out.p) + base + co0;
-        uint4* op4 = reinterpret_cast<uint4*>(op);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < ncols) v[j] = __float_as_uint(__uint_as_float(v[j]) + p.bias[n0 + c0 + j]);
+      }
+      uint8_t* rp = stg + (size_t)lane * pitch + (size_t)c0 * es;
+      if (stage_f32) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(rp + q * 16) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            f[j] = __uint_as_float(v[q * 8 + j]);
-            if (p.bias) f[j] += p.bias[co0 + q * 8 + j];
-          }
-          if (p.accumulate) {
-            uint4 o = op4[q];
-            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              f[2 * j] += __uint_as_float(ow[j] << 16);
-              f[2 * j + 1] += __uint_as_float(ow[j] & 0xffff0000u);
-            }
-          }
           uint4 r;
-          __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]);
-          __nv_bfloat162 b1 = __floats2bfloat162_rn(f[2], f[3]);
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(f[4], f[5]);
-          __nv_bfloat162 b3 = __floats2bfloat162_rn(f[6], f[7]);
+          __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+          __nv_bfloat162 b1 = __floats2bfloat162_rn(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+          __nv_bfloat162 b3 = __floats2bfloat162_rn(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
           r.x = *reinterpret_cast<uint32_t*>(&b0); r.y = *reinterpret_cast<uint32_t*>(&b1);
           r.z = *reinterpret_cast<uint32_t*>(&b2); r.w = *reinterpret_cast<uint32_t*>(&b3);
-          op4[q] = r;
+          *reinterpret_cast<uint4*>(rp + q * 16) = r;
         }
-      } else {
-        for (int j = 0; j < 32; ++j) {
-          const int co = co0 + j;
-          if (co >= p.out.c) break;
-          float f = __uint_as_float(v[j]);
-          if (p.bias) f += p.bias[co];
-          const long long off = base + (long long)co * p.out.sc;
-          if (p.out.dtype == DC_F32) {
-            float* q = reinterpret_cast<float*>(p.out.p) + off;
-            if (p.accumulate) f += *q;
-            *q = f;
-          } else {
-            __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p.out.p) + off;
-            if (p.accumulate) f += __bfloat162float(*q);
-            *q = __float2bfloat16_rn(f);
+      }
+    }
+    __syncwarp();
+    const unsigned okmask = __ballot_sync(0xffffffffu, pix_ok);
+    const int V = stage_f32 ? 4 : 8;            // staged elements per 16-byte lane access
+    // lanes_per_row lanes walk along the channels of one pixel row; 32/lanes_per_row rows per warp instruction
+    int lpr = 1;
+    while (lpr < 32 && lpr * V < ncols) lpr <<= 1;
+    const int rpi = 32 / lpr;
+    const int my_sub = lane / lpr, my_l = lane - my_sub * lpr;
+    const bool raw_copy = !stage_f32 && p.out_vec_ok;     // bf16 staged, bf16 vector output: move 16 bytes as they are
+#pragma unroll 2
+    for (int r0 = 0; r0 < 32; r0 += rpi) {
+      const int r = r0 + my_sub;
+      const long long rbase = __shfl_sync(0xffffffffu, base, r);
+      const bool ok = (okmask >> r) & 1u;
+      const uint8_t* rp = stg + (size_t)r * pitch;
+      for (int col = my_l * V; col < ncols; col += lpr * V) {
+        if (!ok) continue;
+        const int co = n0 + col;
+        if (raw_copy && col + 8 <= ncols) {
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out.p) + rbase + co) =
+              *reinterpret_cast<const uint4*>(rp + (size_t)col * 2);
+          continue;
+        }
+        float f[8];
+        if (stage_f32) {
+          const float4 t = *reinterpret_cast<const float4*>(rp + (size_t)col * 4);
+          f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+        } else {
+          const uint4 t = *reinterpret_cast<const uint4*>(rp + (size_t)col * 2);
+          const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { f[2 * j] = __uint_as_float(w4[j] << 16); f[2 * j + 1] = __uint_as_float(w4[j] & 0xffff0000u); }
+        }
+        if (stage_f32 && p.out_vec_ok && col + 4 <= ncols) {
+          // accumulate into a bf16 row: staged fp32, 4 channels (8 bytes of output) per lane
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out.p) + rbase + co;
+          if (p.accumulate) {
+            const uint2 old = *reinterpret_cast<const uint2*>(op);
+            f[0] += __uint_as_float(old.x << 16); f[1] += __uint_as_float(old.x & 0xffff0000u);
+            f[2] += __uint_as_float(old.y << 16); f[3] += __uint_as_float(old.y & 0xffff0000u);
+          }
+          __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]), b1 = __floats2bfloat162_rn(f[2], f[3]);
+          uint2 o;
+          o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+          *reinterpret_cast<uint2*>(op) = o;
+        } else if (p.out.dtype == DC_F32 && p.out.sc == 1 && col + 4 <= ncols && ((rbase + co) & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(p.out.p) & 15) == 0)) {
+          float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out.p) + rbase + co);
+          float4 o = make_float4(f[0], f[1], f[2], f[3]);
+          if (p.accumulate) { const float4 old = *q; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+          *q = o;
+        } else {
+          for (int j = 0; j < V && col + j < ncols; ++j) {
+            const long long off = rbase + (long long)(co + j) * p.out.sc;
+            float val = f[j];
+            if (p.out.dtype == DC_F32) {
+              float* q = reinterpret_cast<float*>(p.out.p) + off;
+              if (p.accumulate) val += *q;
+              *q = val;
+            } else {
+              __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p.out.p) + off;
+              if (p.accumulate) val += __bfloat162float(*q);
+              *q = __float2bfloat16_rn(val);
+            }
           }
         }
       }
@@ -311,8 +362,9 @@ __global__ void __launch_bounds__(kTcThreads) conv_gemm_tc_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+  if (warp == 1) tmem_dealloc(tmem_base, cfg.tmem_cols);
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // wgrad: D[co (128)][ci (BNW)] += sum over pixel tiles of dY^T X_t ; MN-major operands.
@@ -545,13 +597,46 @@ static int build_gather(const char* what, const dc_conv_desc* d, const dc_view& 
   return 0;
 }
 
-template <int BN>
-static int launch_fprop(const TcMaps& maps, const TcFpropParams& p, int mtiles, int ntiles, cudaStream_t st) {
-  using Cfg = FpropCfg<BN>;
-  cudaError_t attr_err = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-  if (attr_err != cudaSuccess) return fail((int)attr_err, "dc_conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+static inline int round_up_i(int a, int b) { return (a + b - 1) / b * b; }
+
+// Tile configuration: the widest N tile that still gives every SM a CTA (the kernel is L2-bandwidth bound, so
+// wide tiles minimise operand re-reads), then as many pipeline stages as fit (two CTAs per SM when possible so
+// that one CTA's epilogue overlaps the other's main loop).
+static TcFpropCfg pick_fprop_cfg(int mtiles, int Co) {
+  TcFpropCfg c;
+  int BN = std::min(256, round_up_i(Co, 16));
+  int ntiles = ceil_div(Co, BN);
+  while ((long long)mtiles * ntiles < kNumSMs && BN > 64) {
+    ++ntiles;
+    int nb = round_up_i(ceil_div(Co, ntiles), 16);
+    if (nb >= BN) nb = BN - 16;
+    BN = std::max(nb, 64);
+    ntiles = ceil_div(Co, BN);
+  }
+  c.BN = BN;
+  c.stage_bytes = kABytes + BN * 128;
+  const int two_cta_budget = 110 * 1024, one_cta_budget = 200 * 1024;
+  if (3 * c.stage_bytes <= two_cta_budget) c.stages = std::min(6, two_cta_budget / c.stage_bytes);
+  else c.stages = std::max(2, std::min(6, one_cta_budget / c.stage_bytes));
+  const int staging = 4 * 32 * (round_up_i(BN, 32) * 4 + 16);
+  while (c.stages * c.stage_bytes < staging) ++c.stages;
+  c.tmem_cols = 32;
+  while (c.tmem_cols < BN) c.tmem_cols <<= 1;
+  c.smem_bytes = c.stages * c.stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  return c;
+}
+
+static int launch_fprop(const TcMaps& maps, const TcFpropParams& p, const TcFpropCfg& cfg, int mtiles, int ntiles, cudaStream_t st) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail((int)e, "dc_conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
   dim3 grid(mtiles, ntiles, 1);
-  conv_gemm_tc_kernel<BN><<<grid, kTcThreads, Cfg::kSmem, st>>>(maps, p);
+  conv_gemm_tc_kernel<<<grid, kTcThreads, cfg.smem_bytes, st>>>(maps, p, cfg);
   return launch_status("dc_conv_gemm_tc");
 }
 
@@ -592,21 +677,9 @@ int dc_conv_gemm_tc(const dc_conv_desc* d, dc_view in, const void* w, const floa
   if (int r = build_gather("dc_conv_gemm_tc", d, in, p.TH, p.TW, maps, p)) return r;
   const long long Ktot = (long long)d->wtaps * p.kblocks * 64;
   const int mtiles = p.tiles_x * p.tiles_y * out.n;
-  // N tile: prefer the widest tile that keeps >= ~1 wave of CTAs
-  int BN = 256;
-  if (out.c <= 16) BN = 16;
-  else if (out.c <= 32) BN = 32;
-  else if (out.c <= 64) BN = 64;
-  else if (out.c <= 128) BN = 128;
-  else if ((long long)mtiles * ceil_div(out.c, 256) < kNumSMs) BN = 128;
-  if (int r = encode_weight_map(&maps.b, w, Ktot, out.c, BN, "dc_conv_gemm_tc")) return r;
-  cudaStream_t st = as_stream(stream);
-  const int ntiles = ceil_div(out.c, BN);
-  if (BN == 256) return launch_fprop<256>(maps, p, mtiles, ntiles, st);
-  if (BN == 128) return launch_fprop<128>(maps, p, mtiles, ntiles, st);
-  if (BN == 64) return launch_fprop<64>(maps, p, mtiles, ntiles, st);
-  if (BN == 32) return launch_fprop<32>(maps, p, mtiles, ntiles, st);
-  return launch_fprop<16>(maps, p, mtiles, ntiles, st);
+  const TcFpropCfg cfg = pick_fprop_cfg(mtiles, out.c);
+  if (int r = encode_weight_map(&maps.b, w, Ktot, out.c, cfg.BN, "dc_conv_gemm_tc")) return r;
+  return launch_fprop(maps, p, cfg, mtiles, ceil_div(out.c, cfg.BN), as_stream(stream));
 }
 
 int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, void* stream) {

@@ -63,16 +63,29 @@ class Profiler:
         e.record()
         return e
 
-    def end(self, name, start, flops, nbytes):
+    def end(self, name, start, flops, nbytes, tag=""):
         e = torch.cuda.Event(enable_timing=True)
         e.record()
-        self.items.append((name, start, e, flops, nbytes))
+        self.items.append((name, start, e, flops, nbytes, tag))
 
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for name, s, e, fl, nb in self.items:
+        for name, s, e, fl, nb, _tag in self.items:
             d = out.setdefault(name, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["launches"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["flops"] += fl
+            d["bytes"] += nb
+        return out
+
+    def by_tag(self, kinds):
+        """Per-shape breakdown for the given kernel classes (call after summary(), which synchronises)."""
+        out = {}
+        for name, s, e, fl, nb, tag in self.items:
+            if name not in kinds:
+                continue
+            d = out.setdefault(name + " " + tag, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
             d["launches"] += 1
             d["ms"] += s.elapsed_time(e)
             d["flops"] += fl
@@ -92,13 +105,13 @@ def _nbytes(*ts):
     return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
 
 
-def _timed(name, flops, nbytes, rc_fn, what):
+def _timed(name, flops, nbytes, rc_fn, what, tag=""):
     if _prof is None:
         check(rc_fn(), what)
         return
     st = _prof.begin()
     check(rc_fn(), what)
-    _prof.end(name, st, flops, nbytes)
+    _prof.end(name, st, flops, nbytes, tag)
 
 
 # ---- descriptors ---------------------------------------------------------------------------------
@@ -164,7 +177,8 @@ def conv_gemm(desc, x, w, bias, out, impl):
     flops = 2.0 * m * out.shape[3] * x.shape[3] * desc.ntaps
     nbytes = _nbytes(x, out) + desc.ntaps * x.shape[3] * out.shape[3] * x.element_size()
     _timed("conv_gemm_" + impl, flops, nbytes,
-           lambda: fn(ctypes.byref(desc), view(x), _p(w), _p(bias), view(out), _stream()), "dc_conv_gemm_" + impl)
+           lambda: fn(ctypes.byref(desc), view(x), _p(w), _p(bias), view(out), _stream()), "dc_conv_gemm_" + impl,
+           tag="M%d Ci%d Co%d taps%d s%d" % (m, x.shape[3], out.shape[3], desc.ntaps, desc.stride_h))
     return out
 
 
@@ -177,7 +191,8 @@ def conv_wgrad(desc, x, dout, G, impl):
     flops = 2.0 * m * dout.shape[3] * x.shape[3] * desc.ntaps
     nbytes = _nbytes(x, dout) + 4.0 * desc.ntaps * x.shape[3] * dout.shape[3]
     _timed("conv_wgrad_" + impl, flops, nbytes,
-           lambda: fn(ctypes.byref(desc), view(x), view(dout), _p(G), _stream()), "dc_conv_wgrad_" + impl)
+           lambda: fn(ctypes.byref(desc), view(x), view(dout), _p(G), _stream()), "dc_conv_wgrad_" + impl,
+           tag="M%d Ci%d Co%d taps%d s%d" % (m, x.shape[3], dout.shape[3], desc.ntaps, desc.stride_h))
     return G
 
 
