@@ -280,10 +280,11 @@ def run_ours(args):
                 table[k] = dict(launches_per_step=v["launches"] / psteps, ms_per_step=v["ms"] / psteps,
                                 tflops=v["flops"] / s / 1e12 if s > 0 else 0.0, gbs=v["bytes"] / s / 1e9 if s > 0 else 0.0)
             shapes = {}
-            for k, v in sorted(prof.by_tag(tensor_kinds).items(), key=lambda kv: -kv[1]["ms"]):
+            for k, v in sorted(prof.by_tag(set(classes)).items(), key=lambda kv: -kv[1]["ms"]):
                 s = v["ms"] / 1000.0
                 shapes[k] = dict(launches_per_step=v["launches"] / psteps, ms_per_step=v["ms"] / psteps,
-                                 us_per_launch=1000.0 * v["ms"] / v["launches"], tflops=v["flops"] / s / 1e12 if s > 0 else 0.0)
+                                 us_per_launch=1000.0 * v["ms"] / v["launches"], tflops=v["flops"] / s / 1e12 if s > 0 else 0.0,
+                                 gbs=v["bytes"] / s / 1e9 if s > 0 else 0.0)
             with open(os.path.join(out_dir, "bench_kernel_classes.json"), "w") as fh:
                 json.dump(dict(ms_per_step_timed=ms / args.steps, classes=table, conv_shapes=shapes, peaks=peaks), fh, indent=1)
         except Exception:

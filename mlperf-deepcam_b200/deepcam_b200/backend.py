@@ -67,11 +67,17 @@ class BnSpec:
 _COUNTER_TABLES = {}      # tuple of counter addresses -> device table (built once per module instance)
 
 
-def _cached(spec, key, param, make):
+def _cached(spec, key, param, make, always=False):
+    """Kernel-layout copy of a parameter.  The buffer is allocated once and re-packed IN PLACE whenever the master
+    parameter changed, so its address stays valid for captured CUDA graphs; `always` (graph capture) re-packs
+    unconditionally because the pack kernel becomes part of the replayed graph."""
     ver = (param._version, param.data_ptr())
     ent = spec._cache.get(key)
-    if ent is None or ent[0] != ver:
-        ent = (ver, make())
+    if ent is None or ent[1].device != param.device:
+        ent = (ver, make(None))
+        spec._cache[key] = ent
+    elif always or ent[0] != ver:
+        ent = (ver, make(ent[1]))
         spec._cache[key] = ent
     return ent[1]
 
@@ -88,6 +94,8 @@ class CudaBackend:
             use_tc = dtype == torch.bfloat16 and ops._lib.load().dc_device_supports_tcgen05() == 1
         self.use_tc = bool(use_tc)
         self.launches = 0
+        self.graph_mode = False       # True while the owning plan captures CUDA graphs (engine._GraphPlan)
+        self.bwd_phase = False
 
     # ---- memory -----------------------------------------------------------------------------------
     def empty(self, n, h, w, c, dtype=None):
@@ -165,11 +173,11 @@ class CudaBackend:
         else:
             layout, K_pad, N_pad, dt = DC_PACK_TKN, x.shape[3], _round_up(N, 4), x.dtype
 
-        def make():
+        def make(out):
             self.launches += 1
-            return ops.pack_weight(w.detach(), K, N, taps, src_k_first, layout, K_pad, N_pad, dt)
+            return ops.pack_weight(w.detach(), K, N, taps, src_k_first, layout, K_pad, N_pad, dt, out=out)
 
-        return _cached(spec, (role, impl, dt, K_pad, N_pad), w, make)
+        return _cached(spec, (role, impl, dt, K_pad, N_pad), w, make, always=self.graph_mode)
 
     def _gemm(self, taps, stride, accumulate, wtaps, x, w, bias, out, impl):
         desc = ops.make_desc(taps, (stride, stride), accumulate, wtaps)
@@ -258,10 +266,11 @@ class CudaBackend:
 
     # ---- depthwise ---------------------------------------------------------------------------------------------
     def _dw_packed(self, spec):
-        def make():
+        def make(out):
             self.launches += 1
-            return ops.pack_weight(spec.weight.detach(), 1, spec.c, 9, False, DC_PACK_TKN, 1, spec.c, self.dtype)
-        return _cached(spec, ("dw", self.dtype), spec.weight, make)
+            return ops.pack_weight(spec.weight.detach(), 1, spec.c, 9, False, DC_PACK_TKN, 1, spec.c, self.dtype, out=out)
+        # the backward graph reuses the copy packed by the forward graph of the same step
+        return _cached(spec, ("dw", self.dtype), spec.weight, make, always=self.graph_mode and not self.bwd_phase)
 
     def dw_fwd(self, x, spec, out):
         ops.dw_fwd(x, self._dw_packed(spec), spec.stride, spec.dil, out)

@@ -357,6 +357,208 @@ class _PlanFunction(torch.autograd.Function):
         return (None, None, None, None) + tuple(dxs) + grads
 
 
+# ------------------------------------------------------------------------------------------------------------
+# CUDA-graph plans: the whole forward (and backward) of one module call is captured once per configuration and
+# replayed afterwards, so the ~1000 kernel launches of a step cost one cudaGraphLaunch each way on the host.
+# ------------------------------------------------------------------------------------------------------------
+def graphs_enabled():
+    return os.environ.get("DEEPCAM_B200_GRAPHS", "1") not in ("0", "false", "False", "")
+
+
+class _GraphPlan:
+    """Static buffers + captured graphs of one (module, input shapes, mode) configuration.
+
+    Activations, gradient buffers and BatchNorm scratch live in the plan's private memory pool at fixed addresses;
+    the user's input is copied into a static NHWC buffer before the forward graph is replayed and the outputs are
+    converted into fresh NCHW tensors after it.  One forward may be in flight per plan: backward must consume the
+    most recent forward (checked through a generation counter)."""
+
+    def __init__(self, module, precision, device, inputs, params, need_grad):
+        from . import _lib
+        self._lib = _lib
+        self.module = module
+        self.device = device
+        self.need_grad = need_grad
+        self.be = CudaBackend(_PRECISIONS[precision], device)
+        self.be.graph_mode = True
+        self.pool = torch.cuda.graph_pool_handle()
+        self.params = list(params)
+        self.guard = _pointer_guard(module, self.params)
+        self.grads = GradStore(self.params, device) if need_grad else None
+        self.eng = Engine(self.be, need_grad, self.grads)
+        self.xin = []
+        for x in inputs:
+            n, c, h, w = x.shape
+            self.xin.append(Act(self.be.empty(n, h, w, c), needs_grad=bool(x.requires_grad and need_grad)))
+        self.in_dtypes = [x.dtype for x in inputs]
+        self.generation = 0
+        self.fwd_graph = None
+        self.bwd_segments = None
+        self.fwd_kernels = self.bwd_kernels = 0
+        self.outs = None
+
+    # ---- forward ------------------------------------------------------------------------------------------
+    def _load_inputs(self, inputs):
+        for x, act in zip(inputs, self.xin):
+            src = x.detach()
+            if src.dtype not in (torch.float32, torch.bfloat16):
+                src = src.float()
+            ops_copy_view(src.permute(0, 2, 3, 1), act.t)
+
+    def forward(self, inputs):
+        self._load_inputs(inputs)
+        if self.fwd_graph is None:
+            g = torch.cuda.CUDAGraph()
+            l0 = self._lib.launch_count
+            with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
+                self.outs = self.module._emit_root(self.eng, *self.xin)
+                self.eng.finish_forward()
+            self.fwd_kernels = self._lib.launch_count - l0
+            self.fwd_graph = g
+        else:
+            self._lib.launch_count += self.fwd_kernels
+        self.fwd_graph.replay()
+        self.generation += 1
+        self.module._dc_last_launches = self.fwd_kernels + len(self.xin) + len(self.outs)
+        return tuple(self.be.to_nchw_f32(act.t, c) for act, c in self.outs)
+
+    # ---- backward -----------------------------------------------------------------------------------------
+    def backward(self, gouts):
+        be, eng, grads = self.be, self.eng, self.grads
+        sync = getattr(self.module, "_dc_grad_sync", None)
+        first = self.bwd_segments is None
+        if first:
+            flat = grads.begin_backward()
+            for (act, c), g in zip(self.outs, gouts):
+                if g is not None:
+                    n, h, w, cp = act.t.shape
+                    act.grad = be.empty(n, h, w, cp)          # backend dtype, like from_nchw in the eager path
+            self.gout_used = [g is not None for g in gouts]
+        elif [g is not None for g in gouts] != self.gout_used:
+            raise RuntimeError("deepcam_b200: the set of outputs receiving gradients changed between backward calls of a "
+                               "captured plan; set DEEPCAM_B200_GRAPHS=0 for this usage")
+        for (act, c), g in zip(self.outs, gouts):
+            if g is not None:
+                ops_copy_view(g.detach().permute(0, 2, 3, 1), act.grad)        # pad channels are zero-filled
+        if sync is not None:
+            sync.begin(grads)
+        if first:
+            be.bwd_phase = True
+            tape = list(reversed(eng.tape))
+            eng.tape = []
+            segments = []
+            l0 = self._lib.launch_count
+            i = 0
+            while i < len(tape) or not segments:
+                g = torch.cuda.CUDAGraph()
+                if sync is not None:
+                    sync.deferred = []
+                with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
+                    if i == 0:
+                        be.fill_zero_flat(grads.flat)
+                    while i < len(tape):
+                        tape[i]()
+                        i += 1
+                        if sync is not None and sync.deferred:
+                            break
+                buckets = []
+                if sync is not None:
+                    buckets, sync.deferred = sync.deferred, None
+                segments.append((g, buckets))
+                g.replay()
+                for b in buckets:
+                    sync.launch_bucket(b)
+            self.bwd_kernels = self._lib.launch_count - l0
+            self.bwd_segments = segments
+        else:
+            self._lib.launch_count += self.bwd_kernels
+            for g, buckets in self.bwd_segments:
+                g.replay()
+                for b in buckets:
+                    sync.launch_bucket(b)
+        if sync is not None:
+            sync.finish(grads)
+        dxs = []
+        for xa, dt in zip(self.xin, self.in_dtypes):
+            if xa.needs_grad and xa.grad is not None:
+                dxs.append(be.to_nchw_f32(xa.grad, xa.t.shape[3]).to(dt))
+            else:
+                dxs.append(None)
+        self.module._dc_last_launches_bwd = self.bwd_kernels
+        # parameter gradients: views of the static flat buffer; if the caller still holds such views as .grad
+        # (gradient accumulation) autograd would add the buffer to itself, so hand out copies in that case
+        flat = grads.flat
+        lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+        held = any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in self.params)
+        views = grads.take_views()
+        if held:
+            views = tuple(v.clone() if v is not None else None for v in views)
+        return dxs, views
+
+
+def ops_copy_view(src, dst):
+    from . import ops
+    ops.copy_view(src, dst)
+
+
+def _bn_modules(module):
+    bns = module.__dict__.get("_dc_bn_list")
+    if bns is None:
+        bns = [m for m in module.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+        module.__dict__["_dc_bn_list"] = bns
+    return bns
+
+
+def _pointer_guard(module, params):
+    """Addresses baked into a captured graph: parameters and buffers must stay where they are."""
+    return tuple(p.data_ptr() for p in params) + tuple(b.data_ptr() for b in module.buffers())
+
+
+class _GraphFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, n_in, *tensors):
+        results = plan.forward(tensors[:n_in])
+        ctx.plan = plan
+        ctx.gen = plan.generation
+        return results
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        plan = ctx.plan
+        if not plan.need_grad:
+            raise RuntimeError("backward through a deepcam_b200 module that ran without gradient recording")
+        if ctx.gen != plan.generation:
+            raise RuntimeError("deepcam_b200: backward() must follow the forward() it belongs to when CUDA-graph plans "
+                               "are enabled (a newer forward of the same module has overwritten the saved activations); "
+                               "set DEEPCAM_B200_GRAPHS=0 to keep several forwards alive")
+        dxs, grads = plan.backward(gouts)
+        return (None, None) + tuple(dxs) + grads
+
+
+def _graph_plan(module, precision, inputs, params, need_grad):
+    """Returns the captured plan for this configuration, or None while it is still warming up (first call runs
+    eagerly: it fills the kernel-attribute / counter-table caches that must not be touched during capture)."""
+    device = inputs[0].device
+    if device.type != "cuda" or getattr(_state, "factory", None) is not None or not graphs_enabled():
+        return None
+    key = (precision, need_grad, tuple(tuple(x.shape) + (x.dtype, bool(x.requires_grad)) for x in inputs),
+           tuple(m.training for m in _bn_modules(module)), tuple(p.requires_grad for p in params), device.index,
+           torch.cuda.current_stream(device).cuda_stream)
+    plans = module.__dict__.setdefault("_dc_plans", {})
+    ent = plans.get(key)
+    if ent is None:
+        if len(plans) >= 8:
+            plans.clear()
+        plans[key] = [1, None]
+        return None
+    if ent[1] is None:
+        ent[1] = _GraphPlan(module, precision, device, inputs, params, need_grad)
+    elif ent[1].guard != _pointer_guard(module, params):
+        plans[key] = [1, None]            # parameters/buffers moved: run eagerly once, then capture again
+        return None
+    return ent[1]
+
+
 def run_module(module, inputs, precision=None):
     """Execute `module` (any class of architecture/deeplab_xception.py) on NCHW inputs through the engine.
     Returns the tuple of NCHW fp32 outputs."""
@@ -368,4 +570,7 @@ def run_module(module, inputs, precision=None):
         raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
     params = list(module.parameters())
     need_grad = torch.is_grad_enabled() and (any(x.requires_grad for x in inputs) or any(p.requires_grad for p in params))
+    plan = _graph_plan(module, precision, inputs, params, need_grad)
+    if plan is not None:
+        return _GraphFunction.apply(plan, len(inputs), *inputs, *params)
     return _PlanFunction.apply(module, precision, len(inputs), need_grad, *inputs, *params)

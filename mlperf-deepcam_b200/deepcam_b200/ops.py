@@ -105,6 +105,10 @@ def _nbytes(*ts):
     return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
 
 
+def _shape_tag(t):
+    return "%dx%dx%dx%d" % tuple(t.shape)
+
+
 def _timed(name, flops, nbytes, rc_fn, what, tag=""):
     if _prof is None:
         check(rc_fn(), what)
@@ -200,14 +204,16 @@ def conv_wgrad(desc, x, dout, G, impl):
 def dw_fwd(x, w9c, stride, dil, out):
     _require_cuda(x, w9c, out)
     _timed("dw_fwd", 18.0 * out.numel(), _nbytes(x, out),
-           lambda: _lib.load().dc_dw_fwd(view(x), _p(w9c), stride, dil, view(out), _stream()), "dc_dw_fwd")
+           lambda: _lib.load().dc_dw_fwd(view(x), _p(w9c), stride, dil, view(out), _stream()), "dc_dw_fwd",
+           tag="%s s%d d%d" % (_shape_tag(x), stride, dil))
     return out
 
 
 def dw_bwd_data(dout, w9c, stride, dil, din, accumulate):
     _require_cuda(dout, w9c, din)
     _timed("dw_bwd_data", 18.0 * dout.numel(), _nbytes(dout, din) * (1.0 if not accumulate else 1.0) + (_nbytes(din) if accumulate else 0.0),
-           lambda: _lib.load().dc_dw_bwd_data(view(dout), _p(w9c), stride, dil, view(din), int(accumulate), _stream()), "dc_dw_bwd_data")
+           lambda: _lib.load().dc_dw_bwd_data(view(dout), _p(w9c), stride, dil, view(din), int(accumulate), _stream()), "dc_dw_bwd_data",
+           tag="%s s%d d%d acc%d" % (_shape_tag(din), stride, dil, int(accumulate)))
     return din
 
 
@@ -215,7 +221,8 @@ def dw_bwd_weight(x, dout, stride, dil, G9c):
     _require_cuda(x, dout, G9c)
     assert G9c.dtype == torch.float32
     _timed("dw_bwd_weight", 18.0 * dout.numel(), _nbytes(x, dout),
-           lambda: _lib.load().dc_dw_bwd_weight(view(x), view(dout), stride, dil, _p(G9c), _stream()), "dc_dw_bwd_weight")
+           lambda: _lib.load().dc_dw_bwd_weight(view(x), view(dout), stride, dil, _p(G9c), _stream()), "dc_dw_bwd_weight",
+           tag="%s s%d d%d" % (_shape_tag(x), stride, dil))
     return G9c
 
 
@@ -223,7 +230,8 @@ def dw_bwd_weight(x, dout, stride, dil, G9c):
 def bn_stats(y, sums):
     _require_cuda(y, sums)
     assert sums.dtype == torch.float64 and sums.numel() == 2 * y.shape[3]
-    _timed("bn_stats", 3.0 * y.numel(), _nbytes(y), lambda: _lib.load().dc_bn_stats(view(y), _p(sums), _stream()), "dc_bn_stats")
+    _timed("bn_stats", 3.0 * y.numel(), _nbytes(y), lambda: _lib.load().dc_bn_stats(view(y), _p(sums), _stream()), "dc_bn_stats",
+           tag=_shape_tag(y))
     return sums
 
 
@@ -244,7 +252,8 @@ def bn_params(gamma, beta, running_mean, running_var, sums, count, momentum, eps
 def bn_apply(params, y, residual, out):
     _require_cuda(y, residual, out)
     _timed("bn_apply", 3.0 * y.numel(), _nbytes(y, residual, out),
-           lambda: _lib.load().dc_bn_apply(ctypes.byref(params), view(y), view(residual), view(out), _stream()), "dc_bn_apply")
+           lambda: _lib.load().dc_bn_apply(ctypes.byref(params), view(y), view(residual), view(out), _stream()), "dc_bn_apply",
+           tag=_shape_tag(y) + (" res" if residual is not None else ""))
     return out
 
 
@@ -253,7 +262,7 @@ def bn_bwd_reduce(params, dout, out, y, rsums):
     assert rsums.dtype == torch.float64
     _timed("bn_bwd_reduce", 4.0 * dout.numel(), _nbytes(dout, out, y),
            lambda: _lib.load().dc_bn_bwd_reduce(ctypes.byref(params), view(dout), view(out), view(y), _p(rsums), _stream()),
-           "dc_bn_bwd_reduce")
+           "dc_bn_bwd_reduce", tag=_shape_tag(dout))
     return rsums
 
 
@@ -261,7 +270,8 @@ def bn_bwd_apply(params, dout, out, y, rsums, dy, dres, dgamma, dbeta):
     _require_cuda(dout)
     _timed("bn_bwd_apply", 8.0 * dout.numel(), _nbytes(dout, out, y, dy, dres),
            lambda: _lib.load().dc_bn_bwd_apply(ctypes.byref(params), view(dout), view(out), view(y), _p(rsums), view(dy),
-                                               view(dres), _p(dgamma), _p(dbeta), _stream()), "dc_bn_bwd_apply")
+                                               view(dres), _p(dgamma), _p(dbeta), _stream()), "dc_bn_bwd_apply",
+           tag=_shape_tag(dout) + (" res" if dres is not None else "") + (" nody" if dy is None else ""))
 
 
 def channel_sum(x, ws, out_c):

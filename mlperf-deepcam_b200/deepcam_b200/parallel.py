@@ -25,6 +25,7 @@ class _GradSync:
         self.buckets = None          # list of (start, end, [param indices])
         self.pending = None
         self.works = []
+        self.deferred = None         # list while a CUDA-graph plan is capturing: completed buckets are queued, not launched
 
     # -- bucket layout (reverse parameter order ~ backward completion order) --
     def _layout(self, grads):
@@ -67,8 +68,15 @@ class _GradSync:
         self.pending[b] -= 1
         # launch in order so every rank issues the collectives in the same sequence
         while self.next_bucket < len(self.buckets) and self.pending[self.next_bucket] <= 0:
-            self._launch(self.next_bucket)
+            if self.deferred is not None:
+                self.deferred.append(self.next_bucket)
+            else:
+                self._launch(self.next_bucket)
             self.next_bucket += 1
+
+    def launch_bucket(self, b):
+        """Replay path of a captured backward: the plan knows after which graph segment bucket b is complete."""
+        self._launch(b)
 
     def _launch(self, b):
         if self.launched[b]:

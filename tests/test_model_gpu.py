@@ -169,3 +169,51 @@ def test_training_loss_trajectory_tracks_oracle(sd, precision, steps, lr):
     assert diffs[0] < (1e-4 if precision == "fp32" else 2e-2)
     assert max(diffs) < (2e-2 if precision == "fp32" else 1e-1)
     assert mine[-1] < mine[0]              # it trains
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cuda_graph_plan_matches_eager(sd, precision, monkeypatch):
+    """Call 1 of a configuration runs eagerly, call 2 captures the forward/backward CUDA graphs, later calls replay
+    them: all must agree with the eager engine on fresh inputs (atomics reorder fp32 sums, hence the tolerance)."""
+    w = O.class_weights()
+    batches = [O.synthetic_batch(2, 64, 96, seed=40 + i) for i in range(4)]
+
+    def run(graphs):
+        monkeypatch.setenv("DEEPCAM_B200_GRAPHS", "1" if graphs else "0")
+        net = _make(sd, precision).train()
+        res = []
+        for x, label in batches:
+            net.zero_grad()
+            out = net(x.to(DEV))
+            loss = losses.fp_loss(out, label.to(DEV), weight=w, fpw_1=w[1], fpw_2=w[2])
+            loss.backward()
+            res.append((out.detach().clone(), float(loss), {k: p.grad.detach().clone() for k, p in net.named_parameters()}))
+        return net, res
+
+    net_g, res_g = run(True)
+    net_e, res_e = run(False)
+    assert net_g.__dict__["_dc_plans"] and all(v[1] is not None and v[1].bwd_segments for v in net_g._dc_plans.values())
+    tol = 1e-5 if precision == "fp32" else 2e-2
+    for (og, lg, gg), (oe, le, ge) in zip(res_g, res_e):
+        assert _rel(og, oe) < tol
+        assert abs(lg - le) < tol
+        worst = max(_rel(gg[k], ge[k]) for k in gg)
+        assert worst < (1e-3 if precision == "fp32" else 0.25), worst
+    sg, se = net_g.state_dict(), net_e.state_dict()
+    for k in sg:
+        if k.endswith("num_batches_tracked"):
+            assert int(sg[k]) == len(batches) == int(se[k])
+        elif k.endswith("running_mean") or k.endswith("running_var"):
+            assert torch.allclose(sg[k], se[k], rtol=1e-3, atol=1e-4), k
+
+
+def test_cuda_graph_plan_rejects_stale_backward(sd, monkeypatch):
+    monkeypatch.setenv("DEEPCAM_B200_GRAPHS", "1")
+    net = _make(sd, "fp32").train()
+    x, _ = O.synthetic_batch(2, 32, 48, seed=50)
+    net(x.to(DEV)).sum().backward()            # eager warm-up call
+    out1 = net(x.to(DEV))                      # captured
+    out2 = net(x.to(DEV))                      # replay overwrites the activations out1's backward would need
+    with pytest.raises(RuntimeError, match="must follow the forward"):
+        out1.sum().backward()
+    out2.sum().backward()
