@@ -88,6 +88,17 @@ int dc_i64_increment_many(int64_t* const* ptrs, int count, void* stream);
 enum { DC_PACK_TKN = 0, DC_PACK_NTK = 1 };
 int dc_pack_weight(const float* src, int K, int N, int taps, int src_k_first,
                    void* dst, int layout, int K_pad, int N_pad, int dst_dtype, void* stream);
+/* Every weight pack of a training step in one launch.  `jobs_dev` is a DEVICE array of njobs descriptors (same
+ * meaning as the dc_pack_weight arguments); job i owns blocks [block_start, block_start + n_blocks) of the grid and
+ * total_blocks = sum of n_blocks.  taps*K_pad*N_pad of a job must be < 2^31. */
+typedef struct dc_pack_job {
+  const float* src;
+  void*   dst;
+  int32_t K, N, taps, src_k_first;
+  int32_t layout, K_pad, N_pad, dst_dtype;
+  int32_t block_start, n_blocks;
+} dc_pack_job;
+int dc_pack_weights_multi(const dc_pack_job* jobs_dev, int njobs, int total_blocks, void* stream);
 /* Gradient unpack: G is [taps][n][k_stride] fp32 (k < K valid; k_stride >= K allows channel padding);
  * dst is the parameter-layout gradient: dst_k_first=0 -> [n][k][taps], 1 -> [k][n][taps]. */
 int dc_unpack_wgrad(const float* G, int K, int N, int taps, int k_stride, int dst_k_first, float* dst, void* stream);
@@ -115,31 +126,39 @@ int dc_dw_bwd_data(dc_view dout, const void* w9c, int stride, int dil, dc_view d
 int dc_dw_bwd_weight(dc_view in, dc_view dout, int stride, int dil, float* G9c, void* stream);
 
 /* ---- BatchNorm2d (+ReLU, +residual add) (normalizer, DX:70,129,283,348,399; relu DX:79,147; add DX:120) ---- */
-/* per-channel sum / sum of squares accumulated in double (pre-zeroed), sums = [2][C] */
-int dc_bn_stats(dc_view y, double* sums, void* stream);
+/* Per-layer BatchNorm workspace, dc_bn_ws_bytes(C) bytes, ZEROED by the caller before dc_bn_stats / dc_bn_bwd_reduce:
+ *   double sums[2][C] | float coef[4][C] | uint32 ticket.
+ * The reduction kernels accumulate fp64 sums with atomics; the last block to finish converts them into fp32
+ * per-channel coefficients (forward: scale, shift, mean, invstd; backward: A, B, D with dy = A*g + B*y + D), so the
+ * element-wise kernels carry no double-precision prologue and no separate finalize launch exists. */
+size_t dc_bn_ws_bytes(int C);
 enum {
   DC_BN_RELU       = 1,   /* out = relu(...) */
-  DC_BN_TRAIN      = 2,   /* batch statistics from `sums`; update running stats (block 0) */
+  DC_BN_TRAIN      = 2,   /* batch statistics from the workspace `sums` */
   DC_BN_IDENTITY   = 4,   /* skip normalisation (pure relu / add) */
   DC_BN_RES_WRITE  = 8    /* backward: residual gradient is written, not accumulated */
 };
 typedef struct dc_bn_params {
   const float* gamma;  const float* beta;      /* [C] */
-  float* running_mean; float* running_var;     /* [C]; updated in train mode */
-  const double* sums;                          /* [2][C] from dc_bn_stats (train) */
+  float* running_mean; float* running_var;     /* [C]; updated by dc_bn_stats (may both be NULL) */
+  const double* sums;                          /* forward workspace (train mode), see dc_bn_ws_bytes */
   double count;                                /* N*H*W */
   float momentum, eps;
   int32_t flags;
   int32_t reserved;
 } dc_bn_params;
-/* out = [relu]( bn(y) [+ residual] ); residual.ptr may be NULL */
+/* batch statistics of y into p->sums (zeroed workspace) + coefficients + running-statistics update */
+int dc_bn_stats(const dc_bn_params* p, dc_view y, void* stream);
+/* out = [relu]( bn(y) [+ residual] ); residual.ptr may be NULL.  Views: channel-contiguous, 16-byte aligned,
+ * C % 8 == 0 (bf16) or C % 4 == 0 (fp32). */
 int dc_bn_apply(const dc_bn_params* p, dc_view y, dc_view residual, dc_view out, void* stream);
-/* backward pass 1: g = dout * (out > 0 if RELU); rsums[0][c] += sum g, rsums[1][c] += sum g*y   (double, pre-zeroed) */
-int dc_bn_bwd_reduce(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, double* rsums, void* stream);
-/* backward pass 2: dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); optional dres (+)= g;
- * dgamma/dbeta ([C] fp32) written by block 0 when non-NULL. */
-int dc_bn_bwd_apply(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, const double* rsums,
-                    dc_view dy, dc_view dres, float* dgamma, float* dbeta, void* stream);
+/* backward pass 1: g = dout * (out > 0 if RELU); sums of g and g*y into the zeroed workspace `rws`; the last block
+ * writes dgamma/dbeta ([C] fp32, may be NULL) and the coefficients A, B, D. */
+int dc_bn_bwd_reduce(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, void* rws, float* dgamma, float* dbeta,
+                     void* stream);
+/* backward pass 2: dy = A*g + B*y + D (= gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))); optional dres (+)= g */
+int dc_bn_bwd_apply(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, const void* rws,
+                    dc_view dy, dc_view dres, void* stream);
 /* per-channel sum over n,h,w into fp32 [C] (bias gradient of upsample.conv1.6, DX:366); ws_c: C doubles of scratch */
 int dc_channel_sum(dc_view x, double* ws_c, float* out_c, void* stream);
 

@@ -2,261 +2,455 @@
 // Reference semantics: torch.nn.BatchNorm2d as `normalizer` (DX:70,129,283,348,399; eps 1e-5, momentum 0.1),
 // nn.ReLU(inplace=True) (DX:79,147) and the in-place residual add `x += skip` (DX:120).
 //
-// Thread mapping shared by all kernels here ("channel lanes x pixel lanes"):
-//   a block owns `cvb` consecutive 4-channel vectors (<= 32, i.e. <= 128 channels) and `rows = 256/cvb`
-//   pixel lanes; each thread keeps its channel vector fixed and strides over pixels, so a warp reads
-//   up to 256 contiguous bytes per pixel and per-channel coefficients are computed once per thread.
+// Thread mapping shared by all kernels ("channel lanes x pixel lanes"):
+//   a thread owns one vector of V channels (16 bytes: V = 8 bf16 or 4 fp32) and strides over pixels; the 32 lanes
+//   of a warp cover 32 consecutive channel vectors of one pixel (512 contiguous bytes), or, when a pixel has fewer
+//   than 32 vectors, several consecutive pixels.  Per-channel coefficients are loaded once per thread.
+// Statistics: per-thread fp32 partials -> block reduction -> fp64 atomics into the per-layer workspace; the LAST
+// block to finish (atomic ticket) turns the sums into fp32 per-channel coefficients, so the apply kernels carry
+// no double-precision prologue and no extra "finalize" launch is needed.
+//   workspace (dc_bn_ws_bytes(C) bytes, zeroed by the caller):  double sums[2][C] | float coef[4][C] | uint32 ticket
+//     forward : coef = scale, shift, mean, invstd            (out = y*scale + shift)
+//     backward: coef = A, B, D                               (dy  = A*g + B*y + D,  g = dout masked by ReLU)
 // HBM-bound: algorithmic bytes = each tensor read or written exactly once.
 #include "common.cuh"
 #include <algorithm>
 
 namespace dc {
 
-struct ChanGrid {
-  int cv, cvb, rows;
-  dim3 grid;
-};
-static inline ChanGrid chan_grid(int C, long long npix) {
-  ChanGrid g;
-  g.cv = C / 4;
-  g.cvb = std::min(g.cv, 32);
-  g.rows = 256 / g.cvb;
-  int gy = ceil_div(g.cv, g.cvb);
-  long long gx_need = (npix + g.rows - 1) / g.rows;
-  int gx_cap = std::max(1, (kNumSMs * 8) / gy);
-  g.grid = dim3((unsigned)std::min<long long>(gx_need, gx_cap), gy, 1);
-  return g;
-}
-
-__device__ __forceinline__ void decode_pix(int p, int H, int W, int& n, int& h, int& w) {
-  w = p % W;
-  int t = p / W;
-  h = t % H;
-  n = t / H;
-}
-
-struct Coef { float mean, invstd, scale, shift; };
-__device__ __forceinline__ Coef bn_coef(const dc_bn_params& p, int C, int c) {
-  Coef k;
-  if (p.flags & DC_BN_IDENTITY) { k.mean = 0.f; k.invstd = 1.f; k.scale = 1.f; k.shift = 0.f; return k; }
-  double m, var;
-  if (p.flags & DC_BN_TRAIN) {
-    m = p.sums[c] / p.count;
-    var = p.sums[C + c] / p.count - m * m;
-    if (var < 0.0) var = 0.0;
-  } else {
-    m = (double)p.running_mean[c];
-    var = (double)p.running_var[c];
+// ---- 16-byte channel vectors ---------------------------------------------------------------------------
+template <typename T> struct vec16;
+template <> struct vec16<float> {
+  static constexpr int V = 4;
+  __device__ static __forceinline__ uint4 ldraw(const float* p) { return *reinterpret_cast<const uint4*>(p); }
+  __device__ static __forceinline__ void unpack(const uint4& t, float (&f)[4]) {
+    f[0] = __uint_as_float(t.x); f[1] = __uint_as_float(t.y); f[2] = __uint_as_float(t.z); f[3] = __uint_as_float(t.w);
   }
-  double inv = 1.0 / sqrt(var + (double)p.eps);
-  k.mean = (float)m;
-  k.invstd = (float)inv;
-  k.scale = p.gamma[c] * k.invstd;
-  k.shift = p.beta[c] - k.mean * k.scale;
-  return k;
+  __device__ static __forceinline__ void ld(const float* p, float (&f)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+  }
+  __device__ static __forceinline__ void st(float* p, const float (&f)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+template <> struct vec16<__nv_bfloat16> {
+  static constexpr int V = 8;
+  __device__ static __forceinline__ uint4 ldraw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  __device__ static __forceinline__ void unpack(const uint4& t, float (&f)[8]) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f[2 * j] = __uint_as_float(w[j] << 16); f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+  }
+  __device__ static __forceinline__ void ld(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f[2 * j] = __uint_as_float(w[j] << 16); f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+  }
+  __device__ static __forceinline__ void st(__nv_bfloat16* p, const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&b);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// ---- lane mapping ----------------------------------------------------------------------------------------
+struct LaneMap {
+  int cv;        // channel vectors per pixel
+  int cvp;       // lanes per pixel inside a warp (power of two <= 32)
+  int ppw;       // pixels per warp = 32 / cvp
+  int ppb;       // pixels per block = 8 warps * ppw
+  int gy;        // channel blocks
+};
+static inline LaneMap lane_map(int C, int V) {
+  LaneMap m;
+  m.cv = C / V;
+  m.cvp = 1;
+  while (m.cvp < 32 && m.cvp < m.cv) m.cvp <<= 1;
+  m.ppw = 32 / m.cvp;
+  m.ppb = 8 * m.ppw;
+  m.gy = ceil_div(m.cv, m.cvp);
+  return m;
 }
 
-// Reduce `nacc` per-thread fp32 partials (per channel of the thread's vector) across the block's pixel
-// lanes and add them to double accumulators in global memory: dst[a*C + c].
-template <int NACC>
-__device__ __forceinline__ void block_reduce_to_global(float (&acc)[NACC][4], double* dst, int C, int c4, bool lane_ok,
-                                                       int cvb, int rows, int tx, int ty) {
-  extern __shared__ double red[];   // [rows][cvb*4*NACC]
-  const int per_row = cvb * 4 * NACC;
-  if (ty < rows) {
+// strided pixel addressing; `lin` = the view is pixel-linear (offset = pixel * sw), true for dense NHWC tensors and
+// channel slices of concat buffers
+template <typename T>
+struct PixView {
+  T* p;
+  int h, w;
+  long long sn, sh, sw;
+  int lin;
+  __device__ __forceinline__ T* at(long long pix) const {
+    if (lin) return p + pix * sw;
+    int x = (int)(pix % w);
+    long long t = pix / w;
+    int y = (int)(t % h);
+    long long n = t / h;
+    return p + n * sn + y * sh + x * sw;
+  }
+};
+template <typename T>
+static inline PixView<T> pix_view(const dc_view& v) {
+  PixView<T> r;
+  r.p = reinterpret_cast<T*>(v.ptr);
+  r.h = v.h; r.w = v.w; r.sn = v.sn; r.sh = v.sh; r.sw = v.sw;
+  r.lin = (v.ptr != nullptr && v.sh == (long long)v.w * v.sw && v.sn == (long long)v.h * v.sh) ? 1 : 0;
+  return r;
+}
+
+struct BnWs {
+  double* sums;     // [2][C]
+  float* coef;      // [4][C]
+  unsigned* ticket;
+};
+__host__ __device__ static inline BnWs bn_ws(void* ws, int C) {
+  BnWs w;
+  w.sums = reinterpret_cast<double*>(ws);
+  w.coef = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + (size_t)16 * C);
+  w.ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + (size_t)32 * C);
+  return w;
+}
+
+constexpr int kBnThreads = 256;
+constexpr int kUnroll = 4;
+
+// Block reduction of NACC x V per-thread partials over the pixel lanes of a block, then fp64 atomics.
+// smem: float red[8 warps][32 lanes][NACC*V]
+template <int NACC, int V>
+__device__ __forceinline__ void reduce_to_ws(float (&acc)[NACC][V], double* dst, int C, int cvp, int cv_base, int cv_count) {
+  extern __shared__ float red[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // lanes of a warp that share a channel vector (different pixels): butterfly over the pixel-sub index
+  for (int o = cvp; o < 32; o <<= 1) {
 #pragma unroll
     for (int a = 0; a < NACC; ++a)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) red[ty * per_row + (a * cvb + tx) * 4 + j] = lane_ok ? (double)acc[a][j] : 0.0;
+      for (int j = 0; j < V; ++j) acc[a][j] += __shfl_xor_sync(0xffffffffu, acc[a][j], o);
+  }
+  constexpr int PER = NACC * V;
+  if (lane < cvp) {
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+      for (int j = 0; j < V; ++j) red[(warp * 32 + lane) * PER + a * V + j] = acc[a][j];
   }
   __syncthreads();
-  // threads 0..per_row-1 each own one (a, tx, j) column
-  for (int col = threadIdx.x; col < per_row; col += blockDim.x) {
-    double s = 0.0;
-    for (int r = 0; r < rows; ++r) s += red[r * per_row + col];
-    int a = col / (cvb * 4);
-    int rem = col - a * cvb * 4;
-    int ltx = rem >> 2, j = rem & 3;
-    int c = (blockIdx.y * cvb + ltx) * 4 + j;
-    if (c < C) atomicAdd(dst + (size_t)a * C + c, s);
+  for (int col = threadIdx.x; col < cvp * PER; col += kBnThreads) {
+    const int l = col / PER, r = col - l * PER;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[(w * 32 + l) * PER + r];
+    const int a = r / V, j = r - a * V;
+    const int cvi = cv_base + l;
+    if (l < cv_count) atomicAdd(dst + (size_t)a * C + cvi * V + j, (double)s);
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) bn_stats_kernel(View<const T> y, double* sums, int cvb, int rows) {
-  const int tx = threadIdx.x % cvb, ty = threadIdx.x / cvb;
-  const int c4 = blockIdx.y * cvb + tx;
-  const bool ok = (ty < rows) && (c4 * 4 < y.c);
-  const int npix = y.n * y.h * y.w;
-  float acc[2][4] = {};
+// 1/sqrt(v) in fp32: hardware approximation + one Newton-Raphson step (~1 ulp)
+__device__ __forceinline__ float inv_sqrt_f32(float v) {
+  float r = rsqrtf(v);
+  return r * (1.5f - 0.5f * v * r * r);
+}
+
+// returns true in every thread of the block that took the last ticket
+__device__ __forceinline__ bool last_block(unsigned* ticket) {
+  __shared__ unsigned s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y;
+    s_last = (atomicAdd(ticket, 1u) == total - 1u) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0u;
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(dc_bn_params p, PixView<const T> y, int C, long long npix, LaneMap m) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
+  const int cvi = blockIdx.y * m.cvp + cvl;
+  const bool ok = cvi < m.cv;
+  float acc[2][V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  const long long stride = (long long)gridDim.x * m.ppb;
+  long long pix = (long long)blockIdx.x * m.ppb + warp * m.ppw + psub;
   if (ok) {
-    for (int p = blockIdx.x * rows + ty; p < npix; p += gridDim.x * rows) {
-      int n, h, w;
-      decode_pix(p, y.h, y.w, n, h, w);
-      float4 v = elem<T>::ld4(y.at(n, h, w) + c4 * 4);
-      acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
-      acc[1][0] += v.x * v.x; acc[1][1] += v.y * v.y; acc[1][2] += v.z * v.z; acc[1][3] += v.w * v.w;
+    for (; pix + (kUnroll - 1) * stride < npix; pix += kUnroll * stride) {
+      uint4 raw[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) raw[u] = vec16<T>::ldraw(y.at(pix + u * stride) + cvi * V);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        float v[V];
+        vec16<T>::unpack(raw[u], v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) { acc[0][j] += v[j]; acc[1][j] = fmaf(v[j], v[j], acc[1][j]); }
+      }
+    }
+    for (; pix < npix; pix += stride) {
+      float v[V];
+      vec16<T>::ld(y.at(pix) + cvi * V, v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) { acc[0][j] += v[j]; acc[1][j] = fmaf(v[j], v[j], acc[1][j]); }
     }
   }
-  block_reduce_to_global<2>(acc, sums, y.c, c4, ok, cvb, rows, tx, ty);
+  BnWs ws = bn_ws(const_cast<double*>(p.sums), C);
+  reduce_to_ws<2, V>(acc, ws.sums, C, m.cvp, blockIdx.y * m.cvp, min(m.cvp, m.cv - blockIdx.y * m.cvp));
+  if (!last_block(ws.ticket)) return;
+  // ---- finalize: batch statistics -> fp32 coefficients, running statistics (torch uses the unbiased variance there).
+  // mean and variance in double (cancellation), 1/sqrt in fp32 with one Newton step (the apply path is fp32 anyway).
+  const double inv_count = 1.0 / p.count;
+  const double unbias = p.count / (p.count - 1.0);
+  for (int c = threadIdx.x; c < C; c += kBnThreads) {
+    const double s = __ldcg(ws.sums + c), q = __ldcg(ws.sums + C + c);
+    const double mean = s * inv_count;
+    double var = q * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float inv = inv_sqrt_f32((float)(var + (double)p.eps));
+    const float scale = p.gamma[c] * inv;
+    ws.coef[c] = scale;
+    ws.coef[C + c] = p.beta[c] - (float)mean * scale;
+    ws.coef[2 * C + c] = (float)mean;
+    ws.coef[3 * C + c] = inv;
+    if (p.running_mean != nullptr) {
+      p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mean;
+      p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)(var * unbias);
+    }
+  }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) bn_apply_kernel(dc_bn_params p, View<const T> y, View<const T> res, View<T> out,
-                                                       int cvb, int rows) {
-  const int tx = threadIdx.x % cvb, ty = threadIdx.x / cvb;
-  const int c4 = blockIdx.y * cvb + tx;
-  const int C = y.c;
-  if (ty >= rows || c4 * 4 >= C) return;
-  const int npix = y.n * y.h * y.w;
-  Coef k[4];
+// per-thread forward coefficients of V channels
+template <int V>
+__device__ __forceinline__ void load_fwd_coef(const dc_bn_params& p, int C, int c0, float (&scale)[V], float (&shift)[V],
+                                              float (&mean)[V], float (&invstd)[V]) {
+  if (p.flags & DC_BN_IDENTITY) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) k[j] = bn_coef(p, C, c4 * 4 + j);
-  if ((p.flags & DC_BN_TRAIN) && !(p.flags & DC_BN_IDENTITY) && blockIdx.x == 0 && ty == 0 && p.running_mean != nullptr) {
-    // running statistics: torch uses the unbiased variance for the running estimate
+    for (int j = 0; j < V; ++j) { scale[j] = 1.f; shift[j] = 0.f; mean[j] = 0.f; invstd[j] = 1.f; }
+  } else if (p.flags & DC_BN_TRAIN) {
+    const BnWs ws = bn_ws(const_cast<double*>(p.sums), C);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int c = c4 * 4 + j;
-      double m = p.sums[c] / p.count;
-      double var = p.sums[C + c] / p.count - m * m;
-      if (var < 0.0) var = 0.0;
-      double unb = var * (p.count / (p.count - 1.0));
-      p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)m;
-      p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)unb;
+    for (int j = 0; j < V; ++j) {
+      scale[j] = ws.coef[c0 + j]; shift[j] = ws.coef[C + c0 + j];
+      mean[j] = ws.coef[2 * C + c0 + j]; invstd[j] = ws.coef[3 * C + c0 + j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float inv = inv_sqrt_f32(p.running_var[c0 + j] + p.eps);
+      mean[j] = p.running_mean[c0 + j];
+      invstd[j] = inv;
+      scale[j] = p.gamma[c0 + j] * inv;
+      shift[j] = p.beta[c0 + j] - mean[j] * scale[j];
     }
   }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(dc_bn_params p, PixView<const T> y, PixView<const T> res, PixView<T> out,
+                                                              int C, long long npix, LaneMap m) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
+  const int cvi = blockIdx.y * m.cvp + cvl;
+  if (cvi >= m.cv) return;
+  const int c0 = cvi * V;
+  float scale[V], shift[V], mean[V], invstd[V];
+  load_fwd_coef<V>(p, C, c0, scale, shift, mean, invstd);
   const bool relu = (p.flags & DC_BN_RELU) != 0;
   const bool has_res = res.p != nullptr;
-  for (int pix = blockIdx.x * rows + ty; pix < npix; pix += gridDim.x * rows) {
-    int n, h, w;
-    decode_pix(pix, y.h, y.w, n, h, w);
-    float4 v = elem<T>::ld4(y.at(n, h, w) + c4 * 4);
-    float4 o;
-    o.x = fmaf(v.x, k[0].scale, k[0].shift);
-    o.y = fmaf(v.y, k[1].scale, k[1].shift);
-    o.z = fmaf(v.z, k[2].scale, k[2].shift);
-    o.w = fmaf(v.w, k[3].scale, k[3].shift);
-    if (has_res) {
-      float4 r = elem<T>::ld4(res.at(n, h, w) + c4 * 4);
-      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-    }
-    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    elem<T>::st4(out.at(n, h, w) + c4 * 4, o);
-  }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(dc_bn_params p, View<const T> dout, View<const T> out,
-                                                            View<const T> y, double* rsums, int cvb, int rows) {
-  const int tx = threadIdx.x % cvb, ty = threadIdx.x / cvb;
-  const int c4 = blockIdx.y * cvb + tx;
-  const bool ok = (ty < rows) && (c4 * 4 < y.c);
-  const int npix = y.n * y.h * y.w;
-  const bool relu = (p.flags & DC_BN_RELU) != 0;
-  float acc[2][4] = {};
-  if (ok) {
-    for (int pix = blockIdx.x * rows + ty; pix < npix; pix += gridDim.x * rows) {
-      int n, h, w;
-      decode_pix(pix, y.h, y.w, n, h, w);
-      float4 g = elem<T>::ld4(dout.at(n, h, w) + c4 * 4);
-      if (relu) {
-        float4 o = elem<T>::ld4(out.at(n, h, w) + c4 * 4);
-        g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
-        g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+  const long long stride = (long long)gridDim.x * m.ppb;
+  long long pix = (long long)blockIdx.x * m.ppb + warp * m.ppw + psub;
+  for (; pix < npix; pix += kUnroll * stride) {
+    uint4 vraw[kUnroll], rraw[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (pix + u * stride < npix) {
+        vraw[u] = vec16<T>::ldraw(y.at(pix + u * stride) + c0);
+        if (has_res) rraw[u] = vec16<T>::ldraw(res.at(pix + u * stride) + c0);
       }
-      float4 v = elem<T>::ld4(y.at(n, h, w) + c4 * 4);
-      acc[0][0] += g.x; acc[0][1] += g.y; acc[0][2] += g.z; acc[0][3] += g.w;
-      acc[1][0] += g.x * v.x; acc[1][1] += g.y * v.y; acc[1][2] += g.z * v.z; acc[1][3] += g.w * v.w;
-    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (pix + u * stride < npix) {
+        float v[V], r[V], o[V];
+        vec16<T>::unpack(vraw[u], v);
+        if (has_res) vec16<T>::unpack(rraw[u], r);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          o[j] = fmaf(v[j], scale[j], shift[j]);
+          if (has_res) o[j] += r[j];
+          if (relu) o[j] = fmaxf(o[j], 0.f);
+        }
+        vec16<T>::st(out.at(pix + u * stride) + c0, o);
+      }
   }
-  block_reduce_to_global<2>(acc, rsums, y.c, c4, ok, cvb, rows, tx, ty);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(dc_bn_params p, View<const T> dout, View<const T> out,
-                                                           View<const T> y, const double* rsums, View<T> dy, View<T> dres,
-                                                           float* dgamma, float* dbeta, int cvb, int rows) {
-  const int tx = threadIdx.x % cvb, ty = threadIdx.x / cvb;
-  const int c4 = blockIdx.y * cvb + tx;
-  const int C = dout.c;
-  if (ty >= rows || c4 * 4 >= C) return;
-  const int npix = dout.n * dout.h * dout.w;
+template <typename T, int V>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(dc_bn_params p, PixView<const T> dout, PixView<const T> out,
+                                                                   PixView<const T> y, void* rws_raw, float* dgamma, float* dbeta,
+                                                                   int C, long long npix, LaneMap m) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
+  const int cvi = blockIdx.y * m.cvp + cvl;
+  const bool ok = cvi < m.cv;
+  const int c0 = cvi * V;
+  const bool relu = (p.flags & DC_BN_RELU) != 0;
+  float acc[2][V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  const long long stride = (long long)gridDim.x * m.ppb;
+  long long pix = (long long)blockIdx.x * m.ppb + warp * m.ppw + psub;
+  if (ok) {
+    for (; pix < npix; pix += kUnroll * stride) {
+      uint4 graw[kUnroll], oraw[kUnroll], vraw[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if (pix + u * stride < npix) {
+          graw[u] = vec16<T>::ldraw(dout.at(pix + u * stride) + c0);
+          if (relu) oraw[u] = vec16<T>::ldraw(out.at(pix + u * stride) + c0);
+          vraw[u] = vec16<T>::ldraw(y.at(pix + u * stride) + c0);
+        }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if (pix + u * stride < npix) {
+          float g[V], o[V], v[V];
+          vec16<T>::unpack(graw[u], g);
+          if (relu) vec16<T>::unpack(oraw[u], o);
+          vec16<T>::unpack(vraw[u], v);
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            float gg = g[j];
+            if (relu) gg = o[j] > 0.f ? gg : 0.f;
+            acc[0][j] += gg;
+            acc[1][j] = fmaf(gg, v[j], acc[1][j]);
+          }
+        }
+    }
+  }
+  BnWs rws = bn_ws(rws_raw, C);
+  reduce_to_ws<2, V>(acc, rws.sums, C, m.cvp, blockIdx.y * m.cvp, min(m.cvp, m.cv - blockIdx.y * m.cvp));
+  if (!last_block(rws.ticket)) return;
+  // ---- finalize: dgamma, dbeta and the per-channel coefficients of dy = A*g + B*y + D
+  const bool train = (p.flags & DC_BN_TRAIN) != 0;
+  const double inv_count = 1.0 / p.count;
+  for (int c = threadIdx.x; c < C; c += kBnThreads) {
+    double mean, inv;
+    if (train) {                 // the forward workspace holds exactly the coefficients the forward pass applied
+      const BnWs fws = bn_ws(const_cast<double*>(p.sums), C);
+      mean = p.sums[c] * inv_count;
+      inv = (double)fws.coef[3 * C + c];
+    } else {
+      mean = (double)p.running_mean[c];
+      inv = (double)inv_sqrt_f32(p.running_var[c] + p.eps);
+    }
+    const double sg = __ldcg(rws.sums + c), sgy = __ldcg(rws.sums + C + c);
+    const double sgx = inv * (sgy - mean * sg);                  // sum g * xhat
+    if (dgamma) dgamma[c] = (float)sgx;
+    if (dbeta) dbeta[c] = (float)sg;
+    const double scale = (double)p.gamma[c] * inv;
+    double A = scale, B = 0.0, D = 0.0;
+    if (train) {          // eval-mode BN inside a training graph (freeze_bn, DX:467): statistics are constants
+      const double mg = sg * inv_count, mgx = sgx * inv_count;
+      B = -scale * inv * mgx;
+      D = -scale * mg + scale * mean * inv * mgx;
+    }
+    rws.coef[c] = (float)A;
+    rws.coef[C + c] = (float)B;
+    rws.coef[2 * C + c] = (float)D;
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(dc_bn_params p, PixView<const T> dout, PixView<const T> out,
+                                                                  PixView<const T> y, const void* rws_raw, PixView<T> dy, PixView<T> dres,
+                                                                  int C, long long npix, LaneMap m) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
+  const int cvi = blockIdx.y * m.cvp + cvl;
+  if (cvi >= m.cv) return;
+  const int c0 = cvi * V;
   const bool relu = (p.flags & DC_BN_RELU) != 0;
   const bool ident = (p.flags & DC_BN_IDENTITY) != 0;
   const bool has_res = dres.p != nullptr;
   const bool res_write = (p.flags & DC_BN_RES_WRITE) != 0;
   const bool has_dy = dy.p != nullptr;
-  Coef k[4];
-  float mg[4], mgx[4];
+  const bool need_y = has_dy && !ident;
+  float A[V], B[V], D[V];
+  if (need_y) {
+    const BnWs rws = bn_ws(const_cast<void*>(rws_raw), C);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    int c = c4 * 4 + j;
-    k[j] = bn_coef(p, C, c);
-    if (!ident) {
-      double sg = rsums[c], sgy = rsums[C + c];
-      double sgx = (double)k[j].invstd * (sgy - (double)k[j].mean * sg);   // sum g*xhat
-      if (p.flags & DC_BN_TRAIN) {
-        mg[j] = (float)(sg / p.count);
-        mgx[j] = (float)(sgx / p.count);
-      } else {            // eval-mode BN inside a training graph (freeze_bn, DX:467): statistics are constants
-        mg[j] = 0.f; mgx[j] = 0.f;
-      }
-      if (blockIdx.x == 0 && ty == 0) {
-        if (dgamma) dgamma[c] = (float)sgx;
-        if (dbeta) dbeta[c] = (float)sg;
-      }
-    } else { mg[j] = 0.f; mgx[j] = 0.f; }
+    for (int j = 0; j < V; ++j) { A[j] = rws.coef[c0 + j]; B[j] = rws.coef[C + c0 + j]; D[j] = rws.coef[2 * C + c0 + j]; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < V; ++j) { A[j] = 1.f; B[j] = 0.f; D[j] = 0.f; }
   }
-  for (int pix = blockIdx.x * rows + ty; pix < npix; pix += gridDim.x * rows) {
-    int n, h, w;
-    decode_pix(pix, dout.h, dout.w, n, h, w);
-    float4 g = elem<T>::ld4(dout.at(n, h, w) + c4 * 4);
-    if (relu) {
-      float4 o = elem<T>::ld4(out.at(n, h, w) + c4 * 4);
-      g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
-      g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
-    }
-    if (has_res) {
-      T* rp = dres.at(n, h, w) + c4 * 4;
-      float4 r = g;
-      if (!res_write) {
-        float4 old = elem<T>::ld4(rp);
-        r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+  const long long stride = (long long)gridDim.x * m.ppb;
+  long long pix = (long long)blockIdx.x * m.ppb + warp * m.ppw + psub;
+  for (; pix < npix; pix += kUnroll * stride) {
+    uint4 graw[kUnroll], oraw[kUnroll], vraw[kUnroll], rraw[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (pix + u * stride < npix) {
+        graw[u] = vec16<T>::ldraw(dout.at(pix + u * stride) + c0);
+        if (relu) oraw[u] = vec16<T>::ldraw(out.at(pix + u * stride) + c0);
+        if (need_y) vraw[u] = vec16<T>::ldraw(y.at(pix + u * stride) + c0);
+        if (has_res && !res_write) rraw[u] = vec16<T>::ldraw(dres.at(pix + u * stride) + c0);
       }
-      elem<T>::st4(rp, r);
-    }
-    if (has_dy) {
-      float4 d;
-      if (ident) {
-        d = g;
-      } else {
-        float4 v = elem<T>::ld4(y.at(n, h, w) + c4 * 4);
-        d.x = k[0].scale * (g.x - mg[0] - (v.x - k[0].mean) * k[0].invstd * mgx[0]);
-        d.y = k[1].scale * (g.y - mg[1] - (v.y - k[1].mean) * k[1].invstd * mgx[1]);
-        d.z = k[2].scale * (g.z - mg[2] - (v.z - k[2].mean) * k[2].invstd * mgx[2]);
-        d.w = k[3].scale * (g.w - mg[3] - (v.w - k[3].mean) * k[3].invstd * mgx[3]);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (pix + u * stride < npix) {
+        float gg[V], o[V], v[V], r[V];
+        vec16<T>::unpack(graw[u], gg);
+        if (relu) {
+          vec16<T>::unpack(oraw[u], o);
+#pragma unroll
+          for (int j = 0; j < V; ++j) gg[j] = o[j] > 0.f ? gg[j] : 0.f;
+        }
+        if (has_res) {
+          float rr[V];
+          if (!res_write) vec16<T>::unpack(rraw[u], r);
+#pragma unroll
+          for (int j = 0; j < V; ++j) rr[j] = res_write ? gg[j] : gg[j] + r[j];
+          vec16<T>::st(dres.at(pix + u * stride) + c0, rr);
+        }
+        if (has_dy) {
+          float d[V];
+          if (need_y) vec16<T>::unpack(vraw[u], v);
+#pragma unroll
+          for (int j = 0; j < V; ++j) d[j] = need_y ? fmaf(A[j], gg[j], fmaf(B[j], v[j], D[j])) : gg[j];
+          vec16<T>::st(dy.at(pix + u * stride) + c0, d);
+        }
       }
-      elem<T>::st4(dy.at(n, h, w) + c4 * 4, d);
-    }
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) channel_sum_kernel(View<const T> x, double* sums, int cvb, int rows) {
-  const int tx = threadIdx.x % cvb, ty = threadIdx.x / cvb;
-  const int c4 = blockIdx.y * cvb + tx;
-  const bool ok = (ty < rows) && (c4 * 4 < x.c);
-  const int npix = x.n * x.h * x.w;
-  float acc[1][4] = {};
+template <typename T, int V>
+__global__ void __launch_bounds__(kBnThreads) channel_sum_kernel(PixView<const T> x, double* sums, int C, long long npix, LaneMap m) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
+  const int cvi = blockIdx.y * m.cvp + cvl;
+  const bool ok = cvi < m.cv;
+  float acc[1][V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[0][j] = 0.f;
+  const long long stride = (long long)gridDim.x * m.ppb;
   if (ok) {
-    for (int p = blockIdx.x * rows + ty; p < npix; p += gridDim.x * rows) {
-      int n, h, w;
-      decode_pix(p, x.h, x.w, n, h, w);
-      float4 v = elem<T>::ld4(x.at(n, h, w) + c4 * 4);
-      acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
+    for (long long pix = (long long)blockIdx.x * m.ppb + warp * m.ppw + psub; pix < npix; pix += stride) {
+      float v[V];
+      vec16<T>::ld(x.at(pix) + cvi * V, v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[0][j] += v[j];
     }
   }
-  block_reduce_to_global<1>(acc, sums, x.c, c4, ok, cvb, rows, tx, ty);
+  reduce_to_ws<1, V>(acc, sums, C, m.cvp, blockIdx.y * m.cvp, min(m.cvp, m.cv - blockIdx.y * m.cvp));
 }
 
 __global__ void double_to_float_kernel(const double* s, float* d, int n) {
@@ -264,34 +458,61 @@ __global__ void double_to_float_kernel(const double* s, float* d, int n) {
   if (i < n) d[i] = (float)s[i];
 }
 
-static inline size_t red_smem(const ChanGrid& g, int nacc) { return (size_t)g.rows * g.cvb * 4 * nacc * sizeof(double); }
+// ---- host side ---------------------------------------------------------------------------------------------
+// grid.x: enough blocks that every thread handles about `items` pixels, capped at 16 blocks per SM (grid-stride beyond)
+static inline dim3 bn_grid(const LaneMap& m, long long npix, int items) {
+  long long gx = ceil_div64(npix, (long long)m.ppb * items);
+  long long cap = std::max<long long>(1, (long long)kNumSMs * 16 / m.gy);
+  return dim3((unsigned)std::max<long long>(1, std::min(gx, cap)), (unsigned)m.gy, 1);
+}
+template <int NACC, int V> static inline size_t red_smem() { return (size_t)8 * 32 * NACC * V * sizeof(float); }
+
+// 16-byte channel vectors need: unit channel stride, C % V == 0, 16-byte aligned base and pixel strides
+template <typename T>
+static bool vec_ok(const dc_view& v) {
+  const int V = vec16<T>::V;
+  return v.sc == 1 && (v.c % V == 0) && (v.sn % V == 0) && (v.sh % V == 0) && (v.sw % V == 0) &&
+         ((reinterpret_cast<uintptr_t>(v.ptr) % 16) == 0);
+}
 
 template <typename T>
-static int bn_stats_t(const dc_view& y, double* sums, cudaStream_t st) {
-  ChanGrid g = chan_grid(y.c, (long long)y.n * y.h * y.w);
-  bn_stats_kernel<T><<<g.grid, 256, red_smem(g, 2), st>>>(make_view<const T>(y), sums, g.cvb, g.rows);
+static int bn_stats_t(const dc_bn_params& p, const dc_view& y, cudaStream_t st) {
+  constexpr int V = vec16<T>::V;
+  const long long npix = (long long)y.n * y.h * y.w;
+  LaneMap m = lane_map(y.c, V);
+  dim3 grid = bn_grid(m, npix, 4 * kUnroll);
+  bn_stats_kernel<T, V><<<grid, kBnThreads, red_smem<2, V>(), st>>>(p, pix_view<const T>(y), y.c, npix, m);
   return launch_status("dc_bn_stats");
 }
 template <typename T>
 static int bn_apply_t(const dc_bn_params& p, const dc_view& y, const dc_view& res, const dc_view& out, cudaStream_t st) {
-  ChanGrid g = chan_grid(y.c, (long long)y.n * y.h * y.w);
-  View<const T> r = make_view<const T>(res);
-  bn_apply_kernel<T><<<g.grid, 256, 0, st>>>(p, make_view<const T>(y), r, make_view<T>(out), g.cvb, g.rows);
+  constexpr int V = vec16<T>::V;
+  const long long npix = (long long)y.n * y.h * y.w;
+  LaneMap m = lane_map(y.c, V);
+  dim3 grid = bn_grid(m, npix, kUnroll);
+  bn_apply_kernel<T, V><<<grid, kBnThreads, 0, st>>>(p, pix_view<const T>(y), pix_view<const T>(res), pix_view<T>(out), y.c, npix, m);
   return launch_status("dc_bn_apply");
 }
 template <typename T>
-static int bn_bwd_reduce_t(const dc_bn_params& p, const dc_view& dout, const dc_view& out, const dc_view& y, double* rs, cudaStream_t st) {
-  ChanGrid g = chan_grid(y.c, (long long)y.n * y.h * y.w);
-  bn_bwd_reduce_kernel<T><<<g.grid, 256, red_smem(g, 2), st>>>(p, make_view<const T>(dout), make_view<const T>(out),
-                                                               make_view<const T>(y), rs, g.cvb, g.rows);
+static int bn_bwd_reduce_t(const dc_bn_params& p, const dc_view& dout, const dc_view& out, const dc_view& y, void* rws,
+                           float* dgamma, float* dbeta, cudaStream_t st) {
+  constexpr int V = vec16<T>::V;
+  const long long npix = (long long)y.n * y.h * y.w;
+  LaneMap m = lane_map(y.c, V);
+  dim3 grid = bn_grid(m, npix, 4 * kUnroll);
+  bn_bwd_reduce_kernel<T, V><<<grid, kBnThreads, red_smem<2, V>(), st>>>(p, pix_view<const T>(dout), pix_view<const T>(out),
+                                                                         pix_view<const T>(y), rws, dgamma, dbeta, y.c, npix, m);
   return launch_status("dc_bn_bwd_reduce");
 }
 template <typename T>
-static int bn_bwd_apply_t(const dc_bn_params& p, const dc_view& dout, const dc_view& out, const dc_view& y, const double* rs,
-                          const dc_view& dy, const dc_view& dres, float* dgamma, float* dbeta, cudaStream_t st) {
-  ChanGrid g = chan_grid(dout.c, (long long)dout.n * dout.h * dout.w);
-  bn_bwd_apply_kernel<T><<<g.grid, 256, 0, st>>>(p, make_view<const T>(dout), make_view<const T>(out), make_view<const T>(y), rs,
-                                                 make_view<T>(dy), make_view<T>(dres), dgamma, dbeta, g.cvb, g.rows);
+static int bn_bwd_apply_t(const dc_bn_params& p, const dc_view& dout, const dc_view& out, const dc_view& y, const void* rws,
+                          const dc_view& dy, const dc_view& dres, cudaStream_t st) {
+  constexpr int V = vec16<T>::V;
+  const long long npix = (long long)dout.n * dout.h * dout.w;
+  LaneMap m = lane_map(dout.c, V);
+  dim3 grid = bn_grid(m, npix, kUnroll);
+  bn_bwd_apply_kernel<T, V><<<grid, kBnThreads, 0, st>>>(p, pix_view<const T>(dout), pix_view<const T>(out), pix_view<const T>(y), rws,
+                                                         pix_view<T>(dy), pix_view<T>(dres), dout.c, npix, m);
   return launch_status("dc_bn_bwd_apply");
 }
 
@@ -299,25 +520,43 @@ static int bn_bwd_apply_t(const dc_bn_params& p, const dc_view& dout, const dc_v
 
 using namespace dc;
 
-static bool opt_view_ok(const dc_view& v, const dc_view& like) {
+template <typename T>
+static bool opt_ok(const dc_view& v, const dc_view& like) {
   if (v.ptr == nullptr) return true;
-  return view_ok(v) && view_vec4(v) && same_shape(v, like) && v.dtype == like.dtype;
+  return view_ok(v) && vec_ok<T>(v) && same_shape(v, like) && v.dtype == like.dtype;
+}
+#define DC_BN_DISPATCH(view_, expr_f32, expr_bf16) ((view_).dtype == DC_F32 ? (expr_f32) : (expr_bf16))
+
+static bool views_ok(const dc_view& main, const dc_view* opts, int nopt) {
+  if (!view_ok(main)) return false;
+  if (main.dtype == DC_F32) {
+    if (!vec_ok<float>(main)) return false;
+    for (int i = 0; i < nopt; ++i) if (!opt_ok<float>(opts[i], main)) return false;
+  } else {
+    if (!vec_ok<__nv_bfloat16>(main)) return false;
+    for (int i = 0; i < nopt; ++i) if (!opt_ok<__nv_bfloat16>(opts[i], main)) return false;
+  }
+  return true;
 }
 
 extern "C" {
 
-int dc_bn_stats(dc_view y, double* sums, void* stream) {
-  DC_REQUIRE(view_ok(y) && view_vec4(y), "dc_bn_stats: view must be channel-contiguous with C %% 4 == 0");
-  DC_REQUIRE(sums != nullptr, "dc_bn_stats: null sums");
+size_t dc_bn_ws_bytes(int C) { return (size_t)32 * C + 16; }
+
+int dc_bn_stats(const dc_bn_params* p, dc_view y, void* stream) {
+  DC_REQUIRE(p != nullptr && p->sums != nullptr, "dc_bn_stats: null params / workspace");
+  DC_REQUIRE(views_ok(y, nullptr, 0), "dc_bn_stats: view must be channel-contiguous, 16-byte aligned, C %% 8 == 0 (bf16) / C %% 4 == 0 (fp32)");
+  DC_REQUIRE(p->gamma && p->beta, "dc_bn_stats: gamma/beta required");
+  DC_REQUIRE(p->count > 1.0, "dc_bn_stats: Expected more than 1 value per channel when training (count=%g)", p->count);
+  DC_REQUIRE((p->running_mean == nullptr) == (p->running_var == nullptr), "dc_bn_stats: running_mean and running_var go together");
   cudaStream_t st = as_stream(stream);
-  return y.dtype == DC_F32 ? bn_stats_t<float>(y, sums, st) : bn_stats_t<__nv_bfloat16>(y, sums, st);
+  return y.dtype == DC_F32 ? bn_stats_t<float>(*p, y, st) : bn_stats_t<__nv_bfloat16>(*p, y, st);
 }
 
 int dc_bn_apply(const dc_bn_params* p, dc_view y, dc_view residual, dc_view out, void* stream) {
   DC_REQUIRE(p != nullptr, "dc_bn_apply: null params");
-  DC_REQUIRE(view_ok(y) && view_vec4(y), "dc_bn_apply: bad y view");
-  DC_REQUIRE(view_ok(out) && opt_view_ok(out, y), "dc_bn_apply: bad out view");
-  DC_REQUIRE(opt_view_ok(residual, y), "dc_bn_apply: bad residual view");
+  const dc_view opts[2] = {out, residual};
+  DC_REQUIRE(view_ok(out) && views_ok(y, opts, 2), "dc_bn_apply: views must be channel-contiguous, 16-byte aligned and of one shape/dtype");
   if (!(p->flags & DC_BN_IDENTITY)) {
     DC_REQUIRE(p->gamma && p->beta, "dc_bn_apply: gamma/beta required");
     if (p->flags & DC_BN_TRAIN) {
@@ -331,41 +570,47 @@ int dc_bn_apply(const dc_bn_params* p, dc_view y, dc_view residual, dc_view out,
   return y.dtype == DC_F32 ? bn_apply_t<float>(*p, y, residual, out, st) : bn_apply_t<__nv_bfloat16>(*p, y, residual, out, st);
 }
 
-int dc_bn_bwd_reduce(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, double* rsums, void* stream) {
-  DC_REQUIRE(p != nullptr && rsums != nullptr, "dc_bn_bwd_reduce: null argument");
-  DC_REQUIRE(view_ok(y) && view_vec4(y) && opt_view_ok(dout, y) && view_ok(dout), "dc_bn_bwd_reduce: bad views");
-  if (p->flags & DC_BN_RELU) DC_REQUIRE(view_ok(out) && opt_view_ok(out, y), "dc_bn_bwd_reduce: out view required for ReLU mask");
+int dc_bn_bwd_reduce(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, void* rws, float* dgamma, float* dbeta,
+                     void* stream) {
+  DC_REQUIRE(p != nullptr && rws != nullptr, "dc_bn_bwd_reduce: null argument");
+  const dc_view opts[2] = {dout, out};
+  DC_REQUIRE(view_ok(dout) && views_ok(y, opts, 2), "dc_bn_bwd_reduce: bad views");
+  if (p->flags & DC_BN_RELU) DC_REQUIRE(view_ok(out), "dc_bn_bwd_reduce: out view required for ReLU mask");
+  DC_REQUIRE(p->gamma != nullptr, "dc_bn_bwd_reduce: gamma required");
+  if (p->flags & DC_BN_TRAIN) DC_REQUIRE(p->sums != nullptr, "dc_bn_bwd_reduce: forward workspace required in train mode");
+  else DC_REQUIRE(p->running_mean && p->running_var, "dc_bn_bwd_reduce: running statistics required in eval mode");
   cudaStream_t st = as_stream(stream);
-  return y.dtype == DC_F32 ? bn_bwd_reduce_t<float>(*p, dout, out, y, rsums, st)
-                           : bn_bwd_reduce_t<__nv_bfloat16>(*p, dout, out, y, rsums, st);
+  return y.dtype == DC_F32 ? bn_bwd_reduce_t<float>(*p, dout, out, y, rws, dgamma, dbeta, st)
+                           : bn_bwd_reduce_t<__nv_bfloat16>(*p, dout, out, y, rws, dgamma, dbeta, st);
 }
 
-int dc_bn_bwd_apply(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, const double* rsums, dc_view dy,
-                    dc_view dres, float* dgamma, float* dbeta, void* stream) {
+int dc_bn_bwd_apply(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, const void* rws, dc_view dy, dc_view dres,
+                    void* stream) {
   DC_REQUIRE(p != nullptr, "dc_bn_bwd_apply: null params");
-  DC_REQUIRE(view_ok(dout) && view_vec4(dout), "dc_bn_bwd_apply: bad dout view");
-  DC_REQUIRE(opt_view_ok(dy, dout) && opt_view_ok(dres, dout), "dc_bn_bwd_apply: bad dy/dres view");
-  if (p->flags & DC_BN_RELU) DC_REQUIRE(view_ok(out) && opt_view_ok(out, dout), "dc_bn_bwd_apply: out view required for ReLU mask");
-  if (!(p->flags & DC_BN_IDENTITY)) {
-    DC_REQUIRE(rsums != nullptr && view_ok(y) && opt_view_ok(y, dout), "dc_bn_bwd_apply: y and rsums required");
-    DC_REQUIRE(p->gamma && p->beta, "dc_bn_bwd_apply: gamma/beta required");
-  }
+  const dc_view opts[4] = {dy, dres, out, y};
+  DC_REQUIRE(views_ok(dout, opts, 4), "dc_bn_bwd_apply: views must be channel-contiguous, 16-byte aligned and of one shape/dtype");
+  if (p->flags & DC_BN_RELU) DC_REQUIRE(view_ok(out), "dc_bn_bwd_apply: out view required for ReLU mask");
+  if (!(p->flags & DC_BN_IDENTITY) && dy.ptr != nullptr)
+    DC_REQUIRE(rws != nullptr && view_ok(y), "dc_bn_bwd_apply: y and the backward workspace are required");
   cudaStream_t st = as_stream(stream);
-  return dout.dtype == DC_F32 ? bn_bwd_apply_t<float>(*p, dout, out, y, rsums, dy, dres, dgamma, dbeta, st)
-                              : bn_bwd_apply_t<__nv_bfloat16>(*p, dout, out, y, rsums, dy, dres, dgamma, dbeta, st);
+  return dout.dtype == DC_F32 ? bn_bwd_apply_t<float>(*p, dout, out, y, rws, dy, dres, st)
+                              : bn_bwd_apply_t<__nv_bfloat16>(*p, dout, out, y, rws, dy, dres, st);
 }
 
 /* channel sum with a caller-provided double workspace of C elements */
 int dc_channel_sum(dc_view x, double* ws_c, float* out_c, void* stream) {
-  DC_REQUIRE(view_ok(x) && view_vec4(x) && out_c != nullptr && ws_c != nullptr, "dc_channel_sum: bad arguments");
+  DC_REQUIRE(views_ok(x, nullptr, 0) && out_c != nullptr && ws_c != nullptr, "dc_channel_sum: bad arguments");
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(ws_c, 0, sizeof(double) * x.c, st);
   if (e != cudaSuccess) return dc::fail((int)e, "dc_channel_sum: %s", cudaGetErrorString(e));
-  ChanGrid g = chan_grid(x.c, (long long)x.n * x.h * x.w);
-  if (x.dtype == DC_F32)
-    channel_sum_kernel<float><<<g.grid, 256, red_smem(g, 1), st>>>(make_view<const float>(x), ws_c, g.cvb, g.rows);
-  else
-    channel_sum_kernel<__nv_bfloat16><<<g.grid, 256, red_smem(g, 1), st>>>(make_view<const __nv_bfloat16>(x), ws_c, g.cvb, g.rows);
+  const long long npix = (long long)x.n * x.h * x.w;
+  if (x.dtype == DC_F32) {
+    LaneMap m = lane_map(x.c, 4);
+    channel_sum_kernel<float, 4><<<bn_grid(m, npix, 8), kBnThreads, red_smem<1, 4>(), st>>>(pix_view<const float>(x), ws_c, x.c, npix, m);
+  } else {
+    LaneMap m = lane_map(x.c, 8);
+    channel_sum_kernel<__nv_bfloat16, 8><<<bn_grid(m, npix, 8), kBnThreads, red_smem<1, 8>(), st>>>(pix_view<const __nv_bfloat16>(x), ws_c, x.c, npix, m);
+  }
   double_to_float_kernel<<<ceil_div(x.c, 256), 256, 0, st>>>(ws_c, out_c, x.c);
   return launch_status("dc_channel_sum");
 }

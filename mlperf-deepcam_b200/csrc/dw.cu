@@ -3,174 +3,536 @@
 //   fwd : out[n,y,x,c]  = sum_{kh,kw} in[n, y*s - d + kh*d, x*s - d + kw*d, c] * w[kh*3+kw][c]
 //   bwdD: din[n,h,w,c]  = sum_{kh,kw} dout[n, (h + d - kh*d)/s, (w + d - kw*d)/s, c] * w[kh*3+kw][c]   (when divisible)
 //   bwdW: G[kh*3+kw][c] = sum_{n,y,x} in[n, y*s - d + kh*d, x*s - d + kw*d, c] * dout[n,y,x,c]
-// HBM-bound (AI ~ 4 FLOP/B): algorithmic bytes = in + out (+ 9*C weights); neighbours are served from L1/L2.
+// HBM-bound (AI ~ 4 FLOP/B): algorithmic bytes = in + out (+ 9*C weights).
+//
+// Thread mapping: a thread owns one 16-byte channel vector (V = 8 bf16 / 4 fp32) of one pixel COLUMN and walks down
+// the rows of a strip; the 32 lanes of a warp cover 32 consecutive channel vectors of a pixel (512 contiguous bytes)
+// or several consecutive pixels when a pixel has fewer vectors; the 8 warps of a block sit on consecutive pixels,
+// so the x-1 / x+1 taps are L1 hits.  The stride-1 dilation-1 kernels (59 of the 63 layers, and every backward-data
+// of a stride-1 layer = the same kernel with the 3x3 filter flipped) are input-stationary: each input row is loaded
+// and unpacked once per strip and scattered into the three live output rows with packed fp32 FMAs (FFMA2).
 #include "common.cuh"
 #include <algorithm>
 
 namespace dc {
 
-__device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w) {
-  a.x = fmaf(x.x, w.x, a.x); a.y = fmaf(x.y, w.y, a.y); a.z = fmaf(x.z, w.z, a.z); a.w = fmaf(x.w, w.w, a.w);
+// ---- 16-byte channel vectors -------------------------------------------------------------------------------
+template <typename T> struct dwvec;
+template <> struct dwvec<float> {
+  static constexpr int V = 4;
+  __device__ static __forceinline__ void unpack(const uint4& t, float (&f)[4]) {
+    f[0] = __uint_as_float(t.x); f[1] = __uint_as_float(t.y); f[2] = __uint_as_float(t.z); f[3] = __uint_as_float(t.w);
+  }
+  __device__ static __forceinline__ uint4 pack(const float (&f)[4]) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+  }
+};
+template <> struct dwvec<__nv_bfloat16> {
+  static constexpr int V = 8;
+  __device__ static __forceinline__ void unpack(const uint4& t, float (&f)[8]) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f[2 * j] = __uint_as_float(w[j] << 16); f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+  }
+  __device__ static __forceinline__ uint4 pack(const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&b);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+// channel pairs as float2 (operands of the packed fp32 FMA, FFMA2 on sm_100)
+template <typename T> struct dwpair;
+template <> struct dwpair<float> {
+  static constexpr int VP = 2;
+  __device__ static __forceinline__ void unpack(const uint4& t, float2 (&f)[2]) {
+    f[0] = make_float2(__uint_as_float(t.x), __uint_as_float(t.y));
+    f[1] = make_float2(__uint_as_float(t.z), __uint_as_float(t.w));
+  }
+  __device__ static __forceinline__ uint4 pack(const float2 (&f)[2]) {
+    return make_uint4(__float_as_uint(f[0].x), __float_as_uint(f[0].y), __float_as_uint(f[1].x), __float_as_uint(f[1].y));
+  }
+};
+template <> struct dwpair<__nv_bfloat16> {
+  static constexpr int VP = 4;
+  __device__ static __forceinline__ void unpack(const uint4& t, float2 (&f)[4]) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f[j] = make_float2(__uint_as_float(w[j] << 16), __uint_as_float(w[j] & 0xffff0000u));
+  }
+  __device__ static __forceinline__ uint4 pack(const float2 (&f)[4]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 b = __floats2bfloat162_rn(f[j].x, f[j].y);
+      w[j] = *reinterpret_cast<uint32_t*>(&b);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+__device__ __forceinline__ float2 fma2(const float2& a, const float2& b, const float2& c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(const float2& a, const float2& b) { return __fmul2_rn(a, b); }
+
+__device__ __forceinline__ uint4 ld16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void st16(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+struct DwMap {
+  int cv, cvp, ppw, ppb, gy;   // channel vectors / lanes per pixel / pixels per warp / pixels per block / channel blocks
+  int rs, nstrips;             // rows per strip, strips per image
+};
+static inline DwMap dw_map(int C, int V, int rows, int cols, int n_img, int target_blocks, int min_rs) {
+  DwMap m;
+  m.cv = C / V;
+  m.cvp = 1;
+  while (m.cvp < 32 && m.cvp < m.cv) m.cvp <<= 1;
+  m.ppw = 32 / m.cvp;
+  m.ppb = 8 * m.ppw;
+  m.gy = ceil_div(m.cv, m.cvp);
+  const long long per_strip = (long long)ceil_div(cols, m.ppb) * m.gy * n_img;
+  int ns = (int)std::max<long long>(1, target_blocks / std::max<long long>(1, per_strip));
+  ns = std::min(ns, std::max(1, rows / min_rs));
+  m.rs = ceil_div(rows, ns);
+  m.nstrips = ceil_div(rows, m.rs);
+  return m;
 }
 
-// One thread = one output pixel x 4 channels.  Threads of a warp cover consecutive channel vectors of the
-// same pixel, consecutive warps cover consecutive pixels along w (so the 3x3 halo hits L1).
 template <typename T>
-__global__ void __launch_bounds__(256) dw_fwd_kernel(View<const T> in, const T* __restrict__ w9c, int s, int d, View<T> out) {
-  const int cv = out.c >> 2;
-  const long long total = (long long)out.n * out.h * out.w * cv;
-  for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < total;
-       item += (long long)gridDim.x * blockDim.x) {
-    int c4 = (int)(item % cv);
-    int pix = (int)(item / cv);
-    int x = pix % out.w;
-    int t = pix / out.w;
-    int y = t % out.h;
-    int n = t / out.h;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+struct DwView {
+  T* p;
+  int h, w;
+  long long sn, sh, sw;
+};
+template <typename T>
+static inline DwView<T> dw_view(const dc_view& v) {
+  DwView<T> r;
+  r.p = reinterpret_cast<T*>(v.ptr);
+  r.h = v.h; r.w = v.w; r.sn = v.sn; r.sh = v.sh; r.sw = v.sw;
+  return r;
+}
+
+constexpr int kDwThreads = 256;
+
+// common thread decode
+struct DwLane {
+  int cvi, x, n, y0, y1;
+  bool ok;
+};
+__device__ __forceinline__ DwLane dw_lane(const DwMap& m, int rows, int cols) {
+  DwLane l;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
+  l.cvi = blockIdx.y * m.cvp + cvl;
+  l.x = (blockIdx.x * 8 + warp) * m.ppw + psub;
+  l.n = blockIdx.z / m.nstrips;
+  const int strip = blockIdx.z - l.n * m.nstrips;
+  l.y0 = strip * m.rs;
+  l.y1 = min(rows, l.y0 + m.rs);
+  l.ok = (l.cvi < m.cv) && (l.x < cols);
+  return l;
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void load_weights(const T* __restrict__ w9c, int C, int c0, bool flip, float (&wv)[9][V]) {
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      int ih = y * s - d + kh * d;
-      if (ih < 0 || ih >= in.h) continue;
+  for (int k = 0; k < 9; ++k) dwvec<T>::unpack(ld16(w9c + (size_t)(flip ? 8 - k : k) * C + c0), wv[k]);
+}
+
+// ---- stride 1, dilation 1 (forward, and backward-data with flip = 1): input-stationary row walk ----------------------
+// Every input row is loaded and unpacked ONCE; its three vectors update the three live output rows (r+1, r, r-1) with
+// packed fp32 FMAs, then output row r-1 is complete and stored.  No im2col, no padded copy, ~70 instructions per
+// 8-channel output instead of ~165 for the gather form, so the kernel stays HBM-bound.
+template <typename T, int V>
+__global__ void __launch_bounds__(kDwThreads) dw_s1d1_kernel(DwView<const T> in, const T* __restrict__ w9c, DwView<T> out, int C,
+                                                             DwMap m, int flip, int accumulate) {
+  constexpr int VP = V / 2;
+  const DwLane l = dw_lane(m, out.h, out.w);
+  if (!l.ok) return;
+  const int c0 = l.cvi * V;
+  float2 wv[9][VP];
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        int iw = x * s - d + kw * d;
-        if (iw < 0 || iw >= in.w) continue;
-        float4 v = elem<T>::ld4(in.at(n, ih, iw) + c4 * 4);
-        float4 wv = elem<T>::ld4(w9c + (kh * 3 + kw) * out.c + c4 * 4);
-        fma4(acc, v, wv);
-      }
+  for (int k = 0; k < 9; ++k) dwpair<T>::unpack(ld16(w9c + (size_t)(flip ? 8 - k : k) * C + c0), wv[k]);
+  const int H = in.h, W = in.w;
+  const T* base = in.p + l.n * in.sn + (long long)l.x * in.sw + c0;
+  T* obase = out.p + l.n * out.sn + (long long)l.x * out.sw + c0;
+  const bool xl = l.x >= 1, xr = l.x + 1 < W;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  auto ldrow = [&](int r, uint4 (&v)[3]) {
+    if (r < 0 || r >= H) { v[0] = zero; v[1] = zero; v[2] = zero; return; }
+    const T* rp = base + (long long)r * in.sh;
+    v[1] = ld16(rp);
+    v[0] = xl ? ld16(rp - in.sw) : zero;
+    v[2] = xr ? ld16(rp + in.sw) : zero;
+  };
+  // A = output row r-1 (receives filter row 2 and is finished), B = output row r (filter row 1), Cn = output row r+1
+  // (filter row 0, first contribution)
+  auto step = [&](int r, const uint4 (&v)[3], float2 (&A)[VP], float2 (&B)[VP], float2 (&Cn)[VP]) {
+    float2 f[3][VP];
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) dwpair<T>::unpack(v[kw], f[kw]);
+#pragma unroll
+    for (int j = 0; j < VP; ++j) {
+      Cn[j] = mul2(f[0][j], wv[0][j]);
+      Cn[j] = fma2(f[1][j], wv[1][j], Cn[j]);
+      Cn[j] = fma2(f[2][j], wv[2][j], Cn[j]);
+      B[j] = fma2(f[0][j], wv[3][j], B[j]);
+      B[j] = fma2(f[1][j], wv[4][j], B[j]);
+      B[j] = fma2(f[2][j], wv[5][j], B[j]);
+      A[j] = fma2(f[0][j], wv[6][j], A[j]);
+      A[j] = fma2(f[1][j], wv[7][j], A[j]);
+      A[j] = fma2(f[2][j], wv[8][j], A[j]);
     }
-    elem<T>::st4(out.at(n, y, x) + c4 * 4, acc);
+    const int y = r - 1;
+    if (y >= l.y0 && y < l.y1) {
+      T* op = obase + (long long)y * out.sh;
+      if (accumulate) {
+        float2 old[VP];
+        dwpair<T>::unpack(ld16(op), old);
+#pragma unroll
+        for (int j = 0; j < VP; ++j) { A[j].x += old[j].x; A[j].y += old[j].y; }
+      }
+      st16(op, dwpair<T>::pack(A));
+    }
+  };
+  float2 a0[VP], a1[VP], a2[VP];
+#pragma unroll
+  for (int j = 0; j < VP; ++j) { a0[j] = make_float2(0.f, 0.f); a1[j] = a0[j]; a2[j] = a0[j]; }
+  uint4 cur[3], nxt[3];
+  int r = l.y0 - 1;
+  ldrow(r, cur);
+  while (true) {
+    ldrow(r + 1, nxt);
+    step(r, cur, a0, a1, a2);
+    if (++r > l.y1) break;
+    ldrow(r + 1, cur);
+    step(r, nxt, a1, a2, a0);
+    if (++r > l.y1) break;
+    ldrow(r + 1, nxt);
+    step(r, cur, a2, a0, a1);
+    if (++r > l.y1) break;
+    ldrow(r + 1, cur);
+    step(r, nxt, a0, a1, a2);
+    if (++r > l.y1) break;
+    ldrow(r + 1, nxt);
+    step(r, cur, a1, a2, a0);
+    if (++r > l.y1) break;
+    ldrow(r + 1, cur);
+    step(r, nxt, a2, a0, a1);
+    if (++r > l.y1) break;
+    // after six steps the accumulator roles are back to (a0, a1, a2) and `cur` holds row r again
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) dw_bwd_data_kernel(View<const T> dout, const T* __restrict__ w9c, int s, int d,
-                                                          View<T> din, int accumulate) {
-  const int cv = din.c >> 2;
-  const long long total = (long long)din.n * din.h * din.w * cv;
-  for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < total;
-       item += (long long)gridDim.x * blockDim.x) {
-    int c4 = (int)(item % cv);
-    int pix = (int)(item / cv);
-    int x = pix % din.w;
-    int t = pix / din.w;
-    int y = t % din.h;
-    int n = t / din.h;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+// ---- generic stride / dilation forward (and stride-1 backward-data with flip): nine direct taps ----------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(kDwThreads) dw_direct_kernel(DwView<const T> in, const T* __restrict__ w9c, DwView<T> out, int C,
+                                                               DwMap m, int s, int d, int flip, int accumulate) {
+  const DwLane l = dw_lane(m, out.h, out.w);
+  if (!l.ok) return;
+  const int c0 = l.cvi * V;
+  float wv[9][V];
+  load_weights<T, V>(w9c, C, c0, flip != 0, wv);
+  const T* base = in.p + l.n * in.sn + c0;
+  T* obase = out.p + l.n * out.sn + (long long)l.x * out.sw + c0;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  int ix[3];
+  bool vx[3];
+#pragma unroll
+  for (int kw = 0; kw < 3; ++kw) { ix[kw] = l.x * s - d + kw * d; vx[kw] = ix[kw] >= 0 && ix[kw] < in.w; }
+  for (int y = l.y0; y < l.y1; ++y) {
+    uint4 t[9];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
-      int ty = y + d - kh * d;
+      const int ih = y * s - d + kh * d;
+      const bool vy = ih >= 0 && ih < in.h;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+        t[kh * 3 + kw] = (vy && vx[kw]) ? ld16(base + (long long)ih * in.sh + (long long)ix[kw] * in.sw) : zero;
+    }
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float f[V];
+      dwvec<T>::unpack(t[k], f);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = fmaf(f[j], wv[k][j], acc[j]);
+    }
+    T* op = obase + (long long)y * out.sh;
+    if (accumulate) {
+      float old[V];
+      dwvec<T>::unpack(ld16(op), old);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += old[j];
+    }
+    st16(op, dwvec<T>::pack(acc));
+  }
+}
+
+// ---- backward-data of a stride-2 layer: gather over the taps whose parity matches ----------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(kDwThreads) dw_bwd_data_strided_kernel(DwView<const T> dout, const T* __restrict__ w9c, DwView<T> din,
+                                                                         int C, DwMap m, int s, int d, int accumulate) {
+  const DwLane l = dw_lane(m, din.h, din.w);
+  if (!l.ok) return;
+  const int c0 = l.cvi * V;
+  float wv[9][V];
+  load_weights<T, V>(w9c, C, c0, false, wv);
+  const T* base = dout.p + l.n * dout.sn + c0;
+  T* obase = din.p + l.n * din.sn + (long long)l.x * din.sw + c0;
+  int ox[3];
+  bool vx[3];
+#pragma unroll
+  for (int kw = 0; kw < 3; ++kw) {
+    const int tx = l.x + d - kw * d;
+    ox[kw] = tx / s;
+    vx[kw] = tx >= 0 && (tx % s) == 0 && ox[kw] < dout.w;
+  }
+  for (int y = l.y0; y < l.y1; ++y) {
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ty = y + d - kh * d;
       if (ty < 0 || (ty % s) != 0) continue;
-      int oy = ty / s;
+      const int oy = ty / s;
       if (oy >= dout.h) continue;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        int tx = x + d - kw * d;
-        if (tx < 0 || (tx % s) != 0) continue;
-        int ox = tx / s;
-        if (ox >= dout.w) continue;
-        float4 v = elem<T>::ld4(dout.at(n, oy, ox) + c4 * 4);
-        float4 wv = elem<T>::ld4(w9c + (kh * 3 + kw) * din.c + c4 * 4);
-        fma4(acc, v, wv);
+        if (!vx[kw]) continue;
+        float f[V];
+        dwvec<T>::unpack(ld16(base + (long long)oy * dout.sh + (long long)ox[kw] * dout.sw), f);
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = fmaf(f[j], wv[kh * 3 + kw][j], acc[j]);
       }
     }
-    T* dp = din.at(n, y, x) + c4 * 4;
+    T* op = obase + (long long)y * din.sh;
     if (accumulate) {
-      float4 old = elem<T>::ld4(dp);
-      acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+      float old[V];
+      dwvec<T>::unpack(ld16(op), old);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += old[j];
     }
-    elem<T>::st4(dp, acc);
+    st16(op, dwvec<T>::pack(acc));
   }
 }
 
-// Weight gradient: channel lanes x pixel lanes (see bn.cu), 9 taps x 4 channels of fp32 partials per thread,
-// block reduction through shared memory, one fp32 atomicAdd per (tap, channel) per block.
-template <typename T>
-__global__ void __launch_bounds__(256) dw_bwd_weight_kernel(View<const T> in, View<const T> dout, int s, int d,
-                                                            float* __restrict__ G, int cvb, int rows) {
-  extern __shared__ float redf[];   // [rows][cvb*4*9]
-  const int tx = threadIdx.x % cvb, ty = threadIdx.x / cvb;
-  const int c4 = blockIdx.y * cvb + tx;
-  const int C = dout.c;
-  const bool ok = (ty < rows) && (c4 * 4 < C);
-  const int npix = dout.n * dout.h * dout.w;
-  float4 acc[9];
+// ---- weight gradient -------------------------------------------------------------------------------------------------
+// Per-thread 9 x V fp32 partial sums over its column strip; reduction across the pixel lanes of the block in three passes
+// (one filter row each) through shared memory, then one fp32 atomicAdd per (tap, channel) per block.
+template <int V>
+__device__ __forceinline__ void dw_reduce_G(float (&G)[9][V], float* __restrict__ Gout, int C, const DwMap& m, int cvi_base) {
+  extern __shared__ float red[];                       // [8 warps][32 lanes][3*V]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = m.cvp; o < 32; o <<= 1) {
 #pragma unroll
-  for (int k = 0; k < 9; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ok) {
-    for (int pix = blockIdx.x * rows + ty; pix < npix; pix += gridDim.x * rows) {
-      int x = pix % dout.w;
-      int t = pix / dout.w;
-      int y = t % dout.h;
-      int n = t / dout.h;
-      float4 g = elem<T>::ld4(dout.at(n, y, x) + c4 * 4);
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int j = 0; j < V; ++j) G[k][j] += __shfl_xor_sync(0xffffffffu, G[k][j], o);
+  }
+  constexpr int PER = 3 * V;
+  const int cv_count = min(m.cvp, m.cv - cvi_base);
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    if (kh) __syncthreads();
+    if (lane < m.cvp) {
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int j = 0; j < V; ++j) red[(warp * 32 + lane) * PER + kw * V + j] = G[kh * 3 + kw][j];
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < m.cvp * PER; col += kDwThreads) {
+      const int ln = col / PER, r = col - ln * PER;
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[(w * 32 + ln) * PER + r];
+      const int kw = r / V, j = r - kw * V;
+      if (ln < cv_count) atomicAdd(Gout + (size_t)(kh * 3 + kw) * C + (cvi_base + ln) * V + j, s);
+    }
+  }
+}
+
+// input-stationary like dw_s1d1_kernel: input row r meets dout rows r+1 (filter row 0), r (row 1), r-1 (row 2)
+template <typename T, int V>
+__global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_s1d1_kernel(DwView<const T> in, DwView<const T> dout, float* __restrict__ Gout,
+                                                                        int C, DwMap m) {
+  constexpr int VP = V / 2;
+  const DwLane l = dw_lane(m, dout.h, dout.w);
+  float2 G2[9][VP];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int j = 0; j < VP; ++j) G2[k][j] = make_float2(0.f, 0.f);
+  if (l.ok) {
+    const int c0 = l.cvi * V;
+    const int H = in.h, W = in.w;
+    const T* base = in.p + l.n * in.sn + (long long)l.x * in.sw + c0;
+    const T* gbase = dout.p + l.n * dout.sn + (long long)l.x * dout.sw + c0;
+    const bool xl = l.x >= 1, xr = l.x + 1 < W;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    auto ldrow = [&](int r, uint4 (&v)[4]) {          // v[0..2]: input row r at x-1, x, x+1; v[3]: dout row r+1
+      if (r < 0 || r >= H) { v[0] = zero; v[1] = zero; v[2] = zero; }
+      else {
+        const T* rp = base + (long long)r * in.sh;
+        v[1] = ld16(rp);
+        v[0] = xl ? ld16(rp - in.sw) : zero;
+        v[2] = xr ? ld16(rp + in.sw) : zero;
+      }
+      const int y = r + 1;
+      v[3] = (y >= l.y0 && y < l.y1) ? ld16(gbase + (long long)y * dout.sh) : zero;
+    };
+    // gM = dout row r-1, gC = dout row r, gP = dout row r+1 (unpacked here)
+    auto step = [&](const uint4 (&v)[4], const float2 (&gM)[VP], const float2 (&gC)[VP], float2 (&gP)[VP]) {
+      float2 f[3][VP];
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) dwpair<T>::unpack(v[kw], f[kw]);
+      dwpair<T>::unpack(v[3], gP);
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int j = 0; j < VP; ++j) {
+          G2[kw][j] = fma2(f[kw][j], gP[j], G2[kw][j]);
+          G2[3 + kw][j] = fma2(f[kw][j], gC[j], G2[3 + kw][j]);
+          G2[6 + kw][j] = fma2(f[kw][j], gM[j], G2[6 + kw][j]);
+        }
+    };
+    float2 g0[VP], g1[VP], g2[VP];
+#pragma unroll
+    for (int j = 0; j < VP; ++j) { g0[j] = make_float2(0.f, 0.f); g1[j] = g0[j]; g2[j] = g0[j]; }
+    uint4 cur[4], nxt[4];
+    int r = l.y0 - 1;
+    ldrow(r, cur);
+    while (true) {
+      ldrow(r + 1, nxt);
+      step(cur, g0, g1, g2);
+      if (++r > l.y1) break;
+      ldrow(r + 1, cur);
+      step(nxt, g1, g2, g0);
+      if (++r > l.y1) break;
+      ldrow(r + 1, nxt);
+      step(cur, g2, g0, g1);
+      if (++r > l.y1) break;
+      ldrow(r + 1, cur);
+      step(nxt, g0, g1, g2);
+      if (++r > l.y1) break;
+      ldrow(r + 1, nxt);
+      step(cur, g1, g2, g0);
+      if (++r > l.y1) break;
+      ldrow(r + 1, cur);
+      step(nxt, g2, g0, g1);
+      if (++r > l.y1) break;
+    }
+  }
+  float G[9][V];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int j = 0; j < VP; ++j) { G[k][2 * j] = G2[k][j].x; G[k][2 * j + 1] = G2[k][j].y; }
+  dw_reduce_G<V>(G, Gout, C, m, blockIdx.y * m.cvp);
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_direct_kernel(DwView<const T> in, DwView<const T> dout, float* __restrict__ Gout,
+                                                                          int C, DwMap m, int s, int d) {
+  const DwLane l = dw_lane(m, dout.h, dout.w);
+  float G[9][V];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int j = 0; j < V; ++j) G[k][j] = 0.f;
+  if (l.ok) {
+    const int c0 = l.cvi * V;
+    const T* base = in.p + l.n * in.sn + c0;
+    const T* gbase = dout.p + l.n * dout.sn + (long long)l.x * dout.sw + c0;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    int ix[3];
+    bool vx[3];
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) { ix[kw] = l.x * s - d + kw * d; vx[kw] = ix[kw] >= 0 && ix[kw] < in.w; }
+    for (int y = l.y0; y < l.y1; ++y) {
+      uint4 t[9];
+      const uint4 graw = ld16(gbase + (long long)y * dout.sh);
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
-        int ih = y * s - d + kh * d;
-        if (ih < 0 || ih >= in.h) continue;
+        const int ih = y * s - d + kh * d;
+        const bool vy = ih >= 0 && ih < in.h;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          int iw = x * s - d + kw * d;
-          if (iw < 0 || iw >= in.w) continue;
-          float4 v = elem<T>::ld4(in.at(n, ih, iw) + c4 * 4);
-          fma4(acc[kh * 3 + kw], v, g);
-        }
+        for (int kw = 0; kw < 3; ++kw)
+          t[kh * 3 + kw] = (vy && vx[kw]) ? ld16(base + (long long)ih * in.sh + (long long)ix[kw] * in.sw) : zero;
+      }
+      float g[V];
+      dwvec<T>::unpack(graw, g);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        float f[V];
+        dwvec<T>::unpack(t[k], f);
+#pragma unroll
+        for (int j = 0; j < V; ++j) G[k][j] = fmaf(f[j], g[j], G[k][j]);
       }
     }
   }
-  const int per_row = cvb * 36;
-  if (ty < rows) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      float* r = redf + ty * per_row + (k * cvb + tx) * 4;
-      r[0] = ok ? acc[k].x : 0.f; r[1] = ok ? acc[k].y : 0.f; r[2] = ok ? acc[k].z : 0.f; r[3] = ok ? acc[k].w : 0.f;
-    }
-  }
-  __syncthreads();
-  for (int col = threadIdx.x; col < per_row; col += blockDim.x) {
-    float sum = 0.f;
-    for (int r = 0; r < rows; ++r) sum += redf[r * per_row + col];
-    int k = col / (cvb * 4);
-    int rem = col - k * cvb * 4;
-    int c = (blockIdx.y * cvb + (rem >> 2)) * 4 + (rem & 3);
-    if (c < C) atomicAdd(G + k * C + c, sum);
-  }
+  dw_reduce_G<V>(G, Gout, C, m, blockIdx.y * m.cvp);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+template <typename T>
+static bool dw_vec_ok(const dc_view& v) {
+  const int V = dwvec<T>::V;
+  return v.sc == 1 && (v.c % V == 0) && (v.sn % V == 0) && (v.sh % V == 0) && (v.sw % V == 0) &&
+         ((reinterpret_cast<uintptr_t>(v.ptr) % 16) == 0);
+}
+static inline dim3 dw_grid(const DwMap& m, int cols, int n_img) {
+  return dim3((unsigned)ceil_div(cols, m.ppb), (unsigned)m.gy, (unsigned)(n_img * m.nstrips));
 }
 
 template <typename T>
 static int dw_fwd_t(const dc_view& in, const void* w, int s, int d, const dc_view& out, cudaStream_t st) {
-  long long total = (long long)out.n * out.h * out.w * (out.c / 4);
-  int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 32);
-  dw_fwd_kernel<T><<<blocks, 256, 0, st>>>(make_view<const T>(in), (const T*)w, s, d, make_view<T>(out));
+  constexpr int V = dwvec<T>::V;
+  DwMap m = dw_map(out.c, V, out.h, out.w, out.n, kNumSMs * 4, 6);
+  dim3 grid = dw_grid(m, out.w, out.n);
+  if (s == 1 && d == 1)
+    dw_s1d1_kernel<T, V><<<grid, kDwThreads, 0, st>>>(dw_view<const T>(in), (const T*)w, dw_view<T>(out), out.c, m, 0, 0);
+  else
+    dw_direct_kernel<T, V><<<grid, kDwThreads, 0, st>>>(dw_view<const T>(in), (const T*)w, dw_view<T>(out), out.c, m, s, d, 0, 0);
   return launch_status("dc_dw_fwd");
 }
 template <typename T>
 static int dw_bwd_data_t(const dc_view& dout, const void* w, int s, int d, const dc_view& din, int acc, cudaStream_t st) {
-  long long total = (long long)din.n * din.h * din.w * (din.c / 4);
-  int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 32);
-  dw_bwd_data_kernel<T><<<blocks, 256, 0, st>>>(make_view<const T>(dout), (const T*)w, s, d, make_view<T>(din), acc);
+  constexpr int V = dwvec<T>::V;
+  DwMap m = dw_map(din.c, V, din.h, din.w, din.n, kNumSMs * 4, 6);
+  dim3 grid = dw_grid(m, din.w, din.n);
+  if (s == 1 && d == 1)          // full correlation with the flipped filter
+    dw_s1d1_kernel<T, V><<<grid, kDwThreads, 0, st>>>(dw_view<const T>(dout), (const T*)w, dw_view<T>(din), din.c, m, 1, acc);
+  else if (s == 1)
+    dw_direct_kernel<T, V><<<grid, kDwThreads, 0, st>>>(dw_view<const T>(dout), (const T*)w, dw_view<T>(din), din.c, m, 1, d, 1, acc);
+  else
+    dw_bwd_data_strided_kernel<T, V><<<grid, kDwThreads, 0, st>>>(dw_view<const T>(dout), (const T*)w, dw_view<T>(din), din.c, m, s, d, acc);
   return launch_status("dc_dw_bwd_data");
 }
 template <typename T>
 static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d, float* G, cudaStream_t st) {
-  int cv = dout.c / 4;
-  int cvb = std::min(cv, 32);
-  int rows = 256 / cvb;
-  int gy = ceil_div(cv, cvb);
-  long long npix = (long long)dout.n * dout.h * dout.w;
-  long long gx_need = (npix + rows - 1) / rows;
-  int gx_cap = std::max(1, (kNumSMs * 4) / gy);
-  dim3 grid((unsigned)std::min<long long>(gx_need, gx_cap), gy, 1);
-  size_t smem = (size_t)rows * cvb * 36 * sizeof(float);
-  dw_bwd_weight_kernel<T><<<grid, 256, smem, st>>>(make_view<const T>(in), make_view<const T>(dout), s, d, G, cvb, rows);
+  constexpr int V = dwvec<T>::V;
+  DwMap m = dw_map(dout.c, V, dout.h, dout.w, dout.n, kNumSMs * 2, 12);
+  dim3 grid = dw_grid(m, dout.w, dout.n);
+  const size_t smem = (size_t)8 * 32 * 3 * V * sizeof(float);
+  if (s == 1 && d == 1)
+    dw_bwd_weight_s1d1_kernel<T, V><<<grid, kDwThreads, smem, st>>>(dw_view<const T>(in), dw_view<const T>(dout), G, dout.c, m);
+  else
+    dw_bwd_weight_direct_kernel<T, V><<<grid, kDwThreads, smem, st>>>(dw_view<const T>(in), dw_view<const T>(dout), G, dout.c, m, s, d);
   return launch_status("dc_dw_bwd_weight");
 }
 
 static int check_dw(const char* what, const dc_view& big, const dc_view& small, int s, int d) {
-  DC_REQUIRE(view_ok(big) && view_ok(small) && view_vec4(big) && view_vec4(small), "%s: views must be channel-contiguous, C %% 4 == 0", what);
+  DC_REQUIRE(view_ok(big) && view_ok(small), "%s: bad views", what);
   DC_REQUIRE(big.dtype == small.dtype && big.c == small.c && big.n == small.n, "%s: dtype/channel/batch mismatch", what);
+  const bool vec = big.dtype == DC_F32 ? (dw_vec_ok<float>(big) && dw_vec_ok<float>(small))
+                                       : (dw_vec_ok<__nv_bfloat16>(big) && dw_vec_ok<__nv_bfloat16>(small));
+  DC_REQUIRE(vec, "%s: views must be channel-contiguous and 16-byte aligned with C %% 8 == 0 (bf16) / C %% 4 == 0 (fp32)", what);
   DC_REQUIRE((s == 1 || s == 2) && d >= 1, "%s: stride must be 1 or 2, dilation >= 1", what);
   // fixed_padding pads d on every side: H_out = floor((H + 2d - (2d+1)) / s) + 1 = floor((H-1)/s) + 1
   DC_REQUIRE(small.h == (big.h - 1) / s + 1 && small.w == (big.w - 1) / s + 1, "%s: output size mismatch (%dx%d -> %dx%d, stride %d)",
@@ -186,14 +548,14 @@ extern "C" {
 
 int dc_dw_fwd(dc_view in, const void* w9c, int stride, int dil, dc_view out, void* stream) {
   if (int r = check_dw("dc_dw_fwd", in, out, stride, dil)) return r;
-  DC_REQUIRE(w9c != nullptr, "dc_dw_fwd: null weights");
+  DC_REQUIRE(w9c != nullptr && (reinterpret_cast<uintptr_t>(w9c) % 16) == 0, "dc_dw_fwd: weights must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   return in.dtype == DC_F32 ? dw_fwd_t<float>(in, w9c, stride, dil, out, st) : dw_fwd_t<__nv_bfloat16>(in, w9c, stride, dil, out, st);
 }
 
 int dc_dw_bwd_data(dc_view dout, const void* w9c, int stride, int dil, dc_view din, int accumulate, void* stream) {
   if (int r = check_dw("dc_dw_bwd_data", din, dout, stride, dil)) return r;
-  DC_REQUIRE(w9c != nullptr, "dc_dw_bwd_data: null weights");
+  DC_REQUIRE(w9c != nullptr && (reinterpret_cast<uintptr_t>(w9c) % 16) == 0, "dc_dw_bwd_data: weights must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   return din.dtype == DC_F32 ? dw_bwd_data_t<float>(dout, w9c, stride, dil, din, accumulate, st)
                              : dw_bwd_data_t<__nv_bfloat16>(dout, w9c, stride, dil, din, accumulate, st);

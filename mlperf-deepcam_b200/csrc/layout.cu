@@ -164,6 +164,46 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int K, int N, 
   }
 }
 
+// All weight packs of a step in ONE launch: a device table of jobs, each owning a contiguous range of blocks.
+template <typename TD>
+__device__ __forceinline__ void pack_job_elems(const dc_pack_job& j, int local_block, int tid) {
+  const int total = j.taps * j.K_pad * j.N_pad;
+  const float* __restrict__ src = j.src;
+  TD* __restrict__ dst = reinterpret_cast<TD*>(j.dst);
+  for (int i = local_block * 256 + tid; i < total; i += j.n_blocks * 256) {
+    int t, k, n;
+    if (j.layout == DC_PACK_TKN) {
+      n = i % j.N_pad;
+      const int r = i / j.N_pad;
+      k = r % j.K_pad;
+      t = r / j.K_pad;
+    } else {
+      k = i % j.K_pad;
+      const int r = i / j.K_pad;
+      t = r % j.taps;
+      n = r / j.taps;
+    }
+    float v = 0.f;
+    if (k < j.K && n < j.N) {
+      const long long si = j.src_k_first ? ((long long)k * j.N + n) * j.taps + t : ((long long)n * j.K + k) * j.taps + t;
+      v = src[si];
+    }
+    elem<TD>::st(dst + i, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_multi_kernel(const dc_pack_job* __restrict__ jobs, int njobs) {
+  int lo = 0, hi = njobs - 1;
+  const int b = blockIdx.x;
+  while (lo < hi) {                    // last job whose block_start <= b
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block_start <= b) lo = mid; else hi = mid - 1;
+  }
+  const dc_pack_job j = jobs[lo];
+  if (j.dst_dtype == DC_F32) pack_job_elems<float>(j, b - j.block_start, threadIdx.x);
+  else pack_job_elems<__nv_bfloat16>(j, b - j.block_start, threadIdx.x);
+}
+
 __global__ void unpack_wgrad_kernel(const float* __restrict__ G, int K, int N, int taps, int k_stride, int dst_k_first,
                                     float* __restrict__ dst) {
   long long total = (long long)taps * K * N;
@@ -245,6 +285,12 @@ int dc_pack_weight(const float* src, int K, int N, int taps, int src_k_first, vo
   else
     return dc::fail(-1, "dc_pack_weight: bad dtype %d", dst_dtype);
   return launch_status("dc_pack_weight");
+}
+
+int dc_pack_weights_multi(const dc_pack_job* jobs_dev, int njobs, int total_blocks, void* stream) {
+  DC_REQUIRE(jobs_dev != nullptr && njobs > 0 && total_blocks > 0, "dc_pack_weights_multi: bad arguments");
+  pack_multi_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(jobs_dev, njobs);
+  return launch_status("dc_pack_weights_multi");
 }
 
 int dc_unpack_wgrad(const float* G, int K, int N, int taps, int k_stride, int dst_k_first, float* dst, void* stream) {

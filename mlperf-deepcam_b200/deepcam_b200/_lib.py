@@ -33,6 +33,12 @@ class dc_bn_params(Structure):
                 ("flags", c_int32), ("reserved", c_int32)]
 
 
+class dc_pack_job(Structure):
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("K", c_int32), ("N", c_int32), ("taps", c_int32),
+                ("src_k_first", c_int32), ("layout", c_int32), ("K_pad", c_int32), ("N_pad", c_int32),
+                ("dst_dtype", c_int32), ("block_start", c_int32), ("n_blocks", c_int32)]
+
+
 # name -> (restype, argtypes); must list every symbol declared in include/deepcam_b200.h
 SIGNATURES = {
     "dc_abi_version": (c_int, []),
@@ -42,6 +48,7 @@ SIGNATURES = {
     "dc_fill_zero": (c_int, [c_void_p, c_size_t, c_void_p]),
     "dc_i64_increment_many": (c_int, [c_void_p, c_int, c_void_p]),
     "dc_pack_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dc_pack_weights_multi": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "dc_unpack_wgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dc_conv_gemm_simt": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p]),
     "dc_conv_wgrad_simt": (c_int, [POINTER(dc_conv_desc), dc_view, dc_view, c_void_p, c_void_p]),
@@ -50,11 +57,11 @@ SIGNATURES = {
     "dc_dw_fwd": (c_int, [dc_view, c_void_p, c_int, c_int, dc_view, c_void_p]),
     "dc_dw_bwd_data": (c_int, [dc_view, c_void_p, c_int, c_int, dc_view, c_int, c_void_p]),
     "dc_dw_bwd_weight": (c_int, [dc_view, dc_view, c_int, c_int, c_void_p, c_void_p]),
-    "dc_bn_stats": (c_int, [dc_view, c_void_p, c_void_p]),
+    "dc_bn_ws_bytes": (c_size_t, [c_int]),
+    "dc_bn_stats": (c_int, [POINTER(dc_bn_params), dc_view, c_void_p]),
     "dc_bn_apply": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p]),
-    "dc_bn_bwd_reduce": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, c_void_p]),
-    "dc_bn_bwd_apply": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, dc_view, dc_view,
-                                c_void_p, c_void_p, c_void_p]),
+    "dc_bn_bwd_reduce": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dc_bn_bwd_apply": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, dc_view, dc_view, c_void_p]),
     "dc_channel_sum": (c_int, [dc_view, c_void_p, c_void_p, c_void_p]),
     "dc_gap_fwd": (c_int, [dc_view, c_void_p, c_void_p]),
     "dc_broadcast_hw": (c_int, [c_void_p, dc_view, c_void_p]),

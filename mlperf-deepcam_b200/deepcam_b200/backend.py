@@ -67,19 +67,31 @@ class BnSpec:
 _COUNTER_TABLES = {}      # tuple of counter addresses -> device table (built once per module instance)
 
 
-def _cached(spec, key, param, make, always=False):
+def _cached(spec, key, param, job, frozen=False):
     """Kernel-layout copy of a parameter.  The buffer is allocated once and re-packed IN PLACE whenever the master
-    parameter changed, so its address stays valid for captured CUDA graphs; `always` (graph capture) re-packs
-    unconditionally because the pack kernel becomes part of the replayed graph."""
+    parameter changed, so its address stays valid for captured CUDA graphs.  `job` = (K, N, taps, src_k_first, layout,
+    K_pad, N_pad, dtype) of ops.pack_weight.  `frozen` (graph capture): an existing buffer is returned as it is,
+    because the plan re-packs every registered buffer in one launch at the start of its forward graph."""
     ver = (param._version, param.data_ptr())
     ent = spec._cache.get(key)
     if ent is None or ent[1].device != param.device:
-        ent = (ver, make(None))
+        ent = [ver, ops.pack_weight(param.detach(), *job), job, param]
         spec._cache[key] = ent
-    elif always or ent[0] != ver:
-        ent = (ver, make(ent[1]))
-        spec._cache[key] = ent
+    elif not frozen and ent[0] != ver:
+        ops.pack_weight(param.detach(), *job, out=ent[1])
+        ent[0] = ver
     return ent[1]
+
+
+def pack_jobs_of(module):
+    """Every kernel-layout weight copy that exists for the layers under `module` (filled by an eager run)."""
+    jobs = []
+    for m in module.modules():
+        for spec in m.__dict__.get("_dc_specs", {}).values():
+            for ent in getattr(spec, "_cache", {}).values():
+                K, N, taps, skf, layout, K_pad, N_pad, _dt = ent[2]
+                jobs.append((ent[3].detach(), ent[1], K, N, taps, skf, layout, K_pad, N_pad))
+    return jobs
 
 
 class CudaBackend:
@@ -95,7 +107,8 @@ class CudaBackend:
         self.use_tc = bool(use_tc)
         self.launches = 0
         self.graph_mode = False       # True while the owning plan captures CUDA graphs (engine._GraphPlan)
-        self.bwd_phase = False
+        self.arena = None
+        self.arena_used = 0
 
     # ---- memory -----------------------------------------------------------------------------------
     def empty(self, n, h, w, c, dtype=None):
@@ -108,11 +121,30 @@ class CudaBackend:
         return t
 
     def scratch(self, numel, dtype, zero=False):
+        if zero and self.arena is not None:
+            # graph capture: zero-initialised scratch comes out of one arena that the plan clears with a single
+            # memset before every replay (instead of one memset node per BatchNorm workspace / gradient scratch)
+            nbytes = numel * torch.empty((), dtype=dtype).element_size()
+            off = (self.arena_used + 255) // 256 * 256
+            if off + nbytes <= self.arena.numel():
+                self.arena_used = off + nbytes
+                return self.arena[off:off + nbytes].view(dtype)
         t = torch.empty(numel, dtype=dtype, device=self.device)
         if zero:
             ops.fill_zero(t)
             self.launches += 1
         return t
+
+    def begin_arena(self, nbytes):
+        self.arena = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.arena_used = 0
+        return self.arena
+
+    def end_arena(self):
+        """Returns the used prefix of the arena (to be zeroed before every replay) and detaches it."""
+        used = self.arena[:(self.arena_used + 255) // 256 * 256] if self.arena_used else None
+        self.arena = None
+        return used
 
     def fill_zero_flat(self, flat):
         ops.fill_zero(flat)
@@ -173,11 +205,8 @@ class CudaBackend:
         else:
             layout, K_pad, N_pad, dt = DC_PACK_TKN, x.shape[3], _round_up(N, 4), x.dtype
 
-        def make(out):
-            self.launches += 1
-            return ops.pack_weight(w.detach(), K, N, taps, src_k_first, layout, K_pad, N_pad, dt, out=out)
-
-        return _cached(spec, (role, impl, dt, K_pad, N_pad), w, make, always=self.graph_mode)
+        return _cached(spec, (role, impl, dt, K_pad, N_pad), w, (K, N, taps, src_k_first, layout, K_pad, N_pad, dt),
+                       frozen=self.graph_mode)
 
     def _gemm(self, taps, stride, accumulate, wtaps, x, w, bias, out, impl):
         desc = ops.make_desc(taps, (stride, stride), accumulate, wtaps)
@@ -266,11 +295,8 @@ class CudaBackend:
 
     # ---- depthwise ---------------------------------------------------------------------------------------------
     def _dw_packed(self, spec):
-        def make(out):
-            self.launches += 1
-            return ops.pack_weight(spec.weight.detach(), 1, spec.c, 9, False, DC_PACK_TKN, 1, spec.c, self.dtype, out=out)
-        # the backward graph reuses the copy packed by the forward graph of the same step
-        return _cached(spec, ("dw", self.dtype), spec.weight, make, always=self.graph_mode and not self.bwd_phase)
+        return _cached(spec, ("dw", self.dtype), spec.weight, (1, spec.c, 9, False, DC_PACK_TKN, 1, spec.c, self.dtype),
+                       frozen=self.graph_mode)
 
     def dw_fwd(self, x, spec, out):
         ops.dw_fwd(x, self._dw_packed(spec), spec.stride, spec.dil, out)
@@ -302,18 +328,19 @@ class CudaBackend:
             return None
         m = spec.module
         sums = None
+        mom = m.momentum if m.momentum is not None else 0.1
+        track = m.running_mean is not None
         if training:
             if n * h * w <= 1:
                 raise ValueError("Expected more than 1 value per channel when training, got input size %s"
                                  % (torch.Size((n, c, h, w)),))
-            sums = self.scratch(2 * c, torch.float64, zero=True)
-            ops.bn_stats(y, sums)
-            self.launches += 1
+            sums = self.scratch(ops.bn_ws_elems(c), torch.float64, zero=True)        # per-layer BatchNorm workspace
             flags |= DC_BN_TRAIN
-        mom = m.momentum if m.momentum is not None else 0.1
-        track = m.running_mean is not None
         p = ops.bn_params(m.weight.detach(), m.bias.detach(), m.running_mean if track else None,
                           m.running_var if track else None, sums, n * h * w, mom, m.eps, flags)
+        if training:
+            ops.bn_stats(p, y)            # sums + coefficients + running statistics (last block finalizes)
+            self.launches += 1
         ops.bn_apply(p, y, residual, out)
         self.launches += 1
         return sums
@@ -325,16 +352,16 @@ class CudaBackend:
         n, h, w, c = dout.shape
         if spec is None:
             p = ops.bn_params(None, None, None, None, None, n * h * w, 0.0, 0.0, flags | DC_BN_IDENTITY)
-            ops.bn_bwd_apply(p, dout, out, None, None, dy, dres, None, None)
+            ops.bn_bwd_apply(p, dout, out, None, None, dy, dres)
             self.launches += 1
             return
         m = spec.module
         if training:
             flags |= DC_BN_TRAIN
         p = ops.bn_params(m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var, sums, n * h * w, 0.0, m.eps, flags)
-        rsums = self.scratch(2 * c, torch.float64, zero=True)
-        ops.bn_bwd_reduce(p, dout, out if relu else None, y, rsums)
-        ops.bn_bwd_apply(p, dout, out if relu else None, y, rsums, dy, dres, dgamma, dbeta)
+        rws = self.scratch(ops.bn_ws_elems(c), torch.float64, zero=True)
+        ops.bn_bwd_reduce(p, dout, out if relu else None, y, rws, dgamma, dbeta)
+        ops.bn_bwd_apply(p, dout, out if relu else None, y, rws, dy, dres)
         self.launches += 2
 
     # ---- image pooling branch ------------------------------------------------------------------------------------------

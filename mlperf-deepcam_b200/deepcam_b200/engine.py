@@ -361,6 +361,10 @@ class _PlanFunction(torch.autograd.Function):
 # CUDA-graph plans: the whole forward (and backward) of one module call is captured once per configuration and
 # replayed afterwards, so the ~1000 kernel launches of a step cost one cudaGraphLaunch each way on the host.
 # ------------------------------------------------------------------------------------------------------------
+_FWD_ARENA_BYTES = 8 << 20
+_BWD_ARENA_BYTES = 192 << 20
+
+
 def graphs_enabled():
     return os.environ.get("DEEPCAM_B200_GRAPHS", "1") not in ("0", "false", "False", "")
 
@@ -395,6 +399,7 @@ class _GraphPlan:
         self.fwd_graph = None
         self.bwd_segments = None
         self.fwd_kernels = self.bwd_kernels = 0
+        self.fwd_zero = self.bwd_zero = None
         self.outs = None
 
     # ---- forward ------------------------------------------------------------------------------------------
@@ -408,15 +413,25 @@ class _GraphPlan:
     def forward(self, inputs):
         self._load_inputs(inputs)
         if self.fwd_graph is None:
+            from . import ops
+            from .backend import pack_jobs_of
+            jobs = pack_jobs_of(self.module)                 # all kernel-layout weight copies (filled by the eager call)
+            self.pack_table = ops.build_pack_table(jobs, self.device) if jobs else None
             g = torch.cuda.CUDAGraph()
             l0 = self._lib.launch_count
+            self.be.begin_arena(_FWD_ARENA_BYTES)
             with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
+                if self.pack_table is not None:
+                    ops.pack_weights_multi(*self.pack_table)     # one launch re-packs every weight each step
                 self.outs = self.module._emit_root(self.eng, *self.xin)
                 self.eng.finish_forward()
+            self.fwd_zero = self.be.end_arena()
             self.fwd_kernels = self._lib.launch_count - l0
             self.fwd_graph = g
         else:
             self._lib.launch_count += self.fwd_kernels
+        if self.fwd_zero is not None:
+            self.be.fill_zero_flat(self.fwd_zero)            # BatchNorm workspaces of the whole forward: one memset
         self.fwd_graph.replay()
         self.generation += 1
         self.module._dc_last_launches = self.fwd_kernels + len(self.xin) + len(self.outs)
@@ -442,12 +457,15 @@ class _GraphPlan:
                 ops_copy_view(g.detach().permute(0, 2, 3, 1), act.grad)        # pad channels are zero-filled
         if sync is not None:
             sync.begin(grads)
+        if not first and self.bwd_zero is not None:
+            be.fill_zero_flat(self.bwd_zero)                 # BatchNorm / weight-gradient scratch of the whole backward
         if first:
-            be.bwd_phase = True
             tape = list(reversed(eng.tape))
             eng.tape = []
             segments = []
             l0 = self._lib.launch_count
+            be.begin_arena(_BWD_ARENA_BYTES)
+            be.fill_zero_flat(be.arena)                      # (first call only: the used prefix is not known yet)
             i = 0
             while i < len(tape) or not segments:
                 g = torch.cuda.CUDAGraph()
@@ -468,6 +486,7 @@ class _GraphPlan:
                 g.replay()
                 for b in buckets:
                     sync.launch_bucket(b)
+            self.bwd_zero = be.end_arena()
             self.bwd_kernels = self._lib.launch_count - l0
             self.bwd_segments = segments
         else:

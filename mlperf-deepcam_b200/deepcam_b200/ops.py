@@ -165,6 +165,30 @@ def pack_weight(src, K, N, taps, src_k_first, layout, K_pad, N_pad, dtype, out=N
     return out
 
 
+def build_pack_table(jobs, device):
+    """jobs: list of (src fp32 tensor, dst tensor, K, N, taps, src_k_first, layout, K_pad, N_pad).  Returns the device job
+    table (uint8 tensor; keep it alive), the number of jobs and the grid size for pack_weights_multi."""
+    arr = (_lib.dc_pack_job * len(jobs))()
+    start = 0
+    for i, (src, dst, K, N, taps, skf, layout, K_pad, N_pad) in enumerate(jobs):
+        total = taps * K_pad * N_pad
+        assert total < 2 ** 31 and src.dtype == torch.float32 and src.is_contiguous() and dst.numel() == total
+        nb = max(1, min(128, (total + 2047) // 2048))
+        j = arr[i]
+        j.src, j.dst = src.data_ptr(), dst.data_ptr()
+        j.K, j.N, j.taps, j.src_k_first = K, N, taps, int(skf)
+        j.layout, j.K_pad, j.N_pad, j.dst_dtype = layout, K_pad, N_pad, _DT[dst.dtype]
+        j.block_start, j.n_blocks = start, nb
+        start += nb
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device), len(jobs), start
+
+
+def pack_weights_multi(table, njobs, total_blocks):
+    _timed("pack_weights_multi", 0.0, 0.0,
+           lambda: _lib.load().dc_pack_weights_multi(_p(table), njobs, total_blocks, _stream()), "dc_pack_weights_multi")
+
+
 def unpack_wgrad(G, K, N, taps, dst_k_first, dst, k_stride=None):
     assert G.dtype == torch.float32 and dst.dtype == torch.float32 and dst.is_contiguous()
     assert dst.numel() == K * N * taps
@@ -227,12 +251,15 @@ def dw_bwd_weight(x, dout, stride, dil, G9c):
 
 
 # ---- batch norm -----------------------------------------------------------------------------------------
-def bn_stats(y, sums):
-    _require_cuda(y, sums)
-    assert sums.dtype == torch.float64 and sums.numel() == 2 * y.shape[3]
-    _timed("bn_stats", 3.0 * y.numel(), _nbytes(y), lambda: _lib.load().dc_bn_stats(view(y), _p(sums), _stream()), "dc_bn_stats",
-           tag=_shape_tag(y))
-    return sums
+def bn_ws_elems(c):
+    """float64 elements of the per-layer BatchNorm workspace (dc_bn_ws_bytes)."""
+    return (32 * c + 16) // 8
+
+
+def bn_stats(params, y):
+    _require_cuda(y)
+    _timed("bn_stats", 3.0 * y.numel(), _nbytes(y), lambda: _lib.load().dc_bn_stats(ctypes.byref(params), view(y), _stream()),
+           "dc_bn_stats", tag=_shape_tag(y))
 
 
 def bn_params(gamma, beta, running_mean, running_var, sums, count, momentum, eps, flags):
@@ -257,20 +284,21 @@ def bn_apply(params, y, residual, out):
     return out
 
 
-def bn_bwd_reduce(params, dout, out, y, rsums):
-    _require_cuda(dout, rsums)
-    assert rsums.dtype == torch.float64
+def bn_bwd_reduce(params, dout, out, y, rws, dgamma, dbeta):
+    _require_cuda(dout, rws)
+    assert rws.dtype == torch.float64 and rws.numel() >= bn_ws_elems(dout.shape[3])
     _timed("bn_bwd_reduce", 4.0 * dout.numel(), _nbytes(dout, out, y),
-           lambda: _lib.load().dc_bn_bwd_reduce(ctypes.byref(params), view(dout), view(out), view(y), _p(rsums), _stream()),
+           lambda: _lib.load().dc_bn_bwd_reduce(ctypes.byref(params), view(dout), view(out), view(y), _p(rws), _p(dgamma),
+                                                _p(dbeta), _stream()),
            "dc_bn_bwd_reduce", tag=_shape_tag(dout))
-    return rsums
+    return rws
 
 
-def bn_bwd_apply(params, dout, out, y, rsums, dy, dres, dgamma, dbeta):
+def bn_bwd_apply(params, dout, out, y, rws, dy, dres):
     _require_cuda(dout)
     _timed("bn_bwd_apply", 8.0 * dout.numel(), _nbytes(dout, out, y, dy, dres),
-           lambda: _lib.load().dc_bn_bwd_apply(ctypes.byref(params), view(dout), view(out), view(y), _p(rsums), view(dy),
-                                               view(dres), _p(dgamma), _p(dbeta), _stream()), "dc_bn_bwd_apply",
+           lambda: _lib.load().dc_bn_bwd_apply(ctypes.byref(params), view(dout), view(out), view(y), _p(rws), view(dy),
+                                               view(dres), _stream()), "dc_bn_bwd_apply",
            tag=_shape_tag(dout) + (" res" if dres is not None else "") + (" nody" if dy is None else ""))
 
 

@@ -97,8 +97,8 @@ def test_bn_forward_backward(dtype, C, relu, use_res):
         o = torch.relu(o)
     o.backward(dout)
     # ours; y lives in a wider buffer (channel slice) to exercise strides
-    buf = torch.zeros(N, H, W, C + 8, dtype=dtype, device=dev())
-    yv = buf[..., 4:4 + C]
+    buf = torch.zeros(N, H, W, C + 16, dtype=dtype, device=dev())
+    yv = buf[..., 8:8 + C]          # 16-byte aligned channel slice
     yv.copy_(to_nhwc(y, dtype))
     out = be.empty(N, H, W, C)
     sums = be.bn_fwd(yv, BnSpec("bn", bn), relu, to_nhwc(res, dtype) if use_res else None, out, training=True)
