@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <algorithm>
 #include <mutex>
+#include <stdlib.h>
 
 namespace dc {
 
@@ -59,6 +60,22 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -99,6 +116,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void red_add_v4(float* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)),
+               "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -126,6 +148,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 struct TcMaps {
   CUtensorMap a[4];   // activation (gathered operand) parity maps
   CUtensorMap b;      // fprop: packed weights; wgrad: dY
+  CUtensorMap c;      // fprop (persistent kernel): output view for the TMA-store epilogue
 };
 
 struct TcOut {
@@ -367,6 +390,332 @@ __global__ void __launch_bounds__(kTcThreads) conv_gemm_tc_kernel(const __grid_c
 
 
 // ------------------------------------------------------------------------------------------------
+// fprop-like kernel, second generation: PERSISTENT CTAs (one per SM) walking a static tile list, two TMEM
+// accumulators so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1, epilogue staged in 64-column
+// chunks through a dedicated shared-memory buffer, and a B-RESIDENT mode for layers whose whole packed weight tile
+// fits in shared memory (1x1 convolutions with K*N <= 64K elements: the weights are loaded once per CTA instead of
+// once per tile, which removes ~2/3 of the L2 traffic of those HBM-bound layers).
+// ------------------------------------------------------------------------------------------------
+struct TcV2Cfg {
+  int BN;              // N tile (multiple of 16, <= 256)
+  int stages;          // pipeline stages
+  int stage_bytes;     // 16384 (A) [+ BN*128 (B) when streaming]
+  int b_resident;      // whole weight tile resident in shared memory (requires n_ntiles == 1)
+  int bres_bytes;      // wtaps * kblocks * BN * 128 when resident
+  int acc_stride;      // TMEM columns between the two accumulators (power of two >= BN)
+  int tmem_cols;       // 2 * acc_stride
+  int n_mtiles, n_ntiles, total_tiles;
+  int tma_store;       // epilogue writes 128 x 64 bf16 chunks with TMA (dense bf16 output views)
+  int smem_bytes;
+};
+constexpr int kV2StagePitchF32 = 64 * 4 + 16;     // staged row: 64 fp32 columns + 16 B (odd multiple of 16 B: conflict-free)
+constexpr int kV2StagingBytes = 4 * 32 * kV2StagePitchF32;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __grid_constant__ TcMaps maps, const TcFpropParams p,
+                                                                      const TcV2Cfg cfg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int STAGES = cfg.stages;
+  const int BN = cfg.BN;
+  const uint32_t bres_base = smem_base + STAGES * cfg.stage_bytes;
+  const uint32_t stg_off = STAGES * cfg.stage_bytes + cfg.bres_bytes;
+  const uint32_t bar_base = smem_base + stg_off + kV2StagingBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t bres_bar = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+    mbar_init(bres_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, cfg.tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.b);
+    tma_prefetch_desc(&maps.a[p.map_id[0]]);
+    if (cfg.tma_store) tma_prefetch_desc(&maps.c);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int b_block_bytes = BN * 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (cfg.b_resident) {
+        mbar_expect_tx(bres_bar, cfg.bres_bytes);
+        const int nblk = cfg.bres_bytes / b_block_bytes;
+        for (int j = 0; j < nblk; ++j) tma_load_2d(&maps.b, bres_bar, bres_base + j * b_block_bytes, j * 64, 0);
+      }
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x) {
+        const int nt = tile / cfg.n_mtiles;
+        int mt = tile - nt * cfg.n_mtiles;
+        const int tile_x = mt % p.tiles_x; mt /= p.tiles_x;
+        const int tile_y = mt % p.tiles_y;
+        const int img = mt / p.tiles_y;
+        const int x0 = tile_x * p.TW, y0 = tile_y * p.TH;
+        const int n0 = nt * BN;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const CUtensorMap* am = &maps.a[p.map_id[t]];
+          const int bx = x0 + p.qw[t], by = y0 + p.qh[t];
+          const int kb0 = p.wt[t] * p.kblocks;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            mbar_expect_tx(full_bar(s), cfg.stage_bytes);
+            const uint32_t sa = smem_base + s * cfg.stage_bytes;
+            tma_load_4d(am, full_bar(s), sa, kb * 64, bx, by, img);
+            if (!cfg.b_resident) tma_load_2d(&maps.b, full_bar(s), sa + kABytes, (kb0 + kb) * 64, n0);
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, BN, 0, 0);
+      if (cfg.b_resident) { mbar_wait(bres_bar, 0); tc_fence_after(); }
+      int s = 0; uint32_t ph = 0;
+      int i = 0;
+      for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++i) {
+        const int buf = i & 1;
+        mbar_wait(tempty_bar(buf), (((uint32_t)i >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * cfg.acc_stride);
+        int it = 0;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int kb0 = p.wt[t] * p.kblocks;
+          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t sa = smem_base + s * cfg.stage_bytes;
+            const uint32_t sb = cfg.b_resident ? (bres_base + (uint32_t)(kb0 + kb) * b_block_bytes) : (sa + kABytes);
+            const uint64_t da = make_smem_desc(sa, 16, 1024);
+            const uint64_t db = make_smem_desc(sb, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(acc, da + 2u * k, db + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_commit(empty_bar(s));
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
+          }
+        }
+        umma_commit(tfull_bar(buf));
+      }
+    }
+  } else {
+    // ---- epilogue: warps 2..5; warp w may only touch TMEM lanes 32*(w%4) .. +31 ----
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const int ty = row / p.TW, tx = row - ty * p.TW;
+    const bool stage_f32 = (p.accumulate != 0) || (p.out.dtype == DC_F32);
+    const int es = stage_f32 ? 4 : 2;
+    const int pitch = 64 * es + 16;
+    uint8_t* stg = smem_gen + stg_off + (size_t)lg * 32 * kV2StagePitchF32;
+    const int V = stage_f32 ? 4 : 8;
+    const bool raw_copy = !stage_f32 && p.out_vec_ok;
+    int i = 0;
+    int chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++i) {
+      const int nt = tile / cfg.n_mtiles;
+      int mt = tile - nt * cfg.n_mtiles;
+      const int tile_x = mt % p.tiles_x; mt /= p.tiles_x;
+      const int tile_y = mt % p.tiles_y;
+      const int img = mt / p.tiles_y;
+      const int oy = tile_y * p.TH + ty, ox = tile_x * p.TW + tx;
+      const int n0 = nt * BN;
+      const bool pix_ok = (oy < p.out.h) && (ox < p.out.w);
+      const long long base = (long long)img * p.out.sn + (long long)oy * p.out.sh + (long long)ox * p.out.sw;
+      const unsigned okmask = __ballot_sync(0xffffffffu, pix_ok);
+      const int ncols = min(BN, p.out.c - n0);
+      const int buf = i & 1;
+      mbar_wait(tfull_bar(buf), ((uint32_t)i >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * cfg.acc_stride);
+      if (cfg.tma_store) {
+        // ---- fast path: 128 rows x 64 bf16 columns per chunk, 128B-swizzled staging (two buffers), one TMA store
+        //      (or TMA reduce-add for gradient accumulation) per chunk issued by one elected thread ----
+        const bool elected = (threadIdx.x == 64);
+        const uint32_t stg_s = smem_base + stg_off;
+#pragma unroll 1
+        for (int c0 = 0; c0 < ncols; c0 += 64, ++chunk_ctr) {
+          uint32_t v[2][32];
+          const bool two = (c0 + 32 < ncols);
+          tmem_ld32(acc + (uint32_t)c0, v[0]);
+          if (two) tmem_ld32(acc + (uint32_t)(c0 + 32), v[1]);
+          if (elected) tma_store_wait_read<1>();        // the store that used this staging buffer two chunks ago has read it
+          tmem_ld_wait();
+          if (c0 + 64 >= ncols) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+          }
+          epi_bar_sync();
+          const uint32_t sbuf = stg_s + (uint32_t)(chunk_ctr & 1) * 16384u + (uint32_t)row * 128u;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+              if (h == 0 || two) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  f[j] = __uint_as_float(v[h][8 * q + j]);
+                  if (p.bias && c0 + 32 * h + 8 * q + j < ncols) f[j] += p.bias[n0 + c0 + 32 * h + 8 * q + j];
+                }
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]), b1 = __floats2bfloat162_rn(f[2], f[3]);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[4], f[5]), b3 = __floats2bfloat162_rn(f[6], f[7]);
+                w0 = *reinterpret_cast<uint32_t*>(&b0); w1 = *reinterpret_cast<uint32_t*>(&b1);
+                w2 = *reinterpret_cast<uint32_t*>(&b2); w3 = *reinterpret_cast<uint32_t*>(&b3);
+              }
+              const uint32_t j16 = (uint32_t)(4 * h + q);
+              const uint32_t dst = sbuf + ((j16 ^ ((uint32_t)row & 7u)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+            }
+          }
+          fence_proxy_async();
+          epi_bar_sync();
+          if (elected) {
+            const uint32_t src = stg_s + (uint32_t)(chunk_ctr & 1) * 16384u;
+            if (p.accumulate) tma_reduce_add_4d(&maps.c, src, n0 + c0, tile_x * p.TW, tile_y * p.TH, img);
+            else tma_store_4d(&maps.c, src, n0 + c0, tile_x * p.TW, tile_y * p.TH, img);
+            tma_store_commit();
+          }
+        }
+        continue;
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < ncols; c0 += 64) {
+        uint32_t v[2][32];
+        const bool two = (c0 + 32 < ncols);
+        tmem_ld32(acc + (uint32_t)c0, v[0]);
+        if (two) tmem_ld32(acc + (uint32_t)(c0 + 32), v[1]);
+        tmem_ld_wait();
+        if (c0 + 64 >= ncols) {            // last chunk of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (h == 1 && !two) break;
+          const int cb = c0 + 32 * h;
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cb + j < ncols) v[h][j] = __float_as_uint(__uint_as_float(v[h][j]) + p.bias[n0 + cb + j]);
+          }
+          uint8_t* rp = stg + (size_t)lane * pitch + (size_t)(32 * h) * es;
+          if (stage_f32) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4*>(rp + q * 16) = make_uint4(v[h][4 * q], v[h][4 * q + 1], v[h][4 * q + 2], v[h][4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 r;
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(v[h][8 * q + 0]), __uint_as_float(v[h][8 * q + 1]));
+              __nv_bfloat162 b1 = __floats2bfloat162_rn(__uint_as_float(v[h][8 * q + 2]), __uint_as_float(v[h][8 * q + 3]));
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[h][8 * q + 4]), __uint_as_float(v[h][8 * q + 5]));
+              __nv_bfloat162 b3 = __floats2bfloat162_rn(__uint_as_float(v[h][8 * q + 6]), __uint_as_float(v[h][8 * q + 7]));
+              r.x = *reinterpret_cast<uint32_t*>(&b0); r.y = *reinterpret_cast<uint32_t*>(&b1);
+              r.z = *reinterpret_cast<uint32_t*>(&b2); r.w = *reinterpret_cast<uint32_t*>(&b3);
+              *reinterpret_cast<uint4*>(rp + q * 16) = r;
+            }
+          }
+        }
+        __syncwarp();
+        const int ccols = min(64, ncols - c0);
+        int lpr = 1;
+        while (lpr < 32 && lpr * V < ccols) lpr <<= 1;
+        const int rpi = 32 / lpr;
+        const int my_sub = lane / lpr, my_l = lane - my_sub * lpr;
+#pragma unroll 2
+        for (int r0 = 0; r0 < 32; r0 += rpi) {
+          const int r = r0 + my_sub;
+          const long long rbase = __shfl_sync(0xffffffffu, base, r);
+          const bool ok = (okmask >> r) & 1u;
+          const uint8_t* rp = stg + (size_t)r * pitch;
+          for (int col = my_l * V; col < ccols; col += lpr * V) {
+            if (!ok) continue;
+            const int co = n0 + c0 + col;
+            if (raw_copy && col + 8 <= ccols) {
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out.p) + rbase + co) =
+                  *reinterpret_cast<const uint4*>(rp + (size_t)col * 2);
+              continue;
+            }
+            float f[8];
+            if (stage_f32) {
+              const float4 t4 = *reinterpret_cast<const float4*>(rp + (size_t)col * 4);
+              f[0] = t4.x; f[1] = t4.y; f[2] = t4.z; f[3] = t4.w;
+            } else {
+              const uint4 t4 = *reinterpret_cast<const uint4*>(rp + (size_t)col * 2);
+              const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { f[2 * j] = __uint_as_float(w4[j] << 16); f[2 * j + 1] = __uint_as_float(w4[j] & 0xffff0000u); }
+            }
+            if (stage_f32 && p.out_vec_ok && col + 4 <= ccols) {
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out.p) + rbase + co;
+              if (p.accumulate) {
+                const uint2 old = *reinterpret_cast<const uint2*>(op);
+                f[0] += __uint_as_float(old.x << 16); f[1] += __uint_as_float(old.x & 0xffff0000u);
+                f[2] += __uint_as_float(old.y << 16); f[3] += __uint_as_float(old.y & 0xffff0000u);
+              }
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]), b1 = __floats2bfloat162_rn(f[2], f[3]);
+              uint2 o;
+              o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+              *reinterpret_cast<uint2*>(op) = o;
+            } else if (p.out.dtype == DC_F32 && p.out.sc == 1 && col + 4 <= ccols && ((rbase + co) & 3) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(p.out.p) & 15) == 0)) {
+              float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out.p) + rbase + co);
+              float4 o = make_float4(f[0], f[1], f[2], f[3]);
+              if (p.accumulate) { const float4 old = *q; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+              *q = o;
+            } else {
+              for (int j = 0; j < V && col + j < ccols; ++j) {
+                const long long off = rbase + (long long)(co + j) * p.out.sc;
+                float val = f[j];
+                if (p.out.dtype == DC_F32) {
+                  float* q = reinterpret_cast<float*>(p.out.p) + off;
+                  if (p.accumulate) val += *q;
+                  *q = val;
+                } else {
+                  __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p.out.p) + off;
+                  if (p.accumulate) val += __bfloat162float(*q);
+                  *q = __float2bfloat16_rn(val);
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();       // staging rows are reused by the next chunk
+      }
+    }
+  }
+  if (cfg.tma_store && threadIdx.x == 64) tma_store_wait_all();     // staging must stay valid until the last store has read it
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, cfg.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
 // wgrad: D[co (128)][ci (BNW)] += sum over pixel tiles of dY^T X_t ; MN-major operands.
 // ------------------------------------------------------------------------------------------------
 struct TcWgradParams {
@@ -378,6 +727,7 @@ struct TcWgradParams {
   int mtiles_total, mtiles_per_split;
   int n_ci_tiles;
   int Co, Ci;
+  int vec_red;          // G rows are 16-byte aligned and Ci % 4 == 0: use red.global.add.v4.f32
   float* G;
 };
 
@@ -385,7 +735,7 @@ template <int BNW> struct WgradCfg {
   static constexpr int kABytes = 2 * 16384;            // 128 co = 2 boxes of [128 px][64 ch]
   static constexpr int kBBytes = (BNW / 64) * 16384;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = 3;
+  static constexpr int kStages = (kStageBytes > 65536) ? 2 : 3;
   static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
 };
 
@@ -488,10 +838,19 @@ __global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const __grid_
         tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
         tmem_ld_wait();
         if (co < p.Co) {
+          if (p.vec_red) {
+            // 16-byte reductions: 4 consecutive ci of this lane's co row per instruction (Ci % 4 == 0, G 16-byte aligned)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int ci = ci0 + c0 + j;
-            if (ci < p.Ci) atomicAdd(Grow + ci, __uint_as_float(v[j]));
+            for (int q = 0; q < 8; ++q) {
+              const int ci = ci0 + c0 + 4 * q;
+              if (ci < p.Ci) red_add_v4(Grow + ci, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int ci = ci0 + c0 + j;
+              if (ci < p.Ci) atomicAdd(Grow + ci, __uint_as_float(v[j]));
+            }
           }
         }
       }
@@ -640,6 +999,63 @@ static int launch_fprop(const TcMaps& maps, const TcFpropParams& p, const TcFpro
   return launch_status("dc_conv_gemm_tc");
 }
 
+// Tile configuration of the persistent kernel.  Cost model per CTA: rounds * (bytes pulled from L2 per k-block), since
+// these GEMMs are bound by the L2->SM path (~42 B/clk/SM with all SMs pulling), not by the tensor pipe.
+static TcV2Cfg pick_v2_cfg(int mtiles, int Co, int kblocks, int wtaps, bool tma_store) {
+  TcV2Cfg c;
+  const int co16 = round_up_i(Co, 16);
+  int best_bn = std::min(256, co16);
+  double best_cost = 1e30;
+  for (int nt = 1; nt <= 16; ++nt) {
+    int bn = round_up_i(ceil_div(co16, nt), 16);
+    // the TMA-store epilogue writes 64-column chunks: an N tile that is not the last one must be a multiple of 64
+    if (tma_store && nt > 1) bn = round_up_i(bn, 64);
+    if (bn > 256) continue;
+    if (bn < 64 && co16 >= 64) break;
+    const int ntiles = ceil_div(Co, bn);
+    const long long tiles = (long long)mtiles * ntiles;
+    const long long rounds = ceil_div64(tiles, kNumSMs);
+    const double cost = (double)rounds * (16384.0 + 128.0 * bn + 3000.0 / std::max(1, kblocks * wtaps));
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; }
+  }
+  c.BN = best_bn;
+  c.n_mtiles = mtiles;
+  c.n_ntiles = ceil_div(Co, c.BN);
+  c.total_tiles = c.n_mtiles * c.n_ntiles;
+  c.tma_store = tma_store ? 1 : 0;
+  c.acc_stride = 32;
+  while (c.acc_stride < c.BN) c.acc_stride <<= 1;
+  c.tmem_cols = 2 * c.acc_stride;
+  const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - kV2StagingBytes;
+  c.bres_bytes = wtaps * kblocks * c.BN * 128;
+  c.b_resident = (c.n_ntiles == 1 && c.bres_bytes <= 128 * 1024 && c.bres_bytes + 3 * kABytes <= budget) ? 1 : 0;
+  if (!c.b_resident) c.bres_bytes = 0;
+  c.stage_bytes = kABytes + (c.b_resident ? 0 : c.BN * 128);
+  c.stages = std::max(2, std::min(8, (budget - c.bres_bytes) / c.stage_bytes));
+  c.smem_bytes = c.stages * c.stage_bytes + c.bres_bytes + kV2StagingBytes + 1024 + 256;
+  return c;
+}
+
+static int launch_fprop_v2(const TcMaps& maps, const TcFpropParams& p, const TcV2Cfg& cfg, cudaStream_t st) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail((int)e, "dc_conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const int grid = std::min(cfg.total_tiles, kNumSMs);
+  conv_gemm_tc2_kernel<<<grid, kTcThreads, cfg.smem_bytes, st>>>(maps, p, cfg);
+  return launch_status("dc_conv_gemm_tc");
+}
+
+static bool use_v1_kernel() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DEEPCAM_B200_TC_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 template <int BNW>
 static int launch_wgrad(const TcMaps& maps, const TcWgradParams& p, dim3 grid, cudaStream_t st) {
   using Cfg = WgradCfg<BNW>;
@@ -677,6 +1093,16 @@ int dc_conv_gemm_tc(const dc_conv_desc* d, dc_view in, const void* w, const floa
   if (int r = build_gather("dc_conv_gemm_tc", d, in, p.TH, p.TW, maps, p)) return r;
   const long long Ktot = (long long)d->wtaps * p.kblocks * 64;
   const int mtiles = p.tiles_x * p.tiles_y * out.n;
+  if (!use_v1_kernel()) {
+    const bool tma_store = p.out_vec_ok != 0;
+    const TcV2Cfg c2 = pick_v2_cfg(mtiles, out.c, p.kblocks, d->wtaps, tma_store);
+    if (int r = encode_weight_map(&maps.b, w, Ktot, out.c, c2.BN, "dc_conv_gemm_tc")) return r;
+    if (tma_store) {
+      if (int r = encode_act_map(&maps.c, out.ptr, out.c, out.w, out.h, out.n, out.sw, out.sh, out.sn, p.TW, p.TH, "dc_conv_gemm_tc(out)"))
+        return r;
+    }
+    return launch_fprop_v2(maps, p, c2, as_stream(stream));
+  }
   const TcFpropCfg cfg = pick_fprop_cfg(mtiles, out.c);
   if (int r = encode_weight_map(&maps.b, w, Ktot, out.c, cfg.BN, "dc_conv_gemm_tc")) return r;
   return launch_fprop(maps, p, cfg, mtiles, ceil_div(out.c, cfg.BN), as_stream(stream));
@@ -698,16 +1124,20 @@ int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, 
   if (int r = build_gather("dc_conv_wgrad_tc", d, in, p.TH, p.TW, maps, p)) return r;
   if (int r = encode_act_map(&maps.b, dout.ptr, dout.c, dout.w, dout.h, dout.n, dout.sw, dout.sh, dout.sn, p.TW, p.TH, "dc_conv_wgrad_tc"))
     return r;
-  const int BNW = in.c <= 64 ? 64 : 128;
+  // ci tile: 256 when it does not waste columns (wider tiles halve the dY re-reads from L2), else 128 / 64
+  const int BNW = in.c <= 64 ? 64 : ((in.c > 128 && (in.c % 256 == 0 || in.c % 256 > 128)) ? 256 : 128);
   p.n_ci_tiles = ceil_div(in.c, BNW);
   const int n_co_tiles = ceil_div(dout.c, 128);
   const int tiles = n_co_tiles * p.n_ci_tiles * d->ntaps;
-  int splits = std::max(1, std::min(p.mtiles_total, ceil_div(kNumSMs * 2, tiles)));
+  // one CTA per SM (the stages fill the shared memory): split the pixel reduction so that the grid is one wave
+  int splits = std::max(1, std::min(p.mtiles_total, kNumSMs / std::max(1, tiles)));
   p.mtiles_per_split = ceil_div(p.mtiles_total, splits);
   splits = ceil_div(p.mtiles_total, p.mtiles_per_split);
+  p.vec_red = (in.c % 4 == 0 && (reinterpret_cast<uintptr_t>(G) % 16) == 0) ? 1 : 0;
   dim3 grid(n_co_tiles * p.n_ci_tiles, d->ntaps, splits);
   cudaStream_t st = as_stream(stream);
   if (BNW == 64) return launch_wgrad<64>(maps, p, grid, st);
+  if (BNW == 256) return launch_wgrad<256>(maps, p, grid, st);
   return launch_wgrad<128>(maps, p, grid, st);
 }
 
