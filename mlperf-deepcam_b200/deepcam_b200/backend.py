@@ -6,6 +6,8 @@ a torch-CPU interpreter of the same engine operations, used only to check the gr
 Layer specs (ConvSpec / DwSpec / BnSpec) reference the fp32 master parameters owned by the nn.Modules of
 architecture/deeplab_xception.py; kernel-layout copies (bf16, packed) are caches keyed on the parameter version.
 """
+import contextlib
+
 import torch
 
 from . import convdesc, ops
@@ -109,6 +111,8 @@ class CudaBackend:
         self.graph_mode = False       # True while the owning plan captures CUDA graphs (engine._GraphPlan)
         self.arena = None
         self.arena_used = 0
+        self.side_stream = None       # set by a graph plan: weight-gradient kernels run on a parallel graph branch
+        self._side_dirty = False
 
     # ---- memory -----------------------------------------------------------------------------------
     def empty(self, n, h, w, c, dtype=None):
@@ -134,6 +138,30 @@ class CudaBackend:
             ops.fill_zero(t)
             self.launches += 1
         return t
+
+    @contextlib.contextmanager
+    def side_branch(self):
+        """Weight-gradient kernels only feed the optimizer, so inside a captured backward they run on a second stream
+        (a parallel branch of the CUDA graph) and overlap with the latency-bound main chain of data-gradient
+        kernels.  Everything they read was produced on the main stream before the fork; buffers stay alive for the
+        whole capture and zero-initialised scratch comes from the arena, so there is no reuse hazard."""
+        if self.side_stream is None:
+            yield
+            return
+        main = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side_stream.wait_event(ev)
+        self._side_dirty = True
+        with torch.cuda.stream(self.side_stream):
+            yield
+
+    def join_side(self):
+        if self.side_stream is not None and self._side_dirty:
+            ev = torch.cuda.Event()
+            ev.record(self.side_stream)
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            self._side_dirty = False
 
     def begin_arena(self, nbytes):
         self.arena = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -288,7 +316,7 @@ class CudaBackend:
             ops.unpack_wgrad(G, K, N, kk, False, wgrad, k_stride=ks)
             self.launches += 2
         if bgrad is not None:
-            ws = self.scratch(spec.co, torch.float64)
+            ws = self.scratch(spec.co, torch.float64, zero=True)
             ops.channel_sum(dy, ws, bgrad)
             self.launches += 2
         return wgrad

@@ -181,7 +181,8 @@ class Engine:
             return
         if spec.weight.requires_grad:
             bgrad = self.grads.view(spec.bias) if (spec.bias is not None and spec.bias.requires_grad) else None
-            self.be.conv_bwd_weight(x.t, dy, spec, self.grads.view(spec.weight), bgrad)
+            with self.be.side_branch():
+                self.be.conv_bwd_weight(x.t, dy, spec, self.grads.view(spec.weight), bgrad)
             self.grads.ready(spec.weight)
             if bgrad is not None:
                 self.grads.ready(spec.bias)
@@ -203,7 +204,8 @@ class Engine:
         if dy is None:
             return
         if spec.weight.requires_grad:
-            self.be.dw_bwd_weight(x.t, dy, spec, self.grads.view(spec.weight))
+            with self.be.side_branch():
+                self.be.dw_bwd_weight(x.t, dy, spec, self.grads.view(spec.weight))
             self.grads.ready(spec.weight)
         if x.needs_grad:
             dx, acc = self.grad_target(x)
@@ -385,6 +387,8 @@ class _GraphPlan:
         self.need_grad = need_grad
         self.be = CudaBackend(_PRECISIONS[precision], device)
         self.be.graph_mode = True
+        if need_grad and os.environ.get("DEEPCAM_B200_SIDE_BRANCH", "1") not in ("0", "false", ""):
+            self.be.side_stream = torch.cuda.Stream(device=device)
         self.pool = torch.cuda.graph_pool_handle()
         self.params = list(params)
         self.guard = _pointer_guard(module, self.params)
@@ -479,6 +483,7 @@ class _GraphPlan:
                         i += 1
                         if sync is not None and sync.deferred:
                             break
+                    be.join_side()                          # the weight-gradient branch rejoins before the segment ends
                 buckets = []
                 if sync is not None:
                     buckets, sync.deferred = sync.deferred, None

@@ -29,6 +29,10 @@ class TorchBackend:
     def empty(self, n, h, w, c, dtype=None):
         return torch.full((n, h, w, c), float("nan"), dtype=dtype or self.dtype)
 
+    def side_branch(self):
+        import contextlib
+        return contextlib.nullcontext()
+
     def fill_zero_flat(self, flat):
         flat.zero_()
 
