@@ -191,6 +191,19 @@ int dc_iou_finalize(const int64_t* counts, int num_classes, float* score_out, vo
 /* x[i] *= s  (1/world_size after an NCCL SUM all-reduce) */
 int dc_scale_f32(float* x, size_t count, float s, void* stream);
 
+/* ---- optimizer (optim.Adam / optim.AdamW over net.parameters(), TR:213-220, step at TR:364) ----------- */
+/* One launch for all parameters.  jobs_dev: DEVICE array; job i owns blocks [block_start, block_start + n_blocks).
+ * Update rule and state of torch.optim.Adam (adamw = 0: L2 weight decay added to the gradient) or AdamW (adamw = 1:
+ * decoupled decay); bias_c1 = 1 - beta1^t, bias_c2 = 1 - beta2^t for the step being taken (t >= 1).  Hyper-parameters are
+ * doubles: the fp32 scalars of the update (1 - beta, lr / bias_c1, ...) are derived in double like torch does in Python. */
+typedef struct dc_adam_job {
+  float* p; const float* g; float* m; float* v;
+  int64_t numel;
+  int32_t block_start, n_blocks;
+} dc_adam_job;
+int dc_adam_step_multi(const dc_adam_job* jobs_dev, int njobs, int total_blocks, double lr, double beta1, double beta2,
+                       double eps, double weight_decay, double bias_c1, double bias_c2, int adamw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -254,8 +254,8 @@ __device__ __forceinline__ void load_fwd_coef(const dc_bn_params& p, int C, int 
   }
 }
 
-template <typename T, int V>
-__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(dc_bn_params p, PixView<const T> y, PixView<const T> res, PixView<T> out,
+template <typename T, int V, int kUnroll>
+__global__ void __launch_bounds__(kBnThreads, 3) bn_apply_kernel(dc_bn_params p, PixView<const T> y, PixView<const T> res, PixView<T> out,
                                                               int C, long long npix, LaneMap m) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
@@ -368,8 +368,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(dc_bn_params 
   }
 }
 
-template <typename T, int V>
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(dc_bn_params p, PixView<const T> dout, PixView<const T> out,
+template <typename T, int V, int kUnroll>
+__global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_apply_kernel(dc_bn_params p, PixView<const T> dout, PixView<const T> out,
                                                                   PixView<const T> y, const void* rws_raw, PixView<T> dy, PixView<T> dres,
                                                                   int C, long long npix, LaneMap m) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -460,9 +460,10 @@ __global__ void double_to_float_kernel(const double* s, float* d, int n) {
 
 // ---- host side ---------------------------------------------------------------------------------------------
 // grid.x: enough blocks that every thread handles about `items` pixels, capped at 16 blocks per SM (grid-stride beyond)
-static inline dim3 bn_grid(const LaneMap& m, long long npix, int items) {
+constexpr int kApplyUnroll = 2;
+static inline dim3 bn_grid(const LaneMap& m, long long npix, int items, int blocks_per_sm_cap = 16) {
   long long gx = ceil_div64(npix, (long long)m.ppb * items);
-  long long cap = std::max<long long>(1, (long long)kNumSMs * 16 / m.gy);
+  long long cap = std::max<long long>(1, (long long)kNumSMs * blocks_per_sm_cap / m.gy);
   return dim3((unsigned)std::max<long long>(1, std::min(gx, cap)), (unsigned)m.gy, 1);
 }
 template <int NACC, int V> static inline size_t red_smem() { return (size_t)8 * 32 * NACC * V * sizeof(float); }
@@ -489,8 +490,9 @@ static int bn_apply_t(const dc_bn_params& p, const dc_view& y, const dc_view& re
   constexpr int V = vec16<T>::V;
   const long long npix = (long long)y.n * y.h * y.w;
   LaneMap m = lane_map(y.c, V);
-  dim3 grid = bn_grid(m, npix, kUnroll);
-  bn_apply_kernel<T, V><<<grid, kBnThreads, 0, st>>>(p, pix_view<const T>(y), pix_view<const T>(res), pix_view<T>(out), y.c, npix, m);
+  // element-wise: two pixels per thread and as many blocks as that needs (small register footprint, 3 blocks per SM)
+  dim3 grid = bn_grid(m, npix, kApplyUnroll, 1 << 20);
+  bn_apply_kernel<T, V, kApplyUnroll><<<grid, kBnThreads, 0, st>>>(p, pix_view<const T>(y), pix_view<const T>(res), pix_view<T>(out), y.c, npix, m);
   return launch_status("dc_bn_apply");
 }
 template <typename T>
@@ -510,8 +512,8 @@ static int bn_bwd_apply_t(const dc_bn_params& p, const dc_view& dout, const dc_v
   constexpr int V = vec16<T>::V;
   const long long npix = (long long)dout.n * dout.h * dout.w;
   LaneMap m = lane_map(dout.c, V);
-  dim3 grid = bn_grid(m, npix, kUnroll);
-  bn_bwd_apply_kernel<T, V><<<grid, kBnThreads, 0, st>>>(p, pix_view<const T>(dout), pix_view<const T>(out), pix_view<const T>(y), rws,
+  dim3 grid = bn_grid(m, npix, kApplyUnroll, 1 << 20);
+  bn_bwd_apply_kernel<T, V, kApplyUnroll><<<grid, kBnThreads, 0, st>>>(p, pix_view<const T>(dout), pix_view<const T>(out), pix_view<const T>(y), rws,
                                                          pix_view<T>(dy), pix_view<T>(dres), dout.c, npix, m);
   return launch_status("dc_bn_bwd_apply");
 }

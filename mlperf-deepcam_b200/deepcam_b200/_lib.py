@@ -39,6 +39,11 @@ class dc_pack_job(Structure):
                 ("dst_dtype", c_int32), ("block_start", c_int32), ("n_blocks", c_int32)]
 
 
+class dc_adam_job(Structure):
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("numel", c_int64),
+                ("block_start", c_int32), ("n_blocks", c_int32)]
+
+
 # name -> (restype, argtypes); must list every symbol declared in include/deepcam_b200.h
 SIGNATURES = {
     "dc_abi_version": (c_int, []),
@@ -73,6 +78,8 @@ SIGNATURES = {
     "dc_argmax_iou": (c_int, [dc_view, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "dc_iou_finalize": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "dc_scale_f32": (c_int, [c_void_p, c_size_t, c_float, c_void_p]),
+    "dc_adam_step_multi": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_double, c_double,
+                                   c_double, c_int, c_void_p]),
 }
 
 _LIB = None

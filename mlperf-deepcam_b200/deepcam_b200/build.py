@@ -13,7 +13,7 @@ PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))      # mlp
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdeepcam_b200.so")
-SOURCES = ["layout.cu", "bn.cu", "dw.cu", "pool.cu", "loss_metric.cu", "simt_conv.cu", "tc_conv.cu"]
+SOURCES = ["layout.cu", "bn.cu", "dw.cu", "pool.cu", "loss_metric.cu", "simt_conv.cu", "tc_conv.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -389,3 +389,31 @@ def test_conv_tcgen05_writes_concat_slice():
     be.conv_fwd(to_nhwc(x, torch.bfloat16), ConvSpec("c", mod.weight), cat[..., 512:768])
     assert rel(from_nhwc(cat[..., 512:768]), ref) < 2e-2
     assert float(cat[..., :512].abs().max()) == 0.0 and float(cat[..., 768:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("adamw", [False, True])
+def test_fused_adam_matches_torch(adamw):
+    """deepcam_b200.optim.FusedAdam(W) against torch.optim.Adam(W) (the optimizers the reference builds, TR:213-220)."""
+    from deepcam_b200.optim import FusedAdam, FusedAdamW
+    torch.manual_seed(3)
+    shapes = [(728, 728, 1, 1), (7,), (256, 3, 3, 3), (1,), (33, 5)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, device=dev())) for s in shapes]
+    my_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    kw = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2 if adamw else 1e-6)
+    ref = (torch.optim.AdamW if adamw else torch.optim.Adam)(ref_p, **kw)
+    mine = (FusedAdamW if adamw else FusedAdam)(my_p, **kw)
+    for step in range(4):
+        for a, b in zip(ref_p, my_p):
+            g = torch.randn_like(a)
+            a.grad = g.clone()
+            b.grad = g.clone()
+        ref.step()
+        mine.step()
+        for a, b in zip(ref_p, my_p):
+            assert rel(b, a) < 1e-6, (step, tuple(a.shape))
+    sd_ref, sd_mine = ref.state_dict(), mine.state_dict()
+    assert sd_ref["state"].keys() == sd_mine["state"].keys()
+    for k in sd_ref["state"]:
+        assert set(sd_ref["state"][k]) == set(sd_mine["state"][k]) == {"step", "exp_avg", "exp_avg_sq"}
+        assert float(sd_ref["state"][k]["step"]) == float(sd_mine["state"][k]["step"]) == 4.0
+        assert rel(sd_mine["state"][k]["exp_avg_sq"], sd_ref["state"][k]["exp_avg_sq"]) < 1e-6
