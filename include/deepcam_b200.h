@@ -127,7 +127,7 @@ int dc_dw_bwd_weight(dc_view in, dc_view dout, int stride, int dil, float* G9c, 
 
 /* ---- BatchNorm2d (+ReLU, +residual add) (normalizer, DX:70,129,283,348,399; relu DX:79,147; add DX:120) ---- */
 /* Per-layer BatchNorm workspace, dc_bn_ws_bytes(C) bytes, ZEROED by the caller before dc_bn_stats / dc_bn_bwd_reduce:
- *   double sums[2][C] | float coef[4][C] | uint32 ticket.
+ *   double sums[2][C] | float coef[4][C] | uint32 ticket[16].
  * The reduction kernels accumulate fp64 sums with atomics; the last block to finish converts them into fp32
  * per-channel coefficients (forward: scale, shift, mean, invstd; backward: A, B, D with dy = A*g + B*y + D), so the
  * element-wise kernels carry no double-precision prologue and no separate finalize launch exists. */
@@ -159,6 +159,13 @@ int dc_bn_bwd_reduce(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y
 /* backward pass 2: dy = A*g + B*y + D (= gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))); optional dres (+)= g */
 int dc_bn_bwd_apply(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, const void* rws,
                     dc_view dy, dc_view dres, void* stream);
+/* One-pass variants for tensors small enough to be held in shared memory across the GPU (dc_bn_onepass_ok): statistics
+ * and normalisation (forward) / reduction and gradient (backward) in ONE launch with an inter-block barrier; the grid
+ * never exceeds the SM count, so all blocks are co-resident.  Same workspace contract as the two-pass entry points. */
+int dc_bn_onepass_ok(int C, long long npix, int dtype, int backward);
+int dc_bn_fwd_onepass(const dc_bn_params* p, dc_view y, dc_view residual, dc_view out, void* stream);
+int dc_bn_bwd_onepass(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, void* rws, dc_view dy, dc_view dres,
+                      float* dgamma, float* dbeta, void* stream);
 /* per-channel sum over n,h,w into fp32 [C] (bias gradient of upsample.conv1.6, DX:366); ws_c: C doubles of scratch */
 int dc_channel_sum(dc_view x, double* ws_c, float* out_c, void* stream);
 

@@ -9,7 +9,7 @@
 // Statistics: per-thread fp32 partials -> block reduction -> fp64 atomics into the per-layer workspace; the LAST
 // block to finish (atomic ticket) turns the sums into fp32 per-channel coefficients, so the apply kernels carry
 // no double-precision prologue and no extra "finalize" launch is needed.
-//   workspace (dc_bn_ws_bytes(C) bytes, zeroed by the caller):  double sums[2][C] | float coef[4][C] | uint32 ticket
+//   workspace (dc_bn_ws_bytes(C) bytes, zeroed by the caller):  double sums[2][C] | float coef[4][C] | uint32 ticket[16]
 //     forward : coef = scale, shift, mean, invstd            (out = y*scale + shift)
 //     backward: coef = A, B, D                               (dy  = A*g + B*y + D,  g = dout masked by ReLU)
 // HBM-bound: algorithmic bytes = each tensor read or written exactly once.
@@ -67,13 +67,13 @@ struct LaneMap {
   int ppb;       // pixels per block = 8 warps * ppw
   int gy;        // channel blocks
 };
-static inline LaneMap lane_map(int C, int V) {
+static inline LaneMap lane_map(int C, int V, int warps = 8) {
   LaneMap m;
   m.cv = C / V;
   m.cvp = 1;
   while (m.cvp < 32 && m.cvp < m.cv) m.cvp <<= 1;
   m.ppw = 32 / m.cvp;
-  m.ppb = 8 * m.ppw;
+  m.ppb = warps * m.ppw;
   m.gy = ceil_div(m.cv, m.cvp);
   return m;
 }
@@ -121,8 +121,8 @@ constexpr int kBnThreads = 256;
 constexpr int kUnroll = 4;
 
 // Block reduction of NACC x V per-thread partials over the pixel lanes of a block, then fp64 atomics.
-// smem: float red[8 warps][32 lanes][NACC*V]
-template <int NACC, int V>
+// smem: float red[NW warps][32 lanes][NACC*V]
+template <int NACC, int V, int NW = 8>
 __device__ __forceinline__ void reduce_to_ws(float (&acc)[NACC][V], double* dst, int C, int cvp, int cv_base, int cv_count) {
   extern __shared__ float red[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -141,11 +141,11 @@ __device__ __forceinline__ void reduce_to_ws(float (&acc)[NACC][V], double* dst,
       for (int j = 0; j < V; ++j) red[(warp * 32 + lane) * PER + a * V + j] = acc[a][j];
   }
   __syncthreads();
-  for (int col = threadIdx.x; col < cvp * PER; col += kBnThreads) {
+  for (int col = threadIdx.x; col < cvp * PER; col += NW * 32) {
     const int l = col / PER, r = col - l * PER;
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[(w * 32 + l) * PER + r];
+    for (int w = 0; w < NW; ++w) s += red[(w * 32 + l) * PER + r];
     const int a = r / V, j = r - a * V;
     const int cvi = cv_base + l;
     if (l < cv_count) atomicAdd(dst + (size_t)a * C + cvi * V + j, (double)s);
@@ -518,6 +518,315 @@ static int bn_bwd_apply_t(const dc_bn_params& p, const dc_view& dout, const dc_v
   return launch_status("dc_bn_bwd_apply");
 }
 
+
+// ---- one-pass kernels for tensors that fit on chip -----------------------------------------------------------------
+// When a BatchNorm input is small enough to be held in shared memory across the whole GPU (the 50 middle-flow layers:
+// 2 x 48 x 72 x 728 bf16 = 10 MB over 147 SMs), statistics and normalisation run in ONE launch: every block loads its
+// slice once, keeps it in shared memory, publishes its partial sums, waits at an inter-block barrier (all blocks are
+// co-resident: grid <= number of SMs, one block per SM) and then applies the coefficients to the data it holds.  Compared
+// with the stats + apply pair this saves one launch, the serial finalize tail and one full read of the tensor.
+__device__ __forceinline__ void grid_barrier(unsigned* ticket, unsigned expected) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(ticket, 1u);
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ticket) : "memory");
+      if (seen < expected) __nanosleep(64);
+    } while (seen < expected);
+  }
+  __syncthreads();
+}
+
+constexpr int kOnePassWarps = 8;
+constexpr int kOnePassThreads = kOnePassWarps * 32;
+struct OnePassMap {
+  LaneMap m;
+  int gx;        // pixel blocks (grid.x); grid.y = m.gy channel blocks; gx * gy <= SM count
+  int K;         // vectors held per thread
+};
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kOnePassThreads, 1) bn_fwd_onepass_kernel(dc_bn_params p, PixView<const T> y, PixView<const T> res,
+                                                                       PixView<T> out, int C, long long npix, OnePassMap om) {
+  extern __shared__ float red[];                                    // [0, 16 KB): block reduction; then K*256 held vectors
+  uint4* hold = reinterpret_cast<uint4*>(reinterpret_cast<char*>(red) + kOnePassWarps * 32 * 2 * V * sizeof(float));
+  const LaneMap& m = om.m;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
+  const int cvi = blockIdx.y * m.cvp + cvl;
+  const bool ok = cvi < m.cv;
+  const int c0 = cvi * V;
+  float acc[2][V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  const long long stride = (long long)om.gx * m.ppb;
+  const long long pix0 = (long long)blockIdx.x * m.ppb + warp * m.ppw + psub;
+  if (ok) {
+    constexpr int U = 6;                      // loads in flight per thread
+    for (int k0 = 0; k0 < om.K; k0 += U) {
+      uint4 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long pix = pix0 + (k0 + u) * stride;
+        if (k0 + u < om.K && pix < npix) raw[u] = vec16<T>::ldraw(y.at(pix) + c0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long pix = pix0 + (k0 + u) * stride;
+        if (k0 + u < om.K && pix < npix) {
+          hold[(k0 + u) * kOnePassThreads + threadIdx.x] = raw[u];
+          float v[V];
+          vec16<T>::unpack(raw[u], v);
+#pragma unroll
+          for (int j = 0; j < V; ++j) { acc[0][j] += v[j]; acc[1][j] = fmaf(v[j], v[j], acc[1][j]); }
+        }
+      }
+    }
+  }
+  BnWs ws = bn_ws(const_cast<double*>(p.sums), C);
+  reduce_to_ws<2, V, kOnePassWarps>(acc, ws.sums, C, m.cvp, blockIdx.y * m.cvp, min(m.cvp, m.cv - blockIdx.y * m.cvp));
+  grid_barrier(ws.ticket + blockIdx.y, (unsigned)om.gx);
+  if (!ok) return;
+  // every thread derives the coefficients of its own channels (mean / variance in double, 1/sqrt in fp32)
+  const double inv_count = 1.0 / p.count;
+  float scale[V], shift[V];
+  const bool writer = (blockIdx.x == 0 && warp == 0 && psub == 0);
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int c = c0 + j;
+    const double sm = __ldcg(ws.sums + c), sq = __ldcg(ws.sums + C + c);
+    const double mean = sm * inv_count;
+    double var = sq * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float inv = inv_sqrt_f32((float)(var + (double)p.eps));
+    scale[j] = p.gamma[c] * inv;
+    shift[j] = p.beta[c] - (float)mean * scale[j];
+    if (writer) {
+      ws.coef[c] = scale[j];
+      ws.coef[C + c] = shift[j];
+      ws.coef[2 * C + c] = (float)mean;
+      ws.coef[3 * C + c] = inv;
+      if (p.running_mean != nullptr) {
+        const double unbias = p.count / (p.count - 1.0);
+        p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mean;
+        p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)(var * unbias);
+      }
+    }
+  }
+  const bool relu = (p.flags & DC_BN_RELU) != 0;
+  const bool has_res = res.p != nullptr;
+  for (int k = 0; k < om.K; ++k) {
+    const long long pix = pix0 + k * stride;
+    if (pix >= npix) break;
+    float v[V], r[V], o[V];
+    vec16<T>::unpack(hold[k * kOnePassThreads + threadIdx.x], v);
+    if (has_res) vec16<T>::unpack(vec16<T>::ldraw(res.at(pix) + c0), r);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      o[j] = fmaf(v[j], scale[j], shift[j]);
+      if (has_res) o[j] += r[j];
+      if (relu) o[j] = fmaxf(o[j], 0.f);
+    }
+    vec16<T>::st(out.at(pix) + c0, o);
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kOnePassThreads, 1) bn_bwd_onepass_kernel(dc_bn_params p, PixView<const T> dout, PixView<const T> out,
+                                                                       PixView<const T> y, void* rws_raw, PixView<T> dy, PixView<T> dres,
+                                                                       float* dgamma, float* dbeta, int C, long long npix, OnePassMap om) {
+  extern __shared__ float red[];
+  uint4* hold = reinterpret_cast<uint4*>(reinterpret_cast<char*>(red) + kOnePassWarps * 32 * 2 * V * sizeof(float));   // [K][256][2]: g, y
+  const LaneMap& m = om.m;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
+  const int cvi = blockIdx.y * m.cvp + cvl;
+  const bool ok = cvi < m.cv;
+  const int c0 = cvi * V;
+  const bool relu = (p.flags & DC_BN_RELU) != 0;
+  float acc[2][V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  const long long stride = (long long)om.gx * m.ppb;
+  const long long pix0 = (long long)blockIdx.x * m.ppb + warp * m.ppw + psub;
+  if (ok) {
+    constexpr int U = 3;                      // pixels (x 3 loads) in flight per thread
+    for (int k0 = 0; k0 < om.K; k0 += U) {
+      uint4 graws[U], yraws[U], oraws[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long pix = pix0 + (k0 + u) * stride;
+        if (k0 + u < om.K && pix < npix) {
+          graws[u] = vec16<T>::ldraw(dout.at(pix) + c0);
+          yraws[u] = vec16<T>::ldraw(y.at(pix) + c0);
+          if (relu) oraws[u] = vec16<T>::ldraw(out.at(pix) + c0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+      const int k = k0 + u;
+      const long long pix = pix0 + k * stride;
+      if (k < om.K && pix < npix) {
+        const uint4 graw = graws[u];
+        const uint4 yraw = yraws[u];
+        float g[V], v[V];
+        vec16<T>::unpack(graw, g);
+        vec16<T>::unpack(yraw, v);
+        if (relu) {
+          float o[V];
+          vec16<T>::unpack(oraws[u], o);
+#pragma unroll
+          for (int j = 0; j < V; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) { acc[0][j] += g[j]; acc[1][j] = fmaf(g[j], v[j], acc[1][j]); }
+        // the masked gradient is kept in fp32-exact form only if T is float; for bf16 the mask just zeroes lanes, so
+        // re-packing loses nothing
+        uint4 gm;
+        if (sizeof(T) == 4) gm = make_uint4(__float_as_uint(g[0]), __float_as_uint(g[1]), __float_as_uint(g[2]), __float_as_uint(g[3]));
+        else {
+          gm = graw;
+          if (relu) {
+            uint32_t w[4] = {graw.x, graw.y, graw.z, graw.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (g[(2 * q) % V] == 0.f) w[q] &= 0xffff0000u;
+              if (g[(2 * q + 1) % V] == 0.f) w[q] &= 0x0000ffffu;
+            }
+            gm = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        hold[(k * kOnePassThreads + threadIdx.x) * 2] = gm;
+        hold[(k * kOnePassThreads + threadIdx.x) * 2 + 1] = yraw;
+      }
+      }
+    }
+  }
+  BnWs rws = bn_ws(rws_raw, C);
+  reduce_to_ws<2, V, kOnePassWarps>(acc, rws.sums, C, m.cvp, blockIdx.y * m.cvp, min(m.cvp, m.cv - blockIdx.y * m.cvp));
+  grid_barrier(rws.ticket + blockIdx.y, (unsigned)om.gx);
+  if (!ok) return;
+  const bool train = (p.flags & DC_BN_TRAIN) != 0;
+  const double inv_count = 1.0 / p.count;
+  const bool writer = (blockIdx.x == 0 && warp == 0 && psub == 0);
+  float A[V], B[V], D[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int c = c0 + j;
+    double mean, inv;
+    if (train) {
+      const BnWs fws = bn_ws(const_cast<double*>(p.sums), C);
+      mean = p.sums[c] * inv_count;
+      inv = (double)fws.coef[3 * C + c];
+    } else {
+      mean = (double)p.running_mean[c];
+      inv = (double)inv_sqrt_f32(p.running_var[c] + p.eps);
+    }
+    const double sg = __ldcg(rws.sums + c), sgy = __ldcg(rws.sums + C + c);
+    const double sgx = inv * (sgy - mean * sg);
+    const double scale = (double)p.gamma[c] * inv;
+    double a = scale, b = 0.0, d = 0.0;
+    if (train) {
+      const double mg = sg * inv_count, mgx = sgx * inv_count;
+      b = -scale * inv * mgx;
+      d = -scale * mg + scale * mean * inv * mgx;
+    }
+    A[j] = (float)a; B[j] = (float)b; D[j] = (float)d;
+    if (writer) {
+      if (dgamma) dgamma[c] = (float)sgx;
+      if (dbeta) dbeta[c] = (float)sg;
+      rws.coef[c] = A[j]; rws.coef[C + c] = B[j]; rws.coef[2 * C + c] = D[j];
+    }
+  }
+  const bool has_res = dres.p != nullptr;
+  const bool res_write = (p.flags & DC_BN_RES_WRITE) != 0;
+  const bool has_dy = dy.p != nullptr;
+  for (int k = 0; k < om.K; ++k) {
+    const long long pix = pix0 + k * stride;
+    if (pix >= npix) break;
+    float g[V], v[V];
+    vec16<T>::unpack(hold[(k * kOnePassThreads + threadIdx.x) * 2], g);
+    vec16<T>::unpack(hold[(k * kOnePassThreads + threadIdx.x) * 2 + 1], v);
+    if (has_res) {
+      float rr[V];
+      if (!res_write) {
+        float r[V];
+        vec16<T>::unpack(vec16<T>::ldraw(dres.at(pix) + c0), r);
+#pragma unroll
+        for (int j = 0; j < V; ++j) rr[j] = g[j] + r[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) rr[j] = g[j];
+      }
+      vec16<T>::st(dres.at(pix) + c0, rr);
+    }
+    if (has_dy) {
+      float d[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) d[j] = fmaf(A[j], g[j], fmaf(B[j], v[j], D[j]));
+      vec16<T>::st(dy.at(pix) + c0, d);
+    }
+  }
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+    else n = kNumSMs;
+  }
+  return n;
+}
+// per_vec = 16-byte vectors held per (thread, step): 1 forward, 2 backward
+static bool onepass_map(int C, int V, long long npix, int per_vec, OnePassMap& om) {
+  om.m = lane_map(C, V, kOnePassWarps);
+  if (om.m.gy > 16) return false;
+  om.gx = sm_count() / om.m.gy;
+  if (om.gx < 1) return false;
+  const long long per_round = (long long)om.gx * om.m.ppb;
+  const long long K = ceil_div64(npix, per_round);
+  const long long smem = (long long)kOnePassWarps * 32 * 2 * V * 4 + K * kOnePassThreads * 16 * per_vec;
+  if (K < 1 || K > 64 || smem > 200 * 1024) return false;
+  om.K = (int)K;
+  return true;
+}
+template <typename KernelT>
+static int set_smem_attr(KernelT kernel, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+  if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+template <typename T>
+static int bn_fwd_onepass_t(const dc_bn_params& p, const dc_view& y, const dc_view& res, const dc_view& out, cudaStream_t st) {
+  constexpr int V = vec16<T>::V;
+  const long long npix = (long long)y.n * y.h * y.w;
+  OnePassMap om;
+  if (!onepass_map(y.c, V, npix, 1, om)) return fail(-2, "dc_bn_fwd_onepass: tensor does not fit on chip");
+  if (int r = set_smem_attr(bn_fwd_onepass_kernel<T, V>, "dc_bn_fwd_onepass")) return r;
+  const size_t smem = (size_t)kOnePassWarps * 32 * 2 * V * 4 + (size_t)om.K * kOnePassThreads * 16;
+  bn_fwd_onepass_kernel<T, V><<<dim3(om.gx, om.m.gy, 1), kOnePassThreads, smem, st>>>(p, pix_view<const T>(y), pix_view<const T>(res),
+                                                                                 pix_view<T>(out), y.c, npix, om);
+  return launch_status("dc_bn_fwd_onepass");
+}
+template <typename T>
+static int bn_bwd_onepass_t(const dc_bn_params& p, const dc_view& dout, const dc_view& out, const dc_view& y, void* rws, const dc_view& dy,
+                            const dc_view& dres, float* dgamma, float* dbeta, cudaStream_t st) {
+  constexpr int V = vec16<T>::V;
+  const long long npix = (long long)y.n * y.h * y.w;
+  OnePassMap om;
+  if (!onepass_map(y.c, V, npix, 2, om)) return fail(-2, "dc_bn_bwd_onepass: tensor does not fit on chip");
+  if (int r = set_smem_attr(bn_bwd_onepass_kernel<T, V>, "dc_bn_bwd_onepass")) return r;
+  const size_t smem = (size_t)kOnePassWarps * 32 * 2 * V * 4 + (size_t)om.K * kOnePassThreads * 32;
+  bn_bwd_onepass_kernel<T, V><<<dim3(om.gx, om.m.gy, 1), kOnePassThreads, smem, st>>>(p, pix_view<const T>(dout), pix_view<const T>(out),
+                                                                                 pix_view<const T>(y), rws, pix_view<T>(dy), pix_view<T>(dres),
+                                                                                 dgamma, dbeta, y.c, npix, om);
+  return launch_status("dc_bn_bwd_onepass");
+}
+
 }  // namespace dc
 
 using namespace dc;
@@ -543,7 +852,7 @@ static bool views_ok(const dc_view& main, const dc_view* opts, int nopt) {
 
 extern "C" {
 
-size_t dc_bn_ws_bytes(int C) { return (size_t)32 * C + 16; }
+size_t dc_bn_ws_bytes(int C) { return (size_t)32 * C + 64; }
 
 int dc_bn_stats(const dc_bn_params* p, dc_view y, void* stream) {
   DC_REQUIRE(p != nullptr && p->sums != nullptr, "dc_bn_stats: null params / workspace");
@@ -597,6 +906,41 @@ int dc_bn_bwd_apply(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y,
   cudaStream_t st = as_stream(stream);
   return dout.dtype == DC_F32 ? bn_bwd_apply_t<float>(*p, dout, out, y, rws, dy, dres, st)
                               : bn_bwd_apply_t<__nv_bfloat16>(*p, dout, out, y, rws, dy, dres, st);
+}
+
+/* 1 when the one-pass kernels can handle a [npix, C] tensor of this dtype (everything held on chip), else 0 */
+int dc_bn_onepass_ok(int C, long long npix, int dtype, int backward) {
+  OnePassMap om;
+  const int V = dtype == DC_F32 ? 4 : 8;
+  if (C % V) return 0;
+  return onepass_map(C, V, npix, backward ? 2 : 1, om) ? 1 : 0;
+}
+
+/* statistics + coefficients + running statistics + out = [relu](bn(y) [+ residual]) in one launch (train mode) */
+int dc_bn_fwd_onepass(const dc_bn_params* p, dc_view y, dc_view residual, dc_view out, void* stream) {
+  DC_REQUIRE(p != nullptr && p->sums != nullptr && (p->flags & DC_BN_TRAIN) && !(p->flags & DC_BN_IDENTITY),
+             "dc_bn_fwd_onepass: train-mode parameters with a workspace are required");
+  const dc_view opts[2] = {out, residual};
+  DC_REQUIRE(view_ok(out) && views_ok(y, opts, 2), "dc_bn_fwd_onepass: views must be channel-contiguous, 16-byte aligned and of one shape/dtype");
+  DC_REQUIRE(p->gamma && p->beta, "dc_bn_fwd_onepass: gamma/beta required");
+  DC_REQUIRE(p->count > 1.0, "dc_bn_fwd_onepass: Expected more than 1 value per channel when training (count=%g)", p->count);
+  cudaStream_t st = as_stream(stream);
+  return y.dtype == DC_F32 ? bn_fwd_onepass_t<float>(*p, y, residual, out, st) : bn_fwd_onepass_t<__nv_bfloat16>(*p, y, residual, out, st);
+}
+
+/* dc_bn_bwd_reduce + dc_bn_bwd_apply in one launch */
+int dc_bn_bwd_onepass(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, void* rws, dc_view dy, dc_view dres,
+                      float* dgamma, float* dbeta, void* stream) {
+  DC_REQUIRE(p != nullptr && rws != nullptr && !(p->flags & DC_BN_IDENTITY), "dc_bn_bwd_onepass: null argument");
+  const dc_view opts[4] = {dout, out, dy, dres};
+  DC_REQUIRE(view_ok(dout) && views_ok(y, opts, 4), "dc_bn_bwd_onepass: bad views");
+  if (p->flags & DC_BN_RELU) DC_REQUIRE(view_ok(out), "dc_bn_bwd_onepass: out view required for ReLU mask");
+  DC_REQUIRE(p->gamma != nullptr, "dc_bn_bwd_onepass: gamma required");
+  if (p->flags & DC_BN_TRAIN) DC_REQUIRE(p->sums != nullptr, "dc_bn_bwd_onepass: forward workspace required in train mode");
+  else DC_REQUIRE(p->running_mean && p->running_var, "dc_bn_bwd_onepass: running statistics required in eval mode");
+  cudaStream_t st = as_stream(stream);
+  return y.dtype == DC_F32 ? bn_bwd_onepass_t<float>(*p, dout, out, y, rws, dy, dres, dgamma, dbeta, st)
+                           : bn_bwd_onepass_t<__nv_bfloat16>(*p, dout, out, y, rws, dy, dres, dgamma, dbeta, st);
 }
 
 /* channel sum with a caller-provided double workspace of C elements */

@@ -67,6 +67,10 @@ SIGNATURES = {
     "dc_bn_apply": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p]),
     "dc_bn_bwd_reduce": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dc_bn_bwd_apply": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, dc_view, dc_view, c_void_p]),
+    "dc_bn_onepass_ok": (c_int, [c_int, c_int64, c_int, c_int]),
+    "dc_bn_fwd_onepass": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p]),
+    "dc_bn_bwd_onepass": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, dc_view, dc_view, c_void_p,
+                                  c_void_p, c_void_p]),
     "dc_channel_sum": (c_int, [dc_view, c_void_p, c_void_p, c_void_p]),
     "dc_gap_fwd": (c_int, [dc_view, c_void_p, c_void_p]),
     "dc_broadcast_hw": (c_int, [c_void_p, dc_view, c_void_p]),

@@ -7,6 +7,7 @@ Layer specs (ConvSpec / DwSpec / BnSpec) reference the fp32 master parameters ow
 architecture/deeplab_xception.py; kernel-layout copies (bf16, packed) are caches keyed on the parameter version.
 """
 import contextlib
+import os
 
 import torch
 
@@ -111,6 +112,10 @@ class CudaBackend:
         self.graph_mode = False       # True while the owning plan captures CUDA graphs (engine._GraphPlan)
         self.arena = None
         self.arena_used = 0
+        # one-launch BatchNorm for on-chip-sized tensors (inter-block barrier; needs all blocks co-resident).  The
+        # backward variant is switched off by the data-parallel wrapper: NCCL kernels share the SMs during backward.
+        self.onepass = os.environ.get("DEEPCAM_B200_BN_ONEPASS", "1") not in ("0", "false", "")
+        self.onepass_bwd = True
         self.side_stream = None       # set by a graph plan: weight-gradient kernels run on a parallel graph branch
         self._side_dirty = False
 
@@ -366,6 +371,10 @@ class CudaBackend:
             flags |= DC_BN_TRAIN
         p = ops.bn_params(m.weight.detach(), m.bias.detach(), m.running_mean if track else None,
                           m.running_var if track else None, sums, n * h * w, mom, m.eps, flags)
+        if training and self.onepass and ops.bn_onepass_ok(c, n * h * w, y.dtype, False):
+            ops.bn_fwd_onepass(p, y, residual, out)     # statistics + normalisation in one launch (tensor held on chip)
+            self.launches += 1
+            return sums
         if training:
             ops.bn_stats(p, y)            # sums + coefficients + running statistics (last block finalizes)
             self.launches += 1
@@ -388,6 +397,10 @@ class CudaBackend:
             flags |= DC_BN_TRAIN
         p = ops.bn_params(m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var, sums, n * h * w, 0.0, m.eps, flags)
         rws = self.scratch(ops.bn_ws_elems(c), torch.float64, zero=True)
+        if self.onepass and self.onepass_bwd and ops.bn_onepass_ok(c, n * h * w, dout.dtype, True):
+            ops.bn_bwd_onepass(p, dout, out if relu else None, y, rws, dy, dres, dgamma, dbeta)
+            self.launches += 1
+            return
         ops.bn_bwd_reduce(p, dout, out if relu else None, y, rws, dgamma, dbeta)
         ops.bn_bwd_apply(p, dout, out if relu else None, y, rws, dy, dres)
         self.launches += 2

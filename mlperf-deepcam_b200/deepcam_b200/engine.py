@@ -309,6 +309,8 @@ class _PlanFunction(torch.autograd.Function):
         inputs, params = tensors[:n_in], tensors[n_in:]
         device = inputs[0].device
         be = _make_backend(precision, device)
+        if getattr(module, "_dc_grad_sync", None) is not None and hasattr(be, "onepass_bwd"):
+            be.onepass_bwd = False       # NCCL kernels share the SMs during backward: no inter-block barriers there
         need_grad = bool(need_grad)
         grads = None
         if need_grad:
@@ -387,6 +389,8 @@ class _GraphPlan:
         self.need_grad = need_grad
         self.be = CudaBackend(_PRECISIONS[precision], device)
         self.be.graph_mode = True
+        if getattr(module, "_dc_grad_sync", None) is not None:
+            self.be.onepass_bwd = False  # NCCL kernels share the SMs during backward: no inter-block barriers there
         if need_grad and os.environ.get("DEEPCAM_B200_SIDE_BRANCH", "1") not in ("0", "false", ""):
             self.be.side_stream = torch.cuda.Stream(device=device)
         self.pool = torch.cuda.graph_pool_handle()

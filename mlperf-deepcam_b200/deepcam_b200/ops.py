@@ -253,7 +253,35 @@ def dw_bwd_weight(x, dout, stride, dil, G9c):
 # ---- batch norm -----------------------------------------------------------------------------------------
 def bn_ws_elems(c):
     """float64 elements of the per-layer BatchNorm workspace (dc_bn_ws_bytes)."""
-    return (32 * c + 16) // 8
+    return (32 * c + 64) // 8
+
+
+_onepass_cache = {}
+
+
+def bn_onepass_ok(c, npix, dtype, backward):
+    key = (c, npix, dtype, bool(backward))
+    v = _onepass_cache.get(key)
+    if v is None:
+        v = _lib.load().dc_bn_onepass_ok(c, npix, _DT[dtype], int(bool(backward))) == 1
+        _onepass_cache[key] = v
+    return v
+
+
+def bn_fwd_onepass(params, y, residual, out):
+    _require_cuda(y, residual, out)
+    _timed("bn_fwd_onepass", 6.0 * y.numel(), _nbytes(y, residual, out),
+           lambda: _lib.load().dc_bn_fwd_onepass(ctypes.byref(params), view(y), view(residual), view(out), _stream()),
+           "dc_bn_fwd_onepass", tag=_shape_tag(y) + (" res" if residual is not None else ""))
+    return out
+
+
+def bn_bwd_onepass(params, dout, out, y, rws, dy, dres, dgamma, dbeta):
+    _require_cuda(dout, rws)
+    _timed("bn_bwd_onepass", 12.0 * dout.numel(), _nbytes(dout, out, y, dy, dres),
+           lambda: _lib.load().dc_bn_bwd_onepass(ctypes.byref(params), view(dout), view(out), view(y), _p(rws), view(dy),
+                                                 view(dres), _p(dgamma), _p(dbeta), _stream()),
+           "dc_bn_bwd_onepass", tag=_shape_tag(dout) + (" res" if dres is not None else ""))
 
 
 def bn_stats(params, y):

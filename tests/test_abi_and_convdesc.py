@@ -50,7 +50,7 @@ def test_argument_validation_without_gpu():
     assert b"ntaps" in lib.dc_last_error_string()
     rc = lib.dc_bn_stats(None, v, None)
     assert rc < 0 and b"dc_bn_stats" in lib.dc_last_error_string()
-    assert lib.dc_bn_ws_bytes(728) == 32 * 728 + 16
+    assert lib.dc_bn_ws_bytes(728) == 32 * 728 + 64
     rc = lib.dc_iou_counts(None, None, 0, 3, None, None)
     assert rc < 0
 
