@@ -122,8 +122,9 @@ int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, 
 /* out[n,y,x,c] = sum_{kh,kw} in[n, y*stride - dil + kh*dil, x*stride - dil + kw*dil, c] * w[kh*3+kw][c] */
 int dc_dw_fwd(dc_view in, const void* w9c, int stride, int dil, dc_view out, void* stream);
 int dc_dw_bwd_data(dc_view dout, const void* w9c, int stride, int dil, dc_view din, int accumulate, void* stream);
-/* G[9][C] fp32 += ..., pre-zeroed by the caller */
-int dc_dw_bwd_weight(dc_view in, dc_view dout, int stride, int dil, float* G9c, void* stream);
+/* fp32 gradient accumulated with atomics into a pre-zeroed buffer: param_layout = 0 -> G[9][C] (tap-major scratch),
+ * param_layout = 1 -> the parameter's own [C][1][3][3] layout (no unpack needed afterwards) */
+int dc_dw_bwd_weight(dc_view in, dc_view dout, int stride, int dil, float* G9c, int param_layout, void* stream);
 
 /* ---- BatchNorm2d (+ReLU, +residual add) (normalizer, DX:70,129,283,348,399; relu DX:79,147; add DX:120) ---- */
 /* Per-layer BatchNorm workspace, dc_bn_ws_bytes(C) bytes, ZEROED by the caller before dc_bn_stats / dc_bn_bwd_reduce:

@@ -324,8 +324,11 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_data_strided_kernel(DwView<
 // ---- weight gradient -------------------------------------------------------------------------------------------------
 // Per-thread 9 x V fp32 partial sums over its column strip; reduction across the pixel lanes of the block in three passes
 // (one filter row each) through shared memory, then one fp32 atomicAdd per (tap, channel) per block.
+// Gout[(kh*3+kw) * tap_stride + c * c_stride]: tap-major scratch (tap_stride = C, c_stride = 1) or the parameter's own
+// [C][1][3][3] layout (tap_stride = 1, c_stride = 9), which needs no unpack launch afterwards.
 template <int V>
-__device__ __forceinline__ void dw_reduce_G(float (&G)[9][V], float* __restrict__ Gout, int C, const DwMap& m, int cvi_base) {
+__device__ __forceinline__ void dw_reduce_G(float (&G)[9][V], float* __restrict__ Gout, int C, const DwMap& m, int cvi_base,
+                                            int tap_stride, int c_stride) {
   extern __shared__ float red[];                       // [8 warps][32 lanes][3*V]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int o = m.cvp; o < 32; o <<= 1) {
@@ -352,7 +355,7 @@ __device__ __forceinline__ void dw_reduce_G(float (&G)[9][V], float* __restrict_
 #pragma unroll
       for (int w = 0; w < 8; ++w) s += red[(w * 32 + ln) * PER + r];
       const int kw = r / V, j = r - kw * V;
-      if (ln < cv_count) atomicAdd(Gout + (size_t)(kh * 3 + kw) * C + (cvi_base + ln) * V + j, s);
+      if (ln < cv_count) atomicAdd(Gout + (size_t)(kh * 3 + kw) * tap_stride + (size_t)((cvi_base + ln) * V + j) * c_stride, s);
     }
   }
 }
@@ -360,7 +363,7 @@ __device__ __forceinline__ void dw_reduce_G(float (&G)[9][V], float* __restrict_
 // input-stationary like dw_s1d1_kernel: input row r meets dout rows r+1 (filter row 0), r (row 1), r-1 (row 2)
 template <typename T, int V>
 __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_s1d1_kernel(DwView<const T> in, DwView<const T> dout, float* __restrict__ Gout,
-                                                                        int C, DwMap m) {
+                                                                        int C, DwMap m, int tap_stride, int c_stride) {
   constexpr int VP = V / 2;
   const DwLane l = dw_lane(m, dout.h, dout.w);
   float2 G2[9][VP];
@@ -433,12 +436,12 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_s1d1_kernel(DwView<c
   for (int k = 0; k < 9; ++k)
 #pragma unroll
     for (int j = 0; j < VP; ++j) { G[k][2 * j] = G2[k][j].x; G[k][2 * j + 1] = G2[k][j].y; }
-  dw_reduce_G<V>(G, Gout, C, m, blockIdx.y * m.cvp);
+  dw_reduce_G<V>(G, Gout, C, m, blockIdx.y * m.cvp, tap_stride, c_stride);
 }
 
 template <typename T, int V>
 __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_direct_kernel(DwView<const T> in, DwView<const T> dout, float* __restrict__ Gout,
-                                                                          int C, DwMap m, int s, int d) {
+                                                                          int C, DwMap m, int s, int d, int tap_stride, int c_stride) {
   const DwLane l = dw_lane(m, dout.h, dout.w);
   float G[9][V];
 #pragma unroll
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_direct_kernel(DwView
       }
     }
   }
-  dw_reduce_G<V>(G, Gout, C, m, blockIdx.y * m.cvp);
+  dw_reduce_G<V>(G, Gout, C, m, blockIdx.y * m.cvp, tap_stride, c_stride);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
@@ -515,15 +518,18 @@ static int dw_bwd_data_t(const dc_view& dout, const void* w, int s, int d, const
   return launch_status("dc_dw_bwd_data");
 }
 template <typename T>
-static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d, float* G, cudaStream_t st) {
+static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d, float* G, int param_layout, cudaStream_t st) {
+  const int tap_stride = param_layout ? 1 : dout.c, c_stride = param_layout ? 9 : 1;
   constexpr int V = dwvec<T>::V;
   DwMap m = dw_map(dout.c, V, dout.h, dout.w, dout.n, kNumSMs * 2, 12);
   dim3 grid = dw_grid(m, dout.w, dout.n);
   const size_t smem = (size_t)8 * 32 * 3 * V * sizeof(float);
   if (s == 1 && d == 1)
-    dw_bwd_weight_s1d1_kernel<T, V><<<grid, kDwThreads, smem, st>>>(dw_view<const T>(in), dw_view<const T>(dout), G, dout.c, m);
+    dw_bwd_weight_s1d1_kernel<T, V><<<grid, kDwThreads, smem, st>>>(dw_view<const T>(in), dw_view<const T>(dout), G, dout.c, m,
+                                                                    tap_stride, c_stride);
   else
-    dw_bwd_weight_direct_kernel<T, V><<<grid, kDwThreads, smem, st>>>(dw_view<const T>(in), dw_view<const T>(dout), G, dout.c, m, s, d);
+    dw_bwd_weight_direct_kernel<T, V><<<grid, kDwThreads, smem, st>>>(dw_view<const T>(in), dw_view<const T>(dout), G, dout.c, m, s, d,
+                                                                      tap_stride, c_stride);
   return launch_status("dc_dw_bwd_weight");
 }
 
@@ -561,12 +567,12 @@ int dc_dw_bwd_data(dc_view dout, const void* w9c, int stride, int dil, dc_view d
                              : dw_bwd_data_t<__nv_bfloat16>(dout, w9c, stride, dil, din, accumulate, st);
 }
 
-int dc_dw_bwd_weight(dc_view in, dc_view dout, int stride, int dil, float* G9c, void* stream) {
+int dc_dw_bwd_weight(dc_view in, dc_view dout, int stride, int dil, float* G9c, int param_layout, void* stream) {
   if (int r = check_dw("dc_dw_bwd_weight", in, dout, stride, dil)) return r;
   DC_REQUIRE(G9c != nullptr, "dc_dw_bwd_weight: null gradient");
   cudaStream_t st = as_stream(stream);
-  return in.dtype == DC_F32 ? dw_bwd_weight_t<float>(in, dout, stride, dil, G9c, st)
-                            : dw_bwd_weight_t<__nv_bfloat16>(in, dout, stride, dil, G9c, st);
+  return in.dtype == DC_F32 ? dw_bwd_weight_t<float>(in, dout, stride, dil, G9c, param_layout, st)
+                            : dw_bwd_weight_t<__nv_bfloat16>(in, dout, stride, dil, G9c, param_layout, st);
 }
 
 }  // extern "C"

@@ -192,6 +192,38 @@ __device__ __forceinline__ void pack_job_elems(const dc_pack_job& j, int local_b
   }
 }
 
+// Transposing packs (source [k][n][taps] -> destination [n][tap][k_pad]: every dgrad-role Conv2d weight and every fprop-role
+// ConvTranspose2d weight) go through a 32 x 32 shared-memory tile so that both the global reads (along n) and the
+// global writes (along k) are coalesced; the element-wise path would read one 4-byte word per 32-byte sector.
+template <typename TD>
+__device__ __forceinline__ void pack_job_transpose(const dc_pack_job& j, int local_block, int tid) {
+  __shared__ float tile[32][33];
+  const int tx = tid & 31, ty = tid >> 5;            // 32 x 8
+  const int kt = (j.K_pad + 31) >> 5, ntl = (j.N_pad + 31) >> 5;
+  const int ntiles = j.taps * kt * ntl;
+  const float* __restrict__ src = j.src;
+  TD* __restrict__ dst = reinterpret_cast<TD*>(j.dst);
+  for (int tl = local_block; tl < ntiles; tl += j.n_blocks) {
+    const int t = tl / (kt * ntl);
+    const int r = tl - t * kt * ntl;
+    const int k0 = (r / ntl) << 5, n0 = (r % ntl) << 5;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = k0 + ty + 8 * q, n = n0 + tx;
+      float v = 0.f;
+      if (k < j.K && n < j.N) v = src[((long long)k * j.N + n) * j.taps + t];
+      tile[ty + 8 * q][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int n = n0 + ty + 8 * q, k = k0 + tx;
+      if (n < j.N_pad && k < j.K_pad) elem<TD>::st(dst + ((long long)n * j.taps + t) * j.K_pad + k, tile[tx][ty + 8 * q]);
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(256) pack_multi_kernel(const dc_pack_job* __restrict__ jobs, int njobs) {
   int lo = 0, hi = njobs - 1;
   const int b = blockIdx.x;
@@ -200,6 +232,11 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const dc_pack_job* __re
     if (jobs[mid].block_start <= b) lo = mid; else hi = mid - 1;
   }
   const dc_pack_job j = jobs[lo];
+  if (j.layout == DC_PACK_NTK && j.src_k_first) {
+    if (j.dst_dtype == DC_F32) pack_job_transpose<float>(j, b - j.block_start, threadIdx.x);
+    else pack_job_transpose<__nv_bfloat16>(j, b - j.block_start, threadIdx.x);
+    return;
+  }
   if (j.dst_dtype == DC_F32) pack_job_elems<float>(j, b - j.block_start, threadIdx.x);
   else pack_job_elems<__nv_bfloat16>(j, b - j.block_start, threadIdx.x);
 }

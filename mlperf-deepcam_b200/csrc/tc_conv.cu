@@ -406,6 +406,9 @@ struct TcV2Cfg {
   int tmem_cols;       // 2 * acc_stride
   int n_mtiles, n_ntiles, total_tiles;
   int tma_store;       // epilogue writes 128 x 64 bf16 chunks with TMA (dense bf16 output views)
+  int bm2;             // 256-row tiles: two M tiles (two accumulators) share every B tile -> 30 % fewer L2->SM bytes per FLOP;
+                       // single accumulator set (no epilogue/main-loop overlap), used when one round covers the problem
+  int real_mtiles;     // number of 128-row M tiles (n_mtiles counts 256-row super tiles when bm2)
   int smem_bytes;
 };
 constexpr int kV2StagePitchF32 = 64 * 4 + 16;     // staged row: 64 fp32 columns + 16 B (odd multiple of 16 B: conflict-free)
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), cfg.bm2 ? 8 : 4); }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
@@ -466,24 +469,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
         for (int j = 0; j < nblk; ++j) tma_load_2d(&maps.b, bres_bar, bres_base + j * b_block_bytes, j * 64, 0);
       }
       int s = 0; uint32_t ph = 0;
+      const int MT = cfg.bm2 ? 2 : 1;
       for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x) {
         const int nt = tile / cfg.n_mtiles;
-        int mt = tile - nt * cfg.n_mtiles;
-        const int tile_x = mt % p.tiles_x; mt /= p.tiles_x;
-        const int tile_y = mt % p.tiles_y;
-        const int img = mt / p.tiles_y;
-        const int x0 = tile_x * p.TW, y0 = tile_y * p.TH;
+        const int mts = tile - nt * cfg.n_mtiles;
+        int x0[2], y0[2], img[2];
+        for (int sub = 0; sub < MT; ++sub) {
+          int mt = mts * MT + sub;
+          const bool real = mt < cfg.real_mtiles;
+          const int tile_x = mt % p.tiles_x; mt /= p.tiles_x;
+          const int tile_y = mt % p.tiles_y;
+          img[sub] = real ? mt / p.tiles_y : p.out.n;          // past the last image: TMA zero-fills the box
+          x0[sub] = tile_x * p.TW; y0[sub] = tile_y * p.TH;
+        }
         const int n0 = nt * BN;
         for (int t = 0; t < p.ntaps; ++t) {
           const CUtensorMap* am = &maps.a[p.map_id[t]];
-          const int bx = x0 + p.qw[t], by = y0 + p.qh[t];
           const int kb0 = p.wt[t] * p.kblocks;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(empty_bar(s), ph ^ 1u);
             mbar_expect_tx(full_bar(s), cfg.stage_bytes);
             const uint32_t sa = smem_base + s * cfg.stage_bytes;
-            tma_load_4d(am, full_bar(s), sa, kb * 64, bx, by, img);
-            if (!cfg.b_resident) tma_load_2d(&maps.b, full_bar(s), sa + kABytes, (kb0 + kb) * 64, n0);
+            tma_load_4d(am, full_bar(s), sa, kb * 64, x0[0] + p.qw[t], y0[0] + p.qh[t], img[0]);
+            if (cfg.bm2) tma_load_4d(am, full_bar(s), sa + kABytes, kb * 64, x0[1] + p.qw[t], y0[1] + p.qh[t], img[1]);
+            if (!cfg.b_resident) tma_load_2d(&maps.b, full_bar(s), sa + MT * kABytes, (kb0 + kb) * 64, n0);
             if (++s == STAGES) { s = 0; ph ^= 1u; }
           }
         }
@@ -495,9 +504,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
       if (cfg.b_resident) { mbar_wait(bres_bar, 0); tc_fence_after(); }
       int s = 0; uint32_t ph = 0;
       int i = 0;
+      const int MT = cfg.bm2 ? 2 : 1;
       for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++i) {
-        const int buf = i & 1;
-        mbar_wait(tempty_bar(buf), (((uint32_t)i >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
+        // bm2: one accumulator SET (two accumulators side by side); otherwise two alternating accumulators
+        const int buf = cfg.bm2 ? 0 : (i & 1);
+        const uint32_t par = cfg.bm2 ? ((uint32_t)i & 1u) : (((uint32_t)i >> 1) & 1u);
+        mbar_wait(tempty_bar(buf), par ^ 1u);                            // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * cfg.acc_stride);
         int it = 0;
@@ -507,11 +519,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
             mbar_wait(full_bar(s), ph);
             tc_fence_after();
             const uint32_t sa = smem_base + s * cfg.stage_bytes;
-            const uint32_t sb = cfg.b_resident ? (bres_base + (uint32_t)(kb0 + kb) * b_block_bytes) : (sa + kABytes);
+            const uint32_t sb = cfg.b_resident ? (bres_base + (uint32_t)(kb0 + kb) * b_block_bytes) : (sa + MT * kABytes);
             const uint64_t da = make_smem_desc(sa, 16, 1024);
             const uint64_t db = make_smem_desc(sb, 16, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(acc, da + 2u * k, db + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            if (cfg.bm2) {
+              const uint64_t da1 = make_smem_desc(sa + kABytes, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(acc + (uint32_t)cfg.acc_stride, da1 + 2u * k, db + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
             umma_commit(empty_bar(s));
             if (++s == STAGES) { s = 0; ph ^= 1u; }
           }
@@ -532,22 +550,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
     const bool raw_copy = !stage_f32 && p.out_vec_ok;
     int i = 0;
     int chunk_ctr = 0;
+    const int MT = cfg.bm2 ? 2 : 1;
     for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++i) {
+     for (int sub = 0; sub < MT; ++sub) {
       const int nt = tile / cfg.n_mtiles;
-      int mt = tile - nt * cfg.n_mtiles;
+      int mt = (tile - nt * cfg.n_mtiles) * MT + sub;
+      const bool real = mt < cfg.real_mtiles;
       const int tile_x = mt % p.tiles_x; mt /= p.tiles_x;
       const int tile_y = mt % p.tiles_y;
-      const int img = mt / p.tiles_y;
+      const int img = real ? mt / p.tiles_y : p.out.n;           // past the last image: the TMA store is clipped away
       const int oy = tile_y * p.TH + ty, ox = tile_x * p.TW + tx;
       const int n0 = nt * BN;
-      const bool pix_ok = (oy < p.out.h) && (ox < p.out.w);
+      const bool pix_ok = real && (oy < p.out.h) && (ox < p.out.w);
       const long long base = (long long)img * p.out.sn + (long long)oy * p.out.sh + (long long)ox * p.out.sw;
       const unsigned okmask = __ballot_sync(0xffffffffu, pix_ok);
       const int ncols = min(BN, p.out.c - n0);
-      const int buf = i & 1;
-      mbar_wait(tfull_bar(buf), ((uint32_t)i >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t acc = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * cfg.acc_stride);
+      const int buf = cfg.bm2 ? 0 : (i & 1);
+      if (sub == 0) {
+        mbar_wait(tfull_bar(buf), cfg.bm2 ? ((uint32_t)i & 1u) : (((uint32_t)i >> 1) & 1u));
+        tc_fence_after();
+      }
+      const uint32_t acc = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((cfg.bm2 ? sub : buf) * cfg.acc_stride);
       if (cfg.tma_store) {
         // ---- fast path: 128 rows x 64 bf16 columns per chunk, 128B-swizzled staging (two buffers), one TMA store
         //      (or TMA reduce-add for gradient accumulation) per chunk issued by one elected thread ----
@@ -707,6 +730,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
         }
         __syncwarp();       // staging rows are reused by the next chunk
       }
+     }
     }
   }
   if (cfg.tma_store && threadIdx.x == 64) tma_store_wait_all();     // staging must stay valid until the last store has read it
@@ -1004,22 +1028,37 @@ static int launch_fprop(const TcMaps& maps, const TcFpropParams& p, const TcFpro
 static TcV2Cfg pick_v2_cfg(int mtiles, int Co, int kblocks, int wtaps, bool tma_store) {
   TcV2Cfg c;
   const int co16 = round_up_i(Co, 16);
-  int best_bn = std::min(256, co16);
+  int best_bn = std::min(256, co16), best_bm2 = 0;
   double best_cost = 1e30;
-  for (int nt = 1; nt <= 16; ++nt) {
-    int bn = round_up_i(ceil_div(co16, nt), 16);
-    // the TMA-store epilogue writes 64-column chunks: an N tile that is not the last one must be a multiple of 64
-    if (tma_store && nt > 1) bn = round_up_i(bn, 64);
-    if (bn > 256) continue;
-    if (bn < 64 && co16 >= 64) break;
-    const int ntiles = ceil_div(Co, bn);
-    const long long tiles = (long long)mtiles * ntiles;
-    const long long rounds = ceil_div64(tiles, kNumSMs);
-    const double cost = (double)rounds * (16384.0 + 128.0 * bn + 3000.0 / std::max(1, kblocks * wtaps));
-    if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; }
+  const double kiters = (double)kblocks * wtaps;
+  // Cost model (cycles): these GEMMs are bound by the L2->SM path, ~6300 B/clk for the whole chip and ~64 B/clk for
+  // one SM; add a fixed per-tile epilogue/drain cost.
+  static int bm2_enabled = -1;
+  if (bm2_enabled < 0) { const char* e = getenv("DEEPCAM_B200_TC_BM2"); bm2_enabled = (e && e[0] == '1') ? 1 : 0; }   // opt-in: measured slower in the full step (no epilogue overlap)
+  for (int bm2 = 0; bm2 <= bm2_enabled; ++bm2) {
+    if (bm2 && !tma_store) break;
+    for (int nt = 1; nt <= 16; ++nt) {
+      int bn = round_up_i(ceil_div(co16, nt), 16);
+      // the TMA-store epilogue writes 64-column chunks: an N tile that is not the last one must be a multiple of 64
+      if (tma_store && nt > 1) bn = round_up_i(bn, 64);
+      if (bn > 256) continue;
+      if (bn < 64 && co16 >= 64) break;
+      const int ntiles = ceil_div(Co, bn);
+      const int msup = bm2 ? ceil_div(mtiles, 2) : mtiles;
+      const long long tiles = (long long)msup * ntiles;
+      if (bm2 && tiles > kNumSMs) continue;              // 256-row tiles only when one round covers the problem
+      const long long rounds = ceil_div64(tiles, kNumSMs);
+      const double tile_bytes = kiters * ((bm2 ? 2 : 1) * 16384.0 + 128.0 * bn);
+      const double chip = (double)tiles * tile_bytes / 6300.0;
+      const double sm = (double)rounds * tile_bytes / 64.0;
+      const double cost = std::max(chip, sm) + (double)rounds * 1500.0 * (bm2 ? 2 : 1) * (bn / 128.0);
+      if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; best_bm2 = bm2; }
+    }
   }
   c.BN = best_bn;
-  c.n_mtiles = mtiles;
+  c.bm2 = best_bm2;
+  c.real_mtiles = mtiles;
+  c.n_mtiles = c.bm2 ? ceil_div(mtiles, 2) : mtiles;
   c.n_ntiles = ceil_div(Co, c.BN);
   c.total_tiles = c.n_mtiles * c.n_ntiles;
   c.tma_store = tma_store ? 1 : 0;
@@ -1028,9 +1067,9 @@ static TcV2Cfg pick_v2_cfg(int mtiles, int Co, int kblocks, int wtaps, bool tma_
   c.tmem_cols = 2 * c.acc_stride;
   const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - kV2StagingBytes;
   c.bres_bytes = wtaps * kblocks * c.BN * 128;
-  c.b_resident = (c.n_ntiles == 1 && c.bres_bytes <= 128 * 1024 && c.bres_bytes + 3 * kABytes <= budget) ? 1 : 0;
+  c.b_resident = (!c.bm2 && c.n_ntiles == 1 && c.bres_bytes <= 128 * 1024 && c.bres_bytes + 3 * kABytes <= budget) ? 1 : 0;
   if (!c.b_resident) c.bres_bytes = 0;
-  c.stage_bytes = kABytes + (c.b_resident ? 0 : c.BN * 128);
+  c.stage_bytes = (c.bm2 ? 2 : 1) * kABytes + (c.b_resident ? 0 : c.BN * 128);
   c.stages = std::max(2, std::min(8, (budget - c.bres_bytes) / c.stage_bytes));
   c.smem_bytes = c.stages * c.stage_bytes + c.bres_bytes + kV2StagingBytes + 1024 + 256;
   return c;

@@ -342,11 +342,10 @@ class CudaBackend:
         return dx
 
     def dw_bwd_weight(self, x, dy, spec, wgrad):
-        """wgrad: fp32 [C,1,3,3] view of the flat gradient buffer."""
-        G = self.scratch(9 * spec.c, torch.float32, zero=True)
-        ops.dw_bwd_weight(x, dy, spec.stride, spec.dil, G)
-        ops.unpack_wgrad(G, 1, spec.c, 9, False, wgrad)    # G[tap][c][1] -> [c][1][tap]
-        self.launches += 2
+        """wgrad: fp32 [C,1,3,3] view of the flat gradient buffer, ZERO on entry (the engine clears the flat buffer at the
+        start of backward): the kernel accumulates straight into the parameter layout, no scratch and no unpack."""
+        ops.dw_bwd_weight(x, dy, spec.stride, spec.dil, wgrad, param_layout=True)
+        self.launches += 1
         return wgrad
 
     # ---- batch norm (+relu, +residual) ------------------------------------------------------------------------------

@@ -241,11 +241,12 @@ def dw_bwd_data(dout, w9c, stride, dil, din, accumulate):
     return din
 
 
-def dw_bwd_weight(x, dout, stride, dil, G9c):
+def dw_bwd_weight(x, dout, stride, dil, G9c, param_layout=False):
     _require_cuda(x, dout, G9c)
     assert G9c.dtype == torch.float32
     _timed("dw_bwd_weight", 18.0 * dout.numel(), _nbytes(x, dout),
-           lambda: _lib.load().dc_dw_bwd_weight(view(x), view(dout), stride, dil, _p(G9c), _stream()), "dc_dw_bwd_weight",
+           lambda: _lib.load().dc_dw_bwd_weight(view(x), view(dout), stride, dil, _p(G9c), int(param_layout), _stream()),
+           "dc_dw_bwd_weight",
            tag="%s s%d d%d" % (_shape_tag(x), stride, dil))
     return G9c
 
