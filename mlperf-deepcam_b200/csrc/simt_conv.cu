@@ -151,6 +151,43 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(dc_conv_desc d, Vie
   }
 }
 
+
+// Few-row GEMM for the image-pooling branch (DX:425-428: a [N_batch, 2048] x [2048, 256] product and its transpose in
+// backward): the tiled kernel above would run it on 4 blocks for 140 us.  32 output columns x 32 k-lanes per block, fixed
+// reduction order (no atomics: this branch feeds a BatchNorm over N_batch values, which amplifies any run-to-run noise).
+constexpr int kSmallM = 8;
+__global__ void __launch_bounds__(1024) small_m_gemm_kernel(const float* __restrict__ in, long long in_row_stride, int M, int K,
+                                                            const float* __restrict__ W, int n_pad, const float* __restrict__ bias,
+                                                            float* __restrict__ out, long long out_row_stride, int N, int accumulate) {
+  __shared__ float red[32][kSmallM][32];
+  const int nl = threadIdx.x & 31, kl = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + nl;
+  float acc[kSmallM];
+#pragma unroll
+  for (int m = 0; m < kSmallM; ++m) acc[m] = 0.f;
+  if (n < n_pad) {
+#pragma unroll 4
+    for (int k = kl; k < K; k += 32) {
+      const float w = W[(size_t)k * n_pad + n];
+#pragma unroll
+      for (int m = 0; m < kSmallM; ++m)
+        if (m < M) acc[m] = fmaf(in[m * in_row_stride + k], w, acc[m]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < kSmallM; ++m) red[kl][m][nl] = acc[m];
+  __syncthreads();
+  if (kl < M && n < N) {            // warp kl finishes output row m = kl
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) s += red[q][kl][nl];
+    if (bias) s += bias[n];
+    float* o = out + kl * out_row_stride + n;
+    if (accumulate) s += *o;
+    *o = s;
+  }
+}
+
 // wgrad: rows = co (BMC tile, from dout), cols = ci (64 tile, from in), reduction over pixels in chunks of BK.
 template <typename T, int BMC>
 __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(dc_conv_desc d, View<const T> in, View<const T> dout,
@@ -298,6 +335,18 @@ int dc_conv_gemm_simt(const dc_conv_desc* d, dc_view in, const void* w, const fl
   DC_REQUIRE(w != nullptr && (reinterpret_cast<uintptr_t>(w) % 16) == 0, "dc_conv_gemm_simt: weights must be 16-byte aligned");
   DC_REQUIRE((long long)out.n * out.h * out.w < (1ll << 31), "dc_conv_gemm_simt: too many pixels");
   cudaStream_t st = as_stream(stream);
+  // few-row fast path: 1x1, no gather offset, fp32 in and out, pixel-linear rows (the image-pooling conv and its dgrad)
+  const long long M = (long long)out.n * out.h * out.w;
+  if (M <= kSmallM && d->ntaps == 1 && d->dh[0] == 0 && d->dw[0] == 0 && d->stride_h == 1 && d->stride_w == 1 && d->wt[0] == 0 &&
+      in.dtype == DC_F32 && out.dtype == DC_F32 && in.sc == 1 && out.sc == 1 && in.h == out.h && in.w == out.w &&
+      in.sh == (long long)in.w * in.sw && in.sn == (long long)in.h * in.sh && out.sh == (long long)out.w * out.sw &&
+      out.sn == (long long)out.h * out.sh) {
+    const int K = in.c, N = out.c, n_pad = (N + 3) / 4 * 4;
+    small_m_gemm_kernel<<<ceil_div(n_pad, 32), 1024, 0, st>>>(reinterpret_cast<const float*>(in.ptr), in.sw, (int)M, K,
+                                                             reinterpret_cast<const float*>(w), n_pad, bias,
+                                                             reinterpret_cast<float*>(out.ptr), out.sw, N, d->accumulate);
+    return launch_status("dc_conv_gemm_simt");
+  }
   return in.dtype == DC_F32 ? conv_gemm_simt_t<float>(d, in, w, bias, out, st) : conv_gemm_simt_t<__nv_bfloat16>(d, in, w, bias, out, st);
 }
 

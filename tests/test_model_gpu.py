@@ -193,7 +193,9 @@ def test_cuda_graph_plan_matches_eager(sd, precision, monkeypatch):
     net_g, res_g = run(True)
     net_e, res_e = run(False)
     assert net_g.__dict__["_dc_plans"] and all(v[1] is not None and v[1].bwd_segments for v in net_g._dc_plans.values())
-    tol = 1e-5 if precision == "fp32" else 2e-2
+    # fp32: the two engines differ only by the summation order of fp32/fp64 atomics, which the BatchNorm over two values of
+    # the image-pooling branch amplifies; 1e-4 is the north-star fp32 tolerance
+    tol = 1e-4 if precision == "fp32" else 2e-2
     for (og, lg, gg), (oe, le, ge) in zip(res_g, res_e):
         assert _rel(og, oe) < tol
         assert abs(lg - le) < tol
