@@ -255,7 +255,7 @@ __device__ __forceinline__ void load_fwd_coef(const dc_bn_params& p, int C, int 
 }
 
 template <typename T, int V, int kUnroll>
-__global__ void __launch_bounds__(kBnThreads, 3) bn_apply_kernel(dc_bn_params p, PixView<const T> y, PixView<const T> res, PixView<T> out,
+__global__ void __launch_bounds__(kBnThreads, 2) bn_apply_kernel(dc_bn_params p, PixView<const T> y, PixView<const T> res, PixView<T> out,
                                                               int C, long long npix, LaneMap m) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
@@ -460,7 +460,8 @@ __global__ void double_to_float_kernel(const double* s, float* d, int n) {
 
 // ---- host side ---------------------------------------------------------------------------------------------
 // grid.x: enough blocks that every thread handles about `items` pixels, capped at 16 blocks per SM (grid-stride beyond)
-constexpr int kApplyUnroll = 2;
+constexpr int kApplyUnroll = 8;       // forward apply: one read stream -> eight 16-byte loads in flight per thread
+constexpr int kBwdApplyUnroll = 4;    // backward apply: three read streams
 static inline dim3 bn_grid(const LaneMap& m, long long npix, int items, int blocks_per_sm_cap = 16) {
   long long gx = ceil_div64(npix, (long long)m.ppb * items);
   long long cap = std::max<long long>(1, (long long)kNumSMs * blocks_per_sm_cap / m.gy);
@@ -512,8 +513,8 @@ static int bn_bwd_apply_t(const dc_bn_params& p, const dc_view& dout, const dc_v
   constexpr int V = vec16<T>::V;
   const long long npix = (long long)dout.n * dout.h * dout.w;
   LaneMap m = lane_map(dout.c, V);
-  dim3 grid = bn_grid(m, npix, kApplyUnroll, 1 << 20);
-  bn_bwd_apply_kernel<T, V, kApplyUnroll><<<grid, kBnThreads, 0, st>>>(p, pix_view<const T>(dout), pix_view<const T>(out), pix_view<const T>(y), rws,
+  dim3 grid = bn_grid(m, npix, kBwdApplyUnroll, 1 << 20);
+  bn_bwd_apply_kernel<T, V, kBwdApplyUnroll><<<grid, kBnThreads, 0, st>>>(p, pix_view<const T>(dout), pix_view<const T>(out), pix_view<const T>(y), rws,
                                                          pix_view<T>(dy), pix_view<T>(dres), dout.c, npix, m);
   return launch_status("dc_bn_bwd_apply");
 }
