@@ -69,6 +69,10 @@ int         dc_abi_version(void);
 const char* dc_last_error_string(void);
 /* returns 1 when the current device is sm_100 (tcgen05 kernels usable), 0 otherwise, <0 on error */
 int         dc_device_supports_tcgen05(void);
+/* Programmatic dependent launch between consecutive kernels of a stream (prologue of kernel N+1 overlaps the tail
+ * of kernel N; results are identical to plain stream order).  Default on; DEEPCAM_B200_PDL=0 or dc_set_pdl(0) = off. */
+int         dc_set_pdl(int on);
+int         dc_get_pdl(void);
 
 /* ---- layout / packing ------------------------------------------------------ */
 /* Generic strided copy with dtype conversion, dst[n,h,w,c] = src[n,h,w,c] for c < src.c;

@@ -175,6 +175,7 @@ __device__ __forceinline__ bool last_block(unsigned* ticket) {
 template <typename T, int V>
 __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(dc_bn_params p, PixView<const T> y, int C, long long npix, LaneMap m) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_sync();
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
   const int cvi = blockIdx.y * m.cvp + cvl;
   const bool ok = cvi < m.cv;
@@ -258,6 +259,7 @@ template <typename T, int V, int kUnroll>
 __global__ void __launch_bounds__(kBnThreads, 2) bn_apply_kernel(dc_bn_params p, PixView<const T> y, PixView<const T> res, PixView<T> out,
                                                               int C, long long npix, LaneMap m) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_sync();
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
   const int cvi = blockIdx.y * m.cvp + cvl;
   if (cvi >= m.cv) return;
@@ -298,6 +300,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(dc_bn_params 
                                                                    PixView<const T> y, void* rws_raw, float* dgamma, float* dbeta,
                                                                    int C, long long npix, LaneMap m) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_sync();
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
   const int cvi = blockIdx.y * m.cvp + cvl;
   const bool ok = cvi < m.cv;
@@ -373,6 +376,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_apply_kernel(dc_bn_param
                                                                   PixView<const T> y, const void* rws_raw, PixView<T> dy, PixView<T> dres,
                                                                   int C, long long npix, LaneMap m) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_sync();
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
   const int cvi = blockIdx.y * m.cvp + cvl;
   if (cvi >= m.cv) return;
@@ -435,6 +439,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_apply_kernel(dc_bn_param
 template <typename T, int V>
 __global__ void __launch_bounds__(kBnThreads) channel_sum_kernel(PixView<const T> x, double* sums, int C, long long npix, LaneMap m) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_sync();
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
   const int cvi = blockIdx.y * m.cvp + cvl;
   const bool ok = cvi < m.cv;
@@ -483,7 +488,7 @@ static int bn_stats_t(const dc_bn_params& p, const dc_view& y, cudaStream_t st) 
   const long long npix = (long long)y.n * y.h * y.w;
   LaneMap m = lane_map(y.c, V);
   dim3 grid = bn_grid(m, npix, 4 * kUnroll);
-  bn_stats_kernel<T, V><<<grid, kBnThreads, red_smem<2, V>(), st>>>(p, pix_view<const T>(y), y.c, npix, m);
+  launch_k(bn_stats_kernel<T, V>, grid, dim3(kBnThreads), red_smem<2, V>(), st, p, pix_view<const T>(y), y.c, npix, m);
   return launch_status("dc_bn_stats");
 }
 template <typename T>
@@ -493,7 +498,7 @@ static int bn_apply_t(const dc_bn_params& p, const dc_view& y, const dc_view& re
   LaneMap m = lane_map(y.c, V);
   // element-wise: two pixels per thread and as many blocks as that needs (small register footprint, 3 blocks per SM)
   dim3 grid = bn_grid(m, npix, kApplyUnroll, 1 << 20);
-  bn_apply_kernel<T, V, kApplyUnroll><<<grid, kBnThreads, 0, st>>>(p, pix_view<const T>(y), pix_view<const T>(res), pix_view<T>(out), y.c, npix, m);
+  launch_k(bn_apply_kernel<T, V, kApplyUnroll>, grid, dim3(kBnThreads), (size_t)0, st, p, pix_view<const T>(y), pix_view<const T>(res), pix_view<T>(out), y.c, npix, m);
   return launch_status("dc_bn_apply");
 }
 template <typename T>
@@ -503,7 +508,7 @@ static int bn_bwd_reduce_t(const dc_bn_params& p, const dc_view& dout, const dc_
   const long long npix = (long long)y.n * y.h * y.w;
   LaneMap m = lane_map(y.c, V);
   dim3 grid = bn_grid(m, npix, 4 * kUnroll);
-  bn_bwd_reduce_kernel<T, V><<<grid, kBnThreads, red_smem<2, V>(), st>>>(p, pix_view<const T>(dout), pix_view<const T>(out),
+  launch_k(bn_bwd_reduce_kernel<T, V>, grid, dim3(kBnThreads), red_smem<2, V>(), st, p, pix_view<const T>(dout), pix_view<const T>(out),
                                                                          pix_view<const T>(y), rws, dgamma, dbeta, y.c, npix, m);
   return launch_status("dc_bn_bwd_reduce");
 }
@@ -514,7 +519,7 @@ static int bn_bwd_apply_t(const dc_bn_params& p, const dc_view& dout, const dc_v
   const long long npix = (long long)dout.n * dout.h * dout.w;
   LaneMap m = lane_map(dout.c, V);
   dim3 grid = bn_grid(m, npix, kBwdApplyUnroll, 1 << 20);
-  bn_bwd_apply_kernel<T, V, kBwdApplyUnroll><<<grid, kBnThreads, 0, st>>>(p, pix_view<const T>(dout), pix_view<const T>(out), pix_view<const T>(y), rws,
+  launch_k(bn_bwd_apply_kernel<T, V, kBwdApplyUnroll>, grid, dim3(kBnThreads), (size_t)0, st, p, pix_view<const T>(dout), pix_view<const T>(out), pix_view<const T>(y), rws,
                                                          pix_view<T>(dy), pix_view<T>(dres), dout.c, npix, m);
   return launch_status("dc_bn_bwd_apply");
 }
@@ -555,6 +560,7 @@ __global__ void __launch_bounds__(kOnePassThreads, 1) bn_fwd_onepass_kernel(dc_b
   uint4* hold = reinterpret_cast<uint4*>(reinterpret_cast<char*>(red) + kOnePassWarps * 32 * 2 * V * sizeof(float));
   const LaneMap& m = om.m;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_wait();
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
   const int cvi = blockIdx.y * m.cvp + cvl;
   const bool ok = cvi < m.cv;
@@ -589,6 +595,7 @@ __global__ void __launch_bounds__(kOnePassThreads, 1) bn_fwd_onepass_kernel(dc_b
   BnWs ws = bn_ws(const_cast<double*>(p.sums), C);
   reduce_to_ws<2, V, kOnePassWarps>(acc, ws.sums, C, m.cvp, blockIdx.y * m.cvp, min(m.cvp, m.cv - blockIdx.y * m.cvp));
   grid_barrier(ws.ticket + blockIdx.y, (unsigned)om.gx);
+  pdl_trigger();          // only now: every block of this grid is resident (see common.cuh)
   if (!ok) return;
   // every thread derives the coefficients of its own channels (mean / variance in double, 1/sqrt in fp32)
   const double inv_count = 1.0 / p.count;
@@ -642,6 +649,7 @@ __global__ void __launch_bounds__(kOnePassThreads, 1) bn_bwd_onepass_kernel(dc_b
   uint4* hold = reinterpret_cast<uint4*>(reinterpret_cast<char*>(red) + kOnePassWarps * 32 * 2 * V * sizeof(float));   // [K][256][2]: g, y
   const LaneMap& m = om.m;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_wait();
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
   const int cvi = blockIdx.y * m.cvp + cvl;
   const bool ok = cvi < m.cv;
@@ -708,6 +716,7 @@ __global__ void __launch_bounds__(kOnePassThreads, 1) bn_bwd_onepass_kernel(dc_b
   BnWs rws = bn_ws(rws_raw, C);
   reduce_to_ws<2, V, kOnePassWarps>(acc, rws.sums, C, m.cvp, blockIdx.y * m.cvp, min(m.cvp, m.cv - blockIdx.y * m.cvp));
   grid_barrier(rws.ticket + blockIdx.y, (unsigned)om.gx);
+  pdl_trigger();
   if (!ok) return;
   const bool train = (p.flags & DC_BN_TRAIN) != 0;
   const double inv_count = 1.0 / p.count;
@@ -809,7 +818,7 @@ static int bn_fwd_onepass_t(const dc_bn_params& p, const dc_view& y, const dc_vi
   if (!onepass_map(y.c, V, npix, 1, om)) return fail(-2, "dc_bn_fwd_onepass: tensor does not fit on chip");
   if (int r = set_smem_attr(bn_fwd_onepass_kernel<T, V>, "dc_bn_fwd_onepass")) return r;
   const size_t smem = (size_t)kOnePassWarps * 32 * 2 * V * 4 + (size_t)om.K * kOnePassThreads * 16;
-  bn_fwd_onepass_kernel<T, V><<<dim3(om.gx, om.m.gy, 1), kOnePassThreads, smem, st>>>(p, pix_view<const T>(y), pix_view<const T>(res),
+  launch_k(bn_fwd_onepass_kernel<T, V>, dim3(om.gx, om.m.gy, 1), dim3(kOnePassThreads), smem, st, p, pix_view<const T>(y), pix_view<const T>(res),
                                                                                  pix_view<T>(out), y.c, npix, om);
   return launch_status("dc_bn_fwd_onepass");
 }
@@ -822,7 +831,7 @@ static int bn_bwd_onepass_t(const dc_bn_params& p, const dc_view& dout, const dc
   if (!onepass_map(y.c, V, npix, 2, om)) return fail(-2, "dc_bn_bwd_onepass: tensor does not fit on chip");
   if (int r = set_smem_attr(bn_bwd_onepass_kernel<T, V>, "dc_bn_bwd_onepass")) return r;
   const size_t smem = (size_t)kOnePassWarps * 32 * 2 * V * 4 + (size_t)om.K * kOnePassThreads * 32;
-  bn_bwd_onepass_kernel<T, V><<<dim3(om.gx, om.m.gy, 1), kOnePassThreads, smem, st>>>(p, pix_view<const T>(dout), pix_view<const T>(out),
+  launch_k(bn_bwd_onepass_kernel<T, V>, dim3(om.gx, om.m.gy, 1), dim3(kOnePassThreads), smem, st, p, pix_view<const T>(dout), pix_view<const T>(out),
                                                                                  pix_view<const T>(y), rws, pix_view<T>(dy), pix_view<T>(dres),
                                                                                  dgamma, dbeta, y.c, npix, om);
   return launch_status("dc_bn_bwd_onepass");
@@ -953,10 +962,10 @@ int dc_channel_sum(dc_view x, double* ws_c, float* out_c, void* stream) {
   const long long npix = (long long)x.n * x.h * x.w;
   if (x.dtype == DC_F32) {
     LaneMap m = lane_map(x.c, 4);
-    channel_sum_kernel<float, 4><<<bn_grid(m, npix, 8), kBnThreads, red_smem<1, 4>(), st>>>(pix_view<const float>(x), ws_c, x.c, npix, m);
+    launch_k(channel_sum_kernel<float, 4>, bn_grid(m, npix, 8), dim3(kBnThreads), red_smem<1, 4>(), st, pix_view<const float>(x), ws_c, x.c, npix, m);
   } else {
     LaneMap m = lane_map(x.c, 8);
-    channel_sum_kernel<__nv_bfloat16, 8><<<bn_grid(m, npix, 8), kBnThreads, red_smem<1, 8>(), st>>>(pix_view<const __nv_bfloat16>(x), ws_c, x.c, npix, m);
+    launch_k(channel_sum_kernel<__nv_bfloat16, 8>, bn_grid(m, npix, 8), dim3(kBnThreads), red_smem<1, 8>(), st, pix_view<const __nv_bfloat16>(x), ws_c, x.c, npix, m);
   }
   double_to_float_kernel<<<ceil_div(x.c, 256), 256, 0, st>>>(ws_c, out_c, x.c);
   return launch_status("dc_channel_sum");

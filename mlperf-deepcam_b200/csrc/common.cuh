@@ -31,6 +31,37 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 
 constexpr int kNumSMs = 148;
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// A step is ~770 short kernels on one stream.  Launched through launch_k(), kernel N+1 may be scheduled while
+// kernel N drains: its blocks run their prologue (barrier init, TMEM allocation, tensor-map prefetch, index
+// arithmetic) and then block in pdl_wait() until kernel N has completed and its memory is visible.  Rules that keep
+// this equivalent to plain stream order:
+//   * every kernel launched through launch_k() executes pdl_wait() before its first global-memory access
+//     (reads AND writes: the predecessor may still be reading what this kernel overwrites);
+//   * pdl_trigger() comes after pdl_wait(), so at most one successor is ever queued behind a running kernel;
+//   * kernels with an inter-block barrier trigger only after the barrier (all their blocks are resident by then:
+//     a queued successor can never take the slot of a block the barrier is waiting for).
+// Both instructions are no-ops when the kernel was launched without the attribute (dc_set_pdl(0), or <<<>>>).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // errors surface through launch_status()
+}
+
 // ---- element access ----------------------------------------------------------------------------
 template <typename T> struct elem;
 template <> struct elem<float> {

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_kernel(DwView<const T> in,
                                                              DwMap m, int flip, int accumulate) {
   constexpr int VP = V / 2;
   const DwLane l = dw_lane(m, out.h, out.w);
+  pdl_sync();
   if (!l.ok) return;
   const int c0 = l.cvi * V;
   float2 wv[9][VP];
@@ -230,6 +231,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(kDwThreads) dw_direct_kernel(DwView<const T> in, const T* __restrict__ w9c, DwView<T> out, int C,
                                                                DwMap m, int s, int d, int flip, int accumulate) {
   const DwLane l = dw_lane(m, out.h, out.w);
+  pdl_sync();
   if (!l.ok) return;
   const int c0 = l.cvi * V;
   float wv[9][V];
@@ -277,6 +279,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(kDwThreads) dw_bwd_data_strided_kernel(DwView<const T> dout, const T* __restrict__ w9c, DwView<T> din,
                                                                          int C, DwMap m, int s, int d, int accumulate) {
   const DwLane l = dw_lane(m, din.h, din.w);
+  pdl_sync();
   if (!l.ok) return;
   const int c0 = l.cvi * V;
   float wv[9][V];
@@ -366,6 +369,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_s1d1_kernel(DwView<c
                                                                         int C, DwMap m, int tap_stride, int c_stride) {
   constexpr int VP = V / 2;
   const DwLane l = dw_lane(m, dout.h, dout.w);
+  pdl_sync();
   float2 G2[9][VP];
 #pragma unroll
   for (int k = 0; k < 9; ++k)
@@ -443,6 +447,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_direct_kernel(DwView<const T> in, DwView<const T> dout, float* __restrict__ Gout,
                                                                           int C, DwMap m, int s, int d, int tap_stride, int c_stride) {
   const DwLane l = dw_lane(m, dout.h, dout.w);
+  pdl_sync();
   float G[9][V];
 #pragma unroll
   for (int k = 0; k < 9; ++k)
@@ -499,9 +504,9 @@ static int dw_fwd_t(const dc_view& in, const void* w, int s, int d, const dc_vie
   DwMap m = dw_map(out.c, V, out.h, out.w, out.n, kNumSMs * 4, 6);
   dim3 grid = dw_grid(m, out.w, out.n);
   if (s == 1 && d == 1)
-    dw_s1d1_kernel<T, V><<<grid, kDwThreads, 0, st>>>(dw_view<const T>(in), (const T*)w, dw_view<T>(out), out.c, m, 0, 0);
+    launch_k(dw_s1d1_kernel<T, V>, grid, dim3(kDwThreads), (size_t)0, st, dw_view<const T>(in), (const T*)w, dw_view<T>(out), out.c, m, 0, 0);
   else
-    dw_direct_kernel<T, V><<<grid, kDwThreads, 0, st>>>(dw_view<const T>(in), (const T*)w, dw_view<T>(out), out.c, m, s, d, 0, 0);
+    launch_k(dw_direct_kernel<T, V>, grid, dim3(kDwThreads), (size_t)0, st, dw_view<const T>(in), (const T*)w, dw_view<T>(out), out.c, m, s, d, 0, 0);
   return launch_status("dc_dw_fwd");
 }
 template <typename T>
@@ -510,11 +515,11 @@ static int dw_bwd_data_t(const dc_view& dout, const void* w, int s, int d, const
   DwMap m = dw_map(din.c, V, din.h, din.w, din.n, kNumSMs * 4, 6);
   dim3 grid = dw_grid(m, din.w, din.n);
   if (s == 1 && d == 1)          // full correlation with the flipped filter
-    dw_s1d1_kernel<T, V><<<grid, kDwThreads, 0, st>>>(dw_view<const T>(dout), (const T*)w, dw_view<T>(din), din.c, m, 1, acc);
+    launch_k(dw_s1d1_kernel<T, V>, grid, dim3(kDwThreads), (size_t)0, st, dw_view<const T>(dout), (const T*)w, dw_view<T>(din), din.c, m, 1, acc);
   else if (s == 1)
-    dw_direct_kernel<T, V><<<grid, kDwThreads, 0, st>>>(dw_view<const T>(dout), (const T*)w, dw_view<T>(din), din.c, m, 1, d, 1, acc);
+    launch_k(dw_direct_kernel<T, V>, grid, dim3(kDwThreads), (size_t)0, st, dw_view<const T>(dout), (const T*)w, dw_view<T>(din), din.c, m, 1, d, 1, acc);
   else
-    dw_bwd_data_strided_kernel<T, V><<<grid, kDwThreads, 0, st>>>(dw_view<const T>(dout), (const T*)w, dw_view<T>(din), din.c, m, s, d, acc);
+    launch_k(dw_bwd_data_strided_kernel<T, V>, grid, dim3(kDwThreads), (size_t)0, st, dw_view<const T>(dout), (const T*)w, dw_view<T>(din), din.c, m, s, d, acc);
   return launch_status("dc_dw_bwd_data");
 }
 template <typename T>
@@ -525,10 +530,10 @@ static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d,
   dim3 grid = dw_grid(m, dout.w, dout.n);
   const size_t smem = (size_t)8 * 32 * 3 * V * sizeof(float);
   if (s == 1 && d == 1)
-    dw_bwd_weight_s1d1_kernel<T, V><<<grid, kDwThreads, smem, st>>>(dw_view<const T>(in), dw_view<const T>(dout), G, dout.c, m,
+    launch_k(dw_bwd_weight_s1d1_kernel<T, V>, grid, dim3(kDwThreads), (size_t)smem, st, dw_view<const T>(in), dw_view<const T>(dout), G, dout.c, m,
                                                                     tap_stride, c_stride);
   else
-    dw_bwd_weight_direct_kernel<T, V><<<grid, kDwThreads, smem, st>>>(dw_view<const T>(in), dw_view<const T>(dout), G, dout.c, m, s, d,
+    launch_k(dw_bwd_weight_direct_kernel<T, V>, grid, dim3(kDwThreads), (size_t)smem, st, dw_view<const T>(in), dw_view<const T>(dout), G, dout.c, m, s, d,
                                                                       tap_stride, c_stride);
   return launch_status("dc_dw_bwd_weight");
 }

@@ -3,11 +3,22 @@
 // These replace the .to()/.contiguous()/permute glue around the reference model (TR:348-349, DX:441).
 #include "common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace dc {
 
 static thread_local char g_err[512] = "ok";
 char* err_buf() { return g_err; }
+// PDL switch: on by default, DEEPCAM_B200_PDL=0 in the environment (read once) or dc_set_pdl(0) turns it off.
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("DEEPCAM_B200_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+void set_pdl(int on) { g_pdl = on ? 1 : 0; }
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -20,6 +31,7 @@ int fail(int code, const char* fmt, ...) {
 // Path A: both sides channel-contiguous -> vector of 4 channels per thread.
 template <typename TS, typename TD>
 __global__ void copy_vec4_kernel(View<const TS> s, View<TD> d, long long npix) {
+  pdl_sync();
   const int cv = d.c >> 2;
   const int scv = s.c >> 2;
   long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -41,6 +53,7 @@ __global__ void copy_vec4_kernel(View<const TS> s, View<TD> d, long long npix) {
 // tile = 32 (w) x 32 (c); block = (32, 8)
 template <typename TS, typename TD, bool SRC_W_CONTIG>
 __global__ void copy_transpose_kernel(View<const TS> s, View<TD> d) {
+  pdl_sync();
   __shared__ float tile[32][33];
   const int wt = blockIdx.x * 32;
   const int ct = blockIdx.y * 32;
@@ -101,13 +114,13 @@ static int copy_dispatch(const dc_view& src, const dc_view& dst, cudaStream_t st
   if (view_vec4(src) && view_vec4(dst)) {
     long long total = npix * (dst.c / 4);
     int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
-    copy_vec4_kernel<TS, TD><<<blocks, 256, 0, st>>>(s, d, npix);
+    launch_k(copy_vec4_kernel<TS, TD>, dim3(blocks), dim3(256), (size_t)0, st, s, d, npix);
   } else if (src.sw == 1 && dst.sc == 1 && src.c <= dst.c) {
     dim3 grid(ceil_div(dst.w, 32), ceil_div(dst.c, 32), dst.n * dst.h);
-    copy_transpose_kernel<TS, TD, true><<<grid, dim3(32, 8), 0, st>>>(s, d);
+    launch_k(copy_transpose_kernel<TS, TD, true>, grid, dim3(32, 8), (size_t)0, st, s, d);
   } else if (src.sc == 1 && dst.sw == 1 && src.c >= dst.c) {
     dim3 grid(ceil_div(dst.w, 32), ceil_div(dst.c, 32), dst.n * dst.h);
-    copy_transpose_kernel<TS, TD, false><<<grid, dim3(32, 8), 0, st>>>(s, d);
+    launch_k(copy_transpose_kernel<TS, TD, false>, grid, dim3(32, 8), (size_t)0, st, s, d);
   } else {
     long long total = npix * dst.c;
     int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
@@ -225,6 +238,7 @@ __device__ __forceinline__ void pack_job_transpose(const dc_pack_job& j, int loc
 }
 
 __global__ void __launch_bounds__(256) pack_multi_kernel(const dc_pack_job* __restrict__ jobs, int njobs) {
+  pdl_sync();
   int lo = 0, hi = njobs - 1;
   const int b = blockIdx.x;
   while (lo < hi) {                    // last job whose block_start <= b
@@ -243,6 +257,7 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const dc_pack_job* __re
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ G, int K, int N, int taps, int k_stride, int dst_k_first,
                                     float* __restrict__ dst) {
+  pdl_sync();
   long long total = (long long)taps * K * N;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   for (; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -264,6 +279,8 @@ extern "C" {
 
 int dc_abi_version(void) { return DC_ABI_VERSION; }
 const char* dc_last_error_string(void) { return dc::err_buf(); }
+int dc_set_pdl(int on) { dc::set_pdl(on); return 0; }
+int dc_get_pdl(void) { return dc::pdl_enabled() ? 1 : 0; }
 
 int dc_device_supports_tcgen05(void) {
   int dev = 0;
@@ -326,7 +343,7 @@ int dc_pack_weight(const float* src, int K, int N, int taps, int src_k_first, vo
 
 int dc_pack_weights_multi(const dc_pack_job* jobs_dev, int njobs, int total_blocks, void* stream) {
   DC_REQUIRE(jobs_dev != nullptr && njobs > 0 && total_blocks > 0, "dc_pack_weights_multi: bad arguments");
-  pack_multi_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(jobs_dev, njobs);
+  launch_k(pack_multi_kernel, dim3(total_blocks), dim3(256), (size_t)0, as_stream(stream), jobs_dev, njobs);
   return launch_status("dc_pack_weights_multi");
 }
 
@@ -334,7 +351,7 @@ int dc_unpack_wgrad(const float* G, int K, int N, int taps, int k_stride, int ds
   DC_REQUIRE(G && dst && K > 0 && N > 0 && taps > 0 && k_stride >= K, "dc_unpack_wgrad: bad arguments");
   long long total = (long long)taps * K * N;
   int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 8);
-  unpack_wgrad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(G, K, N, taps, k_stride, dst_k_first, dst);
+  launch_k(unpack_wgrad_kernel, dim3(blocks), dim3(256), (size_t)0, as_stream(stream), G, K, N, taps, k_stride, dst_k_first, dst);
   return launch_status("dc_unpack_wgrad");
 }
 

@@ -26,6 +26,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 }
 
 __global__ void __launch_bounds__(256) adam_multi_kernel(const dc_adam_job* __restrict__ jobs, int njobs, AdamScalars a) {
+  pdl_sync();
   int lo = 0, hi = njobs - 1;
   const int b = blockIdx.x;
   while (lo < hi) {
@@ -77,6 +78,6 @@ extern "C" int dc_adam_step_multi(const dc_adam_job* jobs_dev, int njobs, int to
   a.step_size = (float)(lr / bias_c1);
   a.bias_c2_sqrt = (float)sqrt(bias_c2);
   a.adamw = adamw;
-  adam_multi_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(jobs_dev, njobs, a);
+  launch_k(adam_multi_kernel, dim3(total_blocks), dim3(256), (size_t)0, as_stream(stream), jobs_dev, njobs, a);
   return launch_status("dc_adam_step_multi");
 }

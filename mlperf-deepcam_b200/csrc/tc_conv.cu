@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_gemm_tc_kernel(const __grid_c
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_sync();     // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   const int total_k = p.ntaps * p.kblocks;
 
@@ -458,6 +459,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_sync();     // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   const int b_block_bytes = BN * 128;
 
@@ -803,6 +805,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const __grid_
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_sync();     // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (n_iter > 0) {
     if (warp == 0) {
@@ -1019,7 +1022,7 @@ static int launch_fprop(const TcMaps& maps, const TcFpropParams& p, const TcFpro
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   dim3 grid(mtiles, ntiles, 1);
-  conv_gemm_tc_kernel<<<grid, kTcThreads, cfg.smem_bytes, st>>>(maps, p, cfg);
+  launch_k(conv_gemm_tc_kernel, grid, dim3(kTcThreads), (size_t)cfg.smem_bytes, st, maps, p, cfg);
   return launch_status("dc_conv_gemm_tc");
 }
 
@@ -1085,7 +1088,7 @@ static int launch_fprop_v2(const TcMaps& maps, const TcFpropParams& p, const TcV
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int grid = std::min(cfg.total_tiles, kNumSMs);
-  conv_gemm_tc2_kernel<<<grid, kTcThreads, cfg.smem_bytes, st>>>(maps, p, cfg);
+  launch_k(conv_gemm_tc2_kernel, grid, dim3(kTcThreads), (size_t)cfg.smem_bytes, st, maps, p, cfg);
   return launch_status("dc_conv_gemm_tc");
 }
 
@@ -1100,7 +1103,7 @@ static int launch_wgrad(const TcMaps& maps, const TcWgradParams& p, dim3 grid, c
   using Cfg = WgradCfg<BNW>;
   cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
   if (e != cudaSuccess) return fail((int)e, "dc_conv_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  conv_wgrad_tc_kernel<BNW><<<grid, kTcThreads, Cfg::kSmem, st>>>(maps, p);
+  launch_k(conv_wgrad_tc_kernel<BNW>, grid, dim3(kTcThreads), (size_t)Cfg::kSmem, st, maps, p);
   return launch_status("dc_conv_wgrad_tc");
 }
 

@@ -49,6 +49,8 @@ SIGNATURES = {
     "dc_abi_version": (c_int, []),
     "dc_last_error_string": (c_char_p, []),
     "dc_device_supports_tcgen05": (c_int, []),
+    "dc_set_pdl": (c_int, [c_int]),
+    "dc_get_pdl": (c_int, []),
     "dc_copy_view": (c_int, [dc_view, dc_view, c_void_p]),
     "dc_fill_zero": (c_int, [c_void_p, c_size_t, c_void_p]),
     "dc_i64_increment_many": (c_int, [c_void_p, c_int, c_void_p]),
