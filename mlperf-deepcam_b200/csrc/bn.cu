@@ -531,6 +531,13 @@ static int bn_bwd_apply_t(const dc_bn_params& p, const dc_view& dout, const dc_v
 // slice once, keeps it in shared memory, publishes its partial sums, waits at an inter-block barrier (all blocks are
 // co-resident: grid <= number of SMs, one block per SM) and then applies the coefficients to the data it holds.  Compared
 // with the stats + apply pair this saves one launch, the serial finalize tail and one full read of the tensor.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void grid_barrier(unsigned* ticket, unsigned expected) {
   __threadfence();
   __syncthreads();
@@ -571,24 +578,21 @@ __global__ void __launch_bounds__(kOnePassThreads, 1) bn_fwd_onepass_kernel(dc_b
   const long long stride = (long long)om.gx * m.ppb;
   const long long pix0 = (long long)blockIdx.x * m.ppb + warp * m.ppw + psub;
   if (ok) {
-    constexpr int U = 6;                      // loads in flight per thread
-    for (int k0 = 0; k0 < om.K; k0 += U) {
-      uint4 raw[U];
+    // the block's whole slice goes global -> shared memory with 16-byte cp.async copies that are all in flight at once
+    // (K per thread, no register staging): one L2/HBM round trip instead of K/6 dependent ones
+    const uint32_t hold_s = (uint32_t)__cvta_generic_to_shared(hold);
+    for (int k = 0; k < om.K; ++k) {
+      const long long pix = pix0 + k * stride;
+      if (pix < npix) cp_async16(hold_s + (uint32_t)(k * kOnePassThreads + threadIdx.x) * 16u, y.at(pix) + c0);
+    }
+    cp_async_commit_wait_all();
+    for (int k = 0; k < om.K; ++k) {
+      const long long pix = pix0 + k * stride;
+      if (pix < npix) {
+        float v[V];
+        vec16<T>::unpack(hold[k * kOnePassThreads + threadIdx.x], v);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long pix = pix0 + (k0 + u) * stride;
-        if (k0 + u < om.K && pix < npix) raw[u] = vec16<T>::ldraw(y.at(pix) + c0);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long pix = pix0 + (k0 + u) * stride;
-        if (k0 + u < om.K && pix < npix) {
-          hold[(k0 + u) * kOnePassThreads + threadIdx.x] = raw[u];
-          float v[V];
-          vec16<T>::unpack(raw[u], v);
-#pragma unroll
-          for (int j = 0; j < V; ++j) { acc[0][j] += v[j]; acc[1][j] = fmaf(v[j], v[j], acc[1][j]); }
-        }
+        for (int j = 0; j < V; ++j) { acc[0][j] += v[j]; acc[1][j] = fmaf(v[j], v[j], acc[1][j]); }
       }
     }
   }
@@ -660,56 +664,79 @@ __global__ void __launch_bounds__(kOnePassThreads, 1) bn_bwd_onepass_kernel(dc_b
   for (int j = 0; j < V; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
   const long long stride = (long long)om.gx * m.ppb;
   const long long pix0 = (long long)blockIdx.x * m.ppb + warp * m.ppw + psub;
+  const bool train = (p.flags & DC_BN_TRAIN) != 0;
+  // ReLU mask = (out > 0).  Without a residual, out = relu(fma(y, scale, shift)) with the forward coefficients still in the
+  // forward workspace, so the same decision is recomputed from y and `out` is not read at all (one input stream less).
+  const bool mask_from_y = relu && train && dres.p == nullptr;
   if (ok) {
-    constexpr int U = 3;                      // pixels (x 3 loads) in flight per thread
-    for (int k0 = 0; k0 < om.K; k0 += U) {
-      uint4 graws[U], yraws[U], oraws[U];
+    // gradient and pre-BN activation of the block's slice: global -> shared memory, every 16-byte copy in flight at once
+    const uint32_t hold_s = (uint32_t)__cvta_generic_to_shared(hold);
+    for (int k = 0; k < om.K; ++k) {
+      const long long pix = pix0 + k * stride;
+      if (pix < npix) {
+        const uint32_t d = hold_s + (uint32_t)(k * kOnePassThreads + threadIdx.x) * 32u;
+        cp_async16(d, dout.at(pix) + c0);
+        cp_async16(d + 16u, y.at(pix) + c0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    float fsc[V], fsh[V];
+    if (mask_from_y) {
+      const BnWs fws = bn_ws(const_cast<double*>(p.sums), C);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long pix = pix0 + (k0 + u) * stride;
-        if (k0 + u < om.K && pix < npix) {
-          graws[u] = vec16<T>::ldraw(dout.at(pix) + c0);
-          yraws[u] = vec16<T>::ldraw(y.at(pix) + c0);
-          if (relu) oraws[u] = vec16<T>::ldraw(out.at(pix) + c0);
+      for (int j = 0; j < V; ++j) { fsc[j] = fws.coef[c0 + j]; fsh[j] = fws.coef[C + c0 + j]; }
+    }
+    constexpr int U = 6;
+    const bool need_out = relu && !mask_from_y;
+    for (int k0 = 0; k0 < om.K; k0 += U) {
+      uint4 oraws[U];
+      if (need_out) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long pix = pix0 + (k0 + u) * stride;
+          if (k0 + u < om.K && pix < npix) oraws[u] = vec16<T>::ldraw(out.at(pix) + c0);
         }
       }
+      if (k0 == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-      const int k = k0 + u;
-      const long long pix = pix0 + k * stride;
-      if (k < om.K && pix < npix) {
-        const uint4 graw = graws[u];
-        const uint4 yraw = yraws[u];
-        float g[V], v[V];
-        vec16<T>::unpack(graw, g);
-        vec16<T>::unpack(yraw, v);
-        if (relu) {
-          float o[V];
-          vec16<T>::unpack(oraws[u], o);
-#pragma unroll
-          for (int j = 0; j < V; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < V; ++j) { acc[0][j] += g[j]; acc[1][j] = fmaf(g[j], v[j], acc[1][j]); }
-        // the masked gradient is kept in fp32-exact form only if T is float; for bf16 the mask just zeroes lanes, so
-        // re-packing loses nothing
-        uint4 gm;
-        if (sizeof(T) == 4) gm = make_uint4(__float_as_uint(g[0]), __float_as_uint(g[1]), __float_as_uint(g[2]), __float_as_uint(g[3]));
-        else {
-          gm = graw;
+        const int k = k0 + u;
+        const long long pix = pix0 + k * stride;
+        if (k < om.K && pix < npix) {
+          const uint4 graw = hold[(k * kOnePassThreads + threadIdx.x) * 2];
+          const uint4 yraw = hold[(k * kOnePassThreads + threadIdx.x) * 2 + 1];
+          float g[V], v[V];
+          vec16<T>::unpack(graw, g);
+          vec16<T>::unpack(yraw, v);
           if (relu) {
-            uint32_t w[4] = {graw.x, graw.y, graw.z, graw.w};
+            float o[V];
+            if (mask_from_y) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (g[(2 * q) % V] == 0.f) w[q] &= 0xffff0000u;
-              if (g[(2 * q + 1) % V] == 0.f) w[q] &= 0x0000ffffu;
+              for (int j = 0; j < V; ++j) o[j] = fmaf(v[j], fsc[j], fsh[j]);
+            } else {
+              vec16<T>::unpack(oraws[u], o);
             }
-            gm = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+            for (int j = 0; j < V; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < V; ++j) { acc[0][j] += g[j]; acc[1][j] = fmaf(g[j], v[j], acc[1][j]); }
+          if (relu) {
+            // write the masked gradient back (bf16: the mask only zeroes lanes, so re-packing loses nothing)
+            uint4 gm;
+            if (sizeof(T) == 4) gm = make_uint4(__float_as_uint(g[0]), __float_as_uint(g[1]), __float_as_uint(g[2]), __float_as_uint(g[3]));
+            else {
+              uint32_t w[4] = {graw.x, graw.y, graw.z, graw.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (g[(2 * q) % V] == 0.f) w[q] &= 0xffff0000u;
+                if (g[(2 * q + 1) % V] == 0.f) w[q] &= 0x0000ffffu;
+              }
+              gm = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            hold[(k * kOnePassThreads + threadIdx.x) * 2] = gm;
           }
         }
-        hold[(k * kOnePassThreads + threadIdx.x) * 2] = gm;
-        hold[(k * kOnePassThreads + threadIdx.x) * 2 + 1] = yraw;
-      }
       }
     }
   }
@@ -718,7 +745,6 @@ __global__ void __launch_bounds__(kOnePassThreads, 1) bn_bwd_onepass_kernel(dc_b
   grid_barrier(rws.ticket + blockIdx.y, (unsigned)om.gx);
   pdl_trigger();
   if (!ok) return;
-  const bool train = (p.flags & DC_BN_TRAIN) != 0;
   const double inv_count = 1.0 / p.count;
   const bool writer = (blockIdx.x == 0 && warp == 0 && psub == 0);
   float A[V], B[V], D[V];

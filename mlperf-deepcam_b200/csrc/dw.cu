@@ -13,6 +13,7 @@
 // and unpacked once per strip and scattered into the three live output rows with packed fp32 FMAs (FFMA2).
 #include "common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace dc {
 
@@ -223,6 +224,106 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_kernel(DwView<const T> in,
     step(r, nxt, a2, a0, a1);
     if (++r > l.y1) break;
     // after six steps the accumulator roles are back to (a0, a1, a2) and `cur` holds row r again
+  }
+}
+
+// ---- stride 1, dilation 1, shared-memory staged ---------------------------------------------------------------------------
+// Same arithmetic as dw_s1d1_kernel, but the block first pulls its whole input tile ((rs+2) rows x (ppb+2) pixels x cvp
+// channel vectors, <= 48 KB) into shared memory with 16-byte cp.async copies that are ALL in flight at once (zero-filled
+// outside the image = fixed_padding), and only then walks the rows out of shared memory.  The register-pipelined kernel
+// above has one row (3 loads) in flight per thread, i.e. a chain of rs+2 dependent L2/HBM round trips; for the 10 MB
+// middle-flow tensors that chain, not bandwidth, was the kernel's duration.
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_kernel(DwView<const T> in, const T* __restrict__ w9c, DwView<T> out, int C,
+                                                                  DwMap m, int flip, int accumulate) {
+  constexpr int VP = V / 2;
+  extern __shared__ uint4 dw_tile[];                  // [rs + 2][ppb + 2][cvp]
+  const DwLane l = dw_lane(m, out.h, out.w);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
+  const int TW = m.ppb + 2;
+  const int nrows = (l.y1 - l.y0) + 2;                // input rows y0-1 .. y1
+  const int x_base = blockIdx.x * m.ppb - 1, y_base = l.y0 - 1;
+  const int cv0 = blockIdx.y * m.cvp;
+  const int H = in.h, W = in.w;
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(dw_tile);
+  pdl_sync();
+  {
+    const int nvec = nrows * TW * m.cvp;
+    const int cshift = 31 - __clz(m.cvp);
+    const T* nbase = in.p + l.n * in.sn;
+    for (int i = threadIdx.x; i < nvec; i += kDwThreads) {
+      const int cl = i & (m.cvp - 1);
+      const int pix = i >> cshift;
+      const int ty = pix / TW, tx = pix - ty * TW;
+      const int gy = y_base + ty, gx = x_base + tx, cvi = cv0 + cl;
+      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W && cvi < m.cv;
+      const T* src = ok ? nbase + (long long)gy * in.sh + (long long)gx * in.sw + cvi * V : in.p;
+      cp_async16_zfill(tile_s + (uint32_t)i * 16u, src, ok);
+    }
+  }
+  float2 wv[9][VP];
+  if (l.ok) {
+    const int c0 = l.cvi * V;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dwpair<T>::unpack(ld16(w9c + (size_t)(flip ? 8 - k : k) * C + c0), wv[k]);
+  }
+  cp_async_commit_wait_all();
+  __syncthreads();
+  if (!l.ok) return;
+  T* obase = out.p + l.n * out.sn + (long long)l.x * out.sw + l.cvi * V;
+  const uint4* tp = dw_tile + ((warp * m.ppw + psub) * m.cvp + cvl);      // tile column of x-1, row 0
+  const int rstride = TW * m.cvp;
+  auto step = [&](int ty, float2 (&A)[VP], float2 (&B)[VP], float2 (&Cn)[VP]) {
+    const uint4* rp = tp + ty * rstride;
+    float2 f[3][VP];
+    dwpair<T>::unpack(rp[0], f[0]);
+    dwpair<T>::unpack(rp[m.cvp], f[1]);
+    dwpair<T>::unpack(rp[2 * m.cvp], f[2]);
+#pragma unroll
+    for (int j = 0; j < VP; ++j) {
+      Cn[j] = mul2(f[0][j], wv[0][j]);
+      Cn[j] = fma2(f[1][j], wv[1][j], Cn[j]);
+      Cn[j] = fma2(f[2][j], wv[2][j], Cn[j]);
+      B[j] = fma2(f[0][j], wv[3][j], B[j]);
+      B[j] = fma2(f[1][j], wv[4][j], B[j]);
+      B[j] = fma2(f[2][j], wv[5][j], B[j]);
+      A[j] = fma2(f[0][j], wv[6][j], A[j]);
+      A[j] = fma2(f[1][j], wv[7][j], A[j]);
+      A[j] = fma2(f[2][j], wv[8][j], A[j]);
+    }
+    const int y = y_base + ty - 1;                     // output row completed by input row y_base + ty
+    if (y >= l.y0 && y < l.y1) {
+      T* op = obase + (long long)y * out.sh;
+      if (accumulate) {
+        float2 old[VP];
+        dwpair<T>::unpack(ld16(op), old);
+#pragma unroll
+        for (int j = 0; j < VP; ++j) { A[j].x += old[j].x; A[j].y += old[j].y; }
+      }
+      st16(op, dwpair<T>::pack(A));
+    }
+  };
+  float2 a0[VP], a1[VP], a2[VP];
+#pragma unroll
+  for (int j = 0; j < VP; ++j) { a0[j] = make_float2(0.f, 0.f); a1[j] = a0[j]; a2[j] = a0[j]; }
+  int ty = 0;
+  while (true) {
+    step(ty, a0, a1, a2);
+    if (++ty >= nrows) break;
+    step(ty, a1, a2, a0);
+    if (++ty >= nrows) break;
+    step(ty, a2, a0, a1);
+    if (++ty >= nrows) break;
   }
 }
 
@@ -498,9 +599,39 @@ static inline dim3 dw_grid(const DwMap& m, int cols, int n_img) {
   return dim3((unsigned)ceil_div(cols, m.ppb), (unsigned)m.gy, (unsigned)(n_img * m.nstrips));
 }
 
+// DEEPCAM_B200_DW_TILE=0 selects the register-pipelined s1d1 kernels (for A/B measurements); default: staged tiles
+static bool dw_tile_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DEEPCAM_B200_DW_TILE"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+// rows per staged tile: measured on B200 (tools/kbench.py): 12 for the 48-row middle-flow tensors (9.6 us), 16 for the large
+// entry-flow / decoder tensors (3.7 TB/s vs 2.7 TB/s for the register-pipelined kernel); DEEPCAM_B200_DW_TILE_ROWS overrides
+static int dw_tile_rows(int H) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DEEPCAM_B200_DW_TILE_ROWS"); v = e ? atoi(e) : 0; if (v < 0 || v > 32) v = 0; }
+  return v > 0 ? v : (H >= 96 ? 16 : 12);
+}
+template <typename T, int V>
+static bool dw_s1d1_tile_launch(const dc_view& in, const void* w, const dc_view& out, int flip, int acc, cudaStream_t st) {
+  if (!dw_tile_enabled()) return false;
+  DwMap m = dw_map(out.c, V, out.h, out.w, out.n, 1 << 30, dw_tile_rows(out.h));
+  dim3 grid = dw_grid(m, out.w, out.n);
+  const size_t smem = (size_t)(m.rs + 2) * (m.ppb + 2) * m.cvp * 16;
+  if (smem > 200 * 1024) return false;                                         // odd row counts: register-pipelined kernel
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(dw_s1d1_tile_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return false;
+    attr_set = true;
+  }
+  launch_k(dw_s1d1_tile_kernel<T, V>, grid, dim3(kDwThreads), smem, st, dw_view<const T>(in), (const T*)w, dw_view<T>(out), out.c, m, flip, acc);
+  return true;
+}
+
 template <typename T>
 static int dw_fwd_t(const dc_view& in, const void* w, int s, int d, const dc_view& out, cudaStream_t st) {
   constexpr int V = dwvec<T>::V;
+  if (s == 1 && d == 1 && dw_s1d1_tile_launch<T, V>(in, w, out, 0, 0, st)) return launch_status("dc_dw_fwd");
   DwMap m = dw_map(out.c, V, out.h, out.w, out.n, kNumSMs * 4, 6);
   dim3 grid = dw_grid(m, out.w, out.n);
   if (s == 1 && d == 1)
@@ -512,6 +643,7 @@ static int dw_fwd_t(const dc_view& in, const void* w, int s, int d, const dc_vie
 template <typename T>
 static int dw_bwd_data_t(const dc_view& dout, const void* w, int s, int d, const dc_view& din, int acc, cudaStream_t st) {
   constexpr int V = dwvec<T>::V;
+  if (s == 1 && d == 1 && dw_s1d1_tile_launch<T, V>(dout, w, din, 1, acc, st)) return launch_status("dc_dw_bwd_data");
   DwMap m = dw_map(din.c, V, din.h, din.w, din.n, kNumSMs * 4, 6);
   dim3 grid = dw_grid(m, din.w, din.n);
   if (s == 1 && d == 1)          // full correlation with the flipped filter

@@ -90,6 +90,84 @@ __global__ void copy_transpose_kernel(View<const TS> s, View<TD> d) {
   }
 }
 
+// Path B2: few channels (the 16-channel network input, the 3(+pad) logits and their gradient).  One thread per pixel: the
+// planar side is read/written plane by plane (a warp covers 32 consecutive w = 128 contiguous bytes per plane), the pixel
+// side as whole 16-byte vectors; no shared memory, CP independent loads in flight per thread.
+template <typename T, int CP> struct pixvec;
+template <int CP> struct pixvec<float, CP> {
+  __device__ static __forceinline__ void store(float* p, const float (&v)[CP]) {
+#pragma unroll
+    for (int q = 0; q < CP / 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+  __device__ static __forceinline__ void load(const float* p, float (&v)[CP]) {
+#pragma unroll
+    for (int q = 0; q < CP / 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+  }
+};
+template <int CP> struct pixvec<__nv_bfloat16, CP> {
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&v)[CP]) {
+#pragma unroll
+    for (int q = 0; q < CP / 8; ++q) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * q + 2 * j], v[8 * q + 2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&b);
+      }
+      *reinterpret_cast<uint4*>(p + 8 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&v)[CP]) {
+#pragma unroll
+    for (int q = 0; q < CP / 8; ++q) {
+      const uint4 t = *reinterpret_cast<const uint4*>(p + 8 * q);
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { v[8 * q + 2 * j] = __uint_as_float(w[j] << 16); v[8 * q + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+    }
+  }
+};
+
+template <typename TS, typename TD, int CP>
+__global__ void __launch_bounds__(256) copy_planar_to_pixel_kernel(View<const TS> s, View<TD> d, long long npix) {
+  pdl_sync();
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int w = (int)(pix % d.w);
+  const long long t = pix / d.w;
+  const int h = (int)(t % d.h), n = (int)(t / d.h);
+  const TS* sp = s.p + n * s.sn + h * s.sh + w;               // s.sw == 1
+  float v[CP];
+#pragma unroll
+  for (int c = 0; c < CP; ++c) v[c] = (c < s.c) ? elem<TS>::ld(sp + c * s.sc) : 0.f;
+  pixvec<TD, CP>::store(d.at(n, h, w), v);
+}
+template <typename TS, typename TD, int CP>
+__global__ void __launch_bounds__(256) copy_pixel_to_planar_kernel(View<const TS> s, View<TD> d, long long npix) {
+  pdl_sync();
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int w = (int)(pix % d.w);
+  const long long t = pix / d.w;
+  const int h = (int)(t % d.h), n = (int)(t / d.h);
+  float v[CP];
+  pixvec<TS, CP>::load(s.at(n, h, w), v);
+  TD* dp = d.p + n * d.sn + h * d.sh + w;                     // d.sw == 1
+#pragma unroll
+  for (int c = 0; c < CP; ++c)
+    if (c < d.c) elem<TD>::st(dp + c * d.sc, c < s.c ? v[c] : 0.f);
+}
+// the pixel side of a view: CP channels per pixel, unit channel stride, every pixel 16-byte aligned
+static inline bool pixel_side_ok(const dc_view& v, int CP) {
+  const size_t vb = (size_t)CP * dtype_size(v.dtype);
+  const size_t es = dtype_size(v.dtype);
+  return v.sc == 1 && vb % 16 == 0 && (v.sw * es) % 16 == 0 && (v.sh * es) % 16 == 0 && (v.sn * es) % 16 == 0 &&
+         (reinterpret_cast<uintptr_t>(v.ptr) % 16) == 0;
+}
+
 // Path C: fully generic scalar copy.
 template <typename TS, typename TD>
 __global__ void copy_scalar_kernel(View<const TS> s, View<TD> d, long long total) {
@@ -115,6 +193,17 @@ static int copy_dispatch(const dc_view& src, const dc_view& dst, cudaStream_t st
     long long total = npix * (dst.c / 4);
     int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
     launch_k(copy_vec4_kernel<TS, TD>, dim3(blocks), dim3(256), (size_t)0, st, s, d, npix);
+  } else if (src.sw == 1 && src.c <= dst.c && (dst.c == 8 || dst.c == 16) && pixel_side_ok(dst, dst.c)) {
+    const unsigned blocks = (unsigned)ceil_div64(npix, 256);
+    if (dst.c == 8) launch_k(copy_planar_to_pixel_kernel<TS, TD, 8>, dim3(blocks), dim3(256), (size_t)0, st, s, d, npix);
+    else launch_k(copy_planar_to_pixel_kernel<TS, TD, 16>, dim3(blocks), dim3(256), (size_t)0, st, s, d, npix);
+  } else if (dst.sw == 1 && src.c <= src.sw && (src.sw == 8 || src.sw == 16) && pixel_side_ok(src, (int)src.sw) &&
+             (reinterpret_cast<uintptr_t>(src.ptr) % ((size_t)src.sw * dtype_size(src.dtype))) == 0 && src.sh % src.sw == 0 &&
+             src.sn % src.sw == 0) {
+    // the source pixel is read as its whole pitch (8 or 16 elements, e.g. 3 logits padded to 8); pad lanes are ignored
+    const unsigned blocks = (unsigned)ceil_div64(npix, 256);
+    if (src.sw == 8) launch_k(copy_pixel_to_planar_kernel<TS, TD, 8>, dim3(blocks), dim3(256), (size_t)0, st, s, d, npix);
+    else launch_k(copy_pixel_to_planar_kernel<TS, TD, 16>, dim3(blocks), dim3(256), (size_t)0, st, s, d, npix);
   } else if (src.sw == 1 && dst.sc == 1 && src.c <= dst.c) {
     dim3 grid(ceil_div(dst.w, 32), ceil_div(dst.c, 32), dst.n * dst.h);
     launch_k(copy_transpose_kernel<TS, TD, true>, grid, dim3(32, 8), (size_t)0, st, s, d);
@@ -205,33 +294,63 @@ __device__ __forceinline__ void pack_job_elems(const dc_pack_job& j, int local_b
   }
 }
 
-// Transposing packs (source [k][n][taps] -> destination [n][tap][k_pad]: every dgrad-role Conv2d weight and every fprop-role
-// ConvTranspose2d weight) go through a 32 x 32 shared-memory tile so that both the global reads (along n) and the
-// global writes (along k) are coalesced; the element-wise path would read one 4-byte word per 32-byte sector.
+// Packs with more than one tap, or with swapped roles, go through shared memory so that BOTH sides are coalesced; the
+// element-wise path reads one 4-byte word per 36-byte stride (3x3 weights) or per row (transposes), i.e. one useful
+// word per 32-byte sector.
+//
+// (a) source [n][k][taps] -> destination [n][tap][k_pad] (fprop role of a 3x3 Conv2d, dgrad role of a ConvTranspose2d):
+//     a work item is one n and 256 consecutive k: 256*taps contiguous source floats in, `taps` runs of 256 elements out.
+constexpr int kPackMaxTaps = 9;
 template <typename TD>
-__device__ __forceinline__ void pack_job_transpose(const dc_pack_job& j, int local_block, int tid) {
-  __shared__ float tile[32][33];
-  const int tx = tid & 31, ty = tid >> 5;            // 32 x 8
-  const int kt = (j.K_pad + 31) >> 5, ntl = (j.N_pad + 31) >> 5;
-  const int ntiles = j.taps * kt * ntl;
+__device__ __forceinline__ void pack_job_taps(const dc_pack_job& j, int local_block, int tid, float* sm) {
+  const int kchunks = (j.K_pad + 255) >> 8;
+  const int nitems = j.N_pad * kchunks;
+  const float* __restrict__ src = j.src;
+  TD* __restrict__ dst = reinterpret_cast<TD*>(j.dst);
+  for (int it = local_block; it < nitems; it += j.n_blocks) {
+    const int n = it / kchunks, k0 = (it - n * kchunks) << 8;
+    const int kcount = min(256, j.K - k0);                         // valid k of this chunk (<= 0: pure padding)
+    const int nfl = (n < j.N && kcount > 0) ? kcount * j.taps : 0;
+    const float* sp = src + ((long long)n * j.K + k0) * j.taps;
+    for (int e = tid; e < nfl; e += 256) sm[e] = sp[e];
+    __syncthreads();
+    const int kk = k0 + tid;
+    if (kk < j.K_pad) {
+      for (int t = 0; t < j.taps; ++t) {
+        const float v = (tid * j.taps + t < nfl) ? sm[tid * j.taps + t] : 0.f;
+        elem<TD>::st(dst + ((long long)n * j.taps + t) * j.K_pad + kk, v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// (b) source [k][n][taps] -> destination [n][tap][k_pad] (dgrad role of a Conv2d, fprop role of a ConvTranspose2d): a work
+//     item is 64 k x TN n (TN*taps <= 72 floats per k row, contiguous in the source); the destination gets runs of 64 k.
+template <typename TD>
+__device__ __forceinline__ void pack_job_transpose(const dc_pack_job& j, int local_block, int tid, float* sm) {
+  const int TN = j.taps == 1 ? 32 : (j.taps <= 2 ? 16 : 8);
+  const int RW = TN * j.taps;                    // floats per k row of the tile
+  const int pitch = RW | 1;                      // odd pitch: conflict-free column reads
+  const int kt = (j.K_pad + 63) >> 6, ntl = (j.N_pad + TN - 1) / TN;
+  const int ntiles = kt * ntl;
   const float* __restrict__ src = j.src;
   TD* __restrict__ dst = reinterpret_cast<TD*>(j.dst);
   for (int tl = local_block; tl < ntiles; tl += j.n_blocks) {
-    const int t = tl / (kt * ntl);
-    const int r = tl - t * kt * ntl;
-    const int k0 = (r / ntl) << 5, n0 = (r % ntl) << 5;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int k = k0 + ty + 8 * q, n = n0 + tx;
+    const int k0 = (tl / ntl) << 6, n0 = (tl % ntl) * TN;
+    const int rw_valid = max(0, min(RW, (j.N - n0) * j.taps));
+    for (int e = tid; e < 64 * RW; e += 256) {
+      const int k = e / RW, r = e - k * RW;
       float v = 0.f;
-      if (k < j.K && n < j.N) v = src[((long long)k * j.N + n) * j.taps + t];
-      tile[ty + 8 * q][tx] = v;
+      if (k0 + k < j.K && r < rw_valid) v = src[((long long)(k0 + k) * j.N + n0) * j.taps + r];
+      sm[k * pitch + r] = v;
     }
     __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int n = n0 + ty + 8 * q, k = k0 + tx;
-      if (n < j.N_pad && k < j.K_pad) elem<TD>::st(dst + ((long long)n * j.taps + t) * j.K_pad + k, tile[tx][ty + 8 * q]);
+    for (int e = tid; e < 64 * RW; e += 256) {
+      const int kk = e & 63, row = e >> 6;      // row = n_local * taps + t
+      const int nl = row / j.taps, t = row - nl * j.taps;
+      if (n0 + nl < j.N_pad && k0 + kk < j.K_pad)
+        elem<TD>::st(dst + ((long long)(n0 + nl) * j.taps + t) * j.K_pad + k0 + kk, sm[kk * pitch + row]);
     }
     __syncthreads();
   }
@@ -246,13 +365,22 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const dc_pack_job* __re
     if (jobs[mid].block_start <= b) lo = mid; else hi = mid - 1;
   }
   const dc_pack_job j = jobs[lo];
-  if (j.layout == DC_PACK_NTK && j.src_k_first) {
-    if (j.dst_dtype == DC_F32) pack_job_transpose<float>(j, b - j.block_start, threadIdx.x);
-    else pack_job_transpose<__nv_bfloat16>(j, b - j.block_start, threadIdx.x);
-    return;
+  __shared__ float sm[64 * 73];                 // 18.7 KB: 64 x (72 | 1) transpose tile, or 256 x 9 tap chunk
+  const int lb = b - j.block_start;
+  if (j.layout == DC_PACK_NTK && j.taps <= kPackMaxTaps) {
+    if (j.src_k_first) {
+      if (j.dst_dtype == DC_F32) pack_job_transpose<float>(j, lb, threadIdx.x, sm);
+      else pack_job_transpose<__nv_bfloat16>(j, lb, threadIdx.x, sm);
+      return;
+    }
+    if (j.taps > 1) {
+      if (j.dst_dtype == DC_F32) pack_job_taps<float>(j, lb, threadIdx.x, sm);
+      else pack_job_taps<__nv_bfloat16>(j, lb, threadIdx.x, sm);
+      return;
+    }
   }
-  if (j.dst_dtype == DC_F32) pack_job_elems<float>(j, b - j.block_start, threadIdx.x);
-  else pack_job_elems<__nv_bfloat16>(j, b - j.block_start, threadIdx.x);
+  if (j.dst_dtype == DC_F32) pack_job_elems<float>(j, lb, threadIdx.x);
+  else pack_job_elems<__nv_bfloat16>(j, lb, threadIdx.x);
 }
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ G, int K, int N, int taps, int k_stride, int dst_k_first,

@@ -109,7 +109,15 @@ def _shape_tag(t):
     return "%dx%dx%dx%d" % tuple(t.shape)
 
 
+# Measurement aid (tools/ablate.py): kernel classes named in DEEPCAM_B200_ABLATE are NOT launched, so the step time
+# difference is that class's share of the critical path.  Results are garbage while it is set; never set it otherwise.
+import os as _os
+_ABLATE = tuple(s for s in _os.environ.get("DEEPCAM_B200_ABLATE", "").split(",") if s)
+
+
 def _timed(name, flops, nbytes, rc_fn, what, tag=""):
+    if _ABLATE and any(name.startswith(a) for a in _ABLATE):
+        return
     if _prof is None:
         check(rc_fn(), what)
         return

@@ -69,6 +69,20 @@ def test_copy_view_layouts(dtype):
     ops.copy_view(g.permute(0, 2, 3, 1), gp)
     assert torch.equal(gp[..., :3].cpu(), g.permute(0, 2, 3, 1).to(dtype).cpu())
     assert float(gp[..., 3].abs().max()) == 0.0
+    # few-channel fast paths: 3 logits stored with a pitch of 8 -> NCHW planes; NCHW (3 ch) -> pitch-8 pixels (pad zeroed);
+    # a 3-channel slice that does not start at the pixel base must take the generic path and stay correct
+    y8 = torch.rand(2, 25, 41, 8).to(dtype).to(dev())
+    back = torch.full((2, 3, 25, 41), 7.0, dtype=torch.float32, device=dev())
+    ops.copy_view(y8[..., :3], back.permute(0, 2, 3, 1))
+    assert torch.equal(back.cpu(), y8[..., :3].permute(0, 3, 1, 2).float().cpu())
+    back2 = torch.full((2, 3, 25, 41), 7.0, dtype=torch.float32, device=dev())
+    ops.copy_view(y8[..., 4:7], back2.permute(0, 2, 3, 1))
+    assert torch.equal(back2.cpu(), y8[..., 4:7].permute(0, 3, 1, 2).float().cpu())
+    g3 = torch.rand(2, 3, 25, 41, device=dev())
+    gp8 = torch.full((2, 25, 41, 8), 7.0, dtype=dtype, device=dev())
+    ops.copy_view(g3.permute(0, 2, 3, 1), gp8)
+    assert torch.equal(gp8[..., :3].cpu(), g3.permute(0, 2, 3, 1).to(dtype).cpu())
+    assert float(gp8[..., 3:].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -136,12 +150,13 @@ def test_bn_eval_mode_and_n1_error():
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("C,stride,dil", [(64, 1, 1), (128, 2, 1), (728, 1, 1), (1024, 1, 2)])
-def test_depthwise(dtype, C, stride, dil):
+@pytest.mark.parametrize("C,stride,dil,H,W", [(64, 1, 1, 14, 22), (128, 2, 1, 14, 22), (728, 1, 1, 14, 22), (1024, 1, 2, 14, 22),
+                                               (8, 1, 1, 5, 7), (16, 1, 1, 11, 300), (728, 1, 1, 48, 72), (256, 1, 1, 13, 9)])
+def test_depthwise(dtype, C, stride, dil, H, W):
     be = backend(dtype)
     from deepcam_b200.backend import DwSpec
     torch.manual_seed(2)
-    N, H, W = 2, 14, 22
+    N = 2
     w = torch.nn.Parameter(rounded(torch.randn(C, 1, 3, 3) * 0.3, dtype).float().to(dev()))
     spec = DwSpec("dw", w, stride, dil)
     x = rounded(torch.randn(N, C, H, W), dtype)
@@ -417,3 +432,38 @@ def test_fused_adam_matches_torch(adamw):
         assert set(sd_ref["state"][k]) == set(sd_mine["state"][k]) == {"step", "exp_avg", "exp_avg_sq"}
         assert float(sd_ref["state"][k]["step"]) == float(sd_mine["state"][k]["step"]) == 4.0
         assert rel(sd_mine["state"][k]["exp_avg_sq"], sd_ref["state"][k]["exp_avg_sq"]) < 1e-6
+
+
+@pytest.mark.parametrize("dst_dtype", DTYPES)
+def test_multi_pack_matches_definition(dst_dtype):
+    """dc_pack_weights_multi (one launch, shared-memory staged paths) against the layout definition computed with torch
+    indexing: bit-exact for every (taps, role, padding) combination the network uses, plus ragged sizes."""
+    from deepcam_b200 import ops
+    from deepcam_b200._lib import DC_PACK_NTK, DC_PACK_TKN
+    torch.manual_seed(7)
+    cases = [  # K, N, taps, src_k_first, layout, K_pad, N_pad
+        (728, 728, 1, False, DC_PACK_NTK, 768, 728), (728, 728, 1, True, DC_PACK_NTK, 768, 728),
+        (304, 256, 9, False, DC_PACK_NTK, 320, 256), (256, 304, 9, True, DC_PACK_NTK, 256, 304),
+        (16, 32, 9, False, DC_PACK_NTK, 64, 32), (256, 3, 9, True, DC_PACK_NTK, 256, 16),
+        (100, 37, 4, True, DC_PACK_NTK, 128, 48), (100, 37, 2, False, DC_PACK_NTK, 128, 48),
+        (300, 70, 9, True, DC_PACK_NTK, 320, 70), (48, 20, 9, False, DC_PACK_TKN, 48, 20)]
+    jobs, expect = [], []
+    for (K, N, taps, skf, layout, K_pad, N_pad) in cases:
+        src = torch.randn((K, N, taps) if skf else (N, K, taps), device=dev())
+        dst = torch.full((taps * K_pad * N_pad,), 7.0, dtype=dst_dtype, device=dev())
+        knt = src if skf else src.permute(1, 0, 2)                 # [k][n][t]
+        if layout == DC_PACK_NTK:
+            ref = torch.zeros(N_pad, taps, K_pad, device=dev())
+            ref[:N, :, :K] = knt.permute(1, 2, 0)
+        else:
+            ref = torch.zeros(taps, K_pad, N_pad, device=dev())
+            ref[:, :K, :N] = knt.permute(2, 0, 1)
+        jobs.append((src, dst, K, N, taps, skf, layout, K_pad, N_pad))
+        expect.append(ref.reshape(-1).to(dst_dtype))
+    table = ops.build_pack_table(jobs, dev())
+    ops.pack_weights_multi(*table)
+    torch.cuda.synchronize()
+    for (job, ref) in zip(jobs, expect):
+        assert torch.equal(job[1], ref), job[2:]
+        single = ops.pack_weight(job[0], *job[2:], dst_dtype)
+        assert torch.equal(single, ref), job[2:]
