@@ -119,6 +119,13 @@ int dc_conv_wgrad_simt(const dc_conv_desc* d, dc_view in, dc_view dout, float* G
  * `w` is DC_PACK_NTK bf16 with k_pad = round_up(in.c, 64).  in.c % 8 == 0, strides 16-byte aligned. */
 int dc_conv_gemm_tc(const dc_conv_desc* d, dc_view in, const void* w, const float* bias,
                     dc_view out, void* stream);
+/* Same contraction, plus the BatchNorm batch sums of the result: on return (in stream order) sums[c] += sum over pixels of
+ * out[.., c] and sums[out.c + c] += sum of squares, taken from the bf16-rounded values that were stored (`sums` = the
+ * zeroed per-layer workspace of dc_bn_ws_bytes; pass it to dc_bn_apply with DC_BN_TRAIN | DC_BN_SUMS_READY).  The sums come
+ * out of the GEMM epilogue (no extra pass over `out`); output layouts the TMA-store epilogue cannot write get one
+ * statistics pass appended.  d->accumulate must be 0.  Replaces the statistics half of nn.BatchNorm2d after a conv. */
+int dc_conv_gemm_tc_bnstats(const dc_conv_desc* d, dc_view in, const void* w, const float* bias,
+                            dc_view out, double* sums, void* stream);
 /* tcgen05 weight gradient (both operands pixel-major): same contract as dc_conv_wgrad_simt. */
 int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, void* stream);
 
@@ -141,7 +148,10 @@ enum {
   DC_BN_RELU       = 1,   /* out = relu(...) */
   DC_BN_TRAIN      = 2,   /* batch statistics from the workspace `sums` */
   DC_BN_IDENTITY   = 4,   /* skip normalisation (pure relu / add) */
-  DC_BN_RES_WRITE  = 8    /* backward: residual gradient is written, not accumulated */
+  DC_BN_RES_WRITE  = 8,   /* backward: residual gradient is written, not accumulated */
+  DC_BN_SUMS_READY = 16   /* forward apply, train mode: the workspace holds the raw batch sums (left there by
+                             dc_conv_gemm_tc_bnstats); dc_bn_apply derives the coefficients itself, stores them for the
+                             backward pass and updates the running statistics: no dc_bn_stats launch */
 };
 typedef struct dc_bn_params {
   const float* gamma;  const float* beta;      /* [C] */

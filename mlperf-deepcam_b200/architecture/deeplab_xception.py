@@ -95,11 +95,11 @@ class SeparableConv2d(_EngineModule):
         self.conv1 = nn.Conv2d(inplanes, inplanes, kernel_size, stride, padding, dilation, groups=inplanes, bias=bias)
         self.pointwise = nn.Conv2d(inplanes, planes, 1, 1, 0, 1, 1, bias=bias)
 
-    def _emit(self, eng, x):
+    def _emit(self, eng, x, bn=None):
         if self.conv1.padding[0] != self.conv1.dilation[0]:
             raise NotImplementedError("deepcam_b200: SeparableConv2d needs padding == dilation")
         t = eng.dw(x, _dw_spec(self.conv1))
-        return eng.conv(t, _conv_spec(self.pointwise))
+        return eng.conv(t, _conv_spec(self.pointwise), bn=bn)
 
 
 def fixed_padding(inputs, kernel_size, rate):
@@ -120,9 +120,10 @@ class SeparableConv2d_same(_EngineModule):
         self.conv1 = nn.Conv2d(inplanes, inplanes, kernel_size, stride, 0, dilation, groups=inplanes, bias=bias)
         self.pointwise = nn.Conv2d(inplanes, planes, 1, 1, 0, 1, 1, bias=bias)
 
-    def _emit(self, eng, x):
+    def _emit(self, eng, x, bn=None):
+        """bn: BnSpec of the normalizer that follows (its batch sums then come out of the pointwise GEMM's epilogue)."""
         t = eng.dw(x, _dw_spec(self.conv1))
-        return eng.conv(t, _conv_spec(self.pointwise))
+        return eng.conv(t, _conv_spec(self.pointwise), bn=bn)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -168,9 +169,10 @@ class Block(_EngineModule):
             inp = eng.bn(inp, None, relu=True)               # explicit ReLU (stand-alone use on a raw tensor)
         skip_y = None
         if self.skip is not None:                             # emitted first so its strided dgrad accumulates last
-            skip_y = eng.conv(inp, _conv_spec(self.skip))
+            skip_y = eng.conv(inp, _conv_spec(self.skip), bn=_bn_spec(self.skipbn))
         cur, pending = inp, None
-        for m in self.rep._modules.values():
+        mods = list(self.rep._modules.values())
+        for i, m in enumerate(mods):
             if isinstance(m, nn.ReLU):
                 if pending is not None:
                     cur = eng.bn(pending[1], pending[0], relu=True)
@@ -181,7 +183,9 @@ class Block(_EngineModule):
                 if pending is not None:
                     cur = eng.bn(pending[1], pending[0], relu=False)
                     pending = None
-                cur = m._emit(eng, cur)
+                nxt = mods[i + 1] if i + 1 < len(mods) else None
+                follows = nxt is not None and not isinstance(nxt, (nn.ReLU, SeparableConv2d_same))
+                cur = m._emit(eng, cur, bn=_bn_spec(nxt) if follows else None)
             else:
                 pending = (_bn_spec(m), cur)
         if skip_y is not None:
@@ -245,16 +249,16 @@ class Xception(_EngineModule):
                 m.bias.data.zero_()
 
     def _emit(self, eng, x):
-        h = eng.bn(eng.conv(x, _conv_spec(self.conv1)), _bn_spec(self.bn1), relu=True)
-        h = eng.bn(eng.conv(h, _conv_spec(self.conv2)), _bn_spec(self.bn2), relu=True)
+        h = eng.bn(eng.conv(x, _conv_spec(self.conv1), bn=_bn_spec(self.bn1)), _bn_spec(self.bn1), relu=True)
+        h = eng.bn(eng.conv(h, _conv_spec(self.conv2), bn=_bn_spec(self.bn2)), _bn_spec(self.bn2), relu=True)
         h = self.block1._emit(eng, h, out_relu=True)
         low = h                                               # aliases relu(block1 output), DX:206 + SURVEY §0.3
         for i in range(2, 20):
             h = getattr(self, "block%d" % i)._emit(eng, h, out_relu=True)
         h = self.block20._emit(eng, h, out_relu=False)
-        h = eng.bn(self.conv3._emit(eng, h), _bn_spec(self.bn3), relu=True)
-        h = eng.bn(self.conv4._emit(eng, h), _bn_spec(self.bn4), relu=True)
-        h = eng.bn(self.conv5._emit(eng, h), _bn_spec(self.bn5), relu=True)
+        h = eng.bn(self.conv3._emit(eng, h, bn=_bn_spec(self.bn3)), _bn_spec(self.bn3), relu=True)
+        h = eng.bn(self.conv4._emit(eng, h, bn=_bn_spec(self.bn4)), _bn_spec(self.bn4), relu=True)
+        h = eng.bn(self.conv5._emit(eng, h, bn=_bn_spec(self.bn5)), _bn_spec(self.bn5), relu=True)
         return h, low
 
     def _emit_root(self, eng, x):
@@ -283,7 +287,7 @@ class ASPP_module(_EngineModule):
             self.bn.bias.data.zero_()
 
     def _emit(self, eng, x, out=None):
-        y = eng.conv(x, _conv_spec(self.atrous_convolution))
+        y = eng.conv(x, _conv_spec(self.atrous_convolution), bn=_bn_spec(self.bn))
         return eng.bn(y, _bn_spec(self.bn), relu=True, out=out)
 
 
@@ -329,15 +333,15 @@ class DeconvUpsampler(_EngineModule):
         """x: [N,h,w,256]; either `low` ([N,4h,4w,48], copied into the concat buffer) or `cat` (a [N,4h,4w,304]
         buffer whose channels 256..303 already hold the low-level features) must be given."""
         n, h, w, _ = x.shape
-        y = eng.bn(eng.conv(x, _conv_spec(self.deconv1[0])), _bn_spec(self.deconv1[1]), relu=True)
+        y = eng.bn(eng.conv(x, _conv_spec(self.deconv1[0]), bn=_bn_spec(self.deconv1[1])), _bn_spec(self.deconv1[1]), relu=True)
         if cat is None:
             cat = eng.new_act(n, 4 * h, 4 * w, 256 + low.shape[3], x.t.dtype)
             eng.bn(low, None, relu=False, out=cat.slice(256, low.shape[3]))        # copy (torch.cat, DX:379)
-        eng.bn(eng.conv(y, _conv_spec(self.deconv2[0])), _bn_spec(self.deconv2[1]), relu=True, out=cat.slice(0, 256))
-        y = eng.bn(eng.conv(cat, _conv_spec(self.conv1[0])), _bn_spec(self.conv1[1]), relu=True)
-        y = eng.bn(eng.conv(y, _conv_spec(self.conv1[3])), _bn_spec(self.conv1[4]), relu=True)
+        eng.bn(eng.conv(y, _conv_spec(self.deconv2[0]), bn=_bn_spec(self.deconv2[1])), _bn_spec(self.deconv2[1]), relu=True, out=cat.slice(0, 256))
+        y = eng.bn(eng.conv(cat, _conv_spec(self.conv1[0]), bn=_bn_spec(self.conv1[1])), _bn_spec(self.conv1[1]), relu=True)
+        y = eng.bn(eng.conv(y, _conv_spec(self.conv1[3]), bn=_bn_spec(self.conv1[4])), _bn_spec(self.conv1[4]), relu=True)
         y = eng.conv(y, _conv_spec(self.conv1[6]))
-        y = eng.bn(eng.conv(y, _conv_spec(self.deconv3[0])), _bn_spec(self.deconv3[1]), relu=True)
+        y = eng.bn(eng.conv(y, _conv_spec(self.deconv3[0]), bn=_bn_spec(self.deconv3[1])), _bn_spec(self.deconv3[1]), relu=True)
         # logits stay fp32; channels padded for the vectorised kernels (8 in bf16 mode so that the logit gradient
         # is a legal TMA operand: 16-byte pixel pitch)
         co = self.n_output
@@ -396,12 +400,12 @@ class DeepLabv3_plus(_EngineModule):
         for i, aspp in enumerate((self.aspp1, self.aspp2, self.aspp3, self.aspp4)):
             aspp._emit(eng, feat, out=cat.slice(256 * i, 256))
         g = eng.gap(feat)                                                          # fp32 [N,1,1,2048], DX:425
-        g = eng.bn(eng.conv(g, _conv_spec(self.global_avg_pool[1])), _bn_spec(self.global_avg_pool[2]), relu=True)
+        g = eng.bn(eng.conv(g, _conv_spec(self.global_avg_pool[1]), bn=_bn_spec(self.global_avg_pool[2])), _bn_spec(self.global_avg_pool[2]), relu=True)
         eng.broadcast(g, cat.slice(1024, 256))                                     # DX:450
-        y = eng.bn(eng.conv(cat, _conv_spec(self.conv1)), _bn_spec(self.bn1), relu=True)
+        y = eng.bn(eng.conv(cat, _conv_spec(self.conv1), bn=_bn_spec(self.bn1)), _bn_spec(self.bn1), relu=True)
         ln, lh, lw, _ = low.shape
         dcat = eng.new_act(ln, lh, lw, 256 + 48, low.t.dtype)                      # torch.cat target, DX:379
-        eng.bn(eng.conv(low, _conv_spec(self.conv2)), _bn_spec(self.bn2), relu=True, out=dcat.slice(256, 48))
+        eng.bn(eng.conv(low, _conv_spec(self.conv2), bn=_bn_spec(self.bn2)), _bn_spec(self.bn2), relu=True, out=dcat.slice(256, 48))
         return self.upsample._emit(eng, y, cat=dcat)
 
     def _emit_root(self, eng, x):

@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(dc_bn_params p, Pi
   }
   BnWs ws = bn_ws(const_cast<double*>(p.sums), C);
   reduce_to_ws<2, V>(acc, ws.sums, C, m.cvp, blockIdx.y * m.cvp, min(m.cvp, m.cv - blockIdx.y * m.cvp));
+  if (p.flags & DC_BN_SUMS_READY) return;          // sums-only use (bn_accumulate_sums): the consumer finalizes
   if (!last_block(ws.ticket)) return;
   // ---- finalize: batch statistics -> fp32 coefficients, running statistics (torch uses the unbiased variance there).
   // mean and variance in double (cancellation), 1/sqrt in fp32 with one Newton step (the apply path is fp32 anyway).
@@ -232,10 +233,40 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(dc_bn_params p, Pi
 // per-thread forward coefficients of V channels
 template <int V>
 __device__ __forceinline__ void load_fwd_coef(const dc_bn_params& p, int C, int c0, float (&scale)[V], float (&shift)[V],
-                                              float (&mean)[V], float (&invstd)[V]) {
+                                              float (&mean)[V], float (&invstd)[V], bool writer = false) {
   if (p.flags & DC_BN_IDENTITY) {
 #pragma unroll
     for (int j = 0; j < V; ++j) { scale[j] = 1.f; shift[j] = 0.f; mean[j] = 0.f; invstd[j] = 1.f; }
+  } else if ((p.flags & DC_BN_TRAIN) && (p.flags & DC_BN_SUMS_READY)) {
+    // the producer of y (GEMM epilogue) left the raw sums in the workspace: every thread finalizes its own channels (same
+    // arithmetic as the last block of bn_stats_kernel); `writer` threads (one per channel) also publish the coefficients
+    // for the backward pass and update the running statistics
+    const BnWs ws = bn_ws(const_cast<double*>(p.sums), C);
+    const double inv_count = 1.0 / p.count;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int c = c0 + j;
+      const double sm = ws.sums[c], sq = ws.sums[C + c];
+      const double mu = sm * inv_count;
+      double var = sq * inv_count - mu * mu;
+      if (var < 0.0) var = 0.0;
+      const float inv = inv_sqrt_f32((float)(var + (double)p.eps));
+      scale[j] = p.gamma[c] * inv;
+      shift[j] = p.beta[c] - (float)mu * scale[j];
+      mean[j] = (float)mu;
+      invstd[j] = inv;
+      if (writer) {
+        ws.coef[c] = scale[j];
+        ws.coef[C + c] = shift[j];
+        ws.coef[2 * C + c] = mean[j];
+        ws.coef[3 * C + c] = inv;
+        if (p.running_mean != nullptr) {
+          const double unbias = p.count / (p.count - 1.0);
+          p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mu;
+          p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)(var * unbias);
+        }
+      }
+    }
   } else if (p.flags & DC_BN_TRAIN) {
     const BnWs ws = bn_ws(const_cast<double*>(p.sums), C);
 #pragma unroll
@@ -265,7 +296,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_apply_kernel(dc_bn_params p,
   if (cvi >= m.cv) return;
   const int c0 = cvi * V;
   float scale[V], shift[V], mean[V], invstd[V];
-  load_fwd_coef<V>(p, C, c0, scale, shift, mean, invstd);
+  load_fwd_coef<V>(p, C, c0, scale, shift, mean, invstd, blockIdx.x == 0 && warp == 0 && psub == 0);
   const bool relu = (p.flags & DC_BN_RELU) != 0;
   const bool has_res = res.p != nullptr;
   const long long stride = (long long)gridDim.x * m.ppb;
@@ -861,6 +892,16 @@ static int bn_bwd_onepass_t(const dc_bn_params& p, const dc_view& dout, const dc
                                                                                  pix_view<const T>(y), rws, pix_view<T>(dy), pix_view<T>(dres),
                                                                                  dgamma, dbeta, y.c, npix, om);
   return launch_status("dc_bn_bwd_onepass");
+}
+
+int bn_accumulate_sums(const dc_view& y, double* sums, cudaStream_t st) {
+  dc_bn_params p = {};
+  p.sums = sums;
+  p.count = (double)y.n * y.h * y.w;
+  p.flags = DC_BN_TRAIN | DC_BN_SUMS_READY;
+  const bool ok = view_ok(y) && y.sc == 1 && (y.dtype == DC_F32 ? vec_ok<float>(y) : vec_ok<__nv_bfloat16>(y));
+  if (!ok) return fail(-1, "bn_accumulate_sums: view must be channel-contiguous and 16-byte aligned");
+  return y.dtype == DC_F32 ? bn_stats_t<float>(p, y, st) : bn_stats_t<__nv_bfloat16>(p, y, st);
 }
 
 }  // namespace dc

@@ -136,6 +136,9 @@ static inline bool same_shape(const dc_view& a, const dc_view& b) {
   return a.n == b.n && a.h == b.h && a.w == b.w && a.c == b.c;
 }
 
+// bn.cu: sums[0][c] += sum of y[.., c], sums[1][c] += sum of squares (no finalize); used when a producer cannot do it itself
+int bn_accumulate_sums(const dc_view& y, double* sums, cudaStream_t st);
+
 // ---- warp / block reductions -------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -300,9 +300,12 @@ __device__ __forceinline__ void pack_job_elems(const dc_pack_job& j, int local_b
 //
 // (a) source [n][k][taps] -> destination [n][tap][k_pad] (fprop role of a 3x3 Conv2d, dgrad role of a ConvTranspose2d):
 //     a work item is one n and 256 consecutive k: 256*taps contiguous source floats in, `taps` runs of 256 elements out.
+// The tap count is a template parameter (1 and 9 cover the network; 0 = run-time value) so that the index arithmetic is
+// shifts and constant divisions: with run-time divisors the pack was ALU-bound (~100 instructions per element).
 constexpr int kPackMaxTaps = 9;
-template <typename TD>
+template <typename TD, int TAPS>
 __device__ __forceinline__ void pack_job_taps(const dc_pack_job& j, int local_block, int tid, float* sm) {
+  const int taps = TAPS ? TAPS : j.taps;
   const int kchunks = (j.K_pad + 255) >> 8;
   const int nitems = j.N_pad * kchunks;
   const float* __restrict__ src = j.src;
@@ -310,49 +313,95 @@ __device__ __forceinline__ void pack_job_taps(const dc_pack_job& j, int local_bl
   for (int it = local_block; it < nitems; it += j.n_blocks) {
     const int n = it / kchunks, k0 = (it - n * kchunks) << 8;
     const int kcount = min(256, j.K - k0);                         // valid k of this chunk (<= 0: pure padding)
-    const int nfl = (n < j.N && kcount > 0) ? kcount * j.taps : 0;
-    const float* sp = src + ((long long)n * j.K + k0) * j.taps;
+    const int nfl = (n < j.N && kcount > 0) ? kcount * taps : 0;
+    const float* sp = src + ((long long)n * j.K + k0) * taps;
     for (int e = tid; e < nfl; e += 256) sm[e] = sp[e];
     __syncthreads();
     const int kk = k0 + tid;
     if (kk < j.K_pad) {
-      for (int t = 0; t < j.taps; ++t) {
-        const float v = (tid * j.taps + t < nfl) ? sm[tid * j.taps + t] : 0.f;
-        elem<TD>::st(dst + ((long long)n * j.taps + t) * j.K_pad + kk, v);
+#pragma unroll
+      for (int t = 0; t < (TAPS ? TAPS : kPackMaxTaps); ++t) {
+        if (t >= taps) break;
+        const float v = (tid * taps + t < nfl) ? sm[tid * taps + t] : 0.f;
+        elem<TD>::st(dst + ((long long)n * taps + t) * j.K_pad + kk, v);
       }
     }
     __syncthreads();
   }
 }
 
+// (a') taps == 1, same role: a plain fp32 -> storage-type conversion of [n][k] rows into [n][k_pad] rows, four k per thread
+template <typename TD>
+__device__ __forceinline__ void pack_job_rows(const dc_pack_job& j, int local_block, int tid) {
+  const int kq = (j.K_pad + 3) >> 2;                     // quads per destination row (K_pad % 4 == 0 for NTK packs)
+  const int qchunks = (kq + 255) >> 8;
+  const int nitems = j.N_pad * qchunks;
+  const bool vec = (j.K % 4 == 0) && ((reinterpret_cast<uintptr_t>(j.src) & 15) == 0);
+  TD* __restrict__ dst = reinterpret_cast<TD*>(j.dst);
+  for (int it = local_block; it < nitems; it += j.n_blocks) {
+    const int n = it / qchunks, q = ((it - n * qchunks) << 8) + tid;
+    if (q >= kq) continue;
+    const int k = q << 2;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < j.N) {
+      const float* sp = j.src + (long long)n * j.K + k;
+      if (vec && k + 4 <= j.K) v = *reinterpret_cast<const float4*>(sp);
+      else {
+        if (k < j.K) v.x = sp[0];
+        if (k + 1 < j.K) v.y = sp[1];
+        if (k + 2 < j.K) v.z = sp[2];
+        if (k + 3 < j.K) v.w = sp[3];
+      }
+    }
+    elem<TD>::st4(dst + (long long)n * j.K_pad + k, v);
+  }
+}
+
 // (b) source [k][n][taps] -> destination [n][tap][k_pad] (dgrad role of a Conv2d, fprop role of a ConvTranspose2d): a work
 //     item is 64 k x TN n (TN*taps <= 72 floats per k row, contiguous in the source); the destination gets runs of 64 k.
-template <typename TD>
+template <typename TD, int TAPS>
 __device__ __forceinline__ void pack_job_transpose(const dc_pack_job& j, int local_block, int tid, float* sm) {
-  const int TN = j.taps == 1 ? 32 : (j.taps <= 2 ? 16 : 8);
-  const int RW = TN * j.taps;                    // floats per k row of the tile
+  const int taps = TAPS ? TAPS : j.taps;
+  const int TN = TAPS == 1 ? 32 : (TAPS == 9 ? 8 : (taps == 1 ? 32 : (taps <= 2 ? 16 : 8)));
+  const int RW = TN * taps;                      // floats per k row of the tile (32 / 72 when TAPS is 1 / 9)
   const int pitch = RW | 1;                      // odd pitch: conflict-free column reads
   const int kt = (j.K_pad + 63) >> 6, ntl = (j.N_pad + TN - 1) / TN;
   const int ntiles = kt * ntl;
   const float* __restrict__ src = j.src;
   TD* __restrict__ dst = reinterpret_cast<TD*>(j.dst);
   for (int tl = local_block; tl < ntiles; tl += j.n_blocks) {
-    const int k0 = (tl / ntl) << 6, n0 = (tl % ntl) * TN;
-    const int rw_valid = max(0, min(RW, (j.N - n0) * j.taps));
+    const int ktile = tl / ntl;
+    const int k0 = ktile << 6, n0 = (tl - ktile * ntl) * TN;
+    const int rw_valid = max(0, min(RW, (j.N - n0) * taps));
+    const float* sp = src + ((long long)k0 * j.N + n0) * taps;
+    const long long krow = (long long)j.N * taps;
     for (int e = tid; e < 64 * RW; e += 256) {
       const int k = e / RW, r = e - k * RW;
       float v = 0.f;
-      if (k0 + k < j.K && r < rw_valid) v = src[((long long)(k0 + k) * j.N + n0) * j.taps + r];
+      if (k0 + k < j.K && r < rw_valid) v = sp[k * krow + r];
       sm[k * pitch + r] = v;
     }
     __syncthreads();
     for (int e = tid; e < 64 * RW; e += 256) {
       const int kk = e & 63, row = e >> 6;      // row = n_local * taps + t
-      const int nl = row / j.taps, t = row - nl * j.taps;
+      const int nl = row / taps, t = row - nl * taps;
       if (n0 + nl < j.N_pad && k0 + kk < j.K_pad)
-        elem<TD>::st(dst + ((long long)(n0 + nl) * j.taps + t) * j.K_pad + k0 + kk, sm[kk * pitch + row]);
+        elem<TD>::st(dst + ((long long)(n0 + nl) * taps + t) * j.K_pad + k0 + kk, sm[kk * pitch + row]);
     }
     __syncthreads();
+  }
+}
+
+template <typename TD>
+__device__ __forceinline__ void pack_job_ntk(const dc_pack_job& j, int lb, int tid, float* sm) {
+  if (j.src_k_first) {
+    if (j.taps == 1) pack_job_transpose<TD, 1>(j, lb, tid, sm);
+    else if (j.taps == 9) pack_job_transpose<TD, 9>(j, lb, tid, sm);
+    else pack_job_transpose<TD, 0>(j, lb, tid, sm);
+  } else {
+    if (j.taps == 1) pack_job_rows<TD>(j, lb, tid);
+    else if (j.taps == 9) pack_job_taps<TD, 9>(j, lb, tid, sm);
+    else pack_job_taps<TD, 0>(j, lb, tid, sm);
   }
 }
 
@@ -367,17 +416,10 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const dc_pack_job* __re
   const dc_pack_job j = jobs[lo];
   __shared__ float sm[64 * 73];                 // 18.7 KB: 64 x (72 | 1) transpose tile, or 256 x 9 tap chunk
   const int lb = b - j.block_start;
-  if (j.layout == DC_PACK_NTK && j.taps <= kPackMaxTaps) {
-    if (j.src_k_first) {
-      if (j.dst_dtype == DC_F32) pack_job_transpose<float>(j, lb, threadIdx.x, sm);
-      else pack_job_transpose<__nv_bfloat16>(j, lb, threadIdx.x, sm);
-      return;
-    }
-    if (j.taps > 1) {
-      if (j.dst_dtype == DC_F32) pack_job_taps<float>(j, lb, threadIdx.x, sm);
-      else pack_job_taps<__nv_bfloat16>(j, lb, threadIdx.x, sm);
-      return;
-    }
+  if (j.layout == DC_PACK_NTK && j.taps <= kPackMaxTaps && (j.K_pad & 3) == 0) {
+    if (j.dst_dtype == DC_F32) pack_job_ntk<float>(j, lb, threadIdx.x, sm);
+    else pack_job_ntk<__nv_bfloat16>(j, lb, threadIdx.x, sm);
+    return;
   }
   if (j.dst_dtype == DC_F32) pack_job_elems<float>(j, lb, threadIdx.x);
   else pack_job_elems<__nv_bfloat16>(j, lb, threadIdx.x);

@@ -169,6 +169,8 @@ struct TcFpropParams {
   int out_vec_ok;      // output rows are 16-byte aligned bf16 with unit channel stride
   const float* bias;
   TcOut out;
+  double* stats;       // BatchNorm workspace sums[2][stats_C] of the layer that normalises `out` (or null): the epilogue adds the
+  int stats_C;         // per-channel sum and sum of squares of the bf16-rounded outputs it stores (TMA-store path only)
 };
 
 constexpr int kTcThreads = 192;
@@ -610,6 +612,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
                 w0 = *reinterpret_cast<uint32_t*>(&b0); w1 = *reinterpret_cast<uint32_t*>(&b1);
                 w2 = *reinterpret_cast<uint32_t*>(&b2); w3 = *reinterpret_cast<uint32_t*>(&b3);
               }
+              if (p.stats != nullptr && !pix_ok) { w0 = 0; w1 = 0; w2 = 0; w3 = 0; }   // clipped by the store; must not count
               const uint32_t j16 = (uint32_t)(4 * h + q);
               const uint32_t dst = sbuf + ((j16 ^ ((uint32_t)row & 7u)) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
@@ -622,6 +625,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
             if (p.accumulate) tma_reduce_add_4d(&maps.c, src, n0 + c0, tile_x * p.TW, tile_y * p.TH, img);
             else tma_store_4d(&maps.c, src, n0 + c0, tile_x * p.TW, tile_y * p.TH, img);
             tma_store_commit();
+          }
+          if (p.stats != nullptr) {
+            // ---- BatchNorm statistics of this 128 x 64 chunk, from the staged (bf16-rounded) values: warp = 32 rows, lane =
+            //      one column pair (conflict-free 4-byte reads of the swizzled rows); the four row groups are combined through
+            //      2 KB of shared memory and every thread issues ONE fp64 atomic (64 columns x {sum, sum of squares}) ----
+            const uint32_t sb = stg_s + (uint32_t)(chunk_ctr & 1) * 16384u;
+            const uint32_t cj16 = (uint32_t)lane >> 2, coff = ((uint32_t)lane & 3u) * 4u;
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const uint32_t rr = (uint32_t)(lg * 32 + r);
+              uint32_t wv;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(sb + rr * 128u + ((cj16 ^ (rr & 7u)) << 4) + coff));
+              const float a = __uint_as_float(wv << 16), b = __uint_as_float(wv & 0xffff0000u);
+              s0 += a; s1 += b;
+              q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
+            }
+            float* sred = reinterpret_cast<float*>(smem_gen + stg_off + 32768);      // [4 row groups][sum 64 | sumsq 64]
+            sred[lg * 128 + 2 * lane] = s0; sred[lg * 128 + 2 * lane + 1] = s1;
+            sred[lg * 128 + 64 + 2 * lane] = q0; sred[lg * 128 + 64 + 2 * lane + 1] = q1;
+            epi_bar_sync();
+            const int t = (int)threadIdx.x - 64;                 // 0..127: statistic (t >> 6), column (t & 63)
+            const float tot = sred[t] + sred[128 + t] + sred[256 + t] + sred[384 + t];
+            const int col = c0 + (t & 63);
+            if (col < ncols) atomicAdd(p.stats + (size_t)(t >> 6) * p.stats_C + n0 + col, (double)tot);
           }
         }
         continue;
@@ -1113,7 +1141,9 @@ using namespace dc;
 
 extern "C" {
 
-int dc_conv_gemm_tc(const dc_conv_desc* d, dc_view in, const void* w, const float* bias, dc_view out, void* stream) {
+// stats != null: *stats_done tells the caller whether the epilogue accumulated the BatchNorm sums (TMA-store path)
+static int conv_gemm_tc_impl(const dc_conv_desc* d, dc_view in, const void* w, const float* bias, dc_view out, double* stats,
+                             bool* stats_done, void* stream) {
   DC_REQUIRE(d != nullptr && d->ntaps >= 1 && d->ntaps <= DC_MAX_TAPS, "dc_conv_gemm_tc: bad descriptor");
   DC_REQUIRE(tc_view_ok(in), "dc_conv_gemm_tc: input must be bf16, channel-contiguous, C %% 8 == 0, 16-byte aligned strides");
   DC_REQUIRE(view_ok(out) && out.n == in.n, "dc_conv_gemm_tc: bad output view");
@@ -1132,6 +1162,9 @@ int dc_conv_gemm_tc(const dc_conv_desc* d, dc_view in, const void* w, const floa
   p.out.sn = out.sn; p.out.sh = out.sh; p.out.sw = out.sw; p.out.sc = out.sc; p.out.dtype = out.dtype;
   p.out_vec_ok = (out.dtype == DC_BF16 && out.sc == 1 && out.sw % 8 == 0 && out.sh % 8 == 0 && out.sn % 8 == 0 &&
                   (reinterpret_cast<uintptr_t>(out.ptr) % 16) == 0) ? 1 : 0;
+  p.stats = nullptr;
+  p.stats_C = out.c;
+  if (stats_done) *stats_done = false;
   if (int r = build_gather("dc_conv_gemm_tc", d, in, p.TH, p.TW, maps, p)) return r;
   const long long Ktot = (long long)d->wtaps * p.kblocks * 64;
   const int mtiles = p.tiles_x * p.tiles_y * out.n;
@@ -1142,12 +1175,30 @@ int dc_conv_gemm_tc(const dc_conv_desc* d, dc_view in, const void* w, const floa
     if (tma_store) {
       if (int r = encode_act_map(&maps.c, out.ptr, out.c, out.w, out.h, out.n, out.sw, out.sh, out.sn, p.TW, p.TH, "dc_conv_gemm_tc(out)"))
         return r;
+      if (stats != nullptr && !d->accumulate) {
+        p.stats = stats;
+        *stats_done = true;
+      }
     }
     return launch_fprop_v2(maps, p, c2, as_stream(stream));
   }
   const TcFpropCfg cfg = pick_fprop_cfg(mtiles, out.c);
   if (int r = encode_weight_map(&maps.b, w, Ktot, out.c, cfg.BN, "dc_conv_gemm_tc")) return r;
   return launch_fprop(maps, p, cfg, mtiles, ceil_div(out.c, cfg.BN), as_stream(stream));
+}
+
+int dc_conv_gemm_tc(const dc_conv_desc* d, dc_view in, const void* w, const float* bias, dc_view out, void* stream) {
+  return conv_gemm_tc_impl(d, in, w, bias, out, nullptr, nullptr, stream);
+}
+
+int dc_conv_gemm_tc_bnstats(const dc_conv_desc* d, dc_view in, const void* w, const float* bias, dc_view out, double* sums,
+                            void* stream) {
+  DC_REQUIRE(sums != nullptr, "dc_conv_gemm_tc_bnstats: null statistics workspace");
+  DC_REQUIRE(d != nullptr && !d->accumulate, "dc_conv_gemm_tc_bnstats: statistics of an accumulating contraction are undefined");
+  bool done = false;
+  if (int r = conv_gemm_tc_impl(d, in, w, bias, out, sums, &done, stream)) return r;
+  if (done) return 0;
+  return dc::bn_accumulate_sums(out, sums, as_stream(stream));     // output layout without the TMA-store epilogue: one extra pass
 }
 
 int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, void* stream) {

@@ -12,7 +12,7 @@ from . import build as _build
 DC_F32, DC_BF16 = 0, 1
 DC_MAX_TAPS = 9
 DC_PACK_TKN, DC_PACK_NTK = 0, 1
-DC_BN_RELU, DC_BN_TRAIN, DC_BN_IDENTITY, DC_BN_RES_WRITE = 1, 2, 4, 8
+DC_BN_RELU, DC_BN_TRAIN, DC_BN_IDENTITY, DC_BN_RES_WRITE, DC_BN_SUMS_READY = 1, 2, 4, 8, 16
 
 
 class dc_view(Structure):
@@ -60,6 +60,7 @@ SIGNATURES = {
     "dc_conv_gemm_simt": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p]),
     "dc_conv_wgrad_simt": (c_int, [POINTER(dc_conv_desc), dc_view, dc_view, c_void_p, c_void_p]),
     "dc_conv_gemm_tc": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p]),
+    "dc_conv_gemm_tc_bnstats": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p, c_void_p]),
     "dc_conv_wgrad_tc": (c_int, [POINTER(dc_conv_desc), dc_view, dc_view, c_void_p, c_void_p]),
     "dc_dw_fwd": (c_int, [dc_view, c_void_p, c_int, c_int, dc_view, c_void_p]),
     "dc_dw_bwd_data": (c_int, [dc_view, c_void_p, c_int, c_int, dc_view, c_int, c_void_p]),

@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import convdesc, ops
-from ._lib import DC_BN_IDENTITY, DC_BN_RELU, DC_BN_RES_WRITE, DC_BN_TRAIN, DC_PACK_NTK, DC_PACK_TKN
+from ._lib import DC_BN_IDENTITY, DC_BN_RELU, DC_BN_RES_WRITE, DC_BN_SUMS_READY, DC_BN_TRAIN, DC_PACK_NTK, DC_PACK_TKN
 
 
 def _round_up(a, b):
@@ -116,6 +116,8 @@ class CudaBackend:
         # backward variant is switched off by the data-parallel wrapper: NCCL kernels share the SMs during backward.
         self.onepass = os.environ.get("DEEPCAM_B200_BN_ONEPASS", "1") not in ("0", "false", "")
         self.onepass_bwd = True
+        # BatchNorm batch sums out of the producing GEMM's epilogue (dc_conv_gemm_tc_bnstats): no statistics pass at all
+        self.fuse_bn_stats = os.environ.get("DEEPCAM_B200_FUSE_BN_STATS", "1") not in ("0", "false", "")
         self.side_stream = None       # set by a graph plan: weight-gradient kernels run on a parallel graph branch
         self._side_dirty = False
 
@@ -241,27 +243,33 @@ class CudaBackend:
         return _cached(spec, (role, impl, dt, K_pad, N_pad), w, (K, N, taps, src_k_first, layout, K_pad, N_pad, dt),
                        frozen=self.graph_mode)
 
-    def _gemm(self, taps, stride, accumulate, wtaps, x, w, bias, out, impl):
+    def _gemm(self, taps, stride, accumulate, wtaps, x, w, bias, out, impl, bn_sums=None):
         desc = ops.make_desc(taps, (stride, stride), accumulate, wtaps)
-        ops.conv_gemm(desc, x, w, bias, out, impl)
+        ops.conv_gemm(desc, x, w, bias, out, impl, bn_sums)
         self.launches += 1
 
     # ---- dense convolution ---------------------------------------------------------------------------------
-    def conv_fwd(self, x, spec, out):
-        """out <- conv(x) (+ bias).  `out` is a preallocated logical-NHWC tensor (possibly a channel slice)."""
+    def conv_fwd(self, x, spec, out, want_bn_sums=False):
+        """out <- conv(x) (+ bias).  `out` is a preallocated logical-NHWC tensor (possibly a channel slice).
+        want_bn_sums: the caller will batch-normalise `out` in training mode; when the tcgen05 kernel runs, its epilogue
+        also accumulates the per-channel batch sums and the (zeroed) BatchNorm workspace holding them is returned
+        (pass it to bn_fwd as `ready_sums`); otherwise None is returned and bn_fwd computes the statistics itself."""
         impl = "tc" if self._tc_ok(x, spec.co) else "simt"
         w = self._packed(spec, "fprop", impl, x, n_pad=out.shape[3])
         bias = spec.bias.detach() if spec.bias is not None else None
         kk = spec.k * spec.k
+        sums = None
+        if want_bn_sums and impl == "tc" and self.fuse_bn_stats and out.dtype == torch.bfloat16:
+            sums = self.scratch(ops.bn_ws_elems(out.shape[3]), torch.float64, zero=True)
         if not spec.transposed:
-            self._gemm(convdesc.conv_fprop_taps(spec.k, spec.pad, spec.dil), spec.stride, False, kk, x, w, bias, out, impl)
+            self._gemm(convdesc.conv_fprop_taps(spec.k, spec.pad, spec.dil), spec.stride, False, kk, x, w, bias, out, impl, sums)
         else:
             s = spec.stride
             for ph in range(s):
                 for pw in range(s):
                     taps = convdesc.convT_fprop_taps(spec.k, s, spec.pad, ph, pw)
-                    self._gemm(taps, 1, False, kk, x, w, bias, out[:, ph::s, pw::s, :], impl)
-        return out
+                    self._gemm(taps, 1, False, kk, x, w, bias, out[:, ph::s, pw::s, :], impl, sums)
+        return sums
 
     def conv_bwd_data(self, dy, spec, dx, accumulate):
         """dx (+)= conv^T(dy)."""
@@ -349,8 +357,9 @@ class CudaBackend:
         return wgrad
 
     # ---- batch norm (+relu, +residual) ------------------------------------------------------------------------------
-    def bn_fwd(self, y, spec, relu, residual, out, training):
-        """out <- [relu](bn(y) [+ residual]).  spec None = identity (pure relu / add).  Returns the saved statistics."""
+    def bn_fwd(self, y, spec, relu, residual, out, training, ready_sums=None):
+        """out <- [relu](bn(y) [+ residual]).  spec None = identity (pure relu / add).  Returns the saved statistics.
+        ready_sums: workspace returned by conv_fwd(want_bn_sums=True) for the same y (batch sums already accumulated)."""
         flags = DC_BN_RELU if relu else 0
         n, h, w, c = y.shape
         if spec is None:
@@ -366,10 +375,18 @@ class CudaBackend:
             if n * h * w <= 1:
                 raise ValueError("Expected more than 1 value per channel when training, got input size %s"
                                  % (torch.Size((n, c, h, w)),))
-            sums = self.scratch(ops.bn_ws_elems(c), torch.float64, zero=True)        # per-layer BatchNorm workspace
             flags |= DC_BN_TRAIN
+            if ready_sums is not None:
+                sums = ready_sums
+                flags |= DC_BN_SUMS_READY
+            else:
+                sums = self.scratch(ops.bn_ws_elems(c), torch.float64, zero=True)    # per-layer BatchNorm workspace
         p = ops.bn_params(m.weight.detach(), m.bias.detach(), m.running_mean if track else None,
                           m.running_var if track else None, sums, n * h * w, mom, m.eps, flags)
+        if training and ready_sums is not None:
+            ops.bn_apply(p, y, residual, out)      # finalizes the sums itself (coefficients, running statistics), then applies
+            self.launches += 1
+            return sums
         if training and self.onepass and ops.bn_onepass_ok(c, n * h * w, y.dtype, False):
             ops.bn_fwd_onepass(p, y, residual, out)     # statistics + normalisation in one launch (tensor held on chip)
             self.launches += 1

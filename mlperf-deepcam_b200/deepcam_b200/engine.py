@@ -46,10 +46,11 @@ def _make_backend(precision, device):
 
 class Act:
     """Channels-last activation: tensor [N,H,W,C] (possibly a channel slice of a concat buffer) + its gradient."""
-    __slots__ = ("t", "_grad", "is_relu", "needs_grad", "parent", "c_off")
+    __slots__ = ("t", "_grad", "is_relu", "needs_grad", "parent", "c_off", "bn_sums")
 
     def __init__(self, t, is_relu=False, needs_grad=True, parent=None, c_off=0):
         self.t = t
+        self.bn_sums = None       # (BatchNorm module, workspace) when the producing conv already accumulated the batch sums
         self._grad = None
         self.is_relu = is_relu
         self.needs_grad = needs_grad
@@ -163,14 +164,20 @@ class Engine:
         return act.grad, False
 
     # ---- operations -------------------------------------------------------------------------------------
-    def conv(self, x, spec, out=None, out_c=None, out_dtype=None):
+    def conv(self, x, spec, out=None, out_c=None, out_dtype=None, bn=None):
+        """bn: the BnSpec that will normalise the result next (Engine.bn on the returned Act): in training mode the
+        convolution kernel then also produces the batch sums, see CudaBackend.conv_fwd."""
         n, h, w, _ = x.shape
         ho, wo = spec.out_hw(h, w)
         if out is None:
             out = self.new_act(n, ho, wo, out_c or spec.co, out_dtype or x.t.dtype)
         elif out.shape[:3] != (n, ho, wo):
             raise RuntimeError("conv %s: output buffer %s does not match %s" % (spec.name, out.shape, (n, ho, wo)))
-        self.be.conv_fwd(x.t, spec, out.t)
+        want = bn is not None and (bool(bn.module.training) or bn.module.running_mean is None)
+        if want:
+            out.bn_sums = (bn.module, self.be.conv_fwd(x.t, spec, out.t, want_bn_sums=True))
+        else:
+            self.be.conv_fwd(x.t, spec, out.t)
         if self.record:
             self.tape.append(lambda: self._conv_bwd(x, out, spec))
         return out
@@ -223,7 +230,15 @@ class Engine:
         training = bool(spec.module.training) if spec is not None else False
         if spec is not None and not training and spec.module.running_mean is None:
             training = True          # track_running_stats=False always uses batch statistics
-        sums = self.be.bn_fwd(y.t, spec, relu, residual.t if residual is not None else None, out.t, training)
+        ready = None
+        pre = getattr(y, "bn_sums", None)
+        if pre is not None and spec is not None and training and pre[0] is spec.module and pre[1] is not None:
+            ready = pre[1]
+            y.bn_sums = None
+        if ready is not None:
+            sums = self.be.bn_fwd(y.t, spec, relu, residual.t if residual is not None else None, out.t, training, ready_sums=ready)
+        else:
+            sums = self.be.bn_fwd(y.t, spec, relu, residual.t if residual is not None else None, out.t, training)
         if spec is not None and training and spec.module.num_batches_tracked is not None:
             self.bn_trained.append(spec.module)
         if self.record:
@@ -373,6 +388,35 @@ def graphs_enabled():
     return os.environ.get("DEEPCAM_B200_GRAPHS", "1") not in ("0", "false", "False", "")
 
 
+class _capture:
+    """torch.cuda.graph with the cyclic garbage collector paused: a collection that happens to run in the middle of a
+    capture can finalize an older plan (CUDA graphs + their private memory pool -> cudaFree), which is not permitted on a
+    capturing thread and invalidates the capture (seen as 'operation failed due to a previous error during capture')."""
+
+    def __init__(self, graph, pool):
+        self.ctx = torch.cuda.graph(graph, pool=pool, capture_error_mode="thread_local")
+
+    def __enter__(self):
+        import gc
+        self.gc_was_enabled = gc.isenabled()
+        gc.collect()
+        gc.disable()
+        try:
+            return self.ctx.__enter__()
+        except BaseException:
+            if self.gc_was_enabled:
+                gc.enable()
+            raise
+
+    def __exit__(self, *exc):
+        import gc
+        try:
+            return self.ctx.__exit__(*exc)
+        finally:
+            if self.gc_was_enabled:
+                gc.enable()
+
+
 class _GraphPlan:
     """Static buffers + captured graphs of one (module, input shapes, mode) configuration.
 
@@ -428,7 +472,7 @@ class _GraphPlan:
             g = torch.cuda.CUDAGraph()
             l0 = self._lib.launch_count
             self.be.begin_arena(_FWD_ARENA_BYTES)
-            with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
+            with _capture(g, self.pool):
                 if self.pack_table is not None:
                     ops.pack_weights_multi(*self.pack_table)     # one launch re-packs every weight each step
                 self.outs = self.module._emit_root(self.eng, *self.xin)
@@ -479,7 +523,7 @@ class _GraphPlan:
                 g = torch.cuda.CUDAGraph()
                 if sync is not None:
                     sync.deferred = []
-                with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
+                with _capture(g, self.pool):
                     if i == 0:
                         be.fill_zero_flat(grads.flat)
                     while i < len(tape):

@@ -205,16 +205,23 @@ def unpack_wgrad(G, K, N, taps, dst_k_first, dst, k_stride=None):
 
 
 # ---- dense contractions -----------------------------------------------------------------------------
-def conv_gemm(desc, x, w, bias, out, impl):
+def conv_gemm(desc, x, w, bias, out, impl, bn_sums=None):
+    """bn_sums (tcgen05 path only): zeroed BatchNorm workspace; the GEMM epilogue adds the batch sums of `out` to it."""
     _require_cuda(x, w, out)
     lib = _lib.load()
-    fn = lib.dc_conv_gemm_tc if impl == "tc" else lib.dc_conv_gemm_simt
     m = out.shape[0] * out.shape[1] * out.shape[2]
     flops = 2.0 * m * out.shape[3] * x.shape[3] * desc.ntaps
     nbytes = _nbytes(x, out) + desc.ntaps * x.shape[3] * out.shape[3] * x.element_size()
+    tag = "M%d Ci%d Co%d taps%d s%d" % (m, x.shape[3], out.shape[3], desc.ntaps, desc.stride_h)
+    if bn_sums is not None:
+        assert impl == "tc" and bn_sums.dtype == torch.float64 and bn_sums.numel() >= bn_ws_elems(out.shape[3])
+        _timed("conv_gemm_tc", flops, nbytes,
+               lambda: lib.dc_conv_gemm_tc_bnstats(ctypes.byref(desc), view(x), _p(w), _p(bias), view(out), _p(bn_sums), _stream()),
+               "dc_conv_gemm_tc_bnstats", tag=tag + " +bnstats")
+        return out
+    fn = lib.dc_conv_gemm_tc if impl == "tc" else lib.dc_conv_gemm_simt
     _timed("conv_gemm_" + impl, flops, nbytes,
-           lambda: fn(ctypes.byref(desc), view(x), _p(w), _p(bias), view(out), _stream()), "dc_conv_gemm_" + impl,
-           tag="M%d Ci%d Co%d taps%d s%d" % (m, x.shape[3], out.shape[3], desc.ntaps, desc.stride_h))
+           lambda: fn(ctypes.byref(desc), view(x), _p(w), _p(bias), view(out), _stream()), "dc_conv_gemm_" + impl, tag=tag)
     return out
 
 

@@ -467,3 +467,66 @@ def test_multi_pack_matches_definition(dst_dtype):
         assert torch.equal(job[1], ref), job[2:]
         single = ops.pack_weight(job[0], *job[2:], dst_dtype)
         assert torch.equal(single, ref), job[2:]
+
+
+@pytest.mark.parametrize("case", [
+    # name, Ci, Co, k, stride, pad, dil, H, W, transposed, slice
+    ("pw728_mid", 728, 728, 1, 1, 0, 1, 48, 72, False, False),
+    ("pw_ragged_tiles", 128, 48, 1, 1, 0, 1, 19, 27, False, False),
+    ("dec3x3_304", 304, 256, 3, 1, 1, 1, 17, 23, False, False),
+    ("aspp_d6_slice", 256, 256, 3, 1, 6, 6, 16, 24, False, True),
+    ("skip_s2", 128, 256, 1, 2, 0, 1, 24, 40, False, False),
+    ("deconv", 256, 256, 3, 2, 1, 1, 12, 18, True, True),
+], ids=lambda c: c[0])
+def test_conv_tcgen05_bn_sums_and_fused_batchnorm(case):
+    """dc_conv_gemm_tc_bnstats: the batch sums that come out of the GEMM epilogue equal the sums of the tensor that was
+    stored (bf16-rounded values), and BatchNorm on top of them (DC_BN_SUMS_READY) matches the stand-alone statistics
+    path: output, saved coefficients and running statistics."""
+    from deepcam_b200 import ops
+    from deepcam_b200.backend import BnSpec, ConvSpec
+    name, Ci, Co, k, stride, pad, dil, H, W, transposed, use_slice = case
+    torch.manual_seed(12)
+    be = backend(torch.bfloat16, use_tc=True)
+    N = 2
+    if transposed:
+        mod = torch.nn.ConvTranspose2d(Ci, Co, k, stride=stride, padding=pad, output_padding=1, bias=False).to(dev())
+    else:
+        mod = torch.nn.Conv2d(Ci, Co, k, stride=stride, padding=pad, dilation=dil, bias=False).to(dev())
+    spec = ConvSpec("c", mod.weight, None, stride, pad, dil, transposed)
+    Ho, Wo = spec.out_hw(H, W)
+    x = (torch.randn(N, H, W, Ci, device=dev()) + 0.3).bfloat16()
+    buf = torch.zeros(N, Ho, Wo, Co + 512 if use_slice else Co, dtype=torch.bfloat16, device=dev())
+    out = buf[..., 256:256 + Co] if use_slice else buf
+    sums = be.conv_fwd(x, spec, out, want_bn_sums=True)
+    assert sums is not None
+    torch.cuda.synchronize()
+    o64 = out.double().reshape(-1, Co)
+    ref_s, ref_q = o64.sum(0), (o64 * o64).sum(0)
+    got = sums[:2 * Co].reshape(2, Co)
+    assert float((got[0] - ref_s).abs().max()) <= 1e-5 * float(ref_s.abs().max() + o64.abs().sum(0).max())
+    assert rel(got[1], ref_q) < 1e-6
+    # BatchNorm (+ReLU) on the fused sums vs the stand-alone path on the same tensor
+    bn_a = torch.nn.BatchNorm2d(Co).to(dev())
+    bn_b = torch.nn.BatchNorm2d(Co).to(dev())
+    with torch.no_grad():
+        bn_a.weight.uniform_(0.5, 1.5)
+        bn_a.bias.uniform_(-0.5, 0.5)
+    bn_b.load_state_dict(bn_a.state_dict())
+    ya = be.empty(N, Ho, Wo, Co)
+    yb = be.empty(N, Ho, Wo, Co)
+    sa = be.bn_fwd(out, BnSpec("a", bn_a), True, None, ya, training=True, ready_sums=sums)
+    sb = be.bn_fwd(out, BnSpec("b", bn_b), True, None, yb, training=True)
+    torch.cuda.synchronize()
+    assert rel(ya, yb) < 1e-3                      # bf16 outputs: an ulp flips where the fp32 coefficients differ in the last bit
+    assert rel(bn_a.running_mean, bn_b.running_mean) < 1e-5 and rel(bn_a.running_var, bn_b.running_var) < 1e-5
+    ca = sa.view(torch.float32)[4 * Co:8 * Co]      # coef[4][C] follows sums[2][C] (doubles) in the workspace
+    cb = sb.view(torch.float32)[4 * Co:8 * Co]
+    assert rel(ca, cb) < 1e-5
+    # backward through the fused-statistics forward uses the stored coefficients
+    dout = torch.randn(N, Ho, Wo, Co, device=dev()).bfloat16()
+    dya, dyb = be.empty(N, Ho, Wo, Co), be.empty(N, Ho, Wo, Co)
+    ga, gb = (torch.empty(Co, device=dev()) for _ in range(2))
+    ba, bb = (torch.empty(Co, device=dev()) for _ in range(2))
+    be.bn_bwd(dout, ya, out, BnSpec("a", bn_a), sa, True, dya, None, False, ga, ba)
+    be.bn_bwd(dout, yb, out, BnSpec("b", bn_b), sb, True, dyb, None, False, gb, bb)
+    assert rel(dya, dyb) < 2e-3 and rel(ga, gb) < 1e-3 and rel(ba, bb) < 1e-3

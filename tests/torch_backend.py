@@ -53,7 +53,7 @@ class TorchBackend:
     def _f(self, t):
         return _nchw(t).double()
 
-    def conv_fwd(self, x, spec, out):
+    def conv_fwd(self, x, spec, out, want_bn_sums=False):      # returns None: no fused statistics in the interpreter
         w = spec.weight.detach().double()
         b = spec.bias.detach().double() if spec.bias is not None else None
         if spec.transposed:
@@ -65,7 +65,7 @@ class TorchBackend:
         if out.shape[3] > co:
             out[..., co:] = 0
         self.log.append(("conv_fwd", spec.name))
-        return out
+        return None if want_bn_sums else out
 
     def conv_bwd_data(self, dy, spec, dx, accumulate):
         w = spec.weight.detach().double()
@@ -126,7 +126,7 @@ class TorchBackend:
         return wgrad
 
     # ---- batch norm ----
-    def bn_fwd(self, y, spec, relu, residual, out, training):
+    def bn_fwd(self, y, spec, relu, residual, out, training, ready_sums=None):
         v = y.double()
         saved = None
         if spec is not None:
