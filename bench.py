@@ -261,12 +261,39 @@ def run_ours(args):
         xb.record_stream(cur)
         lb.record_stream(cur)
         stage()                                       # exactly one batch is copied per step
-        last["loss"] = step(xb, lb).item()            # device -> host read of the step's result
+        loss = step(xb, lb)
+        # device -> host read of the step's result, every step: the scalar is copied into pinned memory right behind the
+        # step's kernels and the host consumes it one step later (asynchronous logging), so the device never idles while
+        # Python enqueues the next step; --e2e-sync-loss reads it with .item() instead (the device then waits for the host)
+        if args.e2e_sync_loss:
+            last["loss"] = loss.item()
+            return
+        slot = loss_slots[e2e_state["i"] & 1]
+        slot[0].copy_(loss.detach().reshape(1), non_blocking=True)
+        slot[1].record()
+        e2e_state["i"] += 1
+        prev = loss_slots[e2e_state["i"] & 1]
+        if e2e_state["i"] > 1:
+            prev[1].synchronize()
+            last["loss"] = float(prev[0][0])
 
+    def e2e_drain():
+        if not args.e2e_sync_loss and e2e_state["i"] > 0:
+            cur = loss_slots[(e2e_state["i"] - 1) & 1]
+            cur[1].synchronize()
+            last["loss"] = float(cur[0][0])
+
+    loss_slots = [(torch.zeros(1, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(2)]
+    e2e_state = {"i": 0}
     stage()
     for _ in range(2):
         e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+
+    def e2e_run():
+        e2e_step()
+
+    ms_e2e = timed(e2e_run, args.steps)            # timed() synchronises the device on both sides
+    e2e_drain()
     e2e_value = world * LOCAL_BATCH * args.steps / (ms_e2e / 1000.0)
     h2d = x_host.numel() * 4 + label_host.numel() * 8
 
@@ -344,7 +371,9 @@ def run_ours(args):
                                 parallelism="dp%d" % world,
                                 l2="per-step working set (>7 GB of activations) exceeds the 126 MB L2; no explicit flush"),
                     e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
-                             ms_per_step=ms_e2e / args.steps, loss=last.get("loss")),
+                             ms_per_step=ms_e2e / args.steps, loss=last.get("loss"),
+                             loss_readback=".item() every step" if args.e2e_sync_loss else
+                             "4-byte copy into pinned memory every step, consumed by the host one step later"),
                     gpu_launches=launches, clocks=clocks,
                     tensor_frac_of_step=(FWD_BWD_GFLOP_PER_SAMPLE * value / 1000.0) / peaks["tf_sustained"],
                     roofline=roofline, cpu_baseline=cpu_base)
@@ -361,6 +390,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--e2e-sync-loss", action="store_true", help="e2e leg: read the loss with .item() every step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

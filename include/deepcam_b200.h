@@ -149,9 +149,11 @@ enum {
   DC_BN_TRAIN      = 2,   /* batch statistics from the workspace `sums` */
   DC_BN_IDENTITY   = 4,   /* skip normalisation (pure relu / add) */
   DC_BN_RES_WRITE  = 8,   /* backward: residual gradient is written, not accumulated */
-  DC_BN_SUMS_READY = 16   /* forward apply, train mode: the workspace holds the raw batch sums (left there by
+  DC_BN_SUMS_READY = 16,  /* forward apply, train mode: the workspace holds the raw batch sums (left there by
                              dc_conv_gemm_tc_bnstats); dc_bn_apply derives the coefficients itself, stores them for the
                              backward pass and updates the running statistics: no dc_bn_stats launch */
+  DC_BN_MASK_FROM_Y = 32  /* backward, train mode, no residual: the ReLU mask (out > 0) is recomputed from y and the forward
+                             coefficients kept in the forward workspace; `out` is not read and may be a null view */
 };
 typedef struct dc_bn_params {
   const float* gamma;  const float* beta;      /* [C] */

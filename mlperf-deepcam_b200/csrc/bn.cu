@@ -286,8 +286,8 @@ __device__ __forceinline__ void load_fwd_coef(const dc_bn_params& p, int C, int 
   }
 }
 
-template <typename T, int V, int kUnroll>
-__global__ void __launch_bounds__(kBnThreads, 2) bn_apply_kernel(dc_bn_params p, PixView<const T> y, PixView<const T> res, PixView<T> out,
+template <typename T, int V, int kUnroll, bool HAS_RES>
+__global__ void __launch_bounds__(kBnThreads, 3) bn_apply_kernel(dc_bn_params p, PixView<const T> y, PixView<const T> res, PixView<T> out,
                                                               int C, long long npix, LaneMap m) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   pdl_sync();
@@ -298,23 +298,23 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_apply_kernel(dc_bn_params p,
   float scale[V], shift[V], mean[V], invstd[V];
   load_fwd_coef<V>(p, C, c0, scale, shift, mean, invstd, blockIdx.x == 0 && warp == 0 && psub == 0);
   const bool relu = (p.flags & DC_BN_RELU) != 0;
-  const bool has_res = res.p != nullptr;
+  constexpr bool has_res = HAS_RES;
   const long long stride = (long long)gridDim.x * m.ppb;
   long long pix = (long long)blockIdx.x * m.ppb + warp * m.ppw + psub;
   for (; pix < npix; pix += kUnroll * stride) {
-    uint4 vraw[kUnroll], rraw[kUnroll];
+    uint4 vraw[kUnroll], rraw[HAS_RES ? kUnroll : 1];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u)
       if (pix + u * stride < npix) {
         vraw[u] = vec16<T>::ldraw(y.at(pix + u * stride) + c0);
-        if (has_res) rraw[u] = vec16<T>::ldraw(res.at(pix + u * stride) + c0);
+        if (has_res) rraw[HAS_RES ? u : 0] = vec16<T>::ldraw(res.at(pix + u * stride) + c0);
       }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u)
       if (pix + u * stride < npix) {
         float v[V], r[V], o[V];
         vec16<T>::unpack(vraw[u], v);
-        if (has_res) vec16<T>::unpack(rraw[u], r);
+        if (has_res) vec16<T>::unpack(rraw[HAS_RES ? u : 0], r);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
           o[j] = fmaf(v[j], scale[j], shift[j]);
@@ -337,6 +337,16 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(dc_bn_params 
   const bool ok = cvi < m.cv;
   const int c0 = cvi * V;
   const bool relu = (p.flags & DC_BN_RELU) != 0;
+  // DC_BN_MASK_FROM_Y: out = relu(fma(y, scale, shift)) with the forward coefficients still in the forward workspace, so
+  // the ReLU decision is recomputed from y (identical) and `out` is not read: one input stream less
+  const bool mask_y = relu && (p.flags & DC_BN_MASK_FROM_Y) != 0;
+  const bool load_out = relu && !mask_y;
+  float fsc[V], fsh[V];
+  if (mask_y && ok) {
+    const BnWs fws = bn_ws(const_cast<double*>(p.sums), C);
+#pragma unroll
+    for (int j = 0; j < V; ++j) { fsc[j] = fws.coef[c0 + j]; fsh[j] = fws.coef[C + c0 + j]; }
+  }
   float acc[2][V];
 #pragma unroll
   for (int j = 0; j < V; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
@@ -349,7 +359,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(dc_bn_params 
       for (int u = 0; u < kUnroll; ++u)
         if (pix + u * stride < npix) {
           graw[u] = vec16<T>::ldraw(dout.at(pix + u * stride) + c0);
-          if (relu) oraw[u] = vec16<T>::ldraw(out.at(pix + u * stride) + c0);
+          if (load_out) oraw[u] = vec16<T>::ldraw(out.at(pix + u * stride) + c0);
           vraw[u] = vec16<T>::ldraw(y.at(pix + u * stride) + c0);
         }
 #pragma unroll
@@ -357,8 +367,12 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(dc_bn_params 
         if (pix + u * stride < npix) {
           float g[V], o[V], v[V];
           vec16<T>::unpack(graw[u], g);
-          if (relu) vec16<T>::unpack(oraw[u], o);
           vec16<T>::unpack(vraw[u], v);
+          if (load_out) vec16<T>::unpack(oraw[u], o);
+          else if (mask_y) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) o[j] = fmaf(v[j], fsc[j], fsh[j]);
+          }
 #pragma unroll
           for (int j = 0; j < V; ++j) {
             float gg = g[j];
@@ -402,7 +416,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(dc_bn_params 
   }
 }
 
-template <typename T, int V, int kUnroll>
+template <typename T, int V, int kUnroll, bool MASK_Y>
 __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_apply_kernel(dc_bn_params p, PixView<const T> dout, PixView<const T> out,
                                                                   PixView<const T> y, const void* rws_raw, PixView<T> dy, PixView<T> dres,
                                                                   int C, long long npix, LaneMap m) {
@@ -418,6 +432,14 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_apply_kernel(dc_bn_param
   const bool res_write = (p.flags & DC_BN_RES_WRITE) != 0;
   const bool has_dy = dy.p != nullptr;
   const bool need_y = has_dy && !ident;
+  constexpr bool mask_y = MASK_Y;                  // host: relu && DC_BN_MASK_FROM_Y (no residual); see bn_bwd_reduce_kernel
+  const bool load_out = relu && !mask_y;
+  float fsc[MASK_Y ? V : 1], fsh[MASK_Y ? V : 1];
+  if (mask_y) {
+    const BnWs fws = bn_ws(const_cast<double*>(p.sums), C);
+#pragma unroll
+    for (int j = 0; j < V; ++j) { fsc[j] = fws.coef[c0 + j]; fsh[j] = fws.coef[C + c0 + j]; }
+  }
   float A[V], B[V], D[V];
   if (need_y) {
     const BnWs rws = bn_ws(const_cast<void*>(rws_raw), C);
@@ -430,35 +452,40 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_apply_kernel(dc_bn_param
   const long long stride = (long long)gridDim.x * m.ppb;
   long long pix = (long long)blockIdx.x * m.ppb + warp * m.ppw + psub;
   for (; pix < npix; pix += kUnroll * stride) {
-    uint4 graw[kUnroll], oraw[kUnroll], vraw[kUnroll], rraw[kUnroll];
+    constexpr int KO = MASK_Y ? 1 : kUnroll;      // `out` and the residual gradient are not read in mask-from-y mode
+    uint4 graw[kUnroll], oraw[KO], vraw[kUnroll], rraw[KO];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u)
       if (pix + u * stride < npix) {
         graw[u] = vec16<T>::ldraw(dout.at(pix + u * stride) + c0);
-        if (relu) oraw[u] = vec16<T>::ldraw(out.at(pix + u * stride) + c0);
-        if (need_y) vraw[u] = vec16<T>::ldraw(y.at(pix + u * stride) + c0);
-        if (has_res && !res_write) rraw[u] = vec16<T>::ldraw(dres.at(pix + u * stride) + c0);
+        if (load_out) oraw[MASK_Y ? 0 : u] = vec16<T>::ldraw(out.at(pix + u * stride) + c0);
+        if (need_y || mask_y) vraw[u] = vec16<T>::ldraw(y.at(pix + u * stride) + c0);
+        if (!MASK_Y && has_res && !res_write) rraw[MASK_Y ? 0 : u] = vec16<T>::ldraw(dres.at(pix + u * stride) + c0);
       }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u)
       if (pix + u * stride < npix) {
         float gg[V], o[V], v[V], r[V];
         vec16<T>::unpack(graw[u], gg);
+        if (need_y || mask_y) vec16<T>::unpack(vraw[u], v);
         if (relu) {
-          vec16<T>::unpack(oraw[u], o);
+          if (load_out) vec16<T>::unpack(oraw[MASK_Y ? 0 : u], o);
+          else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) o[j] = fmaf(v[j], fsc[MASK_Y ? j : 0], fsh[MASK_Y ? j : 0]);
+          }
 #pragma unroll
           for (int j = 0; j < V; ++j) gg[j] = o[j] > 0.f ? gg[j] : 0.f;
         }
-        if (has_res) {
+        if (!MASK_Y && has_res) {
           float rr[V];
-          if (!res_write) vec16<T>::unpack(rraw[u], r);
+          if (!res_write) vec16<T>::unpack(rraw[MASK_Y ? 0 : u], r);
 #pragma unroll
           for (int j = 0; j < V; ++j) rr[j] = res_write ? gg[j] : gg[j] + r[j];
           vec16<T>::st(dres.at(pix + u * stride) + c0, rr);
         }
         if (has_dy) {
           float d[V];
-          if (need_y) vec16<T>::unpack(vraw[u], v);
 #pragma unroll
           for (int j = 0; j < V; ++j) d[j] = need_y ? fmaf(A[j], gg[j], fmaf(B[j], v[j], D[j])) : gg[j];
           vec16<T>::st(dy.at(pix + u * stride) + c0, d);
@@ -528,8 +555,13 @@ static int bn_apply_t(const dc_bn_params& p, const dc_view& y, const dc_view& re
   const long long npix = (long long)y.n * y.h * y.w;
   LaneMap m = lane_map(y.c, V);
   // element-wise: two pixels per thread and as many blocks as that needs (small register footprint, 3 blocks per SM)
-  dim3 grid = bn_grid(m, npix, kApplyUnroll, 1 << 20);
-  launch_k(bn_apply_kernel<T, V, kApplyUnroll>, grid, dim3(kBnThreads), (size_t)0, st, p, pix_view<const T>(y), pix_view<const T>(res), pix_view<T>(out), y.c, npix, m);
+  if (res.ptr != nullptr) {
+    dim3 grid = bn_grid(m, npix, kApplyUnroll / 2, 1 << 20);
+    launch_k(bn_apply_kernel<T, V, kApplyUnroll / 2, true>, grid, dim3(kBnThreads), (size_t)0, st, p, pix_view<const T>(y), pix_view<const T>(res), pix_view<T>(out), y.c, npix, m);
+  } else {
+    dim3 grid = bn_grid(m, npix, kApplyUnroll, 1 << 20);
+    launch_k(bn_apply_kernel<T, V, kApplyUnroll, false>, grid, dim3(kBnThreads), (size_t)0, st, p, pix_view<const T>(y), pix_view<const T>(res), pix_view<T>(out), y.c, npix, m);
+  }
   return launch_status("dc_bn_apply");
 }
 template <typename T>
@@ -550,7 +582,11 @@ static int bn_bwd_apply_t(const dc_bn_params& p, const dc_view& dout, const dc_v
   const long long npix = (long long)dout.n * dout.h * dout.w;
   LaneMap m = lane_map(dout.c, V);
   dim3 grid = bn_grid(m, npix, kBwdApplyUnroll, 1 << 20);
-  launch_k(bn_bwd_apply_kernel<T, V, kBwdApplyUnroll>, grid, dim3(kBnThreads), (size_t)0, st, p, pix_view<const T>(dout), pix_view<const T>(out), pix_view<const T>(y), rws,
+  if ((p.flags & DC_BN_RELU) && (p.flags & DC_BN_MASK_FROM_Y))
+    launch_k(bn_bwd_apply_kernel<T, V, kBwdApplyUnroll, true>, grid, dim3(kBnThreads), (size_t)0, st, p, pix_view<const T>(dout), pix_view<const T>(out), pix_view<const T>(y), rws,
+                                                         pix_view<T>(dy), pix_view<T>(dres), dout.c, npix, m);
+  else
+    launch_k(bn_bwd_apply_kernel<T, V, kBwdApplyUnroll, false>, grid, dim3(kBnThreads), (size_t)0, st, p, pix_view<const T>(dout), pix_view<const T>(out), pix_view<const T>(y), rws,
                                                          pix_view<T>(dy), pix_view<T>(dres), dout.c, npix, m);
   return launch_status("dc_bn_bwd_apply");
 }
@@ -698,7 +734,7 @@ __global__ void __launch_bounds__(kOnePassThreads, 1) bn_bwd_onepass_kernel(dc_b
   const bool train = (p.flags & DC_BN_TRAIN) != 0;
   // ReLU mask = (out > 0).  Without a residual, out = relu(fma(y, scale, shift)) with the forward coefficients still in the
   // forward workspace, so the same decision is recomputed from y and `out` is not read at all (one input stream less).
-  const bool mask_from_y = relu && train && dres.p == nullptr;
+  const bool mask_from_y = relu && train && (dres.p == nullptr || (p.flags & DC_BN_MASK_FROM_Y) != 0);
   if (ok) {
     // gradient and pre-BN activation of the block's slice: global -> shared memory, every 16-byte copy in flight at once
     const uint32_t hold_s = (uint32_t)__cvta_generic_to_shared(hold);
@@ -963,7 +999,8 @@ int dc_bn_bwd_reduce(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y
   DC_REQUIRE(p != nullptr && rws != nullptr, "dc_bn_bwd_reduce: null argument");
   const dc_view opts[2] = {dout, out};
   DC_REQUIRE(view_ok(dout) && views_ok(y, opts, 2), "dc_bn_bwd_reduce: bad views");
-  if (p->flags & DC_BN_RELU) DC_REQUIRE(view_ok(out), "dc_bn_bwd_reduce: out view required for ReLU mask");
+  if ((p->flags & DC_BN_RELU) && !(p->flags & DC_BN_MASK_FROM_Y)) DC_REQUIRE(view_ok(out), "dc_bn_bwd_reduce: out view required for ReLU mask");
+  if (p->flags & DC_BN_MASK_FROM_Y) DC_REQUIRE((p->flags & DC_BN_TRAIN) && p->sums != nullptr, "dc_bn_bwd_reduce: DC_BN_MASK_FROM_Y needs the train-mode forward workspace");
   DC_REQUIRE(p->gamma != nullptr, "dc_bn_bwd_reduce: gamma required");
   if (p->flags & DC_BN_TRAIN) DC_REQUIRE(p->sums != nullptr, "dc_bn_bwd_reduce: forward workspace required in train mode");
   else DC_REQUIRE(p->running_mean && p->running_var, "dc_bn_bwd_reduce: running statistics required in eval mode");
@@ -977,7 +1014,10 @@ int dc_bn_bwd_apply(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y,
   DC_REQUIRE(p != nullptr, "dc_bn_bwd_apply: null params");
   const dc_view opts[4] = {dy, dres, out, y};
   DC_REQUIRE(views_ok(dout, opts, 4), "dc_bn_bwd_apply: views must be channel-contiguous, 16-byte aligned and of one shape/dtype");
-  if (p->flags & DC_BN_RELU) DC_REQUIRE(view_ok(out), "dc_bn_bwd_apply: out view required for ReLU mask");
+  if ((p->flags & DC_BN_RELU) && !(p->flags & DC_BN_MASK_FROM_Y)) DC_REQUIRE(view_ok(out), "dc_bn_bwd_apply: out view required for ReLU mask");
+  if (p->flags & DC_BN_MASK_FROM_Y)
+    DC_REQUIRE((p->flags & DC_BN_TRAIN) && p->sums != nullptr && view_ok(y) && dres.ptr == nullptr,
+               "dc_bn_bwd_apply: DC_BN_MASK_FROM_Y needs the train-mode forward workspace, y, and no residual");
   if (!(p->flags & DC_BN_IDENTITY) && dy.ptr != nullptr)
     DC_REQUIRE(rws != nullptr && view_ok(y), "dc_bn_bwd_apply: y and the backward workspace are required");
   cudaStream_t st = as_stream(stream);
@@ -1011,7 +1051,8 @@ int dc_bn_bwd_onepass(const dc_bn_params* p, dc_view dout, dc_view out, dc_view 
   DC_REQUIRE(p != nullptr && rws != nullptr && !(p->flags & DC_BN_IDENTITY), "dc_bn_bwd_onepass: null argument");
   const dc_view opts[4] = {dout, out, dy, dres};
   DC_REQUIRE(view_ok(dout) && views_ok(y, opts, 4), "dc_bn_bwd_onepass: bad views");
-  if (p->flags & DC_BN_RELU) DC_REQUIRE(view_ok(out), "dc_bn_bwd_onepass: out view required for ReLU mask");
+  if ((p->flags & DC_BN_RELU) && !((p->flags & DC_BN_TRAIN) && dres.ptr == nullptr))
+    DC_REQUIRE(view_ok(out), "dc_bn_bwd_onepass: out view required for ReLU mask");
   DC_REQUIRE(p->gamma != nullptr, "dc_bn_bwd_onepass: gamma required");
   if (p->flags & DC_BN_TRAIN) DC_REQUIRE(p->sums != nullptr, "dc_bn_bwd_onepass: forward workspace required in train mode");
   else DC_REQUIRE(p->running_mean && p->running_var, "dc_bn_bwd_onepass: running statistics required in eval mode");

@@ -12,7 +12,7 @@ from . import build as _build
 DC_F32, DC_BF16 = 0, 1
 DC_MAX_TAPS = 9
 DC_PACK_TKN, DC_PACK_NTK = 0, 1
-DC_BN_RELU, DC_BN_TRAIN, DC_BN_IDENTITY, DC_BN_RES_WRITE, DC_BN_SUMS_READY = 1, 2, 4, 8, 16
+DC_BN_RELU, DC_BN_TRAIN, DC_BN_IDENTITY, DC_BN_RES_WRITE, DC_BN_SUMS_READY, DC_BN_MASK_FROM_Y = 1, 2, 4, 8, 16, 32
 
 
 class dc_view(Structure):

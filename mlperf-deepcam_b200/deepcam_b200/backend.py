@@ -12,7 +12,8 @@ import os
 import torch
 
 from . import convdesc, ops
-from ._lib import DC_BN_IDENTITY, DC_BN_RELU, DC_BN_RES_WRITE, DC_BN_SUMS_READY, DC_BN_TRAIN, DC_PACK_NTK, DC_PACK_TKN
+from ._lib import (DC_BN_IDENTITY, DC_BN_MASK_FROM_Y, DC_BN_RELU, DC_BN_RES_WRITE, DC_BN_SUMS_READY, DC_BN_TRAIN, DC_PACK_NTK,
+                   DC_PACK_TKN)
 
 
 def _round_up(a, b):
@@ -411,14 +412,20 @@ class CudaBackend:
         m = spec.module
         if training:
             flags |= DC_BN_TRAIN
+        mask_src = out if relu else None
+        if relu and training and dres is None:
+            # out = relu(y * scale + shift) with the coefficients still in the forward workspace: the kernels recompute the
+            # ReLU decision from y (which they read anyway) instead of reading `out`
+            flags |= DC_BN_MASK_FROM_Y
+            mask_src = None
         p = ops.bn_params(m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var, sums, n * h * w, 0.0, m.eps, flags)
         rws = self.scratch(ops.bn_ws_elems(c), torch.float64, zero=True)
         if self.onepass and self.onepass_bwd and ops.bn_onepass_ok(c, n * h * w, dout.dtype, True):
-            ops.bn_bwd_onepass(p, dout, out if relu else None, y, rws, dy, dres, dgamma, dbeta)
+            ops.bn_bwd_onepass(p, dout, mask_src, y, rws, dy, dres, dgamma, dbeta)
             self.launches += 1
             return
-        ops.bn_bwd_reduce(p, dout, out if relu else None, y, rws, dgamma, dbeta)
-        ops.bn_bwd_apply(p, dout, out if relu else None, y, rws, dy, dres)
+        ops.bn_bwd_reduce(p, dout, mask_src, y, rws, dgamma, dbeta)
+        ops.bn_bwd_apply(p, dout, mask_src, y, rws, dy, dres)
         self.launches += 2
 
     # ---- image pooling branch ------------------------------------------------------------------------------------------

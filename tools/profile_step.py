@@ -29,7 +29,8 @@ def main():
     dev = torch.device("cuda:0")
     torch.manual_seed(333)
     net = dx.DeepLabv3_plus(16, 3, 16, _print=False).to(dev).train()
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, eps=1e-8, weight_decay=1e-6)
+    from deepcam_b200.optim import FusedAdam
+    opt = FusedAdam(net.parameters(), lr=1e-3, eps=1e-8, weight_decay=1e-6)      # as in bench.py
     cw = [1.001729912096556, 2.6146112239752224, 1.7164197479589602]
     x = torch.rand(args.batch, 16, args.height, args.width, device=dev)
     label = (torch.rand(args.batch, args.height, args.width, device=dev) > 0.986).long()
