@@ -136,6 +136,15 @@ int dc_dw_bwd_data(dc_view dout, const void* w9c, int stride, int dil, dc_view d
 /* fp32 gradient accumulated with atomics into a pre-zeroed buffer: param_layout = 0 -> G[9][C] (tap-major scratch),
  * param_layout = 1 -> the parameter's own [C][1][3][3] layout (no unpack needed afterwards) */
 int dc_dw_bwd_weight(dc_view in, dc_view dout, int stride, int dil, float* G9c, int param_layout, void* stream);
+/* Backward-data of a stride-1 dilation-1 depthwise conv whose INPUT is a BatchNorm output a = relu(bn(y) [+ residual])
+ * (the ReLU -> depthwise chain of every Block, DX:79-97): this call must be the LAST writer of dL/da.  It stores
+ * g = (dL/da, plus the already stored part when accumulate) masked by a > 0 into `din`, and adds per channel sum(g) and
+ * sum(g*y) to the zeroed BatchNorm backward workspace `bwd_ws`; dc_bn_bwd_apply_reduced then finishes BatchNorm backward
+ * in one element-wise pass (no reduction pass, no one-pass barrier kernel).  act = the stored activation a as the mask
+ * source (needed when the BatchNorm had a residual), or a null view: the mask is recomputed from y and the coefficients in
+ * the forward workspace `fwd_ws`.  relu = 0: no mask.  Returns -2 when the tile does not fit (caller falls back). */
+int dc_dw_bwd_data_bnred(dc_view dout, const void* w9c, dc_view din, int accumulate, dc_view y, dc_view act,
+                         const void* fwd_ws, void* bwd_ws, int relu, void* stream);
 
 /* ---- BatchNorm2d (+ReLU, +residual add) (normalizer, DX:70,129,283,348,399; relu DX:79,147; add DX:120) ---- */
 /* Per-layer BatchNorm workspace, dc_bn_ws_bytes(C) bytes, ZEROED by the caller before dc_bn_stats / dc_bn_bwd_reduce:
@@ -176,6 +185,10 @@ int dc_bn_bwd_reduce(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y
 /* backward pass 2: dy = A*g + B*y + D (= gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))); optional dres (+)= g */
 int dc_bn_bwd_apply(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, const void* rws,
                     dc_view dy, dc_view dres, void* stream);
+/* BatchNorm backward for a gradient already masked and reduced by dc_dw_bwd_data_bnred (train mode): coefficients are
+ * finalized inside the kernel from the workspace sums; writes dy, dgamma, dbeta and dres (+)= g. */
+int dc_bn_bwd_apply_reduced(const dc_bn_params* p, dc_view g, dc_view y, const void* rws, dc_view dy, dc_view dres,
+                            float* dgamma, float* dbeta, void* stream);
 /* One-pass variants for tensors small enough to be held in shared memory across the GPU (dc_bn_onepass_ok): statistics
  * and normalisation (forward) / reduction and gradient (backward) in ONE launch with an inter-block barrier; the grid
  * never exceeds the SM count, so all blocks are co-resident.  Same workspace contract as the two-pass entry points. */

@@ -120,38 +120,6 @@ __host__ __device__ static inline BnWs bn_ws(void* ws, int C) {
 constexpr int kBnThreads = 256;
 constexpr int kUnroll = 4;
 
-// Block reduction of NACC x V per-thread partials over the pixel lanes of a block, then fp64 atomics.
-// smem: float red[NW warps][32 lanes][NACC*V]
-template <int NACC, int V, int NW = 8>
-__device__ __forceinline__ void reduce_to_ws(float (&acc)[NACC][V], double* dst, int C, int cvp, int cv_base, int cv_count) {
-  extern __shared__ float red[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // lanes of a warp that share a channel vector (different pixels): butterfly over the pixel-sub index
-  for (int o = cvp; o < 32; o <<= 1) {
-#pragma unroll
-    for (int a = 0; a < NACC; ++a)
-#pragma unroll
-      for (int j = 0; j < V; ++j) acc[a][j] += __shfl_xor_sync(0xffffffffu, acc[a][j], o);
-  }
-  constexpr int PER = NACC * V;
-  if (lane < cvp) {
-#pragma unroll
-    for (int a = 0; a < NACC; ++a)
-#pragma unroll
-      for (int j = 0; j < V; ++j) red[(warp * 32 + lane) * PER + a * V + j] = acc[a][j];
-  }
-  __syncthreads();
-  for (int col = threadIdx.x; col < cvp * PER; col += NW * 32) {
-    const int l = col / PER, r = col - l * PER;
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) s += red[(w * 32 + l) * PER + r];
-    const int a = r / V, j = r - a * V;
-    const int cvi = cv_base + l;
-    if (l < cv_count) atomicAdd(dst + (size_t)a * C + cvi * V + j, (double)s);
-  }
-}
-
 // 1/sqrt(v) in fp32: hardware approximation + one Newton-Raphson step (~1 ulp)
 __device__ __forceinline__ float inv_sqrt_f32(float v) {
   float r = rsqrtf(v);
@@ -233,40 +201,10 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(dc_bn_params p, Pi
 // per-thread forward coefficients of V channels
 template <int V>
 __device__ __forceinline__ void load_fwd_coef(const dc_bn_params& p, int C, int c0, float (&scale)[V], float (&shift)[V],
-                                              float (&mean)[V], float (&invstd)[V], bool writer = false) {
+                                              float (&mean)[V], float (&invstd)[V]) {
   if (p.flags & DC_BN_IDENTITY) {
 #pragma unroll
     for (int j = 0; j < V; ++j) { scale[j] = 1.f; shift[j] = 0.f; mean[j] = 0.f; invstd[j] = 1.f; }
-  } else if ((p.flags & DC_BN_TRAIN) && (p.flags & DC_BN_SUMS_READY)) {
-    // the producer of y (GEMM epilogue) left the raw sums in the workspace: every thread finalizes its own channels (same
-    // arithmetic as the last block of bn_stats_kernel); `writer` threads (one per channel) also publish the coefficients
-    // for the backward pass and update the running statistics
-    const BnWs ws = bn_ws(const_cast<double*>(p.sums), C);
-    const double inv_count = 1.0 / p.count;
-#pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const int c = c0 + j;
-      const double sm = ws.sums[c], sq = ws.sums[C + c];
-      const double mu = sm * inv_count;
-      double var = sq * inv_count - mu * mu;
-      if (var < 0.0) var = 0.0;
-      const float inv = inv_sqrt_f32((float)(var + (double)p.eps));
-      scale[j] = p.gamma[c] * inv;
-      shift[j] = p.beta[c] - (float)mu * scale[j];
-      mean[j] = (float)mu;
-      invstd[j] = inv;
-      if (writer) {
-        ws.coef[c] = scale[j];
-        ws.coef[C + c] = shift[j];
-        ws.coef[2 * C + c] = mean[j];
-        ws.coef[3 * C + c] = inv;
-        if (p.running_mean != nullptr) {
-          const double unbias = p.count / (p.count - 1.0);
-          p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mu;
-          p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)(var * unbias);
-        }
-      }
-    }
   } else if (p.flags & DC_BN_TRAIN) {
     const BnWs ws = bn_ws(const_cast<double*>(p.sums), C);
 #pragma unroll
@@ -293,10 +231,50 @@ __global__ void __launch_bounds__(kBnThreads, 3) bn_apply_kernel(dc_bn_params p,
   pdl_sync();
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
   const int cvi = blockIdx.y * m.cvp + cvl;
-  if (cvi >= m.cv) return;
   const int c0 = cvi * V;
-  float scale[V], shift[V], mean[V], invstd[V];
-  load_fwd_coef<V>(p, C, c0, scale, shift, mean, invstd, blockIdx.x == 0 && warp == 0 && psub == 0);
+  float scale[V], shift[V];
+  if ((p.flags & DC_BN_TRAIN) && (p.flags & DC_BN_SUMS_READY) && !(p.flags & DC_BN_IDENTITY)) {
+    // The producer of y (GEMM epilogue) left the raw batch sums in the workspace.  The block finalizes its <= 256 channels
+    // cooperatively (thread t -> one channel, same arithmetic as the last block of bn_stats_kernel) into shared memory;
+    // block column 0 also publishes the coefficients for the backward pass and updates the running statistics.
+    __shared__ float s_coef[2][32 * V];
+    const int nch = m.cvp * V;
+    if ((int)threadIdx.x < nch) {
+      const int c = blockIdx.y * nch + threadIdx.x;
+      float sc = 0.f, sh = 0.f;
+      if (c < C) {
+        const BnWs ws = bn_ws(const_cast<double*>(p.sums), C);
+        const double inv_count = 1.0 / p.count;
+        const double mu = ws.sums[c] * inv_count;
+        double var = ws.sums[C + c] * inv_count - mu * mu;
+        if (var < 0.0) var = 0.0;
+        const float inv = inv_sqrt_f32((float)(var + (double)p.eps));
+        sc = p.gamma[c] * inv;
+        sh = p.beta[c] - (float)mu * sc;
+        if (blockIdx.x == 0) {
+          ws.coef[c] = sc;
+          ws.coef[C + c] = sh;
+          ws.coef[2 * C + c] = (float)mu;
+          ws.coef[3 * C + c] = inv;
+          if (p.running_mean != nullptr) {
+            const double unbias = p.count / (p.count - 1.0);
+            p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mu;
+            p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)(var * unbias);
+          }
+        }
+      }
+      s_coef[0][threadIdx.x] = sc;
+      s_coef[1][threadIdx.x] = sh;
+    }
+    __syncthreads();
+    if (cvi >= m.cv) return;
+#pragma unroll
+    for (int j = 0; j < V; ++j) { scale[j] = s_coef[0][cvl * V + j]; shift[j] = s_coef[1][cvl * V + j]; }
+  } else {
+    if (cvi >= m.cv) return;
+    float mean[V], invstd[V];
+    load_fwd_coef<V>(p, C, c0, scale, shift, mean, invstd);
+  }
   const bool relu = (p.flags & DC_BN_RELU) != 0;
   constexpr bool has_res = HAS_RES;
   const long long stride = (long long)gridDim.x * m.ppb;
@@ -419,15 +397,47 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(dc_bn_params 
 template <typename T, int V, int kUnroll, bool MASK_Y>
 __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_apply_kernel(dc_bn_params p, PixView<const T> dout, PixView<const T> out,
                                                                   PixView<const T> y, const void* rws_raw, PixView<T> dy, PixView<T> dres,
-                                                                  int C, long long npix, LaneMap m) {
+                                                                  float* dgamma, float* dbeta, int C, long long npix, LaneMap m) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   pdl_sync();
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
   const int cvi = blockIdx.y * m.cvp + cvl;
-  if (cvi >= m.cv) return;
   const int c0 = cvi * V;
   const bool relu = (p.flags & DC_BN_RELU) != 0;
   const bool ident = (p.flags & DC_BN_IDENTITY) != 0;
+  const bool reduced = !ident && (p.flags & DC_BN_SUMS_READY) != 0;
+  __shared__ float s_abd[3][32 * V];
+  if (reduced) {
+    // dc_bn_bwd_apply_reduced (train mode): the producer of dout (dc_dw_bwd_data_bnred) left sum(g) and sum(g*y) in the
+    // backward workspace; the block finalizes its channels cooperatively (thread t -> one channel, the arithmetic of the
+    // last block of bn_bwd_reduce_kernel); block column 0 also writes the affine gradients
+    const int nch = m.cvp * V;
+    if ((int)threadIdx.x < nch) {
+      const int c = blockIdx.y * nch + threadIdx.x;
+      float a = 0.f, b = 0.f, d = 0.f;
+      if (c < C) {
+        const BnWs rws = bn_ws(const_cast<void*>(rws_raw), C);
+        const BnWs fws = bn_ws(const_cast<double*>(p.sums), C);
+        const double inv_count = 1.0 / p.count;
+        const double mean = p.sums[c] * inv_count;
+        const double inv = (double)fws.coef[3 * C + c];
+        const double sg = rws.sums[c], sgy = rws.sums[C + c];
+        const double sgx = inv * (sgy - mean * sg);
+        const double scale = (double)p.gamma[c] * inv;
+        const double mg = sg * inv_count, mgx = sgx * inv_count;
+        a = (float)scale;
+        b = (float)(-scale * inv * mgx);
+        d = (float)(-scale * mg + scale * mean * inv * mgx);
+        if (blockIdx.x == 0) {
+          if (dgamma) dgamma[c] = (float)sgx;
+          if (dbeta) dbeta[c] = (float)sg;
+        }
+      }
+      s_abd[0][threadIdx.x] = a; s_abd[1][threadIdx.x] = b; s_abd[2][threadIdx.x] = d;
+    }
+    __syncthreads();
+  }
+  if (cvi >= m.cv) return;
   const bool has_res = dres.p != nullptr;
   const bool res_write = (p.flags & DC_BN_RES_WRITE) != 0;
   const bool has_dy = dy.p != nullptr;
@@ -435,13 +445,16 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_apply_kernel(dc_bn_param
   constexpr bool mask_y = MASK_Y;                  // host: relu && DC_BN_MASK_FROM_Y (no residual); see bn_bwd_reduce_kernel
   const bool load_out = relu && !mask_y;
   float fsc[MASK_Y ? V : 1], fsh[MASK_Y ? V : 1];
-  if (mask_y) {
+  if (mask_y && relu) {
     const BnWs fws = bn_ws(const_cast<double*>(p.sums), C);
 #pragma unroll
     for (int j = 0; j < V; ++j) { fsc[j] = fws.coef[c0 + j]; fsh[j] = fws.coef[C + c0 + j]; }
   }
   float A[V], B[V], D[V];
-  if (need_y) {
+  if (reduced) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) { A[j] = s_abd[0][cvl * V + j]; B[j] = s_abd[1][cvl * V + j]; D[j] = s_abd[2][cvl * V + j]; }
+  } else if (need_y) {
     const BnWs rws = bn_ws(const_cast<void*>(rws_raw), C);
 #pragma unroll
     for (int j = 0; j < V; ++j) { A[j] = rws.coef[c0 + j]; B[j] = rws.coef[C + c0 + j]; D[j] = rws.coef[2 * C + c0 + j]; }
@@ -555,11 +568,14 @@ static int bn_apply_t(const dc_bn_params& p, const dc_view& y, const dc_view& re
   const long long npix = (long long)y.n * y.h * y.w;
   LaneMap m = lane_map(y.c, V);
   // element-wise: two pixels per thread and as many blocks as that needs (small register footprint, 3 blocks per SM)
+  // with DC_BN_SUMS_READY every block first finalizes its channels: cap the grid at 3 resident blocks per SM (grid-stride
+  // loop) so that this prologue is paid once per resident block instead of once per 8 pixels
+  const int cap = (p.flags & DC_BN_SUMS_READY) ? 3 : (1 << 20);
   if (res.ptr != nullptr) {
-    dim3 grid = bn_grid(m, npix, kApplyUnroll / 2, 1 << 20);
+    dim3 grid = bn_grid(m, npix, kApplyUnroll / 2, cap);
     launch_k(bn_apply_kernel<T, V, kApplyUnroll / 2, true>, grid, dim3(kBnThreads), (size_t)0, st, p, pix_view<const T>(y), pix_view<const T>(res), pix_view<T>(out), y.c, npix, m);
   } else {
-    dim3 grid = bn_grid(m, npix, kApplyUnroll, 1 << 20);
+    dim3 grid = bn_grid(m, npix, kApplyUnroll, cap);
     launch_k(bn_apply_kernel<T, V, kApplyUnroll, false>, grid, dim3(kBnThreads), (size_t)0, st, p, pix_view<const T>(y), pix_view<const T>(res), pix_view<T>(out), y.c, npix, m);
   }
   return launch_status("dc_bn_apply");
@@ -577,17 +593,19 @@ static int bn_bwd_reduce_t(const dc_bn_params& p, const dc_view& dout, const dc_
 }
 template <typename T>
 static int bn_bwd_apply_t(const dc_bn_params& p, const dc_view& dout, const dc_view& out, const dc_view& y, const void* rws,
-                          const dc_view& dy, const dc_view& dres, cudaStream_t st) {
+                          const dc_view& dy, const dc_view& dres, cudaStream_t st, float* dgamma = nullptr, float* dbeta = nullptr) {
   constexpr int V = vec16<T>::V;
   const long long npix = (long long)dout.n * dout.h * dout.w;
   LaneMap m = lane_map(dout.c, V);
-  dim3 grid = bn_grid(m, npix, kBwdApplyUnroll, 1 << 20);
-  if ((p.flags & DC_BN_RELU) && (p.flags & DC_BN_MASK_FROM_Y))
+  const bool reduced = (p.flags & DC_BN_SUMS_READY) != 0;
+  dim3 grid = bn_grid(m, npix, kBwdApplyUnroll, reduced ? 2 : (1 << 20));      // reduced: per-block finalize prologue, see bn_apply_t
+  // lean instantiation (no `out`, no residual-gradient registers): mask-from-y mode, and reduced mode without a residual
+  if (((p.flags & DC_BN_RELU) && (p.flags & DC_BN_MASK_FROM_Y)) || (reduced && dres.ptr == nullptr))
     launch_k(bn_bwd_apply_kernel<T, V, kBwdApplyUnroll, true>, grid, dim3(kBnThreads), (size_t)0, st, p, pix_view<const T>(dout), pix_view<const T>(out), pix_view<const T>(y), rws,
-                                                         pix_view<T>(dy), pix_view<T>(dres), dout.c, npix, m);
+                                                         pix_view<T>(dy), pix_view<T>(dres), dgamma, dbeta, dout.c, npix, m);
   else
     launch_k(bn_bwd_apply_kernel<T, V, kBwdApplyUnroll, false>, grid, dim3(kBnThreads), (size_t)0, st, p, pix_view<const T>(dout), pix_view<const T>(out), pix_view<const T>(y), rws,
-                                                         pix_view<T>(dy), pix_view<T>(dres), dout.c, npix, m);
+                                                         pix_view<T>(dy), pix_view<T>(dres), dgamma, dbeta, dout.c, npix, m);
   return launch_status("dc_bn_bwd_apply");
 }
 
@@ -1023,6 +1041,24 @@ int dc_bn_bwd_apply(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y,
   cudaStream_t st = as_stream(stream);
   return dout.dtype == DC_F32 ? bn_bwd_apply_t<float>(*p, dout, out, y, rws, dy, dres, st)
                               : bn_bwd_apply_t<__nv_bfloat16>(*p, dout, out, y, rws, dy, dres, st);
+}
+
+/* BatchNorm backward when the gradient has already been masked and reduced by its producer (dc_dw_bwd_data_bnred):
+ * dy = A*g + B*y + D with the coefficients finalized inside the kernel from the workspace sums; dgamma/dbeta written;
+ * dres (+)= g.  Train mode only; p->sums = forward workspace, rws = backward workspace holding sum(g), sum(g*y). */
+int dc_bn_bwd_apply_reduced(const dc_bn_params* p, dc_view g, dc_view y, const void* rws, dc_view dy, dc_view dres, float* dgamma,
+                            float* dbeta, void* stream) {
+  DC_REQUIRE(p != nullptr && rws != nullptr, "dc_bn_bwd_apply_reduced: null argument");
+  DC_REQUIRE((p->flags & DC_BN_TRAIN) && p->sums != nullptr && p->gamma != nullptr && !(p->flags & DC_BN_IDENTITY),
+             "dc_bn_bwd_apply_reduced: train-mode BatchNorm with its forward workspace required");
+  const dc_view opts[3] = {dy, dres, y};
+  DC_REQUIRE(views_ok(g, opts, 3) && view_ok(y), "dc_bn_bwd_apply_reduced: views must be channel-contiguous, 16-byte aligned and of one shape/dtype");
+  dc_bn_params q = *p;
+  q.flags = (q.flags & ~(DC_BN_RELU | DC_BN_MASK_FROM_Y)) | DC_BN_SUMS_READY;       // g is already masked
+  dc_view none = {};
+  cudaStream_t st = as_stream(stream);
+  return g.dtype == DC_F32 ? bn_bwd_apply_t<float>(q, g, none, y, rws, dy, dres, st, dgamma, dbeta)
+                           : bn_bwd_apply_t<__nv_bfloat16>(q, g, none, y, rws, dy, dres, st, dgamma, dbeta);
 }
 
 /* 1 when the one-pass kernels can handle a [npix, C] tensor of this dtype (everything held on chip), else 0 */

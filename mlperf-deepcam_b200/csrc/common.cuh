@@ -151,4 +151,38 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Block reduction of NACC x V per-thread partials over the pixel lanes of a block, then fp64 atomics.
+// smem: float red[NW warps][32 lanes][NACC*V]
+// (shared by bn.cu and the BatchNorm-reducing depthwise backward in dw.cu; lane = psub * cvp + channel-vector lane)
+template <int NACC, int V, int NW = 8>
+__device__ __forceinline__ void reduce_to_ws(float (&acc)[NACC][V], double* dst, int C, int cvp, int cv_base, int cv_count) {
+  extern __shared__ float red[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // lanes of a warp that share a channel vector (different pixels): butterfly over the pixel-sub index
+  for (int o = cvp; o < 32; o <<= 1) {
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[a][j] += __shfl_xor_sync(0xffffffffu, acc[a][j], o);
+  }
+  constexpr int PER = NACC * V;
+  if (lane < cvp) {
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+      for (int j = 0; j < V; ++j) red[(warp * 32 + lane) * PER + a * V + j] = acc[a][j];
+  }
+  __syncthreads();
+  for (int col = threadIdx.x; col < cvp * PER; col += NW * 32) {
+    const int l = col / PER, r = col - l * PER;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += red[(w * 32 + l) * PER + r];
+    const int a = r / V, j = r - a * V;
+    const int cvi = cv_base + l;
+    if (l < cv_count) atomicAdd(dst + (size_t)a * C + cvi * V + j, (double)s);
+  }
+}
+
+
 }  // namespace dc

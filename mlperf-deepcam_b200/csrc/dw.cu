@@ -327,6 +327,173 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_kernel(DwView<const T
   }
 }
 
+// ---- stride 1, dilation 1 backward-data FUSED with the ReLU mask and the BatchNorm backward reduction of the layer below ---
+// The depthwise conv's input a = relu(bn(y) [+ res]) is a BatchNorm output.  This kernel is the last writer of dL/da: it
+// finishes the gradient (adds what other consumers already stored when `accumulate`), rounds it to the storage type, masks
+// it with a > 0 and stores it, and accumulates per channel  sum(g)  and  sum(g * y)  into the BatchNorm backward workspace.
+// BatchNorm backward is then one element-wise launch (dc_bn_bwd_apply_reduced) instead of reduce + apply or the one-pass
+// barrier kernel, and neither `a` nor the gradient is re-read for the reduction.
+//   HAS_X = false: no residual, the mask is recomputed from y and the forward coefficients (like DC_BN_MASK_FROM_Y);
+//   HAS_X = true : the stored activation a is the mask source (residual blocks); the previously stored gradient is
+//                  staged through shared memory as well.
+// Weights stay packed in registers (unpacked per use) so that the kernel fits 2 blocks per SM next to the extra state.
+template <typename T, int V, bool HAS_X>
+__global__ void __launch_bounds__(kDwThreads, 2) dw_s1d1_tile_bnred_kernel(DwView<const T> in, const T* __restrict__ w9c, DwView<T> out,
+                                                                           int C, DwMap m, int accumulate, DwView<const T> yv,
+                                                                           DwView<const T> xv, const float* __restrict__ fcoef,
+                                                                           double* __restrict__ sums, int relu) {
+  constexpr int VP = V / 2;
+  extern __shared__ uint4 dw_tile[];                  // [rs + 2][ppb + 2][cvp] | y [rs][ppb][cvp] | (HAS_X) x, old [rs][ppb][cvp]
+  const DwLane l = dw_lane(m, out.h, out.w);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
+  const int TW = m.ppb + 2;
+  const int nrows = (l.y1 - l.y0) + 2;
+  const int x_base = blockIdx.x * m.ppb - 1, y_base = l.y0 - 1;
+  const int cv0 = blockIdx.y * m.cvp;
+  const int H = in.h, W = in.w;
+  const int in_vecs = (m.rs + 2) * TW * m.cvp;
+  const int int_vecs = m.rs * m.ppb * m.cvp;          // interior tile
+  uint4* ty_s = dw_tile + in_vecs;
+  uint4* tx_s = ty_s + int_vecs;
+  uint4* to_s = tx_s + int_vecs;
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(dw_tile);
+  const int cshift = 31 - __clz(m.cvp);
+  pdl_sync();
+  {
+    const T* nbase = in.p + l.n * in.sn;
+    for (int i = threadIdx.x; i < nrows * TW * m.cvp; i += kDwThreads) {
+      const int cl = i & (m.cvp - 1);
+      const int pix = i >> cshift;
+      const int ty = pix / TW, tx = pix - ty * TW;
+      const int gy = y_base + ty, gx = x_base + tx, cvi = cv0 + cl;
+      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W && cvi < m.cv;
+      const T* src = ok ? nbase + (long long)gy * in.sh + (long long)gx * in.sw + cvi * V : in.p;
+      cp_async16_zfill(tile_s + (uint32_t)i * 16u, src, ok);
+    }
+    const int irows = l.y1 - l.y0;
+    const uint32_t ty_a = (uint32_t)__cvta_generic_to_shared(ty_s), tx_a = (uint32_t)__cvta_generic_to_shared(tx_s);
+    const uint32_t to_a = (uint32_t)__cvta_generic_to_shared(to_s);
+    for (int i = threadIdx.x; i < irows * m.ppb * m.cvp; i += kDwThreads) {
+      const int cl = i & (m.cvp - 1);
+      const int pix = i >> cshift;
+      const int ty = pix / m.ppb, tx = pix - ty * m.ppb;
+      const int gy = l.y0 + ty, gx = blockIdx.x * m.ppb + tx, cvi = cv0 + cl;
+      const bool ok = gx < out.w && cvi < m.cv;
+      const long long off = (long long)gy * yv.sh + (long long)gx * yv.sw + cvi * V;
+      cp_async16_zfill(ty_a + (uint32_t)i * 16u, ok ? yv.p + l.n * yv.sn + off : yv.p, ok);
+      if (HAS_X) {
+        cp_async16_zfill(tx_a + (uint32_t)i * 16u,
+                         ok ? xv.p + l.n * xv.sn + (long long)gy * xv.sh + (long long)gx * xv.sw + cvi * V : xv.p, ok);
+        if (accumulate)
+          cp_async16_zfill(to_a + (uint32_t)i * 16u,
+                           ok ? out.p + l.n * out.sn + (long long)gy * out.sh + (long long)gx * out.sw + cvi * V : out.p, ok);
+      }
+    }
+  }
+  uint4 wraw[9];
+  // forward scale / shift of this block's channels (mask recomputation) live in shared memory behind the tiles: [2][cvp * V]
+  float* fco_s = reinterpret_cast<float*>(HAS_X ? to_s + int_vecs : tx_s);
+  if (!HAS_X && relu) {
+    for (int i = threadIdx.x; i < 2 * m.cvp * V; i += kDwThreads) {
+      const int which = i / (m.cvp * V), c = cv0 * V + (i - which * m.cvp * V);
+      fco_s[i] = c < C ? fcoef[which * C + c] : 0.f;
+    }
+  }
+  if (l.ok) {
+    const int c0 = l.cvi * V;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wraw[k] = ld16(w9c + (size_t)(8 - k) * C + c0);          // flipped filter
+  }
+  cp_async_commit_wait_all();
+  __syncthreads();
+  float acc[2][V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  if (l.ok) {
+    T* obase = out.p + l.n * out.sn + (long long)l.x * out.sw + l.cvi * V;
+    const int pcol = warp * m.ppw + psub;                                   // pixel column inside the tile (interior index)
+    const uint4* tp = dw_tile + (pcol * m.cvp + cvl);                       // halo tile column of x-1, row 0
+    const int rstride = TW * m.cvp;
+    auto step = [&](int ty, float2 (&A)[VP], float2 (&B)[VP], float2 (&Cn)[VP]) {
+      const uint4* rp = tp + ty * rstride;
+      float2 f[3][VP];
+      dwpair<T>::unpack(rp[0], f[0]);
+      dwpair<T>::unpack(rp[m.cvp], f[1]);
+      dwpair<T>::unpack(rp[2 * m.cvp], f[2]);
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        float2 w0[VP], w1[VP], w2[VP];
+        dwpair<T>::unpack(wraw[kw], w0);
+        dwpair<T>::unpack(wraw[3 + kw], w1);
+        dwpair<T>::unpack(wraw[6 + kw], w2);
+#pragma unroll
+        for (int j = 0; j < VP; ++j) {
+          Cn[j] = kw == 0 ? mul2(f[0][j], w0[j]) : fma2(f[kw][j], w0[j], Cn[j]);
+          B[j] = fma2(f[kw][j], w1[j], B[j]);
+          A[j] = fma2(f[kw][j], w2[j], A[j]);
+        }
+      }
+      const int y = y_base + ty - 1;                     // output row completed by input row y_base + ty
+      if (y >= l.y0 && y < l.y1) {
+        const int ii = ((y - l.y0) * m.ppb + pcol) * m.cvp + cvl;
+        if (HAS_X && accumulate) {
+          float2 old[VP];
+          dwpair<T>::unpack(to_s[ii], old);
+#pragma unroll
+          for (int j = 0; j < VP; ++j) { A[j].x += old[j].x; A[j].y += old[j].y; }
+        } else if (accumulate) {
+          float2 old[VP];
+          dwpair<T>::unpack(ld16(obase + (long long)y * out.sh), old);
+#pragma unroll
+          for (int j = 0; j < VP; ++j) { A[j].x += old[j].x; A[j].y += old[j].y; }
+        }
+        float2 g[VP], yy[VP];
+        dwpair<T>::unpack(dwpair<T>::pack(A), g);        // the gradient as it is stored (rounded to T)
+        dwpair<T>::unpack(ty_s[ii], yy);
+        if (relu) {
+          if (HAS_X) {
+            float2 xx[VP];
+            dwpair<T>::unpack(tx_s[ii], xx);
+#pragma unroll
+            for (int j = 0; j < VP; ++j) { g[j].x = xx[j].x > 0.f ? g[j].x : 0.f; g[j].y = xx[j].y > 0.f ? g[j].y : 0.f; }
+          } else {
+            const float2* sc2 = reinterpret_cast<const float2*>(fco_s + cvl * V);
+            const float2* sh2 = reinterpret_cast<const float2*>(fco_s + m.cvp * V + cvl * V);
+#pragma unroll
+            for (int j = 0; j < VP; ++j) {
+              const float2 o = fma2(yy[j], sc2[j], sh2[j]);
+              g[j].x = o.x > 0.f ? g[j].x : 0.f;
+              g[j].y = o.y > 0.f ? g[j].y : 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < VP; ++j) {
+          acc[0][2 * j] += g[j].x; acc[0][2 * j + 1] += g[j].y;
+          acc[1][2 * j] = fmaf(g[j].x, yy[j].x, acc[1][2 * j]);
+          acc[1][2 * j + 1] = fmaf(g[j].y, yy[j].y, acc[1][2 * j + 1]);
+        }
+        st16(obase + (long long)y * out.sh, dwpair<T>::pack(g));
+      }
+    };
+    float2 a0[VP], a1[VP], a2[VP];
+#pragma unroll
+    for (int j = 0; j < VP; ++j) { a0[j] = make_float2(0.f, 0.f); a1[j] = a0[j]; a2[j] = a0[j]; }
+    int ty = 0;
+    while (true) {
+      step(ty, a0, a1, a2);
+      if (++ty >= nrows) break;
+      step(ty, a1, a2, a0);
+      if (++ty >= nrows) break;
+      step(ty, a2, a0, a1);
+      if (++ty >= nrows) break;
+    }
+  }
+  __syncthreads();                                       // the tiles are dead: their memory becomes the reduction scratch
+  reduce_to_ws<2, V>(acc, sums, C, m.cvp, cv0, min(m.cvp, m.cv - cv0));
+}
+
 // ---- generic stride / dilation forward (and stride-1 backward-data with flip): nine direct taps ----------------------
 template <typename T, int V>
 __global__ void __launch_bounds__(kDwThreads) dw_direct_kernel(DwView<const T> in, const T* __restrict__ w9c, DwView<T> out, int C,
@@ -628,6 +795,37 @@ static bool dw_s1d1_tile_launch(const dc_view& in, const void* w, const dc_view&
   return true;
 }
 
+// rows per tile of the fused kernel: (rows + 2) halo rows + rows of y (+ rows of a and of the old gradient) must leave room
+// for 2 blocks per SM
+template <typename T, int V>
+static int dw_bwd_data_bnred_t(const dc_view& dout, const void* w, const dc_view& din, int acc, const dc_view& y, const dc_view& xact,
+                               const float* fcoef, double* sums, int relu, cudaStream_t st) {
+  const bool has_x = xact.ptr != nullptr;
+  // exact strip height: 10 rows (5 with the two extra staged tiles) keep two blocks per SM resident, and the 48-row
+  // middle-flow tensors then need 270 blocks = one wave
+  DwMap m = dw_map(din.c, V, din.h, din.w, din.n, 1 << 30, 1);
+  m.rs = std::min(din.h, has_x ? 5 : 10);
+  m.nstrips = ceil_div(din.h, m.rs);
+  dim3 grid = dw_grid(m, din.w, din.n);
+  const size_t in_b = (size_t)(m.rs + 2) * (m.ppb + 2) * m.cvp * 16, int_b = (size_t)m.rs * m.ppb * m.cvp * 16;
+  const size_t smem = std::max(in_b + int_b * (has_x ? 3 : 1) + (size_t)2 * m.cvp * V * sizeof(float), (size_t)8 * 32 * 2 * V * sizeof(float));
+  if (smem > 110 * 1024) return fail(-2, "dc_dw_bwd_data_bnred: tile does not fit (rows per strip %d)", m.rs);
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[has_x]) {
+    cudaError_t e = has_x ? cudaFuncSetAttribute(dw_s1d1_tile_bnred_kernel<T, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)
+                          : cudaFuncSetAttribute(dw_s1d1_tile_bnred_kernel<T, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    if (e != cudaSuccess) return fail((int)e, "dc_dw_bwd_data_bnred: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set[has_x] = true;
+  }
+  if (has_x)
+    launch_k(dw_s1d1_tile_bnred_kernel<T, V, true>, grid, dim3(kDwThreads), smem, st, dw_view<const T>(dout), (const T*)w, dw_view<T>(din),
+             din.c, m, acc, dw_view<const T>(y), dw_view<const T>(xact), fcoef, sums, relu);
+  else
+    launch_k(dw_s1d1_tile_bnred_kernel<T, V, false>, grid, dim3(kDwThreads), smem, st, dw_view<const T>(dout), (const T*)w, dw_view<T>(din),
+             din.c, m, acc, dw_view<const T>(y), dw_view<const T>(y), fcoef, sums, relu);
+  return launch_status("dc_dw_bwd_data_bnred");
+}
+
 template <typename T>
 static int dw_fwd_t(const dc_view& in, const void* w, int s, int d, const dc_view& out, cudaStream_t st) {
   constexpr int V = dwvec<T>::V;
@@ -702,6 +900,28 @@ int dc_dw_bwd_data(dc_view dout, const void* w9c, int stride, int dil, dc_view d
   cudaStream_t st = as_stream(stream);
   return din.dtype == DC_F32 ? dw_bwd_data_t<float>(dout, w9c, stride, dil, din, accumulate, st)
                              : dw_bwd_data_t<__nv_bfloat16>(dout, w9c, stride, dil, din, accumulate, st);
+}
+
+int dc_dw_bwd_data_bnred(dc_view dout, const void* w9c, dc_view din, int accumulate, dc_view y, dc_view act, const void* fwd_ws,
+                         void* bwd_ws, int relu, void* stream) {
+  if (int r = check_dw("dc_dw_bwd_data_bnred", din, dout, 1, 1)) return r;
+  DC_REQUIRE(w9c != nullptr && (reinterpret_cast<uintptr_t>(w9c) % 16) == 0, "dc_dw_bwd_data_bnred: weights must be 16-byte aligned");
+  DC_REQUIRE(bwd_ws != nullptr && view_ok(y) && same_shape(y, din) && y.dtype == din.dtype, "dc_dw_bwd_data_bnred: y must match the gradient");
+  const bool y_ok = din.dtype == DC_F32 ? dw_vec_ok<float>(y) : dw_vec_ok<__nv_bfloat16>(y);
+  DC_REQUIRE(y_ok, "dc_dw_bwd_data_bnred: y must be channel-contiguous and 16-byte aligned");
+  if (act.ptr != nullptr) {
+    const bool a_ok = view_ok(act) && same_shape(act, din) && act.dtype == din.dtype &&
+                      (din.dtype == DC_F32 ? dw_vec_ok<float>(act) : dw_vec_ok<__nv_bfloat16>(act));
+    DC_REQUIRE(a_ok, "dc_dw_bwd_data_bnred: activation view must match the gradient");
+  } else if (relu) {
+    DC_REQUIRE(fwd_ws != nullptr, "dc_dw_bwd_data_bnred: the forward BatchNorm workspace is required to recompute the ReLU mask");
+  }
+  // workspace layout (bn.cu): double sums[2][C] | float coef[4][C] | ...
+  const float* fcoef = fwd_ws ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(fwd_ws) + (size_t)16 * din.c) : nullptr;
+  double* sums = reinterpret_cast<double*>(bwd_ws);
+  cudaStream_t st = as_stream(stream);
+  return din.dtype == DC_F32 ? dw_bwd_data_bnred_t<float, 4>(dout, w9c, din, accumulate, y, act, fcoef, sums, relu, st)
+                             : dw_bwd_data_bnred_t<__nv_bfloat16, 8>(dout, w9c, din, accumulate, y, act, fcoef, sums, relu, st);
 }
 
 int dc_dw_bwd_weight(dc_view in, dc_view dout, int stride, int dil, float* G9c, int param_layout, void* stream) {

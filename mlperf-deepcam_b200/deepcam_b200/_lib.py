@@ -65,11 +65,14 @@ SIGNATURES = {
     "dc_dw_fwd": (c_int, [dc_view, c_void_p, c_int, c_int, dc_view, c_void_p]),
     "dc_dw_bwd_data": (c_int, [dc_view, c_void_p, c_int, c_int, dc_view, c_int, c_void_p]),
     "dc_dw_bwd_weight": (c_int, [dc_view, dc_view, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "dc_dw_bwd_data_bnred": (c_int, [dc_view, c_void_p, dc_view, c_int, dc_view, dc_view, c_void_p, c_void_p, c_int, c_void_p]),
     "dc_bn_ws_bytes": (c_size_t, [c_int]),
     "dc_bn_stats": (c_int, [POINTER(dc_bn_params), dc_view, c_void_p]),
     "dc_bn_apply": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p]),
     "dc_bn_bwd_reduce": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dc_bn_bwd_apply": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, dc_view, dc_view, c_void_p]),
+    "dc_bn_bwd_apply_reduced": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, c_void_p, dc_view, dc_view, c_void_p, c_void_p,
+                                        c_void_p]),
     "dc_bn_onepass_ok": (c_int, [c_int, c_int64, c_int, c_int]),
     "dc_bn_fwd_onepass": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p]),
     "dc_bn_bwd_onepass": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, dc_view, dc_view, c_void_p,

@@ -119,6 +119,9 @@ class CudaBackend:
         self.onepass_bwd = True
         # BatchNorm batch sums out of the producing GEMM's epilogue (dc_conv_gemm_tc_bnstats): no statistics pass at all
         self.fuse_bn_stats = os.environ.get("DEEPCAM_B200_FUSE_BN_STATS", "1") not in ("0", "false", "")
+        # BatchNorm backward reduction (+ ReLU mask) inside the depthwise backward-data kernel that produces the gradient
+        self.fuse_bn_bwd = os.environ.get("DEEPCAM_B200_FUSE_BN_BWD", "1") not in ("0", "false", "")
+        self.fuse_bn_bwd_max_bytes = int(os.environ.get("DEEPCAM_B200_FUSE_BN_BWD_MAX_BYTES", str(24 << 20)))
         self.side_stream = None       # set by a graph plan: weight-gradient kernels run on a parallel graph branch
         self._side_dirty = False
 
@@ -349,6 +352,31 @@ class CudaBackend:
         ops.dw_bwd_data(dy, self._dw_packed(spec), spec.stride, spec.dil, dx, accumulate)
         self.launches += 1
         return dx
+
+    def dw_bwd_data_bnred(self, dy, spec, dx, accumulate, y, act, fwd_sums, relu, force=False):
+        """dw_bwd_data as the LAST writer of the gradient of a BatchNorm output: also applies the ReLU mask and leaves the
+        BatchNorm backward sums in a fresh workspace, which is returned (None: not applicable, nothing was launched)."""
+        if not self.fuse_bn_bwd or spec.stride != 1 or spec.dil != 1:
+            return None
+        # measured on B200: a win for the L2-resident tensors without a residual (one wave of 270 blocks replaces the
+        # one-pass barrier kernel); residual layers need two more staged tiles (two waves) and on the large tensors the
+        # per-block fp64 atomics outweigh the saved reduction pass, so those keep the separate kernels
+        if not force and (act is not None or dx.numel() * dx.element_size() > self.fuse_bn_bwd_max_bytes):
+            return None
+        rws = self.scratch(ops.bn_ws_elems(dx.shape[3]), torch.float64, zero=True)
+        if not ops.dw_bwd_data_bnred(dy, self._dw_packed(spec), dx, accumulate, y, act, fwd_sums, rws, relu):
+            return None
+        self.launches += 1
+        return rws
+
+    def bn_bwd_reduced(self, g, y, spec, sums, rws, dy, dres, res_accumulate, dgamma, dbeta):
+        """BatchNorm backward (train mode) for a gradient that dw_bwd_data_bnred already masked and reduced."""
+        m = spec.module
+        flags = DC_BN_TRAIN | (0 if res_accumulate else DC_BN_RES_WRITE)
+        n, h, w, c = g.shape
+        p = ops.bn_params(m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var, sums, n * h * w, 0.0, m.eps, flags)
+        ops.bn_bwd_apply_reduced(p, g, y, rws, dy, dres, dgamma, dbeta)
+        self.launches += 1
 
     def dw_bwd_weight(self, x, dy, spec, wgrad):
         """wgrad: fp32 [C,1,3,3] view of the flat gradient buffer, ZERO on entry (the engine clears the flat buffer at the

@@ -46,11 +46,14 @@ def _make_backend(precision, device):
 
 class Act:
     """Channels-last activation: tensor [N,H,W,C] (possibly a channel slice of a concat buffer) + its gradient."""
-    __slots__ = ("t", "_grad", "is_relu", "needs_grad", "parent", "c_off", "bn_sums")
+    __slots__ = ("t", "_grad", "is_relu", "needs_grad", "parent", "c_off", "bn_sums", "consumed", "bn_src", "bn_reduced")
 
     def __init__(self, t, is_relu=False, needs_grad=True, parent=None, c_off=0):
         self.t = t
         self.bn_sums = None       # (BatchNorm module, workspace) when the producing conv already accumulated the batch sums
+        self.consumed = 0         # operations that have taken this activation as an input so far (forward order)
+        self.bn_src = None        # (y, spec, sums, relu, residual) when this is the output of a train-mode BatchNorm
+        self.bn_reduced = None    # backward workspace when the last gradient writer already masked + reduced (fused dw bwd)
         self._grad = None
         self.is_relu = is_relu
         self.needs_grad = needs_grad
@@ -168,6 +171,7 @@ class Engine:
         """bn: the BnSpec that will normalise the result next (Engine.bn on the returned Act): in training mode the
         convolution kernel then also produces the batch sums, see CudaBackend.conv_fwd."""
         n, h, w, _ = x.shape
+        x.consumed += 1
         ho, wo = spec.out_hw(h, w)
         if out is None:
             out = self.new_act(n, ho, wo, out_c or spec.co, out_dtype or x.t.dtype)
@@ -201,12 +205,14 @@ class Engine:
         n, h, w, c = x.shape
         ho, wo = spec.out_hw(h, w)
         out = self.new_act(n, ho, wo, c, x.t.dtype)
+        first = x.consumed == 0       # first consumer in forward order = LAST writer of x's gradient in backward
+        x.consumed += 1
         self.be.dw_fwd(x.t, spec, out.t)
         if self.record:
-            self.tape.append(lambda: self._dw_bwd(x, out, spec))
+            self.tape.append(lambda: self._dw_bwd(x, out, spec, first))
         return out
 
-    def _dw_bwd(self, x, out, spec):
+    def _dw_bwd(self, x, out, spec, last_writer=False):
         dy = out.grad
         if dy is None:
             return
@@ -216,11 +222,24 @@ class Engine:
             self.grads.ready(spec.weight)
         if x.needs_grad:
             dx, acc = self.grad_target(x)
+            src = x.bn_src
+            if last_writer and src is not None and x.parent is None and hasattr(self.be, "dw_bwd_data_bnred"):
+                # x = relu(bn(y) [+ residual]) and this is the last contribution to its gradient: mask it and reduce it for
+                # BatchNorm backward right here; _bn_bwd then only runs the element-wise pass
+                y, _bspec, sums, relu, residual = src
+                act = x.t if (relu and residual is not None) else None
+                rws = self.be.dw_bwd_data_bnred(dy, spec, dx, acc, y.t, act, sums, relu)
+                if rws is not None:
+                    x.bn_reduced = rws
+                    return
             self.be.dw_bwd_data(dy, spec, dx, acc)
 
     def bn(self, y, spec, relu, residual=None, out=None):
         """out = [relu](bn(y) [+ residual]); spec None = identity (plain relu / add / copy)."""
         n, h, w, c = y.shape
+        y.consumed += 1
+        if residual is not None:
+            residual.consumed += 1
         if out is None:
             out = self.new_act(n, h, w, c, y.t.dtype)
         elif out.shape != y.shape:
@@ -242,6 +261,8 @@ class Engine:
         if spec is not None and training and spec.module.num_batches_tracked is not None:
             self.bn_trained.append(spec.module)
         if self.record:
+            if spec is not None and training and sums is not None and out.parent is None and out.t.dtype == y.t.dtype:
+                out.bn_src = (y, spec, sums, relu, residual)
             self.tape.append(lambda: self._bn_bwd(y, out, spec, sums, relu, residual, training))
         return out
 
@@ -264,7 +285,12 @@ class Engine:
                 dgamma = self.grads.view(m.weight)
             if m.bias is not None and m.bias.requires_grad:
                 dbeta = self.grads.view(m.bias)
-        self.be.bn_bwd(dout, out.t, y.t, spec, sums, relu, dy, dres, racc, dgamma, dbeta, training)
+        rws = out.bn_reduced
+        if rws is not None:         # the gradient arrived masked, with its BatchNorm sums (fused depthwise backward)
+            out.bn_reduced = None
+            self.be.bn_bwd_reduced(dout, y.t, spec, sums, rws, dy, dres, racc, dgamma, dbeta)
+        else:
+            self.be.bn_bwd(dout, out.t, y.t, spec, sums, relu, dy, dres, racc, dgamma, dbeta, training)
         if dgamma is not None:
             self.grads.ready(spec.module.weight)
         if dbeta is not None:
@@ -273,6 +299,7 @@ class Engine:
     def gap(self, x):
         """AdaptiveAvgPool2d(1): [N,H,W,C] -> fp32 [N,1,1,C]."""
         n, h, w, c = x.shape
+        x.consumed += 1
         m = self.be.gap_fwd(x.t)
         out = Act(m.view(n, 1, 1, c))
         if self.record:
@@ -289,6 +316,7 @@ class Engine:
     def broadcast(self, src, out):
         """F.interpolate(1x1 -> HxW, bilinear, align_corners=True) == broadcast (DX:450)."""
         n, _, _, c = src.shape
+        src.consumed += 1
         self.be.broadcast_hw(src.t.reshape(n, c), out.t)
         if self.record:
             self.tape.append(lambda: self._broadcast_bwd(src, out))

@@ -338,6 +338,29 @@ def bn_bwd_reduce(params, dout, out, y, rws, dgamma, dbeta):
     return rws
 
 
+def dw_bwd_data_bnred(dy, w9c, dx, accumulate, y, act, fwd_ws, bwd_ws, relu):
+    """Depthwise backward-data fused with the ReLU mask and the BatchNorm backward reduction (dc_dw_bwd_data_bnred).
+    Returns False when the kernel cannot take the shape (caller falls back to the separate kernels)."""
+    _require_cuda(dy, w9c, dx, y)
+    rc = [0]
+
+    def run():
+        rc[0] = _lib.load().dc_dw_bwd_data_bnred(view(dy), _p(w9c), view(dx), int(bool(accumulate)), view(y), view(act), _p(fwd_ws),
+                                                 _p(bwd_ws), int(bool(relu)), _stream())
+        return 0 if rc[0] == -2 else rc[0]
+    _timed("dw_bwd_data_bnred", 22.0 * dx.numel(), _nbytes(dy, dx, y, act) + (dx.numel() * dx.element_size() if accumulate else 0), run,
+           "dc_dw_bwd_data_bnred", tag=_shape_tag(dx) + (" res" if act is not None else ""))
+    return rc[0] == 0
+
+
+def bn_bwd_apply_reduced(params, g, y, rws, dy, dres, dgamma, dbeta):
+    _require_cuda(g, y)
+    _timed("bn_bwd_apply", 6.0 * g.numel(), _nbytes(g, y, dy, dres),
+           lambda: _lib.load().dc_bn_bwd_apply_reduced(ctypes.byref(params), view(g), view(y), _p(rws), view(dy), view(dres),
+                                                       _p(dgamma), _p(dbeta), _stream()), "dc_bn_bwd_apply_reduced",
+           tag=_shape_tag(g) + " reduced" + (" res" if dres is not None else ""))
+
+
 def bn_bwd_apply(params, dout, out, y, rws, dy, dres):
     _require_cuda(dout)
     _timed("bn_bwd_apply", 8.0 * dout.numel(), _nbytes(dout, out, y, dy, dres),

@@ -530,3 +530,52 @@ def test_conv_tcgen05_bn_sums_and_fused_batchnorm(case):
     be.bn_bwd(dout, ya, out, BnSpec("a", bn_a), sa, True, dya, None, False, ga, ba)
     be.bn_bwd(dout, yb, out, BnSpec("b", bn_b), sb, True, dyb, None, False, gb, bb)
     assert rel(dya, dyb) < 2e-3 and rel(ga, gb) < 1e-3 and rel(ba, bb) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,H,W,use_res,relu", [(728, 48, 72, False, True), (728, 48, 72, True, True), (64, 13, 9, False, True),
+                                                 (128, 10, 37, True, True), (256, 12, 20, False, False)])
+def test_depthwise_backward_fused_with_batchnorm_reduction(dtype, C, H, W, use_res, relu):
+    """dc_dw_bwd_data_bnred + dc_bn_bwd_apply_reduced against the separate kernels (dw_bwd_data, then bn_bwd with the ReLU
+    mask) on the same tensors: stored masked gradient, dy, dres, dgamma, dbeta."""
+    from deepcam_b200.backend import BnSpec, DwSpec
+    torch.manual_seed(21)
+    be = backend(dtype)
+    N = 2
+    bn = torch.nn.BatchNorm2d(C).to(dev())
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+    y = to_nhwc(torch.randn(N, C, H, W) * 2 + 0.3, dtype)
+    res = to_nhwc(torch.randn(N, C, H, W), dtype) if use_res else None
+    a = be.empty(N, H, W, C)
+    sums = be.bn_fwd(y, BnSpec("bn", bn), relu, res, a, training=True)
+    wdw = torch.nn.Parameter(torch.randn(C, 1, 3, 3, device=dev()) * 0.3)
+    dws = DwSpec("dw", wdw, 1, 1)
+    gout = to_nhwc(torch.randn(N, C, H, W), dtype)              # gradient of the depthwise output
+    prior = to_nhwc(torch.randn(N, C, H, W), dtype) if use_res else None   # what another consumer already stored in dL/da
+
+    def run(fused):
+        da = prior.clone() if prior is not None else be.empty(N, H, W, C)
+        dy = be.empty(N, H, W, C)
+        dres = be.empty(N, H, W, C) if use_res else None
+        dg, db = torch.zeros(C, device=dev()), torch.zeros(C, device=dev())
+        if fused:
+            rws = be.dw_bwd_data_bnred(gout, dws, da, prior is not None, y, a if (relu and use_res) else None, sums, relu,
+                                       force=True)        # force: also the variants the size/residual policy would skip
+            assert rws is not None
+            be.bn_bwd_reduced(da, y, BnSpec("bn", bn), sums, rws, dy, dres, False, dg, db)
+        else:
+            be.dw_bwd_data(gout, dws, da, prior is not None)
+            be.bn_bwd(da, a, y, BnSpec("bn", bn), sums, relu, dy, dres, False, dg, db)
+        torch.cuda.synchronize()
+        return da, dy, dres, dg, db
+
+    da0, dy0, dres0, dg0, db0 = run(False)
+    da1, dy1, dres1, dg1, db1 = run(True)
+    mask = (a > 0) if relu else torch.ones_like(a, dtype=torch.bool)
+    assert torch.equal(da1, torch.where(mask, da0, torch.zeros_like(da0)))      # same gradient, stored already masked
+    tol = 1e-5 if dtype == torch.float32 else 2e-3
+    assert rel(dy1, dy0) < tol and rel(dg1, dg0) < tol and rel(db1, db0) < tol
+    if use_res:
+        assert rel(dres1, dres0) < tol
