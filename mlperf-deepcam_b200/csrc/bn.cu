@@ -15,6 +15,7 @@
 // HBM-bound: algorithmic bytes = each tensor read or written exactly once.
 #include "common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace dc {
 
@@ -538,6 +539,14 @@ __global__ void double_to_float_kernel(const double* s, float* d, int n) {
 // grid.x: enough blocks that every thread handles about `items` pixels, capped at 16 blocks per SM (grid-stride beyond)
 constexpr int kApplyUnroll = 8;       // forward apply: one read stream -> eight 16-byte loads in flight per thread
 constexpr int kBwdApplyUnroll = 4;    // backward apply: three read streams
+// blocks-per-SM caps of the grid-stride kernels: resident-sized grids amortize the per-block prologue (coefficient loads,
+// finalize) and were measured ~1.4x faster on the 100+ MB tensors than one block per 4-8 pixels.  Tunables for sweeps:
+// DEEPCAM_B200_BN_CAP_{APPLY,BWD_APPLY,REDUCE}.
+static int bn_cap(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : 0;
+  return v > 0 ? v : dflt;
+}
 static inline dim3 bn_grid(const LaneMap& m, long long npix, int items, int blocks_per_sm_cap = 16) {
   long long gx = ceil_div64(npix, (long long)m.ppb * items);
   long long cap = std::max<long long>(1, (long long)kNumSMs * blocks_per_sm_cap / m.gy);
@@ -570,7 +579,7 @@ static int bn_apply_t(const dc_bn_params& p, const dc_view& y, const dc_view& re
   // element-wise: two pixels per thread and as many blocks as that needs (small register footprint, 3 blocks per SM)
   // with DC_BN_SUMS_READY every block first finalizes its channels: cap the grid at 3 resident blocks per SM (grid-stride
   // loop) so that this prologue is paid once per resident block instead of once per 8 pixels
-  const int cap = (p.flags & DC_BN_SUMS_READY) ? 3 : (1 << 20);
+  static const int cap = bn_cap("DEEPCAM_B200_BN_CAP_APPLY", 3);
   if (res.ptr != nullptr) {
     dim3 grid = bn_grid(m, npix, kApplyUnroll / 2, cap);
     launch_k(bn_apply_kernel<T, V, kApplyUnroll / 2, true>, grid, dim3(kBnThreads), (size_t)0, st, p, pix_view<const T>(y), pix_view<const T>(res), pix_view<T>(out), y.c, npix, m);
@@ -586,7 +595,8 @@ static int bn_bwd_reduce_t(const dc_bn_params& p, const dc_view& dout, const dc_
   constexpr int V = vec16<T>::V;
   const long long npix = (long long)y.n * y.h * y.w;
   LaneMap m = lane_map(y.c, V);
-  dim3 grid = bn_grid(m, npix, 4 * kUnroll);
+  static const int cap = bn_cap("DEEPCAM_B200_BN_CAP_REDUCE", 2);
+  dim3 grid = bn_grid(m, npix, 4 * kUnroll, cap);
   launch_k(bn_bwd_reduce_kernel<T, V>, grid, dim3(kBnThreads), red_smem<2, V>(), st, p, pix_view<const T>(dout), pix_view<const T>(out),
                                                                          pix_view<const T>(y), rws, dgamma, dbeta, y.c, npix, m);
   return launch_status("dc_bn_bwd_reduce");
@@ -598,7 +608,8 @@ static int bn_bwd_apply_t(const dc_bn_params& p, const dc_view& dout, const dc_v
   const long long npix = (long long)dout.n * dout.h * dout.w;
   LaneMap m = lane_map(dout.c, V);
   const bool reduced = (p.flags & DC_BN_SUMS_READY) != 0;
-  dim3 grid = bn_grid(m, npix, kBwdApplyUnroll, reduced ? 2 : (1 << 20));      // reduced: per-block finalize prologue, see bn_apply_t
+  static const int cap = bn_cap("DEEPCAM_B200_BN_CAP_BWD_APPLY", 2);
+  dim3 grid = bn_grid(m, npix, kBwdApplyUnroll, cap);
   // lean instantiation (no `out`, no residual-gradient registers): mask-from-y mode, and reduced mode without a residual
   if (((p.flags & DC_BN_RELU) && (p.flags & DC_BN_MASK_FROM_Y)) || (reduced && dres.ptr == nullptr))
     launch_k(bn_bwd_apply_kernel<T, V, kBwdApplyUnroll, true>, grid, dim3(kBnThreads), (size_t)0, st, p, pix_view<const T>(dout), pix_view<const T>(out), pix_view<const T>(y), rws,

@@ -116,7 +116,7 @@ class CudaBackend:
         # one-launch BatchNorm for on-chip-sized tensors (inter-block barrier; needs all blocks co-resident).  The
         # backward variant is switched off by the data-parallel wrapper: NCCL kernels share the SMs during backward.
         self.onepass = os.environ.get("DEEPCAM_B200_BN_ONEPASS", "1") not in ("0", "false", "")
-        self.onepass_bwd = True
+        self.onepass_bwd = os.environ.get("DEEPCAM_B200_BN_ONEPASS_BWD", "1") not in ("0", "false", "")
         # BatchNorm batch sums out of the producing GEMM's epilogue (dc_conv_gemm_tc_bnstats): no statistics pass at all
         self.fuse_bn_stats = os.environ.get("DEEPCAM_B200_FUSE_BN_STATS", "1") not in ("0", "false", "")
         # BatchNorm backward reduction (+ ReLU mask) inside the depthwise backward-data kernel that produces the gradient

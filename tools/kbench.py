@@ -63,6 +63,16 @@ def main():
         dws = DwSpec("dw", wdw, 1, 1)
         add("dw_fwd " + tag, lambda y=y, out=out, dws=dws: be.dw_fwd(y, dws, out), 2 * nb, 18.0 * y.numel())
         add("dw_bwd_data " + tag, lambda dout=dout, dy=dy, dws=dws: be.dw_bwd_data(dout, dws, dy, False), 2 * nb, 18.0 * y.numel())
+        rws_holder = {}
+
+        def f_bnred(dout=dout, dy=dy, dws=dws, y=y, sums0=sums0, h=rws_holder):
+            h["rws"] = be.dw_bwd_data_bnred(dout, dws, dy, False, y, None, sums0, True, force=True)
+        add("dw_bwd_data_bnred " + tag, f_bnred, 3 * nb, 22.0 * y.numel())
+        f_bnred()
+
+        def f_bwd_reduced(dout=dout, y=y, spec=spec, sums0=sums0, dy=dres, h=rws_holder):
+            be.bn_bwd_reduced(dout, y, spec, sums0, h["rws"], dy, None, False, None, None)
+        add("bn_bwd_apply_reduced " + tag, f_bwd_reduced, 3 * nb)
         wg = torch.zeros(c, 1, 3, 3, device=dev)
         add("dw_bwd_weight " + tag, lambda y=y, dout=dout, dws=dws, wg=wg: be.dw_bwd_weight(y, dout, dws, wg), 2 * nb, 18.0 * y.numel())
 
