@@ -16,6 +16,7 @@ import tempfile
 import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
+_JSON_OUT = sys.stdout
 sys.path.insert(0, os.path.join(REPO, "mlperf-deepcam_b200"))
 
 H, W, C_IN, N_CLASSES, LOCAL_BATCH = 768, 1152, 16, 3, 2
@@ -130,7 +131,7 @@ def run_reference(args):
                 config=dict(workload=WORKLOAD, local_batch=LOCAL_BATCH, optimizer="Adam lr=1e-3 eps=1e-8 wd=1e-6"),
                 cpu_baseline=dict(value=value, unit="samples/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def cpu_baseline_sample():
@@ -377,7 +378,7 @@ def run_ours(args):
                     gpu_launches=launches, clocks=clocks,
                     tensor_frac_of_step=(FWD_BWD_GFLOP_PER_SAMPLE * value / 1000.0) / peaks["tf_sustained"],
                     roofline=roofline, cpu_baseline=cpu_base)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -392,6 +393,12 @@ def main():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--e2e-sync-loss", action="store_true", help="e2e leg: read the loss with .item() every step")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that print to file descriptor 1 (NCCL's version banner) are sent to
+    # stderr for the duration of the run, the JSON line goes to the saved descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -80,6 +80,12 @@ int         dc_get_pdl(void);
  * Replaces .to(device)/.contiguous()/permute glue around the model (TR:348, DX:441). */
 int dc_copy_view(dc_view src, dc_view dst, void* stream);
 int dc_fill_zero(void* ptr, size_t bytes, void* stream);
+/* Input ingest: dst[p][c] = (src[p][c] - shift[c]) * scale[c] for npix pixels of C channels, src = the raw fp32 [H][W][C]
+ * block of a CAM5 sample as stored in the HDF5 file, dst = NHWC bf16 (DC_BF16) or fp32 (DC_F32; bit-identical to the
+ * reference's numpy expression).  Replaces the host-side transpose + normalisation of CamDataset.__getitem__
+ * (data/cam_hdf5_dataset.py:126-129); shift = minval, scale = 1 / (maxval - minval) from stats.h5 (:97-102). */
+int dc_ingest_hwc(const float* src, long long npix, int C, const float* shift, const float* scale, void* dst, int dst_dtype,
+                  void* stream);
 /* *ptrs[i] += 1 for i < count  (BatchNorm num_batches_tracked, 77 counters, DX:70.. normalizer) */
 int dc_i64_increment_many(int64_t* const* ptrs, int count, void* stream);
 

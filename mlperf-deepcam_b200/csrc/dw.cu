@@ -856,6 +856,8 @@ template <typename T>
 static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d, float* G, int param_layout, cudaStream_t st) {
   const int tap_stride = param_layout ? 1 : dout.c, c_stride = param_layout ? 9 : 1;
   constexpr int V = dwvec<T>::V;
+  // (a shared-memory staged variant was measured slower here: with one tile per block the 9*C atomics per block dominate;
+  //  the register-pipelined kernels keep long strips per block and reduce once)
   DwMap m = dw_map(dout.c, V, dout.h, dout.w, dout.n, kNumSMs * 2, 12);
   dim3 grid = dw_grid(m, dout.w, dout.n);
   const size_t smem = (size_t)8 * 32 * 3 * V * sizeof(float);

@@ -219,6 +219,29 @@ static int copy_dispatch(const dc_view& src, const dc_view& dst, cudaStream_t st
 }
 
 // ---- small utilities ---------------------------------------------------------------------------
+// Input ingest: the CAM5 files store a sample as [H][W][C] fp32; the reference Dataset transposes it to CHW on
+// the host and computes scale * (data - shift) per channel (DS:126-129).  Here the raw HWC block is normalised on the
+// device in the layout it already has: dst[p][c] = (src[p][c] - shift[c]) * scale[c], stored as NHWC bf16 (or fp32, where
+// it is bit-identical to the reference: separate subtract and multiply, no FMA contraction).
+template <typename TD>
+__global__ void __launch_bounds__(256) ingest_hwc_kernel(const float* __restrict__ src, const float* __restrict__ shift,
+                                                         const float* __restrict__ scale, TD* __restrict__ dst, long long nvec, int cv) {
+  pdl_sync();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const int c4 = (int)(i % cv) * 4;
+    const float4 x = *reinterpret_cast<const float4*>(src + i * 4);
+    const float4 sh = *reinterpret_cast<const float4*>(shift + c4);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c4);
+    float4 o;
+    o.x = __fmul_rn(__fsub_rn(x.x, sh.x), sc.x);
+    o.y = __fmul_rn(__fsub_rn(x.y, sh.y), sc.y);
+    o.z = __fmul_rn(__fsub_rn(x.z, sh.z), sc.z);
+    o.w = __fmul_rn(__fsub_rn(x.w, sh.w), sc.w);
+    elem<TD>::st4(dst + i * 4, o);
+  }
+}
+
 __global__ void i64_increment_kernel(int64_t* const* ptrs, int count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) *ptrs[i] += 1;
@@ -478,6 +501,23 @@ int dc_fill_zero(void* ptr, size_t bytes, void* stream) {
   cudaError_t e = cudaMemsetAsync(ptr, 0, bytes, as_stream(stream));
   if (e != cudaSuccess) return dc::fail((int)e, "dc_fill_zero: %s", cudaGetErrorString(e));
   return 0;
+}
+
+int dc_ingest_hwc(const float* src, long long npix, int C, const float* shift, const float* scale, void* dst, int dst_dtype,
+                  void* stream) {
+  DC_REQUIRE(src && shift && scale && dst && npix > 0 && C > 0 && C % 4 == 0, "dc_ingest_hwc: bad arguments (C %% 4 == 0 required)");
+  DC_REQUIRE(dst_dtype == DC_F32 || dst_dtype == DC_BF16, "dc_ingest_hwc: dst dtype must be fp32 or bf16");
+  DC_REQUIRE((reinterpret_cast<uintptr_t>(src) % 16) == 0 && (reinterpret_cast<uintptr_t>(dst) % 16) == 0 &&
+             (reinterpret_cast<uintptr_t>(shift) % 16) == 0 && (reinterpret_cast<uintptr_t>(scale) % 16) == 0,
+             "dc_ingest_hwc: pointers must be 16-byte aligned");
+  const long long nvec = npix * (C / 4);
+  const unsigned blocks = (unsigned)std::min<long long>((nvec + 255) / 256, (long long)kNumSMs * 8);
+  if (dst_dtype == DC_F32)
+    launch_k(ingest_hwc_kernel<float>, dim3(blocks), dim3(256), (size_t)0, as_stream(stream), src, shift, scale, (float*)dst, nvec, C / 4);
+  else
+    launch_k(ingest_hwc_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), (size_t)0, as_stream(stream), src, shift, scale, (__nv_bfloat16*)dst,
+             nvec, C / 4);
+  return launch_status("dc_ingest_hwc");
 }
 
 int dc_i64_increment_many(int64_t* const* ptrs, int count, void* stream) {

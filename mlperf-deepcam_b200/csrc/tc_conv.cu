@@ -1223,7 +1223,9 @@ int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, 
   const int n_co_tiles = ceil_div(dout.c, 128);
   const int tiles = n_co_tiles * p.n_ci_tiles * d->ntaps;
   // one CTA per SM (the stages fill the shared memory): split the pixel reduction so that the grid is one wave
-  int splits = std::max(1, std::min(p.mtiles_total, kNumSMs / std::max(1, tiles)));
+  static int split_div = -1;      // tuning knob (DEEPCAM_B200_WGRAD_SPLIT_DIV): divide the one-wave split count
+  if (split_div < 0) { const char* e = getenv("DEEPCAM_B200_WGRAD_SPLIT_DIV"); split_div = e ? std::max(1, atoi(e)) : 1; }
+  int splits = std::max(1, std::min(p.mtiles_total, kNumSMs / std::max(1, tiles) / split_div));
   p.mtiles_per_split = ceil_div(p.mtiles_total, splits);
   splits = ceil_div(p.mtiles_total, p.mtiles_per_split);
   p.vec_red = (in.c % 4 == 0 && (reinterpret_cast<uintptr_t>(G) % 16) == 0) ? 1 : 0;

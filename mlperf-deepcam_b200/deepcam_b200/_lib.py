@@ -53,6 +53,7 @@ SIGNATURES = {
     "dc_get_pdl": (c_int, []),
     "dc_copy_view": (c_int, [dc_view, dc_view, c_void_p]),
     "dc_fill_zero": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "dc_ingest_hwc": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "dc_i64_increment_many": (c_int, [c_void_p, c_int, c_void_p]),
     "dc_pack_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dc_pack_weights_multi": (c_int, [c_void_p, c_int, c_int, c_void_p]),
