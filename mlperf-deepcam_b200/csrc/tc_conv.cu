@@ -412,6 +412,9 @@ struct TcV2Cfg {
   int bm2;             // 256-row tiles: two M tiles (two accumulators) share every B tile -> 30 % fewer L2->SM bytes per FLOP;
                        // single accumulator set (no epilogue/main-loop overlap), used when one round covers the problem
   int real_mtiles;     // number of 128-row M tiles (n_mtiles counts 256-row super tiles when bm2)
+  int wide;            // N tile of 257..512 columns: two MMAs per k step (bn_sub0 + the rest) into ONE accumulator of BN TMEM
+  int bn_sub0;         // columns, B tile fetched as two TMA boxes of b_box_rows rows; used when it turns a two-round problem
+  int b_box_rows;      // (e.g. 54 M tiles x 728 columns) into one round over fewer, fatter CTAs
   int smem_bytes;
 };
 constexpr int kV2StagePitchF32 = 64 * 4 + 16;     // staged row: 64 fp32 columns + 16 B (odd multiple of 16 B: conflict-free)
@@ -429,8 +432,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
   const int STAGES = cfg.stages;
   const int BN = cfg.BN;
   const uint32_t bres_base = smem_base + STAGES * cfg.stage_bytes;
-  const uint32_t stg_off = STAGES * cfg.stage_bytes + cfg.bres_bytes;
-  const uint32_t bar_base = smem_base + stg_off + kV2StagingBytes;
+  // wide mode runs exactly one tile per CTA: the epilogue staging aliases pipeline stage 0 (all MMAs have completed, hence
+  // all stages have been consumed, before the first accumulator read), which buys a third pipeline stage
+  const uint32_t stg_off = cfg.wide ? 0u : (uint32_t)(STAGES * cfg.stage_bytes + cfg.bres_bytes);
+  const uint32_t bar_base = smem_base + STAGES * cfg.stage_bytes + cfg.bres_bytes + (cfg.wide ? 0u : (uint32_t)kV2StagingBytes);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
@@ -443,7 +448,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), cfg.bm2 ? 8 : 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), cfg.bm2 ? 8 : 4); }   // (wide: one accumulator, 4 epilogue warps)
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
@@ -496,7 +501,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
             const uint32_t sa = smem_base + s * cfg.stage_bytes;
             tma_load_4d(am, full_bar(s), sa, kb * 64, x0[0] + p.qw[t], y0[0] + p.qh[t], img[0]);
             if (cfg.bm2) tma_load_4d(am, full_bar(s), sa + kABytes, kb * 64, x0[1] + p.qw[t], y0[1] + p.qh[t], img[1]);
-            if (!cfg.b_resident) tma_load_2d(&maps.b, full_bar(s), sa + MT * kABytes, (kb0 + kb) * 64, n0);
+            if (!cfg.b_resident) {
+              tma_load_2d(&maps.b, full_bar(s), sa + MT * kABytes, (kb0 + kb) * 64, n0);
+              if (cfg.wide)
+                tma_load_2d(&maps.b, full_bar(s), sa + MT * kABytes + cfg.b_box_rows * 128, (kb0 + kb) * 64, n0 + cfg.b_box_rows);
+            }
             if (++s == STAGES) { s = 0; ph ^= 1u; }
           }
         }
@@ -504,15 +513,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, BN, 0, 0);
+      const uint32_t idesc = make_idesc(128, cfg.wide ? cfg.bn_sub0 : BN, 0, 0);
+      const uint32_t idesc1 = make_idesc(128, cfg.wide ? BN - cfg.bn_sub0 : 16, 0, 0);
+      const bool single_acc = cfg.bm2 || cfg.wide;
       if (cfg.b_resident) { mbar_wait(bres_bar, 0); tc_fence_after(); }
       int s = 0; uint32_t ph = 0;
       int i = 0;
       const int MT = cfg.bm2 ? 2 : 1;
       for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++i) {
         // bm2: one accumulator SET (two accumulators side by side); otherwise two alternating accumulators
-        const int buf = cfg.bm2 ? 0 : (i & 1);
-        const uint32_t par = cfg.bm2 ? ((uint32_t)i & 1u) : (((uint32_t)i >> 1) & 1u);
+        const int buf = single_acc ? 0 : (i & 1);
+        const uint32_t par = single_acc ? ((uint32_t)i & 1u) : (((uint32_t)i >> 1) & 1u);
         mbar_wait(tempty_bar(buf), par ^ 1u);                            // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * cfg.acc_stride);
@@ -528,6 +539,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
             const uint64_t db = make_smem_desc(sb, 16, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(acc, da + 2u * k, db + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            if (cfg.wide) {
+              // second N sub-tile: B rows bn_sub0.. of the same stage (row offset = bn_sub0 * 128 B, a multiple of 1024),
+              // accumulator columns bn_sub0..BN-1
+              const uint64_t db1 = db + (uint64_t)((cfg.bn_sub0 * 128) >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(acc + (uint32_t)cfg.bn_sub0, da + 2u * k, db1 + 2u * k, idesc1, (it > 0 || k > 0) ? 1u : 0u);
+            }
             if (cfg.bm2) {
               const uint64_t da1 = make_smem_desc(sa + kABytes, 16, 1024);
 #pragma unroll
@@ -569,9 +588,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
       const long long base = (long long)img * p.out.sn + (long long)oy * p.out.sh + (long long)ox * p.out.sw;
       const unsigned okmask = __ballot_sync(0xffffffffu, pix_ok);
       const int ncols = min(BN, p.out.c - n0);
-      const int buf = cfg.bm2 ? 0 : (i & 1);
+      const bool single_acc = cfg.bm2 || cfg.wide;
+      const int buf = single_acc ? 0 : (i & 1);
       if (sub == 0) {
-        mbar_wait(tfull_bar(buf), cfg.bm2 ? ((uint32_t)i & 1u) : (((uint32_t)i >> 1) & 1u));
+        mbar_wait(tfull_bar(buf), single_acc ? ((uint32_t)i & 1u) : (((uint32_t)i >> 1) & 1u));
         tc_fence_after();
       }
       const uint32_t acc = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((cfg.bm2 ? sub : buf) * cfg.acc_stride);
@@ -1066,13 +1086,20 @@ static TcV2Cfg pick_v2_cfg(int mtiles, int Co, int kblocks, int wtaps, bool tma_
   // one SM; add a fixed per-tile epilogue/drain cost.
   static int bm2_enabled = -1;
   if (bm2_enabled < 0) { const char* e = getenv("DEEPCAM_B200_TC_BM2"); bm2_enabled = (e && e[0] == '1') ? 1 : 0; }   // opt-in: measured slower in the full step (no epilogue overlap)
+  static int wide_enabled = -1;
+  if (wide_enabled < 0) { const char* e = getenv("DEEPCAM_B200_TC_WIDE"); wide_enabled = (e && e[0] == '0') ? 0 : 1; }
   for (int bm2 = 0; bm2 <= bm2_enabled; ++bm2) {
     if (bm2 && !tma_store) break;
     for (int nt = 1; nt <= 16; ++nt) {
       int bn = round_up_i(ceil_div(co16, nt), 16);
       // the TMA-store epilogue writes 64-column chunks: an N tile that is not the last one must be a multiple of 64
       if (tma_store && nt > 1) bn = round_up_i(bn, 64);
-      if (bn > 256) continue;
+      // N tiles of 257..512 columns ("wide": two MMAs per k step, one accumulator): only as a one-round configuration with
+      // the TMA-store epilogue, two B boxes per stage and at least two 2-box stages in shared memory
+      const bool wide = bn > 256;
+      if (wide && (!wide_enabled || bm2 || !tma_store || bn > 512 || bn % 64 != 0 ||
+                   (long long)mtiles * ceil_div(Co, bn) > kNumSMs || 2 * (kABytes + bn * 128) > 227 * 1024 - 1280))
+        continue;
       if (bn < 64 && co16 >= 64) break;
       const int ntiles = ceil_div(Co, bn);
       const int msup = bm2 ? ceil_div(mtiles, 2) : mtiles;
@@ -1093,16 +1120,19 @@ static TcV2Cfg pick_v2_cfg(int mtiles, int Co, int kblocks, int wtaps, bool tma_
   c.n_ntiles = ceil_div(Co, c.BN);
   c.total_tiles = c.n_mtiles * c.n_ntiles;
   c.tma_store = tma_store ? 1 : 0;
+  c.wide = c.BN > 256 ? 1 : 0;
+  c.bn_sub0 = c.wide ? (c.BN / 2 + 15) / 16 * 16 : c.BN;       // 384 -> 192 + 192, 320 -> 160 + 160, 448 -> 224 + 224
+  c.b_box_rows = c.wide ? c.BN / 2 : c.BN;                      // BN % 64 == 0 -> a multiple of 8 rows: 1024-byte aligned boxes
   c.acc_stride = 32;
   while (c.acc_stride < c.BN) c.acc_stride <<= 1;
-  c.tmem_cols = 2 * c.acc_stride;
-  const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - kV2StagingBytes;
+  c.tmem_cols = c.wide ? c.acc_stride : 2 * c.acc_stride;
+  const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - (c.wide ? 0 : kV2StagingBytes);
   c.bres_bytes = wtaps * kblocks * c.BN * 128;
-  c.b_resident = (!c.bm2 && c.n_ntiles == 1 && c.bres_bytes <= 128 * 1024 && c.bres_bytes + 3 * kABytes <= budget) ? 1 : 0;
+  c.b_resident = (!c.bm2 && !c.wide && c.n_ntiles == 1 && c.bres_bytes <= 128 * 1024 && c.bres_bytes + 3 * kABytes <= budget) ? 1 : 0;
   if (!c.b_resident) c.bres_bytes = 0;
   c.stage_bytes = (c.bm2 ? 2 : 1) * kABytes + (c.b_resident ? 0 : c.BN * 128);
   c.stages = std::max(2, std::min(8, (budget - c.bres_bytes) / c.stage_bytes));
-  c.smem_bytes = c.stages * c.stage_bytes + c.bres_bytes + kV2StagingBytes + 1024 + 256;
+  c.smem_bytes = c.stages * c.stage_bytes + c.bres_bytes + (c.wide ? 0 : kV2StagingBytes) + 1024 + 256;
   return c;
 }
 
@@ -1171,7 +1201,7 @@ static int conv_gemm_tc_impl(const dc_conv_desc* d, dc_view in, const void* w, c
   if (!use_v1_kernel()) {
     const bool tma_store = p.out_vec_ok != 0;
     const TcV2Cfg c2 = pick_v2_cfg(mtiles, out.c, p.kblocks, d->wtaps, tma_store);
-    if (int r = encode_weight_map(&maps.b, w, Ktot, out.c, c2.BN, "dc_conv_gemm_tc")) return r;
+    if (int r = encode_weight_map(&maps.b, w, Ktot, out.c, c2.b_box_rows, "dc_conv_gemm_tc")) return r;
     if (tma_store) {
       if (int r = encode_act_map(&maps.c, out.ptr, out.c, out.w, out.h, out.n, out.sw, out.sh, out.sn, p.TW, p.TH, "dc_conv_gemm_tc(out)"))
         return r;
