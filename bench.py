@@ -325,6 +325,18 @@ def run_ours(args):
         tensor_kinds = ("conv_gemm_tc", "conv_wgrad_tc", "conv_gemm_simt", "conv_wgrad_simt")
         top = max(classes.items(), key=lambda kv: kv[1]["ms"])
         name, d = top
+        # the dominant kernel = the (kernel, layer shape) with the largest time inside the dominant class; its DRAM traffic
+        # per launch comes from the committed ncu --set full capture of the same shape (profiles/ncu_traffic.json)
+        shapes_top = prof.by_tag({name})
+        shape_name, shape_d = max(shapes_top.items(), key=lambda kv: kv[1]["ms"])
+        traffic = None
+        try:
+            with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as fh:
+                ent = json.load(fh).get(shape_name.replace(" +bnstats", ""))
+            if ent:
+                traffic = ent["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
         sec = d["ms"] / 1000.0
         if name in tensor_kinds:
             ach = d["flops"] / sec / 1e12
@@ -334,6 +346,16 @@ def run_ours(args):
             ach = d["bytes"] / sec / 1e9
             roofline = dict(kernel=name, bound="hbm", achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"],
                             traffic=None)
+        ssec = shape_d["ms"] / 1000.0
+        roofline["traffic"] = traffic
+        roofline["dominant_shape"] = dict(
+            kernel=shape_name, launches_per_step=shape_d["launches"] / psteps, us_per_launch=1000.0 * shape_d["ms"] / shape_d["launches"],
+            algorithmic_bytes_per_launch=shape_d["bytes"] / shape_d["launches"],
+            algorithmic_flops_per_launch=shape_d["flops"] / shape_d["launches"],
+            achieved_tflops=shape_d["flops"] / ssec / 1e12 if ssec > 0 else None,
+            achieved_gbs=shape_d["bytes"] / ssec / 1e9 if ssec > 0 else None,
+            traffic_note="`traffic` = dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this shape "
+                         "(cold caches; written lines still in L2 at kernel end are not counted by the counter)")
         roofline.update(peak_source=peaks["source"] + (" sustained" if name in tensor_kinds else " copy"),
                         launches_per_step=d["launches"] / psteps, avg_launch_us=1000.0 * d["ms"] / d["launches"],
                         class_ms_per_step=d["ms"] / psteps,
