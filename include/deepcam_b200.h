@@ -246,6 +246,12 @@ typedef struct dc_adam_job {
 } dc_adam_job;
 int dc_adam_step_multi(const dc_adam_job* jobs_dev, int njobs, int total_blocks, double lr, double beta1, double beta2,
                        double eps, double weight_decay, double bias_c1, double bias_c2, int adamw, void* stream);
+/* LAMB step for all parameters (apex.optimizers.FusedLAMB as constructed at TR:217-218; algorithm of apex's
+ * multi_tensor_lamb.cu: global gradient-norm clipping, Adam moments, per-tensor trust ratio).  Same job table as
+ * dc_adam_step_multi; the update is written over the gradient; norms = device scratch of 1 + 2*njobs doubles. */
+int dc_lamb_step_multi(const dc_adam_job* jobs_dev, int njobs, int total_blocks, double lr, double beta1, double beta2,
+                       double eps, double weight_decay, double bias_c1, double bias_c2, int adam_w_mode,
+                       int grad_averaging, double max_grad_norm, int use_nvlamb, double* norms, void* stream);
 
 #ifdef __cplusplus
 }

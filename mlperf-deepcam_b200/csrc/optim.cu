@@ -60,9 +60,116 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const dc_adam_job* __re
   }
 }
 
+// ---- LAMB (the optimizer of the reference's DGX recipe: apex.optimizers.FusedLAMB at TR:217-218) ----------------------
+// apex is not vendored in the reference tree; this follows its published algorithm (apex/optimizers/fused_lamb.py,
+// csrc/multi_tensor_lamb.cu): global gradient-norm clipping, Adam moments on the clipped gradient, per-tensor trust ratio
+// ||p|| / ||update||.  Three launches for all parameters: gradient norm; moments + update (written over the gradient, as
+// apex does) + per-tensor norms; parameter update.  norms = double[1 + 2 * njobs]: [0] sum g^2, [1 + 2i] sum p_i^2,
+// [2 + 2i] sum update_i^2 (zeroed by the caller).
+__device__ __forceinline__ int find_job(const dc_adam_job* __restrict__ jobs, int njobs, int b) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block_start <= b) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+__device__ __forceinline__ void block_add(double v, double* dst) {
+  __shared__ double s_part[8];
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_part[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_part[w];
+    atomicAdd(dst, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) lamb_grad_norm_kernel(const dc_adam_job* __restrict__ jobs, int njobs, double* norms) {
+  pdl_sync();
+  const int ji = find_job(jobs, njobs, blockIdx.x);
+  const dc_adam_job j = jobs[ji];
+  const long long stride = (long long)j.n_blocks * 256;
+  double acc = 0.0;
+  for (long long i = (long long)(blockIdx.x - j.block_start) * 256 + threadIdx.x; i < j.numel; i += stride) {
+    const float g = j.g[i];
+    acc += (double)g * (double)g;
+  }
+  block_add(acc, norms);
+}
+
+struct LambScalars {
+  float beta1, beta2, beta3, inv_bc1, inv_bc2, eps, decay, max_grad_norm;
+  int adam_w_mode;
+};
+__global__ void __launch_bounds__(256) lamb_stage1_kernel(const dc_adam_job* __restrict__ jobs, int njobs, LambScalars a, double* norms) {
+  pdl_sync();
+  const int ji = find_job(jobs, njobs, blockIdx.x);
+  const dc_adam_job j = jobs[ji];
+  const float gnorm = (float)sqrt(norms[0]);
+  const float clip = (a.max_grad_norm > 0.f && gnorm > a.max_grad_norm) ? gnorm / a.max_grad_norm : 1.f;
+  const long long stride = (long long)j.n_blocks * 256;
+  double pn = 0.0, un = 0.0;
+  for (long long i = (long long)(blockIdx.x - j.block_start) * 256 + threadIdx.x; i < j.numel; i += stride) {
+    const float p = j.p[i];
+    float g = j.g[i] / clip;
+    if (!a.adam_w_mode) g = g + a.decay * p;                       // L2 mode: decay enters the moments
+    const float m = j.m[i] * a.beta1 + a.beta3 * g;
+    const float v = j.v[i] * a.beta2 + (1.f - a.beta2) * g * g;
+    j.m[i] = m;
+    j.v[i] = v;
+    const float denom = sqrtf(v * a.inv_bc2) + a.eps;
+    float u = (m * a.inv_bc1) / denom;
+    if (a.adam_w_mode) u = u + a.decay * p;
+    const_cast<float*>(j.g)[i] = u;                                  // the update replaces the gradient (stage 2 reads it)
+    pn += (double)p * (double)p;
+    un += (double)u * (double)u;
+  }
+  block_add(pn, norms + 1 + 2 * ji);
+  block_add(un, norms + 2 + 2 * ji);
+}
+__global__ void __launch_bounds__(256) lamb_stage2_kernel(const dc_adam_job* __restrict__ jobs, int njobs, float lr, int use_ratio,
+                                                          const double* __restrict__ norms) {
+  pdl_sync();
+  const int ji = find_job(jobs, njobs, blockIdx.x);
+  const dc_adam_job j = jobs[ji];
+  float ratio = lr;
+  if (use_ratio) {
+    const float pn = (float)sqrt(norms[1 + 2 * ji]), un = (float)sqrt(norms[2 + 2 * ji]);
+    if (pn != 0.f && un != 0.f) ratio = lr * (pn / un);
+  }
+  const long long stride = (long long)j.n_blocks * 256;
+  for (long long i = (long long)(blockIdx.x - j.block_start) * 256 + threadIdx.x; i < j.numel; i += stride)
+    j.p[i] = j.p[i] - ratio * j.g[i];
+}
+
 }  // namespace dc
 
 using namespace dc;
+
+extern "C" int dc_lamb_step_multi(const dc_adam_job* jobs_dev, int njobs, int total_blocks, double lr, double beta1, double beta2,
+                                  double eps, double weight_decay, double bias_c1, double bias_c2, int adam_w_mode,
+                                  int grad_averaging, double max_grad_norm, int use_nvlamb, double* norms, void* stream) {
+  DC_REQUIRE(jobs_dev != nullptr && njobs > 0 && total_blocks > 0 && norms != nullptr, "dc_lamb_step_multi: bad arguments");
+  DC_REQUIRE(bias_c1 > 0.0 && bias_c2 > 0.0, "dc_lamb_step_multi: bias corrections must be positive");
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(norms, 0, sizeof(double) * (size_t)(1 + 2 * njobs), st);
+  if (e != cudaSuccess) return dc::fail((int)e, "dc_lamb_step_multi: %s", cudaGetErrorString(e));
+  LambScalars a;
+  a.beta1 = (float)beta1; a.beta2 = (float)beta2;
+  a.beta3 = grad_averaging ? (float)(1.0 - beta1) : 1.f;
+  a.inv_bc1 = (float)(1.0 / bias_c1); a.inv_bc2 = (float)(1.0 / bias_c2);
+  a.eps = (float)eps; a.decay = (float)weight_decay; a.max_grad_norm = (float)max_grad_norm;
+  a.adam_w_mode = adam_w_mode;
+  launch_k(lamb_grad_norm_kernel, dim3(total_blocks), dim3(256), (size_t)0, st, jobs_dev, njobs, norms);
+  launch_k(lamb_stage1_kernel, dim3(total_blocks), dim3(256), (size_t)0, st, jobs_dev, njobs, a, norms);
+  launch_k(lamb_stage2_kernel, dim3(total_blocks), dim3(256), (size_t)0, st, jobs_dev, njobs, (float)lr,
+           (use_nvlamb || weight_decay != 0.0) ? 1 : 0, (const double*)norms);
+  return launch_status("dc_lamb_step_multi");
+}
 
 extern "C" int dc_adam_step_multi(const dc_adam_job* jobs_dev, int njobs, int total_blocks, double lr, double beta1, double beta2,
                                   double eps, double weight_decay, double bias_c1, double bias_c2, int adamw, void* stream) {

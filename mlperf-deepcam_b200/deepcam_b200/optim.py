@@ -1,4 +1,4 @@
-"""Fused multi-tensor Adam / AdamW for the deepcam_b200 modules.
+"""Fused multi-tensor Adam / AdamW / LAMB for the deepcam_b200 modules.
 
 Drop-in for `torch.optim.Adam(params, lr, betas, eps, weight_decay)` / `torch.optim.AdamW` as the reference constructs
 them (TR:213-220): same constructor arguments, same `param_groups`, same per-parameter state (`step`, `exp_avg`,
@@ -92,3 +92,64 @@ class FusedAdamW(_FusedAdamBase):
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False):
         super().__init__(params, lr, betas, eps, weight_decay, amsgrad)
+
+
+class FusedLAMB(torch.optim.Optimizer):
+    """Drop-in for `apex.optimizers.FusedLAMB(params, lr, eps, weight_decay)` as the reference constructs it for
+    `--optimizer LAMB` (TR:217-218; apex is absent from this image, so the reference cannot take that branch here).
+    Same constructor arguments and defaults as apex (bias_correction, betas, eps=1e-6, weight_decay=0.01, adam_w_mode,
+    grad_averaging, max_grad_norm=1.0, use_nvlamb), same state layout (`exp_avg`, `exp_avg_sq` per parameter, `step` per
+    group).  One step = three sm_100a launches for all parameters (csrc/optim.cu: gradient norm, moments + update + per-tensor
+    norms, trust-ratio update).  Like apex, the step overwrites `.grad` with the update."""
+
+    def __init__(self, params, lr=1e-3, bias_correction=True, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.01, amsgrad=False,
+                 adam_w_mode=True, grad_averaging=True, set_grad_none=True, max_grad_norm=1.0, use_nvlamb=False):
+        if amsgrad:
+            raise RuntimeError("FusedLAMB does not support the AMSGrad variant.")
+        super().__init__(params, dict(lr=lr, bias_correction=bias_correction, betas=betas, eps=eps, weight_decay=weight_decay,
+                                      grad_averaging=grad_averaging, max_grad_norm=max_grad_norm))
+        self.adam_w_mode = 1 if adam_w_mode else 0
+        self.set_grad_none = set_grad_none
+        self.use_nvlamb = use_nvlamb
+        self._tables = {}
+
+    def zero_grad(self, set_to_none=None):
+        super().zero_grad(set_to_none=self.set_grad_none if set_to_none is None else set_to_none)
+
+    _table = _FusedAdamBase._table
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        # apex clips by the norm over ALL groups; with one group (the reference's case) that is the group's own norm
+        if len([g for g in self.param_groups if any(p.grad is not None for p in g["params"])]) > 1:
+            raise NotImplementedError("deepcam_b200 FusedLAMB: a single parameter group is supported (as in TR:217-218)")
+        for gi, group in enumerate(self.param_groups):
+            plist = [p for p in group["params"] if p.grad is not None]
+            if not plist:
+                continue
+            for p in plist:
+                if not p.is_cuda or p.dtype != torch.float32 or p.grad.dtype != torch.float32:
+                    raise RuntimeError("deepcam_b200 FusedLAMB needs fp32 CUDA parameters and gradients (no CPU fallback)")
+                if p.grad.is_sparse or not p.is_contiguous() or not p.grad.is_contiguous():
+                    raise RuntimeError("deepcam_b200 FusedLAMB needs dense contiguous parameters and gradients")
+                st = self.state[p]
+                if len(st) == 0:
+                    st["exp_avg"] = torch.zeros_like(p)
+                    st["exp_avg_sq"] = torch.zeros_like(p)
+            group["step"] = group.get("step", 0) + 1
+            t = group["step"]
+            b1, b2 = group["betas"]
+            bc1 = 1.0 - math.pow(b1, t) if group["bias_correction"] else 1.0
+            bc2 = 1.0 - math.pow(b2, t) if group["bias_correction"] else 1.0
+            table, njobs, blocks = self._table(gi, plist)
+            norms = torch.empty(1 + 2 * njobs, dtype=torch.float64, device=plist[0].device)
+            _lib.check(_lib.load().dc_lamb_step_multi(
+                ctypes.c_void_p(table.data_ptr()), njobs, blocks, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                float(group["weight_decay"]), bc1, bc2, self.adam_w_mode, int(bool(group["grad_averaging"])),
+                float(group["max_grad_norm"] or 0.0), int(bool(self.use_nvlamb)), ctypes.c_void_p(norms.data_ptr()),
+                ops._stream()), "dc_lamb_step_multi")
+        return loss

@@ -579,3 +579,58 @@ def test_depthwise_backward_fused_with_batchnorm_reduction(dtype, C, H, W, use_r
     assert rel(dy1, dy0) < tol and rel(dg1, dg0) < tol and rel(db1, db0) < tol
     if use_res:
         assert rel(dres1, dres0) < tol
+
+
+def _lamb_reference_step(params, grads, state, step, lr, betas, eps, wd, max_grad_norm=1.0, adam_w_mode=True,
+                         grad_averaging=True, bias_correction=True, use_nvlamb=False):
+    """Plain-torch restatement (float64) of apex FusedLAMB's step (apex/optimizers/fused_lamb.py + multi_tensor_lamb.cu):
+    apex itself is not installable here, so LAMB parity is against its published algorithm ("parity unpinned")."""
+    b1, b2 = betas
+    gnorm = torch.sqrt(sum((g.double() ** 2).sum() for g in grads))
+    clip = gnorm / max_grad_norm if (max_grad_norm > 0 and gnorm > max_grad_norm) else 1.0
+    b3 = 1 - b1 if grad_averaging else 1.0
+    bc1 = 1 - b1 ** step if bias_correction else 1.0
+    bc2 = 1 - b2 ** step if bias_correction else 1.0
+    out = []
+    for p, g, (m, v) in zip(params, grads, state):
+        p64, g64 = p.double(), g.double() / clip
+        if not adam_w_mode:
+            g64 = g64 + wd * p64
+        m.mul_(b1).add_(b3 * g64)
+        v.mul_(b2).add_((1 - b2) * g64 * g64)
+        u = (m / bc1) / (torch.sqrt(v / bc2) + eps)
+        if adam_w_mode:
+            u = u + wd * p64
+        pn, un = p64.norm(), u.norm()
+        ratio = lr
+        if (use_nvlamb or wd != 0) and pn != 0 and un != 0:
+            ratio = lr * (pn / un)
+        out.append(p64 - ratio * u)
+    return out
+
+
+@pytest.mark.parametrize("adam_w_mode,wd,max_norm", [(True, 0.01, 1.0), (False, 0.01, 1.0), (True, 0.0, 0.0), (True, 1e-6, 1e9)])
+def test_fused_lamb_matches_published_algorithm(adam_w_mode, wd, max_norm):
+    from deepcam_b200.optim import FusedLAMB
+    torch.manual_seed(5)
+    shapes = [(728, 728, 1, 1), (7,), (256, 3, 3, 3), (1,), (33, 5)]
+    my_p = [torch.nn.Parameter(torch.randn(s, device=dev())) for s in shapes]
+    ref_p = [p.detach().clone() for p in my_p]
+    state = [(torch.zeros_like(p, dtype=torch.float64), torch.zeros_like(p, dtype=torch.float64)) for p in ref_p]
+    opt = FusedLAMB(my_p, lr=2e-3, eps=1e-6, weight_decay=wd, adam_w_mode=adam_w_mode, max_grad_norm=max_norm)
+    for step in range(1, 5):
+        grads = [torch.randn_like(p) * (3.0 if step % 2 else 0.01) for p in my_p]
+        for p, g in zip(my_p, grads):
+            p.grad = g.clone()
+        new = _lamb_reference_step(ref_p, grads, state, step, 2e-3, (0.9, 0.999), 1e-6, wd, max_norm, adam_w_mode)
+        opt.step()
+        torch.cuda.synchronize()
+        for i, (p, r) in enumerate(zip(my_p, new)):
+            assert rel(p, r) < 2e-6, (step, i)
+            ref_p[i] = r.float()
+            with torch.no_grad():
+                p.copy_(ref_p[i])                 # keep both trajectories on identical fp32 parameters
+    sd = opt.state_dict()
+    assert sd["param_groups"][0]["step"] == 4 and set(sd["state"][0]) == {"exp_avg", "exp_avg_sq"}
+    opt.zero_grad()
+    assert all(p.grad is None for p in my_p)
