@@ -219,3 +219,50 @@ def test_cuda_graph_plan_rejects_stale_backward(sd, monkeypatch):
     with pytest.raises(RuntimeError, match="must follow the forward"):
         out1.sum().backward()
     out2.sum().backward()
+
+
+def test_full_size_step_properties(sd):
+    """BASELINE.json's full size (2 x 16 x 768 x 1152, bf16, CUDA-graph plans) through size-independent properties, since the
+    CPU oracle needs ~40 s per step there:
+      * the first BatchNorm's running statistics equal 0.9*old + 0.1*batch statistics of conv1's output, recomputed here
+        with a plain torch fp32 convolution on the same bf16-rounded input/weights (checks the GEMM-epilogue statistics at
+        442 k pixels per channel);
+      * a replayed step reproduces the eagerly executed first step (same input, same weights): loss within 1e-3;
+      * IoU counters are a consistent confusion summary: tp+fn = label histogram, tp+fp = prediction histogram (exact);
+      * every parameter gradient is finite and the loss is within 2e-2 of ln(3)-scale weighted CE sanity bounds."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    net = _make(sd, "bf16").train()
+    x, label = O.synthetic_batch(2, 768, 1152, seed=77)
+    xd, ld = x.to(DEV), label.to(DEV)
+    w = O.class_weights()
+    rm0 = net.xception_features.bn1.running_mean.clone()
+    rv0 = net.xception_features.bn1.running_var.clone()
+    losses_seen = []
+    for it in range(3):                      # call 1 eager, call 2 captures, call 3 replays
+        out = net(xd)
+        loss = losses.fp_loss(out, ld, weight=w, fpw_1=w[1], fpw_2=w[2])
+        net.zero_grad()
+        loss.backward()
+        losses_seen.append(float(loss))
+        if it == 0:
+            conv1 = net.xception_features.conv1
+            y = F.conv2d(xd.bfloat16().float(), conv1.weight.detach().bfloat16().float(), None, 2, 1).bfloat16().float()
+            mean, var = y.mean((0, 2, 3)), y.var((0, 2, 3), unbiased=True)
+            rm, rv = net.xception_features.bn1.running_mean, net.xception_features.bn1.running_var
+            assert torch.allclose(rm, 0.9 * rm0 + 0.1 * mean, rtol=2e-3, atol=2e-4)
+            assert torch.allclose(rv, 0.9 * rv0 + 0.1 * var, rtol=5e-3, atol=1e-5)
+        assert all(bool(torch.isfinite(p.grad).all()) for p in net.parameters())
+    # no optimizer step in between: the three executions see identical weights (running statistics do not enter train mode)
+    assert max(losses_seen) - min(losses_seen) < 1e-3, losses_seen
+    assert 0.0 < losses_seen[0] < 5.0
+    pred = torch.max(out, 1)[1]
+    counts = torch.zeros(9, dtype=torch.int64, device=DEV)
+    from deepcam_b200 import ops
+    ops.iou_counts(pred, ld, 3, counts)
+    tp, fp, fn = counts[0:3], counts[3:6], counts[6:9]
+    assert torch.equal(tp + fn, torch.bincount(ld.flatten(), minlength=3))
+    assert torch.equal(tp + fp, torch.bincount(pred.flatten(), minlength=3))
+    score = dcutils.compute_score(pred, ld, num_classes=3, device_id=0)
+    iou = [(float(tp[j]) / float(tp[j] + fp[j] + fn[j])) if int(tp[j] + fp[j] + fn[j]) else 1.0 for j in range(3)]
+    assert abs(float(score) - sum(iou) / 3.0) < 1e-6
