@@ -382,6 +382,21 @@ __device__ __forceinline__ void pack_job_rows(const dc_pack_job& j, int local_bl
 
 // (b) source [k][n][taps] -> destination [n][tap][k_pad] (dgrad role of a Conv2d, fprop role of a ConvTranspose2d): a work
 //     item is 64 k x TN n (TN*taps <= 72 floats per k row, contiguous in the source); the destination gets runs of 64 k.
+// 8 consecutive destination elements (k run) as one 16-byte (bf16) / two 16-byte (fp32) stores
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+    w[q] = *reinterpret_cast<uint32_t*>(&b);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 template <typename TD, int TAPS>
 __device__ __forceinline__ void pack_job_transpose(const dc_pack_job& j, int local_block, int tid, float* sm) {
   const int taps = TAPS ? TAPS : j.taps;
@@ -392,24 +407,53 @@ __device__ __forceinline__ void pack_job_transpose(const dc_pack_job& j, int loc
   const int ntiles = kt * ntl;
   const float* __restrict__ src = j.src;
   TD* __restrict__ dst = reinterpret_cast<TD*>(j.dst);
+  const long long krow = (long long)j.N * taps;
+  // 16-byte source loads need 4-float alignment of every k row segment; 16-byte destination stores need K_pad % 8 == 0
+  const bool vec_src = (RW % 4 == 0) && (krow % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  const bool vec_dst = (j.K_pad % 8 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+  const int RW4 = RW >> 2;
   for (int tl = local_block; tl < ntiles; tl += j.n_blocks) {
     const int ktile = tl / ntl;
     const int k0 = ktile << 6, n0 = (tl - ktile * ntl) * TN;
     const int rw_valid = max(0, min(RW, (j.N - n0) * taps));
     const float* sp = src + ((long long)k0 * j.N + n0) * taps;
-    const long long krow = (long long)j.N * taps;
-    for (int e = tid; e < 64 * RW; e += 256) {
-      const int k = e / RW, r = e - k * RW;
-      float v = 0.f;
-      if (k0 + k < j.K && r < rw_valid) v = sp[k * krow + r];
-      sm[k * pitch + r] = v;
+    if (vec_src && rw_valid == RW && ((n0 * taps) & 3) == 0) {
+      for (int e = tid; e < 64 * RW4; e += 256) {
+        const int k = e / RW4, r = (e - k * RW4) << 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + k < j.K) v = *reinterpret_cast<const float4*>(sp + k * krow + r);
+        float* d = sm + k * pitch + r;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    } else {
+      for (int e = tid; e < 64 * RW; e += 256) {
+        const int k = e / RW, r = e - k * RW;
+        float v = 0.f;
+        if (k0 + k < j.K && r < rw_valid) v = sp[k * krow + r];
+        sm[k * pitch + r] = v;
+      }
     }
     __syncthreads();
-    for (int e = tid; e < 64 * RW; e += 256) {
-      const int kk = e & 63, row = e >> 6;      // row = n_local * taps + t
-      const int nl = row / taps, t = row - nl * taps;
-      if (n0 + nl < j.N_pad && k0 + kk < j.K_pad)
-        elem<TD>::st(dst + ((long long)(n0 + nl) * taps + t) * j.K_pad + k0 + kk, sm[kk * pitch + row]);
+    if (vec_dst) {
+      // 8 k per thread: 8 rows (n, tap) x 8 k-groups per pass of 64 threads
+      for (int e = tid; e < 8 * RW; e += 256) {
+        const int kg = e & 7, row = e >> 3;       // row = n_local * taps + t
+        const int nl = row / taps, t = row - nl * taps;
+        const int kk = kg << 3;
+        if (n0 + nl < j.N_pad && k0 + kk < j.K_pad) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = sm[(kk + q) * pitch + row];
+          st8(dst + ((long long)(n0 + nl) * taps + t) * j.K_pad + k0 + kk, v);
+        }
+      }
+    } else {
+      for (int e = tid; e < 64 * RW; e += 256) {
+        const int kk = e & 63, row = e >> 6;
+        const int nl = row / taps, t = row - nl * taps;
+        if (n0 + nl < j.N_pad && k0 + kk < j.K_pad)
+          elem<TD>::st(dst + ((long long)(n0 + nl) * taps + t) * j.K_pad + k0 + kk, sm[kk * pitch + row]);
+      }
     }
     __syncthreads();
   }

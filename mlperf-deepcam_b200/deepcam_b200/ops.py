@@ -173,6 +173,12 @@ def pack_weight(src, K, N, taps, src_k_first, layout, K_pad, N_pad, dtype, out=N
     return out
 
 
+# blocks per pack job: every block first finds its job (a chain of dependent table reads), so a block must own enough work
+# to amortise that; sweep knobs for tools/kbench.py --only pack
+_PACK_MAX_BLOCKS = int(_os.environ.get("DEEPCAM_B200_PACK_MAX_BLOCKS", "128"))
+_PACK_ELEMS_PER_BLOCK = int(_os.environ.get("DEEPCAM_B200_PACK_ELEMS_PER_BLOCK", "2048"))
+
+
 def build_pack_table(jobs, device):
     """jobs: list of (src fp32 tensor, dst tensor, K, N, taps, src_k_first, layout, K_pad, N_pad).  Returns the device job
     table (uint8 tensor; keep it alive), the number of jobs and the grid size for pack_weights_multi."""
@@ -181,7 +187,7 @@ def build_pack_table(jobs, device):
     for i, (src, dst, K, N, taps, skf, layout, K_pad, N_pad) in enumerate(jobs):
         total = taps * K_pad * N_pad
         assert total < 2 ** 31 and src.dtype == torch.float32 and src.is_contiguous() and dst.numel() == total
-        nb = max(1, min(128, (total + 2047) // 2048))
+        nb = max(1, min(_PACK_MAX_BLOCKS, (total + _PACK_ELEMS_PER_BLOCK - 1) // _PACK_ELEMS_PER_BLOCK))
         j = arr[i]
         j.src, j.dst = src.data_ptr(), dst.data_ptr()
         j.K, j.N, j.taps, j.src_k_first = K, N, taps, int(skf)

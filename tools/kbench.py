@@ -92,6 +92,20 @@ def main():
         add("conv_dgrad " + tag, lambda dyc=dyc, cs=cs, dx=dx: be.conv_bwd_data(dyc, cs, dx, False), nb, fl)
         add("conv_wgrad " + tag, lambda x=x, dyc=dyc, cs=cs, gw=gw: be.conv_bwd_weight(x, dyc, cs, gw), nb, fl)
 
+    if not args.only or "pack" in args.only:
+        # all weight packs of the real network in one launch (what the forward graph starts with)
+        from architecture import deeplab_xception as dx
+        from deepcam_b200 import ops
+        from deepcam_b200.backend import pack_jobs_of
+        net = dx.DeepLabv3_plus(16, 3, 16, _print=False).to(dev).train()
+        xs = torch.rand(2, 16, 768, 1152, device=dev)      # full size: every layer takes the tcgen05 (NTK pack) path
+        net(xs).sum().backward()                       # eager call: creates every kernel-layout weight copy
+        jobs = pack_jobs_of(net)
+        table = ops.build_pack_table(jobs, dev)
+        src_b = sum(j[0].numel() * 4 for j in jobs)
+        dst_b = sum(j[1].numel() * j[1].element_size() for j in jobs)
+        add("pack_weights_multi (%d jobs)" % len(jobs), lambda table=table: ops.pack_weights_multi(*table), float(src_b + dst_b))
+
     results = {}
     for name, fn, nbytes, flops in cases:
         fn()
