@@ -92,6 +92,25 @@ def main():
         add("conv_dgrad " + tag, lambda dyc=dyc, cs=cs, dx=dx: be.conv_bwd_data(dyc, cs, dx, False), nb, fl)
         add("conv_wgrad " + tag, lambda x=x, dyc=dyc, cs=cs, gw=gw: be.conv_bwd_weight(x, dyc, cs, gw), nb, fl)
 
+    # small-channel layers of the entry flow / last deconv (K or N far below a tensor-core tile)
+    for (n, h, w, ci, co, k, stride, transposed, name) in [(2, 768, 1152, 16, 32, 3, 2, False, "conv1"), (2, 384, 576, 32, 64, 3, 1, False, "conv2"),
+                                                           (2, 384, 576, 256, 3, 3, 2, True, "last_deconv")]:
+        tag = "%s %dx%dx%d %d->%d k%d s%d" % (name, n, h, w, ci, co, k, stride)
+        x = rnd(n, h, w, ci)
+        if transposed:
+            wt = torch.nn.Parameter(torch.randn(ci, co, k, k, device=dev) * 0.05)
+            cs = ConvSpec("c", wt, None, stride, 1, 1, True)
+            ho, wo = h * 2, w * 2
+            out = torch.empty(n, ho, wo, 8, device=dev, dtype=torch.float32)
+        else:
+            wt = torch.nn.Parameter(torch.randn(co, ci, k, k, device=dev) * 0.05)
+            cs = ConvSpec("c", wt, None, stride, 1, 1)
+            ho, wo = cs.out_hw(h, w)
+            out = torch.empty(n, ho, wo, co, device=dev, dtype=bf)
+        fl = 2.0 * n * (h if transposed else ho) * (w if transposed else wo) * ci * co * k * k
+        nb = x.numel() * 2.0 + out.numel() * out.element_size() + wt.numel() * 2.0
+        add("small_fprop " + tag, lambda x=x, cs=cs, out=out: be.conv_fwd(x, cs, out), nb, fl)
+
     if not args.only or "pack" in args.only:
         # all weight packs of the real network in one launch (what the forward graph starts with)
         from architecture import deeplab_xception as dx
