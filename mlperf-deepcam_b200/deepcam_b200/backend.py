@@ -122,6 +122,7 @@ class CudaBackend:
         # BatchNorm backward reduction (+ ReLU mask) inside the depthwise backward-data kernel that produces the gradient
         self.fuse_bn_bwd = os.environ.get("DEEPCAM_B200_FUSE_BN_BWD", "1") not in ("0", "false", "")
         self.fuse_bn_bwd_max_bytes = int(os.environ.get("DEEPCAM_B200_FUSE_BN_BWD_MAX_BYTES", str(24 << 20)))
+        self.fuse_bn_bwd_res = os.environ.get("DEEPCAM_B200_FUSE_BN_BWD_RES", "1") not in ("0", "false", "")
         self.side_stream = None       # set by a graph plan: weight-gradient kernels run on a parallel graph branch
         self._side_dirty = False
 
@@ -358,10 +359,11 @@ class CudaBackend:
         BatchNorm backward sums in a fresh workspace, which is returned (None: not applicable, nothing was launched)."""
         if not self.fuse_bn_bwd or spec.stride != 1 or spec.dil != 1:
             return None
-        # measured on B200: a win for the L2-resident tensors without a residual (one wave of 270 blocks replaces the
-        # one-pass barrier kernel); residual layers need two more staged tiles (two waves) and on the large tensors the
-        # per-block fp64 atomics outweigh the saved reduction pass, so those keep the separate kernels
-        if not force and (act is not None or dx.numel() * dx.element_size() > self.fuse_bn_bwd_max_bytes):
+        # measured on B200: a win for the L2-resident tensors (replaces the one-pass barrier kernel; residual layers stage two
+        # more tiles and run two waves, still 13.58 vs 13.66 ms/step); on the large tensors the per-block fp64 atomics outweigh
+        # the saved reduction pass, so those keep the separate kernels
+        if not force and ((act is not None and not self.fuse_bn_bwd_res) or
+                          dx.numel() * dx.element_size() > self.fuse_bn_bwd_max_bytes):
             return None
         rws = self.scratch(ops.bn_ws_elems(dx.shape[3]), torch.float64, zero=True)
         if not ops.dw_bwd_data_bnred(dy, self._dw_packed(spec), dx, accumulate, y, act, fwd_sums, rws, relu):
