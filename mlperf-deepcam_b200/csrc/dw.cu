@@ -858,7 +858,10 @@ static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d,
   constexpr int V = dwvec<T>::V;
   // (a shared-memory staged variant was measured slower here: with one tile per block the 9*C atomics per block dominate;
   //  the register-pipelined kernels keep long strips per block and reduce once)
-  DwMap m = dw_map(dout.c, V, dout.h, dout.w, dout.n, kNumSMs * 2, 12);
+  static int tb_mult = -1, min_rows = -1;   // sweep knobs: DEEPCAM_B200_DWW_BLOCKS_PER_SM, DEEPCAM_B200_DWW_MIN_ROWS
+  if (tb_mult < 0) { const char* e = getenv("DEEPCAM_B200_DWW_BLOCKS_PER_SM"); tb_mult = e ? std::max(1, atoi(e)) : 2; }
+  if (min_rows < 0) { const char* e = getenv("DEEPCAM_B200_DWW_MIN_ROWS"); min_rows = e ? std::max(1, atoi(e)) : 12; }
+  DwMap m = dw_map(dout.c, V, dout.h, dout.w, dout.n, kNumSMs * tb_mult, min_rows);
   dim3 grid = dw_grid(m, dout.w, dout.n);
   const size_t smem = (size_t)8 * 32 * 3 * V * sizeof(float);
   if (s == 1 && d == 1)
