@@ -420,7 +420,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--e2e-sync-loss", action="store_true", help="e2e leg: read the loss with .item() every step")
+    ap.add_argument("--local-batch", type=int, default=LOCAL_BATCH,
+                    help="samples per GPU (BASELINE.json configs[4] sweep; the headline metric is quoted at the default, 2)")
     args = ap.parse_args()
+    if args.local_batch != LOCAL_BATCH:
+        globals()["LOCAL_BATCH"] = args.local_batch
+        globals()["WORKLOAD"] = WORKLOAD.replace("local batch 2", "local batch %d (configs[4] sweep point)" % args.local_batch)
     # stdout carries exactly ONE JSON line: libraries that print to file descriptor 1 (NCCL's version banner) are sent to
     # stderr for the duration of the run, the JSON line goes to the saved descriptor
     global _JSON_OUT
