@@ -289,6 +289,8 @@ CONV_CASES = [
     ("dec3x3_304", 304, 256, 3, 1, 1, 1, 16, 24, False),
     ("pw_bias", 256, 256, 1, 1, 0, 1, 16, 24, True),
     ("lowlevel48", 128, 48, 1, 1, 0, 1, 16, 24, False),
+    ("conv2_32_64", 32, 64, 3, 1, 1, 1, 24, 40, False),          # fewer gathered channels than one 64-wide k block
+    ("pw32_16", 32, 16, 1, 1, 0, 1, 24, 40, False),
 ]
 
 
