@@ -178,7 +178,15 @@ def run_ours(args):
     if world > 1:
         from deepcam_b200.parallel import DistributedDataParallel
         model = DistributedDataParallel(net)
-    if os.environ.get("DEEPCAM_B200_TORCH_ADAM", "0") == "1":
+    if args.optimizer == "lars":        # BASELINE.json configs[4]; LARS is not part of the reference
+        from deepcam_b200.optim import FusedLARS
+        opt = FusedLARS(net.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-6)
+        opt_name = "deepcam_b200.optim.FusedLARS momentum=0.9 trust=1e-3"
+    elif args.optimizer == "lamb":      # the reference's --optimizer LAMB (apex FusedLAMB, TR:217-218)
+        from deepcam_b200.optim import FusedLAMB
+        opt = FusedLAMB(net.parameters(), lr=1e-3, eps=1e-8, weight_decay=1e-6)
+        opt_name = "deepcam_b200.optim.FusedLAMB (apex FusedLAMB semantics)"
+    elif os.environ.get("DEEPCAM_B200_TORCH_ADAM", "0") == "1":
         opt = torch.optim.Adam(net.parameters(), lr=1e-3, eps=1e-8, weight_decay=1e-6)
         opt_name = "torch.optim.Adam"
     else:       # same update rule / state as torch.optim.Adam, one launch for all 301 parameters
@@ -420,6 +428,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--e2e-sync-loss", action="store_true", help="e2e leg: read the loss with .item() every step")
+    ap.add_argument("--optimizer", default="adam", choices=["adam", "lamb", "lars"],
+                    help="adam = the headline configuration (script default, TR:566-568); lamb / lars: configs[4] sweep")
     ap.add_argument("--local-batch", type=int, default=LOCAL_BATCH,
                     help="samples per GPU (BASELINE.json configs[4] sweep; the headline metric is quoted at the default, 2)")
     args = ap.parse_args()

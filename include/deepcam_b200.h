@@ -252,6 +252,10 @@ int dc_adam_step_multi(const dc_adam_job* jobs_dev, int njobs, int total_blocks,
 int dc_lamb_step_multi(const dc_adam_job* jobs_dev, int njobs, int total_blocks, double lr, double beta1, double beta2,
                        double eps, double weight_decay, double bias_c1, double bias_c2, int adam_w_mode,
                        int grad_averaging, double max_grad_norm, int use_nvlamb, double* norms, void* stream);
+/* LARS step for all parameters (BASELINE.json configs[4]; not part of the reference: You et al. 2017, per-tensor trust ratio
+ * on SGD with momentum).  Job table as above with m = momentum buffer (v unused); norms = device scratch of 2*njobs doubles. */
+int dc_lars_step_multi(const dc_adam_job* jobs_dev, int njobs, int total_blocks, double lr, double momentum,
+                       double weight_decay, double trust_coefficient, double eps, double* norms, void* stream);
 
 #ifdef __cplusplus
 }

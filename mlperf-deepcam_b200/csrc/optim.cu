@@ -146,9 +146,58 @@ __global__ void __launch_bounds__(256) lamb_stage2_kernel(const dc_adam_job* __r
     j.p[i] = j.p[i] - ratio * j.g[i];
 }
 
+// ---- LARS (BASELINE.json configs[4] asks for a LARS sweep; the reference has no LARS, so this follows You et al. 2017 as
+// commonly implemented: per-tensor trust ratio on SGD with momentum) -------------------------------------------------------
+//   local_lr_i = trust * ||w_i|| / (||g_i|| + wd * ||w_i|| + eps)   (1 when either norm is 0)
+//   v = momentum * v + lr * local_lr_i * (g + wd * w);   w -= v
+// norms = double[2 * njobs]: [2i] sum w_i^2, [2i + 1] sum g_i^2 (zeroed by the entry point).
+__global__ void __launch_bounds__(256) lars_norms_kernel(const dc_adam_job* __restrict__ jobs, int njobs, double* norms) {
+  pdl_sync();
+  const int ji = find_job(jobs, njobs, blockIdx.x);
+  const dc_adam_job j = jobs[ji];
+  const long long stride = (long long)j.n_blocks * 256;
+  double wn = 0.0, gn = 0.0;
+  for (long long i = (long long)(blockIdx.x - j.block_start) * 256 + threadIdx.x; i < j.numel; i += stride) {
+    const float w = j.p[i], g = j.g[i];
+    wn += (double)w * (double)w;
+    gn += (double)g * (double)g;
+  }
+  block_add(wn, norms + 2 * ji);
+  block_add(gn, norms + 2 * ji + 1);
+}
+__global__ void __launch_bounds__(256) lars_update_kernel(const dc_adam_job* __restrict__ jobs, int njobs, float lr, float momentum,
+                                                          float wd, float trust, float eps, const double* __restrict__ norms) {
+  pdl_sync();
+  const int ji = find_job(jobs, njobs, blockIdx.x);
+  const dc_adam_job j = jobs[ji];
+  const float wn = (float)sqrt(norms[2 * ji]), gn = (float)sqrt(norms[2 * ji + 1]);
+  float local_lr = 1.f;
+  if (wn > 0.f && gn > 0.f) local_lr = trust * wn / (gn + wd * wn + eps);
+  const float step = lr * local_lr;
+  const long long stride = (long long)j.n_blocks * 256;
+  for (long long i = (long long)(blockIdx.x - j.block_start) * 256 + threadIdx.x; i < j.numel; i += stride) {
+    const float w = j.p[i];
+    const float v = momentum * j.m[i] + step * (j.g[i] + wd * w);      // j.m = momentum buffer
+    j.m[i] = v;
+    j.p[i] = w - v;
+  }
+}
+
 }  // namespace dc
 
 using namespace dc;
+
+extern "C" int dc_lars_step_multi(const dc_adam_job* jobs_dev, int njobs, int total_blocks, double lr, double momentum,
+                                  double weight_decay, double trust_coefficient, double eps, double* norms, void* stream) {
+  DC_REQUIRE(jobs_dev != nullptr && njobs > 0 && total_blocks > 0 && norms != nullptr, "dc_lars_step_multi: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(norms, 0, sizeof(double) * (size_t)(2 * njobs), st);
+  if (e != cudaSuccess) return dc::fail((int)e, "dc_lars_step_multi: %s", cudaGetErrorString(e));
+  launch_k(lars_norms_kernel, dim3(total_blocks), dim3(256), (size_t)0, st, jobs_dev, njobs, norms);
+  launch_k(lars_update_kernel, dim3(total_blocks), dim3(256), (size_t)0, st, jobs_dev, njobs, (float)lr, (float)momentum,
+           (float)weight_decay, (float)trust_coefficient, (float)eps, (const double*)norms);
+  return launch_status("dc_lars_step_multi");
+}
 
 extern "C" int dc_lamb_step_multi(const dc_adam_job* jobs_dev, int njobs, int total_blocks, double lr, double beta1, double beta2,
                                   double eps, double weight_decay, double bias_c1, double bias_c2, int adam_w_mode,

@@ -91,6 +91,7 @@ SIGNATURES = {
     "dc_scale_f32": (c_int, [c_void_p, c_size_t, c_float, c_void_p]),
     "dc_adam_step_multi": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_double, c_double,
                                    c_double, c_int, c_void_p]),
+    "dc_lars_step_multi": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_double, c_void_p, c_void_p]),
     "dc_lamb_step_multi": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_double, c_double,
                                    c_double, c_int, c_int, c_double, c_int, c_void_p, c_void_p]),
 }
@@ -126,7 +127,7 @@ class KernelError(RuntimeError):
 
 
 # kernels launched per successful C call (cudaMemsetAsync nodes are not counted as kernels)
-_KERNELS_PER_CALL = {"dc_fill_zero": 0, "dc_wce_fwd": 2, "dc_channel_sum": 2, "dc_lamb_step_multi": 3}
+_KERNELS_PER_CALL = {"dc_fill_zero": 0, "dc_wce_fwd": 2, "dc_channel_sum": 2, "dc_lamb_step_multi": 3, "dc_lars_step_multi": 2}
 launch_count = 0          # number of deepcam_b200 kernels launched by this process (bench.py reports it)
 launch_hist = {}
 

@@ -153,3 +153,61 @@ class FusedLAMB(torch.optim.Optimizer):
                 float(group["max_grad_norm"] or 0.0), int(bool(self.use_nvlamb)), ctypes.c_void_p(norms.data_ptr()),
                 ops._stream()), "dc_lamb_step_multi")
         return loss
+
+
+class FusedLARS(torch.optim.Optimizer):
+    """LARS (You et al. 2017) for the local-batch sweep of BASELINE.json configs[4].  The reference ships no LARS (its
+    layer-wise optimizer is apex FusedLAMB, see FusedLAMB above), so the update rule is the commonly used one and its parity
+    is pinned only against a plain-torch restatement ("parity unpinned"):
+        local_lr = trust_coefficient * ||w|| / (||g|| + weight_decay * ||w|| + eps)     per tensor (1 if a norm is 0)
+        buf = momentum * buf + lr * local_lr * (g + weight_decay * w);   w -= buf
+    State: `momentum_buffer` per parameter.  One step = two launches for all parameters (csrc/optim.cu)."""
+
+    def __init__(self, params, lr=1e-3, momentum=0.9, weight_decay=0.0, trust_coefficient=0.001, eps=1e-8):
+        if lr < 0.0 or momentum < 0.0 or weight_decay < 0.0 or trust_coefficient <= 0.0:
+            raise ValueError("invalid LARS hyper-parameters")
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay, trust_coefficient=trust_coefficient, eps=eps))
+        self._tables = {}
+
+    def _table(self, gi, plist):
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["momentum_buffer"].data_ptr()) for p in plist)
+        ent = self._tables.get(gi)
+        if ent is not None and ent[0] == key:
+            return ent[1]
+        arr = (_lib.dc_adam_job * len(plist))()
+        start = 0
+        for i, p in enumerate(plist):
+            n = p.numel()
+            nb = max(1, min(256, (n + 4095) // 4096))
+            j = arr[i]
+            j.p, j.g, j.m, j.v = p.data_ptr(), p.grad.data_ptr(), self.state[p]["momentum_buffer"].data_ptr(), None
+            j.numel, j.block_start, j.n_blocks = n, start, nb
+            start += nb
+        table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(plist[0].device)
+        self._tables[gi] = (key, (table, len(plist), start))
+        return self._tables[gi][1]
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            plist = [p for p in group["params"] if p.grad is not None]
+            if not plist:
+                continue
+            for p in plist:
+                if not p.is_cuda or p.dtype != torch.float32 or p.grad.dtype != torch.float32:
+                    raise RuntimeError("deepcam_b200 FusedLARS needs fp32 CUDA parameters and gradients (no CPU fallback)")
+                if p.grad.is_sparse or not p.is_contiguous() or not p.grad.is_contiguous():
+                    raise RuntimeError("deepcam_b200 FusedLARS needs dense contiguous parameters and gradients")
+                if "momentum_buffer" not in self.state[p]:
+                    self.state[p]["momentum_buffer"] = torch.zeros_like(p)
+            table, njobs, blocks = self._table(gi, plist)
+            norms = torch.empty(2 * njobs, dtype=torch.float64, device=plist[0].device)
+            _lib.check(_lib.load().dc_lars_step_multi(
+                ctypes.c_void_p(table.data_ptr()), njobs, blocks, float(group["lr"]), float(group["momentum"]),
+                float(group["weight_decay"]), float(group["trust_coefficient"]), float(group["eps"]),
+                ctypes.c_void_p(norms.data_ptr()), ops._stream()), "dc_lars_step_multi")
+        return loss

@@ -636,3 +636,32 @@ def test_fused_lamb_matches_published_algorithm(adam_w_mode, wd, max_norm):
     assert sd["param_groups"][0]["step"] == 4 and set(sd["state"][0]) == {"exp_avg", "exp_avg_sq"}
     opt.zero_grad()
     assert all(p.grad is None for p in my_p)
+
+
+@pytest.mark.parametrize("wd", [0.0, 1e-4])
+def test_fused_lars_matches_restatement(wd):
+    """FusedLARS against a float64 restatement of the rule in its docstring (LARS is not part of the reference: parity unpinned)."""
+    from deepcam_b200.optim import FusedLARS
+    torch.manual_seed(9)
+    shapes = [(728, 728, 1, 1), (7,), (256, 3, 3, 3), (1,)]
+    my_p = [torch.nn.Parameter(torch.randn(s, device=dev())) for s in shapes]
+    ref_p = [p.detach().double().clone() for p in my_p]
+    bufs = [torch.zeros_like(p) for p in ref_p]
+    lr, mom, trust, eps = 0.1, 0.9, 0.001, 1e-8
+    opt = FusedLARS(my_p, lr=lr, momentum=mom, weight_decay=wd, trust_coefficient=trust, eps=eps)
+    for step in range(4):
+        grads = [torch.randn_like(p) for p in my_p]
+        if step == 2:
+            grads[1].zero_()                                   # zero gradient norm -> local_lr = 1
+        for p, g in zip(my_p, grads):
+            p.grad = g.clone()
+        for i, (w, g) in enumerate(zip(ref_p, grads)):
+            g = g.double()
+            wn, gn = w.norm(), g.norm()
+            local = trust * wn / (gn + wd * wn + eps) if (wn > 0 and gn > 0) else 1.0
+            bufs[i] = mom * bufs[i] + lr * local * (g + wd * w)
+            ref_p[i] = w - bufs[i]
+        opt.step()
+        torch.cuda.synchronize()
+        for p, r in zip(my_p, ref_p):
+            assert rel(p, r) < 2e-6
