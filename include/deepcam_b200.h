@@ -195,6 +195,10 @@ int dc_bn_bwd_apply(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y,
  * finalized inside the kernel from the workspace sums; writes dy, dgamma, dbeta and dres (+)= g. */
 int dc_bn_bwd_apply_reduced(const dc_bn_params* p, dc_view g, dc_view y, const void* rws, dc_view dy, dc_view dres,
                             float* dgamma, float* dbeta, void* stream);
+/* Split BatchNorm backward for L2-resident tensors: dc_bn_bwd_reduce with DC_BN_SUMS_READY in the flags accumulates the sums
+ * only; this call finalizes them per block, applies the mask the flags ask for and writes dy, dres, dgamma, dbeta. */
+int dc_bn_bwd_apply_finalize(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, const void* rws, dc_view dy,
+                             dc_view dres, float* dgamma, float* dbeta, void* stream);
 /* One-pass variants for tensors small enough to be held in shared memory across the GPU (dc_bn_onepass_ok): statistics
  * and normalisation (forward) / reduction and gradient (backward) in ONE launch with an inter-block barrier; the grid
  * never exceeds the SM count, so all blocks are co-resident.  Same workspace contract as the two-pass entry points. */

@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(dc_bn_params 
   }
   BnWs rws = bn_ws(rws_raw, C);
   reduce_to_ws<2, V>(acc, rws.sums, C, m.cvp, blockIdx.y * m.cvp, min(m.cvp, m.cv - blockIdx.y * m.cvp));
+  if (p.flags & DC_BN_SUMS_READY) return;          // sums only: dc_bn_bwd_apply_finalize derives the coefficients itself
   if (!last_block(rws.ticket)) return;
   // ---- finalize: dgamma, dbeta and the per-channel coefficients of dy = A*g + B*y + D
   const bool train = (p.flags & DC_BN_TRAIN) != 0;
@@ -596,7 +597,10 @@ static int bn_bwd_reduce_t(const dc_bn_params& p, const dc_view& dout, const dc_
   const long long npix = (long long)y.n * y.h * y.w;
   LaneMap m = lane_map(y.c, V);
   static const int cap = bn_cap("DEEPCAM_B200_BN_CAP_REDUCE", 2);
-  dim3 grid = bn_grid(m, npix, 4 * kUnroll, cap);
+  static const int cap_small = bn_cap("DEEPCAM_B200_BN_CAP_REDUCE_SMALL", 2), items_small = bn_cap("DEEPCAM_B200_BN_ITEMS_REDUCE_SMALL", 8);
+  // L2-resident tensors (<= 24 MB) are latency-bound: fewer pixels per thread, more resident blocks (tunable)
+  const bool small = (long long)npix * y.c * (long long)sizeof(T) <= (24ll << 20);
+  dim3 grid = small ? bn_grid(m, npix, items_small, cap_small) : bn_grid(m, npix, 4 * kUnroll, cap);
   launch_k(bn_bwd_reduce_kernel<T, V>, grid, dim3(kBnThreads), red_smem<2, V>(), st, p, pix_view<const T>(dout), pix_view<const T>(out),
                                                                          pix_view<const T>(y), rws, dgamma, dbeta, y.c, npix, m);
   return launch_status("dc_bn_bwd_reduce");
@@ -1070,6 +1074,25 @@ int dc_bn_bwd_apply_reduced(const dc_bn_params* p, dc_view g, dc_view y, const v
   cudaStream_t st = as_stream(stream);
   return g.dtype == DC_F32 ? bn_bwd_apply_t<float>(q, g, none, y, rws, dy, dres, st, dgamma, dbeta)
                            : bn_bwd_apply_t<__nv_bfloat16>(q, g, none, y, rws, dy, dres, st, dgamma, dbeta);
+}
+
+/* Second half of the split BatchNorm backward for small tensors: dc_bn_bwd_reduce was called with DC_BN_SUMS_READY (sums
+ * only, no last-block finalize); this call finalizes the coefficients per block (shared memory), applies the ReLU mask as the
+ * flags say (out, or DC_BN_MASK_FROM_Y) and writes dy / dres / dgamma / dbeta.  Train mode. */
+int dc_bn_bwd_apply_finalize(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, const void* rws, dc_view dy, dc_view dres,
+                             float* dgamma, float* dbeta, void* stream) {
+  DC_REQUIRE(p != nullptr && rws != nullptr, "dc_bn_bwd_apply_finalize: null argument");
+  DC_REQUIRE((p->flags & DC_BN_TRAIN) && p->sums != nullptr && p->gamma != nullptr && !(p->flags & DC_BN_IDENTITY),
+             "dc_bn_bwd_apply_finalize: train-mode BatchNorm with its forward workspace required");
+  const dc_view opts[4] = {dy, dres, out, y};
+  DC_REQUIRE(views_ok(dout, opts, 4) && view_ok(y), "dc_bn_bwd_apply_finalize: views must be channel-contiguous, 16-byte aligned and of one shape/dtype");
+  if ((p->flags & DC_BN_RELU) && !(p->flags & DC_BN_MASK_FROM_Y)) DC_REQUIRE(view_ok(out), "dc_bn_bwd_apply_finalize: out view required for ReLU mask");
+  if (p->flags & DC_BN_MASK_FROM_Y) DC_REQUIRE(dres.ptr == nullptr, "dc_bn_bwd_apply_finalize: DC_BN_MASK_FROM_Y excludes a residual");
+  dc_bn_params q = *p;
+  q.flags |= DC_BN_SUMS_READY;
+  cudaStream_t st = as_stream(stream);
+  return dout.dtype == DC_F32 ? bn_bwd_apply_t<float>(q, dout, out, y, rws, dy, dres, st, dgamma, dbeta)
+                              : bn_bwd_apply_t<__nv_bfloat16>(q, dout, out, y, rws, dy, dres, st, dgamma, dbeta);
 }
 
 /* 1 when the one-pass kernels can handle a [npix, C] tensor of this dtype (everything held on chip), else 0 */

@@ -72,6 +72,8 @@ SIGNATURES = {
     "dc_bn_apply": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p]),
     "dc_bn_bwd_reduce": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dc_bn_bwd_apply": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, dc_view, dc_view, c_void_p]),
+    "dc_bn_bwd_apply_finalize": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, dc_view, dc_view, c_void_p,
+                                         c_void_p, c_void_p]),
     "dc_bn_bwd_apply_reduced": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, c_void_p, dc_view, dc_view, c_void_p, c_void_p,
                                         c_void_p]),
     "dc_bn_onepass_ok": (c_int, [c_int, c_int64, c_int, c_int]),

@@ -120,8 +120,10 @@ class CudaBackend:
         # BatchNorm batch sums out of the producing GEMM's epilogue (dc_conv_gemm_tc_bnstats): no statistics pass at all
         self.fuse_bn_stats = os.environ.get("DEEPCAM_B200_FUSE_BN_STATS", "1") not in ("0", "false", "")
         # BatchNorm backward reduction (+ ReLU mask) inside the depthwise backward-data kernel that produces the gradient
-        self.fuse_bn_bwd = os.environ.get("DEEPCAM_B200_FUSE_BN_BWD", "1") not in ("0", "false", "")
+        self.fuse_bn_bwd = os.environ.get("DEEPCAM_B200_FUSE_BN_BWD", "0") not in ("0", "false", "")
         self.fuse_bn_bwd_max_bytes = int(os.environ.get("DEEPCAM_B200_FUSE_BN_BWD_MAX_BYTES", str(24 << 20)))
+        self.bn_bwd_split = os.environ.get("DEEPCAM_B200_BN_BWD_SPLIT", "1") not in ("0", "false", "")
+        self.bn_bwd_split_max_bytes = int(os.environ.get("DEEPCAM_B200_BN_BWD_SPLIT_MAX_BYTES", str(1 << 40)))
         self.fuse_bn_bwd_res = os.environ.get("DEEPCAM_B200_FUSE_BN_BWD_RES", "1") not in ("0", "false", "")
         self.side_stream = None       # set by a graph plan: weight-gradient kernels run on a parallel graph branch
         self._side_dirty = False
@@ -357,11 +359,11 @@ class CudaBackend:
     def dw_bwd_data_bnred(self, dy, spec, dx, accumulate, y, act, fwd_sums, relu, force=False):
         """dw_bwd_data as the LAST writer of the gradient of a BatchNorm output: also applies the ReLU mask and leaves the
         BatchNorm backward sums in a fresh workspace, which is returned (None: not applicable, nothing was launched)."""
-        if not self.fuse_bn_bwd or spec.stride != 1 or spec.dil != 1:
+        if (not self.fuse_bn_bwd and not force) or spec.stride != 1 or spec.dil != 1:
             return None
-        # measured on B200: a win for the L2-resident tensors (replaces the one-pass barrier kernel; residual layers stage two
-        # more tiles and run two waves, still 13.58 vs 13.66 ms/step); on the large tensors the per-block fp64 atomics outweigh
-        # the saved reduction pass, so those keep the separate kernels
+        # measured on B200 (session 4): the fused kernel (24 us + 5.5 us apply on the 10 MB tensors) beats the one-pass barrier
+        # kernel after a plain depthwise backward (9.5 + 20.7 us) but loses to the split reduction (9.5 + 16 us, bn_bwd below),
+        # so it is opt-in (DEEPCAM_B200_FUSE_BN_BWD=1); on the large tensors its per-block fp64 atomics outweigh the saved pass
         if not force and ((act is not None and not self.fuse_bn_bwd_res) or
                           dx.numel() * dx.element_size() > self.fuse_bn_bwd_max_bytes):
             return None
@@ -450,6 +452,16 @@ class CudaBackend:
             mask_src = None
         p = ops.bn_params(m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var, sums, n * h * w, 0.0, m.eps, flags)
         rws = self.scratch(ops.bn_ws_elems(c), torch.float64, zero=True)
+        if training and self.bn_bwd_split and dout.numel() * dout.element_size() <= self.bn_bwd_split_max_bytes:
+            # sums-only reduction + apply that finalizes per block in shared memory (no last-block tail, no inter-block
+            # barrier): measured ahead of the one-pass kernel on the 10 MB tensors (16.0 vs 20.7 us) and of reduce-with-finalize
+            # + coefficient-loading apply on the large ones (13.44 vs 13.52 ms/step)
+            pr = ops.bn_params(m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var, sums, n * h * w, 0.0, m.eps,
+                               flags | DC_BN_SUMS_READY)
+            ops.bn_bwd_reduce(pr, dout, mask_src, y, rws, None, None)
+            ops.bn_bwd_apply_finalize(p, dout, mask_src, y, rws, dy, dres, dgamma, dbeta)
+            self.launches += 2
+            return
         if self.onepass and self.onepass_bwd and ops.bn_onepass_ok(c, n * h * w, dout.dtype, True):
             ops.bn_bwd_onepass(p, dout, mask_src, y, rws, dy, dres, dgamma, dbeta)
             self.launches += 1

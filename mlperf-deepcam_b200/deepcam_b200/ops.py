@@ -359,6 +359,14 @@ def dw_bwd_data_bnred(dy, w9c, dx, accumulate, y, act, fwd_ws, bwd_ws, relu):
     return rc[0] == 0
 
 
+def bn_bwd_apply_finalize(params, dout, out, y, rws, dy, dres, dgamma, dbeta):
+    _require_cuda(dout, y)
+    _timed("bn_bwd_apply", 8.0 * dout.numel(), _nbytes(dout, out, y, dy, dres),
+           lambda: _lib.load().dc_bn_bwd_apply_finalize(ctypes.byref(params), view(dout), view(out), view(y), _p(rws), view(dy),
+                                                        view(dres), _p(dgamma), _p(dbeta), _stream()), "dc_bn_bwd_apply_finalize",
+           tag=_shape_tag(dout) + " finalize" + (" res" if dres is not None else ""))
+
+
 def bn_bwd_apply_reduced(params, g, y, rws, dy, dres, dgamma, dbeta):
     _require_cuda(g, y)
     _timed("bn_bwd_apply", 6.0 * g.numel(), _nbytes(g, y, dy, dres),

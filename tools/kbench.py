@@ -92,6 +92,15 @@ def main():
         add("conv_dgrad " + tag, lambda dyc=dyc, cs=cs, dx=dx: be.conv_bwd_data(dyc, cs, dx, False), nb, fl)
         add("conv_wgrad " + tag, lambda x=x, dyc=dyc, cs=cs, gw=gw: be.conv_bwd_weight(x, dyc, cs, gw), nb, fl)
 
+    # fixed cost of the GEMM kernel at the middle-flow tile count: the same 54 x 2 tiles with 1, 6 and 12 k blocks
+    for ci in (64, 384, 728):
+        x = rnd(2, 48, 72, ci)
+        wt = torch.nn.Parameter(torch.randn(728, ci, 1, 1, device=dev) * 0.05)
+        cs = ConvSpec("c", wt, None, 1, 0, 1)
+        out = torch.empty(2, 48, 72, 728, device=dev, dtype=bf)
+        add("kscan_fprop 2x48x72 %d->728 k1" % ci, lambda x=x, cs=cs, out=out: be.conv_fwd(x, cs, out),
+            (x.numel() + out.numel() + wt.numel()) * 2.0, 2.0 * 6912 * ci * 728)
+
     # small-channel layers of the entry flow / last deconv (K or N far below a tensor-core tile)
     for (n, h, w, ci, co, k, stride, transposed, name) in [(2, 768, 1152, 16, 32, 3, 2, False, "conv1"), (2, 384, 576, 32, 64, 3, 1, False, "conv2"),
                                                            (2, 384, 576, 256, 3, 3, 2, True, "last_deconv")]:
