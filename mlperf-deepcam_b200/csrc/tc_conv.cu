@@ -70,6 +70,11 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -802,6 +807,8 @@ struct TcWgradParams {
   int n_ci_tiles;
   int Co, Ci;
   int vec_red;          // G rows are 16-byte aligned and Ci % 4 == 0: use red.global.add.v4.f32
+  int tma_red;          // ... and the fp32 gradient has a tensor map (maps.c): the epilogue stages 128 x 32 fp32 chunks in shared
+                        // memory and hands them to TMA reduce-add (bulk L2 reductions instead of 8192 red instructions per CTA)
   float* G;
 };
 
@@ -906,6 +913,36 @@ __global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const __grid_
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
       float* Grow = p.G + ((size_t)p.wt[t] * p.Co + (size_t)(co < p.Co ? co : 0)) * p.Ci;
+      if (p.tma_red) {
+        // all MMAs have completed (tmem_full), so every pipeline stage has been consumed: stage memory becomes two 16 KB
+        // staging buffers of 128 rows x 128 B (32 fp32), 128B-swizzled like the tensor map of the gradient
+        const bool elected = (threadIdx.x == 64);
+        const int row = lg * 32 + lane;
+        int chunk = 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BNW; c0 += 32, ++chunk) {
+          if (ci0 + c0 >= p.Ci) break;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
+          if (elected) tma_store_wait_read<1>();       // the reduction that used this buffer two chunks ago has read it
+          tmem_ld_wait();
+          epi_bar_sync();
+          const uint32_t sbuf = smem_base + (uint32_t)(chunk & 1) * 16384u + (uint32_t)row * 128u;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t dst = sbuf + (((uint32_t)q ^ ((uint32_t)row & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[4 * q]), "r"(v[4 * q + 1]), "r"(v[4 * q + 2]),
+                         "r"(v[4 * q + 3]) : "memory");
+          }
+          fence_proxy_async();
+          epi_bar_sync();
+          if (elected) {
+            tma_reduce_add_3d(&maps.c, smem_base + (uint32_t)(chunk & 1) * 16384u, ci0 + c0, co0, p.wt[t]);
+            tma_store_commit();
+          }
+        }
+        if (elected) tma_store_wait_all();             // shared memory must stay valid until the last reduction has read it
+      } else
 #pragma unroll 1
       for (int c0 = 0; c0 < BNW; c0 += 32) {
         if (ci0 + c0 >= p.Ci) break;
@@ -1255,10 +1292,28 @@ int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, 
   // one CTA per SM (the stages fill the shared memory): split the pixel reduction so that the grid is one wave
   static int split_div = -1;      // tuning knob (DEEPCAM_B200_WGRAD_SPLIT_DIV): divide the one-wave split count
   if (split_div < 0) { const char* e = getenv("DEEPCAM_B200_WGRAD_SPLIT_DIV"); split_div = e ? std::max(1, atoi(e)) : 1; }
-  int splits = std::max(1, std::min(p.mtiles_total, kNumSMs / std::max(1, tiles) / split_div));
+  static int split_mul = -1;      // and DEEPCAM_B200_WGRAD_SPLIT_MUL: multiply it (more than one wave of CTAs)
+  if (split_mul < 0) { const char* e = getenv("DEEPCAM_B200_WGRAD_SPLIT_MUL"); split_mul = e ? std::max(1, atoi(e)) : 1; }
+  int splits = std::max(1, std::min(p.mtiles_total, kNumSMs * split_mul / std::max(1, tiles) / split_div));
   p.mtiles_per_split = ceil_div(p.mtiles_total, splits);
   splits = ceil_div(p.mtiles_total, p.mtiles_per_split);
   p.vec_red = (in.c % 4 == 0 && (reinterpret_cast<uintptr_t>(G) % 16) == 0) ? 1 : 0;
+  static int tma_red_enabled = -1;
+  if (tma_red_enabled < 0) { const char* e = getenv("DEEPCAM_B200_WGRAD_TMA_RED"); tma_red_enabled = (e && e[0] == '0') ? 0 : 1; }
+  p.tma_red = 0;
+  if (p.vec_red && tma_red_enabled) {
+    // fp32 gradient G[wtaps][Co][Ci] as a 3-D tensor: boxes of 32 ci x 128 co of one tap, 128B swizzle; rows >= Co and columns
+    // >= Ci of edge tiles are clipped by the TMA unit
+    PFN_encodeTiled enc = get_encode();
+    DC_REQUIRE(enc != nullptr, "dc_conv_wgrad_tc: cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[3] = {(cuuint64_t)in.c, (cuuint64_t)dout.c, (cuuint64_t)d->wtaps};
+    cuuint64_t strides[2] = {(cuuint64_t)in.c * 4, (cuuint64_t)in.c * 4 * (cuuint64_t)dout.c};
+    cuuint32_t box[3] = {32, 128, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&maps.c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, G, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) p.tma_red = 1;
+  }
   dim3 grid(n_co_tiles * p.n_ci_tiles, d->ntaps, splits);
   cudaStream_t st = as_stream(stream);
   if (BNW == 64) return launch_wgrad<64>(maps, p, grid, st);
