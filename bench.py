@@ -101,6 +101,13 @@ def run_reference(args):
     import torch
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     import deepcam_oracle as O
+    # torchrun exports OMP_NUM_THREADS=1 for its workers; this arm is the only process doing work, so it takes every host core
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    if torch.get_num_threads() < avail:
+        torch.set_num_threads(avail)
     cores = torch.get_num_threads()
     sd = O.init_state_dict(C_IN, N_CLASSES, 16, seed=333)
     st = O.TrainState(sd)
