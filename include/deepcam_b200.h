@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DC_ABI_VERSION 1
+#define DC_ABI_VERSION 2
 
 enum { DC_F32 = 0, DC_BF16 = 1 };
 
@@ -62,6 +62,13 @@ typedef struct dc_conv_desc {
   int32_t stride_h, stride_w;
   int32_t accumulate;        /* 1: out += result (gradient accumulation at graph forks) */
   int32_t wtaps;             /* number of tap slices in the packed weight tensor */
+  /* Two-segment output (dc_conv_gemm_* only; 0 = off): output channels co >= out_csplit are stored at
+   * out + out_split_off + (co - out_csplit) * sc instead of out + co * sc.  This is how ONE launch writes two output
+   * rows of a stride-2 nn.ConvTranspose2d (DX:374): channels = (row parity, column parity, co), see
+   * DC_PACK_NTK_CONVT2.  out_csplit % 4 == 0. */
+  int32_t out_csplit;
+  int32_t reserved;
+  int64_t out_split_off;     /* in elements of the output view */
 } dc_conv_desc;
 
 /* ---- library / diagnostics ------------------------------------------------ */
@@ -94,8 +101,12 @@ int dc_i64_increment_many(int64_t* const* ptrs, int count, void* stream);
  *   layout DC_PACK_TKN: dst[tap][k][n_pad]      (SIMT gather-GEMM B operand)
  *   layout DC_PACK_NTK: dst[n][tap][k_pad]      (tcgen05 B operand, K-major rows)
  *   layout DC_PACK_TC : dst[tap][c]             (depthwise, k = 1, n = c)
+ *   layout DC_PACK_NTK_CONVT2: all four output-parity classes of a k3 s2 p1 op1 nn.ConvTranspose2d (DX:374) as ONE
+ *     2x2-tap contraction: src is the parameter [k][n][3][3] (src_k_first = 1), taps = 4 (tap = dh*2+dw, dh,dw in {0,1}),
+ *     N_pad = 4*G (G = channels per class, >= N), dst[(a*2+b)*G + n][tap][k_pad] = src[k][n][a+1-2dh][b+1-2dw]
+ *     (zero where that kernel index is outside 0..2); y[2i+a, 2j+b, n] = sum_tap sum_k x[i+dh, j+dw, k] * dst[..].
  * padded entries are written as zero. */
-enum { DC_PACK_TKN = 0, DC_PACK_NTK = 1 };
+enum { DC_PACK_TKN = 0, DC_PACK_NTK = 1, DC_PACK_NTK_CONVT2 = 2 };
 int dc_pack_weight(const float* src, int K, int N, int taps, int src_k_first,
                    void* dst, int layout, int K_pad, int N_pad, int dst_dtype, void* stream);
 /* Every weight pack of a training step in one launch.  `jobs_dev` is a DEVICE array of njobs descriptors (same

@@ -261,6 +261,16 @@ __global__ void scale_f32_kernel(float* x, size_t count, float s) {
 }
 
 // ---- weight packing ----------------------------------------------------------------------------
+// DC_PACK_NTK_CONVT2: destination element (row nn, tap t, k) of the fused stride-2 transposed-convolution pack -> source
+// index in the [k][n][3][3] parameter, or -1 (zero).  nn = (a*2+b)*G + n, t = dh*2+dw, kernel index = (a+1-2dh, b+1-2dw).
+__device__ __forceinline__ long long convt2_src_index(int k, int nn, int t, int K, int N, int N_pad) {
+  const int G = N_pad >> 2;
+  const int cls = nn / G, n = nn - cls * G;
+  const int kh = (cls >> 1) + 1 - 2 * (t >> 1), kw = (cls & 1) + 1 - 2 * (t & 1);
+  if (k >= K || n >= N || kh < 0 || kh > 2 || kw < 0 || kw > 2) return -1;
+  return ((long long)k * N + n) * 9 + kh * 3 + kw;
+}
+
 // one thread per destination element; destinations are small (<= 4.7 M elements per layer).
 template <typename TD>
 __global__ void pack_weight_kernel(const float* __restrict__ src, int K, int N, int taps, int src_k_first,
@@ -281,7 +291,10 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int K, int N, 
       n = (int)(r / taps);
     }
     float v = 0.f;
-    if (k < K && n < N) {
+    if (layout == DC_PACK_NTK_CONVT2) {
+      const long long si = convt2_src_index(k, n, t, K, N, N_pad);
+      if (si >= 0) v = src[si];
+    } else if (k < K && n < N) {
       long long si = src_k_first ? ((long long)k * N + n) * taps + t : ((long long)n * K + k) * taps + t;
       v = src[si];
     }
@@ -309,7 +322,10 @@ __device__ __forceinline__ void pack_job_elems(const dc_pack_job& j, int local_b
       n = r / j.taps;
     }
     float v = 0.f;
-    if (k < j.K && n < j.N) {
+    if (j.layout == DC_PACK_NTK_CONVT2) {
+      const long long si = convt2_src_index(k, n, t, j.K, j.N, j.N_pad);
+      if (si >= 0) v = src[si];
+    } else if (k < j.K && n < j.N) {
       const long long si = j.src_k_first ? ((long long)k * j.N + n) * j.taps + t : ((long long)n * j.K + k) * j.taps + t;
       v = src[si];
     }
@@ -583,7 +599,9 @@ int dc_scale_f32(float* x, size_t count, float s, void* stream) {
 int dc_pack_weight(const float* src, int K, int N, int taps, int src_k_first, void* dst, int layout,
                    int K_pad, int N_pad, int dst_dtype, void* stream) {
   DC_REQUIRE(src && dst && K > 0 && N > 0 && taps > 0 && K_pad >= K && N_pad >= N, "dc_pack_weight: bad arguments");
-  DC_REQUIRE(layout == DC_PACK_TKN || layout == DC_PACK_NTK, "dc_pack_weight: unknown layout %d", layout);
+  DC_REQUIRE(layout == DC_PACK_TKN || layout == DC_PACK_NTK || layout == DC_PACK_NTK_CONVT2, "dc_pack_weight: unknown layout %d", layout);
+  DC_REQUIRE(layout != DC_PACK_NTK_CONVT2 || (taps == 4 && src_k_first == 1 && N_pad % 4 == 0 && N_pad / 4 >= N),
+             "dc_pack_weight: DC_PACK_NTK_CONVT2 needs taps = 4, src_k_first = 1, N_pad = 4 * (channels per class >= N)");
   long long total = (long long)taps * K_pad * N_pad;
   int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 8);
   if (dst_dtype == DC_F32)

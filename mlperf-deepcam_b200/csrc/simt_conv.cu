@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(dc_conv_desc d, Vie
       if (co >= Co) continue;
       float v = acc[i][j];
       if (bias) v += bias[co];
-      long long off = base + co * out.sc;
+      long long off = base + ((d.out_csplit > 0 && co >= d.out_csplit) ? d.out_split_off + (co - d.out_csplit) * out.sc : co * out.sc);
       if (out.dtype == DC_F32) {
         float* p = reinterpret_cast<float*>(out.p) + off;
         if (d.accumulate) v += *p;
@@ -282,6 +282,7 @@ static int check_desc(const char* what, const dc_conv_desc* d) {
   DC_REQUIRE(d->stride_h >= 1 && d->stride_w >= 1, "%s: bad stride", what);
   DC_REQUIRE(d->wtaps >= 1 && d->wtaps <= DC_MAX_TAPS, "%s: wtaps=%d out of range", what, d->wtaps);
   for (int t = 0; t < d->ntaps; ++t) DC_REQUIRE(d->wt[t] >= 0 && d->wt[t] < d->wtaps, "%s: wt[%d]=%d out of range", what, t, d->wt[t]);
+  DC_REQUIRE(d->out_csplit >= 0 && d->out_csplit % 4 == 0, "%s: out_csplit must be a non-negative multiple of 4", what);
   return 0;
 }
 
@@ -337,7 +338,7 @@ int dc_conv_gemm_simt(const dc_conv_desc* d, dc_view in, const void* w, const fl
   cudaStream_t st = as_stream(stream);
   // few-row fast path: 1x1, no gather offset, fp32 in and out, pixel-linear rows (the image-pooling conv and its dgrad)
   const long long M = (long long)out.n * out.h * out.w;
-  if (M <= kSmallM && d->ntaps == 1 && d->dh[0] == 0 && d->dw[0] == 0 && d->stride_h == 1 && d->stride_w == 1 && d->wt[0] == 0 &&
+  if (M <= kSmallM && d->out_csplit == 0 && d->ntaps == 1 && d->dh[0] == 0 && d->dw[0] == 0 && d->stride_h == 1 && d->stride_w == 1 && d->wt[0] == 0 &&
       in.dtype == DC_F32 && out.dtype == DC_F32 && in.sc == 1 && out.sc == 1 && in.h == out.h && in.w == out.w &&
       in.sh == (long long)in.w * in.sw && in.sn == (long long)in.h * in.sh && out.sh == (long long)out.w * out.sw &&
       out.sn == (long long)out.h * out.sh) {

@@ -161,7 +161,13 @@ struct TcOut {
   int n, h, w, c;
   long long sn, sh, sw, sc;
   int dtype;
+  int csplit;            // dc_conv_desc.out_csplit / out_split_off: channels >= csplit go to a second segment (0 = off)
+  long long split_off;
 };
+
+__device__ __forceinline__ long long out_col_off(const TcOut& o, int co) {
+  return (o.csplit > 0 && co >= o.csplit) ? o.split_off + (long long)(co - o.csplit) * o.sc : (long long)co * o.sc;
+}
 
 struct TcFpropParams {
   int ntaps;
@@ -367,15 +373,15 @@ __global__ void __launch_bounds__(kTcThreads) conv_gemm_tc_kernel(const __grid_c
           uint2 o;
           o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
           *reinterpret_cast<uint2*>(op) = o;
-        } else if (p.out.dtype == DC_F32 && p.out.sc == 1 && col + 4 <= ncols && ((rbase + co) & 3) == 0 &&
+        } else if (p.out.dtype == DC_F32 && p.out.sc == 1 && col + 4 <= ncols && ((rbase + out_col_off(p.out, co)) & 3) == 0 &&
                    ((reinterpret_cast<uintptr_t>(p.out.p) & 15) == 0)) {
-          float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out.p) + rbase + co);
+          float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out.p) + rbase + out_col_off(p.out, co));
           float4 o = make_float4(f[0], f[1], f[2], f[3]);
           if (p.accumulate) { const float4 old = *q; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
           *q = o;
         } else {
           for (int j = 0; j < V && col + j < ncols; ++j) {
-            const long long off = rbase + (long long)(co + j) * p.out.sc;
+            const long long off = rbase + out_col_off(p.out, co + j);
             float val = f[j];
             if (p.out.dtype == DC_F32) {
               float* q = reinterpret_cast<float*>(p.out.p) + off;
@@ -760,15 +766,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
               uint2 o;
               o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
               *reinterpret_cast<uint2*>(op) = o;
-            } else if (p.out.dtype == DC_F32 && p.out.sc == 1 && col + 4 <= ccols && ((rbase + co) & 3) == 0 &&
+            } else if (p.out.dtype == DC_F32 && p.out.sc == 1 && col + 4 <= ccols && ((rbase + out_col_off(p.out, co)) & 3) == 0 &&
                        ((reinterpret_cast<uintptr_t>(p.out.p) & 15) == 0)) {
-              float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out.p) + rbase + co);
+              float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out.p) + rbase + out_col_off(p.out, co));
               float4 o = make_float4(f[0], f[1], f[2], f[3]);
               if (p.accumulate) { const float4 old = *q; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
               *q = o;
             } else {
               for (int j = 0; j < V && col + j < ccols; ++j) {
-                const long long off = rbase + (long long)(co + j) * p.out.sc;
+                const long long off = rbase + out_col_off(p.out, co + j);
                 float val = f[j];
                 if (p.out.dtype == DC_F32) {
                   float* q = reinterpret_cast<float*>(p.out.p) + off;
@@ -1227,7 +1233,10 @@ static int conv_gemm_tc_impl(const dc_conv_desc* d, dc_view in, const void* w, c
   p.bias = bias;
   p.out.p = out.ptr; p.out.n = out.n; p.out.h = out.h; p.out.w = out.w; p.out.c = out.c;
   p.out.sn = out.sn; p.out.sh = out.sh; p.out.sw = out.sw; p.out.sc = out.sc; p.out.dtype = out.dtype;
-  p.out_vec_ok = (out.dtype == DC_BF16 && out.sc == 1 && out.sw % 8 == 0 && out.sh % 8 == 0 && out.sn % 8 == 0 &&
+  DC_REQUIRE(d->out_csplit >= 0 && d->out_csplit % 4 == 0 && d->out_csplit < std::max(out.c, 1),
+             "dc_conv_gemm_tc: out_csplit must be a multiple of 4 below the output channel count");
+  p.out.csplit = d->out_csplit; p.out.split_off = d->out_split_off;
+  p.out_vec_ok = (d->out_csplit == 0 && out.dtype == DC_BF16 && out.sc == 1 && out.sw % 8 == 0 && out.sh % 8 == 0 && out.sn % 8 == 0 &&
                   (reinterpret_cast<uintptr_t>(out.ptr) % 16) == 0) ? 1 : 0;
   p.stats = nullptr;
   p.stats_C = out.c;
@@ -1262,6 +1271,7 @@ int dc_conv_gemm_tc_bnstats(const dc_conv_desc* d, dc_view in, const void* w, co
                             void* stream) {
   DC_REQUIRE(sums != nullptr, "dc_conv_gemm_tc_bnstats: null statistics workspace");
   DC_REQUIRE(d != nullptr && !d->accumulate, "dc_conv_gemm_tc_bnstats: statistics of an accumulating contraction are undefined");
+  DC_REQUIRE(d->out_csplit == 0, "dc_conv_gemm_tc_bnstats: two-segment outputs are not supported");
   bool done = false;
   if (int r = conv_gemm_tc_impl(d, in, w, bias, out, sums, &done, stream)) return r;
   if (done) return 0;

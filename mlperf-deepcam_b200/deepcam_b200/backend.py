@@ -13,7 +13,7 @@ import torch
 
 from . import convdesc, ops
 from ._lib import (DC_BN_IDENTITY, DC_BN_MASK_FROM_Y, DC_BN_RELU, DC_BN_RES_WRITE, DC_BN_SUMS_READY, DC_BN_TRAIN, DC_PACK_NTK,
-                   DC_PACK_TKN)
+                   DC_PACK_NTK_CONVT2, DC_PACK_TKN)
 
 
 def _round_up(a, b):
@@ -119,6 +119,8 @@ class CudaBackend:
         self.onepass_bwd = os.environ.get("DEEPCAM_B200_BN_ONEPASS_BWD", "1") not in ("0", "false", "")
         # BatchNorm batch sums out of the producing GEMM's epilogue (dc_conv_gemm_tc_bnstats): no statistics pass at all
         self.fuse_bn_stats = os.environ.get("DEEPCAM_B200_FUSE_BN_STATS", "1") not in ("0", "false", "")
+        # few-channel stride-2 ConvTranspose2d forward as ONE 2x2-tap contraction over all four output parities
+        self.fuse_convT = os.environ.get("DEEPCAM_B200_FUSE_CONVT", "1") not in ("0", "false", "")
         # BatchNorm backward reduction (+ ReLU mask) inside the depthwise backward-data kernel that produces the gradient
         self.fuse_bn_bwd = os.environ.get("DEEPCAM_B200_FUSE_BN_BWD", "0") not in ("0", "false", "")
         self.fuse_bn_bwd_max_bytes = int(os.environ.get("DEEPCAM_B200_FUSE_BN_BWD_MAX_BYTES", str(24 << 20)))
@@ -250,9 +252,9 @@ class CudaBackend:
         return _cached(spec, (role, impl, dt, K_pad, N_pad), w, (K, N, taps, src_k_first, layout, K_pad, N_pad, dt),
                        frozen=self.graph_mode)
 
-    def _gemm(self, taps, stride, accumulate, wtaps, x, w, bias, out, impl, bn_sums=None):
-        desc = ops.make_desc(taps, (stride, stride), accumulate, wtaps)
-        ops.conv_gemm(desc, x, w, bias, out, impl, bn_sums)
+    def _gemm(self, taps, stride, accumulate, wtaps, x, w, bias, out, impl, bn_sums=None, out_split=None, flop_scale=1.0):
+        desc = ops.make_desc(taps, (stride, stride), accumulate, wtaps, out_split)
+        ops.conv_gemm(desc, x, w, bias, out, impl, bn_sums, flop_scale)
         self.launches += 1
 
     # ---- dense convolution ---------------------------------------------------------------------------------
@@ -262,6 +264,8 @@ class CudaBackend:
         also accumulates the per-channel batch sums and the (zeroed) BatchNorm workspace holding them is returned
         (pass it to bn_fwd as `ready_sums`); otherwise None is returned and bn_fwd computes the statistics itself."""
         impl = "tc" if self._tc_ok(x, spec.co) else "simt"
+        if spec.transposed and impl == "tc" and not want_bn_sums and self._convT_fusable(spec, out):
+            return self._convT_fused_fwd(x, spec, out)
         w = self._packed(spec, "fprop", impl, x, n_pad=out.shape[3])
         bias = spec.bias.detach() if spec.bias is not None else None
         kk = spec.k * spec.k
@@ -277,6 +281,26 @@ class CudaBackend:
                     taps = convdesc.convT_fprop_taps(spec.k, s, spec.pad, ph, pw)
                     self._gemm(taps, 1, False, kk, x, w, bias, out[:, ph::s, pw::s, :], impl, sums)
         return sums
+
+    def _convT_fusable(self, spec, out):
+        """Few-channel stride-2 transposed convolution (last_deconv, DX:374) into a dense output: the four parity launches
+        each re-read the whole input; one 2x2-tap contraction with N = 4 * channels reads it once per tap."""
+        g = out.shape[3]
+        return (self.fuse_convT and spec.k == 3 and spec.stride == 2 and spec.pad == 1 and spec.bias is None and
+                g % 4 == 0 and 4 * g <= 64 and out.stride(3) == 1 and out.stride(2) == g and
+                out.shape[1] % 2 == 0 and out.shape[2] % 2 == 0)
+
+    def _convT_fused_fwd(self, x, spec, out):
+        g = out.shape[3]
+        job = (spec.ci, spec.co, 4, True, DC_PACK_NTK_CONVT2, _round_up(spec.ci, 64), 4 * g, torch.bfloat16)
+        w = _cached(spec, ("fprop_convT2", g), spec.weight, job, frozen=self.graph_mode)
+        n, h2, w2, _ = out.shape
+        # output pixel (2i+a, 2j+b): channels (b, co) of row 2i+a are contiguous, row parity a is the second segment
+        view = out.as_strided((n, h2 // 2, w2 // 2, 4 * g), (out.stride(0), 2 * out.stride(1), 2 * out.stride(2), 1),
+                              out.storage_offset())
+        self._gemm(convdesc.convT_fused_fprop_taps(), 1, False, 4, x, w, None, view, "tc",
+                   out_split=(2 * g, out.stride(1)), flop_scale=9.0 / 16.0)      # 9 of the 16 (class, tap) blocks are non-zero
+        return None
 
     def conv_bwd_data(self, dy, spec, dx, accumulate):
         """dx (+)= conv^T(dy)."""

@@ -39,6 +39,13 @@ def convT_fprop_taps(k, stride, pad, ph, pw):
     return taps
 
 
+def convT_fused_fprop_taps():
+    """nn.ConvTranspose2d(k3, s2, p1, op1) forward (DX:374) with all four output parity classes in ONE contraction:
+    y[2i+a, 2j+b, co] = sum_{dh,dw in {0,1}} x[i+dh, j+dw] * W[:, co, a+1-2dh, b+1-2dw]   (kernel indices outside 0..2: zero)
+    in = x, out channels = ((a*2+b), co), weight slice dh*2+dw of the DC_PACK_NTK_CONVT2 pack."""
+    return [(dh, dw, dh * 2 + dw) for dh in range(2) for dw in range(2)]
+
+
 def convT_dgrad_taps(k, pad):
     """nn.ConvTranspose2d input gradient: dx[i, j] = sum dy[s*i - pad + kh, s*j - pad + kw] * W[:, :, kh, kw];
     in = dy, out = dx, stride = s."""

@@ -127,8 +127,9 @@ def _timed(name, flops, nbytes, rc_fn, what, tag=""):
 
 
 # ---- descriptors ---------------------------------------------------------------------------------
-def make_desc(taps, stride=(1, 1), accumulate=False, wtaps=None):
-    """taps: sequence of (dh, dw, weight_slice)."""
+def make_desc(taps, stride=(1, 1), accumulate=False, wtaps=None, out_split=None):
+    """taps: sequence of (dh, dw, weight_slice).  out_split = (first channel of the second output segment, its element
+    offset from the output view's origin), see dc_conv_desc.out_csplit."""
     if not 1 <= len(taps) <= DC_MAX_TAPS:
         raise ValueError("1..%d taps supported, got %d" % (DC_MAX_TAPS, len(taps)))
     d = dc_conv_desc()
@@ -138,6 +139,8 @@ def make_desc(taps, stride=(1, 1), accumulate=False, wtaps=None):
     d.stride_h, d.stride_w = stride
     d.accumulate = 1 if accumulate else 0
     d.wtaps = wtaps if wtaps is not None else (max(t[2] for t in taps) + 1)
+    if out_split is not None:
+        d.out_csplit, d.out_split_off = int(out_split[0]), int(out_split[1])
     return d
 
 
@@ -211,14 +214,17 @@ def unpack_wgrad(G, K, N, taps, dst_k_first, dst, k_stride=None):
 
 
 # ---- dense contractions -----------------------------------------------------------------------------
-def conv_gemm(desc, x, w, bias, out, impl, bn_sums=None):
-    """bn_sums (tcgen05 path only): zeroed BatchNorm workspace; the GEMM epilogue adds the batch sums of `out` to it."""
+def conv_gemm(desc, x, w, bias, out, impl, bn_sums=None, flop_scale=1.0):
+    """bn_sums (tcgen05 path only): zeroed BatchNorm workspace; the GEMM epilogue adds the batch sums of `out` to it.
+    flop_scale: fraction of the launched MACs that are algorithmic (packs with structural zeros), for the profiler only."""
     _require_cuda(x, w, out)
     lib = _lib.load()
     m = out.shape[0] * out.shape[1] * out.shape[2]
-    flops = 2.0 * m * out.shape[3] * x.shape[3] * desc.ntaps
-    nbytes = _nbytes(x, out) + desc.ntaps * x.shape[3] * out.shape[3] * x.element_size()
+    flops = 2.0 * m * out.shape[3] * x.shape[3] * desc.ntaps * flop_scale
+    nbytes = _nbytes(x, out) + desc.ntaps * x.shape[3] * out.shape[3] * x.element_size() * flop_scale
     tag = "M%d Ci%d Co%d taps%d s%d" % (m, x.shape[3], out.shape[3], desc.ntaps, desc.stride_h)
+    if desc.out_csplit:
+        tag += " split%d" % desc.out_csplit
     if bn_sums is not None:
         assert impl == "tc" and bn_sums.dtype == torch.float64 and bn_sums.numel() >= bn_ws_elems(out.shape[3])
         _timed("conv_gemm_tc", flops, nbytes,

@@ -28,13 +28,13 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "missing export: " + n
         assert n in _lib.SIGNATURES, "ctypes binding missing for " + n
     assert set(_lib.SIGNATURES) == set(names)
-    assert lib.dc_abi_version() == 1
+    assert lib.dc_abi_version() == _lib.DC_ABI_VERSION == 2
     assert isinstance(lib.dc_last_error_string(), bytes)
 
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.dc_view) == 8 + 4 * 4 + 4 * 8 + 8
-    assert ctypes.sizeof(_lib.dc_conv_desc) == 4 * (1 + 3 * 9 + 4)
+    assert ctypes.sizeof(_lib.dc_conv_desc) == 4 * (1 + 3 * 9 + 4) + 4 + 4 + 8
     assert ctypes.sizeof(_lib.dc_bn_params) == 5 * 8 + 8 + 4 * 4
     assert _lib.dc_view.sn.offset == 24 and _lib.dc_view.dtype.offset == 56
 
@@ -138,3 +138,37 @@ def test_conv_transpose_tap_tables():
     # wgrad: gathered = dy (stride 2), enumerated = x  ->  G[tap][ci_in][co_out]
     G = emul_wgrad(convdesc.convT_wgrad_taps(3, 1), 2, dyh, xh, 9)
     assert torch.allclose(G.permute(1, 2, 0).reshape(Ci, Co, 3, 3), w.grad, atol=1e-9)
+
+
+def test_conv_transpose_fused_tap_table_and_pack_definition():
+    """One 2x2-tap contraction over all four output parities (convdesc.convT_fused_fprop_taps + the DC_PACK_NTK_CONVT2
+    definition in include/deepcam_b200.h) + the two-segment output addressing == nn.ConvTranspose2d(k3, s2, p1, op1)."""
+    torch.manual_seed(2)
+    N, Ci, Co, H, W, G = 2, 4, 3, 5, 6, 4
+    x = torch.randn(N, Ci, H, W, dtype=torch.double)
+    w = torch.randn(Ci, Co, 3, 3, dtype=torch.double)
+    y = F.conv_transpose2d(x, w, None, 2, 1, 1).permute(0, 2, 3, 1)
+    wf = []
+    for dh, dw, wt in convdesc.convT_fused_fprop_taps():
+        assert wt == dh * 2 + dw
+        m = torch.zeros(Ci, 4 * G, dtype=torch.double)                          # [ci][(a*2+b)*G + co]
+        for a in range(2):
+            for b in range(2):
+                kh, kw = a + 1 - 2 * dh, b + 1 - 2 * dw
+                if 0 <= kh <= 2 and 0 <= kw <= 2:
+                    m[:, (a * 2 + b) * G:(a * 2 + b) * G + Co] = w[:, :, kh, kw]
+        wf.append(m)
+    fused = emul_gemm(convdesc.convT_fused_fprop_taps(), 1, x.permute(0, 2, 3, 1), wf, H, W)      # [N,H,W,4G]
+    # two-segment store: channels < 2G at out[n, 2i, 2j] onwards (b, co contiguous), channels >= 2G one output row below
+    out = torch.zeros(N, 2 * H, 2 * W, G, dtype=torch.double)
+    flat = out.view(-1)
+    sn, sh, sw, _ = out.stride()
+    for n in range(N):
+        for i in range(H):
+            for j in range(W):
+                base = n * sn + 2 * i * sh + 2 * j * sw
+                for c in range(4 * G):
+                    off = base + (sh + (c - 2 * G) if c >= 2 * G else c)
+                    flat[off] = fused[n, i, j, c]
+    assert torch.allclose(out[..., :Co], y, atol=1e-10)
+    assert float(out[..., Co:].abs().max()) == 0.0

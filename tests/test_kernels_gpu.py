@@ -45,7 +45,7 @@ def backend(dtype, use_tc=None):
 def test_library_loads_and_reports_tcgen05():
     from deepcam_b200 import _lib
     lib = _lib.load()
-    assert lib.dc_abi_version() == 1
+    assert lib.dc_abi_version() == 2
     assert lib.dc_device_supports_tcgen05() == 1, "the GPU box must be an sm_100 B200"
 
 
@@ -469,6 +469,72 @@ def test_multi_pack_matches_definition(dst_dtype):
         assert torch.equal(job[1], ref), job[2:]
         single = ops.pack_weight(job[0], *job[2:], dst_dtype)
         assert torch.equal(single, ref), job[2:]
+
+
+@pytest.mark.parametrize("dst_dtype", DTYPES)
+def test_convT2_pack_matches_definition(dst_dtype):
+    """DC_PACK_NTK_CONVT2 (all four output parities of a k3 s2 p1 ConvTranspose2d as one 2x2-tap contraction): bit-exact
+    against the definition in include/deepcam_b200.h, through the single and the multi-job launch."""
+    from deepcam_b200 import ops
+    from deepcam_b200._lib import DC_PACK_NTK, DC_PACK_NTK_CONVT2
+    torch.manual_seed(17)
+    jobs, expect = [], []
+    for (K, N, K_pad, G) in [(256, 3, 256, 8), (100, 5, 128, 8), (64, 16, 64, 16)]:
+        src = torch.randn(K, N, 9, device=dev())
+        ref = torch.zeros(4 * G, 4, K_pad, device=dev())
+        for a in range(2):
+            for b in range(2):
+                for dh in range(2):
+                    for dw in range(2):
+                        kh, kw = a + 1 - 2 * dh, b + 1 - 2 * dw
+                        if 0 <= kh <= 2 and 0 <= kw <= 2:
+                            c0 = (a * 2 + b) * G
+                            ref[c0:c0 + N, dh * 2 + dw, :K] = src[:, :, kh * 3 + kw].t()
+        dst = torch.full((4 * K_pad * 4 * G,), 7.0, dtype=dst_dtype, device=dev())
+        jobs.append((src, dst, K, N, 4, True, DC_PACK_NTK_CONVT2, K_pad, 4 * G))
+        expect.append(ref.reshape(-1).to(dst_dtype))
+    # a regular job in between: the table walk must not depend on the layout
+    src = torch.randn(40, 24, 9, device=dev())
+    ref = torch.zeros(24, 9, 64, device=dev())
+    ref[:, :, :40] = src.permute(1, 2, 0)
+    jobs.insert(1, (src, torch.full((9 * 64 * 24,), 7.0, dtype=dst_dtype, device=dev()), 40, 24, 9, True, DC_PACK_NTK, 64, 24))
+    expect.insert(1, ref.reshape(-1).to(dst_dtype))
+    ops.pack_weights_multi(*ops.build_pack_table(jobs, dev()))
+    torch.cuda.synchronize()
+    for (job, ref) in zip(jobs, expect):
+        assert torch.equal(job[1], ref), job[2:]
+        assert torch.equal(ops.pack_weight(job[0], *job[2:], dst_dtype), ref), job[2:]
+
+
+@pytest.mark.parametrize("out_dtype", DTYPES)
+@pytest.mark.parametrize("Ci,Co,H,W,cp", [(256, 3, 24, 36, 8), (256, 3, 13, 21, 8), (128, 10, 16, 24, 16), (64, 16, 9, 40, 16)])
+def test_conv_transpose_fused_parities(out_dtype, Ci, Co, H, W, cp):
+    """last_deconv forward (DX:374) as ONE tcgen05 launch over the four output parities (two-segment output rows): same
+    result as nn.ConvTranspose2d and as the four per-parity launches; padded channels are written as zero."""
+    from deepcam_b200.backend import ConvSpec
+    torch.manual_seed(23)
+    N = 2
+    mod = torch.nn.ConvTranspose2d(Ci, Co, 3, stride=2, padding=1, output_padding=1, bias=False)
+    with torch.no_grad():
+        mod.weight.copy_(rounded(mod.weight, torch.bfloat16).float())
+    x = rounded(torch.randn(N, Ci, H, W), torch.bfloat16)
+    ref = mod.double()(x.double()).float()
+    mod = mod.float().to(dev())
+    xg = to_nhwc(x, torch.bfloat16)
+    outs = {}
+    for fused in (True, False):
+        be = backend(torch.bfloat16, use_tc=True)
+        be.fuse_convT = fused
+        spec = ConvSpec("c", mod.weight, None, 2, 1, 1, True)
+        out = torch.full((N, 2 * H, 2 * W, cp), 5.0, dtype=out_dtype, device=dev())
+        n0 = be.launches
+        be.conv_fwd(xg, spec, out)
+        assert be.launches - n0 == (1 if fused else 4)
+        assert ("fprop_convT2", cp) in spec._cache if fused else ("fprop_convT2", cp) not in spec._cache
+        outs[fused] = out
+        assert rel(from_nhwc(out[..., :Co].float()), ref) < (2e-2 if out_dtype == torch.bfloat16 else 2e-3), (fused, out_dtype)
+        assert float(out[..., Co:].float().abs().max()) == 0.0 if cp > Co else True
+    assert rel(outs[True].float(), outs[False].float()) < (1e-2 if out_dtype == torch.bfloat16 else 1e-5)
 
 
 @pytest.mark.parametrize("case", [
