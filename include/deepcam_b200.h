@@ -225,6 +225,10 @@ int dc_gap_fwd(dc_view x, float* mean_nc, void* stream);                       /
 int dc_broadcast_hw(const float* src_nc, dc_view dst, void* stream);           /* dst[n,h,w,c] = src[n][c] */
 int dc_reduce_hw(dc_view x, float* sum_nc, void* stream);                      /* sum over h,w -> [N][C] */
 int dc_gap_bwd(const float* dmean_nc, dc_view dx, int accumulate, void* stream); /* dx (+)= dmean/(H*W) */
+/* F.interpolate(mode='bilinear', align_corners=True) (InterpolationUpsampler, DX:327-331) between any two sizes and its
+ * input gradient (gather form, deterministic).  Channels-last views, C % 4 == 0; out may be fp32 for a bf16 input. */
+int dc_bilinear_fwd(dc_view in, dc_view out, void* stream);
+int dc_bilinear_bwd(dc_view dout, dc_view din, int accumulate, void* stream);    /* din (+)= resize^T(dout) */
 
 /* ---- weighted cross-entropy "fp_loss" (LS:28-52) ------------------------------------------------ */
 /* logits: fp32 view [N,H,W,C] (any strides, e.g. NCHW); target int64 [N*H*W] contiguous;

@@ -13,6 +13,8 @@ Reference quirks reproduced on purpose:
     (DX:206) see relu(input).  Here block outputs that feed such a block are stored already clamped.
   * BatchNorm over the 1x1 image-pooling map fails for batch size 1 in train mode (DX:425-428).
 """
+import math
+
 import torch
 import torch.nn as nn
 
@@ -294,9 +296,10 @@ class ASPP_module(_EngineModule):
 # ---------------------------------------------------------------------------------------------------------
 # DX:315-395
 # ---------------------------------------------------------------------------------------------------------
-class InterpolationUpsampler(nn.Module):
-    """DX:315-344.  Dead code in the reference (DX:438 is commented out); kept importable with its parameters.
-    The bilinear x4 resize kernels are not part of the training hot path."""
+class InterpolationUpsampler(_EngineModule):
+    """DX:315-344: the decoder variant the reference keeps beside DeconvUpsampler (DX:438 is commented out, so
+    DeepLabv3_plus never builds it).  Same constructor, parameters and forward signature; the two
+    F.interpolate(mode='bilinear', align_corners=True) calls run as dc_bilinear_fwd / dc_bilinear_bwd."""
 
     def __init__(self, n_output, normalizer=nn.BatchNorm2d):
         super().__init__()
@@ -305,10 +308,33 @@ class InterpolationUpsampler(nn.Module):
                                        nn.Conv2d(256, 256, kernel_size=3, stride=1, padding=1, bias=False),
                                        normalizer(256), nn.ReLU(),
                                        nn.Conv2d(256, n_output, kernel_size=1, stride=1))
+        self.n_output = n_output
+
+    def _emit(self, eng, x, low):
+        n = x.shape[0]
+        hl, wl, cl = low.shape[1:]
+        out_h, out_w = self._dc_plan_key
+        if (hl, wl) != (int(math.ceil(out_h / 4)), int(math.ceil(out_w / 4))):
+            # the reference fails in torch.cat (DX:329) for the same reason
+            raise RuntimeError("InterpolationUpsampler: low_level_features are %dx%d, ceil(input_size / 4) is %dx%d"
+                               % (hl, wl, int(math.ceil(out_h / 4)), int(math.ceil(out_w / 4))))
+        c = x.shape[3]
+        cat = eng.new_act(n, hl, wl, c + cl, x.t.dtype)
+        eng.bn(low, None, relu=False, out=cat.slice(c, cl))                      # copy (torch.cat, DX:329)
+        eng.bilinear(x, hl, wl, out=cat.slice(0, c))                             # DX:327-328
+        lc = self.last_conv
+        y = eng.bn(eng.conv(cat, _conv_spec(lc[0]), bn=_bn_spec(lc[1])), _bn_spec(lc[1]), relu=True)
+        y = eng.bn(eng.conv(y, _conv_spec(lc[3]), bn=_bn_spec(lc[4])), _bn_spec(lc[4]), relu=True)
+        pad = 8 if y.t.dtype == torch.bfloat16 else 4
+        y = eng.conv(y, _conv_spec(lc[6]), out_c=(self.n_output + pad - 1) // pad * pad)
+        return eng.bilinear(y, out_h, out_w, out_dtype=torch.float32)            # DX:331
+
+    def _emit_root(self, eng, x, low):
+        return [(self._emit(eng, x, low), self.n_output)]
 
     def forward(self, x, low_level_features, input_size):
-        raise NotImplementedError("deepcam_b200: InterpolationUpsampler is not on the DeepCAM hot path "
-                                  "(the reference selects DeconvUpsampler, DX:439)")
+        self._dc_plan_key = (int(input_size[-2]), int(input_size[-1]))
+        return _engine.run_module(self, [x, low_level_features])[0]
 
 
 class DeconvUpsampler(_EngineModule):

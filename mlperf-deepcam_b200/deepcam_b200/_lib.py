@@ -87,6 +87,8 @@ SIGNATURES = {
     "dc_broadcast_hw": (c_int, [c_void_p, dc_view, c_void_p]),
     "dc_reduce_hw": (c_int, [dc_view, c_void_p, c_void_p]),
     "dc_gap_bwd": (c_int, [c_void_p, dc_view, c_int, c_void_p]),
+    "dc_bilinear_fwd": (c_int, [dc_view, dc_view, c_void_p]),
+    "dc_bilinear_bwd": (c_int, [dc_view, dc_view, c_int, c_void_p]),
     "dc_wce_fwd": (c_int, [dc_view, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dc_wce_bwd": (c_int, [dc_view, c_void_p, c_void_p, c_void_p, dc_view, c_void_p]),
     "dc_iou_counts": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),

@@ -518,3 +518,14 @@ class CudaBackend:
         ops.gap_bwd(dmean_nc, dx, accumulate)
         self.launches += 1
         return dx
+
+    # ---- bilinear resize (InterpolationUpsampler, DX:327-331) ----------------------------------------------------
+    def bilinear_fwd(self, x, out):
+        ops.bilinear_fwd(x, out)
+        self.launches += 1
+        return out
+
+    def bilinear_bwd(self, dout, din, accumulate):
+        ops.bilinear_bwd(dout, din, accumulate)
+        self.launches += 1
+        return din

@@ -331,6 +331,26 @@ class Engine:
             raise RuntimeError("broadcast source gradient must have a single writer")
         src.grad = self.be.reduce_hw(g).view(n, 1, 1, c)
 
+    def bilinear(self, x, ho, wo, out=None, out_dtype=None):
+        """F.interpolate(x, size=(ho, wo), mode='bilinear', align_corners=True) (DX:327-331); `out` may be a concat slice."""
+        n, _, _, c = x.shape
+        x.consumed += 1
+        if out is None:
+            out = self.new_act(n, ho, wo, c, out_dtype or x.t.dtype)
+        elif out.shape != (n, ho, wo, c):
+            raise RuntimeError("bilinear: output buffer %s does not match %s" % (out.shape, (n, ho, wo, c)))
+        self.be.bilinear_fwd(x.t, out.t)
+        if self.record:
+            self.tape.append(lambda: self._bilinear_bwd(x, out))
+        return out
+
+    def _bilinear_bwd(self, x, out):
+        g = out.grad
+        if g is None or not x.needs_grad:
+            return
+        dx, acc = self.grad_target(x)
+        self.be.bilinear_bwd(g, dx, acc)
+
     # ---- execution ----------------------------------------------------------------------------------------
     def finish_forward(self):
         if self.bn_trained:
@@ -643,7 +663,7 @@ def _graph_plan(module, precision, inputs, params, need_grad):
         return None
     key = (precision, need_grad, tuple(tuple(x.shape) + (x.dtype, bool(x.requires_grad)) for x in inputs),
            tuple(m.training for m in _bn_modules(module)), tuple(p.requires_grad for p in params), device.index,
-           torch.cuda.current_stream(device).cuda_stream)
+           torch.cuda.current_stream(device).cuda_stream, getattr(module, "_dc_plan_key", None))
     plans = module.__dict__.setdefault("_dc_plans", {})
     ent = plans.get(key)
     if ent is None:

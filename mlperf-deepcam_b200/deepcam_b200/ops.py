@@ -425,6 +425,22 @@ def gap_bwd(dmean_nc, dx, accumulate):
     return dx
 
 
+def bilinear_fwd(x, out):
+    """out <- F.interpolate(x, size=out.shape[1:3], mode='bilinear', align_corners=True) on channels-last views (DX:327-331)."""
+    _require_cuda(x, out)
+    _timed("bilinear_fwd", 8.0 * out.numel(), _nbytes(x, out), lambda: _lib.load().dc_bilinear_fwd(view(x), view(out), _stream()),
+           "dc_bilinear_fwd", tag=_shape_tag(out))
+    return out
+
+
+def bilinear_bwd(dout, din, accumulate):
+    """din (+)= gradient of bilinear_fwd with respect to its input."""
+    _require_cuda(dout, din)
+    _timed("bilinear_bwd", 2.0 * 4 * dout.numel(), _nbytes(dout, din),
+           lambda: _lib.load().dc_bilinear_bwd(view(dout), view(din), int(accumulate), _stream()), "dc_bilinear_bwd", tag=_shape_tag(dout))
+    return din
+
+
 # ---- loss / metric -------------------------------------------------------------------------------------------
 def wce_fwd(logits_nhwc, target, class_w, acc, loss_out):
     _require_cuda(logits_nhwc, target, class_w)

@@ -299,6 +299,22 @@ def forward(P, x, train=True, os=16, tape=None):
     return logits
 
 
+def interpolation_upsampler(P, x, low, input_size, train=True, tape=None):
+    """InterpolationUpsampler.forward, DX:326-333 (the decoder variant DeepLabv3_plus leaves commented out at DX:438).
+    P holds the module's own state_dict keys ("last_conv.0.weight", ...).  Pinned against the live reference class by
+    tests/test_engine_graph_cpu.py::test_interpolation_upsampler_matches_reference."""
+    tape = tape if tape is not None else Tape(False)
+    size = (int(math.ceil(input_size[-2] / 4)), int(math.ceil(input_size[-1] / 4)))
+    y = F.interpolate(x, size=size, mode="bilinear", align_corners=True)
+    y = torch.cat((y, low), dim=1)
+    t = F.conv2d(y, P["last_conv.0.weight"], None, 1, 1)
+    y = _bn(P, "last_conv.1", t, train, tape, relu=True)
+    t = F.conv2d(y, P["last_conv.3.weight"], None, 1, 1)
+    y = _bn(P, "last_conv.4", t, train, tape, relu=True)
+    t = F.conv2d(y, P["last_conv.6.weight"], P["last_conv.6.bias"])
+    return F.interpolate(t, size=tuple(input_size[2:]), mode="bilinear", align_corners=True)
+
+
 # --------------------------------------------------------------------------------------------------
 # loss and metric
 # --------------------------------------------------------------------------------------------------

@@ -195,6 +195,47 @@ def test_os8_configuration_matches_reference():
     assert _rel(b, a) < 2e-4 and _rel(lb, la) < 1e-4
 
 
+@pytest.mark.reference
+def test_interpolation_upsampler_matches_reference():
+    """DX:315-335: same parameters, forward signature and results as the reference class; the oracle
+    restatement used by the GPU parity test is pinned here against the same live reference run."""
+    import refload
+    rdx = refload.deeplab()
+    torch.manual_seed(8)
+    ref = rdx.InterpolationUpsampler(3)
+    torch.manual_seed(8)
+    mine = dx.InterpolationUpsampler(3)
+    mine.precision = "fp32"
+    for (k, v), (k2, v2) in zip(ref.state_dict().items(), mine.state_dict().items()):
+        assert k == k2 and torch.equal(v, v2), k
+    input_size = torch.Size((2, 16, 30, 44))                  # ceil(30/4) x ceil(44/4) = 8 x 11 low-level map
+    x = torch.randn(2, 256, 2, 3)
+    low = torch.randn(2, 48, 8, 11)
+    xr, lr_ = x.clone().requires_grad_(True), low.clone().requires_grad_(True)
+    yr = ref(xr, lr_, input_size)
+    P = {k: v.clone() for k, v in ref.state_dict().items()}
+    # (the reference forward above already updated its running statistics; the oracle gets its own copy of the initial ones)
+    P0 = {k: v.clone() for k, v in mine.state_dict().items()}
+    yo = O.interpolation_upsampler(P0, x, low, input_size)
+    assert torch.allclose(yo, yr, atol=1e-6)
+    for k in P:
+        assert torch.allclose(P0[k].float(), P[k].float(), atol=1e-6), k
+    xm, lm = x.clone().requires_grad_(True), low.clone().requires_grad_(True)
+    ym = mine(xm, lm, input_size)
+    assert ym.shape == yr.shape == (2, 3, 30, 44)
+    assert _rel(ym, yr) < 1e-5
+    g = torch.randn_like(yr)
+    yr.backward(g)
+    ym.backward(g)
+    assert _rel(xm.grad, xr.grad) < 1e-4 and _rel(lm.grad, lr_.grad) < 1e-4
+    for (k, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert _rel(p.grad, q.grad) < 1e-4, k
+    for k, v in mine.state_dict().items():
+        assert torch.allclose(v.float(), ref.state_dict()[k].float(), atol=1e-5), k
+    with pytest.raises(RuntimeError, match="low_level_features"):
+        mine(x, low, torch.Size((2, 16, 64, 64)))
+
+
 def test_cpu_input_without_test_backend_raises_loudly():
     torch_backend.uninstall()
     m = dx.SeparableConv2d_same(8, 16)

@@ -731,3 +731,37 @@ def test_fused_lars_matches_restatement(wd):
         torch.cuda.synchronize()
         for p, r in zip(my_p, ref_p):
             assert rel(p, r) < 2e-6
+
+
+# --------------------------------------------------------------------------------------------------
+# bilinear resize, align_corners=True (InterpolationUpsampler, DX:327-331)
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,out_dtype", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                             (torch.bfloat16, torch.float32)])
+@pytest.mark.parametrize("C,hi,wi,ho,wo", [(256, 6, 9, 24, 36), (4, 48, 72, 192, 288), (8, 8, 11, 30, 44), (16, 13, 7, 5, 20),
+                                           (4, 1, 1, 6, 5), (8, 5, 6, 1, 1), (12, 7, 9, 7, 9)])
+def test_bilinear_resize_matches_torch(dtype, out_dtype, C, hi, wi, ho, wo):
+    """dc_bilinear_fwd / dc_bilinear_bwd against F.interpolate(mode='bilinear', align_corners=True) in float64 on the same
+    storage-rounded inputs: up- and down-sampling, degenerate 1x1 sizes, identity, concat-slice output, accumulation."""
+    torch.manual_seed(31)
+    be = backend(dtype)
+    N = 2
+    x = rounded(torch.randn(N, C, hi, wi), dtype).requires_grad_(True)
+    ref = F.interpolate(x, size=(ho, wo), mode="bilinear", align_corners=True)
+    tol = TOL[torch.float32] if out_dtype == torch.float32 else TOL[torch.bfloat16]
+    xg = to_nhwc(x.detach(), dtype)
+    buf = torch.full((N, ho, wo, C + 8), 3.0, dtype=out_dtype, device=dev())
+    out = buf[..., 4:4 + C]                                       # channel slice of a wider (concat) buffer
+    be.bilinear_fwd(xg, out)
+    assert rel(from_nhwc(out), ref) < tol
+    assert float((buf[..., :4] - 3.0).abs().max()) == 0.0 and float((buf[..., 4 + C:] - 3.0).abs().max()) == 0.0
+    dy = rounded(torch.randn(N, C, ho, wo), dtype)
+    ref.backward(dy)
+    gbuf = torch.zeros(N, ho, wo, C + 8, dtype=dtype, device=dev())
+    gbuf[..., 4:4 + C] = to_nhwc(dy, dtype)
+    dx = torch.full((N, hi, wi, C), 9.0, dtype=dtype, device=dev())
+    be.bilinear_bwd(gbuf[..., 4:4 + C], dx, False)
+    assert rel(from_nhwc(dx), x.grad) < TOL[dtype]
+    first = dx.clone()
+    be.bilinear_bwd(gbuf[..., 4:4 + C], dx, True)
+    assert rel(from_nhwc(dx), 2 * from_nhwc(first)) < TOL[dtype]

@@ -266,3 +266,45 @@ def test_full_size_step_properties(sd):
     score = dcutils.compute_score(pred, ld, num_classes=3, device_id=0)
     iou = [(float(tp[j]) / float(tp[j] + fp[j] + fn[j])) if int(tp[j] + fp[j] + fn[j]) else 1.0 for j in range(3)]
     assert abs(float(score) - sum(iou) / 3.0) < 1e-6
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_interpolation_upsampler_matches_oracle(precision, monkeypatch):
+    """InterpolationUpsampler (DX:315-335) on the CUDA path (bilinear kernels, concat slice, biased 1x1)
+    against the oracle restatement (pinned to the live reference class in tests/test_engine_graph_cpu.py), through the eager
+    engine, the captured CUDA-graph plan and its replay; a different input_size selects a different plan."""
+    monkeypatch.setenv("DEEPCAM_B200_GRAPHS", "1")
+    torch.manual_seed(41)
+    mod = dx.InterpolationUpsampler(3)
+    mod.precision = precision
+    sd0 = {k: v.clone() for k, v in mod.state_dict().items()}
+    mod = mod.to(DEV).train()
+    x = torch.randn(2, 256, 6, 9)
+    low = torch.randn(2, 48, 24, 36)
+    if precision == "bf16":
+        x, low = x.bfloat16().float(), low.bfloat16().float()
+    input_size = torch.Size((2, 16, 96, 144))
+    P = {k: (v.double().requires_grad_(True) if k.endswith("weight") or k.endswith("bias") else
+             (v.double() if v.is_floating_point() else v.clone())) for k, v in sd0.items()}
+    xr, lr_ = x.double().requires_grad_(True), low.double().requires_grad_(True)
+    ref = O.interpolation_upsampler(P, xr, lr_, input_size)
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    tol_out, tol_grad = (1e-4, 1e-3) if precision == "fp32" else (3e-2, 1e-1)
+    for it in range(3):                                            # eager, capture, replay
+        xm, lm = x.to(DEV).requires_grad_(True), low.to(DEV).requires_grad_(True)
+        out = mod(xm, lm, input_size)
+        assert out.shape == (2, 3, 96, 144) and out.dtype == torch.float32
+        assert _rel(out, ref) < tol_out, (it, _rel(out, ref))
+        mod.zero_grad()
+        out.backward(g.float().to(DEV))
+        assert _rel(xm.grad, xr.grad) < tol_grad and _rel(lm.grad, lr_.grad) < tol_grad, it
+        for k, p in mod.named_parameters():
+            assert _rel(p.grad, P[k].grad) < tol_grad, (it, k, _rel(p.grad, P[k].grad))
+    # odd output size (ceil(H/4) low-level map) on the same module: a new plan, same parity
+    input_size2 = torch.Size((2, 16, 94, 141))
+    P2 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd0.items()}
+    ref2 = O.interpolation_upsampler(P2, x.double(), low.double(), input_size2)
+    with torch.no_grad():
+        out2 = mod(x.to(DEV), low.to(DEV), input_size2)
+    assert out2.shape == (2, 3, 94, 141) and _rel(out2, ref2) < tol_out

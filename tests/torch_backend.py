@@ -200,6 +200,22 @@ class TorchBackend:
         return dx
 
 
+    def bilinear_fwd(self, x, out):
+        y = F.interpolate(x.double().permute(0, 3, 1, 2), size=tuple(out.shape[1:3]), mode="bilinear", align_corners=True)
+        out.copy_(y.permute(0, 2, 3, 1).to(out.dtype))
+        return out
+
+    def bilinear_bwd(self, dout, din, accumulate):
+        n, h, w, c = din.shape
+        with torch.enable_grad():
+            x = torch.zeros(n, c, h, w, dtype=torch.double, requires_grad=True)
+            y = F.interpolate(x, size=tuple(dout.shape[1:3]), mode="bilinear", align_corners=True)
+            (g,) = torch.autograd.grad(y, x, dout.double().permute(0, 3, 1, 2))
+        g = g.permute(0, 2, 3, 1)
+        din.copy_(((din.double() + g) if accumulate else g).to(din.dtype))
+        return din
+
+
 def install():
     from deepcam_b200 import engine
     engine.set_backend_factory(lambda dtype, device: TorchBackend(dtype, device))
