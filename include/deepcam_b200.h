@@ -217,8 +217,9 @@ int dc_bn_onepass_ok(int C, long long npix, int dtype, int backward);
 int dc_bn_fwd_onepass(const dc_bn_params* p, dc_view y, dc_view residual, dc_view out, void* stream);
 int dc_bn_bwd_onepass(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, void* rws, dc_view dy, dc_view dres,
                       float* dgamma, float* dbeta, void* stream);
-/* per-channel sum over n,h,w into fp32 [C] (bias gradient of upsample.conv1.6, DX:366); ws_c: C doubles of scratch */
-int dc_channel_sum(dc_view x, double* ws_c, float* out_c, void* stream);
+/* per-channel sum over n,h,w; the first n_out (<= C) sums are written to fp32 out_c (bias gradient of upsample.conv1.6,
+ * DX:366; n_out < C when x carries padding channels); ws_c: C doubles of scratch */
+int dc_channel_sum(dc_view x, double* ws_c, float* out_c, int n_out, void* stream);
 
 /* ---- image-pooling branch (AdaptiveAvgPool2d DX:425, F.interpolate 1x1 -> HxW DX:450) ---------- */
 int dc_gap_fwd(dc_view x, float* mean_nc, void* stream);                       /* [N][C] fp32 */

@@ -1132,8 +1132,9 @@ int dc_bn_bwd_onepass(const dc_bn_params* p, dc_view dout, dc_view out, dc_view 
 }
 
 /* channel sum with a caller-provided double workspace of C elements */
-int dc_channel_sum(dc_view x, double* ws_c, float* out_c, void* stream) {
+int dc_channel_sum(dc_view x, double* ws_c, float* out_c, int n_out, void* stream) {
   DC_REQUIRE(views_ok(x, nullptr, 0) && out_c != nullptr && ws_c != nullptr, "dc_channel_sum: bad arguments");
+  DC_REQUIRE(n_out >= 1 && n_out <= x.c, "dc_channel_sum: n_out must be in 1..C");
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(ws_c, 0, sizeof(double) * x.c, st);
   if (e != cudaSuccess) return dc::fail((int)e, "dc_channel_sum: %s", cudaGetErrorString(e));
@@ -1145,7 +1146,7 @@ int dc_channel_sum(dc_view x, double* ws_c, float* out_c, void* stream) {
     LaneMap m = lane_map(x.c, 8);
     launch_k(channel_sum_kernel<__nv_bfloat16, 8>, bn_grid(m, npix, 8), dim3(kBnThreads), red_smem<1, 8>(), st, pix_view<const __nv_bfloat16>(x), ws_c, x.c, npix, m);
   }
-  double_to_float_kernel<<<ceil_div(x.c, 256), 256, 0, st>>>(ws_c, out_c, x.c);
+  double_to_float_kernel<<<ceil_div(n_out, 256), 256, 0, st>>>(ws_c, out_c, n_out);
   return launch_status("dc_channel_sum");
 }
 

@@ -82,7 +82,7 @@ SIGNATURES = {
     "dc_bn_fwd_onepass": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p]),
     "dc_bn_bwd_onepass": (c_int, [POINTER(dc_bn_params), dc_view, dc_view, dc_view, c_void_p, dc_view, dc_view, c_void_p,
                                   c_void_p, c_void_p]),
-    "dc_channel_sum": (c_int, [dc_view, c_void_p, c_void_p, c_void_p]),
+    "dc_channel_sum": (c_int, [dc_view, c_void_p, c_void_p, c_int, c_void_p]),
     "dc_gap_fwd": (c_int, [dc_view, c_void_p, c_void_p]),
     "dc_broadcast_hw": (c_int, [c_void_p, dc_view, c_void_p]),
     "dc_reduce_hw": (c_int, [dc_view, c_void_p, c_void_p]),

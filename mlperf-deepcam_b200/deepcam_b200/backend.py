@@ -350,7 +350,7 @@ class CudaBackend:
             K, N = spec.ci, spec.co          # G is [tap][co][ci]
         impl = "tc" if (self._tc_ok(gathered, 16) and self._tc_ok(enumerated, 16)) else "simt"
         desc = ops.make_desc(taps, (spec.stride, spec.stride), False, kk)
-        if kk == 1:
+        if kk == 1 and enumerated.shape[3] == N:
             ops.conv_wgrad(desc, gathered, enumerated, wgrad, impl)       # [co][ci] is already the parameter layout
             self.launches += 1
         else:
@@ -360,7 +360,7 @@ class CudaBackend:
             ops.unpack_wgrad(G, K, N, kk, False, wgrad, k_stride=ks)
             self.launches += 2
         if bgrad is not None:
-            ws = self.scratch(spec.co, torch.float64, zero=True)
+            ws = self.scratch(dy.shape[3], torch.float64, zero=True)     # dy may carry padding channels beyond spec.co
             ops.channel_sum(dy, ws, bgrad)
             self.launches += 2
         return wgrad

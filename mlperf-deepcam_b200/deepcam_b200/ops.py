@@ -392,7 +392,8 @@ def bn_bwd_apply(params, dout, out, y, rws, dy, dres):
 def channel_sum(x, ws, out_c):
     _require_cuda(x, ws, out_c)
     assert ws.dtype == torch.float64 and ws.numel() >= x.shape[3] and out_c.dtype == torch.float32
-    check(_lib.load().dc_channel_sum(view(x), _p(ws), _p(out_c), _stream()), "dc_channel_sum")
+    assert 1 <= out_c.numel() <= x.shape[3] and out_c.is_contiguous()
+    check(_lib.load().dc_channel_sum(view(x), _p(ws), _p(out_c), out_c.numel(), _stream()), "dc_channel_sum")
     return out_c
 
 
