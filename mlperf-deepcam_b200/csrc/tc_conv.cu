@@ -184,6 +184,17 @@ struct TcFpropParams {
   int stats_C;         // per-channel sum and sum of squares of the bf16-rounded outputs it stores (TMA-store path only)
 };
 
+// Build with -DDC_TC_TRACE (tools/tc_trace.py) to record SM-clock timestamps of the persistent kernel's phases per CTA:
+// slot 0 entry, 1 after griddepcontrol.wait, 2 first operand stage landed, 3 last MMA issued, 4 accumulator complete (seen by
+// the epilogue), 5 epilogue done, 6 exit, 7 globaltimer at entry,
+// 8 first chunk converted + staged, 9 first chunk's TMA store issued, 10 first chunk's statistics done.  The product build compiles the macro away.
+#ifdef DC_TC_TRACE
+__device__ unsigned long long g_tc_trace[148 * 16];
+#define TC_TRACE(slot) do { g_tc_trace[blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); } while (0)
+#else
+#define TC_TRACE(slot) do { } while (0)
+#endif
+
 constexpr int kTcThreads = 192;
 constexpr int kABytes = 128 * 128;   // 128 rows x 64 bf16
 
@@ -456,6 +467,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef DC_TC_TRACE
+  if (threadIdx.x == 0) {
+    TC_TRACE(0);
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    g_tc_trace[blockIdx.x * 16 + 7] = gt;
+  }
+#endif
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -478,6 +497,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   pdl_sync();     // everything above overlapped the previous kernel's tail; global memory is touched only below
+  if (threadIdx.x == 0) TC_TRACE(1);
 
   const int b_block_bytes = BN * 128;
 
@@ -544,6 +564,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
           for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
             mbar_wait(full_bar(s), ph);
             tc_fence_after();
+            if (i == 0 && it == 0) TC_TRACE(2);
             const uint32_t sa = smem_base + s * cfg.stage_bytes;
             const uint32_t sb = cfg.b_resident ? (bres_base + (uint32_t)(kb0 + kb) * b_block_bytes) : (sa + MT * kABytes);
             const uint64_t da = make_smem_desc(sa, 16, 1024);
@@ -569,6 +590,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
           }
         }
         umma_commit(tfull_bar(buf));
+        TC_TRACE(3);
       }
     }
   } else {
@@ -604,6 +626,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
       if (sub == 0) {
         mbar_wait(tfull_bar(buf), single_acc ? ((uint32_t)i & 1u) : (((uint32_t)i >> 1) & 1u));
         tc_fence_after();
+        if (threadIdx.x == 64) TC_TRACE(4);
       }
       const uint32_t acc = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((cfg.bm2 ? sub : buf) * cfg.acc_stride);
       if (cfg.tma_store) {
@@ -651,11 +674,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
           }
           fence_proxy_async();
           epi_bar_sync();
+          if (elected && c0 == 0) TC_TRACE(8);
           if (elected) {
             const uint32_t src = stg_s + (uint32_t)(chunk_ctr & 1) * 16384u;
             if (p.accumulate) tma_reduce_add_4d(&maps.c, src, n0 + c0, tile_x * p.TW, tile_y * p.TH, img);
             else tma_store_4d(&maps.c, src, n0 + c0, tile_x * p.TW, tile_y * p.TH, img);
             tma_store_commit();
+            if (c0 == 0) TC_TRACE(9);
           }
           if (p.stats != nullptr) {
             // ---- BatchNorm statistics of this 128 x 64 chunk, from the staged (bf16-rounded) values: warp = 32 rows, lane =
@@ -681,6 +706,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
             const float tot = sred[t] + sred[128 + t] + sred[256 + t] + sred[384 + t];
             const int col = c0 + (t & 63);
             if (col < ncols) atomicAdd(p.stats + (size_t)(t >> 6) * p.stats_C + n0 + col, (double)tot);
+            if (elected && c0 == 0) TC_TRACE(10);
           }
         }
         continue;
@@ -794,9 +820,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
      }
     }
   }
+  if (threadIdx.x == 64) TC_TRACE(5);
   if (cfg.tma_store && threadIdx.x == 64) tma_store_wait_all();     // staging must stay valid until the last store has read it
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TC_TRACE(6);
   if (warp == 1) tmem_dealloc(tmem_base, cfg.tmem_cols);
 }
 
@@ -1262,6 +1290,14 @@ static int conv_gemm_tc_impl(const dc_conv_desc* d, dc_view in, const void* w, c
   if (int r = encode_weight_map(&maps.b, w, Ktot, out.c, cfg.BN, "dc_conv_gemm_tc")) return r;
   return launch_fprop(maps, p, cfg, mtiles, ceil_div(out.c, cfg.BN), as_stream(stream));
 }
+
+#ifdef DC_TC_TRACE
+// trace build only (tools/tc_trace.py): copies the 148 x 16 timestamp table to the host
+int dc_tc_trace_read(unsigned long long* host) {
+  cudaError_t e = cudaMemcpyFromSymbol(host, g_tc_trace, sizeof(unsigned long long) * 148 * 16);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+#endif
 
 int dc_conv_gemm_tc(const dc_conv_desc* d, dc_view in, const void* w, const float* bias, dc_view out, void* stream) {
   return conv_gemm_tc_impl(d, in, w, bias, out, nullptr, nullptr, stream);
