@@ -440,13 +440,21 @@ struct TcV2Cfg {
   int smem_bytes;
 };
 constexpr int kV2StagePitchF32 = 64 * 4 + 16;     // staged row: 64 fp32 columns + 16 B (odd multiple of 16 B: conflict-free)
-constexpr int kV2StagingBytes = 4 * 32 * kV2StagePitchF32;
+// generic epilogue: 4 warps x 32 staged rows; TMA-store epilogue: one 16 KB chunk buffer + 2 KB of statistics scratch per
+// epilogue group
+constexpr int kV2StagingBytes = 2 * 16384 + 2 * 2048;
+static_assert(kV2StagingBytes >= 4 * 32 * kV2StagePitchF32, "staging must also hold the generic epilogue's rows");
+// warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue group A, warps 6..9 = epilogue group B.  With one warp
+// per scheduler the epilogue is latency-bound (tools/tc_trace.py: 0.7 us per 128 x 64 chunk, 4.3 of the 11 us of a 728 x 728
+// layer); the two groups drain alternate 64-column chunks of the same accumulator concurrently.
+constexpr int kTc2Threads = 320;
+__device__ __forceinline__ void epi_group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __grid_constant__ TcMaps maps, const TcFpropParams p,
+__global__ void __launch_bounds__(kTc2Threads, 1) conv_gemm_tc2_kernel(const __grid_constant__ TcMaps maps, const TcFpropParams p,
                                                                       const TcV2Cfg cfg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -478,7 +486,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), cfg.bm2 ? 8 : 4); }   // (wide: one accumulator, 4 epilogue warps)
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), cfg.bm2 ? 16 : 8); }   // every epilogue warp of both groups arrives once per (sub-)tile
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
@@ -594,7 +602,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
       }
     }
   } else {
-    // ---- epilogue: warps 2..5; warp w may only touch TMEM lanes 32*(w%4) .. +31 ----
+    // ---- epilogue: warps 2..9 (two groups); warp w may only touch TMEM lanes 32*(w%4) .. +31 ----
+    const int grp = (warp - 2) >> 2;
     const int lg = warp & 3;
     const int row = lg * 32 + lane;
     const int ty = row / p.TW, tx = row - ty * p.TW;
@@ -605,7 +614,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
     const int V = stage_f32 ? 4 : 8;
     const bool raw_copy = !stage_f32 && p.out_vec_ok;
     int i = 0;
-    int chunk_ctr = 0;
     const int MT = cfg.bm2 ? 2 : 1;
     for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++i) {
      for (int sub = 0; sub < MT; ++sub) {
@@ -627,28 +635,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
         mbar_wait(tfull_bar(buf), single_acc ? ((uint32_t)i & 1u) : (((uint32_t)i >> 1) & 1u));
         tc_fence_after();
         if (threadIdx.x == 64) TC_TRACE(4);
+        if (threadIdx.x == 192) TC_TRACE(12);
       }
       const uint32_t acc = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((cfg.bm2 ? sub : buf) * cfg.acc_stride);
       if (cfg.tma_store) {
         // ---- fast path: 128 rows x 64 bf16 columns per chunk, 128B-swizzled staging (two buffers), one TMA store
         //      (or TMA reduce-add for gradient accumulation) per chunk issued by one elected thread ----
-        const bool elected = (threadIdx.x == 64);
-        const uint32_t stg_s = smem_base + stg_off;
+        // group g drains chunks g, g+2, ... through its own 16 KB staging buffer, elected thread and named barrier
+        const bool elected = (threadIdx.x == 64 + 128 * grp);
+        const uint32_t stg_s = smem_base + stg_off + (uint32_t)grp * 16384u;
+        if (grp * 64 >= ncols) {            // no chunk for this group in this N tile: nothing to drain
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
 #pragma unroll 1
-        for (int c0 = 0; c0 < ncols; c0 += 64, ++chunk_ctr) {
+        for (int c0 = grp * 64; c0 < ncols; c0 += 128) {
           uint32_t v[2][32];
           const bool two = (c0 + 32 < ncols);
           tmem_ld32(acc + (uint32_t)c0, v[0]);
           if (two) tmem_ld32(acc + (uint32_t)(c0 + 32), v[1]);
-          if (elected) tma_store_wait_read<1>();        // the store that used this staging buffer two chunks ago has read it
+          if (elected) tma_store_wait_read<0>();        // this group's previous store has read the staging buffer
           tmem_ld_wait();
-          if (c0 + 64 >= ncols) {
+          if (c0 + 128 >= ncols) {                      // this group's last chunk of the accumulator
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
           }
-          epi_bar_sync();
-          const uint32_t sbuf = stg_s + (uint32_t)(chunk_ctr & 1) * 16384u + (uint32_t)row * 128u;
+          epi_group_sync(grp);
+          const uint32_t sbuf = stg_s + (uint32_t)row * 128u;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -673,10 +688,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
             }
           }
           fence_proxy_async();
-          epi_bar_sync();
+          epi_group_sync(grp);
           if (elected && c0 == 0) TC_TRACE(8);
           if (elected) {
-            const uint32_t src = stg_s + (uint32_t)(chunk_ctr & 1) * 16384u;
+            const uint32_t src = stg_s;
             if (p.accumulate) tma_reduce_add_4d(&maps.c, src, n0 + c0, tile_x * p.TW, tile_y * p.TH, img);
             else tma_store_4d(&maps.c, src, n0 + c0, tile_x * p.TW, tile_y * p.TH, img);
             tma_store_commit();
@@ -686,7 +701,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
             // ---- BatchNorm statistics of this 128 x 64 chunk, from the staged (bf16-rounded) values: warp = 32 rows, lane =
             //      one column pair (conflict-free 4-byte reads of the swizzled rows); the four row groups are combined through
             //      2 KB of shared memory and every thread issues ONE fp64 atomic (64 columns x {sum, sum of squares}) ----
-            const uint32_t sb = stg_s + (uint32_t)(chunk_ctr & 1) * 16384u;
+            const uint32_t sb = stg_s;
             const uint32_t cj16 = (uint32_t)lane >> 2, coff = ((uint32_t)lane & 3u) * 4u;
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
@@ -698,17 +713,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
               s0 += a; s1 += b;
               q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
             }
-            float* sred = reinterpret_cast<float*>(smem_gen + stg_off + 32768);      // [4 row groups][sum 64 | sumsq 64]
+            float* sred = reinterpret_cast<float*>(smem_gen + stg_off + 32768 + grp * 2048);      // [4 row groups][sum 64 | sumsq 64]
             sred[lg * 128 + 2 * lane] = s0; sred[lg * 128 + 2 * lane + 1] = s1;
             sred[lg * 128 + 64 + 2 * lane] = q0; sred[lg * 128 + 64 + 2 * lane + 1] = q1;
-            epi_bar_sync();
-            const int t = (int)threadIdx.x - 64;                 // 0..127: statistic (t >> 6), column (t & 63)
+            epi_group_sync(grp);
+            const int t = (int)threadIdx.x - 64 - 128 * grp;     // 0..127: statistic (t >> 6), column (t & 63)
             const float tot = sred[t] + sred[128 + t] + sred[256 + t] + sred[384 + t];
             const int col = c0 + (t & 63);
             if (col < ncols) atomicAdd(p.stats + (size_t)(t >> 6) * p.stats_C + n0 + col, (double)tot);
             if (elected && c0 == 0) TC_TRACE(10);
           }
         }
+        continue;
+      }
+      if (grp == 1) {                       // generic (strided / fp32 / accumulating) epilogue: group A alone, per-warp staging
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(buf));
         continue;
       }
 #pragma unroll 1
@@ -821,7 +842,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc2_kernel(const __gr
     }
   }
   if (threadIdx.x == 64) TC_TRACE(5);
-  if (cfg.tma_store && threadIdx.x == 64) tma_store_wait_all();     // staging must stay valid until the last store has read it
+  if (threadIdx.x == 192) TC_TRACE(11);
+  if (cfg.tma_store && (threadIdx.x == 64 || threadIdx.x == 192)) tma_store_wait_all();     // staging must stay valid until the last store has read it
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TC_TRACE(6);
@@ -1217,7 +1239,7 @@ static int launch_fprop_v2(const TcMaps& maps, const TcFpropParams& p, const TcV
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int grid = std::min(cfg.total_tiles, kNumSMs);
-  launch_k(conv_gemm_tc2_kernel, grid, dim3(kTcThreads), (size_t)cfg.smem_bytes, st, maps, p, cfg);
+  launch_k(conv_gemm_tc2_kernel, grid, dim3(kTc2Threads), (size_t)cfg.smem_bytes, st, maps, p, cfg);
   return launch_status("dc_conv_gemm_tc");
 }
 

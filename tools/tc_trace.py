@@ -19,7 +19,8 @@ sys.path.insert(0, os.path.join(REPO, "mlperf-deepcam_b200"))
 TRACE_DIR = os.path.join(REPO, "tools", "_trace")
 TRACE_LIB = os.path.join(TRACE_DIR, "libdeepcam_b200_trace.so")
 SLOTS = ["entry", "after_pdl_wait", "first_stage_landed", "last_mma_issued", "accumulator_complete", "epilogue_done", "exit",
-         "globaltimer", "chunk0_staged", "chunk0_store_issued", "chunk0_stats_done"]
+         "globaltimer", "chunk0_staged", "chunk0_store_issued", "chunk0_stats_done", "epilogue_done_group_b",
+         "accumulator_complete_group_b"]
 
 
 def build():
@@ -53,10 +54,7 @@ def main():
     dev = torch.device("cuda:0")
     be = CudaBackend(dtype=torch.bfloat16, device=dev, use_tc=True)
     prop = torch.cuda.get_device_properties(0)
-    try:
-        ghz = torch.cuda.clock_rate() / 1000.0           # current SM clock (pynvml); B200 boost is 1.965 GHz
-    except Exception:
-        ghz = 1.965
+    ghz = 1.965            # B200 boost clock; timestamps are SM clocks (nvidia-smi reports the idle clock outside a kernel)
 
     def read():
         torch.cuda.synchronize()
@@ -80,9 +78,9 @@ def main():
         t = read()
         ctas = int((t[:, 6] > 0).sum())
         t = t[:ctas]
-        rel = (t[:, [0, 1, 2, 3, 4, 8, 9, 10, 5, 6]] - t[:, [0]]) / (ghz * 1000.0)          # us since this CTA's entry
+        rel = (t[:, [0, 1, 2, 3, 4, 8, 9, 10, 5, 11, 6]] - t[:, [0]]) / (ghz * 1000.0)          # us since this CTA's entry
         names = ["entry", "after_pdl_wait", "first_stage_landed", "last_mma_issued", "accumulator_complete", "chunk0_staged",
-                 "chunk0_store_issued", "chunk0_stats_done", "epilogue_done", "exit"]
+                 "chunk0_store_issued", "chunk0_stats_done", "epilogue_done", "epilogue_done_group_b", "exit"]
         res = dict(case=name, chain=chain, ctas=ctas, us_per_launch_events=ev[0].elapsed_time(ev[1]) * 1000.0 / chain,
                    entry_skew_us=float(t[:, 7].max() - t[:, 7].min()) / 1000.0, sm_ghz_assumed=ghz,
                    median_us_since_entry={nm: round(float(np.median(rel[:, j])), 2) for j, nm in enumerate(names)},
