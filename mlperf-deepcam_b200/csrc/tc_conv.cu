@@ -11,7 +11,8 @@
 //   * both operands land in shared memory in the 128-byte-swizzled K-major UMMA canonical layout;
 //     one elected thread issues tcgen05.mma (M=128, N=BN, K=16) accumulating in TMEM.
 //   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
-//     (tcgen05.ld -> bias -> bf16 -> global, generic output strides so concat slices / parity sub-grids work).
+//     (tcgen05.ld -> bias -> bf16 -> global, generic output strides so concat slices / parity sub-grids work); the
+//     persistent kernel adds a second epilogue group (warps 6..9) that drains alternate 64-column chunks.
 // wgrad kernel: D[co, ci] = sum_pixels dY[p, co] * X_t[p, ci]; both operands are pixel-major in memory,
 //   i.e. MN-major UMMA operands (a_major = b_major = 1), reduction (pixels) split across CTAs, fp32 atomics.
 #include "common.cuh"
