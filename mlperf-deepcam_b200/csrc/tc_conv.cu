@@ -191,7 +191,9 @@ struct TcFpropParams {
 // 8 first chunk converted + staged, 9 first chunk's TMA store issued, 10 first chunk's statistics done.  The product build compiles the macro away.
 #ifdef DC_TC_TRACE
 __device__ unsigned long long g_tc_trace[148 * 16];
-#define TC_TRACE(slot) do { g_tc_trace[blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); } while (0)
+// (the "memory" clobber keeps the clock read on its side of barriers; a plain clock64() was hoisted above the final __syncthreads)
+#define TC_TRACE(slot) do { unsigned long long tc_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(tc_) :: "memory"); \
+                            g_tc_trace[blockIdx.x * 16 + (slot)] = tc_; } while (0)
 #else
 #define TC_TRACE(slot) do { } while (0)
 #endif
