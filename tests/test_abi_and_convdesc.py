@@ -48,6 +48,13 @@ def test_argument_validation_without_gpu():
     rc = lib.dc_conv_gemm_simt(ctypes.byref(d), v, None, None, v, None)
     assert rc < 0
     assert b"ntaps" in lib.dc_last_error_string()
+    d.ntaps, d.stride_h, d.stride_w, d.wtaps, d.out_csplit = 1, 1, 1, 1, 6      # two-segment outputs split at a multiple of 4
+    rc = lib.dc_conv_gemm_simt(ctypes.byref(d), v, None, None, v, None)
+    assert rc < 0 and b"out_csplit" in lib.dc_last_error_string()
+    rc = lib.dc_bilinear_fwd(v, v, None)
+    assert rc < 0 and b"dc_bilinear_fwd" in lib.dc_last_error_string()
+    rc = lib.dc_pack_weight(ctypes.c_void_p(16), 8, 3, 9, 1, ctypes.c_void_p(16), _lib.DC_PACK_NTK_CONVT2, 64, 32, 1, None)
+    assert rc < 0 and b"DC_PACK_NTK_CONVT2" in lib.dc_last_error_string()          # needs taps = 4
     rc = lib.dc_bn_stats(None, v, None)
     assert rc < 0 and b"dc_bn_stats" in lib.dc_last_error_string()
     assert lib.dc_bn_ws_bytes(728) == 32 * 728 + 64
