@@ -411,6 +411,8 @@ __global__ void __launch_bounds__(kTcThreads) conv_gemm_tc_kernel(const __grid_c
       }
     }
   }
+  __syncwarp();        // warps 0/1: the single-lane role (producer / MMA issuer) rejoins its warp, so every warp arrives at the
+                       // teardown barrier exactly once and the TMEM release below is ordered after the epilogue's last read
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, cfg.tmem_cols);
@@ -847,6 +849,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) conv_gemm_tc2_kernel(const __g
   if (threadIdx.x == 64) TC_TRACE(5);
   if (threadIdx.x == 192) TC_TRACE(11);
   if (cfg.tma_store && (threadIdx.x == 64 || threadIdx.x == 192)) tma_store_wait_all();     // staging must stay valid until the last store has read it
+  __syncwarp();        // warps 0/1: the single-lane role (producer / MMA issuer) rejoins its warp, so every warp arrives at the
+                       // teardown barrier exactly once and the TMEM release below is ordered after the epilogue's last read
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TC_TRACE(6);
@@ -1027,6 +1031,8 @@ __global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const __grid_
       }
     }
   }
+  __syncwarp();        // warps 0/1: the single-lane role (producer / MMA issuer) rejoins its warp, so every warp arrives at the
+                       // teardown barrier exactly once and the TMEM release below is ordered after the epilogue's last read
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, BNW);
