@@ -27,7 +27,11 @@ __global__ void __launch_bounds__(256) wce_fwd_kernel(View<const float> x, const
     decode3(p, x.h, x.w, n, h, w);
     const float* px = x.p + n * x.sn + h * x.sh + w * x.sw;
     long long t = target[p];
-    if (t < 0 || t >= C) continue;   // ignore_index semantics of CrossEntropyLoss (-100): zero loss
+    if (t == -100) continue;         // ignore_index of nn.CrossEntropyLoss (LS:35 keeps the default): zero loss, still counted in the mean
+    if (t < 0 || t >= C) {           // any other label outside [0, C): torch device-asserts; here the loss becomes NaN (loud, no host sync)
+      local += (double)__int_as_float(0x7fc00000);
+      continue;
+    }
     float m = px[0];
     for (int c = 1; c < C; ++c) m = fmaxf(m, px[c * x.sc]);
     float s = 0.f;
@@ -63,13 +67,14 @@ __global__ void __launch_bounds__(256) wce_bwd_kernel(View<const float> x, const
     const float* px = x.p + n * x.sn + h * x.sh + w * x.sw;
     TD* pd = dx.p + n * dx.sn + h * dx.sh + w * dx.sw;
     long long t = target[p];
-    bool valid = (t >= 0 && t < C);
+    const bool valid = (t >= 0 && t < C);
+    const bool poison = !valid && t != -100;     // corrupted label (not ignore_index): NaN gradient, like the NaN loss of wce_fwd
     float m = px[0];
     for (int c = 1; c < C; ++c) m = fmaxf(m, px[c * x.sc]);
     float s = 0.f;
     for (int c = 0; c < C; ++c) s += expf(px[c * x.sc] - m);
     float inv = 1.0f / s;
-    float wt = valid ? cw[t] * gs : 0.f;
+    float wt = valid ? cw[t] * gs : (poison ? __int_as_float(0x7fc00000) : 0.f);
     for (int c = 0; c < dx.c; ++c) {
       float g = 0.f;
       if (c < C) {

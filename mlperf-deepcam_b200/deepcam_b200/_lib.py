@@ -114,9 +114,9 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB_PATH
-    if not os.path.exists(path):
-        path = _build.build()
+    # always consult the source hash: a library built from older csrc/ must not be loaded silently (build() returns at once
+    # when the stamp matches; it serialises concurrent ranks with a file lock)
+    path = _build.build()
     lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)      # AttributeError here = ABI mismatch: fail loudly

@@ -38,15 +38,33 @@ def _source_hash():
     return h.hexdigest()
 
 
+def _up_to_date(stamp, digest):
+    if os.path.exists(LIB_PATH) and os.path.exists(stamp):
+        with open(stamp) as fh:
+            return fh.read().strip() == digest
+    return False
+
+
 def build(force=False, verbose=False):
-    """Compile every .cu file and link the shared library.  Returns the library path."""
+    """Compile every .cu file and link the shared library.  Returns the library path.  Safe to call from several
+    processes at once (torchrun ranks): the compile is serialised by a file lock and the losers find the stamp current."""
     os.makedirs(LIB_DIR, exist_ok=True)
     stamp = os.path.join(LIB_DIR, "build.stamp")
     digest = _source_hash()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
-        with open(stamp) as fh:
-            if fh.read().strip() == digest:
+    if not force and _up_to_date(stamp, digest):
+        return LIB_PATH
+    import fcntl
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(stamp, digest):
                 return LIB_PATH
+            return _build_locked(stamp, digest, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(stamp, digest, verbose):
     nvcc = _nvcc()
     obj_dir = os.path.join(LIB_DIR, "obj")
     os.makedirs(obj_dir, exist_ok=True)

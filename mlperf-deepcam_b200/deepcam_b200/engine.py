@@ -542,6 +542,15 @@ class _GraphPlan:
         be, eng, grads = self.be, self.eng, self.grads
         sync = getattr(self.module, "_dc_grad_sync", None)
         first = self.bwd_segments is None
+        if grads.flat is not None:
+            # gradient accumulation (a second backward without zero_grad(set_to_none=True)): the .grad tensors the caller still
+            # holds are views of the plan's static flat buffer, which the replay below zeroes and overwrites.  Move the held
+            # gradients out first; autograd then adds this backward's views to them (g_old + g_new, as in the eager engine).
+            lo, hi = grads.flat.data_ptr(), grads.flat.data_ptr() + grads.flat.numel() * 4
+            for p in self.params:
+                g = p.grad
+                if g is not None and lo <= g.data_ptr() < hi:
+                    p.grad = g.clone()
         if first:
             flat = grads.begin_backward()
             for (act, c), g in zip(self.outs, gouts):
@@ -605,15 +614,8 @@ class _GraphPlan:
             else:
                 dxs.append(None)
         self.module._dc_last_launches_bwd = self.bwd_kernels
-        # parameter gradients: views of the static flat buffer; if the caller still holds such views as .grad
-        # (gradient accumulation) autograd would add the buffer to itself, so hand out copies in that case
-        flat = grads.flat
-        lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
-        held = any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in self.params)
-        views = grads.take_views()
-        if held:
-            views = tuple(v.clone() if v is not None else None for v in views)
-        return dxs, views
+        # parameter gradients: fresh views of the static flat buffer (held gradients were moved out of it above)
+        return dxs, grads.take_views()
 
 
 def ops_copy_view(src, dst):

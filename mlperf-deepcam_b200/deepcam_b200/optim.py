@@ -14,6 +14,13 @@ import torch
 from . import _lib, ops
 
 
+def _mark_updated(plist):
+    """The kernels write the parameters through raw pointers, which autograd's version counters do not see: bump them so
+    every consumer keyed on `param._version` (the packed bf16 weight copies of deepcam_b200.backend, torch's own
+    saved-tensor checks) notices the update exactly as it would after `torch.optim.Adam.step()`."""
+    torch._C._increment_version(list(plist))
+
+
 class _FusedAdamBase(torch.optim.Optimizer):
     _adamw = False
 
@@ -78,6 +85,7 @@ class _FusedAdamBase(torch.optim.Optimizer):
                 ctypes.c_void_p(table.data_ptr()), njobs, blocks, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                 float(group["weight_decay"]), 1.0 - math.pow(b1, t), 1.0 - math.pow(b2, t), int(self._adamw),
                 ops._stream()), "dc_adam_step_multi")
+            _mark_updated(plist)
         return loss
 
 
@@ -152,6 +160,8 @@ class FusedLAMB(torch.optim.Optimizer):
                 float(group["weight_decay"]), bc1, bc2, self.adam_w_mode, int(bool(group["grad_averaging"])),
                 float(group["max_grad_norm"] or 0.0), int(bool(self.use_nvlamb)), ctypes.c_void_p(norms.data_ptr()),
                 ops._stream()), "dc_lamb_step_multi")
+            _mark_updated(plist)
+            _mark_updated([p.grad for p in plist])      # like apex, the step leaves the update in .grad
         return loss
 
 
@@ -210,4 +220,5 @@ class FusedLARS(torch.optim.Optimizer):
                 ctypes.c_void_p(table.data_ptr()), njobs, blocks, float(group["lr"]), float(group["momentum"]),
                 float(group["weight_decay"]), float(group["trust_coefficient"]), float(group["eps"]),
                 ctypes.c_void_p(norms.data_ptr()), ops._stream()), "dc_lars_step_multi")
+            _mark_updated(plist)
         return loss

@@ -26,6 +26,8 @@ class _GradSync:
         self.pending = None
         self.works = []
         self.deferred = None         # list while a CUDA-graph plan is capturing: completed buckets are queued, not launched
+        self._expected = None        # parameter indices that reported a gradient in the previous backward
+        self._seen = set()
 
     # -- bucket layout (reverse parameter order ~ backward completion order) --
     def _layout(self, grads):
@@ -54,10 +56,16 @@ class _GradSync:
         if self.buckets is None or self._total != grads.total:
             self._total = grads.total
             self._layout(grads)
+            self._expected = None
         self.flat = grads.flat
         self.pending = []
+        # parameters expected to report: those that did in the previous backward of this layout (a requires_grad parameter
+        # that forward does not use never reports and would otherwise stall the in-order launch of every later bucket
+        # until finish()); the first backward expects every trainable parameter
+        expected = self._expected if self._expected is not None else {i for i, p in enumerate(grads.params) if p.requires_grad}
         for (_, _, idxs) in self.buckets:
-            self.pending.append(sum(1 for i in idxs if grads.params[i].requires_grad))
+            self.pending.append(sum(1 for i in idxs if i in expected))
+        self._seen = set()
         self.launched = [False] * len(self.buckets)
         self.works = []
         grads.on_ready = self._ready
@@ -65,6 +73,9 @@ class _GradSync:
 
     def _ready(self, i):
         b = self.bucket_of[i]
+        if i in self._seen:
+            return
+        self._seen.add(i)
         self.pending[b] -= 1
         # launch in order so every rank issues the collectives in the same sequence
         while self.next_bucket < len(self.buckets) and self.pending[self.next_bucket] <= 0:
@@ -91,6 +102,8 @@ class _GradSync:
         self.owner._wait(self.works, self.flat)
         grads.on_ready = None
         self.works = []
+        if self._seen:
+            self._expected = set(self._seen)
 
 
 class DistributedDataParallel(nn.Module):
@@ -130,6 +143,7 @@ class DistributedDataParallel(nn.Module):
                     continue
                 (fl if buf.is_floating_point() else it).append((mod, name, buf))
         self._flat_buffers = []
+        self._buffer_homes = []
         for group in (fl, it):
             if not group:
                 continue
@@ -143,10 +157,22 @@ class DistributedDataParallel(nn.Module):
                     view = flat[off:off + n].view(buf.shape)
                     view.copy_(buf)
                     mod._buffers[name] = view
+                    self._buffer_homes.append((mod, name, view.data_ptr()))
                     off += n
             self._flat_buffers.append(flat)
 
+    def _buffers_aliased(self):
+        """True while every module buffer still is the view of the flat tensors that _flatten_buffers installed
+        (module.to() / .float() / load_state_dict(assign=True) replace the entries of mod._buffers with fresh tensors)."""
+        for mod, name, ptr in self._buffer_homes:
+            b = mod._buffers.get(name)
+            if b is None or b.data_ptr() != ptr:
+                return False
+        return True
+
     def _broadcast_buffers(self):
+        if not self._buffers_aliased():
+            self._flatten_buffers()          # buffers were re-homed behind our back: flatten again, never broadcast stale views
         for flat in self._flat_buffers:
             dist.broadcast(flat, 0, group=self.process_group)
 

@@ -332,3 +332,105 @@ def test_interpolation_upsampler_matches_oracle(precision, monkeypatch):
     with torch.no_grad():
         out2 = mod(x.to(DEV), low.to(DEV), input_size2)
     assert out2.shape == (2, 3, 94, 141) and _rel(out2, ref2) < tol_out
+
+
+@pytest.mark.parametrize("graphs", ["0", "1"])
+def test_fused_adam_trains_the_model_like_torch_adam(sd, graphs, monkeypatch):
+    """the fused optimizers update the fp32 master parameters through raw pointers; the packed bf16 / kernel
+    layout weight copies must follow.  Four steps with FusedAdam against torch.optim.Adam on the same batches, with CUDA-graph
+    plans on and off (eager engine = the documented DEEPCAM_B200_GRAPHS=0 fallback): identical loss trajectory, and the
+    loss must actually move (stale packed weights would repeat step 0 forever)."""
+    from deepcam_b200.optim import FusedAdam
+    monkeypatch.setenv("DEEPCAM_B200_GRAPHS", graphs)
+    w = O.class_weights()
+    batches = [O.synthetic_batch(2, 64, 96, seed=60 + i) for i in range(4)]
+
+    def run(make_opt):
+        net = _make(sd, "bf16").train()
+        opt = make_opt(net.parameters())
+        out_losses = []
+        for x, label in batches:
+            out = net.forward(x.to(DEV))
+            loss = losses.fp_loss(out, label.to(DEV), weight=w, fpw_1=w[1], fpw_2=w[2])
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            out_losses.append(float(loss))
+        return net, out_losses
+
+    net_f, lf = run(lambda ps: FusedAdam(ps, lr=1e-3, eps=1e-8, weight_decay=1e-6))
+    net_t, lt = run(lambda ps: torch.optim.Adam(ps, lr=1e-3, eps=1e-8, weight_decay=1e-6))
+    _record("fused_adam_graphs%s" % graphs, dict(fused=lf, torch=lt))
+    assert abs(lf[1] - lf[0]) > 1e-3, lf                       # the second forward saw updated weights
+    for a, b in zip(lf, lt):
+        assert abs(a - b) < 2e-2, (lf, lt)                     # bf16 trajectories (wgrad atomics reorder sums)
+    pf, pt = dict(net_f.named_parameters()), dict(net_t.named_parameters())
+    k = "xception_features.block5.rep.1.pointwise.weight"
+    assert _rel(pf[k], pt[k]) < 1e-3
+    # an eager call right after fused steps (new plan key: eval mode) must see the CURRENT weights
+    x, _ = batches[0]
+    net_f.eval(); net_t.eval()
+    with torch.no_grad():
+        assert _rel(net_f(x.to(DEV)), net_t(x.to(DEV))) < 5e-2
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_gradient_accumulation_under_graph_plans(sd, precision, monkeypatch):
+    """two backwards without zero_grad on a captured plan must give g1 + g2 (p.grad aliases the plan's
+    static flat gradient buffer, which the replay overwrites)."""
+    monkeypatch.setenv("DEEPCAM_B200_GRAPHS", "1")
+    w = O.class_weights()
+    net = _make(sd, precision).train()
+    batches = [O.synthetic_batch(2, 64, 96, seed=70 + i) for i in range(2)]
+
+    def one(x, label):
+        out = net(x.to(DEV))
+        losses.fp_loss(out, label.to(DEV), weight=w, fpw_1=w[1], fpw_2=w[2]).backward()
+
+    for _ in range(3):                       # eager, capture, replay: plans are live afterwards
+        net.zero_grad()
+        one(*batches[0])
+    assert any(v[1] is not None and v[1].bwd_segments for v in net._dc_plans.values())
+    single = []
+    for b in batches:
+        net.zero_grad()
+        one(*b)
+        single.append({k: p.grad.detach().clone() for k, p in net.named_parameters()})
+    net.zero_grad()
+    one(*batches[0])
+    one(*batches[1])                         # no zero_grad in between
+    tol = 1e-3 if precision == "fp32" else 0.25          # same bound as graph-vs-eager (atomics reorder the sums)
+    worst = 0.0
+    for k, p in net.named_parameters():
+        want = single[0][k] + single[1][k]
+        worst = max(worst, _rel(p.grad, want))
+        # and clearly not 2 * g2 (the failure mode): only meaningful where g1 and g2 differ
+    assert worst < tol, worst
+    k = "upsample.conv1.0.weight"
+    assert _rel(dict(net.named_parameters())[k].grad, 2 * single[1][k]) > 10 * tol or _rel(single[0][k], single[1][k]) < tol
+
+
+def test_fp_loss_ignore_index_and_corrupted_labels():
+    """nn.CrossEntropyLoss semantics (LS:35): -100 is ignored (zero loss, still counted in the mean); any other label outside
+    [0, C) is an error - torch device-asserts, the kernels poison the loss / gradient with NaN instead of lowering it silently."""
+    torch.manual_seed(1)
+    logit = torch.randn(2, 3, 8, 12)
+    target = torch.randint(0, 3, (2, 8, 12))
+    target[0, 0, :5] = -100
+    w = O.class_weights()
+    lg = logit.to(DEV).requires_grad_(True)
+    loss = losses.fp_loss(lg, target.to(DEV), weight=w)
+    crit = torch.nn.CrossEntropyLoss(weight=torch.tensor(w, dtype=torch.float64), reduction="none")
+    lr = logit.double().requires_grad_(True)
+    ref = crit(lr, target).mean()
+    ref.backward()
+    loss.backward()
+    assert abs(float(loss) - float(ref)) < 1e-6
+    assert _rel(lg.grad, lr.grad) < 1e-5
+    bad = target.clone()
+    bad[1, 2, 3] = 7
+    lg2 = logit.to(DEV).requires_grad_(True)
+    loss2 = losses.fp_loss(lg2, bad.to(DEV), weight=w)
+    assert bool(torch.isnan(loss2))
+    loss2.backward()
+    assert bool(torch.isnan(lg2.grad[1, :, 2, 3]).all())

@@ -82,6 +82,32 @@ def _worker(rank, world, port, q):
         assert int(cg[0]) == int(cg[1]) == 2
         # buffers still live in the state_dict under their usual names
         assert "skipbn.running_mean" in net.state_dict()
+
+        # buffers re-homed behind the wrapper's back (module.float() / .to() / load_state_dict(assign=True) install
+        # fresh tensors in mod._buffers) must not silently drop out of the C3 broadcast
+        assert ddp._buffers_aliased()
+        net.skipbn._buffers["running_mean"] = net.skipbn.running_mean.clone() + float(rank + 1)     # ranks now disagree
+        assert not ddp._buffers_aliased()
+        with torch.no_grad():
+            ddp(x)                                       # re-flattens, then broadcasts rank 0's buffers
+        assert ddp._buffers_aliased()
+        gathered = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(gathered, net.skipbn.running_mean.clone())
+        # both ranks started this forward from rank 0's (shifted) statistics and then applied their own batch update;
+        # without the re-flatten they would differ by the injected offset of 1.0
+        assert float((gathered[0] - gathered[1]).abs().max()) < 0.5
+
+        # a trainable parameter that forward never touches must not stall the in-order bucket launch forever:
+        # the first backward learns who reports, later backwards expect only those
+        net.unused = torch.nn.Parameter(torch.zeros(3))
+        net._dc_gradstore = None
+        for it in range(2):
+            net.zero_grad()
+            ddp(x).square().mean().backward()
+            assert ddp._sync._expected is not None and len(ddp._sync._expected) == len(list(net.parameters())) - 1
+        ddp._sync.begin(net._dc_gradstore)               # pending counts of the next backward skip the silent parameter
+        assert sum(ddp._sync.pending) == len(list(net.parameters())) - 1
+        net._dc_gradstore.on_ready = None
         dist.destroy_process_group()
         q.put((rank, "ok"))
     except Exception:
