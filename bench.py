@@ -91,16 +91,100 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
+REF_DIR = os.path.join(REPO, "baseline", "_ref", "deepCam")
+CLASS_WEIGHTS = [1.001729912096556, 2.6146112239752224, 1.7164197479589602]       # TR:204-209 with the default exponent
+OPTIMIZER_CFG = "Adam lr=1e-3 eps=1e-8 wd=1e-6 (script defaults TR:566-568)"
+
+
+def shared_config(world):
+    """`config` of the JSON line: identical for our arm and the reference arm (same workload, same optimizer rule)."""
+    return dict(workload=WORKLOAD, local_batch=LOCAL_BATCH, global_batch=LOCAL_BATCH * world, optimizer=OPTIMIZER_CFG,
+                parallelism="dp%d" % world,
+                l2="per-step working set (>7 GB of activations) exceeds the 126 MB L2; no explicit flush")
+
+
+def load_reference():
+    """The UNMODIFIED reference classes (architecture/deeplab_xception.py, utils/losses.py), staged byte for byte under
+    baseline/_ref/ by baseline/stage_reference.py, loaded by file path under private names (they never shadow the product's
+    `architecture` / `utils` packages).  None when the copy is absent (then the oracle port stands in, kind "port")."""
+    import importlib.util
+    paths = dict(dx=os.path.join(REF_DIR, "architecture", "deeplab_xception.py"), ls=os.path.join(REF_DIR, "utils", "losses.py"))
+    if not all(os.path.exists(v) for v in paths.values()):
+        return None
+    mods = {}
+    for k, v in paths.items():
+        spec = importlib.util.spec_from_file_location("_deepcam_reference_" + k, v)
+        mods[k] = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mods[k])
+    return mods["dx"], mods["ls"]
+
+
+def synthetic_host_batch(seed, local_batch=None):
+    """uniform [0,1) inputs, labels with the class frequencies of the real data (TR:206)."""
+    import torch
+    n = local_batch or LOCAL_BATCH
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand((n, C_IN, H, W), generator=g)
+    u = torch.rand((n, H, W), generator=g)
+    label = torch.zeros((n, H, W), dtype=torch.long)
+    label[u > 0.986267818] = 2
+    label[u > 0.986267818 + 0.013274311] = 1
+    return x, label
+
+
+class ReferenceStep:
+    """Loop body TR:345-371 on the reference's own classes: forward, fp_loss, zero_grad, backward, Adam step."""
+
+    def __init__(self, device, gpu_library=False):
+        import torch
+        ref = load_reference()
+        self.kind = "reference" if ref is not None else "port"
+        self.device = device
+        self.gpu_library = gpu_library
+        torch.manual_seed(333)
+        if ref is not None:
+            dxm, lsm = ref
+            self.net = dxm.DeepLabv3_plus(n_input=C_IN, n_classes=N_CLASSES, os=16, pretrained=False, _print=False).to(device).train()
+            self.loss_fn = lsm.fp_loss
+            if gpu_library:
+                self.net = self.net.to(memory_format=torch.channels_last)
+            kw = dict(fused=True) if gpu_library else {}
+            self.opt = torch.optim.Adam(self.net.parameters(), lr=1e-3, eps=1e-8, weight_decay=1e-6, **kw)
+        else:
+            sys.path.insert(0, os.path.join(REPO, "oracle"))
+            import deepcam_oracle as O
+            self.O = O
+            self.st = O.TrainState({k: v.to(device) for k, v in O.init_state_dict(C_IN, N_CLASSES, 16, seed=333).items()})
+
+    def step(self, x, label):
+        import torch
+        if self.kind == "port":
+            if self.gpu_library:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return self.st.step(x, label)[0]
+            return self.st.step(x, label)[0]
+        cw = CLASS_WEIGHTS
+        if self.gpu_library:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = self.net.forward(x)
+                loss = self.loss_fn(out, label, weight=cw, fpw_1=cw[1], fpw_2=cw[2])
+        else:
+            out = self.net.forward(x)
+            loss = self.loss_fn(out, label, weight=cw, fpw_1=cw[1], fpw_2=cw[2])
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        return loss
+
+
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the step, i.e. the oracle port (the reference is
-    Python/torch and cannot travel to the GPU box; oracle/deepcam_oracle.py restates it op for op and is pinned
-    against it in the build container).  Rank 0 only."""
+    """Reference arm: the reference's own training step (its unmodified classes from baseline/_ref; the oracle port only if
+    that copy is missing) on the host cores, fp32, FULL-SIZE 768x1152 tiles at local batch 2 - the same config as our arm.
+    Rank 0 only; the other ranks exit without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    sys.path.insert(0, os.path.join(REPO, "oracle"))
-    import deepcam_oracle as O
     # torchrun exports OMP_NUM_THREADS=1 for its workers; this arm is the only process doing work, so it takes every host core
     try:
         avail = len(os.sched_getaffinity(0))
@@ -109,54 +193,95 @@ def run_reference(args):
     if torch.get_num_threads() < avail:
         torch.set_num_threads(avail)
     cores = torch.get_num_threads()
-    sd = O.init_state_dict(C_IN, N_CLASSES, 16, seed=333)
-    st = O.TrainState(sd)
-    # calibrate the per-pixel cost on a 192x288 crop, then size the per-step sample so K+W steps fit the budget
-    x, label = O.synthetic_batch(LOCAL_BATCH, 192, 288, seed=333)
+    ref = ReferenceStep(torch.device("cpu"))
+    x, label = synthetic_host_batch(333)
     t0 = time.time()
-    st.step(x, label)
+    ref.step(x, label)                      # cold step = first warm-up step, also the calibration
     t_cal = time.time() - t0
-    budget = float(os.environ.get("DEEPCAM_REF_BUDGET_S", "150"))
-    n_steps = args.steps + args.warmup
-    per_row = t_cal / 192.0 * (W / 288.0)
-    rows = int(budget / max(n_steps, 1) / per_row) // 16 * 16
-    rows = max(32, min(H, rows))
-    x, label = O.synthetic_batch(LOCAL_BATCH, rows, W, seed=333)
-    for _ in range(args.warmup):
-        st.step(x, label)
+    budget = float(os.environ.get("DEEPCAM_REF_BUDGET_S", "300"))
+    warm = max(args.warmup - 1, 0)
+    steps = args.steps
+    note = ""
+    if t_cal * (warm + steps) > budget:      # never crop the tile: run fewer full-size steps instead, and say so
+        warm = min(warm, 1)
+        steps = max(2, min(steps, int(budget / t_cal) - warm))
+        note = "; %d of the requested %d timed steps fit the %.0f s budget" % (steps, args.steps, budget)
+    for _ in range(warm):
+        ref.step(x, label)
     t0 = time.time()
-    for _ in range(args.steps):
-        st.step(x, label)
+    for _ in range(steps):
+        loss = ref.step(x, label)
     dt = time.time() - t0
-    frac = rows / float(H)
-    value = LOCAL_BATCH * frac * args.steps / dt
-    sample = "%d steps of N=%d crops %dx%dx%d (%.4f of a 768x1152 tile each; value scaled by pixel count), fp32, %d threads" % (
-        args.steps, LOCAL_BATCH, rows, W, C_IN, frac, cores)
-    line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1000.0 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", impl="reference",
-                config=dict(workload=WORKLOAD, local_batch=LOCAL_BATCH, optimizer="Adam lr=1e-3 eps=1e-8 wd=1e-6"),
-                cpu_baseline=dict(value=value, unit="samples/s", cores=cores, kind="port", sample=sample),
-                e2e=dict(value=value, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    value = LOCAL_BATCH * steps / dt
+    sample = "%d full-size steps (N=%d, %dx%dx%d, fp32, Adam) of the %s on %d host threads%s" % (
+        steps, LOCAL_BATCH, H, W, C_IN, "unmodified reference classes (baseline/_ref)" if ref.kind == "reference" else
+        "oracle port (baseline/_ref absent)", cores, note)
+    line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=args.gpus, steps=steps, warmup=warm + 1,
+                ms_per_step=1000.0 * dt / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference", config=shared_config(max(1, args.gpus)),
+                cpu_baseline=dict(value=value, unit="samples/s", cores=cores, kind=ref.kind, sample=sample),
+                e2e=dict(value=value, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                loss=float(loss.detach()) if hasattr(loss, "detach") else float(loss))
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def cpu_baseline_sample():
-    """One full-size reference step (N=2, 768x1152x16, fp32) on the host cores with the oracle port."""
+    """Two full-size reference steps (N=2, 768x1152x16, fp32) on the host cores; the second (warm) one is the value."""
     import torch
-    sys.path.insert(0, os.path.join(REPO, "oracle"))
-    import deepcam_oracle as O
     cores = torch.get_num_threads()
-    rows = int(os.environ.get("DEEPCAM_CPU_BASELINE_ROWS", str(H)))
-    sd = O.init_state_dict(C_IN, N_CLASSES, 16, seed=333)
-    st = O.TrainState(sd)
-    x, label = O.synthetic_batch(LOCAL_BATCH, rows, W, seed=333)
+    ref = ReferenceStep(torch.device("cpu"))
+    x, label = synthetic_host_batch(333)
     t0 = time.time()
-    st.step(x, label)
-    dt = time.time() - t0
-    frac = rows / float(H)
-    return dict(value=LOCAL_BATCH * frac / dt, unit="samples/s", cores=cores, kind="port",
-                sample="1 cold step, N=%d, %dx%dx%d, fp32, Adam, %.1f s on %d threads" % (LOCAL_BATCH, rows, W, C_IN, dt, cores))
+    ref.step(x, label)
+    t1 = time.time()
+    ref.step(x, label)
+    dt = time.time() - t1
+    return dict(value=LOCAL_BATCH / dt, unit="samples/s", cores=cores, kind=ref.kind,
+                sample="1 warm full-size step after 1 cold one (%.1f s / %.1f s), N=%d, %dx%dx%d, fp32, Adam, %d threads"
+                       % (dt, t1 - t0, LOCAL_BATCH, H, W, C_IN, cores))
+
+
+def gpu_library_step_time(dev, steps, warmup):
+    """Measurement-only GPU anchor: the reference model on this B200 through stock torch/cuDNN - bf16 autocast,
+    channels_last, cudnn.benchmark, fused torch Adam - same batch, same loop body.  Never part of the product path."""
+    import torch
+    torch.backends.cudnn.benchmark = True
+    ref = ReferenceStep(dev, gpu_library=True)
+    x, label = synthetic_host_batch(333)
+    x = x.to(dev).contiguous(memory_format=torch.channels_last)
+    label = label.to(dev)
+    for _ in range(max(warmup, 3)):
+        ref.step(x, label)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = ref.step(x, label)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    out = dict(value=LOCAL_BATCH / (ms / 1000.0), unit="samples/s", ms_per_step=ms, kind=ref.kind, loss=float(loss),
+               how="reference DeepLabv3_plus + fp_loss + torch.optim.Adam(fused=True) under torch.autocast(bfloat16), channels_last, "
+                   "cudnn.benchmark, torch %s / cuDNN %s; inputs resident in HBM" % (torch.__version__, torch.backends.cudnn.version()),
+               peak_mem_gib=peak_gb)
+    del ref
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_torch_gpu(args):
+    """`--impl torch_gpu`: prints the library anchor as its own JSON line (rank 0 / one GPU)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    r = gpu_library_step_time(dev, args.steps, args.warmup)
+    line = dict(metric=METRIC, value=r["value"], unit="samples/s", n_gpus=1, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                data="synthetic", impl="torch_gpu", config=shared_config(1), gpu_library_baseline=r)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -200,15 +325,10 @@ def run_ours(args):
         from deepcam_b200.optim import FusedAdam
         opt = FusedAdam(net.parameters(), lr=1e-3, eps=1e-8, weight_decay=1e-6)
         opt_name = "deepcam_b200.optim.FusedAdam (torch.optim.Adam semantics)"
-    cw = [1.001729912096556, 2.6146112239752224, 1.7164197479589602]
+    cw = CLASS_WEIGHTS
 
-    g = torch.Generator().manual_seed(333 + rank)
-    x_host = torch.rand((LOCAL_BATCH, C_IN, H, W), generator=g).pin_memory()
-    u = torch.rand((LOCAL_BATCH, H, W), generator=g)
-    label_host = torch.zeros((LOCAL_BATCH, H, W), dtype=torch.long)
-    label_host[u > 0.986267818] = 2
-    label_host[u > 0.986267818 + 0.013274311] = 1
-    label_host = label_host.pin_memory()
+    x_host, label_host = synthetic_host_batch(333 + rank)
+    x_host, label_host = x_host.pin_memory(), label_host.pin_memory()
     x_dev, label_dev = x_host.to(dev), label_host.to(dev)
 
     def step(x, label, delay=None, module=None):
@@ -400,29 +520,127 @@ def run_ours(args):
         except Exception:
             pass
 
+    # ---- N > 1: exposed communication = step time with the gradient exchange minus the same ranks stepping without it ----
+    comm = None
+    if world > 1:
+        saved_sync, saved_key = net._dc_grad_sync, getattr(net, "_dc_plan_key", None)
+        net._dc_grad_sync = None
+        net._dc_plan_key = "no_grad_exchange"           # a plan of its own: one backward graph, no bucket segments
+        for _ in range(3):                               # eager, capture, replay
+            step(x_dev, label_dev, module=net)
+        ms_nc = timed(lambda: step(x_dev, label_dev, module=net), args.steps)
+        net._dc_grad_sync, net._dc_plan_key = saved_sync, saved_key
+        comm = dict(ms_per_step_without_exchange=ms_nc / args.steps, exposed_comm_ms=(ms - ms_nc) / args.steps,
+                    how="same ranks, same batches, bare module (no bucketed all-reduce, no buffer broadcast), max over ranks; "
+                        "the difference to ms_per_step is everything the exchange costs: exposed NCCL time, SM contention, "
+                        "per-bucket graph segments, the buffer broadcast")
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline_sample()
+    gpu_lib = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        try:
+            gpu_lib = gpu_library_step_time(dev, min(args.steps, 10), 3)
+        except Exception as e:                          # the anchor must never take the bench line down
+            gpu_lib = dict(unavailable=repr(e)[:200])
 
     if rank == 0:
         peaks = _peaks()
         line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="bf16" if precision == "bf16" else "f32", data="synthetic",
-                    config=dict(workload=WORKLOAD, local_batch=LOCAL_BATCH, global_batch=LOCAL_BATCH * world,
-                                optimizer=opt_name + " lr=1e-3 eps=1e-8 wd=1e-6 (TR:566-568)",
-                                parallelism="dp%d" % world,
-                                l2="per-step working set (>7 GB of activations) exceeds the 126 MB L2; no explicit flush"),
+                    config=shared_config(world), optimizer_impl=opt_name,
                     e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                              ms_per_step=ms_e2e / args.steps, loss=last.get("loss"),
                              loss_readback=".item() every step" if args.e2e_sync_loss else
                              "4-byte copy into pinned memory every step, consumed by the host one step later"),
                     gpu_launches=launches, clocks=clocks,
-                    tensor_frac_of_step=(FWD_BWD_GFLOP_PER_SAMPLE * value / 1000.0) / peaks["tf_sustained"],
-                    roofline=roofline, cpu_baseline=cpu_base)
+                    tensor_frac_of_step=(FWD_BWD_GFLOP_PER_SAMPLE * value / world / 1000.0) / peaks["tf_sustained"],
+                    roofline=roofline, cpu_baseline=cpu_base, gpu_library_baseline=gpu_lib, comm=comm)
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()              # rank 0 may still be in its instrumented pass: leave together
+        dist.destroy_process_group()
+
+
+def run_eval(args):
+    """BASELINE.json configs[3]: the validation loop TR:423-512 - eval() + no_grad forward, fp_loss, argmax (TR:458) and
+    compute_score (TR:459) per batch, per-rank sums, three scalar all-reduces at the end (TR:490-492) - over a synthetic
+    validation set sharded by rank.  The IoU of every batch comes out of ONE fused kernel pass over the logits
+    (utils.argmax_score: argmax + integer tp/fp/fn + the three divisions), bit-exact with UT:32-60."""
+    import torch
+    import torch.distributed as dist
+    from architecture import deeplab_xception as dx
+    from utils import losses, utils as dcutils
+    from deepcam_b200 import _lib
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(333)
+    net = dx.DeepLabv3_plus(n_input=C_IN, n_classes=N_CLASSES, os=16, _print=False).to(dev).eval()
+    b = args.eval_batch
+    nbuf = 4                                         # distinct batches cycled through (each 113 MB: beyond L2 together with the activations)
+    batches = []
+    for i in range(nbuf):
+        x, label = synthetic_host_batch(5000 + rank * nbuf + i, b)
+        batches.append((x.to(dev), label.to(dev)))
+    iters = max(1, args.eval_samples // b)
+    cw = CLASS_WEIGHTS
+    sums = torch.zeros(3, device=dev)                # count_sum_val, loss_sum_val, iou_sum_val (TR:431-433)
+
+    def one(i):
+        x, label = batches[i % nbuf]
+        with torch.no_grad():
+            out = net.forward(x)
+            loss = losses.fp_loss(out, label, weight=cw, fpw_1=cw[1], fpw_2=cw[2])
+            iou = dcutils.argmax_score(out, label, N_CLASSES)
+            sums[0] += 1.0
+            sums[1] += loss
+            sums[2] += iou
+
+    for i in range(max(args.warmup, 3)):
+        one(i)
+    sums.zero_()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        one(i)
+    if world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)  # the three reductions of TR:490-492 as one
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else {}
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    if rank == 0:
+        total = world * iters * b
+        host = sums.cpu()
+        line = dict(metric="eval_samples_per_s_768x1152x16", value=total / (ms / 1000.0), unit="samples/s", n_gpus=world,
+                    steps=iters, warmup=max(args.warmup, 3), ms_per_step=ms / iters, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype=os.environ.get("DEEPCAM_B200_PRECISION", "bf16"), data="synthetic",
+                    config=dict(workload="configs[3]: eval path, forward + fp_loss + argmax + IoU over a synthetic validation set "
+                                         "(%d samples per rank, batch %d), validation loop TR:423-512" % (iters * b, b),
+                                batch=b, samples=total, parallelism="dp%d (validation set sharded by rank)" % world,
+                                l2="%d distinct batches cycled; activations exceed L2" % nbuf),
+                    eval_loss=float(host[1] / host[0]), eval_iou=float(host[2] / host[0]), gpu_launches=launches, clocks=clocks)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -431,8 +649,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
+    ap.add_argument("--mode", default="train", choices=["train", "eval"],
+                    help="train = the headline metric; eval = BASELINE.json configs[3] (validation loop TR:423-512)")
+    ap.add_argument("--eval-samples", type=int, default=64, help="--mode eval: validation samples per rank")
+    ap.add_argument("--eval-batch", type=int, default=1, help="--mode eval: batch size (the reference validates at 1, TR:302-306)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--e2e-sync-loss", action="store_true", help="e2e leg: read the loss with .item() every step")
     ap.add_argument("--optimizer", default="adam", choices=["adam", "lamb", "lars"],
@@ -451,6 +674,10 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_gpu":
+        run_torch_gpu(args)
+    elif args.mode == "eval":
+        run_eval(args)
     else:
         run_ours(args)
 

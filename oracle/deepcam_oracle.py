@@ -233,6 +233,40 @@ def _block(P, p, spec, inp, train, tape):
     return out, inp
 
 
+def aspp_branch(P, p, feats, rate, train=True, tape=None):
+    """ASPP_module.forward, DX:298-302: conv (1x1, or 3x3 with dilation = padding = rate) -> BN -> ReLU."""
+    tape = tape if tape is not None else Tape(False)
+    pad = 0 if rate == 1 else rate
+    y = F.conv2d(feats, P[p + ".atrous_convolution.weight"], None, 1, pad, rate)
+    tape.add(p + ".atrous_convolution", "conv", feats, y, stride=1, pad=pad, dil=rate)
+    return _bn(P, p + ".bn", y, train, tape, relu=True)
+
+
+def decoder(P, y, ll, train=True, tape=None):
+    """DeconvUpsampler.forward, DX:376-383: y = fused ASPP features [N,256,h,w], ll = reduced low-level features [N,48,4h,4w]."""
+    tape = tape if tape is not None else Tape(False)
+    U = "upsample."
+
+    def deconv(name, v):
+        o = F.conv_transpose2d(v, P[U + name + ".0.weight"], None, 2, 1, 1)
+        tape.add(U + name + ".0", "convT", v, o)
+        return o
+
+    y = _bn(P, U + "deconv1.1", deconv("deconv1", y), train, tape, relu=True)
+    y = _bn(P, U + "deconv2.1", deconv("deconv2", y), train, tape, relu=True)
+    y = torch.cat((y, ll), dim=1)
+    t = F.conv2d(y, P[U + "conv1.0.weight"], None, 1, 1)
+    tape.add(U + "conv1.0", "conv", y, t, stride=1, pad=1, dil=1)
+    y = _bn(P, U + "conv1.1", t, train, tape, relu=True)
+    t = F.conv2d(y, P[U + "conv1.3.weight"], None, 1, 1)
+    tape.add(U + "conv1.3", "conv", y, t, stride=1, pad=1, dil=1)
+    y = _bn(P, U + "conv1.4", t, train, tape, relu=True)
+    t = F.conv2d(y, P[U + "conv1.6.weight"], P[U + "conv1.6.bias"])
+    tape.add(U + "conv1.6", "conv", y, t, stride=1, pad=0, dil=1)
+    y = _bn(P, U + "deconv3.1", deconv("deconv3", t), train, tape, relu=True)
+    return deconv("last_deconv", y)
+
+
 def forward(P, x, train=True, os=16, tape=None):
     """DeepLabv3_plus.forward, DX:441-465 (Xception.forward DX:195-242, DeconvUpsampler.forward DX:376-383).
     x: [N, n_input, H, W] with H, W multiples of 16.  Returns logits [N, n_classes, H, W]."""
@@ -258,11 +292,7 @@ def forward(P, x, train=True, os=16, tape=None):
     feats = h
     branches = []
     for i, rate in enumerate(aspp_rates(os)):
-        p = "aspp%d" % (i + 1)
-        pad = 0 if rate == 1 else rate
-        y = F.conv2d(feats, P[p + ".atrous_convolution.weight"], None, 1, pad, rate)
-        tape.add(p + ".atrous_convolution", "conv", feats, y, stride=1, pad=pad, dil=rate)
-        branches.append(_bn(P, p + ".bn", y, train, tape, relu=True))
+        branches.append(aspp_branch(P, "aspp%d" % (i + 1), feats, rate, train, tape))
     g = F.adaptive_avg_pool2d(feats, 1)
     tape.add("global_avg_pool.0", "gap", feats, g)
     g2 = F.conv2d(g, P["global_avg_pool.1.weight"])
@@ -276,27 +306,7 @@ def forward(P, x, train=True, os=16, tape=None):
     ll = F.conv2d(low, P["conv2.weight"])
     tape.add("conv2", "conv", low, ll, stride=1, pad=0, dil=1)
     ll = _bn(P, "bn2", ll, train, tape, relu=True)
-    U = "upsample."
-
-    def deconv(name, v):
-        o = F.conv_transpose2d(v, P[U + name + ".0.weight"], None, 2, 1, 1)
-        tape.add(U + name + ".0", "convT", v, o)
-        return o
-
-    y = _bn(P, U + "deconv1.1", deconv("deconv1", y), train, tape, relu=True)
-    y = _bn(P, U + "deconv2.1", deconv("deconv2", y), train, tape, relu=True)
-    y = torch.cat((y, ll), dim=1)
-    t = F.conv2d(y, P[U + "conv1.0.weight"], None, 1, 1)
-    tape.add(U + "conv1.0", "conv", y, t, stride=1, pad=1, dil=1)
-    y = _bn(P, U + "conv1.1", t, train, tape, relu=True)
-    t = F.conv2d(y, P[U + "conv1.3.weight"], None, 1, 1)
-    tape.add(U + "conv1.3", "conv", y, t, stride=1, pad=1, dil=1)
-    y = _bn(P, U + "conv1.4", t, train, tape, relu=True)
-    t = F.conv2d(y, P[U + "conv1.6.weight"], P[U + "conv1.6.bias"])
-    tape.add(U + "conv1.6", "conv", y, t, stride=1, pad=0, dil=1)
-    y = _bn(P, U + "deconv3.1", deconv("deconv3", t), train, tape, relu=True)
-    logits = deconv("last_deconv", y)
-    return logits
+    return decoder(P, y, ll, train, tape)
 
 
 def interpolation_upsampler(P, x, low, input_size, train=True, tape=None):
