@@ -581,7 +581,17 @@ def run_eval(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(333)
-    net = dx.DeepLabv3_plus(n_input=C_IN, n_classes=N_CLASSES, os=16, _print=False).to(dev).eval()
+    net = dx.DeepLabv3_plus(n_input=C_IN, n_classes=N_CLASSES, os=16, _print=False).to(dev)
+    # random-init weights with the initial running statistics (0, 1) blow the eval-mode activations up; ten train-mode forward
+    # passes on synthetic batches settle the running statistics first (not timed; what a few training steps would have done)
+    xc, _ = synthetic_host_batch(4000 + rank, 2)
+    xc = xc.to(dev)
+    net.train()
+    with torch.no_grad():
+        for _ in range(10):
+            net.forward(xc)
+    del xc
+    net.eval()
     b = args.eval_batch
     nbuf = 4                                         # distinct batches cycled through (each 113 MB: beyond L2 together with the activations)
     batches = []

@@ -180,6 +180,26 @@ class Tape:
             self.records[name] = dict(kind=kind, inp=inp, out=out, **attrs)
 
 
+_STORAGE = None      # None: the reference arithmetic (fp32/fp64 everywhere).  torch.bfloat16: see set_storage_dtype
+
+
+def set_storage_dtype(dtype):
+    """TEST AID.  With a dtype set, every tensor the reference would materialise between two operators (conv / depthwise /
+    transposed-conv outputs, BatchNorm(+ReLU) outputs, residual sums) is rounded to that dtype and back (straight-through:
+    the gradient passes unchanged), while all arithmetic stays in the tensors' own precision.  This models the product's
+    bf16 STORAGE format on top of the reference arithmetic, so that a multi-layer comparison isolates kernel errors from the
+    format's own effect (e.g. ReLU masks that flip where a bf16-rounded pre-activation crosses zero).  Returns the old value."""
+    global _STORAGE
+    old, _STORAGE = _STORAGE, dtype
+    return old
+
+
+def _q(x):
+    if _STORAGE is None:
+        return x
+    return x + (x.detach().to(_STORAGE).to(x.dtype) - x.detach())
+
+
 def _bn(P, name, x, train, tape, relu=False):
     rm, rv = P[name + ".running_mean"], P[name + ".running_var"]
     if train:
@@ -191,7 +211,7 @@ def _bn(P, name, x, train, tape, relu=False):
     if relu:
         y = F.relu(y)
         tape.add(name + "+relu", "relu", None, y)
-    return y
+    return _q(y)
 
 
 def _sep(P, name, x, stride, dil, tape):
@@ -200,9 +220,10 @@ def _sep(P, name, x, stride, dil, tape):
     c = x.shape[1]
     t = F.conv2d(xp, P[name + ".conv1.weight"], None, stride, 0, dil, c)
     tape.add(name + ".conv1", "dw", x, t, stride=stride, dil=dil)
+    t = _q(t)
     y = F.conv2d(t, P[name + ".pointwise.weight"])
     tape.add(name + ".pointwise", "conv", t, y, stride=1, pad=0, dil=1)
-    return y
+    return _q(y)
 
 
 def _block(P, p, spec, inp, train, tape):
@@ -225,10 +246,10 @@ def _block(P, p, spec, inp, train, tape):
     if (p + ".skip.weight") in P:
         s = F.conv2d(inp, P[p + ".skip.weight"], None, stride)
         tape.add(p + ".skip", "conv", inp, s, stride=stride, pad=0, dil=1)
-        s = _bn(P, p + ".skipbn", s, train, tape)
+        s = _bn(P, p + ".skipbn", _q(s), train, tape)
     else:
         s = inp
-    out = x + s
+    out = _q(x + s) if _STORAGE is not None else x + s
     tape.add(p, "block", inp, out)
     return out, inp
 
@@ -239,7 +260,7 @@ def aspp_branch(P, p, feats, rate, train=True, tape=None):
     pad = 0 if rate == 1 else rate
     y = F.conv2d(feats, P[p + ".atrous_convolution.weight"], None, 1, pad, rate)
     tape.add(p + ".atrous_convolution", "conv", feats, y, stride=1, pad=pad, dil=rate)
-    return _bn(P, p + ".bn", y, train, tape, relu=True)
+    return _bn(P, p + ".bn", _q(y), train, tape, relu=True)
 
 
 def decoder(P, y, ll, train=True, tape=None):
@@ -250,19 +271,22 @@ def decoder(P, y, ll, train=True, tape=None):
     def deconv(name, v):
         o = F.conv_transpose2d(v, P[U + name + ".0.weight"], None, 2, 1, 1)
         tape.add(U + name + ".0", "convT", v, o)
-        return o
+        return o if name == "last_deconv" else _q(o)          # the logits stay fp32 in the product as well
 
     y = _bn(P, U + "deconv1.1", deconv("deconv1", y), train, tape, relu=True)
     y = _bn(P, U + "deconv2.1", deconv("deconv2", y), train, tape, relu=True)
     y = torch.cat((y, ll), dim=1)
     t = F.conv2d(y, P[U + "conv1.0.weight"], None, 1, 1)
     tape.add(U + "conv1.0", "conv", y, t, stride=1, pad=1, dil=1)
+    t = _q(t)
     y = _bn(P, U + "conv1.1", t, train, tape, relu=True)
     t = F.conv2d(y, P[U + "conv1.3.weight"], None, 1, 1)
     tape.add(U + "conv1.3", "conv", y, t, stride=1, pad=1, dil=1)
+    t = _q(t)
     y = _bn(P, U + "conv1.4", t, train, tape, relu=True)
     t = F.conv2d(y, P[U + "conv1.6.weight"], P[U + "conv1.6.bias"])
     tape.add(U + "conv1.6", "conv", y, t, stride=1, pad=0, dil=1)
+    t = _q(t)
     y = _bn(P, U + "deconv3.1", deconv("deconv3", t), train, tape, relu=True)
     return deconv("last_deconv", y)
 
@@ -274,10 +298,10 @@ def forward(P, x, train=True, os=16, tape=None):
     X = "xception_features."
     h = F.conv2d(x, P[X + "conv1.weight"], None, 2, 1)
     tape.add(X + "conv1", "conv", x, h, stride=2, pad=1, dil=1)
-    h = _bn(P, X + "bn1", h, train, tape, relu=True)
+    h = _bn(P, X + "bn1", _q(h), train, tape, relu=True)
     t = F.conv2d(h, P[X + "conv2.weight"], None, 1, 1)
     tape.add(X + "conv2", "conv", h, t, stride=1, pad=1, dil=1)
-    h = _bn(P, X + "bn2", t, train, tape, relu=True)
+    h = _bn(P, X + "bn2", _q(t), train, tape, relu=True)
     blocks, exit_rate = xception_blocks(os)
     low = None
     outs = []
@@ -302,10 +326,10 @@ def forward(P, x, train=True, os=16, tape=None):
     cat = torch.cat(branches + [g2], dim=1)
     y = F.conv2d(cat, P["conv1.weight"])
     tape.add("conv1", "conv", cat, y, stride=1, pad=0, dil=1)
-    y = _bn(P, "bn1", y, train, tape, relu=True)
+    y = _bn(P, "bn1", _q(y), train, tape, relu=True)
     ll = F.conv2d(low, P["conv2.weight"])
     tape.add("conv2", "conv", low, ll, stride=1, pad=0, dil=1)
-    ll = _bn(P, "bn2", ll, train, tape, relu=True)
+    ll = _bn(P, "bn2", _q(ll), train, tape, relu=True)
     return decoder(P, y, ll, train, tape)
 
 

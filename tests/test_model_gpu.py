@@ -375,9 +375,14 @@ def test_fused_adam_trains_the_model_like_torch_adam(sd, graphs, monkeypatch):
     assert abs(lf[1] - lf[0]) > 1e-3, lf                       # the second forward saw updated weights
     for a, b in zip(lf, lt):
         assert abs(a - b) < 2e-2, (lf, lt)                     # bf16 trajectories (wgrad atomics reorder sums)
+    # both runs take bf16 gradients whose fp32 sums are reordered by atomics, and Adam's first steps move every weight by
+    # ~lr * sign(g): element-wise the two trajectories differ wherever a tiny gradient changes sign, so compare the DIRECTION of
+    # the total displacement (the update rule itself is pinned to 1e-6 on bare tensors in test_kernels_gpu.py)
     pf, pt = dict(net_f.named_parameters()), dict(net_t.named_parameters())
     k = "xception_features.block5.rep.1.pointwise.weight"
-    assert _rel(pf[k], pt[k]) < 1e-3
+    p0 = sd[k].to(DEV)
+    df, dt_ = (pf[k].detach() - p0).flatten().double(), (pt[k].detach() - p0).flatten().double()
+    assert float(df.norm()) > 0 and float(torch.dot(df, dt_) / (df.norm() * dt_.norm())) > 0.8
     # an eager call right after fused steps (new plan key: eval mode) must see the CURRENT weights
     x, _ = batches[0]
     net_f.eval(); net_t.eval()
@@ -417,8 +422,10 @@ def test_gradient_accumulation_under_graph_plans(sd, precision, monkeypatch):
         worst = max(worst, _rel(p.grad, want))
         # and clearly not 2 * g2 (the failure mode): only meaningful where g1 and g2 differ
     assert worst < tol, worst
+    # ... and clearly not 2 * g2, the failure mode (the replay overwrote the held gradient and autograd added the buffer to itself)
     k = "upsample.conv1.0.weight"
-    assert _rel(dict(net.named_parameters())[k].grad, 2 * single[1][k]) > 10 * tol or _rel(single[0][k], single[1][k]) < tol
+    assert _rel(single[0][k], single[1][k]) > 0.5          # the two batches give clearly different gradients
+    assert _rel(dict(net.named_parameters())[k].grad, 2 * single[1][k]) > 0.3
 
 
 def test_fp_loss_ignore_index_and_corrupted_labels():
