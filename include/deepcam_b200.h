@@ -195,6 +195,13 @@ int dc_bn_stats(const dc_bn_params* p, dc_view y, void* stream);
 /* out = [relu]( bn(y) [+ residual] ); residual.ptr may be NULL.  Views: channel-contiguous, 16-byte aligned,
  * C % 8 == 0 (bf16) or C % 4 == 0 (fp32). */
 int dc_bn_apply(const dc_bn_params* p, dc_view y, dc_view residual, dc_view out, void* stream);
+/* The ReLU -> SeparableConv2d_same chain of a Block (DX:79-97) in one launch: out = depthwise3x3(a), a = [relu](bn(y)), stride 1,
+ * dilation 1, train-mode BatchNorm whose batch sums are already in the workspace (DC_BN_TRAIN | DC_BN_SUMS_READY, as left by
+ * dc_conv_gemm_tc_bnstats).  The kernel finalizes the coefficients like dc_bn_apply (publishing them for the backward pass and
+ * updating the running statistics), applies them while the y tile sits in shared memory and never reads a back from memory;
+ * `act` (same shape as y, or a null view) receives a, bit-identical to what dc_bn_apply would store.  Returns -2 when the
+ * tile does not fit (the caller then runs dc_bn_apply + dc_dw_fwd). */
+int dc_dw_fwd_bn(const dc_bn_params* p, dc_view y, const void* w9c, dc_view act, dc_view out, void* stream);
 /* backward pass 1: g = dout * (out > 0 if RELU); sums of g and g*y into the zeroed workspace `rws`; the last block
  * writes dgamma/dbeta ([C] fp32, may be NULL) and the coefficients A, B, D. */
 int dc_bn_bwd_reduce(const dc_bn_params* p, dc_view dout, dc_view out, dc_view y, void* rws, float* dgamma, float* dbeta,

@@ -122,9 +122,14 @@ class SeparableConv2d_same(_EngineModule):
         self.conv1 = nn.Conv2d(inplanes, inplanes, kernel_size, stride, 0, dilation, groups=inplanes, bias=bias)
         self.pointwise = nn.Conv2d(inplanes, planes, 1, 1, 0, 1, 1, bias=bias)
 
-    def _emit(self, eng, x, bn=None):
-        """bn: BnSpec of the normalizer that follows (its batch sums then come out of the pointwise GEMM's epilogue)."""
-        t = eng.dw(x, _dw_spec(self.conv1))
+    def _emit(self, eng, x, bn=None, pre=None):
+        """bn: BnSpec of the normalizer that follows (its batch sums then come out of the pointwise GEMM's epilogue).
+        pre = (BnSpec, relu): x is still the PRE-BatchNorm tensor; the normalisation (+ReLU) in front of this unit is applied
+        by the depthwise kernel while it loads its tile (Engine.bn_dw)."""
+        if pre is not None:
+            _, t = eng.bn_dw(x, pre[0], pre[1], _dw_spec(self.conv1))
+        else:
+            t = eng.dw(x, _dw_spec(self.conv1))
         return eng.conv(t, _conv_spec(self.pointwise), bn=bn)
 
 
@@ -174,22 +179,26 @@ class Block(_EngineModule):
             skip_y = eng.conv(inp, _conv_spec(self.skip), bn=_bn_spec(self.skipbn))
         cur, pending = inp, None
         mods = list(self.rep._modules.values())
+        pre_relu = False
         for i, m in enumerate(mods):
             if isinstance(m, nn.ReLU):
                 if pending is not None:
-                    cur = eng.bn(pending[1], pending[0], relu=True)
-                    pending = None
+                    pre_relu = True                           # BatchNorm + this ReLU go into the next unit's depthwise load
                 elif not cur.is_relu:
                     cur = eng.bn(cur, None, relu=True)
             elif isinstance(m, SeparableConv2d_same):
-                if pending is not None:
-                    cur = eng.bn(pending[1], pending[0], relu=False)
-                    pending = None
                 nxt = mods[i + 1] if i + 1 < len(mods) else None
                 follows = nxt is not None and not isinstance(nxt, (nn.ReLU, SeparableConv2d_same))
-                cur = m._emit(eng, cur, bn=_bn_spec(nxt) if follows else None)
+                nbn = _bn_spec(nxt) if follows else None
+                if pending is not None:
+                    cur = m._emit(eng, pending[1], bn=nbn, pre=(pending[0], pre_relu))
+                    pending, pre_relu = None, False
+                else:
+                    cur = m._emit(eng, cur, bn=nbn)
             else:
                 pending = (_bn_spec(m), cur)
+        if pending is not None and pre_relu:                  # (no layout of the reference ends in BatchNorm -> ReLU)
+            cur, pending = eng.bn(pending[1], pending[0], relu=True), None
         if skip_y is not None:
             if pending is not None:
                 cur = eng.bn(pending[1], pending[0], relu=False)

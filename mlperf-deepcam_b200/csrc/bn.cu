@@ -105,27 +105,9 @@ static inline PixView<T> pix_view(const dc_view& v) {
   return r;
 }
 
-struct BnWs {
-  double* sums;     // [2][C]
-  float* coef;      // [4][C]
-  unsigned* ticket;
-};
-__host__ __device__ static inline BnWs bn_ws(void* ws, int C) {
-  BnWs w;
-  w.sums = reinterpret_cast<double*>(ws);
-  w.coef = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + (size_t)16 * C);
-  w.ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + (size_t)32 * C);
-  return w;
-}
-
 constexpr int kBnThreads = 256;
 constexpr int kUnroll = 4;
 
-// 1/sqrt(v) in fp32: hardware approximation + one Newton-Raphson step (~1 ulp)
-__device__ __forceinline__ float inv_sqrt_f32(float v) {
-  float r = rsqrtf(v);
-  return r * (1.5f - 0.5f * v * r * r);
-}
 
 // returns true in every thread of the block that took the last ticket
 __device__ __forceinline__ bool last_block(unsigned* ticket) {

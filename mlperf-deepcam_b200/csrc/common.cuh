@@ -139,6 +139,27 @@ static inline bool same_shape(const dc_view& a, const dc_view& b) {
 // bn.cu: sums[0][c] += sum of y[.., c], sums[1][c] += sum of squares (no finalize); used when a producer cannot do it itself
 int bn_accumulate_sums(const dc_view& y, double* sums, cudaStream_t st);
 
+// ---- BatchNorm workspace (bn.cu; also read by the BatchNorm-fused depthwise kernels in dw.cu) ----------------
+// dc_bn_ws_bytes(C) bytes: double sums[2][C] | float coef[4][C] | uint32 ticket[16]
+struct BnWs {
+  double* sums;     // [2][C]
+  float* coef;      // [4][C]
+  unsigned* ticket;
+};
+__host__ __device__ static inline BnWs bn_ws(void* ws, int C) {
+  BnWs w;
+  w.sums = reinterpret_cast<double*>(ws);
+  w.coef = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + (size_t)16 * C);
+  w.ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + (size_t)32 * C);
+  return w;
+}
+
+// 1/sqrt(v) in fp32: hardware approximation + one Newton-Raphson step (~1 ulp)
+__device__ __forceinline__ float inv_sqrt_f32(float v) {
+  float r = rsqrtf(v);
+  return r * (1.5f - 0.5f * v * r * r);
+}
+
 // ---- warp / block reductions -------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -327,6 +327,150 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_kernel(DwView<const T
   }
 }
 
+// ---- stride 1, dilation 1 forward with the PRECEDING BatchNorm (+ReLU) applied on load ------------------------------
+// The ReLU -> SeparableConv2d_same chain of every Block (DX:79-97) reads a = relu(bn(y)), where y is the previous pointwise
+// convolution's output whose batch sums came out of the GEMM epilogue (DC_BN_SUMS_READY).  Instead of one bn_apply launch
+// that writes a and one depthwise launch that reads it back, this kernel stages the raw y tile (halo included) in shared
+// memory, finalizes the block's <= 256 channels from the sums exactly as bn_apply_kernel does (same arithmetic, so the
+// activation is bit-identical; block (0, y, 0) publishes the coefficients for the backward pass and updates the running
+// statistics), applies scale/shift/ReLU in place - the zero padding of fixed_padding stays zero, it pads a, not y - writes
+// the interior of a (backward needs it: depthwise weight gradient, residual-free mask recompute does not) and then runs the
+// same input-stationary row walk as dw_s1d1_tile_kernel.
+template <typename T, int V>
+__global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_bn_kernel(dc_bn_params p, DwView<const T> in, const T* __restrict__ w9c,
+                                                                     DwView<T> act, DwView<T> out, int C, DwMap m) {
+  constexpr int VP = V / 2;
+  extern __shared__ uint4 dw_tile[];                  // [rs + 2][ppb + 2][cvp] | float scale[cvp * V] | float shift[cvp * V]
+  const DwLane l = dw_lane(m, out.h, out.w);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
+  const int TW = m.ppb + 2;
+  const int nrows = (l.y1 - l.y0) + 2;                // input rows y0-1 .. y1
+  const int x_base = blockIdx.x * m.ppb - 1, y_base = l.y0 - 1;
+  const int cv0 = blockIdx.y * m.cvp;
+  const int H = in.h, W = in.w;
+  const int nvec_max = (m.rs + 2) * TW * m.cvp;
+  float* s_scale = reinterpret_cast<float*>(dw_tile + nvec_max);
+  float* s_shift = s_scale + m.cvp * V;
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(dw_tile);
+  const int nvec = nrows * TW * m.cvp;
+  const int cshift = 31 - __clz(m.cvp);
+  pdl_sync();
+  {
+    const T* nbase = in.p + l.n * in.sn;
+    for (int i = threadIdx.x; i < nvec; i += kDwThreads) {
+      const int cl = i & (m.cvp - 1);
+      const int pix = i >> cshift;
+      const int ty = pix / TW, tx = pix - ty * TW;
+      const int gy = y_base + ty, gx = x_base + tx, cvi = cv0 + cl;
+      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W && cvi < m.cv;
+      const T* src = ok ? nbase + (long long)gy * in.sh + (long long)gx * in.sw + cvi * V : in.p;
+      cp_async16_zfill(tile_s + (uint32_t)i * 16u, src, ok);
+    }
+  }
+  {
+    // per-channel coefficients of this block's channel group while the tile is in flight (thread t -> one channel)
+    const int nch = m.cvp * V;
+    if ((int)threadIdx.x < nch) {
+      const int c = cv0 * V + threadIdx.x;
+      float sc = 0.f, sh = 0.f;
+      if (c < C) {
+        const BnWs ws = bn_ws(const_cast<double*>(p.sums), C);
+        const double inv_count = 1.0 / p.count;
+        const double mu = ws.sums[c] * inv_count;
+        double var = ws.sums[C + c] * inv_count - mu * mu;
+        if (var < 0.0) var = 0.0;
+        const float inv = inv_sqrt_f32((float)(var + (double)p.eps));
+        sc = p.gamma[c] * inv;
+        sh = p.beta[c] - (float)mu * sc;
+        if (blockIdx.x == 0 && blockIdx.z == 0) {
+          ws.coef[c] = sc;
+          ws.coef[C + c] = sh;
+          ws.coef[2 * C + c] = (float)mu;
+          ws.coef[3 * C + c] = inv;
+          if (p.running_mean != nullptr) {
+            const double unbias = p.count / (p.count - 1.0);
+            p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mu;
+            p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)(var * unbias);
+          }
+        }
+      }
+      s_scale[threadIdx.x] = sc;
+      s_shift[threadIdx.x] = sh;
+    }
+  }
+  float2 wv[9][VP];
+  if (l.ok) {
+    const int c0 = l.cvi * V;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dwpair<T>::unpack(ld16(w9c + (size_t)k * C + c0), wv[k]);
+  }
+  cp_async_commit_wait_all();
+  __syncthreads();
+  {
+    // a = [relu](y * scale + shift) in place; pixels outside the image stay zero (they pad a); interior pixels are stored
+    const bool relu = (p.flags & DC_BN_RELU) != 0;
+    T* abase = act.p ? act.p + l.n * act.sn : nullptr;
+    for (int i = threadIdx.x; i < nvec; i += kDwThreads) {
+      const int cl = i & (m.cvp - 1);
+      const int pix = i >> cshift;
+      const int ty = pix / TW, tx = pix - ty * TW;
+      const int gy = y_base + ty, gx = x_base + tx, cvi = cv0 + cl;
+      if (!(gy >= 0 && gy < H && gx >= 0 && gx < W && cvi < m.cv)) continue;
+      float2 f[VP];
+      dwpair<T>::unpack(dw_tile[i], f);
+#pragma unroll
+      for (int j = 0; j < VP; ++j) {
+        f[j].x = fmaf(f[j].x, s_scale[cl * V + 2 * j], s_shift[cl * V + 2 * j]);
+        f[j].y = fmaf(f[j].y, s_scale[cl * V + 2 * j + 1], s_shift[cl * V + 2 * j + 1]);
+        if (relu) { f[j].x = fmaxf(f[j].x, 0.f); f[j].y = fmaxf(f[j].y, 0.f); }
+      }
+      const uint4 o = dwpair<T>::pack(f);
+      dw_tile[i] = o;
+      if (abase != nullptr && ty >= 1 && ty <= nrows - 2 && tx >= 1 && tx <= m.ppb)
+        st16(abase + (long long)gy * act.sh + (long long)gx * act.sw + cvi * V, o);
+    }
+  }
+  __syncthreads();
+  if (!l.ok) return;
+  T* obase = out.p + l.n * out.sn + (long long)l.x * out.sw + l.cvi * V;
+  const uint4* tp = dw_tile + ((warp * m.ppw + psub) * m.cvp + cvl);      // tile column of x-1, row 0
+  const int rstride = TW * m.cvp;
+  auto step = [&](int ty, float2 (&A)[VP], float2 (&B)[VP], float2 (&Cn)[VP]) {
+    const uint4* rp = tp + ty * rstride;
+    float2 f[3][VP];
+    dwpair<T>::unpack(rp[0], f[0]);
+    dwpair<T>::unpack(rp[m.cvp], f[1]);
+    dwpair<T>::unpack(rp[2 * m.cvp], f[2]);
+#pragma unroll
+    for (int j = 0; j < VP; ++j) {
+      Cn[j] = mul2(f[0][j], wv[0][j]);
+      Cn[j] = fma2(f[1][j], wv[1][j], Cn[j]);
+      Cn[j] = fma2(f[2][j], wv[2][j], Cn[j]);
+      B[j] = fma2(f[0][j], wv[3][j], B[j]);
+      B[j] = fma2(f[1][j], wv[4][j], B[j]);
+      B[j] = fma2(f[2][j], wv[5][j], B[j]);
+      A[j] = fma2(f[0][j], wv[6][j], A[j]);
+      A[j] = fma2(f[1][j], wv[7][j], A[j]);
+      A[j] = fma2(f[2][j], wv[8][j], A[j]);
+    }
+    const int y = y_base + ty - 1;                     // output row completed by input row y_base + ty
+    if (y >= l.y0 && y < l.y1) st16(obase + (long long)y * out.sh, dwpair<T>::pack(A));
+  };
+  float2 a0[VP], a1[VP], a2[VP];
+#pragma unroll
+  for (int j = 0; j < VP; ++j) { a0[j] = make_float2(0.f, 0.f); a1[j] = a0[j]; a2[j] = a0[j]; }
+  int ty = 0;
+  while (true) {
+    step(ty, a0, a1, a2);
+    if (++ty >= nrows) break;
+    step(ty, a1, a2, a0);
+    if (++ty >= nrows) break;
+    step(ty, a2, a0, a1);
+    if (++ty >= nrows) break;
+  }
+}
+
 // ---- stride 1, dilation 1 backward-data FUSED with the ReLU mask and the BatchNorm backward reduction of the layer below ---
 // The depthwise conv's input a = relu(bn(y) [+ res]) is a BatchNorm output.  This kernel is the last writer of dL/da: it
 // finishes the gradient (adds what other consumers already stored when `accumulate`), rounds it to the storage type, masks
@@ -795,6 +939,23 @@ static bool dw_s1d1_tile_launch(const dc_view& in, const void* w, const dc_view&
   return true;
 }
 
+template <typename T, int V>
+static int dw_fwd_bn_t(const dc_bn_params& p, const dc_view& in, const void* w, const dc_view& act, const dc_view& out, cudaStream_t st) {
+  DwMap m = dw_map(out.c, V, out.h, out.w, out.n, 1 << 30, dw_tile_rows(out.h));
+  dim3 grid = dw_grid(m, out.w, out.n);
+  const size_t smem = (size_t)(m.rs + 2) * (m.ppb + 2) * m.cvp * 16 + (size_t)2 * m.cvp * V * sizeof(float);
+  if (smem > 200 * 1024) return fail(-2, "dc_dw_fwd_bn: tile does not fit (rows per strip %d)", m.rs);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(dw_s1d1_tile_bn_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return fail((int)e, "dc_dw_fwd_bn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  DwView<T> av = act.ptr ? dw_view<T>(act) : DwView<T>{nullptr, 0, 0, 0, 0, 0};
+  launch_k(dw_s1d1_tile_bn_kernel<T, V>, grid, dim3(kDwThreads), smem, st, p, dw_view<const T>(in), (const T*)w, av, dw_view<T>(out), out.c, m);
+  return launch_status("dc_dw_fwd_bn");
+}
+
 // rows per tile of the fused kernel: (rows + 2) halo rows + rows of y (+ rows of a and of the old gradient) must leave room
 // for 2 blocks per SM
 template <typename T, int V>
@@ -897,6 +1058,20 @@ int dc_dw_fwd(dc_view in, const void* w9c, int stride, int dil, dc_view out, voi
   DC_REQUIRE(w9c != nullptr && (reinterpret_cast<uintptr_t>(w9c) % 16) == 0, "dc_dw_fwd: weights must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   return in.dtype == DC_F32 ? dw_fwd_t<float>(in, w9c, stride, dil, out, st) : dw_fwd_t<__nv_bfloat16>(in, w9c, stride, dil, out, st);
+}
+
+int dc_dw_fwd_bn(const dc_bn_params* p, dc_view y, const void* w9c, dc_view act, dc_view out, void* stream) {
+  DC_REQUIRE(p != nullptr && p->sums != nullptr && p->gamma != nullptr && p->beta != nullptr, "dc_dw_fwd_bn: null BatchNorm argument");
+  DC_REQUIRE((p->flags & DC_BN_TRAIN) && (p->flags & DC_BN_SUMS_READY) && !(p->flags & DC_BN_IDENTITY),
+             "dc_dw_fwd_bn: train-mode BatchNorm whose batch sums are already in the workspace (DC_BN_SUMS_READY) required");
+  DC_REQUIRE(p->count > 1.0, "dc_dw_fwd_bn: more than one value per channel required");
+  if (int r = check_dw("dc_dw_fwd_bn", y, out, 1, 1)) return r;
+  if (act.ptr != nullptr) {
+    if (int r = check_dw("dc_dw_fwd_bn(act)", y, act, 1, 1)) return r;
+  }
+  DC_REQUIRE(w9c != nullptr && (reinterpret_cast<uintptr_t>(w9c) % 16) == 0, "dc_dw_fwd_bn: weights must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  return y.dtype == DC_F32 ? dw_fwd_bn_t<float, 4>(*p, y, w9c, act, out, st) : dw_fwd_bn_t<__nv_bfloat16, 8>(*p, y, w9c, act, out, st);
 }
 
 int dc_dw_bwd_data(dc_view dout, const void* w9c, int stride, int dil, dc_view din, int accumulate, void* stream) {

@@ -127,6 +127,8 @@ class CudaBackend:
         self.bn_bwd_split = os.environ.get("DEEPCAM_B200_BN_BWD_SPLIT", "1") not in ("0", "false", "")
         self.bn_bwd_split_max_bytes = int(os.environ.get("DEEPCAM_B200_BN_BWD_SPLIT_MAX_BYTES", str(1 << 40)))
         self.fuse_bn_bwd_res = os.environ.get("DEEPCAM_B200_FUSE_BN_BWD_RES", "1") not in ("0", "false", "")
+        # BatchNorm(+ReLU) applied while the following depthwise kernel loads its tile (dc_dw_fwd_bn): no bn_apply launch
+        self.fuse_bn_dw = os.environ.get("DEEPCAM_B200_FUSE_BN_DW", "1") not in ("0", "false", "")
         self.side_stream = None       # set by a graph plan: weight-gradient kernels run on a parallel graph branch
         self._side_dirty = False
 
@@ -374,6 +376,26 @@ class CudaBackend:
         ops.dw_fwd(x, self._dw_packed(spec), spec.stride, spec.dil, out)
         self.launches += 1
         return out
+
+    def bn_dw_fwd(self, y, bnspec, relu, dwspec, act, out, ready_sums):
+        """act <- [relu](bn(y)), out <- depthwise(act) in ONE launch (train-mode BatchNorm whose batch sums came out of the
+        producing GEMM's epilogue; stride 1, dilation 1).  Returns the BatchNorm workspace (as bn_fwd does), or None when the
+        fused kernel is not applicable - nothing has been launched then and the caller runs bn_fwd + dw_fwd."""
+        if not self.fuse_bn_dw or ready_sums is None or dwspec.stride != 1 or dwspec.dil != 1 or y.dtype != self.dtype:
+            return None
+        m = bnspec.module
+        n, h, w, c = y.shape
+        if n * h * w <= 1 or m.weight is None or m.bias is None:
+            return None
+        track = m.running_mean is not None
+        mom = m.momentum if m.momentum is not None else 0.1
+        flags = DC_BN_TRAIN | DC_BN_SUMS_READY | (DC_BN_RELU if relu else 0)
+        p = ops.bn_params(m.weight.detach(), m.bias.detach(), m.running_mean if track else None, m.running_var if track else None,
+                          ready_sums, n * h * w, mom, m.eps, flags)
+        if not ops.dw_fwd_bn(p, y, self._dw_packed(dwspec), act, out):
+            return None
+        self.launches += 1
+        return ready_sums
 
     def dw_bwd_data(self, dy, spec, dx, accumulate):
         ops.dw_bwd_data(dy, self._dw_packed(spec), spec.stride, spec.dil, dx, accumulate)

@@ -266,6 +266,34 @@ class Engine:
             self.tape.append(lambda: self._bn_bwd(y, out, spec, sums, relu, residual, training))
         return out
 
+    def bn_dw(self, y, spec, relu, dwspec):
+        """(a, t) with a = [relu](bn(y)) and t = depthwise(a): the ReLU -> SeparableConv2d_same chain of a Block (DX:79-97).
+        One launch when the backend can apply the BatchNorm while the depthwise kernel loads its tile (train mode, batch sums
+        already produced by the GEMM epilogue, stride 1, dilation 1); otherwise exactly bn() followed by dw().  The tape gets
+        the same two backward closures either way."""
+        training = bool(spec.module.training) or spec.module.running_mean is None
+        pre = getattr(y, "bn_sums", None)
+        ready = pre[1] if (pre is not None and training and pre[0] is spec.module and pre[1] is not None) else None
+        if ready is not None and hasattr(self.be, "bn_dw_fwd"):
+            n, h, w, c = y.shape
+            a = self.new_act(n, h, w, c, y.t.dtype)
+            t = self.new_act(n, h, w, c, y.t.dtype)
+            sums = self.be.bn_dw_fwd(y.t, spec, relu, dwspec, a.t, t.t, ready)
+            if sums is not None:
+                y.bn_sums = None
+                y.consumed += 1
+                a.is_relu = relu
+                a.consumed += 1
+                if spec.module.num_batches_tracked is not None:
+                    self.bn_trained.append(spec.module)
+                if self.record:
+                    a.bn_src = (y, spec, sums, relu, None)
+                    self.tape.append(lambda: self._bn_bwd(y, a, spec, sums, relu, None, True))
+                    self.tape.append(lambda: self._dw_bwd(a, t, dwspec, True))
+                return a, t
+        a = self.bn(y, spec, relu)
+        return a, self.dw(a, dwspec)
+
     def _bn_bwd(self, y, out, spec, sums, relu, residual, training):
         dout = out.grad
         if dout is None:

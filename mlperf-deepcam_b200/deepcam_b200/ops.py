@@ -260,6 +260,21 @@ def dw_fwd(x, w9c, stride, dil, out):
     return out
 
 
+def dw_fwd_bn(params, y, w9c, act, out):
+    """out = depthwise3x3(act), act = [relu](bn(y)) in one launch (dc_dw_fwd_bn); returns False when the tile does not fit
+    (nothing was launched)."""
+    _require_cuda(y, w9c, act, out)
+    state = {}
+
+    def run():
+        rc = _lib.load().dc_dw_fwd_bn(ctypes.byref(params), view(y), _p(w9c), view(act), view(out), _stream())
+        state["rc"] = rc
+        return 0 if rc == -2 else rc
+
+    _timed("dw_fwd_bn", 21.0 * out.numel(), _nbytes(y, act, out), run, "dc_dw_fwd_bn", tag="%s s1 d1" % _shape_tag(y))
+    return state["rc"] == 0
+
+
 def dw_bwd_data(dout, w9c, stride, dil, din, accumulate):
     _require_cuda(dout, w9c, din)
     _timed("dw_bwd_data", 18.0 * dout.numel(), _nbytes(dout, din) * (1.0 if not accumulate else 1.0) + (_nbytes(din) if accumulate else 0.0),

@@ -765,3 +765,62 @@ def test_bilinear_resize_matches_torch(dtype, out_dtype, C, hi, wi, ho, wo):
     first = dx.clone()
     be.bilinear_bwd(gbuf[..., 4:4 + C], dx, True)
     assert rel(from_nhwc(dx), 2 * from_nhwc(first)) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,H,W,relu", [(728, 48, 72, True), (128, 40, 52, True), (256, 13, 9, False), (64, 33, 300, True), (8, 5, 7, True)])
+def test_depthwise_forward_with_batchnorm_on_load(dtype, C, H, W, relu):
+    """dc_dw_fwd_bn (BatchNorm + ReLU applied while the depthwise kernel stages its tile) against the two launches it replaces
+    (dc_bn_apply on the GEMM-epilogue sums, then dc_dw_fwd): the stored activation, the depthwise output, the published
+    coefficients and the running statistics must be BIT-IDENTICAL - same arithmetic, one pass less."""
+    from deepcam_b200 import ops
+    from deepcam_b200.backend import BnSpec, DwSpec
+    torch.manual_seed(33)
+    be = backend(dtype)
+    N = 2
+    y = to_nhwc(torch.randn(N, C, H, W) * 1.7 + 0.4, dtype)
+    wdw = torch.nn.Parameter(torch.randn(C, 1, 3, 3, device=dev()) * 0.3)
+    dws = DwSpec("dw", wdw, 1, 1)
+
+    def fresh_bn():
+        torch.manual_seed(34)
+        bn = torch.nn.BatchNorm2d(C).to(dev())
+        with torch.no_grad():
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.uniform_(-0.5, 0.5)
+        return bn
+
+    def sums_of(y):
+        # what dc_conv_gemm_tc_bnstats leaves in the workspace: raw per-channel sum and sum of squares of the stored tensor
+        ws = torch.zeros(ops.bn_ws_elems(C), dtype=torch.float64, device=dev())
+        y64 = y.double().reshape(-1, C)
+        ws[:C] = y64.sum(0)
+        ws[C:2 * C] = (y64 * y64).sum(0)
+        return ws
+
+    bn_a, bn_b = fresh_bn(), fresh_bn()
+    a_ref, t_ref = be.empty(N, H, W, C), be.empty(N, H, W, C)
+    ws_ref = be.bn_fwd(y, BnSpec("a", bn_a), relu, None, a_ref, training=True, ready_sums=sums_of(y))
+    be.dw_fwd(a_ref, dws, t_ref)
+    a, t = torch.full_like(a_ref, 7.0), torch.full_like(t_ref, 7.0)
+    n0 = be.launches
+    ws = be.bn_dw_fwd(y, BnSpec("b", bn_b), relu, dws, a, t, sums_of(y))
+    assert ws is not None and be.launches - n0 == 1
+    torch.cuda.synchronize()
+    assert torch.equal(a, a_ref)
+    assert torch.equal(t, t_ref)
+    assert torch.equal(bn_a.running_mean, bn_b.running_mean) and torch.equal(bn_a.running_var, bn_b.running_var)
+    assert torch.equal(ws.view(torch.float32)[4 * C:8 * C], ws_ref.view(torch.float32)[4 * C:8 * C])      # coef[4][C]
+    # and against torch on the same rounded input
+    ref_bn = torch.nn.BatchNorm2d(C).double()
+    ref_bn.load_state_dict({k: v.cpu().double() if v.is_floating_point() else v.cpu() for k, v in fresh_bn().state_dict().items()})
+    ar = ref_bn(from_nhwc(y))
+    if relu:
+        ar = torch.relu(ar)
+    assert rel(from_nhwc(a), ar) < TOL[dtype]
+    # stride 2 / dilation 2 / eval mode are not fused: the backend declines before launching anything
+    n0 = be.launches
+    assert be.bn_dw_fwd(y, BnSpec("b", bn_b), relu, DwSpec("dw", wdw, 2, 1), a, t, sums_of(y)) is None
+    assert be.bn_dw_fwd(y, BnSpec("b", bn_b), relu, DwSpec("dw", wdw, 1, 2), a, t, sums_of(y)) is None
+    assert be.bn_dw_fwd(y, BnSpec("b", bn_b), relu, dws, a, t, None) is None
+    assert be.launches == n0

@@ -452,3 +452,30 @@ def test_fp_loss_ignore_index_and_corrupted_labels():
     assert bool(torch.isnan(loss2))
     loss2.backward()
     assert bool(torch.isnan(lg2.grad[1, :, 2, 3]).all())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_bn_on_load_depthwise_matches_unfused_model(sd, precision, monkeypatch):
+    """The whole network with dc_dw_fwd_bn (default) against DEEPCAM_B200_FUSE_BN_DW=0 (bn_apply + dw_fwd launches): the fused
+    kernel is bit-identical per layer, so logits and loss agree to the atomics' reordering noise, and the fused forward runs
+    ~40 launches fewer."""
+    monkeypatch.setenv("DEEPCAM_B200_GRAPHS", "0")
+    x, label = O.synthetic_batch(2, 64, 96, seed=81)
+    w = O.class_weights()
+    res = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("DEEPCAM_B200_FUSE_BN_DW", fuse)
+        net = _make(sd, precision).train()
+        out = net(x.to(DEV))
+        loss = losses.fp_loss(out, label.to(DEV), weight=w, fpw_1=w[1], fpw_2=w[2])
+        loss.backward()
+        res[fuse] = (out.detach(), float(loss), net._dc_last_launches, {k: p.grad.detach().clone() for k, p in net.named_parameters()},
+                     {k: v.clone() for k, v in net.state_dict().items() if "running" in k})
+    tol = 1e-4 if precision == "fp32" else 2e-2
+    assert _rel(res["1"][0], res["0"][0]) < tol
+    assert abs(res["1"][1] - res["0"][1]) < tol
+    assert res["0"][2] - res["1"][2] >= 35, (res["0"][2], res["1"][2])
+    worst = max(_rel(res["1"][3][k], res["0"][3][k]) for k in res["1"][3])
+    assert worst < (1e-3 if precision == "fp32" else 0.25), worst
+    for k, v in res["1"][4].items():
+        assert torch.allclose(v, res["0"][4][k], rtol=1e-4, atol=1e-6), k
