@@ -143,6 +143,13 @@ int dc_conv_gemm_tc(const dc_conv_desc* d, dc_view in, const void* w, const floa
  * statistics pass appended.  d->accumulate must be 0.  Replaces the statistics half of nn.BatchNorm2d after a conv. */
 int dc_conv_gemm_tc_bnstats(const dc_conv_desc* d, dc_view in, const void* w, const float* bias,
                             dc_view out, double* sums, void* stream);
+/* Eval-mode Conv2d / ConvTranspose2d-parity-class + BatchNorm2d (+ReLU) in ONE tcgen05 launch (DX:144-149, 291-293, 352-372 under
+ * net.eval(), TR:428): out = [relu]((conv(x) + bias) * scale + shift) with scale = gamma / sqrt(running_var + eps) and
+ * shift = beta - running_mean * scale derived inside the epilogue, applied to the fp32 accumulator before the single bf16
+ * rounding - the pre-BatchNorm tensor is never written.  Needs a bf16 output view the TMA-store epilogue can write; returns
+ * -2 (nothing launched) otherwise, and the caller runs dc_conv_gemm_tc + dc_bn_apply. */
+int dc_conv_gemm_tc_bn_eval(const dc_conv_desc* d, dc_view in, const void* w, const float* bias, dc_view out, const float* gamma,
+                            const float* beta, const float* running_mean, const float* running_var, float eps, int relu, void* stream);
 /* tcgen05 weight gradient (both operands pixel-major): same contract as dc_conv_wgrad_simt. */
 int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, void* stream);
 

@@ -261,14 +261,18 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_kernel(DwView<const T
     const int nvec = nrows * TW * m.cvp;
     const int cshift = 31 - __clz(m.cvp);
     const T* nbase = in.p + l.n * in.sn;
+    // (ty, tx) of this thread's vectors advance by a fixed pixel step < TW per iteration: tracked incrementally, the loop
+    // carries no integer division (it used to be a quarter of the kernel's instructions)
+    const int cl = threadIdx.x & (m.cvp - 1), cvi = cv0 + cl;
+    const int pstep = kDwThreads >> cshift;
+    int ty = (threadIdx.x >> cshift) / TW, tx = (threadIdx.x >> cshift) - ty * TW;
     for (int i = threadIdx.x; i < nvec; i += kDwThreads) {
-      const int cl = i & (m.cvp - 1);
-      const int pix = i >> cshift;
-      const int ty = pix / TW, tx = pix - ty * TW;
-      const int gy = y_base + ty, gx = x_base + tx, cvi = cv0 + cl;
+      const int gy = y_base + ty, gx = x_base + tx;
       const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W && cvi < m.cv;
       const T* src = ok ? nbase + (long long)gy * in.sh + (long long)gx * in.sw + cvi * V : in.p;
       cp_async16_zfill(tile_s + (uint32_t)i * 16u, src, ok);
+      tx += pstep;
+      if (tx >= TW) { tx -= TW; ++ty; }
     }
   }
   float2 wv[9][VP];
@@ -358,14 +362,18 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_bn_kernel(dc_bn_param
   pdl_sync();
   {
     const T* nbase = in.p + l.n * in.sn;
+    // (ty, tx) of this thread's vectors advance by a fixed pixel step < TW per iteration: tracked incrementally, the loop
+    // carries no integer division (it used to be a quarter of the kernel's instructions)
+    const int cl = threadIdx.x & (m.cvp - 1), cvi = cv0 + cl;
+    const int pstep = kDwThreads >> cshift;
+    int ty = (threadIdx.x >> cshift) / TW, tx = (threadIdx.x >> cshift) - ty * TW;
     for (int i = threadIdx.x; i < nvec; i += kDwThreads) {
-      const int cl = i & (m.cvp - 1);
-      const int pix = i >> cshift;
-      const int ty = pix / TW, tx = pix - ty * TW;
-      const int gy = y_base + ty, gx = x_base + tx, cvi = cv0 + cl;
+      const int gy = y_base + ty, gx = x_base + tx;
       const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W && cvi < m.cv;
       const T* src = ok ? nbase + (long long)gy * in.sh + (long long)gx * in.sw + cvi * V : in.p;
       cp_async16_zfill(tile_s + (uint32_t)i * 16u, src, ok);
+      tx += pstep;
+      if (tx >= TW) { tx -= TW; ++ty; }
     }
   }
   {
@@ -411,18 +419,24 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_bn_kernel(dc_bn_param
     // a = [relu](y * scale + shift) in place; pixels outside the image stay zero (they pad a); interior pixels are stored
     const bool relu = (p.flags & DC_BN_RELU) != 0;
     T* abase = act.p ? act.p + l.n * act.sn : nullptr;
-    for (int i = threadIdx.x; i < nvec; i += kDwThreads) {
-      const int cl = i & (m.cvp - 1);
-      const int pix = i >> cshift;
-      const int ty = pix / TW, tx = pix - ty * TW;
-      const int gy = y_base + ty, gx = x_base + tx, cvi = cv0 + cl;
+    const int cl = threadIdx.x & (m.cvp - 1), cvi = cv0 + cl;
+    const int pstep = kDwThreads >> cshift;
+    int ty = (threadIdx.x >> cshift) / TW, tx = (threadIdx.x >> cshift) - ty * TW;
+    float2 sc2[VP], sh2[VP];
+#pragma unroll
+    for (int j = 0; j < VP; ++j) {
+      sc2[j] = make_float2(s_scale[cl * V + 2 * j], s_scale[cl * V + 2 * j + 1]);
+      sh2[j] = make_float2(s_shift[cl * V + 2 * j], s_shift[cl * V + 2 * j + 1]);
+    }
+    for (int i = threadIdx.x; i < nvec; i += kDwThreads, tx += pstep) {
+      if (tx >= TW) { tx -= TW; ++ty; }
+      const int gy = y_base + ty, gx = x_base + tx;
       if (!(gy >= 0 && gy < H && gx >= 0 && gx < W && cvi < m.cv)) continue;
       float2 f[VP];
       dwpair<T>::unpack(dw_tile[i], f);
 #pragma unroll
       for (int j = 0; j < VP; ++j) {
-        f[j].x = fmaf(f[j].x, s_scale[cl * V + 2 * j], s_shift[cl * V + 2 * j]);
-        f[j].y = fmaf(f[j].y, s_scale[cl * V + 2 * j + 1], s_shift[cl * V + 2 * j + 1]);
+        f[j] = fma2(f[j], sc2[j], sh2[j]);
         if (relu) { f[j].x = fmaxf(f[j].x, 0.f); f[j].y = fmaxf(f[j].y, 0.f); }
       }
       const uint4 o = dwpair<T>::pack(f);

@@ -183,6 +183,14 @@ struct TcFpropParams {
   TcOut out;
   double* stats;       // BatchNorm workspace sums[2][stats_C] of the layer that normalises `out` (or null): the epilogue adds the
   int stats_C;         // per-channel sum and sum of squares of the bf16-rounded outputs it stores (TMA-store path only)
+  // eval-mode BatchNorm (+ReLU) folded into the epilogue (TMA-store path only; aff_gamma null = off):
+  //   out = [relu]((acc + bias) * scale + shift), scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale
+  const float* aff_gamma;
+  const float* aff_beta;
+  const float* aff_mean;
+  const float* aff_var;
+  float aff_eps;
+  int aff_relu;
 };
 
 // Build with -DDC_TC_TRACE (tools/tc_trace.py) to record SM-clock timestamps of the persistent kernel's phases per CTA:
@@ -667,6 +675,24 @@ __global__ void __launch_bounds__(kTc2Threads, 1) conv_gemm_tc2_kernel(const __g
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
           }
+          // eval-mode BatchNorm folded into the epilogue: the group's first 64 threads derive scale / shift of the chunk's 64
+          // columns from the running statistics (same arithmetic as the eval branch of bn_apply) into the group's 2 KB scratch
+          float* scoef = reinterpret_cast<float*>(smem_gen + stg_off + 32768 + grp * 2048);      // [scale 64 | shift 64]
+          if (p.aff_gamma != nullptr) {
+            const int t = (int)threadIdx.x - 64 - 128 * grp;
+            if (t < 64) {
+              const int c = n0 + c0 + t;
+              float sc = 0.f, sh = 0.f;
+              if (c0 + t < ncols) {
+                const float inv = inv_sqrt_f32(p.aff_var[c] + p.aff_eps);
+                sc = p.aff_gamma[c] * inv;
+                sh = p.aff_beta[c] - p.aff_mean[c] * sc;
+                if (p.bias) sh = fmaf(p.bias[c], sc, sh);
+              }
+              scoef[t] = sc;
+              scoef[64 + t] = sh;
+            }
+          }
           epi_group_sync(grp);
           const uint32_t sbuf = stg_s + (uint32_t)row * 128u;
 #pragma unroll
@@ -679,7 +705,12 @@ __global__ void __launch_bounds__(kTc2Threads, 1) conv_gemm_tc2_kernel(const __g
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   f[j] = __uint_as_float(v[h][8 * q + j]);
-                  if (p.bias && c0 + 32 * h + 8 * q + j < ncols) f[j] += p.bias[n0 + c0 + 32 * h + 8 * q + j];
+                  if (p.aff_gamma != nullptr) {
+                    f[j] = fmaf(f[j], scoef[32 * h + 8 * q + j], scoef[64 + 32 * h + 8 * q + j]);
+                    if (p.aff_relu) f[j] = fmaxf(f[j], 0.f);
+                  } else if (p.bias && c0 + 32 * h + 8 * q + j < ncols) {
+                    f[j] += p.bias[n0 + c0 + 32 * h + 8 * q + j];
+                  }
                 }
                 __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]), b1 = __floats2bfloat162_rn(f[2], f[3]);
                 __nv_bfloat162 b2 = __floats2bfloat162_rn(f[4], f[5]), b3 = __floats2bfloat162_rn(f[6], f[7]);
@@ -1215,6 +1246,15 @@ static TcV2Cfg pick_v2_cfg(int mtiles, int Co, int kblocks, int wtaps, bool tma_
       if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; best_bm2 = bm2; }
     }
   }
+  {
+    // experiment knob (tools/kbench.py sweeps): DEEPCAM_B200_TC_FORCE_BN=<n> overrides the N tile chosen by the cost model
+    static int force_bn = -1;
+    if (force_bn < 0) { const char* e = getenv("DEEPCAM_B200_TC_FORCE_BN"); force_bn = e ? atoi(e) : 0; }
+    if (force_bn >= 16 && force_bn <= 256 && force_bn % 16 == 0 && (!tma_store || force_bn % 64 == 0 || force_bn >= co16)) {
+      best_bn = std::min(force_bn, co16);
+      best_bm2 = 0;
+    }
+  }
   c.BN = best_bn;
   c.bm2 = best_bm2;
   c.real_mtiles = mtiles;
@@ -1274,8 +1314,12 @@ using namespace dc;
 extern "C" {
 
 // stats != null: *stats_done tells the caller whether the epilogue accumulated the BatchNorm sums (TMA-store path)
+struct TcAffine {           // eval-mode BatchNorm folded into the epilogue (null gamma = none)
+  const float* gamma; const float* beta; const float* mean; const float* var; float eps; int relu;
+};
+
 static int conv_gemm_tc_impl(const dc_conv_desc* d, dc_view in, const void* w, const float* bias, dc_view out, double* stats,
-                             bool* stats_done, void* stream) {
+                             bool* stats_done, void* stream, const TcAffine* aff = nullptr) {
   DC_REQUIRE(d != nullptr && d->ntaps >= 1 && d->ntaps <= DC_MAX_TAPS, "dc_conv_gemm_tc: bad descriptor");
   DC_REQUIRE(tc_view_ok(in), "dc_conv_gemm_tc: input must be bf16, channel-contiguous, C %% 8 == 0, 16-byte aligned strides");
   DC_REQUIRE(view_ok(out) && out.n == in.n, "dc_conv_gemm_tc: bad output view");
@@ -1299,6 +1343,14 @@ static int conv_gemm_tc_impl(const dc_conv_desc* d, dc_view in, const void* w, c
                   (reinterpret_cast<uintptr_t>(out.ptr) % 16) == 0) ? 1 : 0;
   p.stats = nullptr;
   p.stats_C = out.c;
+  p.aff_gamma = p.aff_beta = p.aff_mean = p.aff_var = nullptr;
+  p.aff_eps = 0.f; p.aff_relu = 0;
+  if (aff != nullptr) {
+    // the folded epilogue exists on the persistent kernel's TMA-store path only
+    if (use_v1_kernel() || !p.out_vec_ok || d->accumulate) return fail(-2, "dc_conv_gemm_tc_bn_eval: output layout needs the generic epilogue");
+    p.aff_gamma = aff->gamma; p.aff_beta = aff->beta; p.aff_mean = aff->mean; p.aff_var = aff->var;
+    p.aff_eps = aff->eps; p.aff_relu = aff->relu;
+  }
   if (stats_done) *stats_done = false;
   if (int r = build_gather("dc_conv_gemm_tc", d, in, p.TH, p.TW, maps, p)) return r;
   const long long Ktot = (long long)d->wtaps * p.kblocks * 64;
@@ -1343,6 +1395,15 @@ int dc_conv_gemm_tc_bnstats(const dc_conv_desc* d, dc_view in, const void* w, co
   if (int r = conv_gemm_tc_impl(d, in, w, bias, out, sums, &done, stream)) return r;
   if (done) return 0;
   return dc::bn_accumulate_sums(out, sums, as_stream(stream));     // output layout without the TMA-store epilogue: one extra pass
+}
+
+int dc_conv_gemm_tc_bn_eval(const dc_conv_desc* d, dc_view in, const void* w, const float* bias, dc_view out, const float* gamma,
+                            const float* beta, const float* running_mean, const float* running_var, float eps, int relu, void* stream) {
+  DC_REQUIRE(gamma != nullptr && beta != nullptr && running_mean != nullptr && running_var != nullptr,
+             "dc_conv_gemm_tc_bn_eval: null BatchNorm argument");
+  DC_REQUIRE(d != nullptr && d->out_csplit == 0, "dc_conv_gemm_tc_bn_eval: two-segment outputs are not supported");
+  const TcAffine aff = {gamma, beta, running_mean, running_var, eps, relu ? 1 : 0};
+  return conv_gemm_tc_impl(d, in, w, bias, out, nullptr, nullptr, stream, &aff);
 }
 
 int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, void* stream) {

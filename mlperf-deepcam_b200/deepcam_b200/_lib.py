@@ -64,6 +64,8 @@ SIGNATURES = {
     "dc_conv_wgrad_simt": (c_int, [POINTER(dc_conv_desc), dc_view, dc_view, c_void_p, c_void_p]),
     "dc_conv_gemm_tc": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p]),
     "dc_conv_gemm_tc_bnstats": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p, c_void_p]),
+    "dc_conv_gemm_tc_bn_eval": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_float, c_int, c_void_p]),
     "dc_conv_wgrad_tc": (c_int, [POINTER(dc_conv_desc), dc_view, dc_view, c_void_p, c_void_p]),
     "dc_dw_fwd": (c_int, [dc_view, c_void_p, c_int, c_int, dc_view, c_void_p]),
     "dc_dw_fwd_bn": (c_int, [POINTER(dc_bn_params), dc_view, c_void_p, dc_view, dc_view, c_void_p]),

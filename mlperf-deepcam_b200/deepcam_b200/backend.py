@@ -129,6 +129,8 @@ class CudaBackend:
         self.fuse_bn_bwd_res = os.environ.get("DEEPCAM_B200_FUSE_BN_BWD_RES", "1") not in ("0", "false", "")
         # BatchNorm(+ReLU) applied while the following depthwise kernel loads its tile (dc_dw_fwd_bn): no bn_apply launch
         self.fuse_bn_dw = os.environ.get("DEEPCAM_B200_FUSE_BN_DW", "1") not in ("0", "false", "")
+        # eval mode without gradient recording: BatchNorm (+ReLU) folded into the producing GEMM's epilogue
+        self.fold_bn_eval = os.environ.get("DEEPCAM_B200_FOLD_BN_EVAL", "1") not in ("0", "false", "")
         self.side_stream = None       # set by a graph plan: weight-gradient kernels run on a parallel graph branch
         self._side_dirty = False
 
@@ -283,6 +285,35 @@ class CudaBackend:
                     taps = convdesc.convT_fprop_taps(spec.k, s, spec.pad, ph, pw)
                     self._gemm(taps, 1, False, kk, x, w, bias, out[:, ph::s, pw::s, :], impl, sums)
         return sums
+
+    def conv_bn_eval_fwd(self, x, spec, bnspec, relu, out):
+        """out <- [relu](bn_eval(conv(x))) with the eval-mode BatchNorm folded into the tcgen05 epilogue (no pre-BatchNorm tensor,
+        no bn_apply launch).  Returns False - nothing launched - when this layer cannot take that path (SIMT layers, fp32
+        mode, output layouts that need the generic epilogue); the caller then runs conv_fwd + bn_fwd."""
+        m = bnspec.module
+        if (not self.fold_bn_eval or m.running_mean is None or m.weight is None or m.bias is None or out.dtype != torch.bfloat16
+                or not self._tc_ok(x, spec.co)):
+            return False
+        w = self._packed(spec, "fprop", "tc", x, n_pad=out.shape[3])
+        bias = spec.bias.detach() if spec.bias is not None else None
+        kk = spec.k * spec.k
+        args = (m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var, m.eps, relu)
+        if not spec.transposed:
+            desc = ops.make_desc(convdesc.conv_fprop_taps(spec.k, spec.pad, spec.dil), (spec.stride, spec.stride), False, kk)
+            if not ops.conv_gemm_bn_eval(desc, x, w, bias, out, *args):
+                return False
+            self.launches += 1
+            return True
+        s = spec.stride
+        for ph in range(s):
+            for pw in range(s):
+                desc = ops.make_desc(convdesc.convT_fprop_taps(spec.k, s, spec.pad, ph, pw), (1, 1), False, kk)
+                if not ops.conv_gemm_bn_eval(desc, x, w, bias, out[:, ph::s, pw::s, :], *args):
+                    if ph or pw:
+                        raise RuntimeError("deepcam_b200: transposed-convolution parity classes disagree on the epilogue path")
+                    return False
+                self.launches += 1
+        return True
 
     def _convT_fusable(self, spec, out):
         """Few-channel stride-2 transposed convolution (last_deconv, DX:374) into a dense output: the four parity launches

@@ -46,10 +46,11 @@ def _make_backend(precision, device):
 
 class Act:
     """Channels-last activation: tensor [N,H,W,C] (possibly a channel slice of a concat buffer) + its gradient."""
-    __slots__ = ("t", "_grad", "is_relu", "needs_grad", "parent", "c_off", "bn_sums", "consumed", "bn_src", "bn_reduced")
+    __slots__ = ("t", "_grad", "is_relu", "needs_grad", "parent", "c_off", "bn_sums", "consumed", "bn_src", "bn_reduced", "deferred")
 
     def __init__(self, t, is_relu=False, needs_grad=True, parent=None, c_off=0):
         self.t = t
+        self.deferred = None      # (x, ConvSpec, shape, dtype): a convolution not launched yet (eval-mode BatchNorm folding)
         self.bn_sums = None       # (BatchNorm module, workspace) when the producing conv already accumulated the batch sums
         self.consumed = 0         # operations that have taken this activation as an input so far (forward order)
         self.bn_src = None        # (y, spec, sums, relu, residual) when this is the output of a train-mode BatchNorm
@@ -62,6 +63,8 @@ class Act:
 
     @property
     def shape(self):
+        if self.t is None:
+            return self.deferred[2]
         return tuple(self.t.shape)
 
     @property
@@ -170,14 +173,22 @@ class Engine:
     def conv(self, x, spec, out=None, out_c=None, out_dtype=None, bn=None):
         """bn: the BnSpec that will normalise the result next (Engine.bn on the returned Act): in training mode the
         convolution kernel then also produces the batch sums, see CudaBackend.conv_fwd."""
+        self._materialize(x)
         n, h, w, _ = x.shape
         x.consumed += 1
         ho, wo = spec.out_hw(h, w)
+        want = bn is not None and (bool(bn.module.training) or bn.module.running_mean is None)
+        if (bn is not None and not want and not self.record and out is None and out_c is None
+                and hasattr(self.be, "conv_bn_eval_fwd")):
+            # eval mode, nothing recorded: do not launch yet - Engine.bn folds the normalisation into this GEMM's epilogue
+            # (anything else that touches the result first materialises it, see _materialize)
+            act = Act(None)
+            act.deferred = (x, spec, (n, ho, wo, spec.co), out_dtype or x.t.dtype)
+            return act
         if out is None:
             out = self.new_act(n, ho, wo, out_c or spec.co, out_dtype or x.t.dtype)
         elif out.shape[:3] != (n, ho, wo):
             raise RuntimeError("conv %s: output buffer %s does not match %s" % (spec.name, out.shape, (n, ho, wo)))
-        want = bn is not None and (bool(bn.module.training) or bn.module.running_mean is None)
         if want:
             out.bn_sums = (bn.module, self.be.conv_fwd(x.t, spec, out.t, want_bn_sums=True))
         else:
@@ -185,6 +196,15 @@ class Engine:
         if self.record:
             self.tape.append(lambda: self._conv_bwd(x, out, spec))
         return out
+
+    def _materialize(self, act):
+        """Launch a deferred convolution as it is (its consumer turned out not to be a foldable eval-mode BatchNorm)."""
+        if act.deferred is not None:
+            x, spec, shape, dtype = act.deferred
+            act.deferred = None
+            act.t = self.be.empty(*shape, dtype)
+            self.be.conv_fwd(x.t, spec, act.t)
+        return act
 
     def _conv_bwd(self, x, out, spec):
         dy = out.grad
@@ -202,6 +222,7 @@ class Engine:
             self.be.conv_bwd_data(dy, spec, dx, acc)
 
     def dw(self, x, spec):
+        self._materialize(x)
         n, h, w, c = x.shape
         ho, wo = spec.out_hw(h, w)
         out = self.new_act(n, ho, wo, c, x.t.dtype)
@@ -236,6 +257,18 @@ class Engine:
 
     def bn(self, y, spec, relu, residual=None, out=None):
         """out = [relu](bn(y) [+ residual]); spec None = identity (plain relu / add / copy)."""
+        if y.deferred is not None:
+            x_in, cspec, shape, dtype = y.deferred
+            if spec is not None and residual is None and (out is None or out.shape == shape):
+                dst = out if out is not None else self.new_act(*shape, dtype)
+                if self.be.conv_bn_eval_fwd(x_in.t, cspec, spec, relu, dst.t):
+                    y.deferred = None
+                    y.consumed += 1
+                    dst.is_relu = relu
+                    return dst
+            self._materialize(y)
+        if residual is not None:
+            self._materialize(residual)
         n, h, w, c = y.shape
         y.consumed += 1
         if residual is not None:
@@ -271,6 +304,9 @@ class Engine:
         One launch when the backend can apply the BatchNorm while the depthwise kernel loads its tile (train mode, batch sums
         already produced by the GEMM epilogue, stride 1, dilation 1); otherwise exactly bn() followed by dw().  The tape gets
         the same two backward closures either way."""
+        if y.deferred is not None:                            # eval mode: conv + BatchNorm(+ReLU) fold, then a plain depthwise
+            a = self.bn(y, spec, relu)
+            return a, self.dw(a, dwspec)
         training = bool(spec.module.training) or spec.module.running_mean is None
         pre = getattr(y, "bn_sums", None)
         ready = pre[1] if (pre is not None and training and pre[0] is spec.module and pre[1] is not None) else None
@@ -326,6 +362,7 @@ class Engine:
 
     def gap(self, x):
         """AdaptiveAvgPool2d(1): [N,H,W,C] -> fp32 [N,1,1,C]."""
+        self._materialize(x)
         n, h, w, c = x.shape
         x.consumed += 1
         m = self.be.gap_fwd(x.t)
@@ -361,6 +398,7 @@ class Engine:
 
     def bilinear(self, x, ho, wo, out=None, out_dtype=None):
         """F.interpolate(x, size=(ho, wo), mode='bilinear', align_corners=True) (DX:327-331); `out` may be a concat slice."""
+        self._materialize(x)
         n, _, _, c = x.shape
         x.consumed += 1
         if out is None:

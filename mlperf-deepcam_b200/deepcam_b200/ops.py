@@ -237,6 +237,27 @@ def conv_gemm(desc, x, w, bias, out, impl, bn_sums=None, flop_scale=1.0):
     return out
 
 
+def conv_gemm_bn_eval(desc, x, w, bias, out, gamma, beta, running_mean, running_var, eps, relu):
+    """out = [relu](bn_eval(conv(x) + bias)) in one tcgen05 launch (dc_conv_gemm_tc_bn_eval).  Returns False when the output
+    layout needs the generic epilogue (nothing was launched)."""
+    _require_cuda(x, w, out, gamma, beta, running_mean, running_var)
+    lib = _lib.load()
+    m = out.shape[0] * out.shape[1] * out.shape[2]
+    flops = 2.0 * m * out.shape[3] * x.shape[3] * desc.ntaps
+    nbytes = _nbytes(x, out) + desc.ntaps * x.shape[3] * out.shape[3] * x.element_size()
+    state = {}
+
+    def run():
+        rc = lib.dc_conv_gemm_tc_bn_eval(ctypes.byref(desc), view(x), _p(w), _p(bias), view(out), _p(gamma), _p(beta),
+                                         _p(running_mean), _p(running_var), float(eps), int(bool(relu)), _stream())
+        state["rc"] = rc
+        return 0 if rc == -2 else rc
+
+    _timed("conv_gemm_tc", flops, nbytes, run, "dc_conv_gemm_tc_bn_eval",
+           tag="M%d Ci%d Co%d taps%d s%d +bn_eval" % (m, x.shape[3], out.shape[3], desc.ntaps, desc.stride_h))
+    return state["rc"] == 0
+
+
 def conv_wgrad(desc, x, dout, G, impl):
     _require_cuda(x, dout, G)
     assert G.dtype == torch.float32

@@ -824,3 +824,60 @@ def test_depthwise_forward_with_batchnorm_on_load(dtype, C, H, W, relu):
     assert be.bn_dw_fwd(y, BnSpec("b", bn_b), relu, DwSpec("dw", wdw, 1, 2), a, t, sums_of(y)) is None
     assert be.bn_dw_fwd(y, BnSpec("b", bn_b), relu, dws, a, t, None) is None
     assert be.launches == n0
+
+
+@pytest.mark.parametrize("case", [
+    # name, Ci, Co, k, stride, pad, dil, H, W, transposed, slice, relu, bias
+    ("pw728", 728, 728, 1, 1, 0, 1, 48, 72, False, False, True, False),
+    ("aspp_d6_slice", 256, 256, 3, 1, 6, 6, 16, 24, False, True, True, False),
+    ("skip_s2_norelu", 128, 256, 1, 2, 0, 1, 24, 40, False, False, False, False),
+    ("deconv", 256, 256, 3, 2, 1, 1, 12, 18, True, True, True, False),
+    ("entry3x3s2", 16, 32, 3, 2, 1, 1, 32, 48, False, False, True, False),
+    ("pw_bias", 256, 256, 1, 1, 0, 1, 16, 24, False, False, True, True),
+], ids=lambda c: c[0])
+def test_conv_tcgen05_eval_batchnorm_folded_into_epilogue(case):
+    """dc_conv_gemm_tc_bn_eval (eval-mode BatchNorm + ReLU applied to the fp32 accumulator in the GEMM epilogue) against
+    torch conv -> batch_norm(training=False) -> relu in float64 on the same bf16-rounded operands, and against the two
+    launches it replaces."""
+    from deepcam_b200.backend import BnSpec, ConvSpec
+    name, Ci, Co, k, stride, pad, dil, H, W, transposed, use_slice, relu, bias = case
+    torch.manual_seed(44)
+    be = backend(torch.bfloat16, use_tc=True)
+    N = 2
+    if transposed:
+        mod = torch.nn.ConvTranspose2d(Ci, Co, k, stride=stride, padding=pad, output_padding=1, bias=bias)
+    else:
+        mod = torch.nn.Conv2d(Ci, Co, k, stride=stride, padding=pad, dilation=dil, bias=bias)
+    with torch.no_grad():
+        mod.weight.copy_(mod.weight.bfloat16().float())
+    bn = torch.nn.BatchNorm2d(Co)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.5, 0.5)
+        bn.running_mean.uniform_(-0.3, 0.3); bn.running_var.uniform_(0.5, 2.0)
+    bn.eval()
+    x = rounded(torch.randn(N, Ci, H, W), torch.bfloat16)
+    ref = bn.double()(mod.double()(x))
+    if relu:
+        ref = torch.relu(ref)
+    mod, bn = mod.float().to(dev()), bn.float().to(dev())
+    spec = ConvSpec("c", mod.weight, mod.bias, stride, pad, dil, transposed)
+    Ho, Wo = spec.out_hw(H, W)
+    xg = to_nhwc(x, torch.bfloat16)
+    buf = torch.full((N, Ho, Wo, Co + 512 if use_slice else Co), 3.0, dtype=torch.bfloat16, device=dev())
+    out = buf[..., 256:256 + Co] if use_slice else buf
+    n0 = be.launches
+    assert be.conv_bn_eval_fwd(xg, spec, BnSpec("bn", bn), relu, out)
+    assert be.launches - n0 == (4 if transposed else 1)
+    torch.cuda.synchronize()
+    assert rel(from_nhwc(out), ref) < 4e-3                              # one bf16 rounding of the final value
+    if use_slice:
+        assert float((buf[..., :256] - 3.0).abs().max()) == 0.0 and float((buf[..., 256 + Co:] - 3.0).abs().max()) == 0.0
+    y = be.empty(N, Ho, Wo, Co)
+    be.conv_fwd(xg, spec, y)
+    out2 = be.empty(N, Ho, Wo, Co)
+    be.bn_fwd(y, BnSpec("bn", bn), relu, None, out2, training=False)
+    assert rel(out, out2) < 8e-3                                         # the unfused pair rounds twice
+    # fp32 output views take the generic epilogue: the call declines without launching
+    n0 = be.launches
+    assert not be.conv_bn_eval_fwd(xg, spec, BnSpec("bn", bn), relu, torch.empty(N, Ho, Wo, Co, device=dev()))
+    assert be.launches == n0

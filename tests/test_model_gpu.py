@@ -479,3 +479,69 @@ def test_bn_on_load_depthwise_matches_unfused_model(sd, precision, monkeypatch):
     assert worst < (1e-3 if precision == "fp32" else 0.25), worst
     for k, v in res["1"][4].items():
         assert torch.allclose(v, res["0"][4][k], rtol=1e-4, atol=1e-6), k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_output_stride_8_on_cuda_kernels(precision):
+    """os=8 (DX:136-139, 413-414): block3 stride 1, middle-flow depthwise dilation 2, exit-flow dilation 2 / 4, ASPP rates
+    12 / 24 / 36 - on the CUDA kernels (this configuration had only run on the CPU interpreter).  fp32 mode end to
+    end against the fp64 oracle (logits 1e-4, loss 1e-5, every gradient finite and the bulk within 3e-2); bf16 through the loss."""
+    sd8 = O.init_state_dict(16, 3, 8, seed=333)
+    x, label = O.synthetic_batch(2, 64, 96, seed=91)
+    P = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd8.items()}
+    for k in O.param_names(sd8):
+        P[k].requires_grad_(True)
+    ref_logits = O.forward(P, x.double(), train=True, os=8)
+    w = O.class_weights()
+    ref_loss = O.fp_loss(ref_logits, label, w)
+    ref_loss.backward()
+    net = dx.DeepLabv3_plus(16, 3, 8, _print=False)
+    net.load_state_dict(sd8)
+    net.precision = precision
+    net = net.to(DEV).train()
+    out = net(x.to(DEV))
+    loss = losses.fp_loss(out, label.to(DEV), weight=w, fpw_1=w[1], fpw_2=w[2])
+    loss.backward()
+    assert all(bool(torch.isfinite(p.grad).all()) for p in net.parameters())
+    errs = sorted(_rel(p.grad, P[k].grad) for k, p in net.named_parameters())
+    _record("os8_%s" % precision, dict(logits_rel=_rel(out, ref_logits), loss=float(loss), ref_loss=float(ref_loss),
+                                       median_grad=errs[len(errs) // 2], max_grad=errs[-1]))
+    if precision == "fp32":
+        assert _rel(out, ref_logits) < 1e-4
+        assert abs(float(loss) - float(ref_loss)) < 1e-5
+        assert errs[len(errs) // 2] < 3e-2
+    else:
+        assert abs(float(loss) - float(ref_loss)) < 2e-2
+
+
+def test_eval_mode_folds_batchnorm_into_the_gemms(sd, monkeypatch):
+    """configs[3] eval path: under eval() + no_grad every Conv/ConvTranspose + BatchNorm(+ReLU) pair on the tcgen05 path runs as
+    one launch (dc_conv_gemm_tc_bn_eval).  Same logits as the unfolded path and as the oracle's eval forward; fewer launches;
+    gradients still work afterwards in train mode (the deferred-convolution logic only applies when nothing is recorded)."""
+    monkeypatch.setenv("DEEPCAM_B200_GRAPHS", "0")
+    x, label = O.synthetic_batch(2, 128, 192, seed=95)
+    net = _make(sd, "bf16")
+    net.train()
+    with torch.no_grad():
+        for i in range(6):                                   # settle the running statistics
+            net(O.synthetic_batch(2, 128, 192, seed=96 + i)[0].to(DEV))
+    state = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    net.eval()
+    res = {}
+    for fold in ("1", "0"):
+        monkeypatch.setenv("DEEPCAM_B200_FOLD_BN_EVAL", fold)
+        with torch.no_grad():
+            out = net(x.to(DEV))
+        res[fold] = (out.clone(), net._dc_last_launches)
+    ref = O.forward({k: (v.double() if v.is_floating_point() else v.clone()) for k, v in state.items()}, x.double(), train=False)
+    e_fold, e_plain = _rel(res["1"][0], ref), _rel(res["0"][0], ref)
+    _record("eval_bn_fold", dict(fold_vs_oracle=e_fold, plain_vs_oracle=e_plain, fold_vs_plain=_rel(res["1"][0], res["0"][0]),
+                                 launches_fold=res["1"][1], launches_plain=res["0"][1]))
+    assert res["0"][1] - res["1"][1] >= 60, (res["0"][1], res["1"][1])
+    assert e_fold < max(3e-2, 1.5 * e_plain)                 # eval mode is a fixed affine map per layer: bf16 drift stays small
+    assert (res["1"][0].argmax(1) == res["0"][0].argmax(1)).float().mean() > 0.98
+    net.train()
+    w = O.class_weights()
+    out = net(x.to(DEV))
+    losses.fp_loss(out, label.to(DEV), weight=w, fpw_1=w[1], fpw_2=w[2]).backward()
+    assert all(bool(torch.isfinite(p.grad).all()) for p in net.parameters())

@@ -83,13 +83,24 @@ def _worker(rank, world, port, precision, q):
         for x, label in batches:
             run(solo, x, label)
             solo_grads.append([p.grad.detach().clone() for p in solo.parameters()])
+        # run-to-run floor of the single-process gradients themselves (a second, independent instance on the same batches):
+        # fp32/fp64 atomics reorder sums, and the BatchNorm over two values of the image-pooling branch amplifies that
+        solo2 = make(0)
+        floor, floor_where = 0.0, None
+        for it, (x, label) in enumerate(batches):
+            run(solo2, x, label)
+            for (k, p), g in zip(solo2.named_parameters(), solo_grads[it]):
+                e = _rel(p.grad, g)
+                if e > floor:
+                    floor, floor_where = e, (it, k)
+        del solo2
         # ---- wrapped module ----
         net = make(rank)                                  # rank 1 starts from shifted weights
         ddp = DistributedDataParallel(net)
         for (k, a), (_, b) in zip(net.named_parameters(), solo.named_parameters()):
             assert torch.equal(a, b), "C1 broadcast failed for " + k
         worst, where = 0.0, None
-        per_call = []
+        per_call, errs_last = [], {}
         for it, (x, label) in enumerate(batches):
             run(ddp, x, label)
             call_worst = 0.0
@@ -98,10 +109,13 @@ def _worker(rank, world, port, precision, q):
                 dist.all_gather(parts, g)
                 want = sum(parts) / world
                 e = _rel(p.grad, want)
+                errs_last[k] = e
                 call_worst = max(call_worst, e)
                 if e > worst:
                     worst, where = e, (it, k)
             per_call.append(call_worst)
+        srt = sorted(errs_last.values())
+        top = sorted(errs_last.items(), key=lambda kv: -kv[1])[:6]
         assert len(ddp._sync.buckets) >= 8               # 225.8 MB of gradients in 25 MiB buckets
         plans = [v[1] for v in net._dc_plans.values() if v[1] is not None]
         assert plans and len(plans[0].bwd_segments) >= 2, "the captured backward must be split into per-bucket segments"
@@ -122,7 +136,8 @@ def _worker(rank, world, port, precision, q):
         assert int(cnt[0]) == int(cnt[1]) == len(batches)
         dist.barrier()
         dist.destroy_process_group()
-        q.put((rank, "ok", dict(worst=worst, where=where, per_call=per_call)))
+        q.put((rank, "ok", dict(worst=worst, where=where, per_call=per_call, median=srt[len(srt) // 2], top=top,
+                                solo_run_to_run_floor=floor, floor_where=floor_where)))
     except Exception:
         q.put((rank, traceback.format_exc(), None))
 
@@ -153,4 +168,5 @@ def test_ddp_world2_nccl_gradient_average(precision):
     # graph-vs-eager in test_model_gpu.py; the typical tensor sits at ~1e-6.  bf16: 0.25 as there.
     bound = 1e-3 if precision == "fp32" else 0.25
     for r, _, s in results:
-        assert s["worst"] < bound, s
+        assert s["worst"] < max(bound, 3.0 * s["solo_run_to_run_floor"]), s
+        assert s["median"] < (1e-5 if precision == "fp32" else 2e-2), s

@@ -63,6 +63,15 @@ def main():
         dws = DwSpec("dw", wdw, 1, 1)
         add("dw_fwd " + tag, lambda y=y, out=out, dws=dws: be.dw_fwd(y, dws, out), 2 * nb, 18.0 * y.numel())
         add("dw_bwd_data " + tag, lambda dout=dout, dy=dy, dws=dws: be.dw_bwd_data(dout, dws, dy, False), 2 * nb, 18.0 * y.numel())
+        from deepcam_b200 import ops as _ops
+        ws_ready = torch.zeros(_ops.bn_ws_elems(c), dtype=torch.float64, device=dev)
+        y64 = y.double().reshape(-1, c)
+        ws_ready[:c] = y64.sum(0)
+        ws_ready[c:2 * c] = (y64 * y64).sum(0)
+        del y64
+        add("dw_fwd_bn " + tag, lambda y=y, spec=spec, dws=dws, res=res, out=out, ws=ws_ready: be.bn_dw_fwd(y, spec, True, dws, res, out, ws),
+            3 * nb, 21.0 * y.numel())
+        add("bn_apply(sums ready) " + tag, lambda y=y, spec=spec, out=out, ws=ws_ready: be.bn_fwd(y, spec, True, None, out, True, ready_sums=ws), 2 * nb)
         rws_holder = {}
 
         def f_bnred(dout=dout, dy=dy, dws=dws, y=y, sums0=sums0, h=rws_holder):
