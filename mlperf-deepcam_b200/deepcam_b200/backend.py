@@ -128,7 +128,9 @@ class CudaBackend:
         self.bn_bwd_split_max_bytes = int(os.environ.get("DEEPCAM_B200_BN_BWD_SPLIT_MAX_BYTES", str(1 << 40)))
         self.fuse_bn_bwd_res = os.environ.get("DEEPCAM_B200_FUSE_BN_BWD_RES", "1") not in ("0", "false", "")
         # BatchNorm(+ReLU) applied while the following depthwise kernel loads its tile (dc_dw_fwd_bn): no bn_apply launch
-        self.fuse_bn_dw = os.environ.get("DEEPCAM_B200_FUSE_BN_DW", "1") not in ("0", "false", "")
+        # Opt-in: measured on B200 (round 2, tools/kbench.py, 2x48x72x728): 16.1 us fused vs 8.6 us dw_fwd + 5.3 us bn_apply - the
+        # in-place activation pass over the staged tile and its second block barrier cost more than the launch they save
+        self.fuse_bn_dw = os.environ.get("DEEPCAM_B200_FUSE_BN_DW", "0") not in ("0", "false", "")
         # eval mode without gradient recording: BatchNorm (+ReLU) folded into the producing GEMM's epilogue
         self.fold_bn_eval = os.environ.get("DEEPCAM_B200_FOLD_BN_EVAL", "1") not in ("0", "false", "")
         self.side_stream = None       # set by a graph plan: weight-gradient kernels run on a parallel graph branch

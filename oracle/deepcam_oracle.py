@@ -291,9 +291,8 @@ def decoder(P, y, ll, train=True, tape=None):
     return deconv("last_deconv", y)
 
 
-def forward(P, x, train=True, os=16, tape=None):
-    """DeepLabv3_plus.forward, DX:441-465 (Xception.forward DX:195-242, DeconvUpsampler.forward DX:376-383).
-    x: [N, n_input, H, W] with H, W multiples of 16.  Returns logits [N, n_classes, H, W]."""
+def xception(P, x, train=True, os=16, tape=None):
+    """Xception.forward, DX:195-242: returns (features [N,2048,H/os,W/os], low_level_feat [N,128,H/4,W/4])."""
     tape = tape or Tape(False)
     X = "xception_features."
     h = F.conv2d(x, P[X + "conv1.weight"], None, 2, 1)
@@ -313,7 +312,14 @@ def forward(P, x, train=True, os=16, tape=None):
     for i, name in enumerate(("conv3", "conv4", "conv5")):
         h = _sep(P, X + name, h, 1, exit_rate, tape)
         h = _bn(P, X + "bn%d" % (i + 3), h, train, tape, relu=True)
-    feats = h
+    return h, low
+
+
+def forward(P, x, train=True, os=16, tape=None):
+    """DeepLabv3_plus.forward, DX:441-465 (Xception.forward DX:195-242, DeconvUpsampler.forward DX:376-383).
+    x: [N, n_input, H, W] with H, W multiples of 16.  Returns logits [N, n_classes, H, W]."""
+    tape = tape or Tape(False)
+    feats, low = xception(P, x, train, os, tape)
     branches = []
     for i, rate in enumerate(aspp_rates(os)):
         branches.append(aspp_branch(P, "aspp%d" % (i + 1), feats, rate, train, tape))
