@@ -664,7 +664,7 @@ def main():
                     help="train = the headline metric; eval = BASELINE.json configs[3] (validation loop TR:423-512)")
     ap.add_argument("--eval-samples", type=int, default=64, help="--mode eval: validation samples per rank")
     ap.add_argument("--eval-batch", type=int, default=1, help="--mode eval: batch size (the reference validates at 1, TR:302-306)")
-    ap.add_argument("--bucket-mb", type=float, default=25.0, help="N > 1: gradient bucket size of the data-parallel wrapper")
+    ap.add_argument("--bucket-mb", type=float, default=64.0, help="N > 1: gradient bucket size of the data-parallel wrapper")
     ap.add_argument("--no-broadcast-buffers", action="store_true", help="N > 1: skip the per-forward BatchNorm buffer broadcast (C3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
