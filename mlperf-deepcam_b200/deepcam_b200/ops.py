@@ -55,8 +55,12 @@ def _p(t):
 class Profiler:
     """Collects (kernel class, start event, end event, algorithmic FLOPs, algorithmic bytes) per launch."""
 
-    def __init__(self):
+    def __init__(self, keep_launchers=False):
         self.items = []
+        # one re-launchable closure per (kernel class, shape tag), with the tensors of its first occurrence kept alive:
+        # graph_times() replays each of them back to back inside a CUDA graph, which is how the launch runs in the timed
+        # region (the per-launch event pairs above add ~5-7 us of event/launch overhead to every short kernel)
+        self.launchers = {} if keep_launchers else None
 
     def begin(self):
         e = torch.cuda.Event(enable_timing=True)
@@ -77,6 +81,32 @@ class Profiler:
             d["ms"] += s.elapsed_time(e)
             d["flops"] += fl
             d["bytes"] += nb
+        return out
+
+    def graph_times(self, reps=10):
+        """{class + ' ' + tag: microseconds per launch} with every recorded launch replayed `reps` times back to back inside
+        one CUDA graph (warm-up replay first); kernels that cannot be captured are skipped."""
+        out = {}
+        if not self.launchers:
+            return out
+        torch.cuda.synchronize()
+        for key, (fn, what) in self.launchers.items():
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for _ in range(reps):
+                        fn()
+                g.replay()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                out[key[0] + " " + key[1]] = 1000.0 * e0.elapsed_time(e1) / reps
+                del g
+            except Exception:
+                torch.cuda.synchronize()
         return out
 
     def by_tag(self, kinds):
@@ -124,6 +154,8 @@ def _timed(name, flops, nbytes, rc_fn, what, tag=""):
     st = _prof.begin()
     check(rc_fn(), what)
     _prof.end(name, st, flops, nbytes, tag)
+    if _prof.launchers is not None and (name, tag) not in _prof.launchers:
+        _prof.launchers[(name, tag)] = (rc_fn, what)
 
 
 # ---- descriptors ---------------------------------------------------------------------------------

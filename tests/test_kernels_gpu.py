@@ -777,6 +777,7 @@ def test_depthwise_forward_with_batchnorm_on_load(dtype, C, H, W, relu):
     from deepcam_b200.backend import BnSpec, DwSpec
     torch.manual_seed(33)
     be = backend(dtype)
+    be.fuse_bn_dw = True                   # opt-in kernel (DEEPCAM_B200_FUSE_BN_DW=1): slower than the pair it replaces, kept pinned
     N = 2
     y = to_nhwc(torch.randn(N, C, H, W) * 1.7 + 0.4, dtype)
     wdw = torch.nn.Parameter(torch.randn(C, 1, 3, 3, device=dev()) * 0.3)
