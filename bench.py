@@ -506,8 +506,17 @@ def run_ours(args):
                 roofline["in_graph"] = dict(achieved=d["bytes"] / gsec / 1e9, frac=d["bytes"] / gsec / 1e9 / peaks["hbm"],
                                             class_ms_per_step=d["ms_graph"] / psteps)
         if "in_graph" in roofline:
-            roofline["in_graph"]["how"] = ("same launches, each distinct (kernel, shape) replayed 10x back to back in a CUDA graph and "
-                                           "timed with one event pair; `achieved`/`frac` above are the per-launch event-pair numbers")
+            # headline = the in-graph clock (how the launches execute in the timed region); the per-launch event pairs stay
+            # beside it as `eager_events` (they swing with the host's launch rate: 0.30-0.37 between two runs of one build)
+            ig = roofline.pop("in_graph")
+            roofline["eager_events"] = dict(achieved=roofline["achieved"], frac=roofline["frac"], class_ms_per_step=d["ms"] / psteps,
+                                            how="CUDA event pair around every launch of the class in %d instrumented eager steps "
+                                                "(includes ~5-7 us of event + launch overhead per launch)" % psteps)
+            roofline["achieved"], roofline["frac"] = ig["achieved"], ig["frac"]
+            roofline["class_ms_per_step_in_graph"] = ig["class_ms_per_step"]
+            roofline["timing"] = ("every distinct (kernel, layer shape) launch of the class replayed 10x back to back inside a CUDA "
+                                  "graph, one CUDA event pair per replay, on the launching stream, right after the timed region; "
+                                  "class time = sum over shapes of launches x that duration")
         ssec = shape_d["ms"] / 1000.0
         roofline["traffic"] = traffic
         roofline["dominant_shape"] = dict(

@@ -67,9 +67,14 @@ typedef struct dc_conv_desc {
    * rows of a stride-2 nn.ConvTranspose2d (DX:374): channels = (row parity, column parity, co), see
    * DC_PACK_NTK_CONVT2.  out_csplit % 4 == 0. */
   int32_t out_csplit;
-  int32_t reserved;
+  int32_t flags;             /* DC_CONV_* bits below (0 = none; the field was `reserved`) */
   int64_t out_split_off;     /* in elements of the output view */
 } dc_conv_desc;
+/* dc_conv_desc.flags.  DC_CONV_WEIGHTS_STABLE: the packed weights were NOT written by the kernel that immediately precedes this
+ * call on the stream (they were re-packed at the start of the captured graph, several launches earlier).  The tcgen05 kernels
+ * then fetch their first weight tiles BEFORE griddepcontrol.wait, i.e. while the preceding kernel still drains; only the
+ * activation operand waits for it.  Never set it right after a pack launch. */
+#define DC_CONV_WEIGHTS_STABLE 1
 
 /* ---- library / diagnostics ------------------------------------------------ */
 int         dc_abi_version(void);

@@ -100,17 +100,30 @@ static inline DwMap dw_map(int C, int V, int rows, int cols, int n_img, int targ
   return m;
 }
 
+// dsub > 1: the view addresses the dsub x dsub PARITY SUB-GRIDS of the tensor as separate images (virtual image index
+// vn = (n * dsub + py) * dsub + px, h / w = sub-grid size, sh / sw = dsub x the tensor's strides).  A stride-1 depthwise
+// convolution with dilation d never mixes the parity classes modulo d, and the zero padding of d pixels is a padding of one
+// sub-grid pixel, so a dilation-d layer IS d*d independent dilation-1 layers: every s1d1 kernel below serves dilation 2
+// (exit flow, DX:176-186) and 4 (os=8) through such a view, in one launch.
 template <typename T>
 struct DwView {
   T* p;
   int h, w;
   long long sn, sh, sw;
+  int dsub;
+  __device__ __forceinline__ long long img(int vn) const {
+    if (dsub == 1) return (long long)vn * sn;
+    const int px = vn % dsub, t = vn / dsub;
+    const int py = t % dsub, n = t / dsub;
+    return (long long)n * sn + (long long)py * (sh / dsub) + (long long)px * (sw / dsub);
+  }
 };
 template <typename T>
-static inline DwView<T> dw_view(const dc_view& v) {
+static inline DwView<T> dw_view(const dc_view& v, int dsub = 1) {
   DwView<T> r;
   r.p = reinterpret_cast<T*>(v.ptr);
-  r.h = v.h; r.w = v.w; r.sn = v.sn; r.sh = v.sh; r.sw = v.sw;
+  r.h = v.h / dsub; r.w = v.w / dsub; r.sn = v.sn; r.sh = v.sh * dsub; r.sw = v.sw * dsub;
+  r.dsub = dsub;
   return r;
 }
 
@@ -157,8 +170,8 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_kernel(DwView<const T> in,
 #pragma unroll
   for (int k = 0; k < 9; ++k) dwpair<T>::unpack(ld16(w9c + (size_t)(flip ? 8 - k : k) * C + c0), wv[k]);
   const int H = in.h, W = in.w;
-  const T* base = in.p + l.n * in.sn + (long long)l.x * in.sw + c0;
-  T* obase = out.p + l.n * out.sn + (long long)l.x * out.sw + c0;
+  const T* base = in.p + in.img(l.n) + (long long)l.x * in.sw + c0;
+  T* obase = out.p + out.img(l.n) + (long long)l.x * out.sw + c0;
   const bool xl = l.x >= 1, xr = l.x + 1 < W;
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
   auto ldrow = [&](int r, uint4 (&v)[3]) {
@@ -260,7 +273,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_kernel(DwView<const T
   {
     const int nvec = nrows * TW * m.cvp;
     const int cshift = 31 - __clz(m.cvp);
-    const T* nbase = in.p + l.n * in.sn;
+    const T* nbase = in.p + in.img(l.n);
     // (ty, tx) of this thread's vectors advance by a fixed pixel step < TW per iteration: tracked incrementally, the loop
     // carries no integer division (it used to be a quarter of the kernel's instructions)
     const int cl = threadIdx.x & (m.cvp - 1), cvi = cv0 + cl;
@@ -284,7 +297,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_kernel(DwView<const T
   cp_async_commit_wait_all();
   __syncthreads();
   if (!l.ok) return;
-  T* obase = out.p + l.n * out.sn + (long long)l.x * out.sw + l.cvi * V;
+  T* obase = out.p + out.img(l.n) + (long long)l.x * out.sw + l.cvi * V;
   const uint4* tp = dw_tile + ((warp * m.ppw + psub) * m.cvp + cvl);      // tile column of x-1, row 0
   const int rstride = TW * m.cvp;
   auto step = [&](int ty, float2 (&A)[VP], float2 (&B)[VP], float2 (&Cn)[VP]) {
@@ -361,7 +374,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_bn_kernel(dc_bn_param
   const int cshift = 31 - __clz(m.cvp);
   pdl_sync();
   {
-    const T* nbase = in.p + l.n * in.sn;
+    const T* nbase = in.p + in.img(l.n);
     // (ty, tx) of this thread's vectors advance by a fixed pixel step < TW per iteration: tracked incrementally, the loop
     // carries no integer division (it used to be a quarter of the kernel's instructions)
     const int cl = threadIdx.x & (m.cvp - 1), cvi = cv0 + cl;
@@ -418,7 +431,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_bn_kernel(dc_bn_param
   {
     // a = [relu](y * scale + shift) in place; pixels outside the image stay zero (they pad a); interior pixels are stored
     const bool relu = (p.flags & DC_BN_RELU) != 0;
-    T* abase = act.p ? act.p + l.n * act.sn : nullptr;
+    T* abase = act.p ? act.p + act.img(l.n) : nullptr;
     const int cl = threadIdx.x & (m.cvp - 1), cvi = cv0 + cl;
     const int pstep = kDwThreads >> cshift;
     int ty = (threadIdx.x >> cshift) / TW, tx = (threadIdx.x >> cshift) - ty * TW;
@@ -447,7 +460,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_bn_kernel(dc_bn_param
   }
   __syncthreads();
   if (!l.ok) return;
-  T* obase = out.p + l.n * out.sn + (long long)l.x * out.sw + l.cvi * V;
+  T* obase = out.p + out.img(l.n) + (long long)l.x * out.sw + l.cvi * V;
   const uint4* tp = dw_tile + ((warp * m.ppw + psub) * m.cvp + cvl);      // tile column of x-1, row 0
   const int rstride = TW * m.cvp;
   auto step = [&](int ty, float2 (&A)[VP], float2 (&B)[VP], float2 (&Cn)[VP]) {
@@ -519,7 +532,7 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_s1d1_tile_bnred_kernel(DwVie
   const int cshift = 31 - __clz(m.cvp);
   pdl_sync();
   {
-    const T* nbase = in.p + l.n * in.sn;
+    const T* nbase = in.p + in.img(l.n);
     for (int i = threadIdx.x; i < nrows * TW * m.cvp; i += kDwThreads) {
       const int cl = i & (m.cvp - 1);
       const int pix = i >> cshift;
@@ -539,13 +552,13 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_s1d1_tile_bnred_kernel(DwVie
       const int gy = l.y0 + ty, gx = blockIdx.x * m.ppb + tx, cvi = cv0 + cl;
       const bool ok = gx < out.w && cvi < m.cv;
       const long long off = (long long)gy * yv.sh + (long long)gx * yv.sw + cvi * V;
-      cp_async16_zfill(ty_a + (uint32_t)i * 16u, ok ? yv.p + l.n * yv.sn + off : yv.p, ok);
+      cp_async16_zfill(ty_a + (uint32_t)i * 16u, ok ? yv.p + yv.img(l.n) + off : yv.p, ok);
       if (HAS_X) {
         cp_async16_zfill(tx_a + (uint32_t)i * 16u,
-                         ok ? xv.p + l.n * xv.sn + (long long)gy * xv.sh + (long long)gx * xv.sw + cvi * V : xv.p, ok);
+                         ok ? xv.p + xv.img(l.n) + (long long)gy * xv.sh + (long long)gx * xv.sw + cvi * V : xv.p, ok);
         if (accumulate)
           cp_async16_zfill(to_a + (uint32_t)i * 16u,
-                           ok ? out.p + l.n * out.sn + (long long)gy * out.sh + (long long)gx * out.sw + cvi * V : out.p, ok);
+                           ok ? out.p + out.img(l.n) + (long long)gy * out.sh + (long long)gx * out.sw + cvi * V : out.p, ok);
       }
     }
   }
@@ -569,7 +582,7 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_s1d1_tile_bnred_kernel(DwVie
 #pragma unroll
   for (int j = 0; j < V; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
   if (l.ok) {
-    T* obase = out.p + l.n * out.sn + (long long)l.x * out.sw + l.cvi * V;
+    T* obase = out.p + out.img(l.n) + (long long)l.x * out.sw + l.cvi * V;
     const int pcol = warp * m.ppw + psub;                                   // pixel column inside the tile (interior index)
     const uint4* tp = dw_tile + (pcol * m.cvp + cvl);                       // halo tile column of x-1, row 0
     const int rstride = TW * m.cvp;
@@ -662,8 +675,8 @@ __global__ void __launch_bounds__(kDwThreads) dw_direct_kernel(DwView<const T> i
   const int c0 = l.cvi * V;
   float wv[9][V];
   load_weights<T, V>(w9c, C, c0, flip != 0, wv);
-  const T* base = in.p + l.n * in.sn + c0;
-  T* obase = out.p + l.n * out.sn + (long long)l.x * out.sw + c0;
+  const T* base = in.p + in.img(l.n) + c0;
+  T* obase = out.p + out.img(l.n) + (long long)l.x * out.sw + c0;
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
   int ix[3];
   bool vx[3];
@@ -710,8 +723,8 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_data_strided_kernel(DwView<
   const int c0 = l.cvi * V;
   float wv[9][V];
   load_weights<T, V>(w9c, C, c0, false, wv);
-  const T* base = dout.p + l.n * dout.sn + c0;
-  T* obase = din.p + l.n * din.sn + (long long)l.x * din.sw + c0;
+  const T* base = dout.p + dout.img(l.n) + c0;
+  T* obase = din.p + din.img(l.n) + (long long)l.x * din.sw + c0;
   int ox[3];
   bool vx[3];
 #pragma unroll
@@ -755,6 +768,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_data_strided_kernel(DwView<
 // (one filter row each) through shared memory, then one fp32 atomicAdd per (tap, channel) per block.
 // Gout[(kh*3+kw) * tap_stride + c * c_stride]: tap-major scratch (tap_stride = C, c_stride = 1) or the parameter's own
 // [C][1][3][3] layout (tap_stride = 1, c_stride = 9), which needs no unpack launch afterwards.
+__device__ int g_dww_noatomic = 0;      // experiment knob (DEEPCAM_B200_DWW_NOATOMIC=1, results are garbage): time without the atomics
 template <int V>
 __device__ __forceinline__ void dw_reduce_G(float (&G)[9][V], float* __restrict__ Gout, int C, const DwMap& m, int cvi_base,
                                             int tap_stride, int c_stride) {
@@ -784,7 +798,7 @@ __device__ __forceinline__ void dw_reduce_G(float (&G)[9][V], float* __restrict_
 #pragma unroll
       for (int w = 0; w < 8; ++w) s += red[(w * 32 + ln) * PER + r];
       const int kw = r / V, j = r - kw * V;
-      if (ln < cv_count) atomicAdd(Gout + (size_t)(kh * 3 + kw) * tap_stride + (size_t)((cvi_base + ln) * V + j) * c_stride, s);
+      if (ln < cv_count && !g_dww_noatomic) atomicAdd(Gout + (size_t)(kh * 3 + kw) * tap_stride + (size_t)((cvi_base + ln) * V + j) * c_stride, s);
     }
   }
 }
@@ -804,8 +818,8 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_s1d1_kernel(DwView<c
   if (l.ok) {
     const int c0 = l.cvi * V;
     const int H = in.h, W = in.w;
-    const T* base = in.p + l.n * in.sn + (long long)l.x * in.sw + c0;
-    const T* gbase = dout.p + l.n * dout.sn + (long long)l.x * dout.sw + c0;
+    const T* base = in.p + in.img(l.n) + (long long)l.x * in.sw + c0;
+    const T* gbase = dout.p + dout.img(l.n) + (long long)l.x * dout.sw + c0;
     const bool xl = l.x >= 1, xr = l.x + 1 < W;
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     auto ldrow = [&](int r, uint4 (&v)[4]) {          // v[0..2]: input row r at x-1, x, x+1; v[3]: dout row r+1
@@ -869,6 +883,175 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_s1d1_kernel(DwView<c
   dw_reduce_G<V>(G, Gout, C, m, blockIdx.y * m.cvp, tap_stride, c_stride);
 }
 
+// ---- stride-1 weight gradient, staged + cluster-reduced ------------------------------------------------------------------
+// dw_bwd_weight_s1d1_kernel above walks its strip with one row of global loads in flight per thread (a chain of rs + 2
+// dependent L2 round trips: 11.5 of its 15.3 us on the 10 MB middle-flow tensors, tools/kbench.py) and every block then issues
+// 9 * channels atomics (the other 3.8 us).  Here a block pulls its input tile (halo included) and its dout tile into shared
+// memory with cp.async copies that are all in flight at once, walks them input-stationary from there, reduces its eight pixel
+// columns through shared memory, and the blocks of one thread-block CLUSTER (the strips / images / parity sub-grids that share
+// an x block and a channel group: consecutive blockIdx.z) add their partial sums through distributed shared memory
+// (mapa + ld.shared::cluster), so that only one block's worth of atomics per cluster reaches the L2.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_saddr, uint32_t rank) {
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_saddr), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwView<const T> in, DwView<const T> dout, float* __restrict__ Gout,
+                                                                          int C, DwMap m, int tap_stride, int c_stride) {
+  constexpr int VP = V / 2;
+  extern __shared__ uint4 dww_smem[];                 // in tile [rs + 2][ppb + 2][cvp] | dout tile [rs][ppb][cvp]   (then reused)
+  const DwLane l = dw_lane(m, dout.h, dout.w);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
+  const int TW = m.ppb + 2;
+  const int orows = l.y1 - l.y0, nrows = orows + 2;   // dout rows y0 .. y1-1, input rows y0-1 .. y1
+  const int x0 = blockIdx.x * m.ppb, x_base = x0 - 1, y_base = l.y0 - 1;
+  const int cv0 = blockIdx.y * m.cvp;
+  const int H = in.h, W = in.w;
+  uint4* in_t = dww_smem;
+  uint4* g_t = dww_smem + (m.rs + 2) * TW * m.cvp;
+  const int cshift = 31 - __clz(m.cvp);
+  const int cl = threadIdx.x & (m.cvp - 1), cvi_f = cv0 + cl;
+  const int pstep = kDwThreads >> cshift;
+  pdl_sync();
+  {
+    const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(in_t);
+    const T* nbase = in.p + in.img(l.n);
+    const int nvec = nrows * TW * m.cvp;
+    int ty = (threadIdx.x >> cshift) / TW, tx = (threadIdx.x >> cshift) - ty * TW;
+    for (int i = threadIdx.x; i < nvec; i += kDwThreads) {
+      const int gy = y_base + ty, gx = x_base + tx;
+      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W && cvi_f < m.cv;
+      cp_async16_zfill(in_s + (uint32_t)i * 16u, ok ? nbase + (long long)gy * in.sh + (long long)gx * in.sw + cvi_f * V : in.p, ok);
+      tx += pstep;
+      if (tx >= TW) { tx -= TW; ++ty; }
+    }
+    const uint32_t g_s = (uint32_t)__cvta_generic_to_shared(g_t);
+    const T* gbase = dout.p + dout.img(l.n);
+    const int gvec = orows * m.ppb * m.cvp;
+    ty = (threadIdx.x >> cshift) / m.ppb; tx = (threadIdx.x >> cshift) - ty * m.ppb;
+    for (int i = threadIdx.x; i < gvec; i += kDwThreads) {
+      const int gy = l.y0 + ty, gx = x0 + tx;
+      const bool ok = gx < dout.w && cvi_f < m.cv;
+      cp_async16_zfill(g_s + (uint32_t)i * 16u, ok ? gbase + (long long)gy * dout.sh + (long long)gx * dout.sw + cvi_f * V : dout.p, ok);
+      tx += pstep;
+      while (tx >= m.ppb) { tx -= m.ppb; ++ty; }
+    }
+  }
+  float2 G2[9][VP];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int j = 0; j < VP; ++j) G2[k][j] = make_float2(0.f, 0.f);
+  cp_async_commit_wait_all();
+  __syncthreads();
+  {
+    // thread = (channel vector cvl, pixel column col of the block); input-stationary walk over the staged rows:
+    // input row r meets dout rows r+1 (filter row 0), r (row 1), r-1 (row 2)
+    const int col = warp * m.ppw + psub;
+    const uint4* ip = in_t + (col * m.cvp + cvl);                       // tile column of x-1, row 0
+    const uint4* gp = g_t + (col * m.cvp + cvl);
+    const int irs = TW * m.cvp, grs = m.ppb * m.cvp;
+    auto step = [&](int ty, const float2 (&gM)[VP], const float2 (&gC)[VP], float2 (&gP)[VP]) {
+      // ty = input tile row (input row y0-1+ty); gP <- dout row y0+ty (tile row ty), zero past the strip
+      float2 f[3][VP];
+      const uint4* rp = ip + ty * irs;
+      dwpair<T>::unpack(rp[0], f[0]);
+      dwpair<T>::unpack(rp[m.cvp], f[1]);
+      dwpair<T>::unpack(rp[2 * m.cvp], f[2]);
+      if (ty < orows) dwpair<T>::unpack(gp[ty * grs], gP);
+      else {
+#pragma unroll
+        for (int j = 0; j < VP; ++j) gP[j] = make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int j = 0; j < VP; ++j) {
+          G2[kw][j] = fma2(f[kw][j], gP[j], G2[kw][j]);
+          G2[3 + kw][j] = fma2(f[kw][j], gC[j], G2[3 + kw][j]);
+          G2[6 + kw][j] = fma2(f[kw][j], gM[j], G2[6 + kw][j]);
+        }
+    };
+    float2 g0[VP], g1[VP], g2[VP];
+#pragma unroll
+    for (int j = 0; j < VP; ++j) { g0[j] = make_float2(0.f, 0.f); g1[j] = g0[j]; g2[j] = g0[j]; }
+    int ty = 0;
+    while (true) {
+      step(ty, g0, g1, g2);
+      if (++ty >= nrows) break;
+      step(ty, g1, g2, g0);
+      if (++ty >= nrows) break;
+      step(ty, g2, g0, g1);
+      if (++ty >= nrows) break;
+    }
+  }
+  __syncthreads();                                    // tiles are dead: their memory becomes the reduction scratch
+  // ---- block reduction over the 8 pixel columns (warps) [and the pixel lanes of a warp when a pixel has < 32 vectors] ----
+  float* red = reinterpret_cast<float*>(dww_smem);     // [8 warps][32 lanes][3 * V]
+  float* part = red + 8 * 32 * 3 * V;                  // [9][cvp * V] block partial sums
+  float G[9][V];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int j = 0; j < VP; ++j) { G[k][2 * j] = G2[k][j].x; G[k][2 * j + 1] = G2[k][j].y; }
+  for (int o = m.cvp; o < 32; o <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int j = 0; j < V; ++j) G[k][j] += __shfl_xor_sync(0xffffffffu, G[k][j], o);
+  }
+  constexpr int PER = 3 * V;
+  const int nch = m.cvp * V;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    if (kh) __syncthreads();
+    if (lane < m.cvp) {
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int j = 0; j < V; ++j) red[(warp * 32 + lane) * PER + kw * V + j] = G[kh * 3 + kw][j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < m.cvp * PER; c += kDwThreads) {
+      const int ln = c / PER, r = c - ln * PER;
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += red[(w * 32 + ln) * PER + r];
+      const int kw = r / V, j = r - kw * V;
+      part[(kh * 3 + kw) * nch + ln * V + j] = sum;
+    }
+  }
+  // ---- cluster reduction through distributed shared memory, then one block's worth of atomics per cluster ----
+  cluster_sync_all();                                  // every block's `part` is complete and visible cluster-wide
+  {
+    const uint32_t rank = cluster_ctarank(), nrank = cluster_nctarank();
+    const int total = 9 * nch;
+    const int chunk = (total + (int)nrank - 1) / (int)nrank;
+    const int lo = (int)rank * chunk, hi = min(total, lo + chunk);
+    const uint32_t part_s = (uint32_t)__cvta_generic_to_shared(part);
+    const int cv_count = min(m.cvp, m.cv - cv0);
+    for (int idx = lo + threadIdx.x; idx < hi; idx += kDwThreads) {
+      float sum = 0.f;
+      for (uint32_t r = 0; r < nrank; ++r) sum += ld_dsmem_f32(part_s + (uint32_t)idx * 4u, r);
+      const int k = idx / nch, c = idx - k * nch;
+      if (c < cv_count * V && !g_dww_noatomic)
+        atomicAdd(Gout + (size_t)k * tap_stride + (size_t)(cv0 * V + c) * c_stride, sum);
+    }
+  }
+  cluster_sync_all();                                  // no block may exit (and free its shared memory) while a peer still reads it
+}
+
 template <typename T, int V>
 __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_direct_kernel(DwView<const T> in, DwView<const T> dout, float* __restrict__ Gout,
                                                                           int C, DwMap m, int s, int d, int tap_stride, int c_stride) {
@@ -881,8 +1064,8 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_direct_kernel(DwView
     for (int j = 0; j < V; ++j) G[k][j] = 0.f;
   if (l.ok) {
     const int c0 = l.cvi * V;
-    const T* base = in.p + l.n * in.sn + c0;
-    const T* gbase = dout.p + l.n * dout.sn + (long long)l.x * dout.sw + c0;
+    const T* base = in.p + in.img(l.n) + c0;
+    const T* gbase = dout.p + dout.img(l.n) + (long long)l.x * dout.sw + c0;
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     int ix[3];
     bool vx[3];
@@ -937,11 +1120,21 @@ static int dw_tile_rows(int H) {
   if (v < 0) { const char* e = getenv("DEEPCAM_B200_DW_TILE_ROWS"); v = e ? atoi(e) : 0; if (v < 0 || v > 32) v = 0; }
   return v > 0 ? v : (H >= 96 ? 16 : 12);
 }
+// dilation d of a stride-1 layer as a parity split (see DwView): usable when both extents are multiples of d
+static inline int dw_dsub(int s, int d, int h, int w) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("DEEPCAM_B200_DW_PARITY_SPLIT"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (s != 1) return 0;                                                // 0: not a stride-1 layer / not expressible: direct kernels
+  if (d == 1) return 1;
+  return (enabled && d <= 4 && h % d == 0 && w % d == 0) ? d : 0;
+}
+
 template <typename T, int V>
-static bool dw_s1d1_tile_launch(const dc_view& in, const void* w, const dc_view& out, int flip, int acc, cudaStream_t st) {
+static bool dw_s1d1_tile_launch(const dc_view& in, const void* w, const dc_view& out, int flip, int acc, cudaStream_t st, int dsub = 1) {
   if (!dw_tile_enabled()) return false;
-  DwMap m = dw_map(out.c, V, out.h, out.w, out.n, 1 << 30, dw_tile_rows(out.h));
-  dim3 grid = dw_grid(m, out.w, out.n);
+  const int oh = out.h / dsub, ow = out.w / dsub, nimg = out.n * dsub * dsub;
+  DwMap m = dw_map(out.c, V, oh, ow, nimg, 1 << 30, dw_tile_rows(oh));
+  dim3 grid = dw_grid(m, ow, nimg);
   const size_t smem = (size_t)(m.rs + 2) * (m.ppb + 2) * m.cvp * 16;
   if (smem > 200 * 1024) return false;                                         // odd row counts: register-pipelined kernel
   static bool attr_set = false;
@@ -949,7 +1142,8 @@ static bool dw_s1d1_tile_launch(const dc_view& in, const void* w, const dc_view&
     if (cudaFuncSetAttribute(dw_s1d1_tile_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return false;
     attr_set = true;
   }
-  launch_k(dw_s1d1_tile_kernel<T, V>, grid, dim3(kDwThreads), smem, st, dw_view<const T>(in), (const T*)w, dw_view<T>(out), out.c, m, flip, acc);
+  launch_k(dw_s1d1_tile_kernel<T, V>, grid, dim3(kDwThreads), smem, st, dw_view<const T>(in, dsub), (const T*)w, dw_view<T>(out, dsub), out.c, m,
+           flip, acc);
   return true;
 }
 
@@ -965,7 +1159,7 @@ static int dw_fwd_bn_t(const dc_bn_params& p, const dc_view& in, const void* w, 
     if (e != cudaSuccess) return fail((int)e, "dc_dw_fwd_bn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  DwView<T> av = act.ptr ? dw_view<T>(act) : DwView<T>{nullptr, 0, 0, 0, 0, 0};
+  DwView<T> av = act.ptr ? dw_view<T>(act) : DwView<T>{nullptr, 0, 0, 0, 0, 0, 1};
   launch_k(dw_s1d1_tile_bn_kernel<T, V>, grid, dim3(kDwThreads), smem, st, p, dw_view<const T>(in), (const T*)w, av, dw_view<T>(out), out.c, m);
   return launch_status("dc_dw_fwd_bn");
 }
@@ -1004,7 +1198,8 @@ static int dw_bwd_data_bnred_t(const dc_view& dout, const void* w, const dc_view
 template <typename T>
 static int dw_fwd_t(const dc_view& in, const void* w, int s, int d, const dc_view& out, cudaStream_t st) {
   constexpr int V = dwvec<T>::V;
-  if (s == 1 && d == 1 && dw_s1d1_tile_launch<T, V>(in, w, out, 0, 0, st)) return launch_status("dc_dw_fwd");
+  const int dsub = dw_dsub(s, d, out.h, out.w);
+  if (dsub >= 1 && dw_s1d1_tile_launch<T, V>(in, w, out, 0, 0, st, dsub)) return launch_status("dc_dw_fwd");
   DwMap m = dw_map(out.c, V, out.h, out.w, out.n, kNumSMs * 4, 6);
   dim3 grid = dw_grid(m, out.w, out.n);
   if (s == 1 && d == 1)
@@ -1016,7 +1211,8 @@ static int dw_fwd_t(const dc_view& in, const void* w, int s, int d, const dc_vie
 template <typename T>
 static int dw_bwd_data_t(const dc_view& dout, const void* w, int s, int d, const dc_view& din, int acc, cudaStream_t st) {
   constexpr int V = dwvec<T>::V;
-  if (s == 1 && d == 1 && dw_s1d1_tile_launch<T, V>(dout, w, din, 1, acc, st)) return launch_status("dc_dw_bwd_data");
+  const int dsub = dw_dsub(s, d, din.h, din.w);
+  if (dsub >= 1 && dw_s1d1_tile_launch<T, V>(dout, w, din, 1, acc, st, dsub)) return launch_status("dc_dw_bwd_data");
   DwMap m = dw_map(din.c, V, din.h, din.w, din.n, kNumSMs * 4, 6);
   dim3 grid = dw_grid(m, din.w, din.n);
   if (s == 1 && d == 1)          // full correlation with the flipped filter
@@ -1036,12 +1232,58 @@ static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d,
   static int tb_mult = -1, min_rows = -1;   // sweep knobs: DEEPCAM_B200_DWW_BLOCKS_PER_SM, DEEPCAM_B200_DWW_MIN_ROWS
   if (tb_mult < 0) { const char* e = getenv("DEEPCAM_B200_DWW_BLOCKS_PER_SM"); tb_mult = e ? std::max(1, atoi(e)) : 2; }
   if (min_rows < 0) { const char* e = getenv("DEEPCAM_B200_DWW_MIN_ROWS"); min_rows = e ? std::max(1, atoi(e)) : 12; }
-  DwMap m = dw_map(dout.c, V, dout.h, dout.w, dout.n, kNumSMs * tb_mult, min_rows);
-  dim3 grid = dw_grid(m, dout.w, dout.n);
+  const int dsub = dw_dsub(s, d, dout.h, dout.w);
+  const int gh = dsub >= 1 ? dout.h / dsub : dout.h, gw = dsub >= 1 ? dout.w / dsub : dout.w;
+  const int gn = dsub >= 1 ? dout.n * dsub * dsub : dout.n;
+  static int tile_on = -1;        // DEEPCAM_B200_DWW_TILE=0: the register-pipelined kernel (A/B measurements)
+  if (tile_on < 0) { const char* e = getenv("DEEPCAM_B200_DWW_TILE"); tile_on = (e && e[0] == '0') ? 0 : 1; }
+  if (dsub >= 1 && tile_on) {
+    // strips of <= 10 rows: input + dout tiles stay below 110 KB, two blocks per SM; the 48-row middle-flow tensors then make
+    // 270 blocks = one wave, in 54 clusters of 5 strips
+    DwMap m = dw_map(dout.c, V, gh, gw, gn, 1 << 30, 1);
+    m.nstrips = ceil_div(gh, 10);
+    m.rs = ceil_div(gh, m.nstrips);
+    m.nstrips = ceil_div(gh, m.rs);
+    const size_t tiles = ((size_t)(m.rs + 2) * (m.ppb + 2) + (size_t)m.rs * m.ppb) * m.cvp * 16;
+    const size_t scratch = ((size_t)8 * 32 * 3 * V + (size_t)9 * m.cvp * V) * sizeof(float);
+    const size_t smem = std::max(tiles, scratch);
+    if (smem <= 110 * 1024) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        if (cudaFuncSetAttribute(dw_bwd_weight_tile_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) == cudaSuccess) attr_set = true;
+      }
+      dim3 grid = dw_grid(m, gw, gn);
+      if (attr_set) {
+        // cluster = consecutive blockIdx.z (strips / images / parity sub-grids of one (x block, channel group)): largest divisor <= 8
+        for (int cz = 8; cz >= 1; --cz) {
+          if (grid.z % cz) continue;
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = grid; cfg.blockDim = dim3(kDwThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+          cudaLaunchAttribute attr[2];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = cz;
+          attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          attr[1].val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = attr;
+          cfg.numAttrs = pdl_enabled() ? 2 : 1;
+          cudaError_t e = cudaLaunchKernelEx(&cfg, dw_bwd_weight_tile_kernel<T, V>, dw_view<const T>(in, dsub), dw_view<const T>(dout, dsub), G, dout.c, m,
+                                             tap_stride, c_stride);
+          if (e == cudaSuccess) return launch_status("dc_dw_bwd_weight");
+          cudaGetLastError();                          // this cluster size cannot be scheduled here: try the next divisor
+        }
+      }
+    }
+  }
+  DwMap m = dw_map(dout.c, V, gh, gw, gn, kNumSMs * tb_mult, min_rows);
+  dim3 grid = dw_grid(m, gw, gn);
   const size_t smem = (size_t)8 * 32 * 3 * V * sizeof(float);
-  if (s == 1 && d == 1)
-    launch_k(dw_bwd_weight_s1d1_kernel<T, V>, grid, dim3(kDwThreads), (size_t)smem, st, dw_view<const T>(in), dw_view<const T>(dout), G, dout.c, m,
-                                                                    tap_stride, c_stride);
+  {
+    static int noat = -1;
+    if (noat < 0) { const char* e = getenv("DEEPCAM_B200_DWW_NOATOMIC"); noat = (e && e[0] == '1') ? 1 : 0; if (noat) cudaMemcpyToSymbol(g_dww_noatomic, &noat, sizeof(int)); }
+  }
+  if (dsub >= 1)
+    launch_k(dw_bwd_weight_s1d1_kernel<T, V>, grid, dim3(kDwThreads), (size_t)smem, st, dw_view<const T>(in, dsub), dw_view<const T>(dout, dsub), G,
+             dout.c, m, tap_stride, c_stride);
   else
     launch_k(dw_bwd_weight_direct_kernel<T, V>, grid, dim3(kDwThreads), (size_t)smem, st, dw_view<const T>(in), dw_view<const T>(dout), G, dout.c, m, s, d,
                                                                       tap_stride, c_stride);

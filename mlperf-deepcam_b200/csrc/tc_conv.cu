@@ -185,6 +185,7 @@ struct TcFpropParams {
   int stats_C;         // per-channel sum and sum of squares of the bf16-rounded outputs it stores (TMA-store path only)
   // eval-mode BatchNorm (+ReLU) folded into the epilogue (TMA-store path only; aff_gamma null = off):
   //   out = [relu]((acc + bias) * scale + shift), scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale
+  int b_early;         // DC_CONV_WEIGHTS_STABLE: the first weight tiles may be fetched before griddepcontrol.wait
   const float* aff_gamma;
   const float* aff_beta;
   const float* aff_mean;
@@ -517,19 +518,45 @@ __global__ void __launch_bounds__(kTc2Threads, 1) conv_gemm_tc2_kernel(const __g
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  pdl_sync();     // everything above overlapped the previous kernel's tail; global memory is touched only below
-  if (threadIdx.x == 0) TC_TRACE(1);
-
   const int b_block_bytes = BN * 128;
+  // Weights that the preceding kernel did not write (DC_CONV_WEIGHTS_STABLE) are fetched BEFORE griddepcontrol.wait: the
+  // resident weight tile, or the B halves of the first pipeline stages of this CTA's first tile, are in flight while the
+  // previous kernel drains; only the activation operand (and every store) waits.  early_b = stages whose B part is issued here.
+  int early_b = 0;
+  if (p.b_early && warp == 0 && lane == 0 && blockIdx.x < (unsigned)cfg.total_tiles) {
+    if (cfg.b_resident) {
+      mbar_expect_tx(bres_bar, cfg.bres_bytes);
+      const int nblk = cfg.bres_bytes / b_block_bytes;
+      for (int j = 0; j < nblk; ++j) tma_load_2d(&maps.b, bres_bar, bres_base + j * b_block_bytes, j * 64, 0);
+      early_b = 1;
+    } else {
+      const int MT0 = cfg.bm2 ? 2 : 1;
+      const int n0 = ((int)blockIdx.x / cfg.n_mtiles) * BN;
+      const int total_k0 = p.ntaps * p.kblocks;
+      early_b = min(STAGES, total_k0);
+      for (int it = 0; it < early_b; ++it) {
+        const int t = it / p.kblocks, kb = it - t * p.kblocks;
+        const int kcol = (p.wt[t] * p.kblocks + kb) * 64;
+        mbar_expect_tx(full_bar(it), cfg.stage_bytes);
+        const uint32_t sa = smem_base + it * cfg.stage_bytes;
+        tma_load_2d(&maps.b, full_bar(it), sa + MT0 * kABytes, kcol, n0);
+        if (cfg.wide) tma_load_2d(&maps.b, full_bar(it), sa + MT0 * kABytes + cfg.b_box_rows * 128, kcol, n0 + cfg.b_box_rows);
+      }
+    }
+  }
+  pdl_sync();     // everything above overlapped the previous kernel's tail; activations and outputs are touched only below
+  if (threadIdx.x == 0) TC_TRACE(1);
 
   if (warp == 0) {
     if (lane == 0) {
-      if (cfg.b_resident) {
+      if (cfg.b_resident && !early_b) {
         mbar_expect_tx(bres_bar, cfg.bres_bytes);
         const int nblk = cfg.bres_bytes / b_block_bytes;
         for (int j = 0; j < nblk; ++j) tma_load_2d(&maps.b, bres_bar, bres_base + j * b_block_bytes, j * 64, 0);
       }
+      if (cfg.b_resident) early_b = 0;                 // (the pipeline stages carry no weights in this mode)
       int s = 0; uint32_t ph = 0;
+      int issued = 0;                                  // k steps issued so far by this CTA (first tile first)
       const int MT = cfg.bm2 ? 2 : 1;
       for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x) {
         const int nt = tile / cfg.n_mtiles;
@@ -547,13 +574,16 @@ __global__ void __launch_bounds__(kTc2Threads, 1) conv_gemm_tc2_kernel(const __g
         for (int t = 0; t < p.ntaps; ++t) {
           const CUtensorMap* am = &maps.a[p.map_id[t]];
           const int kb0 = p.wt[t] * p.kblocks;
-          for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            mbar_expect_tx(full_bar(s), cfg.stage_bytes);
+          for (int kb = 0; kb < p.kblocks; ++kb, ++issued) {
+            const bool b_done = issued < early_b;      // this stage's weights (and its expect_tx) were issued before the wait
+            if (!b_done) {
+              mbar_wait(empty_bar(s), ph ^ 1u);
+              mbar_expect_tx(full_bar(s), cfg.stage_bytes);
+            }
             const uint32_t sa = smem_base + s * cfg.stage_bytes;
             tma_load_4d(am, full_bar(s), sa, kb * 64, x0[0] + p.qw[t], y0[0] + p.qh[t], img[0]);
             if (cfg.bm2) tma_load_4d(am, full_bar(s), sa + kABytes, kb * 64, x0[1] + p.qw[t], y0[1] + p.qh[t], img[1]);
-            if (!cfg.b_resident) {
+            if (!cfg.b_resident && !b_done) {
               tma_load_2d(&maps.b, full_bar(s), sa + MT * kABytes, (kb0 + kb) * 64, n0);
               if (cfg.wide)
                 tma_load_2d(&maps.b, full_bar(s), sa + MT * kABytes + cfg.b_box_rows * 128, (kb0 + kb) * 64, n0 + cfg.b_box_rows);
@@ -1343,6 +1373,7 @@ static int conv_gemm_tc_impl(const dc_conv_desc* d, dc_view in, const void* w, c
                   (reinterpret_cast<uintptr_t>(out.ptr) % 16) == 0) ? 1 : 0;
   p.stats = nullptr;
   p.stats_C = out.c;
+  p.b_early = (d->flags & DC_CONV_WEIGHTS_STABLE) ? 1 : 0;
   p.aff_gamma = p.aff_beta = p.aff_mean = p.aff_var = nullptr;
   p.aff_eps = 0.f; p.aff_relu = 0;
   if (aff != nullptr) {

@@ -13,6 +13,7 @@ DC_F32, DC_BF16 = 0, 1
 DC_MAX_TAPS = 9
 DC_PACK_TKN, DC_PACK_NTK, DC_PACK_NTK_CONVT2 = 0, 1, 2
 DC_ABI_VERSION = 2
+DC_CONV_WEIGHTS_STABLE = 1
 DC_BN_RELU, DC_BN_TRAIN, DC_BN_IDENTITY, DC_BN_RES_WRITE, DC_BN_SUMS_READY, DC_BN_MASK_FROM_Y = 1, 2, 4, 8, 16, 32
 
 
@@ -26,7 +27,7 @@ class dc_conv_desc(Structure):
     _fields_ = [("ntaps", c_int32), ("dh", c_int32 * DC_MAX_TAPS), ("dw", c_int32 * DC_MAX_TAPS),
                 ("wt", c_int32 * DC_MAX_TAPS), ("stride_h", c_int32), ("stride_w", c_int32),
                 ("accumulate", c_int32), ("wtaps", c_int32),
-                ("out_csplit", c_int32), ("reserved", c_int32), ("out_split_off", c_int64)]
+                ("out_csplit", c_int32), ("flags", c_int32), ("out_split_off", c_int64)]
 
 
 class dc_bn_params(Structure):

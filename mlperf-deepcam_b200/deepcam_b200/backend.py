@@ -12,8 +12,8 @@ import os
 import torch
 
 from . import convdesc, ops
-from ._lib import (DC_BN_IDENTITY, DC_BN_MASK_FROM_Y, DC_BN_RELU, DC_BN_RES_WRITE, DC_BN_SUMS_READY, DC_BN_TRAIN, DC_PACK_NTK,
-                   DC_PACK_NTK_CONVT2, DC_PACK_TKN)
+from ._lib import (DC_BN_IDENTITY, DC_BN_MASK_FROM_Y, DC_BN_RELU, DC_BN_RES_WRITE, DC_BN_SUMS_READY, DC_BN_TRAIN,
+                   DC_CONV_WEIGHTS_STABLE, DC_PACK_NTK, DC_PACK_NTK_CONVT2, DC_PACK_TKN)
 
 
 def _round_up(a, b):
@@ -133,6 +133,10 @@ class CudaBackend:
         self.fuse_bn_dw = os.environ.get("DEEPCAM_B200_FUSE_BN_DW", "0") not in ("0", "false", "")
         # eval mode without gradient recording: BatchNorm (+ReLU) folded into the producing GEMM's epilogue
         self.fold_bn_eval = os.environ.get("DEEPCAM_B200_FOLD_BN_EVAL", "1") not in ("0", "false", "")
+        # tcgen05 GEMMs fetch their first weight tiles before griddepcontrol.wait when the weights are known to be older than
+        # the preceding kernel (captured plans only, see _weights_stable)
+        self.early_weights = os.environ.get("DEEPCAM_B200_EARLY_WEIGHTS", "1") not in ("0", "false", "")
+        self.pack_mark = 0            # value of self.launches right after the most recent weight-pack launch
         self.side_stream = None       # set by a graph plan: weight-gradient kernels run on a parallel graph branch
         self._side_dirty = False
 
@@ -255,11 +259,21 @@ class CudaBackend:
         else:
             layout, K_pad, N_pad, dt = DC_PACK_TKN, x.shape[3], _round_up(N, 4), x.dtype
 
-        return _cached(spec, (role, impl, dt, K_pad, N_pad), w, (K, N, taps, src_k_first, layout, K_pad, N_pad, dt),
-                       frozen=self.graph_mode)
+        c0 = ops._lib.launch_count
+        buf = _cached(spec, (role, impl, dt, K_pad, N_pad), w, (K, N, taps, src_k_first, layout, K_pad, N_pad, dt),
+                      frozen=self.graph_mode)
+        if ops._lib.launch_count != c0:
+            self.pack_mark = self.launches          # a pack kernel was just launched: the next kernel follows it directly
+        return buf
+
+    def _weights_stable(self):
+        """DC_CONV_WEIGHTS_STABLE for the next GEMM: inside a captured plan every packed weight was refreshed by the ONE pack
+        launch at the start of the forward graph, so any kernel with at least one other launch between it and that pack may
+        fetch its weights before griddepcontrol.wait (the early portion of a kernel only overlaps its immediate predecessor)."""
+        return DC_CONV_WEIGHTS_STABLE if (self.graph_mode and self.early_weights and self.launches > self.pack_mark) else 0
 
     def _gemm(self, taps, stride, accumulate, wtaps, x, w, bias, out, impl, bn_sums=None, out_split=None, flop_scale=1.0):
-        desc = ops.make_desc(taps, (stride, stride), accumulate, wtaps, out_split)
+        desc = ops.make_desc(taps, (stride, stride), accumulate, wtaps, out_split, flags=self._weights_stable() if impl == "tc" else 0)
         ops.conv_gemm(desc, x, w, bias, out, impl, bn_sums, flop_scale)
         self.launches += 1
 
@@ -301,7 +315,8 @@ class CudaBackend:
         kk = spec.k * spec.k
         args = (m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var, m.eps, relu)
         if not spec.transposed:
-            desc = ops.make_desc(convdesc.conv_fprop_taps(spec.k, spec.pad, spec.dil), (spec.stride, spec.stride), False, kk)
+            desc = ops.make_desc(convdesc.conv_fprop_taps(spec.k, spec.pad, spec.dil), (spec.stride, spec.stride), False, kk,
+                                 flags=self._weights_stable())
             if not ops.conv_gemm_bn_eval(desc, x, w, bias, out, *args):
                 return False
             self.launches += 1
@@ -309,7 +324,8 @@ class CudaBackend:
         s = spec.stride
         for ph in range(s):
             for pw in range(s):
-                desc = ops.make_desc(convdesc.convT_fprop_taps(spec.k, s, spec.pad, ph, pw), (1, 1), False, kk)
+                desc = ops.make_desc(convdesc.convT_fprop_taps(spec.k, s, spec.pad, ph, pw), (1, 1), False, kk,
+                                     flags=self._weights_stable())
                 if not ops.conv_gemm_bn_eval(desc, x, w, bias, out[:, ph::s, pw::s, :], *args):
                     if ph or pw:
                         raise RuntimeError("deepcam_b200: transposed-convolution parity classes disagree on the epilogue path")

@@ -589,6 +589,8 @@ class _GraphPlan:
             with _capture(g, self.pool):
                 if self.pack_table is not None:
                     ops.pack_weights_multi(*self.pack_table)     # one launch re-packs every weight each step
+                    self.be.launches += 1
+                    self.be.pack_mark = self.be.launches         # the first kernel after it must not touch weights early
                 self.outs = self.module._emit_root(self.eng, *self.xin)
                 self.eng.finish_forward()
             self.fwd_zero = self.be.end_arena()

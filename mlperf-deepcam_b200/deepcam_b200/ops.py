@@ -159,7 +159,7 @@ def _timed(name, flops, nbytes, rc_fn, what, tag=""):
 
 
 # ---- descriptors ---------------------------------------------------------------------------------
-def make_desc(taps, stride=(1, 1), accumulate=False, wtaps=None, out_split=None):
+def make_desc(taps, stride=(1, 1), accumulate=False, wtaps=None, out_split=None, flags=0):
     """taps: sequence of (dh, dw, weight_slice).  out_split = (first channel of the second output segment, its element
     offset from the output view's origin), see dc_conv_desc.out_csplit."""
     if not 1 <= len(taps) <= DC_MAX_TAPS:
@@ -173,6 +173,7 @@ def make_desc(taps, stride=(1, 1), accumulate=False, wtaps=None, out_split=None)
     d.wtaps = wtaps if wtaps is not None else (max(t[2] for t in taps) + 1)
     if out_split is not None:
         d.out_csplit, d.out_split_off = int(out_split[0]), int(out_split[1])
+    d.flags = int(flags)
     return d
 
 
