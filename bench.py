@@ -306,6 +306,10 @@ def run_ours(args):
     net = dx.DeepLabv3_plus(n_input=C_IN, n_classes=N_CLASSES, os=16, _print=False)
     net.precision = precision
     net = net.to(dev).train()
+    if LOCAL_BATCH == 1:
+        # BatchNorm over ONE pooled value per channel cannot train (the reference raises at DX:425-428); the sweep point
+        # at local batch 1 evaluates that single layer with its running statistics, as SURVEY 8(d) config 1 prescribes
+        net.global_avg_pool[2].eval()
     model = net
     if world > 1:
         from deepcam_b200.parallel import DistributedDataParallel
@@ -584,7 +588,8 @@ def run_ours(args):
         line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="bf16" if precision == "bf16" else "f32", data="synthetic",
-                    config=shared_config(world), optimizer_impl=opt_name,
+                    config=dict(shared_config(world), **({} if args.optimizer == "adam" else {"optimizer": opt_name})),
+                    optimizer_impl=opt_name,
                     e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                              ms_per_step=ms_e2e / args.steps, loss=last.get("loss"),
                              loss_readback=".item() every step" if args.e2e_sync_loss else
