@@ -432,11 +432,15 @@ class DeepLabv3_plus(_EngineModule):
         feat, low = self.xception_features._emit(eng, x)
         fn, fh, fw, _ = feat.shape
         cat = eng.new_act(fn, fh, fw, 5 * 256, feat.t.dtype)                       # torch.cat target, DX:451
+        # five independent branches over the same feature map, disjoint channel slices of the concat buffer (DX:443-451)
         for i, aspp in enumerate((self.aspp1, self.aspp2, self.aspp3, self.aspp4)):
-            aspp._emit(eng, feat, out=cat.slice(256 * i, 256))
-        g = eng.gap(feat)                                                          # fp32 [N,1,1,2048], DX:425
-        g = eng.bn(eng.conv(g, _conv_spec(self.global_avg_pool[1]), bn=_bn_spec(self.global_avg_pool[2])), _bn_spec(self.global_avg_pool[2]), relu=True)
-        eng.broadcast(g, cat.slice(1024, 256))                                     # DX:450
+            with eng.fork(i):
+                aspp._emit(eng, feat, out=cat.slice(256 * i, 256))
+        with eng.fork(4):
+            g = eng.gap(feat)                                                      # fp32 [N,1,1,2048], DX:425
+            g = eng.bn(eng.conv(g, _conv_spec(self.global_avg_pool[1]), bn=_bn_spec(self.global_avg_pool[2])), _bn_spec(self.global_avg_pool[2]), relu=True)
+            eng.broadcast(g, cat.slice(1024, 256))                                 # DX:450
+        eng.join()
         y = eng.bn(eng.conv(cat, _conv_spec(self.conv1), bn=_bn_spec(self.bn1)), _bn_spec(self.bn1), relu=True)
         ln, lh, lw, _ = low.shape
         dcat = eng.new_act(ln, lh, lw, 256 + 48, low.t.dtype)                      # torch.cat target, DX:379

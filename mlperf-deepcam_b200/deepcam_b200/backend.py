@@ -137,6 +137,8 @@ class CudaBackend:
         # the preceding kernel (captured plans only, see _weights_stable)
         self.early_weights = os.environ.get("DEEPCAM_B200_EARLY_WEIGHTS", "1") not in ("0", "false", "")
         self.pack_mark = 0            # value of self.launches right after the most recent weight-pack launch
+        self.fork_branches = os.environ.get("DEEPCAM_B200_FORK_ASPP", "1") not in ("0", "false", "")
+        self._fork_streams, self._fork_dirty = [], set()
         self.side_stream = None       # set by a graph plan: weight-gradient kernels run on a parallel graph branch
         self._side_dirty = False
 
@@ -181,6 +183,34 @@ class CudaBackend:
         self._side_dirty = True
         with torch.cuda.stream(self.side_stream):
             yield
+
+    @contextlib.contextmanager
+    def fork(self, i):
+        """Independent FORWARD branches (the four ASPP branches, DX:443-446, read the same feature map and write disjoint channel
+        slices of the concat buffer): inside a captured plan branch i runs on its own stream = a parallel branch of the CUDA graph,
+        so the 54-CTA atrous GEMMs of three branches share the 148 SMs instead of running one after the other.  join_forks()
+        brings them back before the first consumer of the concat buffer.  Outside a capture this is a no-op."""
+        if not self.graph_mode or not self.fork_branches or not torch.cuda.is_current_stream_capturing():
+            yield
+            return
+        while len(self._fork_streams) <= i:
+            self._fork_streams.append(torch.cuda.Stream(device=self.device))
+        main = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        st = self._fork_streams[i]
+        st.wait_event(ev)
+        self._fork_dirty.add(i)
+        with torch.cuda.stream(st):
+            yield
+
+    def join_forks(self):
+        main = torch.cuda.current_stream(self.device)
+        for i in sorted(self._fork_dirty):
+            ev = torch.cuda.Event()
+            ev.record(self._fork_streams[i])
+            main.wait_event(ev)
+        self._fork_dirty.clear()
 
     def join_side(self):
         if self.side_stream is not None and self._side_dirty:

@@ -417,6 +417,20 @@ class Engine:
         dx, acc = self.grad_target(x)
         self.be.bilinear_bwd(g, dx, acc)
 
+    def fork(self, i):
+        """Context manager: the operations emitted inside form forward branch i, independent of the other branches (see
+        CudaBackend.fork).  The backward tape is unaffected: it replays every closure in reverse order on the main stream."""
+        f = getattr(self.be, "fork", None)
+        if f is None:
+            import contextlib
+            return contextlib.nullcontext()
+        return f(i)
+
+    def join(self):
+        j = getattr(self.be, "join_forks", None)
+        if j is not None:
+            j()
+
     # ---- execution ----------------------------------------------------------------------------------------
     def finish_forward(self):
         if self.bn_trained:
