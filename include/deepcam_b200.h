@@ -75,6 +75,11 @@ typedef struct dc_conv_desc {
  * then fetch their first weight tiles BEFORE griddepcontrol.wait, i.e. while the preceding kernel still drains; only the
  * activation operand waits for it.  Never set it right after a pack launch. */
 #define DC_CONV_WEIGHTS_STABLE 1
+/* DC_CONV_HALO_PACK: the packed weights are K-DENSE, [Co][slice][Ci] with Ci = the gathered operand's channel count (not rounded
+ * up to 64): the layout of the tcgen05 kernel's HALO mode, which stages each tile's input region (halo included) once in shared
+ * memory and builds the per-tap operand tiles from it, instead of one TMA box per tap.  Only pass it after
+ * dc_conv_gemm_tc_halo_ok() returned 1 for the same descriptor and views. */
+#define DC_CONV_HALO_PACK 2
 
 /* ---- library / diagnostics ------------------------------------------------ */
 int         dc_abi_version(void);
@@ -148,6 +153,10 @@ int dc_conv_gemm_tc(const dc_conv_desc* d, dc_view in, const void* w, const floa
  * statistics pass appended.  d->accumulate must be 0.  Replaces the statistics half of nn.BatchNorm2d after a conv. */
 int dc_conv_gemm_tc_bnstats(const dc_conv_desc* d, dc_view in, const void* w, const float* bias,
                             dc_view out, double* sums, void* stream);
+/* 1 when dc_conv_gemm_tc / _bnstats / _bn_eval would run this contraction in HALO mode (multi-tap gather, uniform stride 1 | 2,
+ * gathered or output channels <= 64, everything fits in shared memory): the caller must then pack the weights K-dense and set
+ * DC_CONV_HALO_PACK (for Ci % 64 == 0 the two layouts coincide and the flag is optional). */
+int dc_conv_gemm_tc_halo_ok(const dc_conv_desc* d, dc_view in, dc_view out);
 /* Eval-mode Conv2d / ConvTranspose2d-parity-class + BatchNorm2d (+ReLU) in ONE tcgen05 launch (DX:144-149, 291-293, 352-372 under
  * net.eval(), TR:428): out = [relu]((conv(x) + bias) * scale + shift) with scale = gamma / sqrt(running_var + eps) and
  * shift = beta - running_mean * scale derived inside the epilogue, applied to the fp32 accumulator before the single bf16

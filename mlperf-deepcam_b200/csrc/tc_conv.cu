@@ -451,6 +451,21 @@ struct TcV2Cfg {
   int wide;            // N tile of 257..512 columns: two MMAs per k step (bn_sub0 + the rest) into ONE accumulator of BN TMEM
   int bn_sub0;         // columns, B tile fetched as two TMA boxes of b_box_rows rows; used when it turns a two-round problem
   int b_box_rows;      // (e.g. 54 M tiles x 728 columns) into one round over fewer, fatter CTAs
+  // HALO mode (conv_gemm_tc2_kernel<true>): few-channel / few-output layers whose per-tap TMA boxes would re-read the input once
+  // per tap through the L2->SM path (conv1, conv2 and its dgrad, last_deconv fprop + dgrad: 9 x resp. 4 x their HBM bytes).
+  // The input region of a tile (halo included) is loaded ONCE per tile by one un-swizzled TMA box, four producer warps copy it
+  // tap by tap into the 128B-swizzled K-major A stages (im2col in shared memory, K = tap-major dense: k = slice * Ci + ci), the
+  // whole weight tile is resident, and the MMA / epilogue side is the same as in the streaming mode.
+  int halo;            // 1 = this mode
+  int halo_w, halo_h;  // pixels of the staged input region
+  int halo_bytes;      // halo_w * halo_h * Ci * 2
+  int halo_stride;     // bytes between the halo buffers (multiple of 1024)
+  int halo_bufs;       // 1 or 2 (double-buffered across tiles when shared memory allows)
+  int halo_ci;         // gathered channels
+  int halo_s;          // gather stride (1 | 2)
+  int halo_x0, halo_y0; // smallest tap offset (dw, dh): input coordinate of the region's first pixel relative to stride * tile origin
+  int nkb;             // K blocks of 64 = ceil(wtaps * Ci / 64)
+  int ktot;            // wtaps * Ci
   int smem_bytes;
 };
 constexpr int kV2StagePitchF32 = 64 * 4 + 16;     // staged row: 64 fp32 columns + 16 B (odd multiple of 16 B: conflict-free)
@@ -462,30 +477,36 @@ static_assert(kV2StagingBytes >= 4 * 32 * kV2StagePitchF32, "staging must also h
 // per scheduler the epilogue is latency-bound (tools/tc_trace.py: 0.7 us per 128 x 64 chunk, 4.3 of the 11 us of a 728 x 728
 // layer); the two groups drain alternate 64-column chunks of the same accumulator concurrently.
 constexpr int kTc2Threads = 320;
+constexpr int kTc2HaloThreads = 448;          // + warps 10..13: im2col producers of the halo mode
 __device__ __forceinline__ void epi_group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(kTc2Threads, 1) conv_gemm_tc2_kernel(const __grid_constant__ TcMaps maps, const TcFpropParams p,
-                                                                      const TcV2Cfg cfg) {
+template <bool kHalo>
+__global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv_gemm_tc2_kernel(const __grid_constant__ TcMaps maps,
+                                                                                                const TcFpropParams p, const TcV2Cfg cfg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int STAGES = cfg.stages;
   const int BN = cfg.BN;
   const uint32_t bres_base = smem_base + STAGES * cfg.stage_bytes;
+  const uint32_t halo_region = kHalo ? (uint32_t)(cfg.halo_bufs * cfg.halo_stride) : 0u;
+  const uint32_t halo_off = (uint32_t)(STAGES * cfg.stage_bytes + cfg.bres_bytes);          // halo buffers follow the resident weights
   // wide mode runs exactly one tile per CTA: the epilogue staging aliases pipeline stage 0 (all MMAs have completed, hence
   // all stages have been consumed, before the first accumulator read), which buys a third pipeline stage
-  const uint32_t stg_off = cfg.wide ? 0u : (uint32_t)(STAGES * cfg.stage_bytes + cfg.bres_bytes);
-  const uint32_t bar_base = smem_base + STAGES * cfg.stage_bytes + cfg.bres_bytes + (cfg.wide ? 0u : (uint32_t)kV2StagingBytes);
+  const uint32_t stg_off = cfg.wide ? 0u : (uint32_t)(STAGES * cfg.stage_bytes + cfg.bres_bytes) + halo_region;
+  const uint32_t bar_base = smem_base + STAGES * cfg.stage_bytes + cfg.bres_bytes + halo_region + (cfg.wide ? 0u : (uint32_t)kV2StagingBytes);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   const uint32_t bres_bar = bar_base + 8u * (2 * STAGES + 4);
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 5);
+  auto hfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + b); };
+  auto hempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 8 + b); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -499,9 +520,10 @@ __global__ void __launch_bounds__(kTc2Threads, 1) conv_gemm_tc2_kernel(const __g
 #endif
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), kHalo ? 4 : 1); mbar_init(empty_bar(s), 1); }   // halo: one arrive per producer warp
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), cfg.bm2 ? 16 : 8); }   // every epilogue warp of both groups arrives once per (sub-)tile
     mbar_init(bres_bar, 1);
+    if (kHalo) for (int b = 0; b < 2; ++b) { mbar_init(hfull_bar(b), 1); mbar_init(hempty_bar(b), 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -555,6 +577,22 @@ __global__ void __launch_bounds__(kTc2Threads, 1) conv_gemm_tc2_kernel(const __g
         for (int j = 0; j < nblk; ++j) tma_load_2d(&maps.b, bres_bar, bres_base + j * b_block_bytes, j * 64, 0);
       }
       if (cfg.b_resident) early_b = 0;                 // (the pipeline stages carry no weights in this mode)
+      if (kHalo) {
+        // one un-swizzled box per tile: the tile's whole input region, halo included; out-of-range pixels are zero-filled (= padding)
+        int i = 0;
+        for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++i) {
+          int mt = tile;
+          const int tile_x = mt % p.tiles_x; mt /= p.tiles_x;
+          const int tile_y = mt % p.tiles_y;
+          const int img = mt / p.tiles_y;
+          const int hb = i % cfg.halo_bufs;
+          const uint32_t par = (uint32_t)(i / cfg.halo_bufs) & 1u;
+          mbar_wait(hempty_bar(hb), par ^ 1u);
+          mbar_expect_tx(hfull_bar(hb), cfg.halo_bytes);
+          tma_load_4d(&maps.a[0], hfull_bar(hb), smem_base + halo_off + (uint32_t)(hb * cfg.halo_stride), 0,
+                      tile_x * p.TW * cfg.halo_s + cfg.halo_x0, tile_y * p.TH * cfg.halo_s + cfg.halo_y0, img);
+        }
+      } else {
       int s = 0; uint32_t ph = 0;
       int issued = 0;                                  // k steps issued so far by this CTA (first tile first)
       const int MT = cfg.bm2 ? 2 : 1;
@@ -592,6 +630,53 @@ __global__ void __launch_bounds__(kTc2Threads, 1) conv_gemm_tc2_kernel(const __g
           }
         }
       }
+      }   // !kHalo
+    }
+  } else if (kHalo && warp >= 10) {
+    // ---- halo mode: im2col producers.  A stage = 128 rows (tile pixels, row-major TH x TW) x 64 K elements, K-major, 128B
+    //      swizzle; K element k = slice * Ci + ci, chunk j of k block kb covers k0 = kb*64 + j*8 .. +7 (Ci % 8 == 0, so a chunk
+    //      never straddles two taps).  lane = (rsub, j): a warp instruction moves the 8 chunks (128 contiguous bytes of the
+    //      destination row) of 4 rows; the warp owns rows 32*pw .. +31. ----
+    const int pw = warp - 10, j = lane & 7, rsub = lane >> 3;
+    const int Ci = cfg.halo_ci, Wh = cfg.halo_w, hs = cfg.halo_s;
+    uint32_t src_off[8], dst_off[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = pw * 32 + it * 4 + rsub;
+      const int ty = r / p.TW, tx = r - ty * p.TW;
+      src_off[it] = (uint32_t)((ty * hs * Wh + tx * hs) * Ci * 2);
+      dst_off[it] = (uint32_t)r * 128u + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4);
+    }
+    int s = 0; uint32_t ph = 0;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++i) {
+      const int hb = i % cfg.halo_bufs;
+      mbar_wait(hfull_bar(hb), (uint32_t)(i / cfg.halo_bufs) & 1u);
+      const uint32_t hbase = smem_base + halo_off + (uint32_t)(hb * cfg.halo_stride);
+      for (int kb = 0; kb < cfg.nkb; ++kb) {
+        const int k0 = kb * 64 + j * 8;
+        int t = -1;
+        uint32_t toff = 0;
+        if (k0 < cfg.ktot) {
+          const int slice = k0 / Ci, ci0 = k0 - slice * Ci;
+          for (int q = 0; q < p.ntaps; ++q) if (p.wt[q] == slice) t = q;      // tap that owns this weight slice (none: zeros)
+          if (t >= 0) toff = (uint32_t)(((p.qh[t] * Wh + p.qw[t]) * Ci + ci0) * 2);
+        }
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t sa = smem_base + s * cfg.stage_bytes;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+          if (t >= 0) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(hbase + src_off[it] + toff));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + dst_off[it]), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+        }
+        fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(s));
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(hempty_bar(hb));      // this warp has read the halo buffer for the last time
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -610,9 +695,10 @@ __global__ void __launch_bounds__(kTc2Threads, 1) conv_gemm_tc2_kernel(const __g
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * cfg.acc_stride);
         int it = 0;
-        for (int t = 0; t < p.ntaps; ++t) {
-          const int kb0 = p.wt[t] * p.kblocks;
-          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+        const int nt_loop = kHalo ? 1 : p.ntaps, nk_loop = kHalo ? cfg.nkb : p.kblocks;     // halo: K is dense, nkb blocks in order
+        for (int t = 0; t < nt_loop; ++t) {
+          const int kb0 = kHalo ? 0 : p.wt[t] * p.kblocks;
+          for (int kb = 0; kb < nk_loop; ++kb, ++it) {
             mbar_wait(full_bar(s), ph);
             tc_fence_after();
             if (i == 0 && it == 0) TC_TRACE(2);
@@ -644,7 +730,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) conv_gemm_tc2_kernel(const __g
         TC_TRACE(3);
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ---- epilogue: warps 2..9 (two groups); warp w may only touch TMEM lanes 32*(w%4) .. +31 ----
     const int grp = (warp - 2) >> 2;
     const int lg = warp & 3;
@@ -1240,7 +1326,7 @@ static int launch_fprop(const TcMaps& maps, const TcFpropParams& p, const TcFpro
 // Tile configuration of the persistent kernel.  Cost model per CTA: rounds * (bytes pulled from L2 per k-block), since
 // these GEMMs are bound by the L2->SM path (~42 B/clk/SM with all SMs pulling), not by the tensor pipe.
 static TcV2Cfg pick_v2_cfg(int mtiles, int Co, int kblocks, int wtaps, bool tma_store) {
-  TcV2Cfg c;
+  TcV2Cfg c = TcV2Cfg();
   const int co16 = round_up_i(Co, 16);
   int best_bn = std::min(256, co16), best_bm2 = 0;
   double best_cost = 1e30;
@@ -1313,12 +1399,14 @@ static int launch_fprop_v2(const TcMaps& maps, const TcFpropParams& p, const TcV
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail((int)e, "dc_conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int grid = std::min(cfg.total_tiles, kNumSMs);
-  launch_k(conv_gemm_tc2_kernel, grid, dim3(kTc2Threads), (size_t)cfg.smem_bytes, st, maps, p, cfg);
+  if (cfg.halo) launch_k(conv_gemm_tc2_kernel<true>, grid, dim3(kTc2HaloThreads), (size_t)cfg.smem_bytes, st, maps, p, cfg);
+  else launch_k(conv_gemm_tc2_kernel<false>, grid, dim3(kTc2Threads), (size_t)cfg.smem_bytes, st, maps, p, cfg);
   return launch_status("dc_conv_gemm_tc");
 }
 
@@ -1327,6 +1415,73 @@ static bool use_v1_kernel() {
   if (v < 0) { const char* e = getenv("DEEPCAM_B200_TC_V1"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
+
+// ---- halo mode planning ------------------------------------------------------------------------------------------------
+static bool halo_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DEEPCAM_B200_TC_HALO"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+constexpr int kHaloTH = 8, kHaloTW = 16;      // 128 output pixels as 8 rows x 16 columns: 1.41x halo overhead for a 3x3 stride-1 gather
+
+// Fills cfg (halo fields + the common ones) and returns true when the layer should and can run in halo mode: a multi-tap gather
+// with uniform stride 1 | 2 whose narrow side (gathered channels or output channels) makes the per-tap re-reads dominate,
+// one N tile, resident weights + at least one halo buffer within shared memory.
+static bool plan_halo(const dc_conv_desc* d, const dc_view& in, const dc_view& out, bool tma_store, TcV2Cfg& c) {
+  if (!halo_enabled() || use_v1_kernel()) return false;
+  if (d->ntaps < 2 || d->stride_h != d->stride_w || (d->stride_h != 1 && d->stride_h != 2)) return false;
+  // (gathered operands wider than 64 channels would need the halo staged in channel chunks to leave room for double buffering:
+  //  the fused last_deconv forward, 256 -> 4 x 8 with a 78 KB region, stays on the per-tap boxes for now)
+  if (in.c > 64 || in.c % 8 || out.c > 256) return false;
+  int dh0 = d->dh[0], dh1 = d->dh[0], dw0 = d->dw[0], dw1 = d->dw[0];
+  for (int t = 1; t < d->ntaps; ++t) {
+    dh0 = std::min(dh0, d->dh[t]); dh1 = std::max(dh1, d->dh[t]);
+    dw0 = std::min(dw0, d->dw[t]); dw1 = std::max(dw1, d->dw[t]);
+  }
+  if (dh1 - dh0 > 4 || dw1 - dw0 > 4) return false;
+  const int s = d->stride_h;
+  c = TcV2Cfg();
+  c.halo = 1;
+  c.halo_s = s; c.halo_x0 = dw0; c.halo_y0 = dh0; c.halo_ci = in.c;
+  c.halo_h = (kHaloTH - 1) * s + (dh1 - dh0) + 1;
+  c.halo_w = (kHaloTW - 1) * s + (dw1 - dw0) + 1;
+  if (c.halo_h > 256 || c.halo_w > 256) return false;
+  c.halo_bytes = c.halo_h * c.halo_w * in.c * 2;
+  c.halo_stride = round_up_i(c.halo_bytes, 1024);
+  c.ktot = d->wtaps * in.c;
+  c.nkb = ceil_div(c.ktot, 64);
+  c.BN = round_up_i(out.c, 16);
+  c.bm2 = 0; c.wide = 0; c.bn_sub0 = c.BN; c.b_box_rows = c.BN;
+  c.b_resident = 1;
+  c.bres_bytes = c.nkb * c.BN * 128;
+  c.stage_bytes = kABytes;
+  c.stages = 3;
+  const int budget = 227 * 1024 - 1024 - 256 - kV2StagingBytes - c.stages * c.stage_bytes - c.bres_bytes;
+  if (budget < c.halo_stride) return false;
+  c.halo_bufs = budget >= 2 * c.halo_stride ? 2 : 1;
+  c.acc_stride = 32;
+  while (c.acc_stride < c.BN) c.acc_stride <<= 1;
+  c.tmem_cols = 2 * c.acc_stride;
+  c.tma_store = tma_store ? 1 : 0;
+  c.smem_bytes = c.stages * c.stage_bytes + c.bres_bytes + c.halo_bufs * c.halo_stride + kV2StagingBytes + 1024 + 256;
+  return true;
+}
+
+// un-swizzled 4-D bf16 box {Ci, halo_w, halo_h, 1} over the NHWC input (zero fill outside = padding)
+static int encode_halo_map(CUtensorMap* m, const dc_view& in, int halo_w, int halo_h, const char* what) {
+  PFN_encodeTiled enc = get_encode();
+  DC_REQUIRE(enc != nullptr, "%s: cuTensorMapEncodeTiled unavailable", what);
+  cuuint64_t dims[4] = {(cuuint64_t)in.c, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
+  cuuint64_t strides[3] = {(cuuint64_t)in.sw * 2, (cuuint64_t)in.sh * 2, (cuuint64_t)in.sn * 2};
+  cuuint32_t box[4] = {(cuuint32_t)in.c, (cuuint32_t)halo_w, (cuuint32_t)halo_h, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in.ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DC_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(halo) failed with %d (C=%d box %dx%d)", what, (int)r, in.c, halo_w, halo_h);
+  return 0;
+}
+
 
 template <int BNW>
 static int launch_wgrad(const TcMaps& maps, const TcWgradParams& p, dim3 grid, cudaStream_t st) {
@@ -1383,6 +1538,36 @@ static int conv_gemm_tc_impl(const dc_conv_desc* d, dc_view in, const void* w, c
     p.aff_eps = aff->eps; p.aff_relu = aff->relu;
   }
   if (stats_done) *stats_done = false;
+  {
+    // HALO mode: the caller packed the weights K-dense ([Co][slice][Ci], DC_CONV_HALO_PACK) - or Ci is a multiple of 64, where
+    // the dense and the 64-padded layouts coincide
+    TcV2Cfg hc;
+    const bool dense_pack = (d->flags & DC_CONV_HALO_PACK) || (in.c % 64 == 0);
+    const bool halo = dense_pack && plan_halo(d, in, out, p.out_vec_ok != 0, hc);
+    DC_REQUIRE(halo || !(d->flags & DC_CONV_HALO_PACK) || in.c % 64 == 0,
+               "dc_conv_gemm_tc: DC_CONV_HALO_PACK weights but the layer cannot run in halo mode (query dc_conv_gemm_tc_halo_ok first)");
+    if (halo) {
+      p.TH = kHaloTH; p.TW = kHaloTW;
+      p.tiles_x = ceil_div(out.w, p.TW);
+      p.tiles_y = ceil_div(out.h, p.TH);
+      p.kblocks = hc.nkb;
+      for (int t = 0; t < d->ntaps; ++t) {
+        p.map_id[t] = 0; p.wt[t] = d->wt[t];
+        p.qh[t] = d->dh[t] - hc.halo_y0; p.qw[t] = d->dw[t] - hc.halo_x0;
+      }
+      hc.real_mtiles = p.tiles_x * p.tiles_y * out.n;
+      hc.n_mtiles = hc.real_mtiles; hc.n_ntiles = 1; hc.total_tiles = hc.real_mtiles;
+      if (int r = encode_halo_map(&maps.a[0], in, hc.halo_w, hc.halo_h, "dc_conv_gemm_tc")) return r;
+      for (int id = 1; id < 4; ++id) maps.a[id] = maps.a[0];
+      if (int r = encode_weight_map(&maps.b, w, hc.ktot, out.c, hc.BN, "dc_conv_gemm_tc")) return r;
+      if (hc.tma_store) {
+        if (int r = encode_act_map(&maps.c, out.ptr, out.c, out.w, out.h, out.n, out.sw, out.sh, out.sn, p.TW, p.TH, "dc_conv_gemm_tc(out)"))
+          return r;
+        if (stats != nullptr && !d->accumulate) { p.stats = stats; *stats_done = true; }
+      }
+      return launch_fprop_v2(maps, p, hc, as_stream(stream));
+    }
+  }
   if (int r = build_gather("dc_conv_gemm_tc", d, in, p.TH, p.TW, maps, p)) return r;
   const long long Ktot = (long long)d->wtaps * p.kblocks * 64;
   const int mtiles = p.tiles_x * p.tiles_y * out.n;
@@ -1426,6 +1611,12 @@ int dc_conv_gemm_tc_bnstats(const dc_conv_desc* d, dc_view in, const void* w, co
   if (int r = conv_gemm_tc_impl(d, in, w, bias, out, sums, &done, stream)) return r;
   if (done) return 0;
   return dc::bn_accumulate_sums(out, sums, as_stream(stream));     // output layout without the TMA-store epilogue: one extra pass
+}
+
+int dc_conv_gemm_tc_halo_ok(const dc_conv_desc* d, dc_view in, dc_view out) {
+  if (d == nullptr || d->ntaps < 1 || d->ntaps > DC_MAX_TAPS || !tc_view_ok(in) || !view_ok(out)) return 0;
+  TcV2Cfg hc;
+  return plan_halo(d, in, out, true, hc) ? 1 : 0;
 }
 
 int dc_conv_gemm_tc_bn_eval(const dc_conv_desc* d, dc_view in, const void* w, const float* bias, dc_view out, const float* gamma,

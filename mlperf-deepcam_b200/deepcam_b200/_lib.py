@@ -13,7 +13,7 @@ DC_F32, DC_BF16 = 0, 1
 DC_MAX_TAPS = 9
 DC_PACK_TKN, DC_PACK_NTK, DC_PACK_NTK_CONVT2 = 0, 1, 2
 DC_ABI_VERSION = 2
-DC_CONV_WEIGHTS_STABLE = 1
+DC_CONV_WEIGHTS_STABLE, DC_CONV_HALO_PACK = 1, 2
 DC_BN_RELU, DC_BN_TRAIN, DC_BN_IDENTITY, DC_BN_RES_WRITE, DC_BN_SUMS_READY, DC_BN_MASK_FROM_Y = 1, 2, 4, 8, 16, 32
 
 
@@ -65,6 +65,7 @@ SIGNATURES = {
     "dc_conv_wgrad_simt": (c_int, [POINTER(dc_conv_desc), dc_view, dc_view, c_void_p, c_void_p]),
     "dc_conv_gemm_tc": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p]),
     "dc_conv_gemm_tc_bnstats": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p, c_void_p]),
+    "dc_conv_gemm_tc_halo_ok": (c_int, [POINTER(dc_conv_desc), dc_view, dc_view]),
     "dc_conv_gemm_tc_bn_eval": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_float, c_int, c_void_p]),
     "dc_conv_wgrad_tc": (c_int, [POINTER(dc_conv_desc), dc_view, dc_view, c_void_p, c_void_p]),

@@ -13,7 +13,7 @@ import torch
 
 from . import convdesc, ops
 from ._lib import (DC_BN_IDENTITY, DC_BN_MASK_FROM_Y, DC_BN_RELU, DC_BN_RES_WRITE, DC_BN_SUMS_READY, DC_BN_TRAIN,
-                   DC_CONV_WEIGHTS_STABLE, DC_PACK_NTK, DC_PACK_NTK_CONVT2, DC_PACK_TKN)
+                   DC_CONV_HALO_PACK, DC_CONV_WEIGHTS_STABLE, DC_PACK_NTK, DC_PACK_NTK_CONVT2, DC_PACK_TKN)
 
 
 def _round_up(a, b):
@@ -274,8 +274,17 @@ class CudaBackend:
             return False
         return gathered.shape[0] * gathered.shape[1] * gathered.shape[2] >= 128
 
-    def _packed(self, spec, role, impl, x, n_pad=None):
-        """role: 'fprop' (k = op input channels) or 'dgrad' (k = op output channels); x = gathered operand."""
+    def _halo(self, taps, stride, wtaps, x, out):
+        """DC_CONV_HALO_PACK when the tcgen05 kernel will run this gather in halo mode AND the gathered channel count is not a
+        multiple of 64 (then the weights must be packed K-dense, see _packed(k_dense=True)); 0 otherwise."""
+        if x.shape[3] % 64 == 0:
+            return 0                                    # dense and 64-padded packs coincide: the C side decides alone
+        desc = ops.make_desc(taps, (stride, stride), False, wtaps)
+        return DC_CONV_HALO_PACK if ops.conv_halo_ok(desc, x, out) else 0
+
+    def _packed(self, spec, role, impl, x, n_pad=None, k_dense=False):
+        """role: 'fprop' (k = op input channels) or 'dgrad' (k = op output channels); x = gathered operand.
+        k_dense: halo-mode layout [N][slice][C] with C = the gathered operand's channels instead of a multiple of 64."""
         w = spec.weight
         taps = spec.k * spec.k
         if role == "fprop":
@@ -285,7 +294,7 @@ class CudaBackend:
             K, N = spec.co, spec.ci
             src_k_first = not spec.transposed      # Conv weight is [co][ci][taps] = [k][n]
         if impl == "tc":
-            layout, K_pad, N_pad, dt = DC_PACK_NTK, _round_up(K, 64), max(N, n_pad or 0), torch.bfloat16
+            layout, K_pad, N_pad, dt = DC_PACK_NTK, (x.shape[3] if k_dense else _round_up(K, 64)), max(N, n_pad or 0), torch.bfloat16
         else:
             layout, K_pad, N_pad, dt = DC_PACK_TKN, x.shape[3], _round_up(N, 4), x.dtype
 
@@ -302,8 +311,9 @@ class CudaBackend:
         fetch its weights before griddepcontrol.wait (the early portion of a kernel only overlaps its immediate predecessor)."""
         return DC_CONV_WEIGHTS_STABLE if (self.graph_mode and self.early_weights and self.launches > self.pack_mark) else 0
 
-    def _gemm(self, taps, stride, accumulate, wtaps, x, w, bias, out, impl, bn_sums=None, out_split=None, flop_scale=1.0):
-        desc = ops.make_desc(taps, (stride, stride), accumulate, wtaps, out_split, flags=self._weights_stable() if impl == "tc" else 0)
+    def _gemm(self, taps, stride, accumulate, wtaps, x, w, bias, out, impl, bn_sums=None, out_split=None, flop_scale=1.0, flags=0):
+        desc = ops.make_desc(taps, (stride, stride), accumulate, wtaps, out_split,
+                             flags=(flags | self._weights_stable()) if impl == "tc" else 0)
         ops.conv_gemm(desc, x, w, bias, out, impl, bn_sums, flop_scale)
         self.launches += 1
 
@@ -316,14 +326,18 @@ class CudaBackend:
         impl = "tc" if self._tc_ok(x, spec.co) else "simt"
         if spec.transposed and impl == "tc" and not want_bn_sums and self._convT_fusable(spec, out):
             return self._convT_fused_fwd(x, spec, out)
-        w = self._packed(spec, "fprop", impl, x, n_pad=out.shape[3])
-        bias = spec.bias.detach() if spec.bias is not None else None
         kk = spec.k * spec.k
+        halo = 0
+        if impl == "tc" and not spec.transposed and kk > 1:
+            halo = self._halo(convdesc.conv_fprop_taps(spec.k, spec.pad, spec.dil), spec.stride, kk, x, out)
+        w = self._packed(spec, "fprop", impl, x, n_pad=out.shape[3], k_dense=bool(halo))
+        bias = spec.bias.detach() if spec.bias is not None else None
         sums = None
         if want_bn_sums and impl == "tc" and self.fuse_bn_stats and out.dtype == torch.bfloat16:
             sums = self.scratch(ops.bn_ws_elems(out.shape[3]), torch.float64, zero=True)
         if not spec.transposed:
-            self._gemm(convdesc.conv_fprop_taps(spec.k, spec.pad, spec.dil), spec.stride, False, kk, x, w, bias, out, impl, sums)
+            self._gemm(convdesc.conv_fprop_taps(spec.k, spec.pad, spec.dil), spec.stride, False, kk, x, w, bias, out, impl, sums,
+                       flags=halo)
         else:
             s = spec.stride
             for ph in range(s):
@@ -340,13 +354,16 @@ class CudaBackend:
         if (not self.fold_bn_eval or m.running_mean is None or m.weight is None or m.bias is None or out.dtype != torch.bfloat16
                 or not self._tc_ok(x, spec.co)):
             return False
-        w = self._packed(spec, "fprop", "tc", x, n_pad=out.shape[3])
-        bias = spec.bias.detach() if spec.bias is not None else None
         kk = spec.k * spec.k
+        halo = 0
+        if not spec.transposed and kk > 1:
+            halo = self._halo(convdesc.conv_fprop_taps(spec.k, spec.pad, spec.dil), spec.stride, kk, x, out)
+        w = self._packed(spec, "fprop", "tc", x, n_pad=out.shape[3], k_dense=bool(halo))
+        bias = spec.bias.detach() if spec.bias is not None else None
         args = (m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var, m.eps, relu)
         if not spec.transposed:
             desc = ops.make_desc(convdesc.conv_fprop_taps(spec.k, spec.pad, spec.dil), (spec.stride, spec.stride), False, kk,
-                                 flags=self._weights_stable())
+                                 flags=self._weights_stable() | halo)
             if not ops.conv_gemm_bn_eval(desc, x, w, bias, out, *args):
                 return False
             self.launches += 1
@@ -386,10 +403,13 @@ class CudaBackend:
     def conv_bwd_data(self, dy, spec, dx, accumulate):
         """dx (+)= conv^T(dy)."""
         impl = "tc" if self._tc_ok(dy, spec.ci) else "simt"
-        w = self._packed(spec, "dgrad", impl, dy)
         kk = spec.k * spec.k
+        halo = 0
+        if impl == "tc" and spec.transposed:
+            halo = self._halo(convdesc.convT_dgrad_taps(spec.k, spec.pad), spec.stride, kk, dy, dx)
+        w = self._packed(spec, "dgrad", impl, dy, k_dense=bool(halo))
         if spec.transposed:
-            self._gemm(convdesc.convT_dgrad_taps(spec.k, spec.pad), spec.stride, accumulate, kk, dy, w, None, dx, impl)
+            self._gemm(convdesc.convT_dgrad_taps(spec.k, spec.pad), spec.stride, accumulate, kk, dy, w, None, dx, impl, flags=halo)
         elif spec.stride == 1:
             self._gemm(convdesc.conv_dgrad_taps(spec.k, spec.pad, spec.dil), 1, accumulate, kk, dy, w, None, dx, impl)
         else:

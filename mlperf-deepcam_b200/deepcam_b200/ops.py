@@ -270,6 +270,12 @@ def conv_gemm(desc, x, w, bias, out, impl, bn_sums=None, flop_scale=1.0):
     return out
 
 
+def conv_halo_ok(desc, x, out):
+    """True when the tcgen05 kernel would run this contraction in halo mode (dc_conv_gemm_tc_halo_ok): the weights must then
+    be packed K-dense (K_pad = x.shape[3]) and the call flagged DC_CONV_HALO_PACK."""
+    return _lib.load().dc_conv_gemm_tc_halo_ok(ctypes.byref(desc), view(x), view(out)) == 1
+
+
 def conv_gemm_bn_eval(desc, x, w, bias, out, gamma, beta, running_mean, running_var, eps, relu):
     """out = [relu](bn_eval(conv(x) + bias)) in one tcgen05 launch (dc_conv_gemm_tc_bn_eval).  Returns False when the output
     layout needs the generic epilogue (nothing was launched)."""
