@@ -48,6 +48,22 @@ class _GradSync:
             cur_start = start
         if cur:
             buckets.append((cur_start, cur_end, cur))
+        # The LAST bucket (the earliest layers) completes when backward ends, so its all-reduce cannot hide behind anything:
+        # keep it small (tail_cap) by splitting off its lowest-offset parameters - the entry flow's few MB - into a bucket of
+        # their own; the bulk of the former last bucket then still overlaps with the entry flow's backward kernels.
+        tail_cap = self.owner.tail_cap_elems
+        if buckets and tail_cap > 0:
+            start, end, idxs = buckets[-1]
+            if end - start > tail_cap and len(idxs) > 1:
+                k = len(idxs)
+                while k > 1 and (grads.offsets[idxs[k - 2] + 1] if idxs[k - 2] + 1 < n else grads.total) - start <= tail_cap:
+                    k -= 1
+                # idxs[k-1:] = the parameters of the small tail bucket (k-1 >= 1 keeps at least one parameter in the head part)
+                k = max(k, 2)
+                cut = grads.offsets[idxs[k - 1] + 1] if idxs[k - 1] + 1 < n else grads.total      # end offset of the tail part
+                if start < cut < end:
+                    buckets[-1] = (cut, end, idxs[:k - 1])
+                    buckets.append((start, cut, idxs[k - 1:]))
         self.buckets = buckets
         self.bucket_of = {}
         for b, (_, _, idxs) in enumerate(buckets):
@@ -110,7 +126,7 @@ class _GradSync:
 
 class DistributedDataParallel(nn.Module):
     def __init__(self, module, device_ids=None, output_device=None, broadcast_buffers=True, bucket_cap_mb=64,
-                 process_group=None):
+                 process_group=None, tail_cap_mb=8):
         super().__init__()
         if not dist.is_initialized():
             raise RuntimeError("deepcam_b200.parallel.DistributedDataParallel needs torch.distributed to be initialised")
@@ -119,6 +135,7 @@ class DistributedDataParallel(nn.Module):
         self.world_size = dist.get_world_size(process_group)
         self.broadcast_buffers = broadcast_buffers
         self.bucket_cap_elems = int(bucket_cap_mb * 1024 * 1024 // 4)
+        self.tail_cap_elems = int(tail_cap_mb * 1024 * 1024 // 4)
         p0 = next(module.parameters())
         self.on_cuda = p0.is_cuda
         self.comm_stream = torch.cuda.Stream(device=p0.device) if self.on_cuda else None
