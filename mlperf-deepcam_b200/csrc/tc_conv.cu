@@ -478,6 +478,7 @@ static_assert(kV2StagingBytes >= 4 * 32 * kV2StagePitchF32, "staging must also h
 // layer); the two groups drain alternate 64-column chunks of the same accumulator concurrently.
 constexpr int kTc2Threads = 320;
 constexpr int kTc2HaloThreads = 448;          // + warps 10..13: im2col producers of the halo mode
+constexpr int kHaloTH = 8, kHaloTW = 16;      // halo-mode tile: 128 output pixels as 8 rows x 16 columns (1.41x halo overhead for a 3x3 stride-1 gather)
 __device__ __forceinline__ void epi_group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -520,7 +521,7 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
 #endif
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), kHalo ? 4 : 1); mbar_init(empty_bar(s), 1); }   // halo: one arrive per producer warp
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }   // (halo: ONE producer warp builds a stage)
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), cfg.bm2 ? 16 : 8); }   // every epilogue warp of both groups arrives once per (sub-)tile
     mbar_init(bres_bar, 1);
     if (kHalo) for (int b = 0; b < 2; ++b) { mbar_init(hfull_bar(b), 1); mbar_init(hempty_bar(b), 4); }
@@ -639,41 +640,43 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
     //      destination row) of 4 rows; the warp owns rows 32*pw .. +31. ----
     const int pw = warp - 10, j = lane & 7, rsub = lane >> 3;
     const int Ci = cfg.halo_ci, Wh = cfg.halo_w, hs = cfg.halo_s;
-    uint32_t src_off[8], dst_off[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = pw * 32 + it * 4 + rsub;
-      const int ty = r / p.TW, tx = r - ty * p.TW;
-      src_off[it] = (uint32_t)((ty * hs * Wh + tx * hs) * Ci * 2);
-      dst_off[it] = (uint32_t)r * 128u + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4);
-    }
-    int s = 0; uint32_t ph = 0;
+    // Producer warp pw builds the k blocks kb = pw, pw + 4, ... of every tile ALONE (all 128 rows, 32 warp instructions of
+    // 4 rows x 8 chunks), so the four warps work on four different pipeline stages at once and every stage costs ONE
+    // generic->async proxy fence and ONE barrier arrival (with all four warps on the same k block the per-block handshake
+    // - 4 arrivals, fence, MMA commit, empty wait - serialised: 0.68 us per k block, measured round 2).
     int i = 0;
     for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++i) {
       const int hb = i % cfg.halo_bufs;
       mbar_wait(hfull_bar(hb), (uint32_t)(i / cfg.halo_bufs) & 1u);
       const uint32_t hbase = smem_base + halo_off + (uint32_t)(hb * cfg.halo_stride);
-      for (int kb = 0; kb < cfg.nkb; ++kb) {
+      for (int kb = pw; kb < cfg.nkb; kb += 4) {
+        const int q = i * cfg.nkb + kb;                 // running k-block number of this CTA: stage and phase follow from it
+        const int s = q % STAGES;
+        const uint32_t ph = (uint32_t)(q / STAGES) & 1u;
         const int k0 = kb * 64 + j * 8;
         int t = -1;
         uint32_t toff = 0;
         if (k0 < cfg.ktot) {
           const int slice = k0 / Ci, ci0 = k0 - slice * Ci;
-          for (int q = 0; q < p.ntaps; ++q) if (p.wt[q] == slice) t = q;      // tap that owns this weight slice (none: zeros)
+          for (int qq = 0; qq < p.ntaps; ++qq) if (p.wt[qq] == slice) t = qq;      // tap that owns this weight slice (none: zeros)
           if (t >= 0) toff = (uint32_t)(((p.qh[t] * Wh + p.qw[t]) * Ci + ci0) * 2);
         }
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t sa = smem_base + s * cfg.stage_bytes;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
+        const uint32_t src0 = hbase + toff;
+#pragma unroll 8
+        for (int it = 0; it < 32; ++it) {
+          const int r = it * 4 + rsub;
+          const int ty = r / kHaloTW, tx = r % kHaloTW;  // (the host fixes TH x TW = 8 x 16 in this mode)
           uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-          if (t >= 0) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(hbase + src_off[it] + toff));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + dst_off[it]), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+          if (t >= 0) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                                   : "r"(src0 + (uint32_t)((ty * hs * Wh + tx * hs) * Ci * 2)));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + (uint32_t)r * 128u + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4)),
+                       "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
         }
         fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core's async proxy
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(s));
-        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(hempty_bar(hb));      // this warp has read the halo buffer for the last time
@@ -744,6 +747,21 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
     const bool raw_copy = !stage_f32 && p.out_vec_ok;
     int i = 0;
     const int MT = cfg.bm2 ? 2 : 1;
+    // BatchNorm statistics carried across this CTA's tiles (see the statistics block below)
+    double stat_acc0 = 0.0, stat_acc1 = 0.0, stat_acc2 = 0.0, stat_acc3 = 0.0;
+    int stat_nt = -1;
+    auto stats_flush = [&]() {
+      if (p.stats == nullptr || stat_nt < 0) return;
+      const int t = (int)threadIdx.x - 64 - 128 * grp;
+      const int fn0 = stat_nt * BN, fncols = min(BN, p.out.c - fn0);
+      double* dst = p.stats + (size_t)(t >> 6) * p.stats_C + fn0;
+      const int cbase = grp * 64 + (t & 63);
+      if (cbase < fncols && stat_acc0 != 0.0) atomicAdd(dst + cbase, stat_acc0);
+      if (cbase + 128 < fncols && stat_acc1 != 0.0) atomicAdd(dst + cbase + 128, stat_acc1);
+      if (cbase + 256 < fncols && stat_acc2 != 0.0) atomicAdd(dst + cbase + 256, stat_acc2);
+      if (cbase + 384 < fncols && stat_acc3 != 0.0) atomicAdd(dst + cbase + 384, stat_acc3);
+      stat_acc0 = stat_acc1 = stat_acc2 = stat_acc3 = 0.0;
+    };
     for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++i) {
      for (int sub = 0; sub < MT; ++sub) {
       const int nt = tile / cfg.n_mtiles;
@@ -871,8 +889,18 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
             epi_group_sync(grp);
             const int t = (int)threadIdx.x - 64 - 128 * grp;     // 0..127: statistic (t >> 6), column (t & 63)
             const float tot = sred[t] + sred[128 + t] + sred[256 + t] + sred[384 + t];
-            const int col = c0 + (t & 63);
-            if (col < ncols) atomicAdd(p.stats + (size_t)(t >> 6) * p.stats_C + n0 + col, (double)tot);
+            // The chunk totals of ALL tiles this persistent CTA processes in one N tile are summed in registers (fp64) and
+            // flushed with one atomic per (statistic, column) when the N tile changes / at the end: the large-M layers run
+            // ~23 tiles per CTA, and 3456 tiles x 128 fp64 atomics on the same 64-128 addresses serialised in the L2
+            // (conv1 / conv2: 62 / 93 us of which the tiles' own work is ~25 us).
+            if (nt != stat_nt) { stats_flush(); stat_nt = nt; }
+            const int slot = (c0 - grp * 64) >> 7;
+            if (c0 + (t & 63) < ncols) {
+              if (slot == 0) stat_acc0 += (double)tot;
+              else if (slot == 1) stat_acc1 += (double)tot;
+              else if (slot == 2) stat_acc2 += (double)tot;
+              else stat_acc3 += (double)tot;                     // wide tiles of 512 columns: four chunks per group
+            }
             if (elected && c0 == 0) TC_TRACE(10);
           }
         }
@@ -992,6 +1020,7 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
       }
      }
     }
+    stats_flush();
   }
   if (threadIdx.x == 64) TC_TRACE(5);
   if (threadIdx.x == 192) TC_TRACE(11);
@@ -1422,7 +1451,6 @@ static bool halo_enabled() {
   if (v < 0) { const char* e = getenv("DEEPCAM_B200_TC_HALO"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
-constexpr int kHaloTH = 8, kHaloTW = 16;      // 128 output pixels as 8 rows x 16 columns: 1.41x halo overhead for a 3x3 stride-1 gather
 
 // Fills cfg (halo fields + the common ones) and returns true when the layer should and can run in halo mode: a multi-tap gather
 // with uniform stride 1 | 2 whose narrow side (gathered channels or output channels) makes the per-tap re-reads dominate,
@@ -1455,10 +1483,11 @@ static bool plan_halo(const dc_conv_desc* d, const dc_view& in, const dc_view& o
   c.b_resident = 1;
   c.bres_bytes = c.nkb * c.BN * 128;
   c.stage_bytes = kABytes;
-  c.stages = 3;
-  const int budget = 227 * 1024 - 1024 - 256 - kV2StagingBytes - c.stages * c.stage_bytes - c.bres_bytes;
-  if (budget < c.halo_stride) return false;
-  c.halo_bufs = budget >= 2 * c.halo_stride ? 2 : 1;
+  const int fixed = 1024 + 256 + kV2StagingBytes + c.bres_bytes;
+  if (227 * 1024 - fixed - 3 * c.stage_bytes < c.halo_stride) return false;
+  c.halo_bufs = (227 * 1024 - fixed - 4 * c.stage_bytes >= 2 * c.halo_stride) ? 2 : 1;
+  // the four producer warps fill four stages at once: as many stages as fit (4..8), never fewer than 3
+  c.stages = std::max(3, std::min(8, (227 * 1024 - fixed - c.halo_bufs * c.halo_stride) / c.stage_bytes));
   c.acc_stride = 32;
   while (c.acc_stride < c.BN) c.acc_stride <<= 1;
   c.tmem_cols = 2 * c.acc_stride;
