@@ -55,6 +55,12 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -464,8 +470,12 @@ struct TcV2Cfg {
   int halo_ci;         // gathered channels
   int halo_s;          // gather stride (1 | 2)
   int halo_x0, halo_y0; // smallest tap offset (dw, dh): input coordinate of the region's first pixel relative to stride * tile origin
+  int halo_nbox;        // the region is fetched as halo_nbox boxes of {256 flattened (w, c) elements, halo_h rows}: W and C are one
+                        // contiguous dimension of a dense NHWC row, so a TMA "row" is 512 bytes instead of one Ci-wide pixel (the
+                        // TMA unit is row-rate bound: 561 32-byte rows per tile for conv1 took 1.7 us, 3 x 17 rows of 512 B do not)
   int nkb;             // K blocks of 64 = ceil(wtaps * Ci / 64)
   int ktot;            // wtaps * Ci
+  int dbg;             // experiments only (DEEPCAM_B200_TC_HALO_DBG, results are garbage): 1 = producers skip the copy, 2 = skip the MMAs
   int smem_bytes;
 };
 constexpr int kV2StagePitchF32 = 64 * 4 + 16;     // staged row: 64 fp32 columns + 16 B (odd multiple of 16 B: conflict-free)
@@ -589,9 +599,13 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
           const int hb = i % cfg.halo_bufs;
           const uint32_t par = (uint32_t)(i / cfg.halo_bufs) & 1u;
           mbar_wait(hempty_bar(hb), par ^ 1u);
+          if (cfg.dbg & 8) { mbar_arrive(hfull_bar(hb)); continue; }      // experiment: no halo load at all
           mbar_expect_tx(hfull_bar(hb), cfg.halo_bytes);
-          tma_load_4d(&maps.a[0], hfull_bar(hb), smem_base + halo_off + (uint32_t)(hb * cfg.halo_stride), 0,
-                      tile_x * p.TW * cfg.halo_s + cfg.halo_x0, tile_y * p.TH * cfg.halo_s + cfg.halo_y0, img);
+          const int fx = (tile_x * p.TW * cfg.halo_s + cfg.halo_x0) * cfg.halo_ci;       // first flattened (w, c) element
+          const int hy = tile_y * p.TH * cfg.halo_s + cfg.halo_y0;
+          for (int b = 0; b < cfg.halo_nbox; ++b)
+            tma_load_3d(&maps.a[0], hfull_bar(hb), smem_base + halo_off + (uint32_t)(hb * cfg.halo_stride + b * cfg.halo_h * 512), fx + b * 256,
+                        hy, img);
         }
       } else {
       int s = 0; uint32_t ph = 0;
@@ -639,7 +653,7 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
     //      never straddles two taps).  lane = (rsub, j): a warp instruction moves the 8 chunks (128 contiguous bytes of the
     //      destination row) of 4 rows; the warp owns rows 32*pw .. +31. ----
     const int pw = warp - 10, j = lane & 7, rsub = lane >> 3;
-    const int Ci = cfg.halo_ci, Wh = cfg.halo_w, hs = cfg.halo_s;
+    const int Ci = cfg.halo_ci, hs = cfg.halo_s;
     // Producer warp pw builds the k blocks kb = pw, pw + 4, ... of every tile ALONE (all 128 rows, 32 warp instructions of
     // 4 rows x 8 chunks), so the four warps work on four different pipeline stages at once and every stage costs ONE
     // generic->async proxy fence and ONE barrier arrival (with all four warps on the same k block the per-block handshake
@@ -655,22 +669,25 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
         const uint32_t ph = (uint32_t)(q / STAGES) & 1u;
         const int k0 = kb * 64 + j * 8;
         int t = -1;
-        uint32_t toff = 0;
+        int tqh = 0, tf0 = 0;
         if (k0 < cfg.ktot) {
           const int slice = k0 / Ci, ci0 = k0 - slice * Ci;
           for (int qq = 0; qq < p.ntaps; ++qq) if (p.wt[qq] == slice) t = qq;      // tap that owns this weight slice (none: zeros)
-          if (t >= 0) toff = (uint32_t)(((p.qh[t] * Wh + p.qw[t]) * Ci + ci0) * 2);
+          if (t >= 0) { tqh = p.qh[t]; tf0 = p.qw[t] * Ci + ci0; }
         }
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t sa = smem_base + s * cfg.stage_bytes;
-        const uint32_t src0 = hbase + toff;
+        const int boxpitch = cfg.halo_h * 256;            // elements per staged box: [halo_h rows][256 flattened (w, c) elements]
 #pragma unroll 8
-        for (int it = 0; it < 32; ++it) {
+        for (int it = 0; it < ((cfg.dbg & 1) ? 0 : 32); ++it) {
           const int r = it * 4 + rsub;
           const int ty = r / kHaloTW, tx = r % kHaloTW;  // (the host fixes TH x TW = 8 x 16 in this mode)
+          // source pixel (ty*hs + qh, tx*hs + qw), channel ci0: flattened column f -> box f / 256, element f % 256 of row hy
+          const int f = tx * hs * Ci + tf0, hyy = ty * hs + tqh;
+          const uint32_t soff = (uint32_t)(((f >> 8) * boxpitch + hyy * 256 + (f & 255)) * 2);
           uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
           if (t >= 0) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
-                                   : "r"(src0 + (uint32_t)((ty * hs * Wh + tx * hs) * Ci * 2)));
+                                   : "r"(hbase + soff));
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + (uint32_t)r * 128u + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4)),
                        "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
         }
@@ -710,7 +727,8 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
             const uint64_t da = make_smem_desc(sa, 16, 1024);
             const uint64_t db = make_smem_desc(sb, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(acc, da + 2u * k, db + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              if (!(kHalo && (cfg.dbg & 2))) umma_bf16(acc, da + 2u * k, db + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
             if (cfg.wide) {
               // second N sub-tile: B rows bn_sub0.. of the same stage (row offset = bn_sub0 * 128 B, a multiple of 1024),
               // accumulator columns bn_sub0..BN-1
@@ -860,7 +878,7 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
           fence_proxy_async();
           epi_group_sync(grp);
           if (elected && c0 == 0) TC_TRACE(8);
-          if (elected) {
+          if (elected && !(kHalo && (cfg.dbg & 4))) {
             const uint32_t src = stg_s;
             if (p.accumulate) tma_reduce_add_4d(&maps.c, src, n0 + c0, tile_x * p.TW, tile_y * p.TH, img);
             else tma_store_4d(&maps.c, src, n0 + c0, tile_x * p.TW, tile_y * p.TH, img);
@@ -1474,7 +1492,9 @@ static bool plan_halo(const dc_conv_desc* d, const dc_view& in, const dc_view& o
   c.halo_h = (kHaloTH - 1) * s + (dh1 - dh0) + 1;
   c.halo_w = (kHaloTW - 1) * s + (dw1 - dw0) + 1;
   if (c.halo_h > 256 || c.halo_w > 256) return false;
-  c.halo_bytes = c.halo_h * c.halo_w * in.c * 2;
+  if (in.sw != in.c || in.sc != 1) return false;        // W and C must be one contiguous dimension (dense NHWC rows)
+  c.halo_nbox = ceil_div(c.halo_w * in.c, 256);
+  c.halo_bytes = c.halo_nbox * c.halo_h * 512;          // every box is charged in full (out-of-range parts are zero-filled)
   c.halo_stride = round_up_i(c.halo_bytes, 1024);
   c.ktot = d->wtaps * in.c;
   c.nkb = ceil_div(c.ktot, 64);
@@ -1492,6 +1512,14 @@ static bool plan_halo(const dc_conv_desc* d, const dc_view& in, const dc_view& o
   while (c.acc_stride < c.BN) c.acc_stride <<= 1;
   c.tmem_cols = 2 * c.acc_stride;
   c.tma_store = tma_store ? 1 : 0;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("DEEPCAM_B200_TC_HALO_DBG"); dbg = e ? atoi(e) : 0; }
+    c.dbg = dbg;
+    static int force_stages = -1;
+    if (force_stages < 0) { const char* e = getenv("DEEPCAM_B200_TC_HALO_STAGES"); force_stages = e ? atoi(e) : 0; }
+    if (force_stages >= 2 && force_stages <= c.stages) c.stages = force_stages;
+  }
   c.smem_bytes = c.stages * c.stage_bytes + c.bres_bytes + c.halo_bufs * c.halo_stride + kV2StagingBytes + 1024 + 256;
   return true;
 }
@@ -1500,11 +1528,13 @@ static bool plan_halo(const dc_conv_desc* d, const dc_view& in, const dc_view& o
 static int encode_halo_map(CUtensorMap* m, const dc_view& in, int halo_w, int halo_h, const char* what) {
   PFN_encodeTiled enc = get_encode();
   DC_REQUIRE(enc != nullptr, "%s: cuTensorMapEncodeTiled unavailable", what);
-  cuuint64_t dims[4] = {(cuuint64_t)in.c, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
-  cuuint64_t strides[3] = {(cuuint64_t)in.sw * 2, (cuuint64_t)in.sh * 2, (cuuint64_t)in.sn * 2};
-  cuuint32_t box[4] = {(cuuint32_t)in.c, (cuuint32_t)halo_w, (cuuint32_t)halo_h, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in.ptr), dims, strides, box, es,
+  (void)halo_w;
+  // {W * C, H, N}: a dense NHWC row is one contiguous run of W * C elements; boxes of 256 elements x halo_h rows
+  cuuint64_t dims[3] = {(cuuint64_t)in.w * (cuuint64_t)in.c, (cuuint64_t)in.h, (cuuint64_t)in.n};
+  cuuint64_t strides[2] = {(cuuint64_t)in.sh * 2, (cuuint64_t)in.sn * 2};
+  cuuint32_t box[3] = {256, (cuuint32_t)halo_h, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(in.ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DC_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(halo) failed with %d (C=%d box %dx%d)", what, (int)r, in.c, halo_w, halo_h);
