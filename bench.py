@@ -485,12 +485,13 @@ def run_ours(args):
         # per launch comes from the committed ncu --set full capture of the same shape (profiles/ncu_traffic.json)
         shapes_top = prof.by_tag({name})
         shape_name, shape_d = max(shapes_top.items(), key=lambda kv: kv[1]["ms"])
-        traffic = None
+        traffic = traffic_l2 = None
         try:
             with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as fh:
                 ent = json.load(fh).get(shape_name.replace(" +bnstats", ""))
             if ent:
                 traffic = ent["dram_bytes_per_launch"]
+                traffic_l2 = ent.get("l2_to_sm_bytes_per_launch")
         except Exception:
             traffic = None
         sec = d["ms"] / 1000.0
@@ -523,6 +524,7 @@ def run_ours(args):
                                   "class time = sum over shapes of launches x that duration")
         ssec = shape_d["ms"] / 1000.0
         roofline["traffic"] = traffic
+        roofline["traffic_l2_to_sm"] = traffic_l2      # l1tex__m_xbar2l1tex_read_bytes.sum of the same capture: what the SMs pulled from L2
         roofline["dominant_shape"] = dict(
             kernel=shape_name, launches_per_step=shape_d["launches"] / psteps, us_per_launch=1000.0 * shape_d["ms"] / shape_d["launches"],
             algorithmic_bytes_per_launch=shape_d["bytes"] / shape_d["launches"],
@@ -530,7 +532,9 @@ def run_ours(args):
             achieved_tflops=shape_d["flops"] / ssec / 1e12 if ssec > 0 else None,
             achieved_gbs=shape_d["bytes"] / ssec / 1e9 if ssec > 0 else None,
             traffic_note="`traffic` = dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this shape "
-                         "(cold caches; written lines still in L2 at kernel end are not counted by the counter)")
+                         "(cold caches; written lines still in L2 at kernel end are not counted by the counter, so it can read below "
+                         "the algorithmic bytes); `traffic_l2_to_sm` = L2->SM bytes of the same capture, the figure that shows operand "
+                         "re-fetch (4.1x the algorithmic bytes for the 728x728 layer: every CTA pulls its own copy of the weights)")
         roofline.update(peak_source=peaks["source"] + (" sustained" if name in tensor_kinds else " copy"),
                         launches_per_step=d["launches"] / psteps, avg_launch_us=1000.0 * d["ms"] / d["launches"],
                         class_ms_per_step=d["ms"] / psteps,
