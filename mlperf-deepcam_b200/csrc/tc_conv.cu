@@ -209,8 +209,18 @@ __device__ unsigned long long g_tc_trace[148 * 16];
 // (the "memory" clobber keeps the clock read on its side of barriers; a plain clock64() was hoisted above the final __syncthreads)
 #define TC_TRACE(slot) do { unsigned long long tc_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(tc_) :: "memory"); \
                             g_tc_trace[blockIdx.x * 16 + (slot)] = tc_; } while (0)
+// per-TILE timeline of CTA 0 in halo mode (tools/halo_trace.py): [tile < 32][slot]: 0 halo load issued, 1 producer warp 0 saw the
+// halo, 2 producer warp 0 done with the tile, 3 MMA lane owns the accumulator, 4 MMA lane committed the tile, 5 epilogue saw the
+// accumulator, 6 epilogue released it, 7 epilogue done with the tile
+__device__ unsigned long long g_halo_trace[32 * 8 + 8];      // + 8: phases of one k block of producer warp 0 in tile 6
+#define HALO_TRACE2(i, slot) do { if (blockIdx.x == 0 && (i) == 6 && pw == ((i) * cfg.nkb) % 4 && lane == 0) { unsigned long long tc_; \
+                                  asm volatile("mov.u64 %0, %%clock64;" : "=l"(tc_) :: "memory"); g_halo_trace[32 * 8 + (slot)] = tc_; } } while (0)
+#define HALO_TRACE(i, slot) do { if (blockIdx.x == 0 && (i) < 32) { unsigned long long tc_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(tc_) :: "memory"); \
+                                 g_halo_trace[(i) * 8 + (slot)] = tc_; } } while (0)
 #else
 #define TC_TRACE(slot) do { } while (0)
+#define HALO_TRACE(i, slot) do { } while (0)
+#define HALO_TRACE2(i, slot) do { } while (0)
 #endif
 
 constexpr int kTcThreads = 192;
@@ -516,8 +526,8 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   const uint32_t bres_bar = bar_base + 8u * (2 * STAGES + 4);
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 5);
-  auto hfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + b); };
-  auto hempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 8 + b); };
+  auto hfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + b); };      // up to 4 halo buffers
+  auto hempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 10 + b); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -534,7 +544,7 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }   // (halo: ONE producer warp builds a stage)
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), cfg.bm2 ? 16 : 8); }   // every epilogue warp of both groups arrives once per (sub-)tile
     mbar_init(bres_bar, 1);
-    if (kHalo) for (int b = 0; b < 2; ++b) { mbar_init(hfull_bar(b), 1); mbar_init(hempty_bar(b), 4); }
+    if (kHalo) for (int b = 0; b < 4; ++b) { mbar_init(hfull_bar(b), 1); mbar_init(hempty_bar(b), 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -603,6 +613,7 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
           mbar_expect_tx(hfull_bar(hb), cfg.halo_bytes);
           const int fx = (tile_x * p.TW * cfg.halo_s + cfg.halo_x0) * cfg.halo_ci;       // first flattened (w, c) element
           const int hy = tile_y * p.TH * cfg.halo_s + cfg.halo_y0;
+          HALO_TRACE(i, 0);
           for (int b = 0; b < cfg.halo_nbox; ++b)
             tma_load_3d(&maps.a[0], hfull_bar(hb), smem_base + halo_off + (uint32_t)(hb * cfg.halo_stride + b * cfg.halo_h * 512), fx + b * 256,
                         hy, img);
@@ -662,9 +673,13 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
     for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++i) {
       const int hb = i % cfg.halo_bufs;
       mbar_wait(hfull_bar(hb), (uint32_t)(i / cfg.halo_bufs) & 1u);
-      const uint32_t hbase = smem_base + halo_off + (uint32_t)(hb * cfg.halo_stride);
-      for (int kb = pw; kb < cfg.nkb; kb += 4) {
-        const int q = i * cfg.nkb + kb;                 // running k-block number of this CTA: stage and phase follow from it
+      if (pw == 0 && lane == 0) HALO_TRACE(i, 1);
+      const uint8_t* hptr = smem_gen + halo_off + (uint32_t)(hb * cfg.halo_stride);
+      // k block q (running number over this CTA's tiles) belongs to warp q % 4: five k blocks per tile then alternate between
+      // the warps instead of always giving warp 0 two of them
+      const int q0 = i * cfg.nkb;
+      for (int kb = ((pw - q0) % 4 + 4) % 4; kb < cfg.nkb; kb += 4) {
+        const int q = q0 + kb;                          // stage and phase follow from the running k-block number
         const int s = q % STAGES;
         const uint32_t ph = (uint32_t)(q / STAGES) & 1u;
         const int k0 = kb * 64 + j * 8;
@@ -675,28 +690,42 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
           for (int qq = 0; qq < p.ntaps; ++qq) if (p.wt[qq] == slice) t = qq;      // tap that owns this weight slice (none: zeros)
           if (t >= 0) { tqh = p.qh[t]; tf0 = p.qw[t] * Ci + ci0; }
         }
+        HALO_TRACE2(i, 0);
         mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t sa = smem_base + s * cfg.stage_bytes;
+        HALO_TRACE2(i, 1);
+        uint8_t* sptr = smem_gen + s * cfg.stage_bytes;
         const int boxpitch = cfg.halo_h * 256;            // elements per staged box: [halo_h rows][256 flattened (w, c) elements]
-#pragma unroll 8
-        for (int it = 0; it < ((cfg.dbg & 1) ? 0 : 32); ++it) {
-          const int r = it * 4 + rsub;
-          const int ty = r / kHaloTW, tx = r % kHaloTW;  // (the host fixes TH x TW = 8 x 16 in this mode)
-          // source pixel (ty*hs + qh, tx*hs + qw), channel ci0: flattened column f -> box f / 256, element f % 256 of row hy
-          const int f = tx * hs * Ci + tf0, hyy = ty * hs + tqh;
-          const uint32_t soff = (uint32_t)(((f >> 8) * boxpitch + hyy * 256 + (f & 255)) * 2);
-          uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-          if (t >= 0) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
-                                   : "r"(hbase + soff));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + (uint32_t)r * 128u + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4)),
-                       "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+        const int nit = (cfg.dbg & 1) ? 0 : 4;
+        // 4 batches of 8 warp instructions: eight independent 16-byte loads in flight, then their eight stores (a load -> store
+        // chain per row ran at ~100 clk per row, 1.6 us per k block: tools/halo_trace.py, round 2).
+        // row r = it*4 + rsub of the 8 x 16 tile: ty = it >> 2, tx = (it & 3)*4 + rsub; source pixel (ty*hs + qh, tx*hs + qw),
+        // channel ci0 -> flattened column f -> box f / 256, element f % 256 of row hy
+        for (int b8 = 0; b8 < nit; ++b8) {
+          uint4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int it = b8 * 8 + u;
+            const int ty = it >> 2, tx = (it & 3) * 4 + rsub;
+            const int f = tx * hs * Ci + tf0, hyy = ty * hs + tqh;
+            const int soff = ((f >> 8) * boxpitch + hyy * 256 + (f & 255)) * 2;
+            v[u] = (t >= 0) ? *reinterpret_cast<const uint4*>(hptr + soff) : make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int r = (b8 * 8 + u) * 4 + rsub;
+            *reinterpret_cast<uint4*>(sptr + r * 128 + ((j ^ (r & 7)) << 4)) = v[u];
+          }
         }
+        HALO_TRACE2(i, 2);
         fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core's async proxy
+        HALO_TRACE2(i, 3);
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(s));
+        HALO_TRACE2(i, 4);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(hempty_bar(hb));      // this warp has read the halo buffer for the last time
+      if (pw == 0 && lane == 0) HALO_TRACE(i, 2);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -713,6 +742,7 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
         const uint32_t par = single_acc ? ((uint32_t)i & 1u) : (((uint32_t)i >> 1) & 1u);
         mbar_wait(tempty_bar(buf), par ^ 1u);                            // epilogue has drained this accumulator
         tc_fence_after();
+        if (kHalo) HALO_TRACE(i, 3);
         const uint32_t acc = tmem_base + (uint32_t)(buf * cfg.acc_stride);
         int it = 0;
         const int nt_loop = kHalo ? 1 : p.ntaps, nk_loop = kHalo ? cfg.nkb : p.kblocks;     // halo: K is dense, nkb blocks in order
@@ -749,6 +779,7 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
         }
         umma_commit(tfull_bar(buf));
         TC_TRACE(3);
+        if (kHalo) HALO_TRACE(i, 4);
       }
     }
   } else if (warp >= 2) {
@@ -801,6 +832,7 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
         tc_fence_after();
         if (threadIdx.x == 64) TC_TRACE(4);
         if (threadIdx.x == 192) TC_TRACE(12);
+        if (kHalo && threadIdx.x == 64) HALO_TRACE(i, 5);
       }
       const uint32_t acc = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((cfg.bm2 ? sub : buf) * cfg.acc_stride);
       if (cfg.tma_store) {
@@ -826,6 +858,7 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
+            if (kHalo && threadIdx.x == 64) HALO_TRACE(i, 6);
           }
           // eval-mode BatchNorm folded into the epilogue: the group's first 64 threads derive scale / shift of the chunk's 64
           // columns from the running statistics (same arithmetic as the eval branch of bn_apply) into the group's 2 KB scratch
@@ -922,6 +955,7 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
             if (elected && c0 == 0) TC_TRACE(10);
           }
         }
+        if (kHalo && threadIdx.x == 64) HALO_TRACE(i, 7);
         continue;
       }
       if (grp == 1) {                       // generic (strided / fp32 / accumulating) epilogue: group A alone, per-warp staging
@@ -1505,7 +1539,14 @@ static bool plan_halo(const dc_conv_desc* d, const dc_view& in, const dc_view& o
   c.stage_bytes = kABytes;
   const int fixed = 1024 + 256 + kV2StagingBytes + c.bres_bytes;
   if (227 * 1024 - fixed - 3 * c.stage_bytes < c.halo_stride) return false;
-  c.halo_bufs = (227 * 1024 - fixed - 4 * c.stage_bytes >= 2 * c.halo_stride) ? 2 : 1;
+  // halo buffers = tiles of prefetch distance: the load for tile i + bufs is issued when the producers leave tile i, and a
+  // load takes 0.8-1.2 us (tools/halo_trace.py), about as long as the producers spend on a tile: up to 4, at least 1
+  c.halo_bufs = std::max(1, std::min(4, (227 * 1024 - fixed - 4 * c.stage_bytes) / c.halo_stride));
+  {
+    static int force_bufs = -1;
+    if (force_bufs < 0) { const char* e = getenv("DEEPCAM_B200_TC_HALO_BUFS"); force_bufs = e ? atoi(e) : 0; }
+    if (force_bufs >= 1 && force_bufs <= c.halo_bufs) c.halo_bufs = force_bufs;
+  }
   // the four producer warps fill four stages at once: as many stages as fit (4..8), never fewer than 3
   c.stages = std::max(3, std::min(8, (227 * 1024 - fixed - c.halo_bufs * c.halo_stride) / c.stage_bytes));
   c.acc_stride = 32;
@@ -1651,6 +1692,10 @@ static int conv_gemm_tc_impl(const dc_conv_desc* d, dc_view in, const void* w, c
 
 #ifdef DC_TC_TRACE
 // trace build only (tools/tc_trace.py): copies the 148 x 16 timestamp table to the host
+int dc_halo_trace_read(unsigned long long* host) {
+  cudaError_t e = cudaMemcpyFromSymbol(host, g_halo_trace, sizeof(unsigned long long) * (32 * 8 + 8));
+  return e == cudaSuccess ? 0 : (int)e;
+}
 int dc_tc_trace_read(unsigned long long* host) {
   cudaError_t e = cudaMemcpyFromSymbol(host, g_tc_trace, sizeof(unsigned long long) * 148 * 16);
   return e == cudaSuccess ? 0 : (int)e;
