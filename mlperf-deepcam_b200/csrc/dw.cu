@@ -883,6 +883,104 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_s1d1_kernel(DwView<c
   dw_reduce_G<V>(G, Gout, C, m, blockIdx.y * m.cvp, tap_stride, c_stride);
 }
 
+// ---- stride 2, dilation 1 backward-data, staged (the last separable unit of blocks 1-3, DX:99-101) ------------------------------
+// out[y,x] = sum in[2y-1+kh, 2x-1+kw] * w[kh][kw], so every dout pixel (y, x) owns the 2 x 2 input quad (2y.., 2x..):
+//   din[2y  , 2x  ] = d[y,x] w11
+//   din[2y  , 2x+1] = d[y,x] w12 + d[y,x+1] w10
+//   din[2y+1, 2x  ] = d[y,x] w21 + d[y+1,x] w01
+//   din[2y+1, 2x+1] = d[y,x] w22 + d[y,x+1] w20 + d[y+1,x] w02 + d[y+1,x+1] w00
+// A block stages its dout tile (one halo row below, one halo column right, zero outside) with cp.async copies that are all in
+// flight at once; a thread (channel vector, dout column) walks down the rows keeping d[y][x], d[y][x+1] in registers and writes
+// the quad's four 16-byte vectors.  The gather-form dw_bwd_data_strided_kernel it replaces ran at 1.1 TB/s on the 113 MB
+// gradient of block1 (124 us): per input pixel it tested nine taps for parity and issued dependent global loads.
+template <typename T, int V>
+__global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_data_s2_tile_kernel(DwView<const T> dout, const T* __restrict__ w9c, DwView<T> din,
+                                                                           int C, DwMap m, int accumulate) {
+  constexpr int VP = V / 2;
+  extern __shared__ uint4 dw_tile[];                  // [rs + 1][ppb + 1][cvp]
+  const DwLane l = dw_lane(m, dout.h, dout.w);        // rows / columns of dout
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
+  const int TW = m.ppb + 1;
+  const int nrows = (l.y1 - l.y0) + 1;                // dout rows y0 .. y1 (y1 = halo)
+  const int x0 = blockIdx.x * m.ppb;
+  const int cv0 = blockIdx.y * m.cvp;
+  const int Ho = dout.h, Wo = dout.w;
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(dw_tile);
+  const int cshift = 31 - __clz(m.cvp);
+  pdl_sync();
+  {
+    const T* nbase = dout.p + dout.img(l.n);
+    const int nvec = nrows * TW * m.cvp;
+    const int cl = threadIdx.x & (m.cvp - 1), cvi = cv0 + cl;
+    const int pstep = kDwThreads >> cshift;
+    int ty = (threadIdx.x >> cshift) / TW, tx = (threadIdx.x >> cshift) - ty * TW;
+    for (int i = threadIdx.x; i < nvec; i += kDwThreads) {
+      const int gy = l.y0 + ty, gx = x0 + tx;
+      const bool ok = gy < Ho && gx < Wo && cvi < m.cv;
+      cp_async16_zfill(tile_s + (uint32_t)i * 16u, ok ? nbase + (long long)gy * dout.sh + (long long)gx * dout.sw + cvi * V : dout.p, ok);
+      tx += pstep;
+      while (tx >= TW) { tx -= TW; ++ty; }
+    }
+  }
+  float2 wv[9][VP];
+  if (l.ok) {
+    const int c0 = l.cvi * V;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dwpair<T>::unpack(ld16(w9c + (size_t)k * C + c0), wv[k]);
+  }
+  cp_async_commit_wait_all();
+  __syncthreads();
+  if (!l.ok) return;
+  const int H = din.h, W = din.w;
+  const int ix = 2 * l.x;
+  T* ibase = din.p + din.img(l.n) + (long long)ix * din.sw + l.cvi * V;
+  const bool x1ok = ix + 1 < W;
+  const uint4* tp = dw_tile + ((warp * m.ppw + psub) * m.cvp + cvl);      // tile column of x, row 0
+  const int rstride = TW * m.cvp;
+  float2 a[VP], b[VP];                                // d[y][x], d[y][x+1]
+  dwpair<T>::unpack(tp[0], a);
+  dwpair<T>::unpack(tp[m.cvp], b);
+  auto put = [&](T* dst, float2 (&v)[VP]) {
+    if (accumulate) {
+      float2 old[VP];
+      dwpair<T>::unpack(ld16(dst), old);
+#pragma unroll
+      for (int j = 0; j < VP; ++j) { v[j].x += old[j].x; v[j].y += old[j].y; }
+    }
+    st16(dst, dwpair<T>::pack(v));
+  };
+  for (int ty = 0; ty + 1 < nrows; ++ty) {
+    float2 c[VP], d[VP];                              // d[y+1][x], d[y+1][x+1]
+    dwpair<T>::unpack(tp[(ty + 1) * rstride], c);
+    dwpair<T>::unpack(tp[(ty + 1) * rstride + m.cvp], d);
+    const int iy = 2 * (l.y0 + ty);
+    T* r0 = ibase + (long long)iy * din.sh;
+    float2 o[VP];
+#pragma unroll
+    for (int j = 0; j < VP; ++j) o[j] = mul2(a[j], wv[4][j]);
+    put(r0, o);
+    if (x1ok) {
+#pragma unroll
+      for (int j = 0; j < VP; ++j) o[j] = fma2(b[j], wv[3][j], mul2(a[j], wv[5][j]));
+      put(r0 + din.sw, o);
+    }
+    if (iy + 1 < H) {
+      T* r1 = r0 + din.sh;
+#pragma unroll
+      for (int j = 0; j < VP; ++j) o[j] = fma2(c[j], wv[1][j], mul2(a[j], wv[7][j]));
+      put(r1, o);
+      if (x1ok) {
+#pragma unroll
+        for (int j = 0; j < VP; ++j) o[j] = fma2(d[j], wv[0][j], fma2(c[j], wv[2][j], fma2(b[j], wv[6][j], mul2(a[j], wv[8][j]))));
+        put(r1 + din.sw, o);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VP; ++j) { a[j] = c[j]; b[j] = d[j]; }
+  }
+}
+
 // ---- stride-1 weight gradient, staged + cluster-reduced ------------------------------------------------------------------
 // dw_bwd_weight_s1d1_kernel above walks its strip with one row of global loads in flight per thread (a chain of rs + 2
 // dependent L2 round trips: 11.5 of its 15.3 us on the 10 MB middle-flow tensors, tools/kbench.py) and every block then issues
@@ -1219,8 +1317,26 @@ static int dw_bwd_data_t(const dc_view& dout, const void* w, int s, int d, const
     launch_k(dw_s1d1_kernel<T, V>, grid, dim3(kDwThreads), (size_t)0, st, dw_view<const T>(dout), (const T*)w, dw_view<T>(din), din.c, m, 1, acc);
   else if (s == 1)
     launch_k(dw_direct_kernel<T, V>, grid, dim3(kDwThreads), (size_t)0, st, dw_view<const T>(dout), (const T*)w, dw_view<T>(din), din.c, m, 1, d, 1, acc);
-  else
+  else {
+    static int s2_tile = -1;      // DEEPCAM_B200_DW_S2_TILE=0: gather-form kernel (A/B measurements)
+    if (s2_tile < 0) { const char* e = getenv("DEEPCAM_B200_DW_S2_TILE"); s2_tile = (e && e[0] == '0') ? 0 : 1; }
+    if (s == 2 && d == 1 && s2_tile && dout.h == (din.h - 1) / 2 + 1 && dout.w == (din.w - 1) / 2 + 1) {
+      DwMap mt = dw_map(dout.c, V, dout.h, dout.w, dout.n, 1 << 30, 8);       // strips of >= 8 dout rows
+      mt.nstrips = ceil_div(dout.h, 16);
+      mt.rs = ceil_div(dout.h, mt.nstrips);
+      mt.nstrips = ceil_div(dout.h, mt.rs);
+      const size_t smem = (size_t)(mt.rs + 1) * (mt.ppb + 1) * mt.cvp * 16;
+      static bool attr_set = false;
+      if (!attr_set && cudaFuncSetAttribute(dw_bwd_data_s2_tile_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) == cudaSuccess)
+        attr_set = true;
+      if (attr_set && smem <= 110 * 1024) {
+        launch_k(dw_bwd_data_s2_tile_kernel<T, V>, dw_grid(mt, dout.w, dout.n), dim3(kDwThreads), smem, st, dw_view<const T>(dout), (const T*)w,
+                 dw_view<T>(din), din.c, mt, acc);
+        return launch_status("dc_dw_bwd_data");
+      }
+    }
     launch_k(dw_bwd_data_strided_kernel<T, V>, grid, dim3(kDwThreads), (size_t)0, st, dw_view<const T>(dout), (const T*)w, dw_view<T>(din), din.c, m, s, d, acc);
+  }
   return launch_status("dc_dw_bwd_data");
 }
 template <typename T>
