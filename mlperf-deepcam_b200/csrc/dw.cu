@@ -1005,15 +1005,18 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_saddr, uint32_t ran
 
 template <typename T, int V>
 __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwView<const T> in, DwView<const T> dout, float* __restrict__ Gout,
-                                                                          int C, DwMap m, int tap_stride, int c_stride) {
+                                                                          int C, DwMap m, int tap_stride, int c_stride, int spc) {
   constexpr int VP = V / 2;
   extern __shared__ uint4 dww_smem[];                 // in tile [rs + 2][ppb + 2][cvp] | dout tile [rs][ppb][cvp]   (then reused)
-  const DwLane l = dw_lane(m, dout.h, dout.w);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
   const int TW = m.ppb + 2;
-  const int orows = l.y1 - l.y0, nrows = orows + 2;   // dout rows y0 .. y1-1, input rows y0-1 .. y1
-  const int x0 = blockIdx.x * m.ppb, x_base = x0 - 1, y_base = l.y0 - 1;
+  // blockIdx.z = (virtual image, chunk of `spc` consecutive strips): a block walks its strips one after the other and keeps the
+  // 9 x V partial sums in registers, so the block reduction + cluster reduction + atomics are paid once per `spc` strips (the
+  // 113 MB entry-flow tensors would otherwise pay them 2808 times for 160-pixel tiles)
+  const int nchunks = (m.nstrips + spc - 1) / spc;
+  const int vn = blockIdx.z / nchunks, chunk = blockIdx.z - vn * nchunks;
+  const int x0 = blockIdx.x * m.ppb, x_base = x0 - 1;
   const int cv0 = blockIdx.y * m.cvp;
   const int H = in.h, W = in.w;
   uint4* in_t = dww_smem;
@@ -1021,77 +1024,84 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwVie
   const int cshift = 31 - __clz(m.cvp);
   const int cl = threadIdx.x & (m.cvp - 1), cvi_f = cv0 + cl;
   const int pstep = kDwThreads >> cshift;
-  pdl_sync();
-  {
-    const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(in_t);
-    const T* nbase = in.p + in.img(l.n);
-    const int nvec = nrows * TW * m.cvp;
-    int ty = (threadIdx.x >> cshift) / TW, tx = (threadIdx.x >> cshift) - ty * TW;
-    for (int i = threadIdx.x; i < nvec; i += kDwThreads) {
-      const int gy = y_base + ty, gx = x_base + tx;
-      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W && cvi_f < m.cv;
-      cp_async16_zfill(in_s + (uint32_t)i * 16u, ok ? nbase + (long long)gy * in.sh + (long long)gx * in.sw + cvi_f * V : in.p, ok);
-      tx += pstep;
-      if (tx >= TW) { tx -= TW; ++ty; }
-    }
-    const uint32_t g_s = (uint32_t)__cvta_generic_to_shared(g_t);
-    const T* gbase = dout.p + dout.img(l.n);
-    const int gvec = orows * m.ppb * m.cvp;
-    ty = (threadIdx.x >> cshift) / m.ppb; tx = (threadIdx.x >> cshift) - ty * m.ppb;
-    for (int i = threadIdx.x; i < gvec; i += kDwThreads) {
-      const int gy = l.y0 + ty, gx = x0 + tx;
-      const bool ok = gx < dout.w && cvi_f < m.cv;
-      cp_async16_zfill(g_s + (uint32_t)i * 16u, ok ? gbase + (long long)gy * dout.sh + (long long)gx * dout.sw + cvi_f * V : dout.p, ok);
-      tx += pstep;
-      while (tx >= m.ppb) { tx -= m.ppb; ++ty; }
-    }
-  }
   float2 G2[9][VP];
 #pragma unroll
   for (int k = 0; k < 9; ++k)
 #pragma unroll
     for (int j = 0; j < VP; ++j) G2[k][j] = make_float2(0.f, 0.f);
-  cp_async_commit_wait_all();
-  __syncthreads();
-  {
-    // thread = (channel vector cvl, pixel column col of the block); input-stationary walk over the staged rows:
-    // input row r meets dout rows r+1 (filter row 0), r (row 1), r-1 (row 2)
-    const int col = warp * m.ppw + psub;
-    const uint4* ip = in_t + (col * m.cvp + cvl);                       // tile column of x-1, row 0
-    const uint4* gp = g_t + (col * m.cvp + cvl);
-    const int irs = TW * m.cvp, grs = m.ppb * m.cvp;
-    auto step = [&](int ty, const float2 (&gM)[VP], const float2 (&gC)[VP], float2 (&gP)[VP]) {
-      // ty = input tile row (input row y0-1+ty); gP <- dout row y0+ty (tile row ty), zero past the strip
-      float2 f[3][VP];
-      const uint4* rp = ip + ty * irs;
-      dwpair<T>::unpack(rp[0], f[0]);
-      dwpair<T>::unpack(rp[m.cvp], f[1]);
-      dwpair<T>::unpack(rp[2 * m.cvp], f[2]);
-      if (ty < orows) dwpair<T>::unpack(gp[ty * grs], gP);
-      else {
-#pragma unroll
-        for (int j = 0; j < VP; ++j) gP[j] = make_float2(0.f, 0.f);
+  pdl_sync();
+  const int strip_end = min(m.nstrips, (chunk + 1) * spc);
+  for (int strip = chunk * spc; strip < strip_end; ++strip) {
+    const int y0 = strip * m.rs, y1 = min(dout.h, y0 + m.rs);
+    const int orows = y1 - y0, nrows = orows + 2;     // dout rows y0 .. y1-1, input rows y0-1 .. y1
+    const int y_base = y0 - 1;
+    if (strip != chunk * spc) __syncthreads();        // the previous strip's walk is over: its tiles may be overwritten
+    {
+      const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(in_t);
+      const T* nbase = in.p + in.img(vn);
+      const int nvec = nrows * TW * m.cvp;
+      int ty = (threadIdx.x >> cshift) / TW, tx = (threadIdx.x >> cshift) - ty * TW;
+      for (int i = threadIdx.x; i < nvec; i += kDwThreads) {
+        const int gy = y_base + ty, gx = x_base + tx;
+        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W && cvi_f < m.cv;
+        cp_async16_zfill(in_s + (uint32_t)i * 16u, ok ? nbase + (long long)gy * in.sh + (long long)gx * in.sw + cvi_f * V : in.p, ok);
+        tx += pstep;
+        if (tx >= TW) { tx -= TW; ++ty; }
       }
+      const uint32_t g_s = (uint32_t)__cvta_generic_to_shared(g_t);
+      const T* gbase = dout.p + dout.img(vn);
+      const int gvec = orows * m.ppb * m.cvp;
+      ty = (threadIdx.x >> cshift) / m.ppb; tx = (threadIdx.x >> cshift) - ty * m.ppb;
+      for (int i = threadIdx.x; i < gvec; i += kDwThreads) {
+        const int gy = y0 + ty, gx = x0 + tx;
+        const bool ok = gx < dout.w && cvi_f < m.cv;
+        cp_async16_zfill(g_s + (uint32_t)i * 16u, ok ? gbase + (long long)gy * dout.sh + (long long)gx * dout.sw + cvi_f * V : dout.p, ok);
+        tx += pstep;
+        while (tx >= m.ppb) { tx -= m.ppb; ++ty; }
+      }
+    }
+    cp_async_commit_wait_all();
+    __syncthreads();
+    {
+      // thread = (channel vector cvl, pixel column col of the block); input-stationary walk over the staged rows:
+      // input row r meets dout rows r+1 (filter row 0), r (row 1), r-1 (row 2)
+      const int col = warp * m.ppw + psub;
+      const uint4* ip = in_t + (col * m.cvp + cvl);                       // tile column of x-1, row 0
+      const uint4* gp = g_t + (col * m.cvp + cvl);
+      const int irs = TW * m.cvp, grs = m.ppb * m.cvp;
+      auto step = [&](int ty, const float2 (&gM)[VP], const float2 (&gC)[VP], float2 (&gP)[VP]) {
+        // ty = input tile row (input row y0-1+ty); gP <- dout row y0+ty (tile row ty), zero past the strip
+        float2 f[3][VP];
+        const uint4* rp = ip + ty * irs;
+        dwpair<T>::unpack(rp[0], f[0]);
+        dwpair<T>::unpack(rp[m.cvp], f[1]);
+        dwpair<T>::unpack(rp[2 * m.cvp], f[2]);
+        if (ty < orows) dwpair<T>::unpack(gp[ty * grs], gP);
+        else {
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-        for (int j = 0; j < VP; ++j) {
-          G2[kw][j] = fma2(f[kw][j], gP[j], G2[kw][j]);
-          G2[3 + kw][j] = fma2(f[kw][j], gC[j], G2[3 + kw][j]);
-          G2[6 + kw][j] = fma2(f[kw][j], gM[j], G2[6 + kw][j]);
+          for (int j = 0; j < VP; ++j) gP[j] = make_float2(0.f, 0.f);
         }
-    };
-    float2 g0[VP], g1[VP], g2[VP];
 #pragma unroll
-    for (int j = 0; j < VP; ++j) { g0[j] = make_float2(0.f, 0.f); g1[j] = g0[j]; g2[j] = g0[j]; }
-    int ty = 0;
-    while (true) {
-      step(ty, g0, g1, g2);
-      if (++ty >= nrows) break;
-      step(ty, g1, g2, g0);
-      if (++ty >= nrows) break;
-      step(ty, g2, g0, g1);
-      if (++ty >= nrows) break;
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int j = 0; j < VP; ++j) {
+            G2[kw][j] = fma2(f[kw][j], gP[j], G2[kw][j]);
+            G2[3 + kw][j] = fma2(f[kw][j], gC[j], G2[3 + kw][j]);
+            G2[6 + kw][j] = fma2(f[kw][j], gM[j], G2[6 + kw][j]);
+          }
+      };
+      float2 g0[VP], g1[VP], g2[VP];
+#pragma unroll
+      for (int j = 0; j < VP; ++j) { g0[j] = make_float2(0.f, 0.f); g1[j] = g0[j]; g2[j] = g0[j]; }
+      int ty = 0;
+      while (true) {
+        step(ty, g0, g1, g2);
+        if (++ty >= nrows) break;
+        step(ty, g1, g2, g0);
+        if (++ty >= nrows) break;
+        step(ty, g2, g0, g1);
+        if (++ty >= nrows) break;
+      }
     }
   }
   __syncthreads();                                    // tiles are dead: their memory becomes the reduction scratch
@@ -1368,7 +1378,12 @@ static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d,
       if (!attr_set) {
         if (cudaFuncSetAttribute(dw_bwd_weight_tile_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) == cudaSuccess) attr_set = true;
       }
-      dim3 grid = dw_grid(m, gw, gn);
+      // strips per block: one for the 48-row tensors (270 blocks = one wave); the large entry-flow / decoder tensors get
+      // several strips per block so that ~600 blocks walk the tensor and reduce once each
+      const long long nblk1 = (long long)ceil_div(gw, m.ppb) * m.gy * gn * m.nstrips;
+      const int spc = (int)std::min<long long>(m.nstrips, std::max<long long>(1, nblk1 / 592));
+      const int nchunks = ceil_div(m.nstrips, spc);
+      dim3 grid((unsigned)ceil_div(gw, m.ppb), (unsigned)m.gy, (unsigned)(gn * nchunks));
       if (attr_set) {
         // cluster = consecutive blockIdx.z (strips / images / parity sub-grids of one (x block, channel group)): largest divisor <= 8
         for (int cz = 8; cz >= 1; --cz) {
@@ -1383,7 +1398,7 @@ static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d,
           cfg.attrs = attr;
           cfg.numAttrs = pdl_enabled() ? 2 : 1;
           cudaError_t e = cudaLaunchKernelEx(&cfg, dw_bwd_weight_tile_kernel<T, V>, dw_view<const T>(in, dsub), dw_view<const T>(dout, dsub), G, dout.c, m,
-                                             tap_stride, c_stride);
+                                             tap_stride, c_stride, spc);
           if (e == cudaSuccess) return launch_status("dc_dw_bwd_weight");
           cudaGetLastError();                          // this cluster size cannot be scheduled here: try the next divisor
         }
