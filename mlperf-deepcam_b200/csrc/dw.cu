@@ -1361,6 +1361,10 @@ static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d,
   const int dsub = dw_dsub(s, d, dout.h, dout.w);
   const int gh = dsub >= 1 ? dout.h / dsub : dout.h, gw = dsub >= 1 ? dout.w / dsub : dout.w;
   const int gn = dsub >= 1 ? dout.n * dsub * dsub : dout.n;
+  {
+    static int noat = -1;
+    if (noat < 0) { const char* e = getenv("DEEPCAM_B200_DWW_NOATOMIC"); noat = (e && e[0] == '1') ? 1 : 0; if (noat) cudaMemcpyToSymbol(g_dww_noatomic, &noat, sizeof(int)); }
+  }
   static int tile_on = -1;        // DEEPCAM_B200_DWW_TILE=0: the register-pipelined kernel (A/B measurements)
   if (tile_on < 0) { const char* e = getenv("DEEPCAM_B200_DWW_TILE"); tile_on = (e && e[0] == '0') ? 0 : 1; }
   if (dsub >= 1 && tile_on) {
@@ -1386,7 +1390,9 @@ static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d,
       dim3 grid((unsigned)ceil_div(gw, m.ppb), (unsigned)m.gy, (unsigned)(gn * nchunks));
       if (attr_set) {
         // cluster = consecutive blockIdx.z (strips / images / parity sub-grids of one (x block, channel group)): largest divisor <= 8
-        for (int cz = 8; cz >= 1; --cz) {
+        static int cz_max = -1;         // DEEPCAM_B200_DWW_CLUSTER: largest cluster size tried (1 = no cluster reduction)
+        if (cz_max < 0) { const char* e = getenv("DEEPCAM_B200_DWW_CLUSTER"); cz_max = e ? std::max(1, std::min(8, atoi(e))) : 8; }
+        for (int cz = cz_max; cz >= 1; --cz) {
           if (grid.z % cz) continue;
           cudaLaunchConfig_t cfg = {};
           cfg.gridDim = grid; cfg.blockDim = dim3(kDwThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -1408,10 +1414,6 @@ static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d,
   DwMap m = dw_map(dout.c, V, gh, gw, gn, kNumSMs * tb_mult, min_rows);
   dim3 grid = dw_grid(m, gw, gn);
   const size_t smem = (size_t)8 * 32 * 3 * V * sizeof(float);
-  {
-    static int noat = -1;
-    if (noat < 0) { const char* e = getenv("DEEPCAM_B200_DWW_NOATOMIC"); noat = (e && e[0] == '1') ? 1 : 0; if (noat) cudaMemcpyToSymbol(g_dww_noatomic, &noat, sizeof(int)); }
-  }
   if (dsub >= 1)
     launch_k(dw_bwd_weight_s1d1_kernel<T, V>, grid, dim3(kDwThreads), (size_t)smem, st, dw_view<const T>(in, dsub), dw_view<const T>(dout, dsub), G,
              dout.c, m, tap_stride, c_stride);

@@ -5,6 +5,7 @@
 # judged into profiles/.
 #   gpurun --gpus 8 --timeout 1500 -- 'bash tools/multi_gpu_suite.sh r02'
 TAG=${1:-rNN}
+SHORT=${2:-}          # "short": DDP parity + the N = 1 / 2 / 4 / 8 bench lines + eval at N = 8, no sweep
 OUT=gpurun_out
 mkdir -p $OUT
 run() { # nproc, extra args...
@@ -12,9 +13,11 @@ run() { # nproc, extra args...
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $n "$@" 2>>$OUT/${TAG}_multi.err
 }
 python -m pytest tests/test_parallel_nccl_gpu.py -m gpu -q -p no:cacheprovider > $OUT/${TAG}_ddp_test.log 2>&1; tail -3 $OUT/${TAG}_ddp_test.log
+python bench.py --steps 20 --warmup 5 --no-profile --no-cpu-baseline --no-gpu-baseline > $OUT/${TAG}_bench_1gpu_samebox.json 2>>$OUT/${TAG}_multi.err
 for n in 2 4 8; do run $n --steps 20 --warmup 5 --no-profile > $OUT/${TAG}_bench_${n}gpu.json; done
 run 8 --mode eval --eval-samples 64 > $OUT/${TAG}_eval_8gpu.json
 python bench.py --mode eval --eval-samples 64 > $OUT/${TAG}_eval_1gpu.json 2>>$OUT/${TAG}_multi.err
+if [ "$SHORT" = "short" ]; then for f in $OUT/${TAG}_bench_*gpu*.json $OUT/${TAG}_eval_*gpu.json; do echo "== $f"; cut -c1-200 $f; done; exit 0; fi
 : > $OUT/${TAG}_sweep_lars.jsonl
 for b in 1 4 8; do run 8 --steps 10 --warmup 3 --no-profile --optimizer lars --local-batch $b >> $OUT/${TAG}_sweep_lars.jsonl; done
 run 8 --steps 10 --warmup 3 --no-profile --optimizer lars --local-batch 2 >> $OUT/${TAG}_sweep_lars.jsonl
