@@ -90,6 +90,15 @@ int         dc_device_supports_tcgen05(void);
  * of kernel N; results are identical to plain stream order).  Default on; DEEPCAM_B200_PDL=0 or dc_set_pdl(0) = off. */
 int         dc_set_pdl(int on);
 int         dc_get_pdl(void);
+/* Deterministic mode (what `torch.use_deterministic_algorithms(True)` asks of the cuDNN path the reference runs on,
+ * train_hdf5_ddp.py:345-364 being the same step): kernels that split a reduction over blocks and need no workspace switch to their
+ * single-writer form (dc_reduce_hw / dc_gap_fwd: one block per channel chunk and image).  The weight-gradient kernels have explicit
+ * two-stage entry points below (dc_conv_wgrad_tc_det, dc_conv_wgrad_simt_det, dc_dw_bwd_weight_det) that take a workspace: every
+ * split stores its partial result into its own slice and a second launch adds the slices in slice order, so two runs on the same
+ * inputs give bit-identical gradients.  The BatchNorm batch sums stay fp64 atomics of fp32 partial sums (order effects ~1e-16,
+ * below the fp32 rounding of the statistics derived from them). */
+int         dc_set_deterministic(int on);
+int         dc_get_deterministic(void);
 
 /* ---- layout / packing ------------------------------------------------------ */
 /* Generic strided copy with dtype conversion, dst[n,h,w,c] = src[n,h,w,c] for c < src.c;
@@ -141,6 +150,10 @@ int dc_conv_gemm_simt(const dc_conv_desc* d, dc_view in, const void* w, const fl
                       dc_view out, void* stream);
 /* SIMT weight gradient: G[wt[t]][co][ci] += sum_m in[pix(m,t), ci] * dout[m, co]; G fp32, pre-zeroed by caller. */
 int dc_conv_wgrad_simt(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, void* stream);
+/* Deterministic two-stage form.  ws: fp32 workspace of at least dc_conv_wgrad_simt_ws_elems() elements (0 = the launch does not
+ * split the pixel reduction and ws may be null; -1 = bad arguments), 16-byte aligned, contents irrelevant on entry. */
+long long dc_conv_wgrad_simt_ws_elems(const dc_conv_desc* d, dc_view in, dc_view dout);
+int dc_conv_wgrad_simt_det(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, float* ws, long long ws_elems, void* stream);
 
 /* tcgen05/TMEM/TMA implicit GEMM, bf16 operands, fp32 accumulation (sm_100a only).
  * `w` is DC_PACK_NTK bf16 with k_pad = round_up(in.c, 64).  in.c % 8 == 0, strides 16-byte aligned. */
@@ -166,6 +179,10 @@ int dc_conv_gemm_tc_bn_eval(const dc_conv_desc* d, dc_view in, const void* w, co
                             const float* beta, const float* running_mean, const float* running_var, float eps, int relu, void* stream);
 /* tcgen05 weight gradient (both operands pixel-major): same contract as dc_conv_wgrad_simt. */
 int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, void* stream);
+/* Deterministic two-stage form (TMA stores of the per-split partial tiles into ws[split][wtaps][Co][Ci] instead of TMA reduce-add
+ * into G, then one launch that adds the slices to G in split order); same workspace contract as dc_conv_wgrad_simt_det. */
+long long dc_conv_wgrad_tc_ws_elems(const dc_conv_desc* d, dc_view in, dc_view dout);
+int dc_conv_wgrad_tc_det(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, float* ws, long long ws_elems, void* stream);
 
 /* ---- depthwise 3x3 (SeparableConv2d_same.conv1 + fixed_padding, DX:45-51, 58-59, 63-64) --------- */
 /* out[n,y,x,c] = sum_{kh,kw} in[n, y*stride - dil + kh*dil, x*stride - dil + kw*dil, c] * w[kh*3+kw][c] */
@@ -174,6 +191,11 @@ int dc_dw_bwd_data(dc_view dout, const void* w9c, int stride, int dil, dc_view d
 /* fp32 gradient accumulated with atomics into a pre-zeroed buffer: param_layout = 0 -> G[9][C] (tap-major scratch),
  * param_layout = 1 -> the parameter's own [C][1][3][3] layout (no unpack needed afterwards) */
 int dc_dw_bwd_weight(dc_view in, dc_view dout, int stride, int dil, float* G9c, int param_layout, void* stream);
+/* Deterministic two-stage form: every block (cluster) stores its 9 x C partial sums into its own slice of ws (fp32,
+ * dc_dw_bwd_weight_ws_elems() elements, contents irrelevant on entry), a second launch adds the slices to G9c in slice order. */
+long long dc_dw_bwd_weight_ws_elems(dc_view in, dc_view dout, int stride, int dil);
+int dc_dw_bwd_weight_det(dc_view in, dc_view dout, int stride, int dil, float* G9c, int param_layout, float* ws, long long ws_elems,
+                         void* stream);
 /* Backward-data of a stride-1 dilation-1 depthwise conv whose INPUT is a BatchNorm output a = relu(bn(y) [+ residual])
  * (the ReLU -> depthwise chain of every Block, DX:79-97): this call must be the LAST writer of dL/da.  It stores
  * g = (dL/da, plus the already stored part when accumulate) masked by a > 0 into `din`, and adds per channel sum(g) and

@@ -206,4 +206,13 @@ __device__ __forceinline__ void reduce_to_ws(float (&acc)[NACC][V], double* dst,
 }
 
 
+// ---- deterministic two-stage reductions (dc_*_det entry points, dc_set_deterministic) --------------------------------------------
+// A split reduction stores the partial result of split z into slice z of a workspace (one writer per element); this launch then
+// adds the slices to the destination in slice order: dst[wt * per_tap + i] += sum_z ws[z * slice_stride + wt * per_tap + i] for the
+// weight taps of the call.  Same summation order on every run, whatever order the splits finished in.
+struct SplitReduceTaps { int n; int wt[DC_MAX_TAPS]; };
+int launch_split_reduce(const float* ws, int nslices, long long slice_stride, const SplitReduceTaps& taps, long long per_tap, float* dst,
+                        cudaStream_t st);
+bool deterministic();          // dc_set_deterministic(): kernels that need no workspace pick their single-writer form
+
 }  // namespace dc

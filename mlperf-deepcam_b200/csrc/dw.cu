@@ -771,7 +771,10 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_data_strided_kernel(DwView<
 __device__ int g_dww_noatomic = 0;      // experiment knob (DEEPCAM_B200_DWW_NOATOMIC=1, results are garbage): time without the atomics
 template <int V>
 __device__ __forceinline__ void dw_reduce_G(float (&G)[9][V], float* __restrict__ Gout, int C, const DwMap& m, int cvi_base,
-                                            int tap_stride, int c_stride) {
+                                            int tap_stride, int c_stride, int det) {
+  // det (dc_dw_bwd_weight_det): Gout is a workspace [slices][9][C]; this block STORES its sums into slice (blockIdx.x, blockIdx.z) -
+  // one writer per element - and dww_slice_reduce_kernel adds the slices in order
+  if (det) Gout += ((size_t)blockIdx.x + (size_t)gridDim.x * blockIdx.z) * 9 * C;
   extern __shared__ float red[];                       // [8 warps][32 lanes][3*V]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int o = m.cvp; o < 32; o <<= 1) {
@@ -798,7 +801,10 @@ __device__ __forceinline__ void dw_reduce_G(float (&G)[9][V], float* __restrict_
 #pragma unroll
       for (int w = 0; w < 8; ++w) s += red[(w * 32 + ln) * PER + r];
       const int kw = r / V, j = r - kw * V;
-      if (ln < cv_count && !g_dww_noatomic) atomicAdd(Gout + (size_t)(kh * 3 + kw) * tap_stride + (size_t)((cvi_base + ln) * V + j) * c_stride, s);
+      if (ln < cv_count && !g_dww_noatomic) {
+        float* dst = Gout + (size_t)(kh * 3 + kw) * tap_stride + (size_t)((cvi_base + ln) * V + j) * c_stride;
+        if (det) *dst = s; else atomicAdd(dst, s);
+      }
     }
   }
 }
@@ -806,7 +812,7 @@ __device__ __forceinline__ void dw_reduce_G(float (&G)[9][V], float* __restrict_
 // input-stationary like dw_s1d1_kernel: input row r meets dout rows r+1 (filter row 0), r (row 1), r-1 (row 2)
 template <typename T, int V>
 __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_s1d1_kernel(DwView<const T> in, DwView<const T> dout, float* __restrict__ Gout,
-                                                                        int C, DwMap m, int tap_stride, int c_stride) {
+                                                                        int C, DwMap m, int tap_stride, int c_stride, int det) {
   constexpr int VP = V / 2;
   const DwLane l = dw_lane(m, dout.h, dout.w);
   pdl_sync();
@@ -880,7 +886,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_s1d1_kernel(DwView<c
   for (int k = 0; k < 9; ++k)
 #pragma unroll
     for (int j = 0; j < VP; ++j) { G[k][2 * j] = G2[k][j].x; G[k][2 * j + 1] = G2[k][j].y; }
-  dw_reduce_G<V>(G, Gout, C, m, blockIdx.y * m.cvp, tap_stride, c_stride);
+  dw_reduce_G<V>(G, Gout, C, m, blockIdx.y * m.cvp, tap_stride, c_stride, det);
 }
 
 // ---- stride 2, dilation 1 backward-data, staged (the last separable unit of blocks 1-3, DX:99-101) ------------------------------
@@ -1005,7 +1011,7 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_saddr, uint32_t ran
 
 template <typename T, int V>
 __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwView<const T> in, DwView<const T> dout, float* __restrict__ Gout,
-                                                                          int C, DwMap m, int tap_stride, int c_stride, int spc) {
+                                                                          int C, DwMap m, int tap_stride, int c_stride, int spc, int det) {
   constexpr int VP = V / 2;
   extern __shared__ uint4 dww_smem[];                 // in tile [rs + 2][ppb + 2][cvp] | dout tile [rs][ppb][cvp]   (then reused)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1144,6 +1150,8 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwVie
   cluster_sync_all();                                  // every block's `part` is complete and visible cluster-wide
   {
     const uint32_t rank = cluster_ctarank(), nrank = cluster_nctarank();
+    // det: the cluster STORES its sums into workspace slice (blockIdx.x, cluster index along z), every element written by one rank
+    if (det) Gout += ((size_t)blockIdx.x + (size_t)gridDim.x * (blockIdx.z / nrank)) * 9 * C;
     const int total = 9 * nch;
     const int chunk = (total + (int)nrank - 1) / (int)nrank;
     const int lo = (int)rank * chunk, hi = min(total, lo + chunk);
@@ -1153,8 +1161,10 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwVie
       float sum = 0.f;
       for (uint32_t r = 0; r < nrank; ++r) sum += ld_dsmem_f32(part_s + (uint32_t)idx * 4u, r);
       const int k = idx / nch, c = idx - k * nch;
-      if (c < cv_count * V && !g_dww_noatomic)
-        atomicAdd(Gout + (size_t)k * tap_stride + (size_t)(cv0 * V + c) * c_stride, sum);
+      if (c < cv_count * V && !g_dww_noatomic) {
+        float* dst = Gout + (size_t)k * tap_stride + (size_t)(cv0 * V + c) * c_stride;
+        if (det) *dst = sum; else atomicAdd(dst, sum);
+      }
     }
   }
   cluster_sync_all();                                  // no block may exit (and free its shared memory) while a peer still reads it
@@ -1162,7 +1172,7 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwVie
 
 template <typename T, int V>
 __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_direct_kernel(DwView<const T> in, DwView<const T> dout, float* __restrict__ Gout,
-                                                                          int C, DwMap m, int s, int d, int tap_stride, int c_stride) {
+                                                                          int C, DwMap m, int s, int d, int tap_stride, int c_stride, int det) {
   const DwLane l = dw_lane(m, dout.h, dout.w);
   pdl_sync();
   float G[9][V];
@@ -1201,7 +1211,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_direct_kernel(DwView
       }
     }
   }
-  dw_reduce_G<V>(G, Gout, C, m, blockIdx.y * m.cvp, tap_stride, c_stride);
+  dw_reduce_G<V>(G, Gout, C, m, blockIdx.y * m.cvp, tap_stride, c_stride, det);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
@@ -1349,28 +1359,46 @@ static int dw_bwd_data_t(const dc_view& dout, const void* w, int s, int d, const
   }
   return launch_status("dc_dw_bwd_data");
 }
+// second stage of the deterministic depthwise weight gradient: G[k * tap_stride + c * c_stride] += sum over slices (in order)
+__global__ void __launch_bounds__(256) dww_slice_reduce_kernel(const float* __restrict__ ws, int nslices, int C, float* __restrict__ G,
+                                                               int tap_stride, int c_stride) {
+  pdl_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // i = k * C + c
+  if (i >= 9 * C) return;
+  float a = 0.f;
+  for (int z = 0; z < nslices; ++z) a += ws[(size_t)z * 9 * C + i];
+  const int k = i / C, c = i - k * C;
+  G[(size_t)k * tap_stride + (size_t)c * c_stride] += a;
+}
+
+struct DwwPlan {
+  bool tile;
+  int dsub, gn, gw, spc;
+  DwMap m;
+  dim3 grid;
+  size_t smem;
+};
 template <typename T>
-static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d, float* G, int param_layout, cudaStream_t st) {
-  const int tap_stride = param_layout ? 1 : dout.c, c_stride = param_layout ? 9 : 1;
+static DwwPlan dww_plan(const dc_view& in, const dc_view& dout, int s, int d) {
   constexpr int V = dwvec<T>::V;
-  // (a shared-memory staged variant was measured slower here: with one tile per block the 9*C atomics per block dominate;
-  //  the register-pipelined kernels keep long strips per block and reduce once)
+  // (a shared-memory staged variant with one tile per block was measured slower: the 9*C atomics per block dominate; the tile kernel
+  //  below reduces across a cluster first, the register-pipelined kernels keep long strips per block and reduce once)
   static int tb_mult = -1, min_rows = -1;   // sweep knobs: DEEPCAM_B200_DWW_BLOCKS_PER_SM, DEEPCAM_B200_DWW_MIN_ROWS
   if (tb_mult < 0) { const char* e = getenv("DEEPCAM_B200_DWW_BLOCKS_PER_SM"); tb_mult = e ? std::max(1, atoi(e)) : 2; }
   if (min_rows < 0) { const char* e = getenv("DEEPCAM_B200_DWW_MIN_ROWS"); min_rows = e ? std::max(1, atoi(e)) : 12; }
-  const int dsub = dw_dsub(s, d, dout.h, dout.w);
-  const int gh = dsub >= 1 ? dout.h / dsub : dout.h, gw = dsub >= 1 ? dout.w / dsub : dout.w;
-  const int gn = dsub >= 1 ? dout.n * dsub * dsub : dout.n;
-  {
-    static int noat = -1;
-    if (noat < 0) { const char* e = getenv("DEEPCAM_B200_DWW_NOATOMIC"); noat = (e && e[0] == '1') ? 1 : 0; if (noat) cudaMemcpyToSymbol(g_dww_noatomic, &noat, sizeof(int)); }
-  }
   static int tile_on = -1;        // DEEPCAM_B200_DWW_TILE=0: the register-pipelined kernel (A/B measurements)
   if (tile_on < 0) { const char* e = getenv("DEEPCAM_B200_DWW_TILE"); tile_on = (e && e[0] == '0') ? 0 : 1; }
-  if (dsub >= 1 && tile_on) {
+  DwwPlan pl;
+  pl.dsub = dw_dsub(s, d, dout.h, dout.w);
+  const int gh = pl.dsub >= 1 ? dout.h / pl.dsub : dout.h;
+  pl.gw = pl.dsub >= 1 ? dout.w / pl.dsub : dout.w;
+  pl.gn = pl.dsub >= 1 ? dout.n * pl.dsub * pl.dsub : dout.n;
+  pl.tile = false;
+  pl.spc = 1;
+  if (pl.dsub >= 1 && tile_on) {
     // strips of <= 10 rows: input + dout tiles stay below 110 KB, two blocks per SM; the 48-row middle-flow tensors then make
     // 270 blocks = one wave, in 54 clusters of 5 strips
-    DwMap m = dw_map(dout.c, V, gh, gw, gn, 1 << 30, 1);
+    DwMap m = dw_map(dout.c, V, gh, pl.gw, pl.gn, 1 << 30, 1);
     m.nstrips = ceil_div(gh, 10);
     m.rs = ceil_div(gh, m.nstrips);
     m.nstrips = ceil_div(gh, m.rs);
@@ -1378,49 +1406,96 @@ static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d,
     const size_t scratch = ((size_t)8 * 32 * 3 * V + (size_t)9 * m.cvp * V) * sizeof(float);
     const size_t smem = std::max(tiles, scratch);
     if (smem <= 110 * 1024) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        if (cudaFuncSetAttribute(dw_bwd_weight_tile_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) == cudaSuccess) attr_set = true;
-      }
       // strips per block: one for the 48-row tensors (270 blocks = one wave); the large entry-flow / decoder tensors get
       // several strips per block so that ~600 blocks walk the tensor and reduce once each
-      const long long nblk1 = (long long)ceil_div(gw, m.ppb) * m.gy * gn * m.nstrips;
-      const int spc = (int)std::min<long long>(m.nstrips, std::max<long long>(1, nblk1 / 592));
-      const int nchunks = ceil_div(m.nstrips, spc);
-      dim3 grid((unsigned)ceil_div(gw, m.ppb), (unsigned)m.gy, (unsigned)(gn * nchunks));
-      if (attr_set) {
-        // cluster = consecutive blockIdx.z (strips / images / parity sub-grids of one (x block, channel group)): largest divisor <= 8
-        static int cz_max = -1;         // DEEPCAM_B200_DWW_CLUSTER: largest cluster size tried (1 = no cluster reduction)
-        if (cz_max < 0) { const char* e = getenv("DEEPCAM_B200_DWW_CLUSTER"); cz_max = e ? std::max(1, std::min(8, atoi(e))) : 8; }
-        for (int cz = cz_max; cz >= 1; --cz) {
-          if (grid.z % cz) continue;
-          cudaLaunchConfig_t cfg = {};
-          cfg.gridDim = grid; cfg.blockDim = dim3(kDwThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-          cudaLaunchAttribute attr[2];
-          attr[0].id = cudaLaunchAttributeClusterDimension;
-          attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = cz;
-          attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-          attr[1].val.programmaticStreamSerializationAllowed = 1;
-          cfg.attrs = attr;
-          cfg.numAttrs = pdl_enabled() ? 2 : 1;
-          cudaError_t e = cudaLaunchKernelEx(&cfg, dw_bwd_weight_tile_kernel<T, V>, dw_view<const T>(in, dsub), dw_view<const T>(dout, dsub), G, dout.c, m,
-                                             tap_stride, c_stride, spc);
-          if (e == cudaSuccess) return launch_status("dc_dw_bwd_weight");
+      const long long nblk1 = (long long)ceil_div(pl.gw, m.ppb) * m.gy * pl.gn * m.nstrips;
+      pl.spc = (int)std::min<long long>(m.nstrips, std::max<long long>(1, nblk1 / 592));
+      const int nchunks = ceil_div(m.nstrips, pl.spc);
+      pl.grid = dim3((unsigned)ceil_div(pl.gw, m.ppb), (unsigned)m.gy, (unsigned)(pl.gn * nchunks));
+      pl.m = m;
+      pl.smem = smem;
+      pl.tile = true;
+      return pl;
+    }
+  }
+  pl.m = dw_map(dout.c, V, gh, pl.gw, pl.gn, kNumSMs * tb_mult, min_rows);
+  pl.grid = dw_grid(pl.m, pl.gw, pl.gn);
+  pl.smem = (size_t)8 * 32 * 3 * V * sizeof(float);
+  return pl;
+}
+
+/* ws != null: deterministic two-stage form (dc_dw_bwd_weight_det) */
+template <typename T>
+static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d, float* G, int param_layout, float* ws, long long ws_elems,
+                           cudaStream_t st) {
+  const int g_tap_stride = param_layout ? 1 : dout.c, g_c_stride = param_layout ? 9 : 1;
+  constexpr int V = dwvec<T>::V;
+  {
+    static int noat = -1;
+    if (noat < 0) { const char* e = getenv("DEEPCAM_B200_DWW_NOATOMIC"); noat = (e && e[0] == '1') ? 1 : 0; if (noat) cudaMemcpyToSymbol(g_dww_noatomic, &noat, sizeof(int)); }
+  }
+  DwwPlan pl = dww_plan<T>(in, dout, s, d);
+  const int det = ws != nullptr ? 1 : 0;
+  if (det)
+    DC_REQUIRE(ws_elems >= (long long)pl.grid.x * pl.grid.z * 9 * dout.c, "dc_dw_bwd_weight_det: workspace of %lld floats required, %lld given",
+               (long long)pl.grid.x * pl.grid.z * 9 * dout.c, ws_elems);
+  float* target = det ? ws : G;
+  const int tap_stride = det ? dout.c : g_tap_stride, c_stride = det ? 1 : g_c_stride;
+  int nslices = (int)(pl.grid.x * pl.grid.z);
+  bool launched = false;
+  if (pl.tile) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(dw_bwd_weight_tile_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) == cudaSuccess) attr_set = true;
+    }
+    if (attr_set) {
+      // cluster = consecutive blockIdx.z (strips / images / parity sub-grids of one (x block, channel group)): largest divisor <= 8
+      static int cz_max = -1;         // DEEPCAM_B200_DWW_CLUSTER: largest cluster size tried (1 = no cluster reduction)
+      if (cz_max < 0) { const char* e = getenv("DEEPCAM_B200_DWW_CLUSTER"); cz_max = e ? std::max(1, std::min(8, atoi(e))) : 8; }
+      for (int cz = cz_max; cz >= 1 && !launched; --cz) {
+        if (pl.grid.z % cz) continue;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = pl.grid; cfg.blockDim = dim3(kDwThreads); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = cz;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, dw_bwd_weight_tile_kernel<T, V>, dw_view<const T>(in, pl.dsub), dw_view<const T>(dout, pl.dsub), target,
+                                           dout.c, pl.m, tap_stride, c_stride, pl.spc, det);
+        if (e == cudaSuccess) {
+          launched = true;
+          nslices = (int)(pl.grid.x * (pl.grid.z / cz));
+        } else {
           cudaGetLastError();                          // this cluster size cannot be scheduled here: try the next divisor
         }
       }
     }
+    if (!launched) {                                   // the staged kernel cannot run here: register-pipelined kernel, its own grid
+      pl.m = dw_map(dout.c, V, pl.dsub >= 1 ? dout.h / pl.dsub : dout.h, pl.gw, pl.gn, kNumSMs * 2, 12);
+      pl.grid = dw_grid(pl.m, pl.gw, pl.gn);
+      pl.smem = (size_t)8 * 32 * 3 * V * sizeof(float);
+      nslices = (int)(pl.grid.x * pl.grid.z);
+      if (det)
+        DC_REQUIRE(ws_elems >= (long long)nslices * 9 * dout.c, "dc_dw_bwd_weight_det: workspace too small for the fallback kernel (%lld floats)",
+                   (long long)nslices * 9 * dout.c);
+    }
   }
-  DwMap m = dw_map(dout.c, V, gh, gw, gn, kNumSMs * tb_mult, min_rows);
-  dim3 grid = dw_grid(m, gw, gn);
-  const size_t smem = (size_t)8 * 32 * 3 * V * sizeof(float);
-  if (dsub >= 1)
-    launch_k(dw_bwd_weight_s1d1_kernel<T, V>, grid, dim3(kDwThreads), (size_t)smem, st, dw_view<const T>(in, dsub), dw_view<const T>(dout, dsub), G,
-             dout.c, m, tap_stride, c_stride);
-  else
-    launch_k(dw_bwd_weight_direct_kernel<T, V>, grid, dim3(kDwThreads), (size_t)smem, st, dw_view<const T>(in), dw_view<const T>(dout), G, dout.c, m, s, d,
-                                                                      tap_stride, c_stride);
-  return launch_status("dc_dw_bwd_weight");
+  if (!launched) {
+    if (pl.dsub >= 1)
+      launch_k(dw_bwd_weight_s1d1_kernel<T, V>, pl.grid, dim3(kDwThreads), pl.smem, st, dw_view<const T>(in, pl.dsub), dw_view<const T>(dout, pl.dsub),
+               target, dout.c, pl.m, tap_stride, c_stride, det);
+    else
+      launch_k(dw_bwd_weight_direct_kernel<T, V>, pl.grid, dim3(kDwThreads), pl.smem, st, dw_view<const T>(in), dw_view<const T>(dout), target, dout.c,
+               pl.m, s, d, tap_stride, c_stride, det);
+  }
+  if (int r = launch_status("dc_dw_bwd_weight")) return r;
+  if (!det) return 0;
+  launch_k(dww_slice_reduce_kernel, dim3((unsigned)ceil_div(9 * dout.c, 256)), dim3(256), (size_t)0, st, (const float*)ws, nslices, dout.c, G,
+           g_tap_stride, g_c_stride);
+  return launch_status("dc_dw_bwd_weight_det");
 }
 
 static int check_dw(const char* what, const dc_view& big, const dc_view& small, int s, int d) {
@@ -1497,8 +1572,32 @@ int dc_dw_bwd_weight(dc_view in, dc_view dout, int stride, int dil, float* G9c, 
   if (int r = check_dw("dc_dw_bwd_weight", in, dout, stride, dil)) return r;
   DC_REQUIRE(G9c != nullptr, "dc_dw_bwd_weight: null gradient");
   cudaStream_t st = as_stream(stream);
-  return in.dtype == DC_F32 ? dw_bwd_weight_t<float>(in, dout, stride, dil, G9c, param_layout, st)
-                            : dw_bwd_weight_t<__nv_bfloat16>(in, dout, stride, dil, G9c, param_layout, st);
+  return in.dtype == DC_F32 ? dw_bwd_weight_t<float>(in, dout, stride, dil, G9c, param_layout, nullptr, 0, st)
+                            : dw_bwd_weight_t<__nv_bfloat16>(in, dout, stride, dil, G9c, param_layout, nullptr, 0, st);
+}
+
+long long dc_dw_bwd_weight_ws_elems(dc_view in, dc_view dout, int stride, int dil) {
+  if (check_dw("dc_dw_bwd_weight_ws_elems", in, dout, stride, dil)) return -1;
+  const DwwPlan pl = in.dtype == DC_F32 ? dww_plan<float>(in, dout, stride, dil) : dww_plan<__nv_bfloat16>(in, dout, stride, dil);
+  long long n = (long long)pl.grid.x * pl.grid.z;
+  if (pl.tile) {                                       // the register-pipelined fallback of the staged kernel has its own grid
+    const int V = in.dtype == DC_F32 ? 4 : 8;
+    const DwMap m = dw_map(dout.c, V, dout.h / pl.dsub, pl.gw, pl.gn, kNumSMs * 2, 12);
+    const dim3 g = dw_grid(m, pl.gw, pl.gn);
+    n = std::max(n, (long long)g.x * g.z);
+  }
+  return n * 9 * dout.c;
+}
+
+/* deterministic form: every block (cluster) stores its partial sums into its own workspace slice, a second launch adds the slices to
+   G9c in slice order.  G9c is accumulated into, as in dc_dw_bwd_weight. */
+int dc_dw_bwd_weight_det(dc_view in, dc_view dout, int stride, int dil, float* G9c, int param_layout, float* ws, long long ws_elems,
+                         void* stream) {
+  if (int r = check_dw("dc_dw_bwd_weight_det", in, dout, stride, dil)) return r;
+  DC_REQUIRE(G9c != nullptr && ws != nullptr, "dc_dw_bwd_weight_det: null gradient or workspace");
+  cudaStream_t st = as_stream(stream);
+  return in.dtype == DC_F32 ? dw_bwd_weight_t<float>(in, dout, stride, dil, G9c, param_layout, ws, ws_elems, st)
+                            : dw_bwd_weight_t<__nv_bfloat16>(in, dout, stride, dil, G9c, param_layout, ws, ws_elems, st);
 }
 
 }  // extern "C"

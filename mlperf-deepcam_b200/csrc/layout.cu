@@ -524,6 +524,48 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ G, int K, int N, i
   }
 }
 
+// deterministic second stage of the split weight-gradient reductions (common.cuh)
+template <int VEC>
+__global__ void __launch_bounds__(256) split_reduce_kernel(const float* __restrict__ ws, int nslices, long long slice_stride, SplitReduceTaps taps,
+                                                           long long per_tap, float* __restrict__ dst) {
+  pdl_sync();
+  const long long off = (long long)taps.wt[blockIdx.y] * per_tap;
+  const long long n = per_tap / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (VEC == 4) {
+      const float4* src = reinterpret_cast<const float4*>(ws + off) + i;
+      float4 a = *src;
+      for (int z = 1; z < nslices; ++z) {
+        const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (long long)z * slice_stride);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      float4* d = reinterpret_cast<float4*>(dst + off) + i;
+      float4 o = *d;
+      o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      *d = o;
+    } else {
+      float a = ws[off + i];
+      for (int z = 1; z < nslices; ++z) a += ws[(long long)z * slice_stride + off + i];
+      dst[off + i] += a;
+    }
+  }
+}
+
+int launch_split_reduce(const float* ws, int nslices, long long slice_stride, const SplitReduceTaps& taps, long long per_tap, float* dst,
+                        cudaStream_t st) {
+  const bool vec = per_tap % 4 == 0 && slice_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(ws) % 16) == 0 &&
+                   (reinterpret_cast<uintptr_t>(dst) % 16) == 0;
+  const long long n = vec ? per_tap / 4 : per_tap;
+  const int bx = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)kNumSMs * 8 / std::max(1, taps.n)));
+  dim3 grid((unsigned)bx, (unsigned)taps.n);
+  if (vec) launch_k(split_reduce_kernel<4>, grid, dim3(256), (size_t)0, st, ws, nslices, slice_stride, taps, per_tap, dst);
+  else launch_k(split_reduce_kernel<1>, grid, dim3(256), (size_t)0, st, ws, nslices, slice_stride, taps, per_tap, dst);
+  return launch_status("dc_split_reduce");
+}
+
+static int g_deterministic = 0;
+bool deterministic() { return g_deterministic != 0; }
+
 }  // namespace dc
 
 using namespace dc;
@@ -534,6 +576,8 @@ int dc_abi_version(void) { return DC_ABI_VERSION; }
 const char* dc_last_error_string(void) { return dc::err_buf(); }
 int dc_set_pdl(int on) { dc::set_pdl(on); return 0; }
 int dc_get_pdl(void) { return dc::pdl_enabled() ? 1 : 0; }
+int dc_set_deterministic(int on) { dc::g_deterministic = on ? 1 : 0; return 0; }
+int dc_get_deterministic(void) { return dc::g_deterministic; }
 
 int dc_device_supports_tcgen05(void) {
   int dev = 0;

@@ -174,6 +174,7 @@ static int reduce_hw_t(const dc_view& x, float* out, float scale, cudaStream_t s
   int cv = x.c / 4, cvb = std::min(cv, 32), rows = 256 / cvb, gy = ceil_div(cv, cvb);
   int hw = x.h * x.w;
   int gx = std::max(1, std::min(ceil_div(hw, rows * 4), std::max(1, (kNumSMs * 4) / (gy * x.n))));
+  if (deterministic()) gx = 1;      // dc_set_deterministic: one block per (channel chunk, image) - a single add onto the zeroed output
   dim3 grid(gx, gy, x.n);
   reduce_hw_kernel<T><<<grid, 256, (size_t)rows * cvb * 4 * sizeof(float), st>>>(make_view<const T>(x), out, scale, cvb, rows);
   return launch_status(what);

@@ -191,7 +191,9 @@ __global__ void __launch_bounds__(1024) small_m_gemm_kernel(const float* __restr
 // wgrad: rows = co (BMC tile, from dout), cols = ci (64 tile, from in), reduction over pixels in chunks of BK.
 template <typename T, int BMC>
 __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(dc_conv_desc d, View<const T> in, View<const T> dout,
-                                                              float* __restrict__ G, int pix_per_split, int n_ci_tiles) {
+                                                              float* __restrict__ G, int pix_per_split, int n_ci_tiles, int det_wtaps) {
+  // det_wtaps > 0 (dc_conv_wgrad_simt_det): G is a workspace [splits][wtaps][Co][Ci]; pixel split z STORES its partial sums into
+  // slice z (one writer per element) and launch_split_reduce adds the slices in split order
   constexpr int BNC = 64;
   constexpr int TM = BMC / 16, TN = BNC / 16;
   __shared__ __align__(16) float As[BK][BMC];   // [pixel][co]
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(dc_conv_desc d, Vi
     __syncthreads();
   }
 
-  float* Gt = G + (size_t)d.wt[t] * Co * Ci;
+  float* Gt = G + (size_t)(det_wtaps > 0 ? (int)blockIdx.z * det_wtaps + d.wt[t] : d.wt[t]) * Co * Ci;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     int co = co0 + ty * TM + i;
@@ -271,7 +273,9 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(dc_conv_desc d, Vi
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       int ci = ci0 + tx * TN + j;
-      if (ci < Ci) atomicAdd(Gt + (size_t)co * Ci + ci, acc[i][j]);
+      if (ci >= Ci) continue;
+      if (det_wtaps > 0) Gt[(size_t)co * Ci + ci] = acc[i][j];
+      else atomicAdd(Gt + (size_t)co * Ci + ci, acc[i][j]);
     }
   }
 }
@@ -305,22 +309,45 @@ static int conv_gemm_simt_t(const dc_conv_desc* d, const dc_view& in, const void
   return launch_status("dc_conv_gemm_simt");
 }
 
-template <typename T>
-static int conv_wgrad_simt_t(const dc_conv_desc* d, const dc_view& in, const dc_view& dout, float* G, cudaStream_t st) {
+static void wgrad_simt_plan(const dc_conv_desc* d, const dc_view& in, const dc_view& dout, int& bmc, int& pix_per_split, int& splits) {
   const int M = dout.n * dout.h * dout.w;
-  const int bmc = dout.c <= 16 ? 16 : 64;
-  const int n_co_tiles = ceil_div(dout.c, bmc), n_ci_tiles = ceil_div(in.c, 64);
-  const int tiles = n_co_tiles * n_ci_tiles * d->ntaps;
+  bmc = dout.c <= 16 ? 16 : 64;
+  const int tiles = ceil_div(dout.c, bmc) * ceil_div(in.c, 64) * d->ntaps;
   // split the pixel reduction so that the grid has ~4 waves of blocks
-  int splits = std::max(1, std::min(ceil_div(kNumSMs * 4, tiles), ceil_div(M, 256)));
-  int pix_per_split = ceil_div(ceil_div(M, splits), BK) * BK;
+  splits = std::max(1, std::min(ceil_div(kNumSMs * 4, tiles), ceil_div(M, 256)));
+  pix_per_split = ceil_div(ceil_div(M, splits), BK) * BK;
   splits = ceil_div(M, pix_per_split);
+}
+
+template <typename T>
+static int conv_wgrad_simt_t(const dc_conv_desc* d, const dc_view& in, const dc_view& dout, float* G, float* ws, long long ws_elems,
+                             cudaStream_t st) {
+  int bmc, pix_per_split, splits;
+  wgrad_simt_plan(d, in, dout, bmc, pix_per_split, splits);
+  const int n_co_tiles = ceil_div(dout.c, bmc), n_ci_tiles = ceil_div(in.c, 64);
+  const long long per_tap = (long long)dout.c * in.c, slice = per_tap * d->wtaps;
+  const bool det = ws != nullptr && splits > 1;
+  if (det) {
+    DC_REQUIRE(ws_elems >= slice * splits, "dc_conv_wgrad_simt_det: workspace of %lld floats required, %lld given", slice * splits, ws_elems);
+    for (int a = 0; a < d->ntaps; ++a)
+      for (int b = a + 1; b < d->ntaps; ++b)
+        DC_REQUIRE(d->wt[a] != d->wt[b], "dc_conv_wgrad_simt_det: two taps of one launch share weight tap %d", d->wt[a]);
+  }
+  float* target = det ? ws : G;
+  const int det_wtaps = det ? d->wtaps : 0;
   dim3 grid(n_co_tiles * n_ci_tiles, d->ntaps, splits);
   if (bmc == 16)
-    conv_wgrad_simt_kernel<T, 16><<<grid, 256, 0, st>>>(*d, make_view<const T>(in), make_view<const T>(dout), G, pix_per_split, n_ci_tiles);
+    conv_wgrad_simt_kernel<T, 16><<<grid, 256, 0, st>>>(*d, make_view<const T>(in), make_view<const T>(dout), target, pix_per_split, n_ci_tiles,
+                                                        det_wtaps);
   else
-    conv_wgrad_simt_kernel<T, 64><<<grid, 256, 0, st>>>(*d, make_view<const T>(in), make_view<const T>(dout), G, pix_per_split, n_ci_tiles);
-  return launch_status("dc_conv_wgrad_simt");
+    conv_wgrad_simt_kernel<T, 64><<<grid, 256, 0, st>>>(*d, make_view<const T>(in), make_view<const T>(dout), target, pix_per_split, n_ci_tiles,
+                                                        det_wtaps);
+  if (int r = launch_status("dc_conv_wgrad_simt")) return r;
+  if (!det) return 0;
+  SplitReduceTaps taps;
+  taps.n = d->ntaps;
+  for (int t = 0; t < d->ntaps; ++t) taps.wt[t] = d->wt[t];
+  return launch_split_reduce(ws, splits, slice, taps, per_tap, G, st);
 }
 
 }  // namespace dc
@@ -351,13 +378,32 @@ int dc_conv_gemm_simt(const dc_conv_desc* d, dc_view in, const void* w, const fl
   return in.dtype == DC_F32 ? conv_gemm_simt_t<float>(d, in, w, bias, out, st) : conv_gemm_simt_t<__nv_bfloat16>(d, in, w, bias, out, st);
 }
 
-int dc_conv_wgrad_simt(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, void* stream) {
-  if (int r = check_desc("dc_conv_wgrad_simt", d)) return r;
-  DC_REQUIRE(view_ok(in) && view_vec4(in) && view_ok(dout) && view_vec4(dout), "dc_conv_wgrad_simt: views must be channel-contiguous, C %% 4 == 0");
-  DC_REQUIRE(in.dtype == dout.dtype && in.n == dout.n, "dc_conv_wgrad_simt: dtype/batch mismatch");
-  DC_REQUIRE(G != nullptr, "dc_conv_wgrad_simt: null gradient");
+static int conv_wgrad_simt_impl(const char* what, const dc_conv_desc* d, dc_view in, dc_view dout, float* G, float* ws, long long ws_elems,
+                                void* stream) {
+  if (int r = check_desc(what, d)) return r;
+  DC_REQUIRE(view_ok(in) && view_vec4(in) && view_ok(dout) && view_vec4(dout), "%s: views must be channel-contiguous, C %% 4 == 0", what);
+  DC_REQUIRE(in.dtype == dout.dtype && in.n == dout.n, "%s: dtype/batch mismatch", what);
+  DC_REQUIRE(G != nullptr, "%s: null gradient", what);
   cudaStream_t st = as_stream(stream);
-  return in.dtype == DC_F32 ? conv_wgrad_simt_t<float>(d, in, dout, G, st) : conv_wgrad_simt_t<__nv_bfloat16>(d, in, dout, G, st);
+  return in.dtype == DC_F32 ? conv_wgrad_simt_t<float>(d, in, dout, G, ws, ws_elems, st)
+                            : conv_wgrad_simt_t<__nv_bfloat16>(d, in, dout, G, ws, ws_elems, st);
+}
+
+int dc_conv_wgrad_simt(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, void* stream) {
+  return conv_wgrad_simt_impl("dc_conv_wgrad_simt", d, in, dout, G, nullptr, 0, stream);
+}
+
+long long dc_conv_wgrad_simt_ws_elems(const dc_conv_desc* d, dc_view in, dc_view dout) {
+  if (d == nullptr || d->ntaps < 1 || d->ntaps > DC_MAX_TAPS || !view_ok(in) || !view_ok(dout)) return -1;
+  int bmc, pps, splits;
+  wgrad_simt_plan(d, in, dout, bmc, pps, splits);
+  return splits > 1 ? (long long)splits * d->wtaps * dout.c * in.c : 0;
+}
+
+/* deterministic form: partial sums per pixel split in ws, added to G in split order by a second launch */
+int dc_conv_wgrad_simt_det(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, float* ws, long long ws_elems, void* stream) {
+  DC_REQUIRE(ws != nullptr || dc_conv_wgrad_simt_ws_elems(d, in, dout) == 0, "dc_conv_wgrad_simt_det: workspace required (dc_conv_wgrad_simt_ws_elems)");
+  return conv_wgrad_simt_impl("dc_conv_wgrad_simt_det", d, in, dout, G, ws, ws_elems, stream);
 }
 
 }  // extern "C"

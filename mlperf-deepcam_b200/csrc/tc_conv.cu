@@ -82,6 +82,11 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -1100,6 +1105,8 @@ struct TcWgradParams {
   int vec_red;          // G rows are 16-byte aligned and Ci % 4 == 0: use red.global.add.v4.f32
   int tma_red;          // ... and the fp32 gradient has a tensor map (maps.c): the epilogue stages 128 x 32 fp32 chunks in shared
                         // memory and hands them to TMA reduce-add (bulk L2 reductions instead of 8192 red instructions per CTA)
+  int det_wtaps;        // > 0: deterministic two-stage reduction (dc_conv_wgrad_tc_det).  G is a workspace [splits][wtaps][Co][Ci] and
+                        // pixel split z STORES its partial tile into slice z (one writer per element, no reduction in this kernel)
   float* G;
 };
 
@@ -1203,7 +1210,8 @@ __global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const __grid_
       const int co = co0 + lg * 32 + lane;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
-      float* Grow = p.G + ((size_t)p.wt[t] * p.Co + (size_t)(co < p.Co ? co : 0)) * p.Ci;
+      const int wslice = p.det_wtaps > 0 ? (int)blockIdx.z * p.det_wtaps + p.wt[t] : p.wt[t];
+      float* Grow = p.G + ((size_t)wslice * p.Co + (size_t)(co < p.Co ? co : 0)) * p.Ci;
       if (p.tma_red) {
         // all MMAs have completed (tmem_full), so every pipeline stage has been consumed: stage memory becomes two 16 KB
         // staging buffers of 128 rows x 128 B (32 fp32), 128B-swizzled like the tensor map of the gradient
@@ -1228,7 +1236,8 @@ __global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const __grid_
           fence_proxy_async();
           epi_bar_sync();
           if (elected) {
-            tma_reduce_add_3d(&maps.c, smem_base + (uint32_t)(chunk & 1) * 16384u, ci0 + c0, co0, p.wt[t]);
+            if (p.det_wtaps > 0) tma_store_3d(&maps.c, smem_base + (uint32_t)(chunk & 1) * 16384u, ci0 + c0, co0, wslice);
+            else tma_reduce_add_3d(&maps.c, smem_base + (uint32_t)(chunk & 1) * 16384u, ci0 + c0, co0, wslice);
             tma_store_commit();
           }
         }
@@ -1240,7 +1249,13 @@ __global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const __grid_
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (co < p.Co) {
+        if (co < p.Co && p.det_wtaps > 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int ci = ci0 + c0 + j;
+            if (ci < p.Ci) Grow[ci] = __uint_as_float(v[j]);
+          }
+        } else if (co < p.Co) {
           if (p.vec_red) {
             // 16-byte reductions: 4 consecutive ci of this lane's co row per instruction (Ci % 4 == 0, G 16-byte aligned)
 #pragma unroll
@@ -1732,7 +1747,27 @@ int dc_conv_gemm_tc_bn_eval(const dc_conv_desc* d, dc_view in, const void* w, co
   return conv_gemm_tc_impl(d, in, w, bias, out, nullptr, nullptr, stream, &aff);
 }
 
-int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, void* stream) {
+// ci tile and pixel-split count of the weight-gradient kernel (shared by the launch and by dc_conv_wgrad_tc_ws_elems)
+static void wgrad_split_plan(const dc_conv_desc* d, const dc_view& in, const dc_view& dout, int& BNW, int& mtiles_total, int& per_split, int& splits) {
+  int TH, TW;
+  pick_tile(dout.h, dout.w, TH, TW);
+  mtiles_total = ceil_div(dout.w, TW) * ceil_div(dout.h, TH) * dout.n;
+  // ci tile: 256 when it does not waste columns (wider tiles halve the dY re-reads from L2), else 128 / 64
+  BNW = in.c <= 64 ? 64 : ((in.c > 128 && (in.c % 256 == 0 || in.c % 256 > 128)) ? 256 : 128);
+  const int tiles = ceil_div(dout.c, 128) * ceil_div(in.c, BNW) * d->ntaps;
+  // one CTA per SM (the stages fill the shared memory): split the pixel reduction so that the grid is one wave
+  static int split_div = -1;      // tuning knob (DEEPCAM_B200_WGRAD_SPLIT_DIV): divide the one-wave split count
+  if (split_div < 0) { const char* e = getenv("DEEPCAM_B200_WGRAD_SPLIT_DIV"); split_div = e ? std::max(1, atoi(e)) : 1; }
+  static int split_mul = -1;      // and DEEPCAM_B200_WGRAD_SPLIT_MUL: multiply it (more than one wave of CTAs)
+  if (split_mul < 0) { const char* e = getenv("DEEPCAM_B200_WGRAD_SPLIT_MUL"); split_mul = e ? std::max(1, atoi(e)) : 1; }
+  splits = std::max(1, std::min(mtiles_total, kNumSMs * split_mul / std::max(1, tiles) / split_div));
+  per_split = ceil_div(mtiles_total, splits);
+  splits = ceil_div(mtiles_total, per_split);
+}
+
+/* ws != null: deterministic two-stage form - the pixel splits store their partial tiles into ws[split][wtaps][Co][Ci] and a second
+   launch adds the slices to G in split order */
+static int conv_wgrad_tc_impl(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, float* ws, long long ws_elems, void* stream) {
   DC_REQUIRE(d != nullptr && d->ntaps >= 1 && d->ntaps <= DC_MAX_TAPS, "dc_conv_wgrad_tc: bad descriptor");
   DC_REQUIRE(tc_view_ok(in) && tc_view_ok(dout), "dc_conv_wgrad_tc: views must be bf16, channel-contiguous, C %% 8 == 0, aligned");
   DC_REQUIRE(in.n == dout.n && G != nullptr, "dc_conv_wgrad_tc: bad arguments");
@@ -1743,46 +1778,68 @@ int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, 
   p.tiles_x = ceil_div(dout.w, p.TW);
   p.tiles_y = ceil_div(dout.h, p.TH);
   p.n_img = dout.n;
-  p.mtiles_total = p.tiles_x * p.tiles_y * dout.n;
   p.Co = dout.c; p.Ci = in.c; p.G = G;
+  p.det_wtaps = 0;
   if (int r = build_gather("dc_conv_wgrad_tc", d, in, p.TH, p.TW, maps, p)) return r;
   if (int r = encode_act_map(&maps.b, dout.ptr, dout.c, dout.w, dout.h, dout.n, dout.sw, dout.sh, dout.sn, p.TW, p.TH, "dc_conv_wgrad_tc"))
     return r;
-  // ci tile: 256 when it does not waste columns (wider tiles halve the dY re-reads from L2), else 128 / 64
-  const int BNW = in.c <= 64 ? 64 : ((in.c > 128 && (in.c % 256 == 0 || in.c % 256 > 128)) ? 256 : 128);
+  int BNW, splits;
+  wgrad_split_plan(d, in, dout, BNW, p.mtiles_total, p.mtiles_per_split, splits);
   p.n_ci_tiles = ceil_div(in.c, BNW);
   const int n_co_tiles = ceil_div(dout.c, 128);
-  const int tiles = n_co_tiles * p.n_ci_tiles * d->ntaps;
-  // one CTA per SM (the stages fill the shared memory): split the pixel reduction so that the grid is one wave
-  static int split_div = -1;      // tuning knob (DEEPCAM_B200_WGRAD_SPLIT_DIV): divide the one-wave split count
-  if (split_div < 0) { const char* e = getenv("DEEPCAM_B200_WGRAD_SPLIT_DIV"); split_div = e ? std::max(1, atoi(e)) : 1; }
-  static int split_mul = -1;      // and DEEPCAM_B200_WGRAD_SPLIT_MUL: multiply it (more than one wave of CTAs)
-  if (split_mul < 0) { const char* e = getenv("DEEPCAM_B200_WGRAD_SPLIT_MUL"); split_mul = e ? std::max(1, atoi(e)) : 1; }
-  int splits = std::max(1, std::min(p.mtiles_total, kNumSMs * split_mul / std::max(1, tiles) / split_div));
-  p.mtiles_per_split = ceil_div(p.mtiles_total, splits);
-  splits = ceil_div(p.mtiles_total, p.mtiles_per_split);
-  p.vec_red = (in.c % 4 == 0 && (reinterpret_cast<uintptr_t>(G) % 16) == 0) ? 1 : 0;
+  const long long per_tap = (long long)dout.c * in.c, slice = per_tap * d->wtaps;
+  const bool det = ws != nullptr && splits > 1;     // one split: every element has one contribution, nothing to order
+  if (det) {
+    DC_REQUIRE(ws_elems >= slice * splits, "dc_conv_wgrad_tc_det: workspace of %lld floats required, %lld given", slice * splits, ws_elems);
+    DC_REQUIRE((reinterpret_cast<uintptr_t>(ws) % 16) == 0, "dc_conv_wgrad_tc_det: workspace must be 16-byte aligned");
+    for (int a = 0; a < d->ntaps; ++a)
+      for (int b = a + 1; b < d->ntaps; ++b)
+        DC_REQUIRE(d->wt[a] != d->wt[b], "dc_conv_wgrad_tc_det: two taps of one launch share weight tap %d", d->wt[a]);
+    p.G = ws;
+    p.det_wtaps = d->wtaps;
+  }
+  float* target = p.G;
+  p.vec_red = (in.c % 4 == 0 && (reinterpret_cast<uintptr_t>(target) % 16) == 0) ? 1 : 0;
   static int tma_red_enabled = -1;
   if (tma_red_enabled < 0) { const char* e = getenv("DEEPCAM_B200_WGRAD_TMA_RED"); tma_red_enabled = (e && e[0] == '0') ? 0 : 1; }
   p.tma_red = 0;
   if (p.vec_red && tma_red_enabled) {
-    // fp32 gradient G[wtaps][Co][Ci] as a 3-D tensor: boxes of 32 ci x 128 co of one tap, 128B swizzle; rows >= Co and columns
-    // >= Ci of edge tiles are clipped by the TMA unit
+    // fp32 gradient G[wtaps][Co][Ci] (deterministic form: [splits * wtaps][Co][Ci]) as a 3-D tensor: boxes of 32 ci x 128 co of one
+    // tap, 128B swizzle; rows >= Co and columns >= Ci of edge tiles are clipped by the TMA unit
     PFN_encodeTiled enc = get_encode();
     DC_REQUIRE(enc != nullptr, "dc_conv_wgrad_tc: cuTensorMapEncodeTiled unavailable");
-    cuuint64_t dims[3] = {(cuuint64_t)in.c, (cuuint64_t)dout.c, (cuuint64_t)d->wtaps};
+    cuuint64_t dims[3] = {(cuuint64_t)in.c, (cuuint64_t)dout.c, (cuuint64_t)d->wtaps * (cuuint64_t)(det ? splits : 1)};
     cuuint64_t strides[2] = {(cuuint64_t)in.c * 4, (cuuint64_t)in.c * 4 * (cuuint64_t)dout.c};
     cuuint32_t box[3] = {32, 128, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&maps.c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, G, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(&maps.c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, target, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_SUCCESS) p.tma_red = 1;
   }
   dim3 grid(n_co_tiles * p.n_ci_tiles, d->ntaps, splits);
   cudaStream_t st = as_stream(stream);
-  if (BNW == 64) return launch_wgrad<64>(maps, p, grid, st);
-  if (BNW == 256) return launch_wgrad<256>(maps, p, grid, st);
-  return launch_wgrad<128>(maps, p, grid, st);
+  int rc = BNW == 64 ? launch_wgrad<64>(maps, p, grid, st) : BNW == 256 ? launch_wgrad<256>(maps, p, grid, st) : launch_wgrad<128>(maps, p, grid, st);
+  if (rc != 0 || !det) return rc;
+  SplitReduceTaps taps;
+  taps.n = d->ntaps;
+  for (int t = 0; t < d->ntaps; ++t) taps.wt[t] = d->wt[t];
+  return launch_split_reduce(ws, splits, slice, taps, per_tap, G, st);
+}
+
+int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, void* stream) {
+  return conv_wgrad_tc_impl(d, in, dout, G, nullptr, 0, stream);
+}
+
+long long dc_conv_wgrad_tc_ws_elems(const dc_conv_desc* d, dc_view in, dc_view dout) {
+  if (d == nullptr || d->ntaps < 1 || d->ntaps > DC_MAX_TAPS || !tc_view_ok(in) || !tc_view_ok(dout)) return -1;
+  int BNW, total, per, splits;
+  wgrad_split_plan(d, in, dout, BNW, total, per, splits);
+  return splits > 1 ? (long long)splits * d->wtaps * dout.c * in.c : 0;
+}
+
+int dc_conv_wgrad_tc_det(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, float* ws, long long ws_elems, void* stream) {
+  DC_REQUIRE(ws != nullptr || dc_conv_wgrad_tc_ws_elems(d, in, dout) == 0, "dc_conv_wgrad_tc_det: workspace required (dc_conv_wgrad_tc_ws_elems)");
+  return conv_wgrad_tc_impl(d, in, dout, G, ws, ws_elems, stream);
 }
 
 }  // extern "C"

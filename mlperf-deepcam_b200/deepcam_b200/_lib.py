@@ -54,6 +54,8 @@ SIGNATURES = {
     "dc_device_supports_tcgen05": (c_int, []),
     "dc_set_pdl": (c_int, [c_int]),
     "dc_get_pdl": (c_int, []),
+    "dc_set_deterministic": (c_int, [c_int]),
+    "dc_get_deterministic": (c_int, []),
     "dc_copy_view": (c_int, [dc_view, dc_view, c_void_p]),
     "dc_fill_zero": (c_int, [c_void_p, c_size_t, c_void_p]),
     "dc_ingest_hwc": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
@@ -63,16 +65,22 @@ SIGNATURES = {
     "dc_unpack_wgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dc_conv_gemm_simt": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p]),
     "dc_conv_wgrad_simt": (c_int, [POINTER(dc_conv_desc), dc_view, dc_view, c_void_p, c_void_p]),
+    "dc_conv_wgrad_simt_ws_elems": (c_int64, [POINTER(dc_conv_desc), dc_view, dc_view]),
+    "dc_conv_wgrad_simt_det": (c_int, [POINTER(dc_conv_desc), dc_view, dc_view, c_void_p, c_void_p, c_int64, c_void_p]),
     "dc_conv_gemm_tc": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p]),
     "dc_conv_gemm_tc_bnstats": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p, c_void_p]),
     "dc_conv_gemm_tc_halo_ok": (c_int, [POINTER(dc_conv_desc), dc_view, dc_view]),
     "dc_conv_gemm_tc_bn_eval": (c_int, [POINTER(dc_conv_desc), dc_view, c_void_p, c_void_p, dc_view, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_float, c_int, c_void_p]),
     "dc_conv_wgrad_tc": (c_int, [POINTER(dc_conv_desc), dc_view, dc_view, c_void_p, c_void_p]),
+    "dc_conv_wgrad_tc_ws_elems": (c_int64, [POINTER(dc_conv_desc), dc_view, dc_view]),
+    "dc_conv_wgrad_tc_det": (c_int, [POINTER(dc_conv_desc), dc_view, dc_view, c_void_p, c_void_p, c_int64, c_void_p]),
     "dc_dw_fwd": (c_int, [dc_view, c_void_p, c_int, c_int, dc_view, c_void_p]),
     "dc_dw_fwd_bn": (c_int, [POINTER(dc_bn_params), dc_view, c_void_p, dc_view, dc_view, c_void_p]),
     "dc_dw_bwd_data": (c_int, [dc_view, c_void_p, c_int, c_int, dc_view, c_int, c_void_p]),
     "dc_dw_bwd_weight": (c_int, [dc_view, dc_view, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "dc_dw_bwd_weight_ws_elems": (c_int64, [dc_view, dc_view, c_int, c_int]),
+    "dc_dw_bwd_weight_det": (c_int, [dc_view, dc_view, c_int, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     "dc_dw_bwd_data_bnred": (c_int, [dc_view, c_void_p, dc_view, c_int, dc_view, dc_view, c_void_p, c_void_p, c_int, c_void_p]),
     "dc_bn_ws_bytes": (c_size_t, [c_int]),
     "dc_bn_stats": (c_int, [POINTER(dc_bn_params), dc_view, c_void_p]),
@@ -138,7 +146,8 @@ class KernelError(RuntimeError):
 
 
 # kernels launched per successful C call (cudaMemsetAsync nodes are not counted as kernels)
-_KERNELS_PER_CALL = {"dc_fill_zero": 0, "dc_wce_fwd": 2, "dc_channel_sum": 2, "dc_lamb_step_multi": 3, "dc_lars_step_multi": 2}
+_KERNELS_PER_CALL = {"dc_fill_zero": 0, "dc_wce_fwd": 2, "dc_channel_sum": 2, "dc_lamb_step_multi": 3, "dc_lars_step_multi": 2,
+                     "dc_conv_wgrad_tc_det": 2, "dc_conv_wgrad_simt_det": 2, "dc_dw_bwd_weight_det": 2}
 launch_count = 0          # number of deepcam_b200 kernels launched by this process (bench.py reports it)
 launch_hist = {}
 

@@ -110,6 +110,9 @@ class CudaBackend:
             use_tc = dtype == torch.bfloat16 and ops._lib.load().dc_device_supports_tcgen05() == 1
         self.use_tc = bool(use_tc)
         self.launches = 0
+        # bit-identical gradients from run to run (engine.deterministic()): two-stage weight-gradient reductions through a
+        # workspace, single-writer pooling reduction
+        self.deterministic = False
         self.graph_mode = False       # True while the owning plan captures CUDA graphs (engine._GraphPlan)
         self.arena = None
         self.arena_used = 0
@@ -451,13 +454,19 @@ class CudaBackend:
             K, N = spec.ci, spec.co          # G is [tap][co][ci]
         impl = "tc" if (self._tc_ok(gathered, 16) and self._tc_ok(enumerated, 16)) else "simt"
         desc = ops.make_desc(taps, (spec.stride, spec.stride), False, kk)
+        ws = None
+        if self.deterministic:
+            nws = ops.conv_wgrad_ws_elems(desc, gathered, enumerated, impl)
+            if nws > 0:
+                ws = self.scratch(nws, torch.float32)
+                self.launches += 1               # the ordered second stage
         if kk == 1 and enumerated.shape[3] == N:
-            ops.conv_wgrad(desc, gathered, enumerated, wgrad, impl)       # [co][ci] is already the parameter layout
+            ops.conv_wgrad(desc, gathered, enumerated, wgrad, impl, ws=ws)       # [co][ci] is already the parameter layout
             self.launches += 1
         else:
             ks = gathered.shape[3]               # >= K when the gathered operand is channel-padded (3 -> 4 logits)
             G = self.scratch(kk * ks * enumerated.shape[3], torch.float32, zero=True)
-            ops.conv_wgrad(desc, gathered, enumerated, G, impl)
+            ops.conv_wgrad(desc, gathered, enumerated, G, impl, ws=ws)
             ops.unpack_wgrad(G, K, N, kk, False, wgrad, k_stride=ks)
             self.launches += 2
         if bgrad is not None:
@@ -530,7 +539,11 @@ class CudaBackend:
     def dw_bwd_weight(self, x, dy, spec, wgrad):
         """wgrad: fp32 [C,1,3,3] view of the flat gradient buffer, ZERO on entry (the engine clears the flat buffer at the
         start of backward): the kernel accumulates straight into the parameter layout, no scratch and no unpack."""
-        ops.dw_bwd_weight(x, dy, spec.stride, spec.dil, wgrad, param_layout=True)
+        ws = None
+        if self.deterministic:
+            ws = self.scratch(ops.dw_bwd_weight_ws_elems(x, dy, spec.stride, spec.dil), torch.float32)
+            self.launches += 1                   # the ordered second stage
+        ops.dw_bwd_weight(x, dy, spec.stride, spec.dil, wgrad, param_layout=True, ws=ws)
         self.launches += 1
         return wgrad
 
@@ -619,6 +632,7 @@ class CudaBackend:
     def gap_fwd(self, x):
         n, _, _, c = x.shape
         out = torch.empty((n, c), dtype=torch.float32, device=self.device)
+        ops.set_deterministic(self.deterministic)
         ops.gap_fwd(x, out)
         self.launches += 2
         return out
@@ -626,6 +640,7 @@ class CudaBackend:
     def reduce_hw(self, x):
         n, _, _, c = x.shape
         out = torch.empty((n, c), dtype=torch.float32, device=self.device)
+        ops.set_deterministic(self.deterministic)
         ops.reduce_hw(x, out)
         self.launches += 2
         return out

@@ -27,6 +27,26 @@ def default_precision():
     return os.environ.get("DEEPCAM_B200_PRECISION", "bf16")
 
 
+_deterministic_override = None
+
+
+def set_deterministic(flag):
+    """True / False: force the deterministic kernels on / off; None: follow DEEPCAM_B200_DETERMINISTIC=1 and
+    torch.use_deterministic_algorithms() (what a user of the reference would call to get reproducible cuDNN gradients)."""
+    global _deterministic_override
+    _deterministic_override = None if flag is None else bool(flag)
+
+
+def deterministic():
+    """Whether module calls use the two-stage (workspace + ordered reduction) weight-gradient kernels and the single-writer
+    pooling reduction: bit-identical gradients from run to run, at the cost of one extra launch per split weight gradient."""
+    if _deterministic_override is not None:
+        return _deterministic_override
+    if os.environ.get("DEEPCAM_B200_DETERMINISTIC", "0") not in ("0", "false", "False", ""):
+        return True
+    return bool(torch.are_deterministic_algorithms_enabled())
+
+
 def set_backend_factory(factory):
     """TEST HOOK: tests/ installs a torch-CPU interpreter of the backend interface to check the graph logic
     without a GPU.  The product never calls this; the default factory builds the CUDA backend and raises on CPU."""
@@ -452,6 +472,8 @@ class _PlanFunction(torch.autograd.Function):
         inputs, params = tensors[:n_in], tensors[n_in:]
         device = inputs[0].device
         be = _make_backend(precision, device)
+        if hasattr(be, "deterministic"):
+            be.deterministic = deterministic()
         if getattr(module, "_dc_grad_sync", None) is not None and hasattr(be, "onepass_bwd"):
             be.onepass_bwd = False       # NCCL kernels share the SMs during backward: no inter-block barriers there
         need_grad = bool(need_grad)
@@ -561,6 +583,7 @@ class _GraphPlan:
         self.need_grad = need_grad
         self.be = CudaBackend(_PRECISIONS[precision], device)
         self.be.graph_mode = True
+        self.be.deterministic = deterministic()
         if getattr(module, "_dc_grad_sync", None) is not None:
             self.be.onepass_bwd = False  # NCCL kernels share the SMs during backward: no inter-block barriers there
         if need_grad and os.environ.get("DEEPCAM_B200_SIDE_BRANCH", "1") not in ("0", "false", ""):
@@ -747,7 +770,7 @@ def _graph_plan(module, precision, inputs, params, need_grad):
         return None
     key = (precision, need_grad, tuple(tuple(x.shape) + (x.dtype, bool(x.requires_grad)) for x in inputs),
            tuple(m.training for m in _bn_modules(module)), tuple(p.requires_grad for p in params), device.index,
-           torch.cuda.current_stream(device).cuda_stream, getattr(module, "_dc_plan_key", None))
+           torch.cuda.current_stream(device).cuda_stream, getattr(module, "_dc_plan_key", None), deterministic())
     plans = module.__dict__.setdefault("_dc_plans", {})
     ent = plans.get(key)
     if ent is None:

@@ -297,17 +297,43 @@ def conv_gemm_bn_eval(desc, x, w, bias, out, gamma, beta, running_mean, running_
     return state["rc"] == 0
 
 
-def conv_wgrad(desc, x, dout, G, impl):
+def set_deterministic(on):
+    """Library switch for the kernels that need no workspace to be deterministic (the pooling reduction)."""
+    lib = _lib.load()
+    if bool(lib.dc_get_deterministic()) != bool(on):
+        lib.dc_set_deterministic(int(bool(on)))
+
+
+def conv_wgrad_ws_elems(desc, x, dout, impl):
+    """fp32 elements of the workspace the deterministic two-stage weight gradient needs (0: the launch does not split)."""
+    lib = _lib.load()
+    fn = lib.dc_conv_wgrad_tc_ws_elems if impl == "tc" else lib.dc_conv_wgrad_simt_ws_elems
+    n = fn(ctypes.byref(desc), view(x), view(dout))
+    if n < 0:
+        raise ValueError("dc_conv_wgrad_%s_ws_elems: bad arguments" % impl)
+    return int(n)
+
+
+def conv_wgrad(desc, x, dout, G, impl, ws=None):
+    """ws (fp32, conv_wgrad_ws_elems() elements): deterministic two-stage form - per-split partial results in the workspace, added to
+    G in split order by a second launch."""
     _require_cuda(x, dout, G)
     assert G.dtype == torch.float32
     lib = _lib.load()
-    fn = lib.dc_conv_wgrad_tc if impl == "tc" else lib.dc_conv_wgrad_simt
     m = dout.shape[0] * dout.shape[1] * dout.shape[2]
     flops = 2.0 * m * dout.shape[3] * x.shape[3] * desc.ntaps
     nbytes = _nbytes(x, dout) + 4.0 * desc.ntaps * x.shape[3] * dout.shape[3]
+    tag = "M%d Ci%d Co%d taps%d s%d" % (m, x.shape[3], dout.shape[3], desc.ntaps, desc.stride_h)
+    if ws is not None:
+        assert ws.dtype == torch.float32 and ws.is_contiguous()
+        fn = lib.dc_conv_wgrad_tc_det if impl == "tc" else lib.dc_conv_wgrad_simt_det
+        _timed("conv_wgrad_" + impl, flops, nbytes + 8.0 * ws.numel(),
+               lambda: fn(ctypes.byref(desc), view(x), view(dout), _p(G), _p(ws), ws.numel(), _stream()), "dc_conv_wgrad_%s_det" % impl,
+               tag=tag + " det")
+        return G
+    fn = lib.dc_conv_wgrad_tc if impl == "tc" else lib.dc_conv_wgrad_simt
     _timed("conv_wgrad_" + impl, flops, nbytes,
-           lambda: fn(ctypes.byref(desc), view(x), view(dout), _p(G), _stream()), "dc_conv_wgrad_" + impl,
-           tag="M%d Ci%d Co%d taps%d s%d" % (m, x.shape[3], dout.shape[3], desc.ntaps, desc.stride_h))
+           lambda: fn(ctypes.byref(desc), view(x), view(dout), _p(G), _stream()), "dc_conv_wgrad_" + impl, tag=tag)
     return G
 
 
@@ -343,9 +369,24 @@ def dw_bwd_data(dout, w9c, stride, dil, din, accumulate):
     return din
 
 
-def dw_bwd_weight(x, dout, stride, dil, G9c, param_layout=False):
+def dw_bwd_weight_ws_elems(x, dout, stride, dil):
+    n = _lib.load().dc_dw_bwd_weight_ws_elems(view(x), view(dout), stride, dil)
+    if n < 0:
+        raise ValueError("dc_dw_bwd_weight_ws_elems: bad arguments")
+    return int(n)
+
+
+def dw_bwd_weight(x, dout, stride, dil, G9c, param_layout=False, ws=None):
+    """ws (fp32, dw_bwd_weight_ws_elems() elements): deterministic two-stage form."""
     _require_cuda(x, dout, G9c)
     assert G9c.dtype == torch.float32
+    if ws is not None:
+        assert ws.dtype == torch.float32 and ws.is_contiguous()
+        _timed("dw_bwd_weight", 18.0 * dout.numel(), _nbytes(x, dout),
+               lambda: _lib.load().dc_dw_bwd_weight_det(view(x), view(dout), stride, dil, _p(G9c), int(param_layout), _p(ws), ws.numel(),
+                                                        _stream()),
+               "dc_dw_bwd_weight_det", tag="%s s%d d%d det" % (_shape_tag(x), stride, dil))
+        return G9c
     _timed("dw_bwd_weight", 18.0 * dout.numel(), _nbytes(x, dout),
            lambda: _lib.load().dc_dw_bwd_weight(view(x), view(dout), stride, dil, _p(G9c), int(param_layout), _stream()),
            "dc_dw_bwd_weight",

@@ -882,3 +882,123 @@ def test_conv_tcgen05_eval_batchnorm_folded_into_epilogue(case):
     n0 = be.launches
     assert not be.conv_bn_eval_fwd(xg, spec, BnSpec("bn", bn), relu, torch.empty(N, Ho, Wo, Co, device=dev()))
     assert be.launches == n0
+
+
+# --------------------------------------------------------------------------------------------------
+# Deterministic mode (dc_*_det entry points + dc_set_deterministic): the split reductions of the weight-gradient kernels go through
+# a workspace and an ordered second stage.  Same parity bound as the default kernels, and two runs are bit-identical.
+DET_CONV_CASES = CONV_CASES + [
+    ("pw728_fullsize", 728, 728, 1, 1, 0, 1, 48, 72, False),      # 8 pixel splits, 256-wide ci tiles, TMA stores into the workspace
+    ("dec3x3_256", 256, 256, 3, 1, 1, 1, 40, 56, False),
+    ("skip_s2_1024", 728, 1024, 1, 2, 0, 1, 24, 36, False),
+]
+
+
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+@pytest.mark.parametrize("case", DET_CONV_CASES, ids=[c[0] for c in DET_CONV_CASES])
+def test_deterministic_conv_weight_gradient(impl, case):
+    from deepcam_b200 import ops
+    dtype = torch.bfloat16 if impl == "tc" else torch.float32
+    torch.manual_seed(16)
+    be = backend(dtype, use_tc=(impl == "tc"))
+    be.deterministic = True
+    res = _conv_case(be, dtype, *case[1:])
+    assert res["wgrad"] < TOL[dtype], (case[0], res)
+    # bit-identical repeats, and the workspace really is in play for the split launches
+    from deepcam_b200.backend import ConvSpec
+    _, Ci, Co, k, stride, pad, dil, H, W, _ = case
+    mod = torch.nn.Conv2d(Ci, Co, k, stride=stride, padding=pad, dilation=dil, bias=False).to(dev())
+    spec = ConvSpec("c", mod.weight, None, stride, pad, dil, False)
+    Ho, Wo = spec.out_hw(H, W)
+    x = torch.randn(2, H, W, Ci, device=dev()).to(dtype)
+    dy = torch.randn(2, Ho, Wo, Co, device=dev()).to(dtype)
+    runs = []
+    for _ in range(3):
+        wg = torch.zeros_like(mod.weight)
+        be.conv_bwd_weight(x, dy, spec, wg)
+        runs.append(wg)
+    torch.cuda.synchronize()
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2]), case[0]
+    be2 = backend(dtype, use_tc=(impl == "tc"))            # default (atomic / TMA reduce-add) path: same value up to summation order
+    wg2 = torch.zeros_like(mod.weight)
+    be2.conv_bwd_weight(x, dy, spec, wg2)
+    assert rel(wg2, runs[0]) < 1e-5, (case[0], rel(wg2, runs[0]))
+
+
+def test_deterministic_conv_weight_gradient_workspace_contract():
+    """dc_conv_wgrad_tc_det: the workspace size comes from dc_conv_wgrad_tc_ws_elems, a short workspace is refused, a launch that does
+    not split needs none, and the result is ADDED to G (as the default kernel does)."""
+    from deepcam_b200 import ops, convdesc
+    x = torch.randn(2, 48, 72, 728, device=dev()).bfloat16()
+    dy = torch.randn(2, 48, 72, 728, device=dev()).bfloat16()
+    desc = ops.make_desc(convdesc.conv_wgrad_taps(1, 0, 1), (1, 1), False, 1)
+    n = ops.conv_wgrad_ws_elems(desc, x, dy, "tc")
+    assert n > 0 and n % (728 * 728) == 0 and n // (728 * 728) >= 2            # one slice per pixel split
+    G = torch.zeros(728, 728, device=dev())
+    ws = torch.full((n,), float("nan"), device=dev())                            # contents irrelevant on entry
+    ops.conv_wgrad(desc, x, dy, G, "tc", ws=ws)
+    torch.cuda.synchronize()
+    assert torch.isfinite(G).all()
+    G2 = G.clone()
+    ops.conv_wgrad(desc, x, dy, G2, "tc", ws=ws)
+    assert rel(G2, 2 * G) < 1e-6
+    with pytest.raises(RuntimeError, match="workspace"):
+        ops.conv_wgrad(desc, x, dy, G, "tc", ws=ws[: n // 2])
+    # 2048 -> 256 3x3 at 12x18: 2 x 8 x 9 = 144 tiles, no pixel split - no workspace
+    xs = torch.randn(2, 12, 18, 2048, device=dev()).bfloat16()
+    dys = torch.randn(2, 12, 18, 256, device=dev()).bfloat16()
+    d9 = ops.make_desc(convdesc.conv_wgrad_taps(3, 6, 6), (1, 1), False, 9)
+    assert ops.conv_wgrad_ws_elems(d9, xs, dys, "tc") == 0
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,stride,dil,H,W", [(728, 1, 1, 48, 72), (128, 2, 1, 14, 22), (1024, 1, 2, 14, 22), (8, 1, 1, 5, 7),
+                                               (128, 1, 1, 96, 144), (256, 2, 1, 96, 144), (16, 1, 1, 11, 300), (1536, 1, 2, 48, 72)])
+def test_deterministic_depthwise_weight_gradient(dtype, C, stride, dil, H, W):
+    """dc_dw_bwd_weight_det over the staged + cluster kernel (stride 1, also through the dilation sub-grid view), and the gather
+    kernel (stride 2): parity with F.conv2d's weight gradient, bit-identical repeats, accumulation into G."""
+    from deepcam_b200.backend import DwSpec
+    torch.manual_seed(12)
+    be = backend(dtype)
+    be.deterministic = True
+    N = 2
+    w = torch.nn.Parameter(torch.randn(C, 1, 3, 3, device=dev()) * 0.3)
+    spec = DwSpec("dw", w, stride, dil)
+    x = rounded(torch.randn(N, C, H, W), dtype)
+    wr = w.detach().double().cpu().requires_grad_(True)
+    ref = F.conv2d(F.pad(x, (dil, dil, dil, dil)), wr, None, stride, 0, dil, C)
+    dy = rounded(torch.randn_like(ref), dtype)
+    ref.backward(dy)
+    xg, dyg = to_nhwc(x, dtype), to_nhwc(dy, dtype)
+    runs = []
+    for _ in range(3):
+        wg = torch.zeros(C, 1, 3, 3, device=dev())
+        be.dw_bwd_weight(xg, dyg, spec, wg)
+        runs.append(wg)
+    torch.cuda.synchronize()
+    assert rel(runs[0], wr.grad) < TOL[dtype]
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+    acc = runs[0].clone()
+    be.dw_bwd_weight(xg, dyg, spec, acc)
+    assert rel(acc, 2 * runs[0]) < 1e-6
+    be2 = backend(dtype)
+    wg2 = torch.zeros(C, 1, 3, 3, device=dev())
+    be2.dw_bwd_weight(xg, dyg, spec, wg2)
+    assert rel(wg2, runs[0]) < 1e-5
+
+
+def test_deterministic_pooling_reduction():
+    """dc_set_deterministic(1): AdaptiveAvgPool2d's reduction (DX:425) runs one block per (channel chunk, image), so the fp32 sums
+    feeding the two-value BatchNorm of the image-pooling branch are the same bits on every run."""
+    from deepcam_b200 import ops
+    be = backend(torch.bfloat16)
+    be.deterministic = True
+    x = torch.randn(2, 48, 72, 2048, device=dev()).bfloat16()
+    outs = [be.gap_fwd(x).clone() for _ in range(4)]
+    torch.cuda.synchronize()
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    assert rel(outs[0], x.float().mean(dim=(1, 2))) < 1e-5
+    be2 = backend(torch.bfloat16)
+    o2 = be2.gap_fwd(x)
+    assert ops._lib.load().dc_get_deterministic() == 0
+    assert rel(o2, outs[0]) < 1e-5

@@ -244,6 +244,78 @@ def test_cuda_graph_plan_matches_eager(sd, precision, monkeypatch):
             assert torch.allclose(sg[k], se[k], rtol=1e-3, atol=1e-4), k
 
 
+@pytest.mark.parametrize("precision,h,w_", [("fp32", 64, 96), ("bf16", 64, 96), ("fp32", 128, 192), ("bf16", 768, 1152)])
+def test_deterministic_mode_is_bit_reproducible(sd, precision, h, w_, monkeypatch):
+    """engine.set_deterministic(True) (also DEEPCAM_B200_DETERMINISTIC=1 / torch.use_deterministic_algorithms): the weight-gradient
+    reductions go through a workspace + ordered second stage and the pooling reduction has one writer, so two independent runs of
+    the same batches - eager call, capturing call, graph replays - give bit-identical logits, losses, gradients and running
+    statistics, and the eager engine agrees bit for bit with the captured plans.  The default mode's run-to-run difference is
+    recorded beside it (SURVEY section 7 'Hard parts': deterministic two-stage reduction)."""
+    from deepcam_b200 import engine
+    w = O.class_weights()
+    batches = [O.synthetic_batch(2, h, w_, seed=70 + i) for i in range(4 if h < 768 else 3)]
+
+    def run(graphs):
+        monkeypatch.setenv("DEEPCAM_B200_GRAPHS", "1" if graphs else "0")
+        net = _make(sd, precision).train()
+        res = []
+        for x, label in batches:
+            net.zero_grad()
+            out = net(x.to(DEV))
+            loss = losses.fp_loss(out, label.to(DEV), weight=w, fpw_1=w[1], fpw_2=w[2])
+            loss.backward()
+            res.append((out.detach().clone(), loss.detach().clone(), {k: p.grad.detach().clone() for k, p in net.named_parameters()}))
+        net._dc_plan_facts = [(v[1].be.deterministic, bool(v[1].bwd_segments)) for v in net.__dict__.get("_dc_plans", {}).values()
+                              if v[1] is not None]
+        if h >= 768:
+            net.__dict__.get("_dc_plans", {}).clear()          # full size: release the plan's private pool before the next instance
+        return net, res
+
+    def worst_diff(ra, rb):
+        worst = 0.0
+        for (oa, la, ga), (ob, lb, gb) in zip(ra, rb):
+            worst = max(worst, _rel(oa, ob), max(_rel(ga[k], gb[k]) for k in ga))
+        return worst
+
+    _, d1 = run(True)
+    _, d2 = run(True)
+    default_run_to_run = worst_diff(d1, d2)
+    engine.set_deterministic(True)
+    try:
+        assert engine.deterministic()
+        net_a, ra = run(True)
+        net_b, rb = run(True)
+        net_e, re_ = run(False)
+    finally:
+        engine.set_deterministic(None)
+    assert not engine.deterministic()
+    assert net_a._dc_plan_facts and all(det and segs for det, segs in net_a._dc_plan_facts)
+    mism = []
+    for name, other in (("second run", rb), ("eager engine", re_)):
+        for it, ((oa, la, ga), (ob, lb, gb)) in enumerate(zip(ra, other)):
+            if not torch.equal(oa, ob):
+                mism.append((name, it, "logits", _rel(oa, ob)))
+            if not torch.equal(la, lb):
+                mism.append((name, it, "loss", float(la - lb)))
+            for k in ga:
+                if not torch.equal(ga[k], gb[k]):
+                    mism.append((name, it, k, _rel(ga[k], gb[k])))
+    sa = net_a.state_dict()
+    for name, other in (("second run", net_b), ("eager engine", net_e)):
+        so = other.state_dict()
+        for k in sa:
+            if (k.endswith("running_mean") or k.endswith("running_var")) and not torch.equal(sa[k], so[k]):
+                mism.append((name, "buffers", k, _rel(sa[k], so[k])))
+    _record("deterministic_%s_%dx%d" % (precision, h, w_), dict(tile=[h, w_], calls=["eager", "capture", "replay", "replay"][:len(batches)],
+                                                 tensors_compared=len(ra) * (2 + len(ra[0][2])) * 2,
+                                                 mismatches=[list(map(str, m)) for m in mism[:20]], n_mismatches=len(mism),
+                                                 default_mode_run_to_run_worst_rel=default_run_to_run,
+                                                 deterministic_vs_default_worst_rel=worst_diff(ra, d1)))
+    assert not mism, mism[:10]
+    # same mathematics as the default kernels: only the summation order differs
+    assert worst_diff(ra, d1) < (1e-3 if precision == "fp32" else 0.25)
+
+
 def test_cuda_graph_plan_rejects_stale_backward(sd, monkeypatch):
     monkeypatch.setenv("DEEPCAM_B200_GRAPHS", "1")
     net = _make(sd, "fp32").train()
