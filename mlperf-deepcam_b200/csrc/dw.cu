@@ -12,10 +12,45 @@
 // of a stride-1 layer = the same kernel with the 3x3 filter flipped) are input-stationary: each input row is loaded
 // and unpacked once per strip and scattered into the three live output rows with packed fp32 FMAs (FFMA2).
 #include "common.cuh"
+#include <cuda.h>
 #include <algorithm>
+#include <mutex>
 #include <stdlib.h>
+#include <string.h>
 
 namespace dc {
+
+// ---- TMA tile fill of the staged kernels -----------------------------------------------------------------------------------
+// The staged kernels used to fill their shared-memory tiles with one 16-byte cp.async per thread and vector: 43-61 instructions
+// per vector for address + bounds arithmetic, 46 % of all instructions of the weight-gradient kernel on the 113 MB tensors (ncu
+// source page, round 2).  One un-swizzled 4-D TMA box per tile ({cvp*V channels, tile width, tile rows, 1 image} of the NHWC
+// tensor, out-of-range pixels and channels zero-filled = fixed_padding) is issued by ONE thread and lands in exactly the
+// [row][pixel][channel vector] layout the row walk reads.
+__device__ __forceinline__ void dw_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void dw_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dw_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void dw_tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 
 // ---- 16-byte channel vectors -------------------------------------------------------------------------------
 template <typename T> struct dwvec;
@@ -255,11 +290,12 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-template <typename T, int V>
+template <typename T, int V, bool kTma>
 __global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_kernel(DwView<const T> in, const T* __restrict__ w9c, DwView<T> out, int C,
-                                                                  DwMap m, int flip, int accumulate) {
+                                                                  DwMap m, int flip, int accumulate, const __grid_constant__ CUtensorMap in_map) {
   constexpr int VP = V / 2;
-  extern __shared__ uint4 dw_tile[];                  // [rs + 2][ppb + 2][cvp]
+  extern __shared__ __align__(128) uint4 dw_tile[];   // [rs + 2][ppb + 2][cvp]
+  __shared__ __align__(8) uint64_t tma_bar;
   const DwLane l = dw_lane(m, out.h, out.w);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
@@ -269,8 +305,19 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_kernel(DwView<const T
   const int cv0 = blockIdx.y * m.cvp;
   const int H = in.h, W = in.w;
   const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(dw_tile);
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+  if (kTma) {
+    if (threadIdx.x == 0) dw_mbar_init(bar_s, 1);
+    __syncthreads();
+  }
   pdl_sync();
-  {
+  if (kTma) {
+    // one box = the whole tile, halo included; rows / pixels / channels outside the tensor arrive as zeros
+    if (threadIdx.x == 0) {
+      dw_mbar_expect_tx(bar_s, (uint32_t)((m.rs + 2) * TW * m.cvp * 16));
+      dw_tma_load_4d(&in_map, bar_s, tile_s, cv0 * V, x_base, y_base, l.n);
+    }
+  } else {
     const int nvec = nrows * TW * m.cvp;
     const int cshift = 31 - __clz(m.cvp);
     const T* nbase = in.p + in.img(l.n);
@@ -294,8 +341,12 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_kernel(DwView<const T
 #pragma unroll
     for (int k = 0; k < 9; ++k) dwpair<T>::unpack(ld16(w9c + (size_t)(flip ? 8 - k : k) * C + c0), wv[k]);
   }
-  cp_async_commit_wait_all();
-  __syncthreads();
+  if (kTma) {
+    dw_mbar_wait(bar_s, 0);
+  } else {
+    cp_async_commit_wait_all();
+    __syncthreads();
+  }
   if (!l.ok) return;
   T* obase = out.p + out.img(l.n) + (long long)l.x * out.sw + l.cvi * V;
   const uint4* tp = dw_tile + ((warp * m.ppw + psub) * m.cvp + cvl);      // tile column of x-1, row 0
@@ -1009,11 +1060,14 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_saddr, uint32_t ran
   return v;
 }
 
-template <typename T, int V>
+template <typename T, int V, bool kTma>
 __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwView<const T> in, DwView<const T> dout, float* __restrict__ Gout,
-                                                                          int C, DwMap m, int tap_stride, int c_stride, int spc, int det) {
+                                                                          int C, DwMap m, int tap_stride, int c_stride, int spc, int det,
+                                                                          const __grid_constant__ CUtensorMap in_map,
+                                                                          const __grid_constant__ CUtensorMap g_map) {
   constexpr int VP = V / 2;
-  extern __shared__ uint4 dww_smem[];                 // in tile [rs + 2][ppb + 2][cvp] | dout tile [rs][ppb][cvp]   (then reused)
+  extern __shared__ __align__(128) uint4 dww_smem[];  // in tile [rs + 2][ppb + 2][cvp] | dout tile [rs][ppb][cvp]   (then reused)
+  __shared__ __align__(8) uint64_t tma_bar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
   const int TW = m.ppb + 2;
@@ -1026,7 +1080,13 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwVie
   const int cv0 = blockIdx.y * m.cvp;
   const int H = in.h, W = in.w;
   uint4* in_t = dww_smem;
-  uint4* g_t = dww_smem + (m.rs + 2) * TW * m.cvp;
+  uint4* g_t = dww_smem + (((m.rs + 2) * TW * m.cvp + 7) & ~7);       // 128-byte aligned (TMA destination)
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+  uint32_t tma_phase = 0;
+  if (kTma) {
+    if (threadIdx.x == 0) dw_mbar_init(bar_s, 1);
+    __syncthreads();
+  }
   const int cshift = 31 - __clz(m.cvp);
   const int cl = threadIdx.x & (m.cvp - 1), cvi_f = cv0 + cl;
   const int pstep = kDwThreads >> cshift;
@@ -1042,7 +1102,17 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwVie
     const int orows = y1 - y0, nrows = orows + 2;     // dout rows y0 .. y1-1, input rows y0-1 .. y1
     const int y_base = y0 - 1;
     if (strip != chunk * spc) __syncthreads();        // the previous strip's walk is over: its tiles may be overwritten
-    {
+    if (kTma) {
+      // two boxes: input rows y0-1 .. y0+rs with a one-pixel halo left and right, dout rows y0 .. y0+rs-1; everything outside the
+      // tensors (and the rows past a short last strip, which lie outside the image) arrives as zeros
+      if (threadIdx.x == 0) {
+        dw_mbar_expect_tx(bar_s, (uint32_t)(((m.rs + 2) * TW + m.rs * m.ppb) * m.cvp * 16));
+        dw_tma_load_4d(&in_map, bar_s, (uint32_t)__cvta_generic_to_shared(in_t), cv0 * V, x_base, y_base, vn);
+        dw_tma_load_4d(&g_map, bar_s, (uint32_t)__cvta_generic_to_shared(g_t), cv0 * V, x0, y0, vn);
+      }
+      dw_mbar_wait(bar_s, tma_phase);
+      tma_phase ^= 1u;
+    } else {
       const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(in_t);
       const T* nbase = in.p + in.img(vn);
       const int nvec = nrows * TW * m.cvp;
@@ -1065,9 +1135,9 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwVie
         tx += pstep;
         while (tx >= m.ppb) { tx -= m.ppb; ++ty; }
       }
+      cp_async_commit_wait_all();
+      __syncthreads();
     }
-    cp_async_commit_wait_all();
-    __syncthreads();
     {
       // thread = (channel vector cvl, pixel column col of the block); input-stationary walk over the staged rows:
       // input row r meets dout rows r+1 (filter row 0), r (row 1), r-1 (row 2)
@@ -1247,6 +1317,46 @@ static inline int dw_dsub(int s, int d, int h, int w) {
   return (enabled && d <= 4 && h % d == 0 && w % d == 0) ? d : 0;
 }
 
+// ---- host side of the TMA tile fill ----------------------------------------------------------------------------------------
+typedef CUresult (*PFN_dwEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_dwEncodeTiled dw_get_encode() {
+  static PFN_dwEncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_dwEncodeTiled>(f);
+  });
+  return fn;
+}
+// DEEPCAM_B200_DW_TMA=0: cp.async tile fills (A/B measurements)
+static bool dw_tma_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DEEPCAM_B200_DW_TMA"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+// un-swizzled 4-D map {C, W, H, N} of an NHWC view with box {box_c, box_w, box_h, 1}; false = not expressible (the caller keeps
+// the cp.async fill): box extents > 256, strides that are not multiples of 16 bytes, encode failure
+static bool dw_encode_tile_map(CUtensorMap* map, const dc_view& v, int box_c, int box_w, int box_h) {
+  if (!dw_tma_enabled()) return false;
+  PFN_dwEncodeTiled enc = dw_get_encode();
+  if (enc == nullptr) return false;
+  const int es = v.dtype == DC_F32 ? 4 : 2;
+  if (box_c > 256 || box_w > 256 || box_h > 256 || box_c < 1 || box_w < 1 || box_h < 1 || (box_c * es) % 16) return false;
+  if (v.sc != 1 || (v.sw * es) % 16 || (v.sh * es) % 16 || (v.sn * es) % 16 || (reinterpret_cast<uintptr_t>(v.ptr) % 16)) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)v.c, (cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)v.n};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sw * es, (cuuint64_t)v.sh * es, (cuuint64_t)std::max<long long>(v.sn, 1) * es};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, v.dtype == DC_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 template <typename T, int V>
 static bool dw_s1d1_tile_launch(const dc_view& in, const void* w, const dc_view& out, int flip, int acc, cudaStream_t st, int dsub = 1) {
   if (!dw_tile_enabled()) return false;
@@ -1255,13 +1365,23 @@ static bool dw_s1d1_tile_launch(const dc_view& in, const void* w, const dc_view&
   dim3 grid = dw_grid(m, ow, nimg);
   const size_t smem = (size_t)(m.rs + 2) * (m.ppb + 2) * m.cvp * 16;
   if (smem > 200 * 1024) return false;                                         // odd row counts: register-pipelined kernel
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(dw_s1d1_tile_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return false;
-    attr_set = true;
+  static bool attr_set[2] = {false, false};
+  CUtensorMap map;
+  const bool tma = dsub == 1 && dw_encode_tile_map(&map, in, m.cvp * V, m.ppb + 2, m.rs + 2);
+  if (!attr_set[tma]) {
+    cudaError_t e = tma ? cudaFuncSetAttribute(dw_s1d1_tile_kernel<T, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                        : cudaFuncSetAttribute(dw_s1d1_tile_kernel<T, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return false;
+    attr_set[tma] = true;
   }
-  launch_k(dw_s1d1_tile_kernel<T, V>, grid, dim3(kDwThreads), smem, st, dw_view<const T>(in, dsub), (const T*)w, dw_view<T>(out, dsub), out.c, m,
-           flip, acc);
+  if (tma)
+    launch_k(dw_s1d1_tile_kernel<T, V, true>, grid, dim3(kDwThreads), smem, st, dw_view<const T>(in, dsub), (const T*)w, dw_view<T>(out, dsub), out.c,
+             m, flip, acc, map);
+  else {
+    memset(&map, 0, sizeof(map));
+    launch_k(dw_s1d1_tile_kernel<T, V, false>, grid, dim3(kDwThreads), smem, st, dw_view<const T>(in, dsub), (const T*)w, dw_view<T>(out, dsub), out.c,
+             m, flip, acc, map);
+  }
   return true;
 }
 
@@ -1402,7 +1522,8 @@ static DwwPlan dww_plan(const dc_view& in, const dc_view& dout, int s, int d) {
     m.nstrips = ceil_div(gh, 10);
     m.rs = ceil_div(gh, m.nstrips);
     m.nstrips = ceil_div(gh, m.rs);
-    const size_t tiles = ((size_t)(m.rs + 2) * (m.ppb + 2) + (size_t)m.rs * m.ppb) * m.cvp * 16;
+    const size_t in_vecs = ((size_t)(m.rs + 2) * (m.ppb + 2) * m.cvp + 7) & ~(size_t)7;      // dout tile starts 128-byte aligned
+    const size_t tiles = (in_vecs + (size_t)m.rs * m.ppb * m.cvp) * 16;
     const size_t scratch = ((size_t)8 * 32 * 3 * V + (size_t)9 * m.cvp * V) * sizeof(float);
     const size_t smem = std::max(tiles, scratch);
     if (smem <= 110 * 1024) {
@@ -1444,10 +1565,17 @@ static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d,
   int nslices = (int)(pl.grid.x * pl.grid.z);
   bool launched = false;
   if (pl.tile) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      if (cudaFuncSetAttribute(dw_bwd_weight_tile_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) == cudaSuccess) attr_set = true;
+    static bool attr_done[2] = {false, false};
+    CUtensorMap in_map, g_map;
+    const bool tma = pl.dsub == 1 && dw_encode_tile_map(&in_map, in, pl.m.cvp * V, pl.m.ppb + 2, pl.m.rs + 2) &&
+                     dw_encode_tile_map(&g_map, dout, pl.m.cvp * V, pl.m.ppb, pl.m.rs);
+    if (!tma) { memset(&in_map, 0, sizeof(in_map)); memset(&g_map, 0, sizeof(g_map)); }
+    if (!attr_done[tma]) {
+      cudaError_t e = tma ? cudaFuncSetAttribute(dw_bwd_weight_tile_kernel<T, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)
+                          : cudaFuncSetAttribute(dw_bwd_weight_tile_kernel<T, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+      if (e == cudaSuccess) attr_done[tma] = true;
     }
+    const bool attr_set = attr_done[tma];
     if (attr_set) {
       // cluster = consecutive blockIdx.z (strips / images / parity sub-grids of one (x block, channel group)): largest divisor <= 8
       static int cz_max = -1;         // DEEPCAM_B200_DWW_CLUSTER: largest cluster size tried (1 = no cluster reduction)
@@ -1463,8 +1591,10 @@ static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d,
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = pdl_enabled() ? 2 : 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, dw_bwd_weight_tile_kernel<T, V>, dw_view<const T>(in, pl.dsub), dw_view<const T>(dout, pl.dsub), target,
-                                           dout.c, pl.m, tap_stride, c_stride, pl.spc, det);
+        cudaError_t e = tma ? cudaLaunchKernelEx(&cfg, dw_bwd_weight_tile_kernel<T, V, true>, dw_view<const T>(in, pl.dsub),
+                                                 dw_view<const T>(dout, pl.dsub), target, dout.c, pl.m, tap_stride, c_stride, pl.spc, det, in_map, g_map)
+                            : cudaLaunchKernelEx(&cfg, dw_bwd_weight_tile_kernel<T, V, false>, dw_view<const T>(in, pl.dsub),
+                                                 dw_view<const T>(dout, pl.dsub), target, dout.c, pl.m, tap_stride, c_stride, pl.spc, det, in_map, g_map);
         if (e == cudaSuccess) {
           launched = true;
           nslices = (int)(pl.grid.x * (pl.grid.z / cz));
