@@ -950,11 +950,13 @@ __global__ void __launch_bounds__(kDwThreads) dw_bwd_weight_s1d1_kernel(DwView<c
 // flight at once; a thread (channel vector, dout column) walks down the rows keeping d[y][x], d[y][x+1] in registers and writes
 // the quad's four 16-byte vectors.  The gather-form dw_bwd_data_strided_kernel it replaces ran at 1.1 TB/s on the 113 MB
 // gradient of block1 (124 us): per input pixel it tested nine taps for parity and issued dependent global loads.
-template <typename T, int V>
+template <typename T, int V, bool kTma>
 __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_data_s2_tile_kernel(DwView<const T> dout, const T* __restrict__ w9c, DwView<T> din,
-                                                                           int C, DwMap m, int accumulate) {
+                                                                           int C, DwMap m, int accumulate,
+                                                                           const __grid_constant__ CUtensorMap g_map) {
   constexpr int VP = V / 2;
-  extern __shared__ uint4 dw_tile[];                  // [rs + 1][ppb + 1][cvp]
+  extern __shared__ __align__(128) uint4 dw_tile[];   // [rs + 1][ppb + 1][cvp]
+  __shared__ __align__(8) uint64_t tma_bar;
   const DwLane l = dw_lane(m, dout.h, dout.w);        // rows / columns of dout
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
@@ -965,8 +967,18 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_data_s2_tile_kernel(DwVi
   const int Ho = dout.h, Wo = dout.w;
   const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(dw_tile);
   const int cshift = 31 - __clz(m.cvp);
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+  if (kTma) {
+    if (threadIdx.x == 0) dw_mbar_init(bar_s, 1);
+    __syncthreads();
+  }
   pdl_sync();
-  {
+  if (kTma) {
+    if (threadIdx.x == 0) {
+      dw_mbar_expect_tx(bar_s, (uint32_t)((m.rs + 1) * TW * m.cvp * 16));
+      dw_tma_load_4d(&g_map, bar_s, tile_s, cv0 * V, x0, l.y0, l.n);
+    }
+  } else {
     const T* nbase = dout.p + dout.img(l.n);
     const int nvec = nrows * TW * m.cvp;
     const int cl = threadIdx.x & (m.cvp - 1), cvi = cv0 + cl;
@@ -986,8 +998,12 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_data_s2_tile_kernel(DwVi
 #pragma unroll
     for (int k = 0; k < 9; ++k) dwpair<T>::unpack(ld16(w9c + (size_t)k * C + c0), wv[k]);
   }
-  cp_async_commit_wait_all();
-  __syncthreads();
+  if (kTma) {
+    dw_mbar_wait(bar_s, 0);
+  } else {
+    cp_async_commit_wait_all();
+    __syncthreads();
+  }
   if (!l.ok) return;
   const int H = din.h, W = din.w;
   const int ix = 2 * l.x;
@@ -1466,12 +1482,22 @@ static int dw_bwd_data_t(const dc_view& dout, const void* w, int s, int d, const
       mt.rs = ceil_div(dout.h, mt.nstrips);
       mt.nstrips = ceil_div(dout.h, mt.rs);
       const size_t smem = (size_t)(mt.rs + 1) * (mt.ppb + 1) * mt.cvp * 16;
-      static bool attr_set = false;
-      if (!attr_set && cudaFuncSetAttribute(dw_bwd_data_s2_tile_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) == cudaSuccess)
-        attr_set = true;
-      if (attr_set && smem <= 110 * 1024) {
-        launch_k(dw_bwd_data_s2_tile_kernel<T, V>, dw_grid(mt, dout.w, dout.n), dim3(kDwThreads), smem, st, dw_view<const T>(dout), (const T*)w,
-                 dw_view<T>(din), din.c, mt, acc);
+      static bool attr_done[2] = {false, false};
+      CUtensorMap g_map;
+      const bool tma = smem <= 110 * 1024 && dw_encode_tile_map(&g_map, dout, mt.cvp * V, mt.ppb + 1, mt.rs + 1);
+      if (!tma) memset(&g_map, 0, sizeof(g_map));
+      if (!attr_done[tma]) {
+        cudaError_t e = tma ? cudaFuncSetAttribute(dw_bwd_data_s2_tile_kernel<T, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)
+                            : cudaFuncSetAttribute(dw_bwd_data_s2_tile_kernel<T, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        if (e == cudaSuccess) attr_done[tma] = true;
+      }
+      if (attr_done[tma] && smem <= 110 * 1024) {
+        if (tma)
+          launch_k(dw_bwd_data_s2_tile_kernel<T, V, true>, dw_grid(mt, dout.w, dout.n), dim3(kDwThreads), smem, st, dw_view<const T>(dout), (const T*)w,
+                   dw_view<T>(din), din.c, mt, acc, g_map);
+        else
+          launch_k(dw_bwd_data_s2_tile_kernel<T, V, false>, dw_grid(mt, dout.w, dout.n), dim3(kDwThreads), smem, st, dw_view<const T>(dout), (const T*)w,
+                   dw_view<T>(din), din.c, mt, acc, g_map);
         return launch_status("dc_dw_bwd_data");
       }
     }

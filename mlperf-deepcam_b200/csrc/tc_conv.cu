@@ -1282,6 +1282,223 @@ __global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
+// wgrad, HALO mode: multi-tap weight gradients whose gathered operand has few channels (conv1 16 -> 32 k3 s2, conv2 32 -> 64 k3,
+// last_deconv's 256 -> 3(8) k3 s2: DX:144,148,374).  conv_wgrad_tc_kernel runs ONE tap per CTA with a 64-channel TMA box per
+// operand: 9 CTAs re-read the same dY tile, three quarters of every gathered box are zero fill, and each 128x64x16 MMA costs
+// ~165 clk of issue for 16 useful columns (145 / 92 / 260 us for 13 / 13 / 39 us of HBM time, profiles/r02_roofline_table.md).
+// Here a CTA owns ALL taps of a tap group: per 128-pixel tile it loads the dY tile once (A, MN-major, 128B swizzle, as before) and
+// the tile's input REGION once (un-swizzled boxes, halo included, zero fill = padding); four builder warps copy the region into
+// ONE MN-major B operand whose N index is (tap, channel) - 16-byte chunks, 128B-swizzled rows of 64 N elements - so that a tile
+// takes 8 MMAs of N = taps x Ci (<= 192) instead of 8 per tap.  D[co][tap * Ci + ci] accumulates in TMEM over the CTA's pixel
+// split and is added to G[wt[tap]][co][ci] at the end (red.global.add.v4.f32, or plain stores into the split's workspace slice
+// in deterministic mode).
+// ------------------------------------------------------------------------------------------------
+struct TcWgradHaloParams {
+  int tiles_x, tiles_y, n_img;
+  int mtiles_total, mtiles_per_split;
+  int Co, Ci;                       // Ci = gathered channels (multiple of 8, <= 64)
+  int s;                            // gather stride 1 | 2
+  int halo_w, halo_h, halo_nbox, halo_bytes, halo_stride;
+  int halo_x0, halo_y0;             // smallest tap offset: input coordinate of the region's first pixel relative to stride * tile origin
+  int a_boxes, a_bytes;             // 64-channel dY boxes per tile (1 when Co <= 64), bytes per A stage
+  int sa, sr;                       // A stages, region stages
+  int nblk;                         // 64-column blocks of the B operand (ceil(npad / 64))
+  int ngroups;
+  int g_first[3], g_count[3], g_npad[3];     // taps of tap group g: [g_first, g_first + g_count), N padded to a multiple of 16
+  int qh[DC_MAX_TAPS], qw[DC_MAX_TAPS], wt[DC_MAX_TAPS];
+  int det_wtaps;
+  int tmem_cols;
+  float* G;
+};
+constexpr int kWgradHaloThreads = 448;    // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue, warps 6..13 B builders
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kWgradHaloThreads, 1) conv_wgrad_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcWgradHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // [A stages][region stages][2 B buffers][barriers]
+  const uint32_t a_off = 0u, r_off = (uint32_t)(p.sa * p.a_bytes), b_off = r_off + (uint32_t)(p.sr * p.halo_stride);
+  const uint32_t b_bytes = (uint32_t)p.nblk * 16384u;
+  const uint32_t bar_base = smem_base + b_off + 2u * b_bytes;
+  auto afull = [&](int i) { return bar_base + 8u * i; };
+  auto aempty = [&](int i) { return bar_base + 8u * (4 + i); };
+  auto rfull = [&](int i) { return bar_base + 8u * (8 + i); };
+  auto rempty = [&](int i) { return bar_base + 8u * (12 + i); };
+  auto bfull = [&](int i) { return bar_base + 8u * (16 + i); };
+  auto bempty = [&](int i) { return bar_base + 8u * (18 + i); };
+  const uint32_t tmem_full_bar = bar_base + 8u * 20;
+  const uint32_t tmem_slot = bar_base + 8u * 21;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.x * 128;
+  const int g = blockIdx.y;
+  const int t0 = p.g_first[g], nt = p.g_count[g], npad = p.g_npad[g];
+  const int mt_begin = blockIdx.z * p.mtiles_per_split;
+  const int mt_end = min(p.mtiles_total, mt_begin + p.mtiles_per_split);
+  const int n_iter = mt_end - mt_begin;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(afull(i), 1); mbar_init(aempty(i), 1); mbar_init(rfull(i), 1); mbar_init(rempty(i), 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bfull(i), 8); mbar_init(bempty(i), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.b);
+    tma_prefetch_desc(&maps.a[0]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_sync();
+
+  if (n_iter > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int it = 0; it < n_iter; ++it) {
+          int r = mt_begin + it;
+          const int tile_x = r % p.tiles_x; r /= p.tiles_x;
+          const int tile_y = r % p.tiles_y;
+          const int img = r / p.tiles_y;
+          const int sa = it % p.sa, sr = it % p.sr;
+          // A = dY tile: one or two 64-channel boxes of 128 pixels (8 rows x 16 columns)
+          mbar_wait(aempty(sa), (((uint32_t)(it / p.sa)) & 1u) ^ 1u);
+          mbar_expect_tx(afull(sa), (uint32_t)p.a_bytes);
+          for (int b = 0; b < p.a_boxes; ++b)
+            tma_load_4d(&maps.b, afull(sa), smem_base + a_off + (uint32_t)(sa * p.a_bytes + b * 16384), co0 + b * 64, tile_x * kHaloTW,
+                        tile_y * kHaloTH, img);
+          // the tile's input region: halo_nbox boxes of {256 flattened (w, c) elements, halo_h rows}
+          mbar_wait(rempty(sr), (((uint32_t)(it / p.sr)) & 1u) ^ 1u);
+          mbar_expect_tx(rfull(sr), (uint32_t)p.halo_bytes);
+          const int fx = (tile_x * kHaloTW * p.s + p.halo_x0) * p.Ci;
+          const int hy = tile_y * kHaloTH * p.s + p.halo_y0;
+          for (int b = 0; b < p.halo_nbox; ++b)
+            tma_load_3d(&maps.a[0], rfull(sr), smem_base + r_off + (uint32_t)(sr * p.halo_stride + b * p.halo_h * 512), fx + b * 256, hy, img);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc(128, npad, 1, 1);
+        for (int it = 0; it < n_iter; ++it) {
+          const int sa = it % p.sa, bb = it & 1;
+          mbar_wait(afull(sa), ((uint32_t)(it / p.sa)) & 1u);
+          mbar_wait(bfull(bb), ((uint32_t)(it >> 1)) & 1u);
+          tc_fence_after();
+          // MN-major SW128 operands: LBO = stride between 64-element MN blocks (16 KB), SBO = 8 k-rows = 1024 B
+          const uint64_t da = make_smem_desc(smem_base + a_off + (uint32_t)(sa * p.a_bytes), 16384, 1024);
+          const uint64_t db = make_smem_desc(smem_base + b_off + (uint32_t)bb * b_bytes, 16384, 1024);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)      // 16 pixels (K) per instruction = 16 rows of 128 B = +128 in the (>>4) address field
+            umma_bf16(tmem_base, da + 128u * k, db + 128u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(aempty(sa));
+          umma_commit(bempty(bb));
+        }
+        umma_commit(tmem_full_bar);
+      }
+    } else if (warp >= 6) {
+      // ---- B builders: row = tile pixel (ty, tx) = K index, N index = tap * Ci + ci.  Chunk q of a row (q = tap * Ci / 8 + c) is
+      //      the 16 bytes of channels 8c .. 8c+7 of the pixel the tap gathers: region -> block (q / 8), logical chunk q % 8 of the
+      //      row, physical chunk = logical ^ (row & 7) (the 128B swizzle the MN-major descriptor expects).
+      //      lane = (rsub, j): a warp instruction moves chunks 8*qb + j (j = 0..7) of 4 rows, so a quarter-warp reads one row's
+      //      consecutive chunks - the taps (kh, 0..2) of a pixel are adjacent pixels, i.e. one contiguous run of the region -
+      //      and writes 8 distinct 16-byte columns of one 128-byte line: no bank conflicts on either side (one thread per row
+      //      with a tap-major walk cost 4-way conflicts on every load: 1600 of the ~3000 clk per tile, round 2).  Warp bw owns rows
+      //      16*bw .. +15 (4 passes of 4 rows); all source / destination offsets are tile-independent and live in registers. ----
+      const int bw = warp - 6;
+      const int rsub = lane >> 3, j = lane & 7;
+      const int c16 = p.Ci >> 3;
+      const int boxpitch = p.halo_h * 256;
+      const int nchunks = nt * c16;
+      const int nqb = ((npad >> 3) + 7) >> 3;                          // batches of 8 chunks, the zero padding chunk included
+      int soff[3][4];                                                   // < 0: nothing to move; -2: write zeros (padding chunk)
+      uint32_t doff[3][4];
+#pragma unroll
+      for (int qb = 0; qb < 3; ++qb)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int q = qb * 8 + j;
+          const int row = bw * 16 + u * 4 + rsub;
+          const int ty = row >> 4, tx = row & 15;
+          soff[qb][u] = -1;
+          doff[qb][u] = (uint32_t)row * 128u + (uint32_t)(q >> 3) * 16384u + (uint32_t)(((q & 7) ^ (row & 7)) << 4);
+          if (q < nchunks) {
+            const int t = q / c16, c = q - t * c16;
+            const int hyy = ty * p.s + p.qh[t0 + t];
+            const int f = (tx * p.s + p.qw[t0 + t]) * p.Ci + c * 8;
+            soff[qb][u] = ((f >> 8) * boxpitch + hyy * 256 + (f & 255)) * 2;
+          } else if (q == nchunks && q * 8 < npad) {
+            soff[qb][u] = -2;
+          }
+        }
+      for (int it = 0; it < n_iter; ++it) {
+        const int sr = it % p.sr, bb = it & 1;
+        mbar_wait(rfull(sr), ((uint32_t)(it / p.sr)) & 1u);
+        mbar_wait(bempty(bb), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+        const uint8_t* hptr = smem_gen + r_off + (uint32_t)(sr * p.halo_stride);
+        uint8_t* bptr = smem_gen + b_off + (uint32_t)bb * b_bytes;
+#pragma unroll
+        for (int qb = 0; qb < 3; ++qb) {
+          if (qb < nqb) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              v[u] = soff[qb][u] >= 0 ? *reinterpret_cast<const uint4*>(hptr + soff[qb][u]) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (soff[qb][u] != -1) *reinterpret_cast<uint4*>(bptr + doff[qb][u]) = v[u];
+          }
+        }
+        fence_proxy_async();                          // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(bfull(bb)); mbar_arrive(rempty(sr)); }
+      }
+    } else {
+      // ---- epilogue: lane = co row; tap by tap, 8 columns at a time ----
+      const int lg = warp & 3;
+      const int co = co0 + lg * 32 + lane;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      for (int t = 0; t < nt; ++t) {
+        const int wt = p.wt[t0 + t];
+        const int wslice = p.det_wtaps > 0 ? (int)blockIdx.z * p.det_wtaps + wt : wt;
+        float* Grow = p.G + ((size_t)wslice * p.Co + (size_t)(co < p.Co ? co : 0)) * p.Ci;
+        for (int c0 = 0; c0 < p.Ci; c0 += 8) {
+          uint32_t v[8];
+          tmem_ld8(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * p.Ci + c0), v);
+          tmem_ld_wait();
+          if (co < p.Co) {
+            if (p.det_wtaps > 0) {
+              *reinterpret_cast<float4*>(Grow + c0) = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+              *reinterpret_cast<float4*>(Grow + c0 + 4) = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+            } else {
+              red_add_v4(Grow + c0, v[0], v[1], v[2], v[3]);
+              red_add_v4(Grow + c0 + 4, v[4], v[5], v[6], v[7]);
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1765,6 +1982,68 @@ static void wgrad_split_plan(const dc_conv_desc* d, const dc_view& in, const dc_
   splits = ceil_div(mtiles_total, per_split);
 }
 
+// Halo mode of the weight gradient (conv_wgrad_tc_halo_kernel): multi-tap, uniform stride 1 | 2, gathered operand with <= 64
+// channels in dense NHWC rows.  Fills p (everything but G / det_wtaps) and the split count; false = use the per-tap kernel.
+static bool plan_wgrad_halo(const dc_conv_desc* d, const dc_view& in, const dc_view& dout, TcWgradHaloParams& p, int& splits, int& smem_bytes) {
+  static int enabled = -1;        // DEEPCAM_B200_WGRAD_HALO=0: per-tap kernel (A/B measurements)
+  if (enabled < 0) { const char* e = getenv("DEEPCAM_B200_WGRAD_HALO"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (!enabled) return false;
+  if (d->ntaps < 2 || d->stride_h != d->stride_w || (d->stride_h != 1 && d->stride_h != 2)) return false;
+  if (in.c > 64 || in.c % 8 || in.sw != in.c || in.sc != 1) return false;
+  int dh0 = d->dh[0], dh1 = d->dh[0], dw0 = d->dw[0], dw1 = d->dw[0];
+  for (int t = 1; t < d->ntaps; ++t) {
+    dh0 = std::min(dh0, d->dh[t]); dh1 = std::max(dh1, d->dh[t]);
+    dw0 = std::min(dw0, d->dw[t]); dw1 = std::max(dw1, d->dw[t]);
+  }
+  if (dh1 - dh0 > 4 || dw1 - dw0 > 4) return false;
+  for (int a = 0; a < d->ntaps; ++a)
+    for (int b = a + 1; b < d->ntaps; ++b)
+      if (d->wt[a] == d->wt[b]) return false;
+  p = TcWgradHaloParams();
+  p.s = d->stride_h;
+  p.Co = dout.c; p.Ci = in.c;
+  p.tiles_x = ceil_div(dout.w, kHaloTW);
+  p.tiles_y = ceil_div(dout.h, kHaloTH);
+  p.n_img = dout.n;
+  p.mtiles_total = p.tiles_x * p.tiles_y * dout.n;
+  p.halo_x0 = dw0; p.halo_y0 = dh0;
+  p.halo_h = (kHaloTH - 1) * p.s + (dh1 - dh0) + 1;
+  p.halo_w = (kHaloTW - 1) * p.s + (dw1 - dw0) + 1;
+  p.halo_nbox = ceil_div(p.halo_w * in.c, 256);
+  p.halo_bytes = p.halo_nbox * p.halo_h * 512;
+  p.halo_stride = round_up_i(p.halo_bytes, 1024);
+  // tap groups: N = taps x Ci <= 192 per CTA (three 64-column blocks of the B operand, double buffered)
+  const int per_group = std::max(1, 192 / in.c);
+  p.ngroups = ceil_div(d->ntaps, per_group);
+  if (p.ngroups > 3) return false;
+  const int even = ceil_div(d->ntaps, p.ngroups);
+  int first = 0, max_npad = 0;
+  for (int g = 0; g < p.ngroups; ++g) {
+    p.g_first[g] = first;
+    p.g_count[g] = std::min(even, d->ntaps - first);
+    p.g_npad[g] = round_up_i(p.g_count[g] * in.c, 16);
+    max_npad = std::max(max_npad, p.g_npad[g]);
+    first += p.g_count[g];
+  }
+  for (int t = 0; t < d->ntaps; ++t) { p.qh[t] = d->dh[t] - dh0; p.qw[t] = d->dw[t] - dw0; p.wt[t] = d->wt[t]; }
+  p.nblk = ceil_div(max_npad, 64);
+  p.tmem_cols = 32;
+  while (p.tmem_cols < max_npad) p.tmem_cols <<= 1;
+  p.a_boxes = dout.c > 64 ? 2 : 1;
+  p.a_bytes = p.a_boxes * 16384;
+  const int fixed = 2 * p.nblk * 16384 + 1024 + 256;
+  int st = 4;
+  while (st >= 2 && fixed + st * (p.a_bytes + p.halo_stride) > 227 * 1024) --st;
+  if (st < 2) return false;
+  p.sa = p.sr = st;
+  smem_bytes = fixed + st * (p.a_bytes + p.halo_stride);
+  const int n_co_tiles = ceil_div(dout.c, 128);
+  splits = std::max(1, std::min(p.mtiles_total, kNumSMs / (n_co_tiles * p.ngroups)));
+  p.mtiles_per_split = ceil_div(p.mtiles_total, splits);
+  splits = ceil_div(p.mtiles_total, p.mtiles_per_split);
+  return true;
+}
+
 /* ws != null: deterministic two-stage form - the pixel splits store their partial tiles into ws[split][wtaps][Co][Ci] and a second
    launch adds the slices to G in split order */
 static int conv_wgrad_tc_impl(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, float* ws, long long ws_elems, void* stream) {
@@ -1772,6 +2051,39 @@ static int conv_wgrad_tc_impl(const dc_conv_desc* d, dc_view in, dc_view dout, f
   DC_REQUIRE(tc_view_ok(in) && tc_view_ok(dout), "dc_conv_wgrad_tc: views must be bf16, channel-contiguous, C %% 8 == 0, aligned");
   DC_REQUIRE(in.n == dout.n && G != nullptr, "dc_conv_wgrad_tc: bad arguments");
   TcMaps maps;
+  {
+    TcWgradHaloParams hp;
+    int hsplits = 1, hsmem = 0;
+    if ((reinterpret_cast<uintptr_t>(G) % 16) == 0 && plan_wgrad_halo(d, in, dout, hp, hsplits, hsmem)) {
+      const long long per_tap = (long long)dout.c * in.c, slice = per_tap * d->wtaps;
+      const bool det = ws != nullptr && hsplits > 1;
+      if (det) {
+        DC_REQUIRE(ws_elems >= slice * hsplits, "dc_conv_wgrad_tc_det: workspace of %lld floats required, %lld given", slice * hsplits, ws_elems);
+        DC_REQUIRE((reinterpret_cast<uintptr_t>(ws) % 16) == 0, "dc_conv_wgrad_tc_det: workspace must be 16-byte aligned");
+      }
+      hp.G = det ? ws : G;
+      hp.det_wtaps = det ? d->wtaps : 0;
+      if (int r = encode_act_map(&maps.b, dout.ptr, dout.c, dout.w, dout.h, dout.n, dout.sw, dout.sh, dout.sn, kHaloTW, kHaloTH, "dc_conv_wgrad_tc"))
+        return r;
+      if (int r = encode_halo_map(&maps.a[0], in, hp.halo_w, hp.halo_h, "dc_conv_wgrad_tc")) return r;
+      for (int id = 1; id < 4; ++id) maps.a[id] = maps.a[0];
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail((int)e, "dc_conv_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+      }
+      dim3 grid((unsigned)ceil_div(dout.c, 128), (unsigned)hp.ngroups, (unsigned)hsplits);
+      cudaStream_t st = as_stream(stream);
+      launch_k(conv_wgrad_tc_halo_kernel, grid, dim3(kWgradHaloThreads), (size_t)hsmem, st, maps, hp);
+      if (int r = launch_status("dc_conv_wgrad_tc")) return r;
+      if (!det) return 0;
+      SplitReduceTaps taps;
+      taps.n = d->ntaps;
+      for (int t = 0; t < d->ntaps; ++t) taps.wt[t] = d->wt[t];
+      return launch_split_reduce(ws, hsplits, slice, taps, per_tap, G, st);
+    }
+  }
   TcWgradParams p;
   p.ntaps = d->ntaps;
   pick_tile(dout.h, dout.w, p.TH, p.TW);
@@ -1833,7 +2145,9 @@ int dc_conv_wgrad_tc(const dc_conv_desc* d, dc_view in, dc_view dout, float* G, 
 long long dc_conv_wgrad_tc_ws_elems(const dc_conv_desc* d, dc_view in, dc_view dout) {
   if (d == nullptr || d->ntaps < 1 || d->ntaps > DC_MAX_TAPS || !tc_view_ok(in) || !tc_view_ok(dout)) return -1;
   int BNW, total, per, splits;
-  wgrad_split_plan(d, in, dout, BNW, total, per, splits);
+  TcWgradHaloParams hp;
+  int hsmem = 0;
+  if (!plan_wgrad_halo(d, in, dout, hp, splits, hsmem)) wgrad_split_plan(d, in, dout, BNW, total, per, splits);
   return splits > 1 ? (long long)splits * d->wtaps * dout.c * in.c : 0;
 }
 

@@ -128,6 +128,9 @@ def main():
         fl = 2.0 * n * (h if transposed else ho) * (w if transposed else wo) * ci * co * k * k
         nb = x.numel() * 2.0 + out.numel() * out.element_size() + wt.numel() * 2.0
         add("small_fprop " + tag, lambda x=x, cs=cs, out=out: be.conv_fwd(x, cs, out), nb, fl)
+        dys = rnd(n, ho, wo, 8 if transposed else co)
+        gws = torch.zeros_like(wt)
+        add("small_wgrad " + tag, lambda x=x, dys=dys, cs=cs, gws=gws: be.conv_bwd_weight(x, dys, cs, gws), nb, fl)
 
     if not args.only or "pack" in args.only:
         # all weight packs of the real network in one launch (what the forward graph starts with)
