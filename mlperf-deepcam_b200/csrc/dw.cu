@@ -45,11 +45,29 @@ __device__ __forceinline__ void dw_mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+__device__ __forceinline__ void dw_tma_load_5d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void dw_tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+// tile box of virtual image vn: rank-4 map {C, W, H, N} for plain views; rank-5 map {C, W/d, H/d, d (px), N*H (n*H + py)} for the
+// parity sub-grids of a dilated layer (DwView::dsub = d, hsub = sub-grid height)
+__device__ __forceinline__ void dw_tma_load_tile(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int x, int y, int vn, int dsub, int hsub) {
+  if (dsub == 1) {
+    dw_tma_load_4d(map, bar, dst, c0, x, y, vn);
+  } else {
+    const int px = vn % dsub, t = vn / dsub;
+    const int py = t % dsub, n = t / dsub;
+    dw_tma_load_5d(map, bar, dst, c0, x, y, px, n * hsub * dsub + py);
+  }
 }
 
 // ---- 16-byte channel vectors -------------------------------------------------------------------------------
@@ -315,7 +333,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_s1d1_tile_kernel(DwView<const T
     // one box = the whole tile, halo included; rows / pixels / channels outside the tensor arrive as zeros
     if (threadIdx.x == 0) {
       dw_mbar_expect_tx(bar_s, (uint32_t)((m.rs + 2) * TW * m.cvp * 16));
-      dw_tma_load_4d(&in_map, bar_s, tile_s, cv0 * V, x_base, y_base, l.n);
+      dw_tma_load_tile(&in_map, bar_s, tile_s, cv0 * V, x_base, y_base, l.n, in.dsub, in.h);
     }
   } else {
     const int nvec = nrows * TW * m.cvp;
@@ -1123,8 +1141,8 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwVie
       // tensors (and the rows past a short last strip, which lie outside the image) arrives as zeros
       if (threadIdx.x == 0) {
         dw_mbar_expect_tx(bar_s, (uint32_t)(((m.rs + 2) * TW + m.rs * m.ppb) * m.cvp * 16));
-        dw_tma_load_4d(&in_map, bar_s, (uint32_t)__cvta_generic_to_shared(in_t), cv0 * V, x_base, y_base, vn);
-        dw_tma_load_4d(&g_map, bar_s, (uint32_t)__cvta_generic_to_shared(g_t), cv0 * V, x0, y0, vn);
+        dw_tma_load_tile(&in_map, bar_s, (uint32_t)__cvta_generic_to_shared(in_t), cv0 * V, x_base, y_base, vn, in.dsub, in.h);
+        dw_tma_load_tile(&g_map, bar_s, (uint32_t)__cvta_generic_to_shared(g_t), cv0 * V, x0, y0, vn, dout.dsub, dout.h);
       }
       dw_mbar_wait(bar_s, tma_phase);
       tma_phase ^= 1u;
@@ -1356,8 +1374,27 @@ static bool dw_tma_enabled() {
 }
 // un-swizzled 4-D map {C, W, H, N} of an NHWC view with box {box_c, box_w, box_h, 1}; false = not expressible (the caller keeps
 // the cp.async fill): box extents > 256, strides that are not multiples of 16 bytes, encode failure
-static bool dw_encode_tile_map(CUtensorMap* map, const dc_view& v, int box_c, int box_w, int box_h) {
+static bool dw_encode_tile_map(CUtensorMap* map, const dc_view& v, int box_c, int box_w, int box_h, int dsub = 1) {
   if (!dw_tma_enabled()) return false;
+  if (dsub > 1) {
+    // parity sub-grids of a dilated layer: {C, W/d (stride d*sw), H/d (stride d*sh), px (stride sw), n*H + py (stride sh)}; the last
+    // dimension folds image and row parity into one index, which needs densely stacked images (sn == H * sh)
+    PFN_dwEncodeTiled enc5 = dw_get_encode();
+    if (enc5 == nullptr) return false;
+    const int es5 = v.dtype == DC_F32 ? 4 : 2;
+    if (box_c > 256 || box_w > 256 || box_h > 256 || (box_c * es5) % 16) return false;
+    if (v.sc != 1 || v.w % dsub || v.h % dsub || v.sn != (long long)v.h * v.sh || (v.sw * es5) % 16 || (v.sh * es5) % 16 ||
+        (reinterpret_cast<uintptr_t>(v.ptr) % 16))
+      return false;
+    cuuint64_t dims[5] = {(cuuint64_t)v.c, (cuuint64_t)(v.w / dsub), (cuuint64_t)(v.h / dsub), (cuuint64_t)dsub, (cuuint64_t)v.n * v.h};
+    cuuint64_t strides[4] = {(cuuint64_t)v.sw * dsub * es5, (cuuint64_t)v.sh * dsub * es5, (cuuint64_t)v.sw * es5, (cuuint64_t)v.sh * es5};
+    cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc5(map, v.dtype == DC_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(v.ptr), dims,
+                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+  }
   PFN_dwEncodeTiled enc = dw_get_encode();
   if (enc == nullptr) return false;
   const int es = v.dtype == DC_F32 ? 4 : 2;
@@ -1383,7 +1420,7 @@ static bool dw_s1d1_tile_launch(const dc_view& in, const void* w, const dc_view&
   if (smem > 200 * 1024) return false;                                         // odd row counts: register-pipelined kernel
   static bool attr_set[2] = {false, false};
   CUtensorMap map;
-  const bool tma = dsub == 1 && dw_encode_tile_map(&map, in, m.cvp * V, m.ppb + 2, m.rs + 2);
+  const bool tma = dw_encode_tile_map(&map, in, m.cvp * V, m.ppb + 2, m.rs + 2, dsub);
   if (!attr_set[tma]) {
     cudaError_t e = tma ? cudaFuncSetAttribute(dw_s1d1_tile_kernel<T, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
                         : cudaFuncSetAttribute(dw_s1d1_tile_kernel<T, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1593,8 +1630,8 @@ static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d,
   if (pl.tile) {
     static bool attr_done[2] = {false, false};
     CUtensorMap in_map, g_map;
-    const bool tma = pl.dsub == 1 && dw_encode_tile_map(&in_map, in, pl.m.cvp * V, pl.m.ppb + 2, pl.m.rs + 2) &&
-                     dw_encode_tile_map(&g_map, dout, pl.m.cvp * V, pl.m.ppb, pl.m.rs);
+    const bool tma = dw_encode_tile_map(&in_map, in, pl.m.cvp * V, pl.m.ppb + 2, pl.m.rs + 2, pl.dsub) &&
+                     dw_encode_tile_map(&g_map, dout, pl.m.cvp * V, pl.m.ppb, pl.m.rs, pl.dsub);
     if (!tma) { memset(&in_map, 0, sizeof(in_map)); memset(&g_map, 0, sizeof(g_map)); }
     if (!attr_done[tma]) {
       cudaError_t e = tma ? cudaFuncSetAttribute(dw_bwd_weight_tile_kernel<T, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)
