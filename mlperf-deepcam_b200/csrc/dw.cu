@@ -1072,6 +1072,70 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_data_s2_tile_kernel(DwVi
   }
 }
 
+// ---- stride 2 forward, staged (TMA) ---------------------------------------------------------------------------------------
+// The three stride-2 layers of the entry flow (DX:151-159, block1-3 rep[-1]) used the gather kernel: nine global loads per output
+// vector, 61 us per step for ~40 us of HBM time.  Here one TMA box brings the (2 rs + 1) x (2 ppb + 1) input pixels of a tile of
+// rs x ppb outputs into shared memory (zero fill outside the image = fixed_padding) and every thread walks its output column down
+// the strip, nine 16-byte shared-memory loads per output.
+template <typename T, int V>
+__global__ void __launch_bounds__(kDwThreads, 2) dw_fwd_s2_tile_kernel(const T* __restrict__ w9c, DwView<T> out, int C, DwMap m,
+                                                                       const __grid_constant__ CUtensorMap in_map) {
+  constexpr int VP = V / 2;
+  extern __shared__ __align__(128) uint4 dw_tile[];   // [2 rs + 1][2 ppb + 1][cvp]
+  __shared__ __align__(8) uint64_t tma_bar;
+  const DwLane l = dw_lane(m, out.h, out.w);          // rows / columns of out
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
+  const int TW = 2 * m.ppb + 1;
+  const int cv0 = blockIdx.y * m.cvp;
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(dw_tile);
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+  if (threadIdx.x == 0) dw_mbar_init(bar_s, 1);
+  __syncthreads();
+  pdl_sync();
+  if (threadIdx.x == 0) {
+    dw_mbar_expect_tx(bar_s, (uint32_t)((2 * m.rs + 1) * TW * m.cvp * 16));
+    dw_tma_load_4d(&in_map, bar_s, tile_s, cv0 * V, 2 * (int)blockIdx.x * m.ppb - 1, 2 * l.y0 - 1, l.n);
+  }
+  float2 wv[9][VP];
+  if (l.ok) {
+    const int c0 = l.cvi * V;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dwpair<T>::unpack(ld16(w9c + (size_t)k * C + c0), wv[k]);
+  }
+  dw_mbar_wait(bar_s, 0);
+  if (!l.ok) return;
+  T* obase = out.p + out.img(l.n) + (long long)l.x * out.sw + l.cvi * V;
+  const uint4* tp = dw_tile + (2 * (warp * m.ppw + psub) * m.cvp + cvl);      // tile column of input x = 2 * x_out - 1, row 0
+  const int rstride = TW * m.cvp;
+  float2 f0[3][VP];                                   // input row 2 ty (filter row 0 of output row ty): carried over from row ty - 1
+#pragma unroll
+  for (int kw = 0; kw < 3; ++kw) dwpair<T>::unpack(tp[kw * m.cvp], f0[kw]);
+  for (int ty = 0; ty < l.y1 - l.y0; ++ty) {
+    const uint4* r1 = tp + (2 * ty + 1) * rstride;
+    float2 f1[3][VP], f2[3][VP], acc[VP];
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) { dwpair<T>::unpack(r1[kw * m.cvp], f1[kw]); dwpair<T>::unpack(r1[rstride + kw * m.cvp], f2[kw]); }
+#pragma unroll
+    for (int j = 0; j < VP; ++j) {
+      acc[j] = mul2(f0[0][j], wv[0][j]);
+      acc[j] = fma2(f0[1][j], wv[1][j], acc[j]);
+      acc[j] = fma2(f0[2][j], wv[2][j], acc[j]);
+      acc[j] = fma2(f1[0][j], wv[3][j], acc[j]);
+      acc[j] = fma2(f1[1][j], wv[4][j], acc[j]);
+      acc[j] = fma2(f1[2][j], wv[5][j], acc[j]);
+      acc[j] = fma2(f2[0][j], wv[6][j], acc[j]);
+      acc[j] = fma2(f2[1][j], wv[7][j], acc[j]);
+      acc[j] = fma2(f2[2][j], wv[8][j], acc[j]);
+    }
+    st16(obase + (long long)(l.y0 + ty) * out.sh, dwpair<T>::pack(acc));
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+      for (int j = 0; j < VP; ++j) f0[kw][j] = f2[kw][j];
+  }
+}
+
 // ---- stride-1 weight gradient, staged + cluster-reduced ------------------------------------------------------------------
 // dw_bwd_weight_s1d1_kernel above walks its strip with one row of global loads in flight per thread (a chain of rs + 2
 // dependent L2 round trips: 11.5 of its 15.3 us on the 10 MB middle-flow tensors, tools/kbench.py) and every block then issues
@@ -1094,7 +1158,7 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_saddr, uint32_t ran
   return v;
 }
 
-template <typename T, int V, bool kTma>
+template <typename T, int V, bool kTma, int S>
 __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwView<const T> in, DwView<const T> dout, float* __restrict__ Gout,
                                                                           int C, DwMap m, int tap_stride, int c_stride, int spc, int det,
                                                                           const __grid_constant__ CUtensorMap in_map,
@@ -1104,17 +1168,20 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwVie
   __shared__ __align__(8) uint64_t tma_bar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cvl = lane & (m.cvp - 1), psub = lane / m.cvp;
-  const int TW = m.ppb + 2;
+  // S = 2 (TMA fill only): stride-2 layers - the input tile holds the 2 rs + 1 rows x 2 ppb + 1 pixels the rs x ppb dout pixels
+  // gather from, and the row walk is dout-stationary (nine shared-memory loads per dout pixel)
+  const int TW = S == 2 ? 2 * m.ppb + 1 : m.ppb + 2;
+  const int TR = S == 2 ? 2 * m.rs + 1 : m.rs + 2;
   // blockIdx.z = (virtual image, chunk of `spc` consecutive strips): a block walks its strips one after the other and keeps the
   // 9 x V partial sums in registers, so the block reduction + cluster reduction + atomics are paid once per `spc` strips (the
   // 113 MB entry-flow tensors would otherwise pay them 2808 times for 160-pixel tiles)
   const int nchunks = (m.nstrips + spc - 1) / spc;
   const int vn = blockIdx.z / nchunks, chunk = blockIdx.z - vn * nchunks;
-  const int x0 = blockIdx.x * m.ppb, x_base = x0 - 1;
+  const int x0 = blockIdx.x * m.ppb, x_base = S * x0 - 1;
   const int cv0 = blockIdx.y * m.cvp;
   const int H = in.h, W = in.w;
   uint4* in_t = dww_smem;
-  uint4* g_t = dww_smem + (((m.rs + 2) * TW * m.cvp + 7) & ~7);       // 128-byte aligned (TMA destination)
+  uint4* g_t = dww_smem + ((TR * TW * m.cvp + 7) & ~7);               // 128-byte aligned (TMA destination)
   const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&tma_bar);
   uint32_t tma_phase = 0;
   if (kTma) {
@@ -1134,13 +1201,13 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwVie
   for (int strip = chunk * spc; strip < strip_end; ++strip) {
     const int y0 = strip * m.rs, y1 = min(dout.h, y0 + m.rs);
     const int orows = y1 - y0, nrows = orows + 2;     // dout rows y0 .. y1-1, input rows y0-1 .. y1
-    const int y_base = y0 - 1;
+    const int y_base = S * y0 - 1;
     if (strip != chunk * spc) __syncthreads();        // the previous strip's walk is over: its tiles may be overwritten
     if (kTma) {
       // two boxes: input rows y0-1 .. y0+rs with a one-pixel halo left and right, dout rows y0 .. y0+rs-1; everything outside the
       // tensors (and the rows past a short last strip, which lie outside the image) arrives as zeros
       if (threadIdx.x == 0) {
-        dw_mbar_expect_tx(bar_s, (uint32_t)(((m.rs + 2) * TW + m.rs * m.ppb) * m.cvp * 16));
+        dw_mbar_expect_tx(bar_s, (uint32_t)((TR * TW + m.rs * m.ppb) * m.cvp * 16));
         dw_tma_load_tile(&in_map, bar_s, (uint32_t)__cvta_generic_to_shared(in_t), cv0 * V, x_base, y_base, vn, in.dsub, in.h);
         dw_tma_load_tile(&g_map, bar_s, (uint32_t)__cvta_generic_to_shared(g_t), cv0 * V, x0, y0, vn, dout.dsub, dout.h);
       }
@@ -1172,7 +1239,27 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_bwd_weight_tile_kernel(DwVie
       cp_async_commit_wait_all();
       __syncthreads();
     }
-    {
+    if (S == 2) {
+      const int col = warp * m.ppw + psub;
+      const uint4* ip = in_t + (2 * col * m.cvp + cvl);                   // tile column of input x = 2 * x_out - 1, row 0
+      const uint4* gp = g_t + (col * m.cvp + cvl);
+      const int irs = TW * m.cvp, grs = m.ppb * m.cvp;
+      for (int ty = 0; ty < orows; ++ty) {
+        float2 g[VP];
+        dwpair<T>::unpack(gp[ty * grs], g);
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const uint4* rp = ip + (2 * ty + kh) * irs;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            float2 f[VP];
+            dwpair<T>::unpack(rp[kw * m.cvp], f);
+#pragma unroll
+            for (int j = 0; j < VP; ++j) G2[kh * 3 + kw][j] = fma2(f[j], g[j], G2[kh * 3 + kw][j]);
+          }
+        }
+      }
+    } else {
       // thread = (channel vector cvl, pixel column col of the block); input-stationary walk over the staged rows:
       // input row r meets dout rows r+1 (filter row 0), r (row 1), r-1 (row 2)
       const int col = warp * m.ppw + psub;
@@ -1491,6 +1578,25 @@ static int dw_fwd_t(const dc_view& in, const void* w, int s, int d, const dc_vie
   constexpr int V = dwvec<T>::V;
   const int dsub = dw_dsub(s, d, out.h, out.w);
   if (dsub >= 1 && dw_s1d1_tile_launch<T, V>(in, w, out, 0, 0, st, dsub)) return launch_status("dc_dw_fwd");
+  static int s2_tile = -1;        // DEEPCAM_B200_DW_S2_TILE=0: gather-form kernels (A/B measurements)
+  if (s2_tile < 0) { const char* e = getenv("DEEPCAM_B200_DW_S2_TILE"); s2_tile = (e && e[0] == '0') ? 0 : 1; }
+  if (s == 2 && d == 1 && s2_tile && dw_tile_enabled()) {
+    DwMap mt = dw_map(out.c, V, out.h, out.w, out.n, 1 << 30, 1);
+    mt.nstrips = ceil_div(out.h, 4);                   // strips of <= 4 output rows: 9 input rows x (2 ppb + 1) pixels stay below 110 KB
+    mt.rs = ceil_div(out.h, mt.nstrips);
+    mt.nstrips = ceil_div(out.h, mt.rs);
+    const size_t smem = (size_t)(2 * mt.rs + 1) * (2 * mt.ppb + 1) * mt.cvp * 16;
+    CUtensorMap map;
+    if (smem <= 110 * 1024 && dw_encode_tile_map(&map, in, mt.cvp * V, 2 * mt.ppb + 1, 2 * mt.rs + 1)) {
+      static bool attr_set = false;
+      if (!attr_set && cudaFuncSetAttribute(dw_fwd_s2_tile_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) == cudaSuccess)
+        attr_set = true;
+      if (attr_set) {
+        launch_k(dw_fwd_s2_tile_kernel<T, V>, dw_grid(mt, out.w, out.n), dim3(kDwThreads), smem, st, (const T*)w, dw_view<T>(out), out.c, mt, map);
+        return launch_status("dc_dw_fwd");
+      }
+    }
+  }
   DwMap m = dw_map(out.c, V, out.h, out.w, out.n, kNumSMs * 4, 6);
   dim3 grid = dw_grid(m, out.w, out.n);
   if (s == 1 && d == 1)
@@ -1556,6 +1662,7 @@ __global__ void __launch_bounds__(256) dww_slice_reduce_kernel(const float* __re
 
 struct DwwPlan {
   bool tile;
+  bool s2;                     // stride-2 staged form (TMA fill only)
   int dsub, gn, gw, spc;
   DwMap m;
   dim3 grid;
@@ -1577,7 +1684,34 @@ static DwwPlan dww_plan(const dc_view& in, const dc_view& dout, int s, int d) {
   pl.gw = pl.dsub >= 1 ? dout.w / pl.dsub : dout.w;
   pl.gn = pl.dsub >= 1 ? dout.n * pl.dsub * pl.dsub : dout.n;
   pl.tile = false;
+  pl.s2 = false;
   pl.spc = 1;
+  static int s2_on = -1;          // DEEPCAM_B200_DW_S2_TILE=0: gather-form kernels for the stride-2 layers
+  if (s2_on < 0) { const char* e = getenv("DEEPCAM_B200_DW_S2_TILE"); s2_on = (e && e[0] == '0') ? 0 : 1; }
+  if (s == 2 && d == 1 && tile_on && s2_on && dw_tma_enabled()) {
+    // strips of <= 4 dout rows: 9 input rows x (2 ppb + 1) pixels + the dout tile stay below 110 KB
+    DwMap m = dw_map(dout.c, V, dout.h, dout.w, dout.n, 1 << 30, 1);
+    m.nstrips = ceil_div(dout.h, 4);
+    m.rs = ceil_div(dout.h, m.nstrips);
+    m.nstrips = ceil_div(dout.h, m.rs);
+    const size_t in_vecs = ((size_t)(2 * m.rs + 1) * (2 * m.ppb + 1) * m.cvp + 7) & ~(size_t)7;
+    const size_t tiles = (in_vecs + (size_t)m.rs * m.ppb * m.cvp) * 16;
+    const size_t scratch = ((size_t)8 * 32 * 3 * V + (size_t)9 * m.cvp * V) * sizeof(float);
+    const size_t smem = std::max(tiles, scratch);
+    if (smem <= 110 * 1024) {
+      const long long nblk1 = (long long)ceil_div(dout.w, m.ppb) * m.gy * dout.n * m.nstrips;
+      pl.spc = (int)std::min<long long>(m.nstrips, std::max<long long>(1, nblk1 / 592));
+      const int nchunks = ceil_div(m.nstrips, pl.spc);
+      pl.grid = dim3((unsigned)ceil_div(dout.w, m.ppb), (unsigned)m.gy, (unsigned)(dout.n * nchunks));
+      pl.m = m;
+      pl.smem = smem;
+      pl.tile = true;
+      pl.s2 = true;
+      pl.dsub = 1;               // plain views
+      pl.gw = dout.w; pl.gn = dout.n;
+      return pl;
+    }
+  }
   if (pl.dsub >= 1 && tile_on) {
     // strips of <= 10 rows: input + dout tiles stay below 110 KB, two blocks per SM; the 48-row middle-flow tensors then make
     // 270 blocks = one wave, in 54 clusters of 5 strips
@@ -1628,17 +1762,21 @@ static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d,
   int nslices = (int)(pl.grid.x * pl.grid.z);
   bool launched = false;
   if (pl.tile) {
-    static bool attr_done[2] = {false, false};
+    static bool attr_done[3] = {false, false, false};
     CUtensorMap in_map, g_map;
-    const bool tma = dw_encode_tile_map(&in_map, in, pl.m.cvp * V, pl.m.ppb + 2, pl.m.rs + 2, pl.dsub) &&
-                     dw_encode_tile_map(&g_map, dout, pl.m.cvp * V, pl.m.ppb, pl.m.rs, pl.dsub);
+    const bool tma = pl.s2 ? (dw_encode_tile_map(&in_map, in, pl.m.cvp * V, 2 * pl.m.ppb + 1, 2 * pl.m.rs + 1) &&
+                              dw_encode_tile_map(&g_map, dout, pl.m.cvp * V, pl.m.ppb, pl.m.rs))
+                           : (dw_encode_tile_map(&in_map, in, pl.m.cvp * V, pl.m.ppb + 2, pl.m.rs + 2, pl.dsub) &&
+                              dw_encode_tile_map(&g_map, dout, pl.m.cvp * V, pl.m.ppb, pl.m.rs, pl.dsub));
     if (!tma) { memset(&in_map, 0, sizeof(in_map)); memset(&g_map, 0, sizeof(g_map)); }
-    if (!attr_done[tma]) {
-      cudaError_t e = tma ? cudaFuncSetAttribute(dw_bwd_weight_tile_kernel<T, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)
-                          : cudaFuncSetAttribute(dw_bwd_weight_tile_kernel<T, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-      if (e == cudaSuccess) attr_done[tma] = true;
+    const int variant = pl.s2 ? 2 : (tma ? 1 : 0);
+    if (!attr_done[variant] && !(pl.s2 && !tma)) {
+      cudaError_t e = variant == 2 ? cudaFuncSetAttribute(dw_bwd_weight_tile_kernel<T, V, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)
+                      : variant == 1 ? cudaFuncSetAttribute(dw_bwd_weight_tile_kernel<T, V, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)
+                                     : cudaFuncSetAttribute(dw_bwd_weight_tile_kernel<T, V, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+      if (e == cudaSuccess) attr_done[variant] = true;
     }
-    const bool attr_set = attr_done[tma];
+    const bool attr_set = attr_done[variant] && !(pl.s2 && !tma);     // the stride-2 form exists with the TMA fill only
     if (attr_set) {
       // cluster = consecutive blockIdx.z (strips / images / parity sub-grids of one (x block, channel group)): largest divisor <= 8
       static int cz_max = -1;         // DEEPCAM_B200_DWW_CLUSTER: largest cluster size tried (1 = no cluster reduction)
@@ -1654,10 +1792,13 @@ static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d,
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = pdl_enabled() ? 2 : 1;
-        cudaError_t e = tma ? cudaLaunchKernelEx(&cfg, dw_bwd_weight_tile_kernel<T, V, true>, dw_view<const T>(in, pl.dsub),
-                                                 dw_view<const T>(dout, pl.dsub), target, dout.c, pl.m, tap_stride, c_stride, pl.spc, det, in_map, g_map)
-                            : cudaLaunchKernelEx(&cfg, dw_bwd_weight_tile_kernel<T, V, false>, dw_view<const T>(in, pl.dsub),
-                                                 dw_view<const T>(dout, pl.dsub), target, dout.c, pl.m, tap_stride, c_stride, pl.spc, det, in_map, g_map);
+        cudaError_t e =
+            variant == 2 ? cudaLaunchKernelEx(&cfg, dw_bwd_weight_tile_kernel<T, V, true, 2>, dw_view<const T>(in, pl.dsub), dw_view<const T>(dout, pl.dsub),
+                                              target, dout.c, pl.m, tap_stride, c_stride, pl.spc, det, in_map, g_map)
+            : variant == 1 ? cudaLaunchKernelEx(&cfg, dw_bwd_weight_tile_kernel<T, V, true, 1>, dw_view<const T>(in, pl.dsub), dw_view<const T>(dout, pl.dsub),
+                                                target, dout.c, pl.m, tap_stride, c_stride, pl.spc, det, in_map, g_map)
+                           : cudaLaunchKernelEx(&cfg, dw_bwd_weight_tile_kernel<T, V, false, 1>, dw_view<const T>(in, pl.dsub), dw_view<const T>(dout, pl.dsub),
+                                                target, dout.c, pl.m, tap_stride, c_stride, pl.spc, det, in_map, g_map);
         if (e == cudaSuccess) {
           launched = true;
           nslices = (int)(pl.grid.x * (pl.grid.z / cz));
@@ -1677,7 +1818,7 @@ static int dw_bwd_weight_t(const dc_view& in, const dc_view& dout, int s, int d,
     }
   }
   if (!launched) {
-    if (pl.dsub >= 1)
+    if (pl.dsub >= 1 && !pl.s2)
       launch_k(dw_bwd_weight_s1d1_kernel<T, V>, pl.grid, dim3(kDwThreads), pl.smem, st, dw_view<const T>(in, pl.dsub), dw_view<const T>(dout, pl.dsub),
                target, dout.c, pl.m, tap_stride, c_stride, det);
     else
