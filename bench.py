@@ -601,6 +601,9 @@ def run_ours(args):
                     gpu_launches=launches, clocks=clocks,
                     tensor_frac_of_step=(FWD_BWD_GFLOP_PER_SAMPLE * value / world / 1000.0) / peaks["tf_sustained"],
                     roofline=roofline, cpu_baseline=cpu_base, gpu_library_baseline=gpu_lib, comm=comm)
+        from deepcam_b200 import engine as _engine
+        if _engine.deterministic():
+            line["deterministic"] = True      # DEEPCAM_B200_DETERMINISTIC=1: two-stage weight-gradient reductions (bit-reproducible)
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()              # rank 0 may still be in its instrumented pass: leave together
