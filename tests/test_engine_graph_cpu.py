@@ -241,3 +241,44 @@ def test_cpu_input_without_test_backend_raises_loudly():
     m = dx.SeparableConv2d_same(8, 16)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.rand(1, 8, 8, 8))
+
+
+def test_deterministic_switch_sources(monkeypatch):
+    """engine.deterministic(): explicit override > DEEPCAM_B200_DETERMINISTIC > torch.use_deterministic_algorithms (what a user of the
+    reference calls for reproducible cuDNN gradients); the flag is part of the CUDA-graph plan key (engine._graph_plan)."""
+    import inspect
+    from deepcam_b200 import engine
+    monkeypatch.delenv("DEEPCAM_B200_DETERMINISTIC", raising=False)
+    engine.set_deterministic(None)
+    assert engine.deterministic() is False
+    monkeypatch.setenv("DEEPCAM_B200_DETERMINISTIC", "1")
+    assert engine.deterministic() is True
+    engine.set_deterministic(False)
+    try:
+        assert engine.deterministic() is False           # the override wins over the environment
+    finally:
+        engine.set_deterministic(None)
+    monkeypatch.setenv("DEEPCAM_B200_DETERMINISTIC", "0")
+    assert engine.deterministic() is False
+    prev = torch.are_deterministic_algorithms_enabled()
+    torch.use_deterministic_algorithms(True)
+    try:
+        assert engine.deterministic() is True
+    finally:
+        torch.use_deterministic_algorithms(prev)
+    assert engine.deterministic() is False
+    assert "deterministic()" in inspect.getsource(engine._graph_plan)
+
+
+def test_deterministic_flag_does_not_change_the_cpu_interpreter_result(net):
+    """The flag only selects kernels of the CUDA backend; a backend without the attribute (the test interpreter) is left alone."""
+    from deepcam_b200 import engine
+    x, label = O.synthetic_batch(2, 32, 48, seed=5)
+    net.train()
+    out0 = net(x).detach().clone()
+    engine.set_deterministic(True)
+    try:
+        out1 = net(x).detach().clone()
+    finally:
+        engine.set_deterministic(None)
+    assert torch.equal(out0, out1)
