@@ -761,9 +761,12 @@ __global__ void __launch_bounds__(kHalo ? kTc2HaloThreads : kTc2Threads, 1) conv
             const uint32_t sb = cfg.b_resident ? (bres_base + (uint32_t)(kb0 + kb) * b_block_bytes) : (sa + MT * kABytes);
             const uint64_t da = make_smem_desc(sa, 16, 1024);
             const uint64_t db = make_smem_desc(sb, 16, 1024);
+            // halo: K is dense, so the last k block may hold fewer than four 16-element steps (conv1: K = 144 = 64 + 64 + 16,
+            // last_deconv's dgrad: 72 = 64 + 8) - the steps beyond ktot multiply zero columns by zero weight rows and are skipped
+            const int kmax = kHalo ? min(4, (cfg.ktot - kb * 64 + 15) >> 4) : 4;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if (!(kHalo && (cfg.dbg & 2))) umma_bf16(acc, da + 2u * k, db + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              if (k < kmax && !(kHalo && (cfg.dbg & 2))) umma_bf16(acc, da + 2u * k, db + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
             if (cfg.wide) {
               // second N sub-tile: B rows bn_sub0.. of the same stage (row offset = bn_sub0 * 128 B, a multiple of 1024),
               // accumulator columns bn_sub0..BN-1
