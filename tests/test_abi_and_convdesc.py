@@ -179,3 +179,76 @@ def test_conv_transpose_fused_tap_table_and_pack_definition():
                     flat[off] = fused[n, i, j, c]
     assert torch.allclose(out[..., :Co], y, atol=1e-10)
     assert float(out[..., Co:].abs().max()) == 0.0
+
+
+def _fake_view(n, h, w, c, dtype=_lib.DC_BF16, ptr=0x10000):
+    """A dense NHWC view over a made-up, aligned address: the planning queries below never dereference it."""
+    v = _lib.dc_view()
+    v.ptr, v.n, v.h, v.w, v.c = ptr, n, h, w, c
+    v.sc, v.sw, v.sh, v.sn = 1, c, w * c, h * w * c
+    v.dtype = dtype
+    return v
+
+
+def _desc(taps, stride, wtaps):
+    from deepcam_b200 import ops
+    return ops.make_desc(taps, (stride, stride), False, wtaps)
+
+
+def test_deterministic_workspace_planning_without_gpu(monkeypatch):
+    """Host-side launch planning of the deterministic weight gradients (no kernel is launched, no device is touched): the workspace
+    queries return splits x wtaps x Co x Ci for the pixel-split plan the launch would use - the per-tap kernel's one-wave split for
+    the 728x728 layers, the halo-mode plan (all taps of a tap group per CTA) for conv1 / conv2 / last_deconv - and 0 when the
+    launch does not split."""
+    for k in ("DEEPCAM_B200_WGRAD_SPLIT_DIV", "DEEPCAM_B200_WGRAD_SPLIT_MUL", "DEEPCAM_B200_WGRAD_HALO", "DEEPCAM_B200_DWW_TILE",
+              "DEEPCAM_B200_DW_S2_TILE", "DEEPCAM_B200_DW_TMA", "DEEPCAM_B200_DWW_BLOCKS_PER_SM", "DEEPCAM_B200_DWW_MIN_ROWS"):
+        monkeypatch.delenv(k, raising=False)
+    lib = _lib.load()
+    q = lib.dc_conv_wgrad_tc_ws_elems
+    # middle flow: 728 -> 728 pointwise at 2x48x72: 6 co tiles x 3 ci tiles of 256 -> 148 // 18 = 8 pixel splits
+    d1 = _desc(convdesc.conv_wgrad_taps(1, 0, 1), 1, 1)
+    assert q(ctypes.byref(d1), _fake_view(2, 48, 72, 728), _fake_view(2, 48, 72, 728)) == 8 * 728 * 728
+    # ASPP 3x3 2048 -> 256 at 2x48x72: 2 x 8 x 9 = 144 tiles, no split, no workspace
+    d9 = _desc(convdesc.conv_wgrad_taps(3, 6, 6), 1, 9)
+    assert q(ctypes.byref(d9), _fake_view(2, 48, 72, 2048), _fake_view(2, 48, 72, 256)) == 0
+    # conv1 16 -> 32 k3 s2 on 768x1152 (halo mode, one tap group): 3456 tiles of 8 x 16 pixels over 148 CTAs -> 24 per CTA -> 144 splits
+    c1 = _desc(convdesc.conv_wgrad_taps(3, 1, 1), 2, 9)
+    assert q(ctypes.byref(c1), _fake_view(2, 768, 1152, 16), _fake_view(2, 384, 576, 32)) == 144 * 9 * 32 * 16
+    # conv2 32 -> 64 k3 s1 (halo mode, 9 taps x 32 channels = 288 > 192 -> two tap groups): 74 splits
+    c2 = _desc(convdesc.conv_wgrad_taps(3, 1, 1), 1, 9)
+    assert q(ctypes.byref(c2), _fake_view(2, 384, 576, 32), _fake_view(2, 384, 576, 64)) == 74 * 9 * 64 * 32
+    # 64 gathered channels, 3 taps per group -> three groups; more than 64 channels -> per-tap kernel
+    c3 = _desc(convdesc.conv_wgrad_taps(3, 1, 1), 1, 9)
+    assert q(ctypes.byref(c3), _fake_view(2, 96, 144, 64), _fake_view(2, 96, 144, 128)) % (9 * 128 * 64) == 0
+    bad = _fake_view(2, 48, 72, 730)                                    # C % 8 != 0: not a tcgen05 view
+    assert q(ctypes.byref(d1), bad, _fake_view(2, 48, 72, 728)) == -1
+    # depthwise: one slice of 9 x C per (x block, strip / image) - 9 x blocks x 10 (image, strip) pairs for the middle-flow tensors
+    qd = lib.dc_dw_bwd_weight_ws_elems
+    assert qd(_fake_view(2, 48, 72, 728), _fake_view(2, 48, 72, 728), 1, 1) == 9 * 10 * 9 * 728
+    n_s2 = qd(_fake_view(2, 384, 576, 128), _fake_view(2, 192, 288, 128), 2, 1)
+    assert n_s2 > 0 and n_s2 % (9 * 128) == 0
+    assert qd(_fake_view(2, 48, 72, 728), _fake_view(2, 24, 36, 728), 1, 1) == -1          # output size does not match the stride
+    # the switch itself is plain host state
+    assert lib.dc_get_deterministic() == 0
+    lib.dc_set_deterministic(1)
+    assert lib.dc_get_deterministic() == 1
+    lib.dc_set_deterministic(0)
+
+
+def test_halo_mode_selection_without_gpu(monkeypatch):
+    """dc_conv_gemm_tc_halo_ok is pure host planning: the halo mode of the persistent GEMM serves multi-tap gathers with <= 64
+    gathered channels in dense NHWC rows (conv1, conv2, their gradients), not the 1x1 layers and not the wide 3x3 layers."""
+    for k in ("DEEPCAM_B200_TC_HALO", "DEEPCAM_B200_TC_V1", "DEEPCAM_B200_TC_HALO_BUFS", "DEEPCAM_B200_TC_HALO_STAGES", "DEEPCAM_B200_TC_HALO_DBG"):
+        monkeypatch.delenv(k, raising=False)
+    lib = _lib.load()
+    ok = lib.dc_conv_gemm_tc_halo_ok
+    conv1 = _desc(convdesc.conv_fprop_taps(3, 1, 1), 2, 9)
+    assert ok(ctypes.byref(conv1), _fake_view(2, 768, 1152, 16), _fake_view(2, 384, 576, 32)) == 1
+    conv2 = _desc(convdesc.conv_fprop_taps(3, 1, 1), 1, 9)
+    assert ok(ctypes.byref(conv2), _fake_view(2, 384, 576, 32), _fake_view(2, 384, 576, 64)) == 1
+    assert ok(ctypes.byref(conv2), _fake_view(2, 192, 288, 256), _fake_view(2, 192, 288, 256)) == 0      # 256 gathered channels
+    pw = _desc(convdesc.conv_fprop_taps(1, 0, 1), 1, 1)
+    assert ok(ctypes.byref(pw), _fake_view(2, 48, 72, 64), _fake_view(2, 48, 72, 128)) == 0               # one tap: nothing to share
+    strided = _fake_view(2, 384, 576, 32)
+    strided.sw = 64                                                                                      # channel slice of a wider buffer
+    assert ok(ctypes.byref(conv2), strided, _fake_view(2, 384, 576, 64)) == 0
